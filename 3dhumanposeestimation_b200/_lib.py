@@ -1,0 +1,85 @@
+"""ctypes binding of libpose_b200.so -- the only way the Python host side reaches the GPU kernels.
+
+There is deliberately no fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch  # noqa: F401  (loads the CUDA runtime the library links against)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpose_b200.so")
+
+c_int, c_float, c_size_t, c_void_p = C.c_int, C.c_float, C.c_size_t, C.c_void_p
+
+
+class PoseAugLaunch(C.Structure):
+    """Mirror of `pose_aug_launch` in include/pose_b200.h."""
+
+    _fields_ = [(n, C.c_int32) for n in ("max_out_h", "max_out_w", "max_rot_rows", "max_band_rows", "max_ksize",
+                                        "smem_bytes", "cluster", "reserved")]
+
+
+POSE_AUG_PLAN_BYTES = 256
+
+# name -> (restype, argtypes); must list every symbol include/pose_b200.h declares
+SIGNATURES = {
+    "pose_b200_abi_version": (c_int, []),
+    "pose_b200_error_string": (C.c_char_p, [c_int]),
+    "pose_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "pose_loss_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, C.POINTER(c_float), c_void_p, c_void_p, c_float,
+                                  c_void_p, c_size_t, c_void_p]),
+    "pose_heatmap_render": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_int, c_int,
+                                    c_void_p]),
+    "pose_augment_plan": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, C.POINTER(PoseAugLaunch)]),
+    "pose_augment_workspace_bytes": (c_size_t, [c_int, c_int, c_int, C.POINTER(PoseAugLaunch)]),
+    "pose_augment_batch": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   C.POINTER(PoseAugLaunch), c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                   c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pose_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                               c_int, c_int, c_void_p]),
+    "pose_cast_f32_bf16": (c_int, [c_void_p, c_void_p, C.c_long, c_void_p]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python 3dhumanposeestimation_b200/build.py` "
+                "(this package has no CPU or eager fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = lib().pose_b200_error_string(code).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {code})")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    """The kernels only accept contiguous CUDA tensors of the exact dtype; anything else raises."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the B200 kernels have no CPU fallback")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    return t

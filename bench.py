@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 pose hot path (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+N > 1 is launched by torchrun (one rank per GPU).  Rank 0 prints ONE JSON line.
+
+Workloads (BASELINE.json configs):
+  preproc_b256   configs[1]: PoseAugmentor + heat-map / regression head + composite loss kernels,
+                 batch 256 of 256x256 RGB-D per GPU.  One step = one pass of that chain over one batch.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 42
+B, H, W, J, HS, SIGMA = 256, 256, 256, 17, 256, 10.0
+HEAD_IN, HEAD_HIDDEN = 1024, (1024, 512)
+
+
+# ----------------------------------------------------------------------------------------------------
+# synthetic inputs: seeded, identical for every implementation
+# ----------------------------------------------------------------------------------------------------
+def make_inputs(rank: int, batch: int = B):
+    rng = np.random.default_rng(SEED + rank)
+    img = rng.random((batch, 3, H, W), dtype=np.float32)
+    dep = rng.random((batch, 1, H, W), dtype=np.float32)
+    kp = rng.uniform(0.05, 0.95, (batch, J, 2)).astype(np.float32)
+    kp[rng.random((batch, J)) < 0.05] = -1.0
+    joints = rng.normal(0, 300, (batch, J, 3)).astype(np.float32)
+    joints[:, :, 2] += 4000
+    cam = np.tile(np.array([1145.0 * W / 1000, 1144.0 * H / 1000, W / 2.0, H / 2.0]), (batch, 1))
+    feat = rng.normal(0, 1, (batch, HEAD_IN)).astype(np.float32)
+    return dict(image=img, depth=dep, kp=kp, joints=joints, cam=cam, feat=feat)
+
+
+def draw_params(aug, batch):
+    np.random.seed(SEED)
+    return aug.draw_params(batch)
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on the host cores (bounded sample)
+# ----------------------------------------------------------------------------------------------------
+def cpu_chain_samples_per_s(n_samples: int, threads: int, inputs=None, params=None):
+    """Times the oracle port (C, one sample per call, ctypes releases the GIL) of the same chain:
+    augment -> heat-map -> (head: fp32 numpy GEMMs) -> loss, on `n_samples` samples with `threads` threads."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    oracle.build()
+    oracle.lib()
+    inp = inputs or make_inputs(0, n_samples)
+    pose = importlib.import_module("3dhumanposeestimation_b200")
+    aug = pose.PoseAugmentor()
+    if params is None:
+        params = draw_params(aug, n_samples)
+    rng = np.random.default_rng(SEED)
+    dims = (HEAD_IN,) + HEAD_HIDDEN + (J * 3,)
+    Ws = [rng.normal(0, 0.02, (dims[i + 1], dims[i])).astype(np.float32) for i in range(len(dims) - 1)]
+
+    def one(i):
+        o = oracle.augment_sample(inp["image"][i], inp["depth"][i], inp["kp"][i], inp["joints"][i], inp["cam"][i],
+                                  params[i], aug.flags)
+        oracle.heatmap(o["keypoints_2d"][None], HS, SIGMA)
+        return o["joints_3d"]
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        gts = list(ex.map(one, range(n_samples)))
+    x = inp["feat"][:n_samples]
+    for k, w in enumerate(Ws):
+        x = x @ w.T
+        if k < len(Ws) - 1:
+            x = x / (1.0 + np.exp(-x))
+    oracle.pose_loss(x.reshape(n_samples, J, 3), np.stack(gts))
+    dt = time.perf_counter() - t0
+    return n_samples / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python and
+    cannot travel to the GPU box, so this arm times the oracle port (oracle/pose_oracle.c, pinned bit-exact
+    against the live reference) with all host threads; each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 64
+    inp = make_inputs(0, sample)
+    for _ in range(args.warmup):
+        cpu_chain_samples_per_s(min(sample, 16), cores, inp)
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        v, _dt = cpu_chain_samples_per_s(sample, cores, inp)
+        vals.append(v)
+    ms = (time.perf_counter() - t0) * 1e3 / max(1, args.steps)
+    value = float(np.median(vals))
+    line = {
+        "impl": "reference", "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8+f32", "data": "synthetic",
+        "config": {"workload": "preproc_b256", "note": f"each step = {sample} of the 256 samples of one batch"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} samples/step of the B=256 augment+heatmap+head+loss chain"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N > 1 with torchrun (see module docstring)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    importlib.import_module("3dhumanposeestimation_b200.build").build()
+    pose = importlib.import_module("3dhumanposeestimation_b200")
+    from importlib import import_module
+    ops = import_module("3dhumanposeestimation_b200.ops")
+
+    inp = make_inputs(rank)
+    aug = pose.PoseAugmentor()
+    params = draw_params(aug, B)
+    crit = pose.ComprehensivePoseLoss()
+    head = pose.PoseRegressionHead(HEAD_IN, J, hidden_dims=list(HEAD_HIDDEN), dropout=0.2, activation="silu").to(dev).eval()
+    hm_gen = pose.GaussianHeatmapGenerator(J, HS, SIGMA).to(dev)
+
+    # host (pinned) and device copies of one batch
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in inp.items()}
+    d = {k: v.to(dev) for k, v in host.items()}
+    PAD = (308, 308)  # int(256 * 1.2) = 307 rows, width rounded up to a multiple of 4
+    stream = torch.cuda.current_stream()
+    ev = {}
+
+    def mark(name, i, which):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        ev.setdefault(name, {}).setdefault(i, {})[which] = e
+
+    def step(src, i=None):
+        """One pass of the hot path over one batch; returns the 5 loss scalars (device tensor)."""
+        if i is not None: mark("augment", i, 0)
+        a = aug.augment_batch(src["image"], src["depth"], src["kp"], src["joints"], src["cam"], params=params, pad_to=PAD)
+        if i is not None: mark("augment", i, 1); mark("heatmap", i, 0)
+        hm = hm_gen(a["keypoints_2d"])
+        if i is not None: mark("heatmap", i, 1); mark("head", i, 0)
+        with torch.no_grad():
+            pred = head(src["feat"])
+        if i is not None: mark("head", i, 1); mark("loss", i, 0)
+        out5, grad = pose.loss.pose_loss_fwd_bwd(pred, a["joints_3d"], crit._weights())
+        if i is not None: mark("loss", i, 1)
+        return out5, hm, a, grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches_per_step = 3 + 1 + ops.MLP_HEAD_LAUNCHES(len(HEAD_HIDDEN) + 1) + 1
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(d)
+    barrier()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        t_start.record(stream)
+        for i in range(args.steps):
+            out5, hm, a, grad = step(d, i)
+        t_end.record(stream)
+        barrier()
+    ms_total = t_start.elapsed_time(t_end)
+    if aug.kernel_error_flag() != 0:
+        raise RuntimeError("augment kernel reported a launch-geometry error")
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    kern_ms = {k: float(np.mean([v[i][0].elapsed_time(v[i][1]) for i in v])) for k, v in ev.items()}
+
+    # ---- end to end: pinned host inputs -> device, result scalars back, every step ------------------
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ("image", "depth", "kp", "joints", "cam", "feat"))
+    res_host = torch.empty(5, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    bufs = [{k: torch.empty_like(d[k]) for k in host} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    free = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_steps(n):
+        for f in free:
+            f.record(stream)
+        for i in range(n + 1):
+            if i < n:  # stage batch i on the copy stream (overlaps the compute of batch i-1)
+                s = i & 1
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(free[s])
+                    for k in host:
+                        bufs[s][k].copy_(host[k], non_blocking=True)
+                    ready[s].record(copy_stream)
+            if i > 0:
+                s = (i - 1) & 1
+                stream.wait_event(ready[s])
+                o5, *_ = step(bufs[s])
+                res_host.copy_(o5, non_blocking=True)
+                free[s].record(stream)
+        torch.cuda.synchronize()
+
+    e2e_steps(max(args.warmup, 3))
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    e2e_steps(args.steps)
+    e1.record(stream)
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        # dominant kernel by bytes and time: the heat-map render (J*hs*hs*4 B written + 8*J B read per sample)
+        hm_bytes = B * (J * HS * HS * 4 + J * 8)
+        achieved = hm_bytes / (kern_ms["heatmap"] * 1e-3) / 1e9
+        sizes = a["sizes"].cpu().numpy().astype(np.int64)
+        aug_bytes = int(B * (16 * H * W) + 16 * int((sizes[:, 0] * sizes[:, 1]).sum()) + B * J * 20 * 2)
+        cpu_n = 48
+        cores = os.cpu_count() or 1
+        cpu_v, cpu_dt = cpu_chain_samples_per_s(cpu_n, cores)
+        line = {
+            "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8+f32 (head: bf16 x bf16 -> f32)", "data": "synthetic",
+            "config": {"workload": "preproc_b256", "batch_per_gpu": B, "image": [H, W], "heatmap": [HS, SIGMA],
+                       "chain": "PoseAugmentor(all stages) -> GaussianHeatmap(256, sigma 10) -> PoseRegressionHead "
+                                "1024-1024-512-51 -> ComprehensivePoseLoss fwd+bwd",
+                       "l2": "inputs (268 MB/batch) and outputs (1.5 GB/batch) exceed the 126 MB L2"},
+            "clocks": clocks.summary(),
+            "gpu_launches": launches_per_step * args.steps,
+            "kernel_ms": kern_ms,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 20,
+                    "note": "fp32 pinned host batch (reference sample schema) -> device every step, double-buffered"},
+            "roofline": {"kernel": "heatmap_planes_kernel<float>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "others": {"augment(pack+tables+fused)": {"bytes": aug_bytes, "GB/s": aug_bytes / (kern_ms["augment"] * 1e-3) / 1e9},
+                                    "loss": {"bytes": B * 632, "ms": kern_ms["loss"]}, "head": {"ms": kern_ms["head"]}}},
+            "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": f"{cpu_n} samples of the same B=256 chain ({cpu_dt:.1f} s), oracle port (C) on all host threads"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="preproc_b256")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

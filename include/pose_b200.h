@@ -1,0 +1,130 @@
+/*
+ * pose_b200.h -- C ABI of libpose_b200.so: the B200 (sm_100a) implementation of the per-sample
+ * training / inference hot path of AliEmreSenel/3DHumanPoseEstimation.
+ *
+ * The reference has no FFI of its own: its boundary is a Python module API.  Each
+ * entry point below is what the body of one reference callable binds to; the reference symbol it
+ * replaces is cited as file:line into the reference tree.  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every DEVICE pointer is owned by the caller (the library never
+ *     allocates, frees or retains device memory); HOST pointers are marked [host].
+ *   - all device work is enqueued asynchronously on `stream` (a CUstream / cudaStream_t); no hidden
+ *     synchronisation.
+ *   - return value: 0 = ok; > 0 = cudaError_t from a launch; < 0 = POSE_E_* argument error.
+ *     pose_b200_error_string() maps any of them to text.  No exceptions cross the ABI.
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef POSE_B200_H
+#define POSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *pose_stream_t; /* cudaStream_t */
+
+enum {
+    POSE_OK = 0,
+    POSE_E_NULL = -1,        /* required pointer is NULL */
+    POSE_E_SHAPE = -2,       /* unsupported / inconsistent shape */
+    POSE_E_WORKSPACE = -3,   /* workspace too small */
+    POSE_E_UNSUPPORTED = -4, /* valid request the sm_100a kernels do not cover (documented per call) */
+    POSE_E_ALIGN = -5        /* pointer not aligned as required */
+};
+
+int pose_b200_abi_version(void);
+const char *pose_b200_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * F. ComprehensivePoseLoss.forward                      reference: src/loss.py:57-85 (+ :29-55)
+ *    One fused forward + backward pass.
+ *    pred, gt   [B, J, 3] fp32 contiguous
+ *    weights    [host] {mse_weight, l1_weight, inter_joint_loss_weight, abs_root_loss_weight}
+ *    out5       [5] fp32: {mse, l1, inter_joint, abs_root, total}   (the reference's dict values)
+ *    grad       [B, J, 3] fp32 or NULL: grad_scale * d(total)/d(pred)
+ *    workspace  pose_loss_workspace_bytes(B, J) bytes, zero-filled before its FIRST use; the
+ *               kernel leaves it zero-filled again, so it can be reused without clearing.
+ * ------------------------------------------------------------------------------------------- */
+size_t pose_loss_workspace_bytes(int B, int J);
+int pose_loss_fwd_bwd(const float *pred, const float *gt, int B, int J, const float *weights, float *out5,
+                      float *grad, float grad_scale, void *workspace, size_t workspace_bytes,
+                      pose_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * B. GaussianHeatmapGenerator.forward                    reference: src/models/common.py:23-51
+ *    kp         [B, J, 2] fp32 normalised key-points
+ *    out        out_layout 0: [B, J, hs, hs] planes (the reference's layout)
+ *               out_layout 1: [B, hs, hs, c_stride] channels-last, plane j at channel c_offset + j
+ *                             (the CNN's 21-channel conv1 operand: src/models/cnn.py:644-648)
+ *    out_dtype  0 = fp32, 1 = bf16
+ * ------------------------------------------------------------------------------------------- */
+int pose_heatmap_render(const float *kp, int B, int J, int hs, float sigma, void *out, int out_dtype,
+                        int out_layout, int c_stride, int c_offset, pose_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * A. PoseAugmentor.__call__ (batched)            reference: src/dataset/augmentation.py:182-351
+ *    The random draws are made by the caller in the reference's order (np.random: flip, angle,
+ *    scale, tx, ty, brightness, contrast) and handed over explicitly; the kernels are RNG-free.
+ *
+ *    params     [host] [B, 8] fp64: {flip (0/1, i.e. random() < flip_prob), angle_deg, scale,
+ *               tx_fraction, ty_fraction, brightness, contrast, unused}
+ *    flags      bit mask of POSE_AUG_* = the reference's enable_* constructor switches
+ *
+ *    pose_augment_plan   [host-only, no GPU work] derives, per sample, everything that needs libm or
+ *                        decimal rounding (PIL's round(cos, 15) matrix, R_y, output size) and the
+ *                        launch geometry.  plan_out: [host] B * POSE_AUG_PLAN_BYTES, to be copied to
+ *                        the device by the caller.  launch_out: [host] pose_aug_launch.
+ *    pose_augment_batch  [device] quantise+pack -> per-sample tables -> fused cluster kernel.
+ *      image     [B,3,H,W], depth [B,1,H,W]; in_dtype 0 = fp32 in [0,1] (the reference's sample
+ *                schema, chunked_dataset.py:219-231), 1 = uint8
+ *      kp [B,J,2] fp32, joints [B,J,3] fp32, cam [B,4] fp64 {fx,fy,cx,cy}
+ *      plan      device copy of plan_out
+ *      image_out [B,3,PH,PW] fp32, depth_out [B,1,PH,PW] fp32: sample i occupies the top-left
+ *                out_hw[i] = {H'_i, W'_i} corner, zero elsewhere (Human36MCollator padding,
+ *                src/dataset/collator.py:20-44).  PW % 4 == 0, PH >= max H', PW >= max W'.
+ *      kp_out [B,J,2], joints_out [B,J,3] fp32, cam_out [B,4] fp64, out_hw [B,2] int32
+ *      workspace pose_augment_workspace_bytes(...) bytes
+ * ------------------------------------------------------------------------------------------- */
+enum { POSE_AUG_FLIP = 1, POSE_AUG_ROTATE = 2, POSE_AUG_SCALE = 4, POSE_AUG_TRANSLATE = 8, POSE_AUG_COLOR = 16 };
+#define POSE_AUG_PLAN_BYTES 256
+
+typedef struct pose_aug_launch {
+    int32_t max_out_h, max_out_w; /* over the batch: smallest legal PH / PW (before PW % 4 rounding) */
+    int32_t max_rot_rows;         /* rows of the rotated band a CTA stages in shared memory */
+    int32_t max_band_rows;        /* output rows per CTA */
+    int32_t max_ksize;            /* taps of the antialiased resize */
+    int32_t smem_bytes;           /* dynamic shared memory of the fused kernel */
+    int32_t cluster;              /* CTAs per sample */
+    int32_t reserved;
+} pose_aug_launch;
+
+int pose_augment_plan(const double *params, int B, int H, int W, int flags, void *plan_out,
+                      pose_aug_launch *launch_out);
+size_t pose_augment_workspace_bytes(int B, int H, int W, const pose_aug_launch *launch);
+int pose_augment_batch(const void *image, const void *depth, int in_dtype, const float *kp, const float *joints,
+                       const double *cam, const void *plan, const pose_aug_launch *launch, int B, int H, int W,
+                       int J, int flags, float *image_out, float *depth_out, int PH, int PW, float *kp_out,
+                       float *joints_out, double *cam_out, int32_t *out_hw, void *workspace,
+                       size_t workspace_bytes, pose_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * C. nn.Linear / 1x1 convolution contraction      reference: src/models/common.py:73-89 (head),
+ *    src/models/cnn.py:16-18 (SE), :122-131 (1x1 convs in NHWC), src/models/transformers.py:20-26
+ *    C[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) on tcgen05 tensor cores (bf16 in, fp32 accumulate).
+ *    A [M,K] bf16 row-major (pitch lda elements), W [N,K] bf16 row-major (torch Linear layout, pitch
+ *    ldw), bias [N] fp32 or NULL, C [M,N] fp32 (out_dtype 0) or bf16 (1), pitch ldc.
+ *    lda, ldw multiples of 8; A, W 16-byte aligned.  act: 0 none, 1 relu, 2 silu, 3 gelu(erf).
+ *    pose_cast_f32_bf16 prepares operands (n elements, 16-byte aligned pointers).
+ * ------------------------------------------------------------------------------------------- */
+int pose_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, void *C, int ldc, int M,
+                   int N, int K, int act, int out_dtype, pose_stream_t stream);
+int pose_cast_f32_bf16(const float *in, void *out, long n, pose_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSE_B200_H */

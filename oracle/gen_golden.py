@@ -1,0 +1,186 @@
+"""Generates tests/golden/*.npz from the LIVE reference (run in this container only).
+
+    python oracle/gen_golden.py            # needs /root/reference; writes tests/golden/
+
+The reference is pure Python and cannot travel to the GPU box, so its outputs on small seeded inputs
+are frozen here.  Library versions are recorded in every file (the reference pins torchvision 0.19.0 /
+Pillow 11.1.0 / numpy 1.26.4; this container has newer ones -- see `versions`).
+The script runs from a scratch directory because importing the reference's `config` creates
+./logs and ./dataset_cache (src/config.py:41-45).
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(REPO, "tests", "golden")
+REF = os.environ.get("POSE_REFERENCE", "/root/reference")
+
+
+def versions():
+    import PIL
+    import torch
+    import torchvision
+    return json.dumps({"torch": torch.__version__, "torchvision": torchvision.__version__, "pillow": PIL.__version__,
+                       "numpy": np.__version__})
+
+
+def make_sample(rng, H, W, root_relative):
+    import torch
+    img8 = rng.integers(0, 256, (3, H, W), dtype=np.uint8)
+    dep8 = rng.integers(0, 256, (1, H, W), dtype=np.uint8)
+    # smooth half of the image so the bilinear / antialias paths see flat and graded regions too
+    yy, xx = np.mgrid[0:H, 0:W]
+    img8[:, :, : W // 2] = ((yy[:, : W // 2] * 3 + xx[:, : W // 2] * 2) % 256).astype(np.uint8)[None]
+    img8[1, : H // 3, :] = 255
+    kp = rng.uniform(0.05, 0.95, (17, 2)).astype(np.float32)
+    joints = rng.normal(0, 300, (17, 3)).astype(np.float32)
+    if not root_relative:
+        joints[:, 2] += 4000
+    cam = [1145.0 * W / 1000, 1144.0 * H / 1000, W / 2.0, H / 2.0]
+    sample = dict(image=torch.from_numpy(img8.astype(np.float32) / np.float32(255)),
+                  depth=torch.from_numpy(dep8.astype(np.float32) / np.float32(255)),
+                  keypoints_2d=torch.from_numpy(kp), joints_3d=torch.from_numpy(joints),
+                  camera_params=dict(R=None, t=None, f=cam[:2], c=cam[2:]))
+    return sample, img8, dep8, kp, joints, np.array(cam, np.float64)
+
+
+def gen_augment():
+    from dataset.augmentation import PoseAugmentor
+    cases = [
+        (0, 64, 64, {}), (1, 64, 64, {}), (2, 64, 64, {}), (3, 64, 64, {}),
+        (4, 48, 80, {}), (5, 80, 48, {}),
+        (6, 64, 64, dict(enable_rotation=False, enable_scale=False)),
+        (7, 64, 64, dict(enable_flip=False, enable_translate=False, enable_color=False)),
+        (8, 64, 64, dict(flip_prob=1.0, enable_rotation=False, enable_scale=False, enable_translate=False,
+                         enable_color=False)),
+        (9, 64, 64, dict(brightness_range=(0.3, 1.9), contrast_range=(0.2, 2.5), rotation_range=(-180, 180),
+                         scale_range=(0.5, 1.7))),
+        (10, 64, 64, dict(enable_flip=False, enable_rotation=False, enable_scale=True, enable_translate=False,
+                          enable_color=False)),
+        (11, 256, 256, {}),
+    ]
+    out = {"versions": versions(), "n": len(cases)}
+    for idx, (seed, H, W, kw) in enumerate(cases):
+        rng = np.random.default_rng(1000 + seed)
+        sample, img8, dep8, kp, joints, cam = make_sample(rng, H, W, root_relative=(seed % 3 == 2))
+        aug = PoseAugmentor(**kw)
+        # replay the global-RNG draws in the reference's order to record the explicit parameters
+        np.random.seed(seed)
+        p = np.zeros(8)
+        if aug.enable_flip:
+            p[0] = float(np.random.random() < aug.flip_prob)
+        if aug.enable_rotation:
+            p[1] = np.random.uniform(*aug.rotation_range)
+        if aug.enable_scale:
+            p[2] = np.random.uniform(*aug.scale_range)
+        if aug.enable_translate:
+            p[3] = np.random.uniform(*aug.translate_range)
+            p[4] = np.random.uniform(*aug.translate_range)
+        if aug.enable_color:
+            p[5] = np.random.uniform(*aug.brightness_range)
+            p[6] = np.random.uniform(*aug.contrast_range)
+        np.random.seed(seed)
+        ref = aug(sample)
+        flags = (1 * aug.enable_flip) | (2 * aug.enable_rotation) | (4 * aug.enable_scale) | \
+                (8 * aug.enable_translate) | (16 * aug.enable_color)
+        oi = ref["image"].numpy()
+        od = ref["depth"].numpy()
+        oi8 = np.round(oi * 255).astype(np.uint8)
+        od8 = np.round(od * 255).astype(np.uint8)
+        assert np.array_equal(oi8.astype(np.float32) / np.float32(255), oi)
+        assert np.array_equal(od8.astype(np.float32) / np.float32(255), od)
+        cp = ref["camera_params"]
+        k = f"c{idx}_"
+        out[k + "seed"] = seed
+        out[k + "ctor"] = json.dumps(kw)
+        out[k + "flags"] = flags
+        out[k + "params"] = p
+        out[k + "image_u8"] = img8
+        out[k + "depth_u8"] = dep8
+        out[k + "kp"] = kp
+        out[k + "joints"] = joints
+        out[k + "cam"] = cam
+        out[k + "out_image_u8"] = oi8
+        out[k + "out_depth_u8"] = od8
+        out[k + "out_kp"] = ref["keypoints_2d"].numpy()
+        out[k + "out_joints"] = ref["joints_3d"].numpy()
+        out[k + "out_cam"] = np.array(list(cp["f"]) + list(cp["c"]), np.float64)
+    np.savez_compressed(os.path.join(OUT, "augment.npz"), **out)
+
+
+def gen_heatmap():
+    import torch
+    from models.common import GaussianHeatmapGenerator
+    rng = np.random.default_rng(7)
+    out = {"versions": versions()}
+    for name, hs, sigma, B in [("s32", 32, 1.5, 2), ("vit", 64, 2.0, 3), ("cnn", 256, 10.0, 2), ("odd", 50, 3.0, 2)]:
+        kp = rng.uniform(0.02, 0.98, (B, 17, 2)).astype(np.float32)
+        kp[0, 3] = [-1, -1]
+        kp[0, 5, 0] = 0.0
+        kp[1, 2] = [0.5, 0.5]
+        kp[1, 1] = [1.0, 1.0]
+        kp[1, 7] = [1e-6, 0.3]
+        hm = GaussianHeatmapGenerator(17, hs, sigma)(torch.from_numpy(kp)).numpy()
+        out[name + "_kp"] = kp
+        out[name + "_hs"] = hs
+        out[name + "_sigma"] = sigma
+        out[name + "_argmax"] = hm.reshape(B, 17, -1).argmax(-1).astype(np.int32)
+        out[name + "_sum"] = hm.astype(np.float64).sum((2, 3))
+        out[name + "_max"] = hm.max((2, 3))
+        if hs <= 32:
+            out[name + "_full"] = hm
+        else:
+            out[name + "_rows"] = hm[:, :, :: max(1, hs // 8), :]  # every (hs/8)-th row
+    np.savez_compressed(os.path.join(OUT, "heatmap.npz"), **out)
+
+
+def gen_loss():
+    import torch
+    from loss import ComprehensivePoseLoss
+    rng = np.random.default_rng(11)
+    out = {"versions": versions()}
+    keys = ["mse_loss", "l1_loss", "inter_joint_loss", "abs_root_loss", "total_loss"]
+    for name, B, w in [("b8", 8, None), ("b1", 1, None), ("b33_w", 33, dict(l1_weight=0.5, mse_weight=2.0,
+                                                                          inter_joint_loss_weight=10.0,
+                                                                          abs_root_loss_weight=3.0))]:
+        gt = rng.normal(0, 300, (B, 17, 3)).astype(np.float32)
+        pred = (gt + rng.normal(0, 50, (B, 17, 3))).astype(np.float32)
+        pred[0, 3] = pred[0, 4]      # coincident predicted joints: zero gradient through the norm
+        pred[0, 7] = gt[0, 7]        # zero difference: sign(0) = 0
+        p = torch.from_numpy(pred).requires_grad_()
+        crit = ComprehensivePoseLoss(**(w or {}))
+        total, comps = crit(p, torch.from_numpy(gt))
+        total.backward()
+        out[name + "_pred"] = pred
+        out[name + "_gt"] = gt
+        out[name + "_weights"] = np.array([crit.mse_weight, crit.l1_weight, crit.inter_joint_loss_weight,
+                                           crit.abs_root_loss_weight], np.float32)
+        out[name + "_out5"] = np.array([comps[k].item() for k in keys], np.float32)
+        out[name + "_grad"] = p.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "loss.npz"), **out)
+
+
+def gen_config():
+    from model_config import ModelConfig
+    out = {"cnn": ModelConfig("cnn").to_dict(), "transformer": ModelConfig("transformer").to_dict(),
+           "cnn_256": ModelConfig("cnn", image_size=(256, 256), heatmap_size=256).to_dict()}
+    with open(os.path.join(OUT, "model_config.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    sys.path.insert(0, os.path.join(REF, "src"))
+    os.chdir(tempfile.mkdtemp(prefix="pose_golden_"))
+    which = sys.argv[1:] or ["augment", "heatmap", "loss", "config"]
+    for w in which:
+        globals()["gen_" + w]()
+        print("wrote", w)
+
+
+if __name__ == "__main__":
+    main()

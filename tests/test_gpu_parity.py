@@ -1,0 +1,380 @@
+"""GPU: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs, against the
+goldens frozen from the live reference, and -- at BASELINE.json's full sizes -- through size-independent
+properties.  Tolerances are the ones BASELINE.json:north_star states."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _t(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------ loss
+def _loss_case(rng, B, J=17):
+    gt = rng.normal(0, 300, (B, J, 3)).astype(np.float32)
+    pred = (gt + rng.normal(0, 50, (B, J, 3))).astype(np.float32)
+    if J > 5:
+        pred[0, 3] = pred[0, 4]  # coincident joints
+        pred[0, 2] = gt[0, 2]    # zero difference
+    return pred, gt
+
+
+@pytest.mark.parametrize("B", [1, 7, 8, 256, 5000])
+def test_loss_matches_oracle(pose, oracle, B):
+    rng = np.random.default_rng(B)
+    pred, gt = _loss_case(rng, B)
+    w = (1.0, 1.0, 100.0, 1.0)
+    ref5, refg = oracle.pose_loss(pred, gt, w)
+    p = _t(pred).requires_grad_()
+    total, comps = pose.ComprehensivePoseLoss()(p, _t(gt))
+    total.backward()
+    got5 = np.array([comps[k].item() for k in ("mse_loss", "l1_loss", "inter_joint_loss", "abs_root_loss", "total_loss")])
+    assert np.allclose(got5, ref5, rtol=1e-3, atol=0), (got5, ref5)   # north_star: 1e-3 relative on fp32 losses
+    assert np.allclose(got5, ref5, rtol=2e-6), "fp32 kernel should be far inside the budget"
+    g = p.grad.cpu().numpy()
+    assert np.isfinite(g).all()
+    assert np.abs(g - refg).max() <= 1e-5 * np.abs(refg).max()
+    assert total.dim() == 0 and comps["mse_loss"].dim() == 0
+
+
+def test_loss_matches_reference_golden(pose, golden):
+    g = golden("loss.npz")
+    for name in ("b8", "b1", "b33_w"):
+        w = g[name + "_weights"]
+        crit = pose.ComprehensivePoseLoss(mse_weight=float(w[0]), l1_weight=float(w[1]),
+                                          inter_joint_loss_weight=float(w[2]), abs_root_loss_weight=float(w[3]))
+        p = _t(g[name + "_pred"]).requires_grad_()
+        total, comps = crit(p, _t(g[name + "_gt"]))
+        (total * 0.5).backward()  # upstream gradient scaling goes through autograd
+        got5 = np.array([comps[k].item() for k in ("mse_loss", "l1_loss", "inter_joint_loss", "abs_root_loss", "total_loss")])
+        assert np.allclose(got5, g[name + "_out5"], rtol=1e-5)
+        ref = g[name + "_grad"] * 0.5
+        assert np.abs(p.grad.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_loss_workspace_reuse_and_determinism(pose):
+    rng = np.random.default_rng(0)
+    pred, gt = _loss_case(rng, 4096)
+    crit = pose.ComprehensivePoseLoss()
+    outs = []
+    for _ in range(3):
+        p = _t(pred).requires_grad_()
+        total, _ = crit(p, _t(gt))
+        total.backward()
+        outs.append((total.item(), p.grad.clone()))
+    assert outs[0][0] == outs[1][0] == outs[2][0]
+    assert torch.equal(outs[0][1], outs[2][1])
+
+
+def test_loss_other_joint_counts_and_errors(pose, oracle):
+    rng = np.random.default_rng(1)
+    for J in (1, 2, 32):
+        pred, gt = _loss_case(rng, 5, J)
+        ref5, refg = oracle.pose_loss(pred, gt)
+        out5, grad = pose.loss.pose_loss_fwd_bwd(_t(pred), _t(gt), (1.0, 1.0, 100.0, 1.0))
+        got = out5.cpu().numpy()
+        if J == 1:  # mean over zero pairs is NaN in torch and in both implementations
+            assert np.isnan(got[2]) and np.isnan(ref5[2])
+            assert np.allclose(got[[0, 1, 3]], ref5[[0, 1, 3]], rtol=2e-6)
+        else:
+            assert np.allclose(got, ref5, rtol=2e-6)
+            assert np.abs(grad.cpu().numpy() - refg).max() <= 1e-5 * np.abs(refg).max()
+    with pytest.raises(RuntimeError):
+        pose.loss.pose_loss_fwd_bwd(torch.zeros(2, 40, 3, device=DEV), torch.zeros(2, 40, 3, device=DEV), (1, 1, 1, 1))
+    with pytest.raises(ValueError):
+        pose.loss.pose_loss_fwd_bwd(torch.zeros(2, 17, 3, device=DEV), torch.zeros(3, 17, 3, device=DEV), (1, 1, 1, 1))
+
+
+# --------------------------------------------------------------------------------------------- heatmap
+def _kp_case(rng, B, J=17):
+    kp = rng.uniform(0.02, 0.98, (B, J, 2)).astype(np.float32)
+    m = rng.random((B, J)) < 0.05
+    kp[m] = -1.0                 # invalid rows (<= 0) exercise the mask
+    kp[0, 0] = [0.5, 0.5]
+    if B > 1:
+        kp[1, 1] = [1.0, 1.0]
+        kp[1, 2] = [0.0, 0.4]   # exactly 0 is invalid (strict >)
+    return kp
+
+
+@pytest.mark.parametrize("hs,sigma,B", [(64, 2.0, 8), (256, 10.0, 4), (32, 1.5, 3), (50, 3.0, 2), (500, 10.0, 1)])
+def test_heatmap_matches_oracle(pose, oracle, hs, sigma, B):
+    kp = _kp_case(np.random.default_rng(hs), B)
+    ref = oracle.heatmap(kp, hs, sigma)
+    got = pose.GaussianHeatmapGenerator(17, hs, sigma).to(DEV)(_t(kp))
+    assert got.shape == (B, 17, hs, hs) and got.dtype == torch.float32
+    g = got.cpu().numpy()
+    # arg-max location per plane: bit-exact (north_star)
+    peak = oracle.heatmap_peak(kp, hs)
+    am = g.reshape(B, 17, -1).argmax(-1)
+    valid = peak >= 0
+    assert np.array_equal(am[valid], peak[valid])
+    assert (g[~valid] == 0).all()
+    # values: CUDA expf vs glibc expf, <= 2 ulp on normal numbers
+    assert np.allclose(g, ref, rtol=2.5e-7, atol=1e-37)
+
+
+def test_heatmap_matches_reference_golden(pose, golden):
+    g = golden("heatmap.npz")
+    for name in ("s32", "vit", "cnn", "odd"):
+        kp, hs, sigma = g[name + "_kp"], int(g[name + "_hs"]), float(g[name + "_sigma"])
+        hm = pose.GaussianHeatmapGenerator(17, hs, sigma).to(DEV)(_t(kp)).cpu().numpy()
+        B = kp.shape[0]
+        assert np.array_equal(hm.reshape(B, 17, -1).argmax(-1), g[name + "_argmax"])
+        ref, got = (g[name + "_full"], hm) if name + "_full" in g else (g[name + "_rows"], hm[:, :, :: max(1, hs // 8), :])
+        assert np.allclose(got, ref, rtol=4e-7, atol=1e-37)
+        assert np.allclose(hm.astype(np.float64).sum((2, 3)), g[name + "_sum"], rtol=1e-6)
+
+
+def test_heatmap_nan_keypoint_and_layouts(pose, oracle):
+    kp = _kp_case(np.random.default_rng(9), 3)
+    hs, sigma = 64, 2.0
+    ref = oracle.heatmap(kp, hs, sigma)
+    common = pose.models.common
+    # bf16 planes
+    b16 = common.render_heatmaps(_t(kp), hs, sigma, dtype=torch.bfloat16).float().cpu().numpy()
+    assert np.allclose(b16, ref, rtol=2 ** -8, atol=1e-30)
+    # channels-last into the 21-channel conv operand (3 RGB + 1 depth + 17 heat-maps), fp32 and bf16
+    for dt, tol in ((torch.float32, 2.5e-7), (torch.bfloat16, 2 ** -8)):
+        x = torch.full((3, hs, hs, 24), -7.0, dtype=dt, device=DEV)
+        common.render_heatmaps(_t(kp), hs, sigma, out=x, dtype=dt, channels_last=True, c_offset=4)
+        xc = x.float().cpu().numpy()
+        assert np.allclose(xc[..., 4:21].transpose(0, 3, 1, 2), ref, rtol=tol, atol=1e-30)
+        assert (xc[..., :4] == -7.0).all() and (xc[..., 21:] == -7.0).all()
+    # a NaN key-point gives a NaN plane (NaN * 0), like the reference
+    kp2 = kp.copy()
+    kp2[2, 5, 0] = np.nan
+    hm = pose.GaussianHeatmapGenerator(17, hs, sigma).to(DEV)(_t(kp2)).cpu().numpy()
+    assert np.isnan(hm[2, 5]).all() and np.isfinite(np.delete(hm.reshape(51, -1), 2 * 17 + 5, 0)).all()
+
+
+def test_heatmap_full_size_properties(pose, oracle):
+    """BASELINE config 2 size (B=256, hs=256): properties that do not need the oracle at full size."""
+    B, hs, sigma = 256, 256, 10.0
+    kp = _kp_case(np.random.default_rng(2), B)
+    hm = pose.GaussianHeatmapGenerator(17, hs, sigma).to(DEV)(_t(kp))
+    flat = hm.view(B, 17, -1)
+    am = flat.argmax(-1).cpu().numpy()
+    peak = oracle.heatmap_peak(kp, hs)
+    valid = peak >= 0
+    assert np.array_equal(am[valid], peak[valid])
+    mx = flat.max(-1).values.cpu().numpy()
+    assert (mx[~valid] == 0).all() and (mx[valid] <= 1.0).all() and (mx[valid] > 0.99).all()
+    assert torch.isfinite(hm).all() and (hm >= 0).all()
+    # spot-check 3 samples against the oracle
+    idx = [0, 101, 255]
+    assert np.allclose(hm[idx].cpu().numpy(), oracle.heatmap(kp[idx], hs, sigma), rtol=2.5e-7, atol=1e-37)
+
+
+# --------------------------------------------------------------------------------------------- augment
+def _aug_inputs(rng, B, H, W, root_relative=False):
+    img = rng.random((B, 3, H, W), dtype=np.float32)
+    dep = rng.random((B, 1, H, W), dtype=np.float32)
+    img[:, :, : H // 4, : W // 3] = 0.5          # flat patch: integer-valued bilinear results
+    img[:, 1, H // 2:, :] = np.float32(1.0)       # saturated plane
+    kp = rng.uniform(0.05, 0.95, (B, 17, 2)).astype(np.float32)
+    joints = rng.normal(0, 300, (B, 17, 3)).astype(np.float32)
+    if not root_relative:
+        joints[:, :, 2] += 4000
+    cam = np.tile(np.array([1145.0 * W / 1000, 1144.0 * H / 1000, W / 2.0, H / 2.0]), (B, 1))
+    return img, dep, kp, joints, cam
+
+
+def _check_aug(pose, oracle, aug, img, dep, kp, joints, cam, params, pad_to=None):
+    B = img.shape[0]
+    out = aug.augment_batch(_t(img), _t(dep), _t(kp), _t(joints), _t(cam), params=params, pad_to=pad_to)
+    assert aug.kernel_error_flag() == 0
+    o_img, o_dep = out["image"].cpu().numpy(), out["depth"].cpu().numpy()
+    sizes = out["sizes"].cpu().numpy()
+    for i in range(B):
+        ref = oracle.augment_sample(img[i], dep[i], kp[i], joints[i], cam[i], params[i], aug.flags)
+        h, w = ref["image"].shape[1:]
+        assert tuple(sizes[i]) == (h, w), (i, sizes[i], h, w)
+        # uint8 pixels: north_star allows 1 LSB; this implementation is bit-exact
+        assert np.array_equal(o_img[i, :, :h, :w], ref["image"]), f"sample {i}: RGB differs, params {params[i]}"
+        assert np.array_equal(o_dep[i, :, :h, :w], ref["depth"]), f"sample {i}: depth differs"
+        # collator-style zero padding
+        assert (o_img[i, :, h:, :] == 0).all() and (o_img[i, :, :, w:] == 0).all()
+        assert (o_dep[i, :, h:, :] == 0).all() and (o_dep[i, :, :, w:] == 0).all()
+        # key-point / joint arithmetic: bit-exact fp32
+        assert np.array_equal(out["keypoints_2d"][i].cpu().numpy().view(np.uint32), ref["keypoints_2d"].view(np.uint32)), i
+        assert np.array_equal(out["joints_3d"][i].cpu().numpy().view(np.uint32), ref["joints_3d"].view(np.uint32)), i
+        assert np.array_equal(out["camera"][i].cpu().numpy(), ref["cam"])
+    return out
+
+
+@pytest.mark.parametrize("H,W,B", [(64, 64, 16), (256, 256, 6), (48, 80, 8), (128, 128, 9)])
+def test_augment_matches_oracle_all_stages(pose, oracle, H, W, B):
+    rng = np.random.default_rng(H * 7 + W)
+    img, dep, kp, joints, cam = _aug_inputs(rng, B, H, W, root_relative=(H == 128))
+    aug = pose.PoseAugmentor()
+    np.random.seed(H + W)
+    params = aug.draw_params(B)
+    params[0, 2] = 1.0     # unchanged size: Pillow's resize returns a copy
+    params[1, 2] = 0.8
+    params[2, 2] = 1.2
+    _check_aug(pose, oracle, aug, img, dep, kp, joints, cam, params)
+
+
+def test_augment_stage_subsets_and_extremes(pose, oracle):
+    rng = np.random.default_rng(5)
+    H = W = 96
+    B = 6
+    img, dep, kp, joints, cam = _aug_inputs(rng, B, H, W)
+    ctors = [dict(enable_rotation=False, enable_scale=False), dict(enable_flip=False, enable_translate=False, enable_color=False),
+             dict(flip_prob=1.0, enable_rotation=False, enable_scale=False, enable_translate=False, enable_color=False),
+             dict(enable_flip=False, enable_rotation=False, enable_scale=True, enable_translate=False, enable_color=False),
+             dict(brightness_range=(0.3, 1.9), contrast_range=(0.2, 2.5), rotation_range=(-180, 180), scale_range=(0.5, 1.7)),
+             dict(enable_flip=False, enable_rotation=False, enable_scale=False, enable_translate=False, enable_color=False)]
+    for kw in ctors:
+        aug = pose.PoseAugmentor(**kw)
+        np.random.seed(11)
+        params = aug.draw_params(B)
+        _check_aug(pose, oracle, aug, img, dep, kp, joints, cam, params)
+    # exact multiples of 90 degrees take Pillow's transpose shortcuts; big translations leave only fill
+    aug = pose.PoseAugmentor()
+    np.random.seed(3)
+    params = aug.draw_params(B)
+    params[:, 1] = [0.0, 90.0, 180.0, -90.0, 360.0, 29.999]
+    params[4, 3:5] = [0.99, -0.99]
+    _check_aug(pose, oracle, aug, img, dep, kp, joints, cam, params, pad_to=(120, 120))
+
+
+def test_augment_matches_reference_golden(pose, golden):
+    g = golden("augment.npz")
+    for i in range(int(g["n"])):
+        k = f"c{i}_"
+        aug = pose.PoseAugmentor(**json.loads(str(g[k + "ctor"])))
+        img8, dep8 = g[k + "image_u8"], g[k + "depth_u8"]
+        img = img8.astype(np.float32) / np.float32(255)
+        dep = dep8.astype(np.float32) / np.float32(255)
+        for as_u8 in (False, True):
+            if as_u8 and not np.array_equal((img * np.float32(255)).astype(np.uint8), img8):
+                continue  # u8/255*255 truncates below the original for some values: fp32 and u8 inputs differ
+            a = (_t(img8[None]), _t(dep8[None])) if as_u8 else (_t(img[None]), _t(dep[None]))
+            out = aug.augment_batch(a[0], a[1], _t(g[k + "kp"][None]), _t(g[k + "joints"][None]), _t(g[k + "cam"][None]),
+                                    params=g[k + "params"][None])
+            h, w = out["sizes"][0].tolist()
+            ref_i, ref_d = g[k + "out_image_u8"], g[k + "out_depth_u8"]
+            assert (h, w) == ref_i.shape[1:], (i, h, w, ref_i.shape)
+            got_i = out["image"][0, :, :h, :w].cpu().numpy()
+            got_d = out["depth"][0, :, :h, :w].cpu().numpy()
+            assert np.array_equal(got_i, ref_i.astype(np.float32) / np.float32(255)), f"golden case {i}"
+            assert np.array_equal(got_d, ref_d.astype(np.float32) / np.float32(255)), f"golden case {i}"
+            assert np.array_equal(out["keypoints_2d"][0].cpu().numpy().view(np.uint32), g[k + "out_kp"].view(np.uint32))
+            assert np.array_equal(out["joints_3d"][0].cpu().numpy().view(np.uint32), g[k + "out_joints"].view(np.uint32))
+            assert np.array_equal(out["camera"][0].cpu().numpy(), g[k + "out_cam"])
+
+
+def test_augment_call_is_drop_in(pose, oracle):
+    """__call__(sample) -> sample, CPU tensors in and out like the reference, global np.random consumed in order."""
+    rng = np.random.default_rng(8)
+    img, dep, kp, joints, cam = _aug_inputs(rng, 1, 64, 64)
+    sample = dict(image=torch.from_numpy(img[0]), depth=torch.from_numpy(dep[0]), keypoints_2d=torch.from_numpy(kp[0]),
+                  joints_3d=torch.from_numpy(joints[0]), camera_params=dict(R=None, t=None, f=list(cam[0, :2]), c=list(cam[0, 2:])),
+                  extra="kept")
+    aug = pose.PoseAugmentor()
+    np.random.seed(21)
+    params = aug.draw_params(1)
+    np.random.seed(21)
+    out = aug(sample)
+    ref = oracle.augment_sample(img[0], dep[0], kp[0], joints[0], cam[0], params[0], aug.flags)
+    assert out["extra"] == "kept" and out["image"].device.type == "cpu"
+    assert np.array_equal(out["image"].numpy(), ref["image"]) and np.array_equal(out["depth"].numpy(), ref["depth"])
+    assert np.array_equal(out["keypoints_2d"].numpy(), ref["keypoints_2d"])
+    assert out["camera_params"]["f"] == list(ref["cam"][:2]) and sample["camera_params"]["f"] == list(cam[0, :2])
+
+
+def test_augment_full_size_properties(pose, oracle):
+    """BASELINE config 2 size (B=256, 256x256): identity parameters round-trip; flip twice is the identity;
+    random samples spot-checked against the oracle."""
+    B, H, W = 256, 256, 256
+    rng = np.random.default_rng(4)
+    img, dep, kp, joints, cam = _aug_inputs(rng, B, H, W)
+    aug = pose.PoseAugmentor()
+    ident = np.zeros((B, 8))
+    ident[:, 2] = 1.0
+    ident[:, 5:7] = 1.0
+    out = aug.augment_batch(_t(img), _t(dep), _t(kp), _t(joints), _t(cam), params=ident)
+    q = lambda a: (a * np.float32(255)).astype(np.uint8).astype(np.float32) / np.float32(255)
+    assert out["image"].shape == (B, 3, 256, 256)
+    assert np.array_equal(out["image"].cpu().numpy(), q(img)) and np.array_equal(out["depth"].cpu().numpy(), q(dep))
+    flip = ident.copy()
+    flip[:, 0] = 1.0
+    o1 = aug.augment_batch(_t(img), _t(dep), _t(kp), _t(joints), _t(cam), params=flip)
+    assert np.array_equal(o1["image"].cpu().numpy(), q(img)[..., ::-1])
+    np.random.seed(0)
+    params = aug.draw_params(B)
+    out = aug.augment_batch(_t(img), _t(dep), _t(kp), _t(joints), _t(cam), params=params)
+    assert aug.kernel_error_flag() == 0
+    sizes = out["sizes"].cpu().numpy()
+    assert np.array_equal(sizes[:, 0], (256 * params[:, 2]).astype(int))
+    for i in (0, 17, 128, 255):
+        ref = oracle.augment_sample(img[i], dep[i], kp[i], joints[i], cam[i], params[i], aug.flags)
+        h, w = ref["image"].shape[1:]
+        assert np.array_equal(out["image"][i, :, :h, :w].cpu().numpy(), ref["image"])
+        assert np.array_equal(out["depth"][i, :, :h, :w].cpu().numpy(), ref["depth"])
+        assert np.array_equal(out["keypoints_2d"][i].cpu().numpy(), ref["keypoints_2d"])
+
+
+# ------------------------------------------------------------------------------ tcgen05 GEMM / head
+def _ref_linear(a_bf16, w_bf16, bias, act):
+    """Plain PyTorch fp32 reference of the same op on the same bf16-rounded operands."""
+    y = a_bf16.float() @ w_bf16.float().t()
+    if bias is not None:
+        y = y + bias
+    if act == "silu":
+        y = torch.nn.functional.silu(y)
+    elif act == "gelu":
+        y = torch.nn.functional.gelu(y)
+    elif act == "relu":
+        y = torch.relu(y)
+    return y
+
+
+@pytest.mark.parametrize("M,N,K,act", [(256, 1024, 1024, "silu"), (128, 128, 64, None), (1, 51, 512, None),
+                                       (300, 200, 136, "gelu"), (257, 768, 3072, "relu"), (4096, 64, 64, None),
+                                       (130, 16, 512, None), (1000, 3072, 768, "gelu")])
+def test_gemm_tcgen05_matches_fp32_reference(pose, M, N, K, act):
+    g = torch.Generator(device="cpu").manual_seed(M * 31 + N)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) * (1.0 / K ** 0.5)).to(DEV).bfloat16()
+    bias = torch.randn(N, generator=g).to(DEV)
+    ops = pose.ops
+    ref = _ref_linear(a, w, bias, act)
+    got = ops.gemm_bf16(a, w, bias, act=act, out_dtype=torch.float32)
+    # fp32 accumulation of exact bf16 products: only summation order differs
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), (got - ref).abs().max().item()
+    got16 = ops.gemm_bf16(a, w, None, act=None, out_dtype=torch.bfloat16)
+    ref16 = _ref_linear(a, w, None, None)
+    assert torch.allclose(got16.float(), ref16, rtol=2 ** -7, atol=1e-2)
+
+
+def test_regression_head_matches_fp32_reference(pose):
+    """PoseRegressionHead (common.py:55-89) CNN flavour 1024-1024-512-51 SiLU and ViT-style dims with GELU.
+    Tolerance: bf16 operands / fp32 accumulate against the fp32 module on outputs of O(1)."""
+    for in_f, hidden, act in ((1024, [1024, 512], "silu"), (768, [1024, 512, 256], "gelu")):
+        torch.manual_seed(0)
+        head = pose.PoseRegressionHead(in_f, 17, hidden_dims=hidden, dropout=0.2, activation=act).to(DEV).eval()
+        x = torch.randn(256, in_f, device=DEV)
+        with torch.no_grad():
+            got = head(x)
+            h = x
+            lins = [m[0] if isinstance(m, torch.nn.Sequential) else m for m in head.decoder]
+            for i, lin in enumerate(lins):
+                h = torch.nn.functional.linear(h, lin.weight, lin.bias)
+                if i < len(lins) - 1:
+                    h = torch.nn.functional.silu(h) if act == "silu" else torch.nn.functional.gelu(h)
+            ref = h.view(-1, 17, 3)
+        assert got.shape == (256, 17, 3) and got.dtype == torch.float32
+        err = (got - ref).abs().max().item()
+        assert err < 3e-2 * max(1.0, ref.abs().max().item()), err

@@ -1,0 +1,43 @@
+"""CPU: host-side logic of the drop-in classes (no kernels launched)."""
+import numpy as np
+
+
+def test_draw_params_consumes_rng_in_reference_order(pose, golden):
+    """The goldens record the explicit draws of the live reference for each seed/constructor."""
+    import json
+    g = golden("augment.npz")
+    for i in range(int(g["n"])):
+        k = f"c{i}_"
+        aug = pose.PoseAugmentor(**json.loads(str(g[k + "ctor"])))
+        assert aug.flags == int(g[k + "flags"])
+        np.random.seed(int(g[k + "seed"]))
+        p = aug.draw_params(1)[0]
+        assert np.array_equal(p, g[k + "params"]), (i, p, g[k + "params"])
+
+
+def test_draw_params_batch_is_sequential(pose):
+    aug = pose.PoseAugmentor()
+    np.random.seed(5)
+    a = aug.draw_params(3)
+    np.random.seed(5)
+    b = np.stack([aug.draw_params(1)[0] for _ in range(3)])
+    assert np.array_equal(a, b)
+
+
+def test_state_dict_keys_of_common_modules(pose):
+    hm = pose.GaussianHeatmapGenerator(17, 64, 2.0)
+    assert sorted(hm.state_dict()) == ["x_grid", "y_grid"]
+    assert hm.state_dict()["x_grid"][3, 5] == 5 and hm.state_dict()["y_grid"][3, 5] == 3
+    head = pose.PoseRegressionHead(1024, 17, hidden_dims=[1024, 512], dropout=0.2, activation="silu")
+    assert sorted(head.state_dict()) == sorted(
+        ["decoder.0.0.weight", "decoder.0.0.bias", "decoder.1.0.weight", "decoder.1.0.bias", "decoder.2.weight",
+         "decoder.2.bias"])
+    assert head.state_dict()["decoder.2.weight"].shape == (51, 512)
+
+
+def test_loss_module_attributes(pose):
+    crit = pose.ComprehensivePoseLoss()
+    assert (crit.mse_weight, crit.l1_weight, crit.inter_joint_loss_weight, crit.abs_root_loss_weight) == (1, 1, 100, 1)
+    crit = pose.ComprehensivePoseLoss(l1_weight=0.5, mse_weight=2.0, inter_joint_loss_weight=10.0,
+                                      abs_root_loss_weight=3.0)
+    assert crit._weights() == (2.0, 0.5, 10.0, 3.0)
