@@ -153,10 +153,10 @@ struct AugSmemLayout {
 };
 static AugSmemLayout smem_layout(int W, const pose_aug_launch &l) {
     AugSmemLayout s;
-    s.tab_ints = l.max_out_w * (2 + l.max_ksize + 2);
+    s.tab_ints = l.max_out_w * (2 + l.max_ksize + 2) + l.max_band_rows * (4 + l.max_ksize);
     s.tab_ints = (s.tab_ints + 3) & ~3;
-    s.h_px = l.max_rot_rows * l.max_out_w;
-    int a = l.max_rot_rows * W, b = l.max_band_rows * l.max_out_w;
+    s.h_px = (l.max_rot_rows * l.max_out_w + 3) & ~3;
+    int a = l.max_rot_rows * W, b = l.max_band_rows * ((l.max_out_w + 3) & ~3);
     s.rot_px = a > b ? a : b;
     s.bytes = (size_t)s.tab_ints * 4 + (size_t)s.h_px * 4 + (size_t)s.rot_px * 4;
     return s;
@@ -329,7 +329,7 @@ __device__ __forceinline__ unsigned clip8(int v) {
     v >>= kPrecisionBits;
     return (unsigned)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
-// Blend.c ImagingBlend, one channel
+// Blend.c ImagingBlend, one channel (used to build the 256-entry brightness / contrast tables)
 __device__ __forceinline__ unsigned blend8(int p1, int p2, float alpha, int extrapolate) {
     float tmp = (float)p1 + alpha * (float)(p2 - p1);
     if (!extrapolate) return (unsigned)__float2int_rz(tmp) & 0xffu;
@@ -338,18 +338,24 @@ __device__ __forceinline__ unsigned blend8(int p1, int p2, float alpha, int extr
     return (unsigned)__float2int_rz(tmp);
 }
 
+// byte k of a packed pixel as an exact float without the conversion pipe: 0x4B0000bb = 2^23 + bb
+__device__ __forceinline__ float byte_f(unsigned w, unsigned sel) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
+}
+
 // bilinear_filter32RGB for one channel: fp32 evaluation guarded by an error bound, exact fp64
 // re-evaluation only when the truncation could differ (|fp32 - fp64| < 2.5e-4 by construction)
-__device__ __forceinline__ unsigned bilerp8(int p0, int p1, int q0, int q1, float dxf, float dyf, double dx, double dy) {
-    if (p0 == p1 && p0 == q0 && p0 == q1) return (unsigned)p0;
-    float v1 = fmaf((float)(p1 - p0), dxf, (float)p0);
-    float v2 = fmaf((float)(q1 - q0), dxf, (float)q0);
-    float v = fmaf(v2 - v1, dyf, v1);
-    float fl = floorf(v), fr = v - fl;
-    if (fr > 2.5e-4f && fr < 1.0f - 2.5e-4f) return (unsigned)(int)fl;
-    double a = (double)p0 + ((double)p1 - (double)p0) * dx;
-    double b = (double)q0 + ((double)q1 - (double)q0) * dx;
-    double r = a + (b - a) * dy;
+__device__ __forceinline__ unsigned bilerp8(float p0, float p1, float q0, float q1, float dxf, float dyf, double dx,
+                                            double dy) {
+    const float v1 = fmaf(p1 - p0, dxf, p0);
+    const float v2 = fmaf(q1 - q0, dxf, q0);
+    const float v = fmaf(v2 - v1, dyf, v1);
+    const float t = __fadd_rz(v, 8388608.0f);  // v in [0, 256): truncation == floor, via the 2^23 trick
+    const float fl = t - 8388608.0f, fr = v - fl;
+    if (fr > 2.5e-4f && fr < 1.0f - 2.5e-4f) return __float_as_uint(t) & 0xffu;
+    const double a = (double)p0 + ((double)p1 - (double)p0) * dx;
+    const double b = (double)q0 + ((double)q1 - (double)q0) * dx;
+    const double r = a + (b - a) * dy;
     return (unsigned)(int)r & 0xffu;
 }
 
@@ -363,12 +369,28 @@ __device__ __forceinline__ void transpose_src(int mode, int r, int c, int H, int
     else { sy = H - 1 - c; sx = r; }
 }
 
-__global__ void __launch_bounds__(kAugThreads, 1)
+// work items are (column, group of consecutive rows): a thread keeps its column's constants in registers
+// for the rows of the group, and items are dealt round-robin so every phase is balanced for any width.
+// Exact i / d for i * d < 2^32 with one multiply-high.
+struct FastDiv {
+    unsigned m;
+    int d;
+    __device__ explicit FastDiv(int d_) : m(d_ > 1 ? 0xFFFFFFFFu / (unsigned)d_ + 1u : 0u), d(d_) {}
+    __device__ __forceinline__ void divmod(int i, int &q, int &r) const {
+        q = d > 1 ? (int)__umulhi((unsigned)i, m) : i;
+        r = i - q * d;
+    }
+};
+
+constexpr double kFloorMagic = 6755399441055744.0;  // 2^52 + 2^51
+
+template <int KS>
+__global__ void __launch_bounds__(kAugThreads, 2)
 aug_fused_kernel(const uchar4 *__restrict__ packed, const AugPlan *__restrict__ plans, const int *__restrict__ tables,
                  const float *__restrict__ kp_in, const float *__restrict__ joints_in, const double *__restrict__ cam_in,
                  float *__restrict__ image_out, float *__restrict__ depth_out, float *__restrict__ kp_out,
                  float *__restrict__ joints_out, double *__restrict__ cam_out, int32_t *__restrict__ out_hw,
-                 int H, int W, int J, int PH, int PW, int maxW, int maxH, int KS, int max_rot_rows, int max_band_rows,
+                 int H, int W, int J, int PH, int PW, int maxW, int maxH, int max_rot_rows, int max_band_rows,
                  int tab_ints, int h_px, int flags, int *__restrict__ err_flag) {
     cg::cluster_group cluster = cg::this_cluster();
     const int CL = (int)cluster.num_blocks();
@@ -377,10 +399,11 @@ aug_fused_kernel(const uchar4 *__restrict__ packed, const AugPlan *__restrict__ 
     const int tid = threadIdx.x;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int *s_bh = (int *)smem_raw;
-    int *s_kh = s_bh + maxW * 2;
-    int *s_nnx = s_kh + maxW * KS;
-    int *s_trx = s_nnx + maxW;
+    int *s_bh = (int *)smem_raw;              // [maxW][2]  horizontal bounds
+    int *s_kh = s_bh + maxW * 2;              // [maxW][KS] horizontal coefficients
+    int *s_nnx = s_kh + maxW * KS;            // [maxW]     nearest-resize source column
+    int *s_trx = s_nnx + maxW;                // [maxW]     translate source column
+    int *s_row = s_trx + maxW;                // [max_band_rows][4 + KS]: sy, ry, ymin - rr0, cnt, kv[KS]
     uchar4 *s_h = (uchar4 *)(smem_raw + (size_t)tab_ints * 4);
     uchar4 *s_rot = s_h + h_px;   // phases A-B
     uchar4 *s_out = s_rot;        // phases C-E (the rotated band is dead by then)
@@ -389,6 +412,9 @@ aug_fused_kernel(const uchar4 *__restrict__ packed, const AugPlan *__restrict__ 
     __shared__ int s_rng[4];          // R0, R1 (resized rows), rr0, rr1 (rotated rows)
     __shared__ unsigned s_grey;       // this CTA's grey-level partial sum
     __shared__ unsigned s_total;
+    __shared__ unsigned char s_lutb[256];  // brightness: u8 -> u8
+    __shared__ float s_lutc[256];          // contrast then /255: u8 -> fp32
+    __shared__ float s_lutd[256];          // /255: u8 -> fp32
 
     if (tid < (int)(sizeof(AugPlan) / 4)) ((int *)&pl)[tid] = ((const int *)(plans + b))[tid];
     if (tid == 0) s_grey = 0u;
@@ -397,13 +423,19 @@ aug_fused_kernel(const uchar4 *__restrict__ packed, const AugPlan *__restrict__ 
     const AugTables t = table_offsets(maxW, maxH, KS);
     const int *T = tables + (size_t)b * t.stride;
     const int oW = pl.oW, oH = pl.oH, flip = pl.flip, mode = pl.rot_mode;
+    const int opitch = (oW + 3) & ~3;
     const int rows_per = (oH + CL - 1) / CL;
     const int y0 = min(oH, rank * rows_per), y1 = min(oH, y0 + rows_per);
     const int nband = y1 - y0;
     const uchar4 *src = packed + (size_t)b * H * W;
+    const bool color = flags & POSE_AUG_COLOR;
 
     // tables shared by every row of the band -> smem (one contiguous block: bh, kh, nnx, trx)
     for (int i = tid; i < maxW * (2 + KS + 2); i += kAugThreads) s_bh[i] = __ldg(T + i);
+    if (tid < 256) {
+        s_lutb[tid] = (unsigned char)(color ? blend8(0, tid, pl.bright, pl.bright_ex) : (unsigned)tid);
+        s_lutd[tid] = __fdiv_rn((float)tid, 255.0f);
+    }
     // resized-row range needed by this band (translate is a monotone shift), then rotated-row range
     if (tid < 32) {
         int lo = 0x7fffffff, hi = -1;
@@ -434,105 +466,163 @@ aug_fused_kernel(const uchar4 *__restrict__ packed, const AugPlan *__restrict__ 
     const int R1 = s_rng[1], rr0 = s_rng[2], rr1 = s_rng[3];
     const int n_rot = rr1 - rr0;
     const bool have_rows = R1 > 0;
+    // per-row table of the band for phase C
+    for (int i = tid; i < nband; i += kAugThreads) {
+        int *rt = s_row + i * (4 + KS);
+        const int sy = have_rows ? __ldg(T + t.try_ + y0 + i) : -1;
+        rt[0] = sy;
+        if (sy >= 0) {
+            rt[1] = __ldg(T + t.nny + sy);
+            rt[2] = __ldg(T + t.bv + sy * 2) - rr0;
+            rt[3] = __ldg(T + t.bv + sy * 2 + 1);
+#pragma unroll
+            for (int q = 0; q < KS; ++q) rt[4 + q] = __ldg(T + t.kv + sy * KS + q);
+        }
+    }
 
     // ---- phase A: rotated band (rows rr0..rr1 of the rotated image, all W columns) ----
     if (mode == 0) {
-        const double a0 = pl.rot[0], a1 = pl.rot[1], a2 = pl.rot[2], a3 = pl.rot[3], a4 = pl.rot[4], a5 = pl.rot[5];
-        for (int idx = tid; idx < n_rot * W; idx += kAugThreads) {
-            const int ry = idx / W, xo = idx - ry * W, yo = rr0 + ry;
-            const double xs = (double)xo + 0.5, ys = (double)yo + 0.5;
-            double xin = a0 * xs + a1 * ys + a2;
-            double yin = a3 * xs + a4 * ys + a5;
-            uchar4 o = make_uchar4(0, 0, 0, 0);
-            if (!(xin < 0.0 || xin >= (double)W || yin < 0.0 || yin >= (double)H)) {
-                xin -= 0.5;
-                yin -= 0.5;
-                const int x = __double2int_rd(xin), y = __double2int_rd(yin);
-                const double dx = xin - (double)x, dy = yin - (double)y;
-                const int x0 = src_col(clampi(x, 0, W - 1), W, flip), x1 = src_col(clampi(x + 1, 0, W - 1), W, flip);
-                const int yc = clampi(y, 0, H - 1);
-                const int yn = (y + 1 >= 0 && y + 1 < H) ? y + 1 : yc;  // v2 = v1 when the lower row is outside
-                const uchar4 p0 = __ldg(src + (size_t)yc * W + x0), p1 = __ldg(src + (size_t)yc * W + x1);
-                const uchar4 q0 = __ldg(src + (size_t)yn * W + x0), q1 = __ldg(src + (size_t)yn * W + x1);
-                const float dxf = (float)dx, dyf = (float)dy;
-                o.x = (unsigned char)bilerp8(p0.x, p1.x, q0.x, q1.x, dxf, dyf, dx, dy);
-                o.y = (unsigned char)bilerp8(p0.y, p1.y, q0.y, q1.y, dxf, dyf, dx, dy);
-                o.z = (unsigned char)bilerp8(p0.z, p1.z, q0.z, q1.z, dxf, dyf, dx, dy);
+        const double a1 = pl.rot[1], a2 = pl.rot[2], a4 = pl.rot[4], a5 = pl.rot[5];
+        constexpr int RG = 2;
+        const FastDiv dv(W);
+        const int n_items = W * ((n_rot + RG - 1) / RG);
+        for (int it = tid; it < n_items; it += kAugThreads) {
+            int rq, xo;
+            dv.divmod(it, rq, xo);
+            const double xs = (double)xo + 0.5;
+            const double a0xs = pl.rot[0] * xs, a3xs = pl.rot[3] * xs;
+#pragma unroll
+            for (int u = 0; u < RG; ++u) {
+                const int ry = rq * RG + u;
+                if (ry >= n_rot) break;
+                const double ys = (double)(rr0 + ry) + 0.5;
+                double xin = (a0xs + a1 * ys) + a2;
+                double yin = (a3xs + a4 * ys) + a5;
+                unsigned o = 0;
+                if (!(xin < 0.0 || xin >= (double)W || yin < 0.0 || yin >= (double)H)) {
+                    xin -= 0.5;
+                    yin -= 0.5;
+                    // floor without the conversion pipe: round-down add of 2^52 + 2^51 leaves floor() in the low word
+                    const double tx_ = __dadd_rd(xin, kFloorMagic), ty_ = __dadd_rd(yin, kFloorMagic);
+                    const int x = __double2loint(tx_), y = __double2loint(ty_);
+                    const double dx = xin - (tx_ - kFloorMagic), dy = yin - (ty_ - kFloorMagic);
+                    const int x0 = src_col(clampi(x, 0, W - 1), W, flip), x1 = src_col(clampi(x + 1, 0, W - 1), W, flip);
+                    const int yc = clampi(y, 0, H - 1);
+                    const int yn = (y + 1 >= 0 && y + 1 < H) ? y + 1 : yc;  // v2 = v1 when the lower row is outside
+                    const uchar4 *r0p = src + (size_t)yc * W, *r1p = src + (size_t)yn * W;
+                    const unsigned p0 = __ldg((const unsigned *)(r0p + x0)), p1 = __ldg((const unsigned *)(r0p + x1));
+                    const unsigned q0 = __ldg((const unsigned *)(r1p + x0)), q1 = __ldg((const unsigned *)(r1p + x1));
+                    if (((p0 ^ p1) | (p0 ^ q0) | (p0 ^ q1)) << 8 == 0) {
+                        o = p0 & 0x00ffffffu;  // flat RGB neighbourhood: exact in any arithmetic
+                    } else {
+                        const float dxf = (float)dx, dyf = (float)dy;
+                        const unsigned r = bilerp8(byte_f(p0, 0x7540), byte_f(p1, 0x7540), byte_f(q0, 0x7540), byte_f(q1, 0x7540), dxf, dyf, dx, dy);
+                        const unsigned g = bilerp8(byte_f(p0, 0x7541), byte_f(p1, 0x7541), byte_f(q0, 0x7541), byte_f(q1, 0x7541), dxf, dyf, dx, dy);
+                        const unsigned bl = bilerp8(byte_f(p0, 0x7542), byte_f(p1, 0x7542), byte_f(q0, 0x7542), byte_f(q1, 0x7542), dxf, dyf, dx, dy);
+                        o = r | (g << 8) | (bl << 16);
+                    }
+                }
+                ((unsigned *)s_rot)[ry * W + xo] = o;
             }
-            s_rot[idx] = o;
         }
     } else {
-        for (int idx = tid; idx < n_rot * W; idx += kAugThreads) {
-            const int ry = idx / W, xo = idx - ry * W;
-            int sy, sx;
+        const FastDiv dv(W);
+        for (int it = tid; it < n_rot * W; it += kAugThreads) {
+            int ry, xo, sy, sx;
+            dv.divmod(it, ry, xo);
             transpose_src(mode, rr0 + ry, xo, H, W, sy, sx);
-            s_rot[idx] = __ldg(src + (size_t)sy * W + src_col(sx, W, flip));
+            s_rot[it] = __ldg(src + (size_t)sy * W + src_col(sx, W, flip));
         }
     }
     __syncthreads();
 
-    // ---- phase B: horizontal antialias pass over the band ----
-    for (int idx = tid; idx < n_rot * oW; idx += kAugThreads) {
-        const int row = idx / oW, xx = idx - row * oW;
-        const int xmin = s_bh[xx * 2], cnt = s_bh[xx * 2 + 1];
-        const int *k = s_kh + xx * KS;
-        const uchar4 *in = s_rot + row * W + xmin;
-        int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-        for (int q = 0; q < cnt; ++q) {
-            const uchar4 p = in[q];
-            const int kq = k[q];
-            s0 += (int)p.x * kq;
-            s1 += (int)p.y * kq;
-            s2 += (int)p.z * kq;
+    // ---- phase B: horizontal antialias pass over the band (coefficients of the column in registers) ----
+    {
+        constexpr int RG = 4;
+        const FastDiv dv(oW);
+        const int n_items = oW * ((n_rot + RG - 1) / RG);
+        for (int it = tid; it < n_items; it += kAugThreads) {
+            int rq, xx;
+            dv.divmod(it, rq, xx);
+            const int xmin = s_bh[xx * 2], cnt = s_bh[xx * 2 + 1];
+            int k[KS];
+#pragma unroll
+            for (int q = 0; q < KS; ++q) k[q] = q < cnt ? s_kh[xx * KS + q] : 0;
+#pragma unroll
+            for (int u = 0; u < RG; ++u) {
+                const int row = rq * RG + u;
+                if (row >= n_rot) break;
+                const unsigned *in = (const unsigned *)s_rot + row * W + xmin;
+                int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+#pragma unroll
+                for (int q = 0; q < KS; ++q) {
+                    if (q < cnt) {
+                        const unsigned p = in[q];
+                        s0 += (int)(p & 0xffu) * k[q];
+                        s1 += (int)((p >> 8) & 0xffu) * k[q];
+                        s2 += (int)((p >> 16) & 0xffu) * k[q];
+                    }
+                }
+                ((unsigned *)s_h)[row * oW + xx] = clip8(s0) | (clip8(s1) << 8) | (clip8(s2) << 16);
+            }
         }
-        s_h[idx] = make_uchar4(clip8(s0), clip8(s1), clip8(s2), 0);
     }
     __syncthreads();  // s_rot is dead from here on; s_out aliases it
 
     // ---- phase C: vertical pass at the translated source position, depth gather, brightness ----
     unsigned grey = 0;
-    for (int idx = tid; idx < nband * oW; idx += kAugThreads) {
-        const int yy = idx / oW, x = idx - yy * oW, y = y0 + yy;
-        const int sy = __ldg(T + t.try_ + y), sx = s_trx[x];
-        uchar4 o = make_uchar4(0, 0, 0, 0);
-        if (have_rows && sy >= 0 && sx >= 0) {
-            const int ymin = __ldg(T + t.bv + sy * 2) - rr0, cnt = __ldg(T + t.bv + sy * 2 + 1);
-            const int *k = T + t.kv + sy * KS;
-            int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-            for (int q = 0; q < cnt; ++q) {
-                const uchar4 p = s_h[(ymin + q) * oW + sx];
-                const int kq = __ldg(k + q);
-                s0 += (int)p.x * kq;
-                s1 += (int)p.y * kq;
-                s2 += (int)p.z * kq;
-            }
-            unsigned r = clip8(s0), g = clip8(s1), bl = clip8(s2);
-            if (flags & POSE_AUG_COLOR) {
-                r = blend8(0, (int)r, pl.bright, pl.bright_ex);
-                g = blend8(0, (int)g, pl.bright, pl.bright_ex);
-                bl = blend8(0, (int)bl, pl.bright, pl.bright_ex);
-            }
-            grey += (19595u * r + 38470u * g + 7471u * bl + 0x8000u) >> 16;
-            // depth: nearest translate -> nearest resize -> nearest rotate (16.16) -> flip
-            unsigned d = 0;
-            const int ry = __ldg(T + t.nny + sy), rx = s_nnx[sx];
-            if (ry >= 0 && rx >= 0) {
-                int iy, ix;
-                bool ok = true;
-                if (mode == 0) {
-                    const int xxf = pl.fix[2] + ry * pl.fix[1] + rx * pl.fix[0];
-                    const int yyf = pl.fix[5] + ry * pl.fix[4] + rx * pl.fix[3];
-                    ix = xxf >> 16;
-                    iy = yyf >> 16;
-                    ok = ix >= 0 && ix < W && iy >= 0 && iy < H;
-                } else {
-                    transpose_src(mode, ry, rx, H, W, iy, ix);
+    {
+        constexpr int RG = 4;
+        const FastDiv dv(opitch);
+        const int n_items = opitch * ((nband + RG - 1) / RG);
+        for (int it = tid; it < n_items; it += kAugThreads) {
+            int rq, x;
+            dv.divmod(it, rq, x);
+            const int sx = x < oW ? s_trx[x] : -1;
+            const int rx = sx >= 0 ? s_nnx[sx] : -1;
+            const int cxf = rx * pl.fix[0], cyf = rx * pl.fix[3];
+#pragma unroll
+            for (int u = 0; u < RG; ++u) {
+                const int yy = rq * RG + u;
+                if (yy >= nband) break;
+                const int *rt = s_row + yy * (4 + KS);
+                const int sy = rt[0];
+                unsigned o = 0;
+                if (sy >= 0 && sx >= 0) {
+                    const int ry = rt[1], ymin = rt[2], cnt = rt[3];
+                    const unsigned *in = (const unsigned *)s_h + ymin * oW + sx;
+                    int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+#pragma unroll
+                    for (int q = 0; q < KS; ++q) {
+                        if (q < cnt) {
+                            const unsigned p = in[q * oW];
+                            const int kq = rt[4 + q];
+                            s0 += (int)(p & 0xffu) * kq;
+                            s1 += (int)((p >> 8) & 0xffu) * kq;
+                            s2 += (int)((p >> 16) & 0xffu) * kq;
+                        }
+                    }
+                    const unsigned r = s_lutb[clip8(s0)], g = s_lutb[clip8(s1)], bl = s_lutb[clip8(s2)];
+                    grey += (19595u * r + 38470u * g + 7471u * bl + 0x8000u) >> 16;
+                    // depth: nearest translate -> nearest resize -> nearest rotate (16.16) -> flip
+                    unsigned d = 0;
+                    if (ry >= 0 && rx >= 0) {
+                        int iy, ix;
+                        bool ok = true;
+                        if (mode == 0) {
+                            ix = (pl.fix[2] + ry * pl.fix[1] + cxf) >> 16;
+                            iy = (pl.fix[5] + ry * pl.fix[4] + cyf) >> 16;
+                            ok = ix >= 0 && ix < W && iy >= 0 && iy < H;
+                        } else {
+                            transpose_src(mode, ry, rx, H, W, iy, ix);
+                        }
+                        if (ok) d = __ldg((const unsigned char *)(src + (size_t)iy * W + src_col(ix, W, flip)) + 3);
+                    }
+                    o = r | (g << 8) | (bl << 16) | (d << 24);
                 }
-                if (ok) d = __ldg(src + (size_t)iy * W + src_col(ix, W, flip)).w;
+                ((unsigned *)s_out)[yy * opitch + x] = o;
             }
-            o = make_uchar4(r, g, bl, d);
         }
-        s_out[idx] = o;
     }
     grey = warp_sum_u32(grey);
     if ((tid & 31) == 0 && grey) atomicAdd(&s_grey, grey);
@@ -632,43 +722,41 @@ aug_fused_kernel(const uchar4 *__restrict__ packed, const AugPlan *__restrict__ 
     }
     __syncthreads();
     cluster.sync();  // no CTA may exit while its s_grey can still be read remotely
-    int mean = 0;
-    if (flags & POSE_AUG_COLOR) {
-        const double m = (double)s_total / (double)((long)oW * oH);
-        mean = (int)(m + 0.5);
+    if (tid < 256) {
+        unsigned v = tid;
+        if (color) {
+            const double m = (double)s_total / (double)((long)oW * oH);
+            v = blend8((int)(m + 0.5), tid, pl.contrast, pl.contrast_ex);
+        }
+        s_lutc[tid] = __fdiv_rn((float)v, 255.0f);
     }
+    __syncthreads();
 
-    // ---- phase E: contrast, /255, write fp32 planes (zero padded to PH x PW) ----
+    // ---- phase E: contrast + /255 by table, write fp32 planes (zero padded to PH x PW) ----
     const size_t plane = (size_t)PH * PW;
     float *oimg = image_out + (size_t)b * 3 * plane;
     float *odep = depth_out + (size_t)b * plane;
     const int PW4 = PW >> 2;
-    for (int idx = tid; idx < nband * PW4; idx += kAugThreads) {
-        const int yy = idx / PW4, x4 = idx - yy * PW4, y = y0 + yy;
-        float rr[4], gg[4], bb[4], dd[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int x = x4 * 4 + k;
-            rr[k] = gg[k] = bb[k] = dd[k] = 0.0f;
-            if (x < oW) {
-                const uchar4 p = s_out[yy * oW + x];
-                unsigned r = p.x, g = p.y, bl = p.z;
-                if (flags & POSE_AUG_COLOR) {
-                    r = blend8(mean, (int)r, pl.contrast, pl.contrast_ex);
-                    g = blend8(mean, (int)g, pl.contrast, pl.contrast_ex);
-                    bl = blend8(mean, (int)bl, pl.contrast, pl.contrast_ex);
-                }
-                rr[k] = __fdiv_rn((float)r, 255.0f);
-                gg[k] = __fdiv_rn((float)g, 255.0f);
-                bb[k] = __fdiv_rn((float)bl, 255.0f);
-                dd[k] = __fdiv_rn((float)p.w, 255.0f);
+    {
+        const FastDiv dv(PW4);
+        for (int it = tid; it < nband * PW4; it += kAugThreads) {
+            int yy, x4;
+            dv.divmod(it, yy, x4);
+            const int xb = x4 * 4;
+            float4 R = make_float4(0.f, 0.f, 0.f, 0.f), G = R, Bc = R, D = R;
+            if (xb < oW) {
+                const uint4 p = *(const uint4 *)((const unsigned *)s_out + yy * opitch + xb);
+                R.x = s_lutc[p.x & 0xff]; G.x = s_lutc[(p.x >> 8) & 0xff]; Bc.x = s_lutc[(p.x >> 16) & 0xff]; D.x = s_lutd[p.x >> 24];
+                if (xb + 1 < oW) { R.y = s_lutc[p.y & 0xff]; G.y = s_lutc[(p.y >> 8) & 0xff]; Bc.y = s_lutc[(p.y >> 16) & 0xff]; D.y = s_lutd[p.y >> 24]; }
+                if (xb + 2 < oW) { R.z = s_lutc[p.z & 0xff]; G.z = s_lutc[(p.z >> 8) & 0xff]; Bc.z = s_lutc[(p.z >> 16) & 0xff]; D.z = s_lutd[p.z >> 24]; }
+                if (xb + 3 < oW) { R.w = s_lutc[p.w & 0xff]; G.w = s_lutc[(p.w >> 8) & 0xff]; Bc.w = s_lutc[(p.w >> 16) & 0xff]; D.w = s_lutd[p.w >> 24]; }
             }
+            const size_t off = (size_t)(y0 + yy) * PW + xb;
+            st_stream_f4(oimg + off, R);
+            st_stream_f4(oimg + plane + off, G);
+            st_stream_f4(oimg + 2 * plane + off, Bc);
+            st_stream_f4(odep + off, D);
         }
-        const size_t off = (size_t)y * PW + x4 * 4;
-        st_stream_f4(oimg + off, make_float4(rr[0], rr[1], rr[2], rr[3]));
-        st_stream_f4(oimg + plane + off, make_float4(gg[0], gg[1], gg[2], gg[3]));
-        st_stream_f4(oimg + 2 * plane + off, make_float4(bb[0], bb[1], bb[2], bb[3]));
-        st_stream_f4(odep + off, make_float4(dd[0], dd[1], dd[2], dd[3]));
     }
     // padding rows oH..PH, dealt round-robin to the CTAs of the cluster
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -772,7 +860,11 @@ POSE_API int pose_augment_batch(const void *image, const void *depth, int in_dty
                                         launch->max_ksize, flags, tables);
 
     AugSmemLayout sl = smem_layout(W, *launch);
-    cudaError_t e = cudaFuncSetAttribute(aug_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.bytes);
+    auto kern = launch->max_ksize == 3 ? aug_fused_kernel<3> : launch->max_ksize == 5 ? aug_fused_kernel<5>
+              : launch->max_ksize == 7 ? aug_fused_kernel<7> : aug_fused_kernel<9>;
+    if (launch->max_ksize != 3 && launch->max_ksize != 5 && launch->max_ksize != 7 && launch->max_ksize != 9)
+        return POSE_E_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.bytes);
     if (e != cudaSuccess) return (int)e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -792,8 +884,9 @@ POSE_API int pose_augment_batch(const void *image, const void *depth, int in_dty
     const int *ctables = tables;
     int maxW = launch->max_out_w, maxH = launch->max_out_h, KS = launch->max_ksize, mrr = launch->max_rot_rows,
         mbr = launch->max_band_rows;
-    e = cudaLaunchKernelEx(&cfg, aug_fused_kernel, cpacked, cplan, ctables, kp, joints, cam, image_out, depth_out,
-                           kp_out, joints_out, cam_out, out_hw, H, W, J, PH, PW, maxW, maxH, KS, mrr, mbr,
+    (void)KS;
+    e = cudaLaunchKernelEx(&cfg, kern, cpacked, cplan, ctables, kp, joints, cam, image_out, depth_out,
+                           kp_out, joints_out, cam_out, out_hw, H, W, J, PH, PW, maxW, maxH, mrr, mbr,
                            sl.tab_ints, sl.h_px, flags, err_flag);
     if (e != cudaSuccess) return (int)e;
     return launch_status();

@@ -308,9 +308,15 @@ def run_b200(args):
         achieved = hm_bytes / (kern_ms["heatmap"] * 1e-3) / 1e9
         sizes = a["sizes"].cpu().numpy().astype(np.int64)
         aug_bytes = int(B * (16 * H * W) + 16 * int((sizes[:, 0] * sizes[:, 1]).sum()) + B * J * 20 * 2)
-        cpu_n = 48
+        cpu_n = 256
         cores = os.cpu_count() or 1
-        cpu_v, cpu_dt = cpu_chain_samples_per_s(cpu_n, cores)
+        cpu_chain_samples_per_s(32, cores, inp)  # warm-up (page-in, thread pool)
+        reps, cpu_dt = 0, 0.0
+        while cpu_dt < 4.0 and reps < 64:  # bounded: a few seconds of wall clock on all host threads
+            _v, dt1 = cpu_chain_samples_per_s(cpu_n, cores, inp, params)
+            cpu_dt += dt1
+            reps += 1
+        cpu_v = cpu_n * reps / cpu_dt
         line = {
             "metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -329,7 +335,7 @@ def run_b200(args):
                          "others": {"augment(pack+tables+fused)": {"bytes": aug_bytes, "GB/s": aug_bytes / (kern_ms["augment"] * 1e-3) / 1e9},
                                     "loss": {"bytes": B * 632, "ms": kern_ms["loss"]}, "head": {"ms": kern_ms["head"]}}},
             "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{cpu_n} samples of the same B=256 chain ({cpu_dt:.1f} s), oracle port (C) on all host threads"},
+                             "sample": f"{reps} x the same B=256 batch ({cpu_dt:.1f} s wall, {cpu_dt * cores:.0f} core-s), oracle port (C) on all host threads"},
         }
         print(json.dumps(line))
     if world > 1:
