@@ -15,6 +15,14 @@ LIB_PATH = os.path.join(_HERE, "libpose_b200.so")
 c_int, c_float, c_size_t, c_void_p = C.c_int, C.c_float, C.c_size_t, C.c_void_p
 
 
+class PoseGemmEpilogue(C.Structure):
+    """Mirror of `pose_gemm_epilogue` in include/pose_b200.h."""
+
+    _fields_ = [("bias", C.c_void_p), ("residual", C.c_void_p), ("C", C.c_void_p), ("ldc", C.c_int32),
+                ("ldr", C.c_int32), ("act", C.c_int32), ("out_dtype", C.c_int32), ("out_scale", C.c_float),
+                ("res_scale", C.c_float)]
+
+
 class PoseAugLaunch(C.Structure):
     """Mirror of `pose_aug_launch` in include/pose_b200.h."""
 
@@ -41,6 +49,21 @@ SIGNATURES = {
     "pose_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_void_p]),
     "pose_cast_f32_bf16": (c_int, [c_void_p, c_void_p, C.c_long, c_void_p]),
+    "pose_gemm_bf16_ex": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, C.POINTER(PoseGemmEpilogue),
+                                  c_void_p]),
+    "pose_conv2d_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, C.POINTER(PoseGemmEpilogue), c_void_p]),
+    "pose_cnn_input_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "pose_dwconv3x3_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p]),
+    "pose_pool_sum_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pose_se_gate": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pose_eca_gate": (c_int, [c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "pose_channel_affine_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, C.c_long, c_int, c_void_p, c_void_p]),
+    "pose_coord_pool_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pose_coord_apply_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pose_avgpool2x2_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pose_sums_to_bf16": (c_int, [c_void_p, c_float, C.c_long, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,440 @@
+// cnn_ops.cu -- the bandwidth-bound pieces of CNNPoseEstimation.forward (src/models/cnn.py) in channels-last
+// bf16: fused input assembly (heat-map render + concat + cast), depthwise 3x3 + BN + SiLU (+ squeeze sums),
+// SE / ECA / CoordAttention gates, pooling.  The dense convolutions and Linear layers run on the tcgen05
+// GEMM (gemm_tcgen05.cu); everything here moves each activation through HBM exactly once per op.
+#include "common.cuh"
+
+namespace pose {
+
+__device__ __forceinline__ float act_f(float v, int act) {
+    switch (act) {
+        case 1: return v > 0.f ? v : 0.f;
+        case 2: return v / (1.0f + __expf(-v));
+        case 3: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+        case 4: return 1.0f / (1.0f + __expf(-v));
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ void unpack8(const uint4 &p, float (&f)[8]) {
+    const __nv_bfloat162 *h = (const __nv_bfloat162 *)&p;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 t = __bfloat1622float2(h[q]);
+        f[2 * q] = t.x;
+        f[2 * q + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+    return *(uint4 *)h;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Input assembly: torch.cat([image, depth, heatmaps], 1) (cnn.py:644-648) written directly as the conv1
+// operand: [B, S, S, 32] bf16 = {R, G, B, depth, 17 heat-maps, 11 zero pad}.  The 17 fp32 planes of the
+// reference (4.46 MB/sample at S=256) never exist.  One thread per pixel, 64 B written per pixel.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cnn_input_pack_kernel(const float *__restrict__ image, const float *__restrict__ depth, const float *__restrict__ kp,
+                      int B, int S, int J, float scale, float denom, float rcp, __nv_bfloat16 *__restrict__ out) {
+    __shared__ float s_mu[32][2];
+    __shared__ float s_valid[32];
+    const long npx = (long)S * S;
+    const int blocks_per_img = (int)((npx + 255) / 256);
+    const int b = blockIdx.x / blocks_per_img;
+    const long px = (long)(blockIdx.x % blocks_per_img) * 256 + threadIdx.x;
+    if (threadIdx.x < J) {
+        const float kx = kp[((long)b * J + threadIdx.x) * 2], ky = kp[((long)b * J + threadIdx.x) * 2 + 1];
+        s_mu[threadIdx.x][0] = __fmul_rn(kx, scale);
+        s_mu[threadIdx.x][1] = __fmul_rn(ky, scale);
+        s_valid[threadIdx.x] = (kx > 0.0f && ky > 0.0f) ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    if (px >= npx) return;
+    const int y = (int)(px / S), x = (int)(px - (long)y * S);
+    float v[32];
+    v[0] = __ldg(image + ((long)b * 3 + 0) * npx + px);
+    v[1] = __ldg(image + ((long)b * 3 + 1) * npx + px);
+    v[2] = __ldg(image + ((long)b * 3 + 2) * npx + px);
+    v[3] = __ldg(depth + (long)b * npx + px);
+#pragma unroll
+    for (int j = 0; j < 28; ++j) {
+        float r = 0.0f;
+        if (j < J) {
+            const float dx = __fsub_rn((float)x, s_mu[j][0]), dy = __fsub_rn((float)y, s_mu[j][1]);
+            const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            const float q0 = __fmul_rn(d2, rcp);
+            const float q1 = __fmaf_rn(__fmaf_rn(-q0, denom, d2), rcp, q0);  // RN(d2 / denom)
+            r = (q1 > 104.0f ? 0.0f : expf(-q1)) * s_valid[j];
+        }
+        v[4 + j] = r;
+    }
+    uint4 *dst = (uint4 *)(out + ((long)b * npx + px) * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = v[q * 8 + k];
+        dst[q] = pack8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Depthwise 3x3 conv (pad 1, stride 1 or 2) + folded BatchNorm + activation, NHWC bf16, 8 channels per thread.
+// Optionally accumulates per-(image, channel) sums of the OUTPUT (the squeeze of SE / ECA, cnn.py:22-23,40-41).
+// grid.x = B * chunks (a CTA stays inside one image), grid.y = channel slabs of CG*8 channels.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ Wd, const float *__restrict__ bias,
+                 int H, int W, int C, int stride, int act, __nv_bfloat16 *__restrict__ Y, float *__restrict__ pool,
+                 int Ho, int Wo, int chunks, int CG) {
+    extern __shared__ float s_w[];  // [9][CG*8] weights + [CG*8] bias for this channel slab
+    const int slab_c0 = blockIdx.y * CG * 8;
+    const int slab_c = min(CG * 8, C - slab_c0);
+    for (int i = threadIdx.x; i < 9 * CG * 8; i += 256) {
+        const int t = i / (CG * 8), c = i - t * (CG * 8);
+        s_w[i] = c < slab_c ? __ldg(Wd + (long)t * C + slab_c0 + c) : 0.f;
+    }
+    for (int i = threadIdx.x; i < CG * 8; i += 256) s_w[9 * CG * 8 + i] = i < slab_c ? __ldg(bias + slab_c0 + i) : 0.f;
+    __syncthreads();
+    const int cg_lane = threadIdx.x % CG, plane = threadIdx.x / CG, planes = 256 / CG;
+    const int c0 = slab_c0 + cg_lane * 8;
+    if (c0 >= C || plane >= planes) return;
+    const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    const int npx = Ho * Wo;
+    const int per = (npx + chunks - 1) / chunks;
+    const int p_begin = chunk * per, p_end = min(npx, p_begin + per);
+    const __nv_bfloat16 *xb = X + (long)b * H * W * C;
+    float w[9][8], bs[8], psum[8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[t][k] = s_w[t * CG * 8 + cg_lane * 8 + k];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        bs[k] = s_w[9 * CG * 8 + cg_lane * 8 + k];
+        psum[k] = 0.f;
+    }
+    for (int p = p_begin + plane; p < p_end; p += planes) {
+        const int oy = p / Wo, ox = p - oy * Wo;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = bs[k];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * stride + ky - 1;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox * stride + kx - 1;
+                if (ix < 0 || ix >= W) continue;
+                float f[8];
+                unpack8(__ldg((const uint4 *)(xb + ((long)iy * W + ix) * C + c0)), f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], w[ky * 3 + kx][k], acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            acc[k] = act_f(acc[k], act);
+            psum[k] += acc[k];
+        }
+        *(uint4 *)(Y + ((long)b * npx + p) * C + c0) = pack8(acc);
+    }
+    if (pool != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(pool + (long)b * C + c0 + k, psum[k]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Channel sums over the pixels of each image: X [B, HW, C] bf16 -> S [B, C] fp32 (+=, S zeroed by the caller)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pool_sum_kernel(const __nv_bfloat16 *__restrict__ X, int HW, int C, float *__restrict__ S, int chunks) {
+    const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    const int C8 = C >> 3;
+    const int per = (HW + chunks - 1) / chunks;
+    const int p0 = chunk * per, p1 = min(HW, p0 + per);
+    for (int cg = threadIdx.x; cg < C8; cg += 256) {
+        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int p = p0; p < p1; ++p) {
+            float f[8];
+            unpack8(__ldg((const uint4 *)(X + ((long)b * HW + p) * C + cg * 8)), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] += f[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(S + (long)b * C + cg * 8 + k, s[k]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SE gate (cnn.py:9-26): gate = sigmoid(W2 . act(W1 . mean)); one CTA per image.
+// ECA gate (cnn.py:29-45): gate = sigmoid(conv1d_k(mean)) across channels (zero padded).
+// Both read channel SUMS and scale by inv_hw.  `feat_out` (optional, bf16 [B, C]) receives mean * gate: the
+// global_features tail (ECABlock followed by AdaptiveAvgPool2d(1), cnn.py:612-613) needs nothing else.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+se_gate_kernel(const float *__restrict__ pool, float inv_hw, const float *__restrict__ W1, const float *__restrict__ W2,
+               int C, int Cr, int act, float *__restrict__ gate) {
+    extern __shared__ float sm[];  // mean[C] + hidden[Cr]
+    float *mean = sm, *hid = sm + C;
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = threadIdx.x; c < C; c += 256) mean[c] = pool[(long)b * C + c] * inv_hw;
+    __syncthreads();
+    for (int r = warp; r < Cr; r += 8) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(W1 + (long)r * C + c), mean[c], s);
+        s = warp_sum(s);
+        if (lane == 0) hid[r] = act_f(s, act);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float s = 0.f;
+        for (int r = 0; r < Cr; ++r) s = fmaf(__ldg(W2 + (long)c * Cr + r), hid[r], s);
+        gate[(long)b * C + c] = 1.0f / (1.0f + __expf(-s));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+eca_gate_kernel(const float *__restrict__ pool, float inv_hw, const float *__restrict__ w, int k, int C,
+                float *__restrict__ gate, __nv_bfloat16 *__restrict__ feat_out) {
+    const int b = blockIdx.x;
+    const int half = (k - 1) / 2;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float s = 0.f;
+        for (int t = 0; t < k; ++t) {
+            const int cc = c + t - half;
+            if (cc >= 0 && cc < C) s = fmaf(__ldg(w + t), pool[(long)b * C + cc] * inv_hw, s);
+        }
+        const float g = 1.0f / (1.0f + __expf(-s));
+        if (gate != nullptr) gate[(long)b * C + c] = g;
+        if (feat_out != nullptr) feat_out[(long)b * C + c] = __float2bfloat16_rn(pool[(long)b * C + c] * inv_hw * g);
+    }
+}
+
+// X[b, p, c] = X[b, p, c] * mul[b, c] + add[b, c]   (either vector may be null); in place or to Y
+__global__ void __launch_bounds__(256)
+channel_affine_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ mul, const __nv_bfloat16 *__restrict__ add,
+                      long HW, int C, long total8, __nv_bfloat16 *__restrict__ Y) {
+    const int C8 = C >> 3;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        const long b = (i / C8) / HW;
+        float f[8];
+        unpack8(__ldg((const uint4 *)X + i), f);
+        if (mul != nullptr) {
+            const float4 m0 = __ldg((const float4 *)(mul + b * C + cg * 8)), m1 = __ldg((const float4 *)(mul + b * C + cg * 8) + 1);
+            f[0] *= m0.x; f[1] *= m0.y; f[2] *= m0.z; f[3] *= m0.w;
+            f[4] *= m1.x; f[5] *= m1.y; f[6] *= m1.z; f[7] *= m1.w;
+        }
+        if (add != nullptr) {
+            float a[8];
+            unpack8(__ldg((const uint4 *)(add + b * C + cg * 8)), a);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] += a[k];
+        }
+        ((uint4 *)Y)[i] = pack8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CoordAttention (cnn.py:48-98): directional means, then out = x * a_h * a_w.
+//   coord_pool:  X [B,H,W,C] -> P [B, H+W, C] bf16: rows 0..H-1 = mean over w, rows H.. = mean over h
+//   coord_apply: G [B, H+W, 2C] bf16 sigmoid gates (cols 0..C-1 from conv_h, C..2C-1 from conv_w)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+coord_pool_kernel(const __nv_bfloat16 *__restrict__ X, int H, int W, int C, __nv_bfloat16 *__restrict__ P) {
+    const int b = blockIdx.x, C8 = C >> 3;
+    const int n_rows = H + W;
+    for (int i = threadIdx.x; i < n_rows * C8; i += 256) {
+        const int r = i / C8, cg = i - r * C8;
+        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const bool is_h = r < H;
+        const int n = is_h ? W : H;
+        for (int q = 0; q < n; ++q) {
+            const int y = is_h ? r : q, x = is_h ? q : r - H;
+            float f[8];
+            unpack8(__ldg((const uint4 *)(X + (((long)b * H + y) * W + x) * C + cg * 8)), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] += f[k];
+        }
+        const float inv = 1.0f / (float)n;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] *= inv;
+        *(uint4 *)(P + ((long)b * n_rows + r) * C + cg * 8) = pack8(s);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+coord_apply_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__restrict__ G, int H, int W, int C,
+                   long total8, __nv_bfloat16 *__restrict__ Y) {
+    const int C8 = C >> 3;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        long p = i / C8;
+        const int x = (int)(p % W);
+        p /= W;
+        const int y = (int)(p % H);
+        const long b = p / H;
+        float f[8], gh[8], gw[8];
+        unpack8(__ldg((const uint4 *)X + i), f);
+        unpack8(__ldg((const uint4 *)(G + ((b * (H + W) + y) * 2L * C) + cg * 8)), gh);
+        unpack8(__ldg((const uint4 *)(G + ((b * (H + W) + H + x) * 2L * C) + C + cg * 8)), gw);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = f[k] * gh[k] * gw[k];
+        ((uint4 *)Y)[i] = pack8(f);
+    }
+}
+
+// 2x2 average pooling (AdaptiveAvgPool2d(8) on a 16x16 map, cnn.py:602), NHWC bf16
+__global__ void __launch_bounds__(256)
+avgpool2x2_kernel(const __nv_bfloat16 *__restrict__ X, int H, int W, int C, long total8, __nv_bfloat16 *__restrict__ Y) {
+    const int C8 = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        long p = i / C8;
+        const int x = (int)(p % Wo);
+        p /= Wo;
+        const int y = (int)(p % Ho);
+        const long b = p / Ho;
+        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                float f[8];
+                unpack8(__ldg((const uint4 *)(X + (((b * H + 2 * y + dy) * W) + 2 * x + dx) * C + cg * 8)), f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s[k] += f[k];
+            }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] *= 0.25f;
+        ((uint4 *)Y)[i] = pack8(s);
+    }
+}
+
+// S [B, C] fp32 sums -> bf16 means (operand of the WASP global-branch GEMM)
+__global__ void __launch_bounds__(256)
+sums_to_bf16_kernel(const float *__restrict__ S, float scale, long n, __nv_bfloat16 *__restrict__ out) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        out[i] = __float2bfloat16_rn(S[i] * scale);
+}
+
+static int grid_for(long items, int per_block = 256, int max_waves = 16) {
+    long blocks = (items + per_block - 1) / per_block;
+    long cap = (long)kNumSMs * max_waves;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace pose
+
+using namespace pose;
+
+POSE_API int pose_cnn_input_pack(const float *image, const float *depth, const float *kp, int B, int S, int J,
+                                 float sigma, void *out, pose_stream_t stream) {
+    if (!image || !depth || !kp || !out) return POSE_E_NULL;
+    if (B <= 0 || S <= 0 || J <= 0 || J > 28 || !(sigma > 0.f)) return POSE_E_SHAPE;
+    if ((uintptr_t)out % 16) return POSE_E_ALIGN;
+    const float denom = (float)(2.0 * (double)sigma * (double)sigma);
+    const long npx = (long)S * S;
+    const int blocks_per_img = (int)((npx + 255) / 256);
+    cnn_input_pack_kernel<<<B * blocks_per_img, 256, 0, (cudaStream_t)stream>>>(
+        image, depth, kp, B, S, J, (float)(S - 1), denom, (float)(1.0 / (double)denom), (__nv_bfloat16 *)out);
+    return launch_status();
+}
+
+POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, const float *Wd, const float *bias, int stride,
+                                 int act, void *Y, float *pool_sum, pose_stream_t stream) {
+    if (!X || !Wd || !bias || !Y) return POSE_E_NULL;
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 || (stride != 1 && stride != 2)) return POSE_E_SHAPE;
+    if ((uintptr_t)X % 16 || (uintptr_t)Y % 16) return POSE_E_ALIGN;
+    const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+    int CG = C / 8;
+    if (CG > 32) CG = 32;
+    while (256 % CG) --CG;  // channel groups per CTA must divide the CTA
+    const int slabs = (C / 8 + CG - 1) / CG;
+    // enough CTAs to fill the chip, but every CTA stays inside one image (squeeze sums are per image)
+    int chunks = (kNumSMs * 8 + B * slabs - 1) / (B * slabs);
+    const int npx = Ho * Wo, planes = 256 / CG;
+    if (chunks > (npx + planes - 1) / planes) chunks = (npx + planes - 1) / planes;
+    if (chunks < 1) chunks = 1;
+    const size_t smem = (size_t)(10 * CG * 8) * sizeof(float);
+    dim3 grid(B * chunks, slabs);
+    dwconv3x3_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, Wd, bias, H, W, C, stride, act,
+                                                               (__nv_bfloat16 *)Y, pool_sum, Ho, Wo, chunks, CG);
+    return launch_status();
+}
+
+POSE_API int pose_pool_sum_bf16(const void *X, int B, int HW, int C, float *sums, pose_stream_t stream) {
+    if (!X || !sums) return POSE_E_NULL;
+    if (B <= 0 || HW <= 0 || C <= 0 || C % 8) return POSE_E_SHAPE;
+    int chunks = (kNumSMs * 4 + B - 1) / B;
+    if (chunks > HW) chunks = HW;
+    if (chunks < 1) chunks = 1;
+    pool_sum_kernel<<<B * chunks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, HW, C, sums, chunks);
+    return launch_status();
+}
+
+POSE_API int pose_se_gate(const float *pool_sum, float inv_hw, const float *W1, const float *W2, int B, int C, int Cr,
+                          int act, float *gate, pose_stream_t stream) {
+    if (!pool_sum || !W1 || !W2 || !gate) return POSE_E_NULL;
+    if (B <= 0 || C <= 0 || Cr <= 0) return POSE_E_SHAPE;
+    se_gate_kernel<<<B, 256, (size_t)(C + Cr) * sizeof(float), (cudaStream_t)stream>>>(pool_sum, inv_hw, W1, W2, C, Cr, act, gate);
+    return launch_status();
+}
+
+POSE_API int pose_eca_gate(const float *pool_sum, float inv_hw, const float *w, int k, int B, int C, float *gate,
+                           void *feat_out, pose_stream_t stream) {
+    if (!pool_sum || !w || (!gate && !feat_out)) return POSE_E_NULL;
+    if (B <= 0 || C <= 0 || k <= 0 || !(k & 1)) return POSE_E_SHAPE;
+    eca_gate_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(pool_sum, inv_hw, w, k, C, gate, (__nv_bfloat16 *)feat_out);
+    return launch_status();
+}
+
+POSE_API int pose_channel_affine_bf16(const void *X, const float *mul, const void *add, int B, long HW, int C, void *Y,
+                                      pose_stream_t stream) {
+    if (!X || !Y) return POSE_E_NULL;
+    if (B <= 0 || HW <= 0 || C <= 0 || C % 8) return POSE_E_SHAPE;
+    if ((uintptr_t)X % 16 || (uintptr_t)Y % 16 || (mul && (uintptr_t)mul % 16) || (add && (uintptr_t)add % 16)) return POSE_E_ALIGN;
+    const long total8 = (long)B * HW * (C / 8);
+    channel_affine_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, mul, (const __nv_bfloat16 *)add,
+                                                                             HW, C, total8, (__nv_bfloat16 *)Y);
+    return launch_status();
+}
+
+POSE_API int pose_coord_pool_bf16(const void *X, int B, int H, int W, int C, void *P, pose_stream_t stream) {
+    if (!X || !P) return POSE_E_NULL;
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8) return POSE_E_SHAPE;
+    coord_pool_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, H, W, C, (__nv_bfloat16 *)P);
+    return launch_status();
+}
+
+POSE_API int pose_coord_apply_bf16(const void *X, const void *G, int B, int H, int W, int C, void *Y, pose_stream_t stream) {
+    if (!X || !G || !Y) return POSE_E_NULL;
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8) return POSE_E_SHAPE;
+    const long total8 = (long)B * H * W * (C / 8);
+    coord_apply_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, (const __nv_bfloat16 *)G, H, W,
+                                                                          C, total8, (__nv_bfloat16 *)Y);
+    return launch_status();
+}
+
+POSE_API int pose_avgpool2x2_bf16(const void *X, int B, int H, int W, int C, void *Y, pose_stream_t stream) {
+    if (!X || !Y) return POSE_E_NULL;
+    if (B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C <= 0 || C % 8) return POSE_E_SHAPE;
+    const long total8 = (long)B * (H / 2) * (W / 2) * (C / 8);
+    avgpool2x2_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, H, W, C, total8,
+                                                                         (__nv_bfloat16 *)Y);
+    return launch_status();
+}
+
+POSE_API int pose_sums_to_bf16(const float *sums, float scale, long n, void *out, pose_stream_t stream) {
+    if (!sums || !out) return POSE_E_NULL;
+    if (n <= 0) return POSE_E_SHAPE;
+    sums_to_bf16_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(sums, scale, n, (__nv_bfloat16 *)out);
+    return launch_status();
+}

@@ -15,6 +15,12 @@
 //            times per stage; tcgen05.commit releases the stage (`empty`) and finally signals `acc_full`
 //   warps 2-5  epilogue: tcgen05.ld the fp32 accumulator (each warp owns its 32-lane TMEM quarter),
 //            bias + activation, convert, store
+// The same kernel is the implicit-GEMM convolution (MODE 1): the A tile of a k-block is one filter tap
+// x one channel chunk, fetched by a 4-D tiled TMA box over the NHWC activation (box = channels x TW x TH
+// output-pixel patch, element strides = conv stride, start = tap offset - padding; out-of-bounds
+// elements are zero-filled by the TMA unit, which is exactly the conv padding).  Weights are KRSC
+// ([Cout][kh][kw][Cin]) so the B operand stays a plain K-major 2-D tile.  Dense 3x3 / 5x5 / dilated /
+// strided convolutions of src/models/cnn.py:122-131 never materialise an im2col matrix.
 // All mbarrier waits are bounded (trap instead of hanging the GPU if a descriptor is wrong).
 #include <cuda.h>
 #include <mutex>
@@ -56,6 +62,13 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -95,13 +108,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
 //   [0,14) start >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) | [32,46) SBO >> 4 (8 rows x 128 B)
 //   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+//   rows of ROWB = 128 B use SWIZZLE_128B (layout 2, SBO 1024 B); rows of 64 B use SWIZZLE_64B (layout 4, SBO 512 B)
+template <int ROWB>
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((8 * ROWB) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;
     return d;
 }
 // cute::UMMA::InstrDescriptor for kind::f16: D = F32, A = B = BF16, both K-major
@@ -114,26 +129,45 @@ __device__ __forceinline__ float apply_act(float v, int act) {
         case 1: return v > 0.f ? v : 0.f;                                   // relu
         case 2: return v / (1.0f + __expf(-v));                             // silu
         case 3: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));  // gelu (erf form, nn.GELU default)
+        case 4: return 1.0f / (1.0f + __expf(-v));                          // sigmoid
         default: return v;
     }
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-template <int BN, int kStages>
+struct Epilogue {
+    const float *bias;               // [N] fp32 or null   (BatchNorm folded into weights leaves only this)
+    const __nv_bfloat16 *residual;   // [M, ldr] bf16 or null
+    void *C;
+    int ldc, ldr, act, out_bf16;
+    float out_scale, res_scale;      // C = act(acc + bias) * out_scale + residual * res_scale
+};
+
+struct ConvGeom {          // MODE 1 only
+    int Ho, Wo;            // output height / width
+    int TH, TW, TN;        // output patch of one M tile: TN images x TH x TW pixels (= 128), Ho % TH == 0, Wo % TW == 0
+    int Nimg;
+    int KW, taps;          // filter width, KH * KW
+    int stride, dil, pad;
+    int cchunks;           // Cin_pad / BKC
+};
+
+template <int BN, int kStages, int BKC>
 struct GemmSmem {
-    static constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
+    static constexpr int kABytes = BM * BKC * 2, kBBytes = BN * BKC * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarrierBytes = 256;
     static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
+    static_assert(kStageBytes % 1024 == 0, "stage bases must stay 1024 B aligned");
 };
 
-template <int BN, int kStages>
+template <int BN, int kStages, int BKC, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N,
-                    int K, const float *__restrict__ bias, int act, void *__restrict__ C, int ldc, int out_bf16) {
-    using S = GemmSmem<BN, kStages>;
+                    int K, const Epilogue ep, const ConvGeom cg) {
+    using S = GemmSmem<BN, kStages, BKC>;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B: 1024 B
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);  // swizzle atoms: 1024 B
     unsigned char *bars = smem + kStages * S::kStageBytes;
     uint64_t *full = (uint64_t *)bars;
     uint64_t *empty = full + kStages;
@@ -141,9 +175,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t *tmem_slot = (uint32_t *)(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int num_kb = (K + BK - 1) / BK;
+    const int n0 = blockIdx.x * BN;
+    const int num_kb = (K + BKC - 1) / BKC;
     constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;  // power of two >= 32
+
+    // M tile -> rows of C.  MODE 0: 128 consecutive rows.  MODE 1: a TH x TW patch of output pixels of one image.
+    int m0 = blockIdx.y * BM;
+    int img = 0, oh0 = 0, ow0 = 0;
+    if (MODE == 1) {
+        const int tiles_w = cg.Wo / cg.TW, tiles_h = cg.Ho / cg.TH;
+        int t = blockIdx.y;
+        const int tw = t % tiles_w;
+        t /= tiles_w;
+        const int th = t % tiles_h;
+        img = (t / tiles_h) * cg.TN;
+        oh0 = th * cg.TH;
+        ow0 = tw * cg.TW;
+    }
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -175,8 +223,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 mbar_wait(empty + s, ph ^ 1);
                 unsigned char *sa = smem + s * S::kStageBytes, *sb = sa + S::kABytes;
                 mbar_expect_tx(full + s, S::kStageBytes);
-                tma_load_2d(sa, &map_a, full + s, kb * BK, m0);
-                tma_load_2d(sb, &map_w, full + s, kb * BK, n0);
+                if (MODE == 0) {
+                    tma_load_2d(sa, &map_a, full + s, kb * BKC, m0);
+                } else {
+                    const int tap = kb / cg.cchunks, cc = kb - tap * cg.cchunks;
+                    const int kh = tap / cg.KW, kw = tap - kh * cg.KW;
+                    tma_load_4d(sa, &map_a, full + s, cc * BKC, ow0 * cg.stride + kw * cg.dil - cg.pad,
+                                oh0 * cg.stride + kh * cg.dil - cg.pad, img);
+                }
+                tma_load_2d(sb, &map_w, full + s, kb * BKC, n0);
             }
         }
     } else if (warp == 1) {
@@ -189,10 +244,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t sa = smem_u32(smem + s * S::kStageBytes), sb = sa + S::kABytes;
-                const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sb);
+                const uint64_t da = umma_desc_k<BKC * 2>(sa), db = umma_desc_k<BKC * 2>(sb);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    // advancing K by 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
+                for (int k = 0; k < BKC / UMMA_K; ++k) {
+                    // advancing K by 16 bf16 = 32 B inside the swizzled row: +2 in the (>>4) address field
                     tc_mma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
                 }
                 tc_commit(empty + s);                      // frees the smem stage when these MMAs retire
@@ -205,24 +260,54 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int quarter = warp & 3;
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        const int row = m0 + quarter * 32 + lane;
-        const bool row_ok = row < M;
+        const int r = quarter * 32 + lane;
+        long row;
+        bool row_ok;
+        if (MODE == 0) {
+            row = (long)m0 + r;
+            row_ok = row < M;
+        } else {
+            const int per_img = cg.TH * cg.TW;
+            const int dn = r / per_img, rr = r - dn * per_img;
+            const int dh = rr / cg.TW, dw = rr - dh * cg.TW;
+            row = ((long)(img + dn) * cg.Ho + oh0 + dh) * cg.Wo + ow0 + dw;
+            row_ok = img + dn < cg.Nimg;
+        }
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), acc);
             const int col0 = n0 + c * 32;
             if (!row_ok || col0 >= N) continue;
+            const bool full_chunk = col0 + 32 <= N;
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                float x = __uint_as_float(r[j]);
-                if (bias != nullptr && col0 + j < N) x += __ldg(bias + col0 + j);
-                v[j] = apply_act(x, act);
+                float x = __uint_as_float(acc[j]);
+                if (ep.bias != nullptr && (full_chunk || col0 + j < N)) x += __ldg(ep.bias + col0 + j);
+                v[j] = apply_act(x, ep.act) * ep.out_scale;
             }
-            if (out_bf16) {
-                __nv_bfloat16 *dst = (__nv_bfloat16 *)C + (size_t)row * ldc + col0;
-                if (col0 + 32 <= N && (((uintptr_t)dst) & 15) == 0) {
+            if (ep.residual != nullptr) {
+                const __nv_bfloat16 *rs = ep.residual + row * ep.ldr + col0;
+                if (full_chunk && (((uintptr_t)rs) & 15) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        const uint4 pk = __ldg((const uint4 *)(rs + j));
+                        const __nv_bfloat162 *h = (const __nv_bfloat162 *)&pk;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 f = __bfloat1622float2(h[q]);
+                            v[j + 2 * q] += f.x * ep.res_scale;
+                            v[j + 2 * q + 1] += f.y * ep.res_scale;
+                        }
+                    }
+                } else {
+                    for (int j = 0; j < 32 && col0 + j < N; ++j) v[j] += __bfloat162float(rs[j]) * ep.res_scale;
+                }
+            }
+            if (ep.out_bf16) {
+                __nv_bfloat16 *dst = (__nv_bfloat16 *)ep.C + row * ep.ldc + col0;
+                if (full_chunk && (((uintptr_t)dst) & 15) == 0) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
@@ -234,8 +319,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     for (int j = 0; j < 32 && col0 + j < N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
                 }
             } else {
-                float *dst = (float *)C + (size_t)row * ldc + col0;
-                if (col0 + 32 <= N && (((uintptr_t)dst) & 15) == 0) {
+                float *dst = (float *)ep.C + row * ep.ldc + col0;
+                if (full_chunk && (((uintptr_t)dst) & 15) == 0) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) *(float4 *)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 } else {
@@ -282,56 +367,139 @@ static EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] tensor, box = box_rows x 64 columns, 128 B swizzle, OOB reads give zeros
-static int make_map_bf16(CUtensorMap *map, const void *ptr, long rows, long cols, long ld_elems, int box_rows) {
+// 2-D bf16 row-major [rows, cols] tensor, box = box_rows x bkc columns, swizzle = row bytes, OOB reads give zeros
+static int make_map_2d(CUtensorMap *map, const void *ptr, long rows, long cols, long ld_elems, int box_rows, int bkc) {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) return POSE_E_UNSUPPORTED;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bkc, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, bkc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? POSE_OK : POSE_E_SHAPE;
 }
 
-template <int BN, int kStages>
-static int launch_gemm(const void *A, int lda, const void *W, int ldw, const float *bias, void *C, int ldc, int M,
-                       int N, int K, int act, int out_bf16, cudaStream_t s) {
-    using S = GemmSmem<BN, kStages>;
-    CUtensorMap ma, mw;
-    int e = make_map_bf16(&ma, A, M, K, lda, BM);
-    if (e) return e;
-    e = make_map_bf16(&mw, W, N, K, ldw, BN);
-    if (e) return e;
-    auto kern = gemm_bf16_tn_kernel<BN, kStages>;
+// 4-D NHWC bf16 activation [N, H, W, C]; box = bkc channels x (TW, TH) output pixels traversed with the conv stride
+static int make_map_nhwc(CUtensorMap *map, const void *ptr, int Nimg, int H, int W, int C, int bkc, int TW, int TH,
+                         int TN, int stride) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return POSE_E_UNSUPPORTED;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)bkc, (cuuint32_t)(TW * stride), (cuuint32_t)(TH * stride), (cuuint32_t)TN};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    if (box[1] > 256 || box[2] > 256) return POSE_E_UNSUPPORTED;
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, bkc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? POSE_OK : POSE_E_SHAPE;
+}
+
+template <int BN, int kStages, int BKC, int MODE>
+static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int N, int K, const Epilogue &ep,
+                       const ConvGeom &cg, int m_tiles, cudaStream_t s) {
+    using S = GemmSmem<BN, kStages, BKC>;
+    auto kern = gemm_bf16_tn_kernel<BN, kStages, BKC, MODE>;
     static bool configured = false;
     if (!configured) {
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
         if (ce != cudaSuccess) return (int)ce;
         configured = true;
     }
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-    kern<<<grid, kGemmThreads, S::kTotal, s>>>(ma, mw, M, N, K, bias, act, C, ldc, out_bf16);
+    dim3 grid((N + BN - 1) / BN, m_tiles);
+    kern<<<grid, kGemmThreads, S::kTotal, s>>>(ma, mw, M, N, K, ep, cg);
     return launch_status();
+}
+
+template <int BKC, int MODE>
+static int dispatch_bn(const CUtensorMap &ma, const void *W, int ldw, int M, int N, int K, const Epilogue &ep,
+                       const ConvGeom &cg, int m_tiles, cudaStream_t s) {
+    CUtensorMap mw;
+    const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+    int e = make_map_2d(&mw, W, N, K, ldw, bn, BKC);
+    if (e) return e;
+    if (bn == 32) return launch_gemm<32, 8, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
+    if (bn == 64) return launch_gemm<64, 8, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
+    return launch_gemm<128, 6, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
+}
+
+static int check_epilogue(const pose_gemm_epilogue *e, int N, Epilogue &ep) {
+    if (!e || !e->C) return POSE_E_NULL;
+    if (e->ldc < N || (e->residual && e->ldr < N)) return POSE_E_SHAPE;
+    if (e->act < 0 || e->act > 4 || (e->out_dtype != 0 && e->out_dtype != 1)) return POSE_E_UNSUPPORTED;
+    ep.bias = e->bias;
+    ep.residual = (const __nv_bfloat16 *)e->residual;
+    ep.C = e->C;
+    ep.ldc = e->ldc;
+    ep.ldr = e->ldr;
+    ep.act = e->act;
+    ep.out_bf16 = e->out_dtype;
+    ep.out_scale = e->out_scale;
+    ep.res_scale = e->res_scale;
+    return POSE_OK;
 }
 
 }  // namespace pose
 
-POSE_API int pose_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, void *C, int ldc,
-                            int M, int N, int K, int act, int out_dtype, pose_stream_t stream) {
+POSE_API int pose_gemm_bf16_ex(const void *A, int lda, const void *W, int ldw, int M, int N, int K,
+                               const pose_gemm_epilogue *epilogue, pose_stream_t stream) {
     using namespace pose;
-    if (!A || !W || !C) return POSE_E_NULL;
+    if (!A || !W) return POSE_E_NULL;
     if (M <= 0 || N <= 0 || K <= 0) return POSE_E_SHAPE;
-    if (lda < K || ldw < K || ldc < N) return POSE_E_SHAPE;
+    if (lda < K || ldw < K) return POSE_E_SHAPE;
     if (lda % 8 || ldw % 8) return POSE_E_SHAPE;  // TMA: row pitch must be a multiple of 16 bytes
     if ((uintptr_t)A % 16 || (uintptr_t)W % 16) return POSE_E_ALIGN;
-    if (act < 0 || act > 3 || (out_dtype != 0 && out_dtype != 1)) return POSE_E_UNSUPPORTED;
+    Epilogue ep;
+    int e = check_epilogue(epilogue, N, ep);
+    if (e) return e;
+    CUtensorMap ma;
+    e = make_map_2d(&ma, A, M, K, lda, BM, 64);
+    if (e) return e;
+    ConvGeom cg = {};
+    return dispatch_bn<64, 0>(ma, W, ldw, M, N, K, ep, cg, (M + BM - 1) / BM, (cudaStream_t)stream);
+}
+
+POSE_API int pose_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, void *C, int ldc,
+                            int M, int N, int K, int act, int out_dtype, pose_stream_t stream) {
+    pose_gemm_epilogue e = {bias, nullptr, C, ldc, 0, act, out_dtype, 1.0f, 0.0f};
+    return pose_gemm_bf16_ex(A, lda, W, ldw, M, N, K, &e, stream);
+}
+
+POSE_API int pose_conv2d_bf16(const void *X, int Nimg, int H, int Wd, int Cin, const void *Wt, int Cout, int KH, int KW,
+                              int stride, int dil, int pad, const pose_gemm_epilogue *epilogue, pose_stream_t stream) {
+    using namespace pose;
+    if (!X || !Wt) return POSE_E_NULL;
+    if (Nimg <= 0 || H <= 0 || Wd <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || stride <= 0 || dil <= 0 || pad < 0)
+        return POSE_E_SHAPE;
+    if ((uintptr_t)X % 16 || (uintptr_t)Wt % 16) return POSE_E_ALIGN;
+    const int bkc = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 0);
+    if (!bkc) return POSE_E_UNSUPPORTED;  // channels-last activations are padded to a multiple of 32 channels
+    const int Ho = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, Wo = (Wd + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+    // output patch per M tile: TW = largest power of two <= 128 dividing Wo, then rows, then whole images
+    int TW = 128;
+    while (TW > 1 && (Wo % TW)) TW >>= 1;
+    int TH = BM / TW, TN = 1;
+    if (TH > Ho) {
+        if ((TH % Ho) || TW != Wo) return POSE_E_UNSUPPORTED;
+        TN = TH / Ho;
+        TH = Ho;
+    }
+    if (TW * TH * TN != BM || Ho % TH || Wo % TW) return POSE_E_UNSUPPORTED;
+    const int K = KH * KW * Cin, N = Cout;
+    Epilogue ep;
+    int e = check_epilogue(epilogue, N, ep);
+    if (e) return e;
+    CUtensorMap ma;
+    e = make_map_nhwc(&ma, X, Nimg, H, Wd, Cin, bkc, TW, TH, TN, stride);
+    if (e) return e;
+    ConvGeom cg = {Ho, Wo, TH, TW, TN, Nimg, KW, KH * KW, stride, dil, pad, Cin / bkc};
+    const int m_tiles = ((Nimg + TN - 1) / TN) * (Ho / TH) * (Wo / TW);
+    const int M = Nimg * Ho * Wo;
     cudaStream_t s = (cudaStream_t)stream;
-    if (N <= 32) return launch_gemm<32, 8>(A, lda, W, ldw, bias, C, ldc, M, N, K, act, out_dtype, s);
-    if (N <= 64) return launch_gemm<64, 8>(A, lda, W, ldw, bias, C, ldc, M, N, K, act, out_dtype, s);
-    return launch_gemm<128, 6>(A, lda, W, ldw, bias, C, ldc, M, N, K, act, out_dtype, s);
+    if (bkc == 64) return dispatch_bn<64, 1>(ma, Wt, K, M, N, K, ep, cg, m_tiles, s);
+    return dispatch_bn<32, 1>(ma, Wt, K, M, N, K, ep, cg, m_tiles, s);
 }
 
 POSE_API int pose_cast_f32_bf16(const float *in, void *out, long n, pose_stream_t stream) {

@@ -124,6 +124,65 @@ int pose_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *
                    int N, int K, int act, int out_dtype, pose_stream_t stream);
 int pose_cast_f32_bf16(const float *in, void *out, long n, pose_stream_t stream);
 
+/* Extended epilogue shared by the GEMM and the implicit-GEMM convolution:
+ *    C = act(acc + bias) * out_scale + residual * res_scale
+ * bias [N] fp32 or NULL (a folded BatchNorm leaves only this), residual [M, ldr] bf16 or NULL, C [M, ldc] fp32
+ * (out_dtype 0) or bf16 (1).  Writing with ldc > N into a column slice implements torch.cat along channels.
+ * act: 0 none, 1 relu, 2 silu, 3 gelu(erf), 4 sigmoid. */
+typedef struct pose_gemm_epilogue {
+    const float *bias;
+    const void *residual;
+    void *C;
+    int32_t ldc, ldr, act, out_dtype;
+    float out_scale, res_scale;
+} pose_gemm_epilogue;
+
+int pose_gemm_bf16_ex(const void *A, int lda, const void *W, int ldw, int M, int N, int K,
+                      const pose_gemm_epilogue *epilogue, pose_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * D. dense nn.Conv2d as implicit GEMM on tcgen05      reference: ConvBnAct, src/models/cnn.py:101-139
+ *    X  [Nimg, H, W, Cin] bf16 channels-last (Cin a multiple of 32; 21-channel input padded to 32)
+ *    Wt [Cout, KH, KW, Cin] bf16 (KRSC), square stride / dilation, zero padding `pad`
+ *    output rows are the Nimg*Ho*Wo output pixels in NHWC order, columns the Cout channels (epilogue).
+ *    Ho, Wo must tile into 128-pixel patches (TW = largest power of two dividing Wo, TH = 128 / TW).
+ * ------------------------------------------------------------------------------------------- */
+int pose_conv2d_bf16(const void *X, int Nimg, int H, int W, int Cin, const void *Wt, int Cout, int KH, int KW,
+                     int stride, int dil, int pad, const pose_gemm_epilogue *epilogue, pose_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * D. bandwidth-bound pieces of CNNPoseEstimation.forward, channels-last bf16
+ *    (reference: src/models/cnn.py; each activation crosses HBM once per call)
+ *  pose_cnn_input_pack   cat([image, depth, heatmaps], 1) (cnn.py:644-648) written as the conv1 operand
+ *                        [B,S,S,32] bf16 = {R,G,B,depth, J heat-maps, zero pad}; heat-maps rendered in flight
+ *  pose_dwconv3x3_bf16   depthwise 3x3, pad 1, stride 1|2 + per-channel bias (folded BN) + act; Wd [3,3,C]
+ *                        fp32; pool_sum [B,C] fp32 (optional, += sums of the OUTPUT: SE/ECA squeeze)
+ *  pose_pool_sum_bf16    sums [B,C] fp32 += sum over pixels of X [B,HW,C]
+ *  pose_se_gate          SEBlock (cnn.py:9-26): gate = sigmoid(W2 . act(W1 . (pool_sum*inv_hw)))
+ *  pose_eca_gate         ECABlock (cnn.py:29-45): gate = sigmoid(conv1d_k(mean)); feat_out (optional,
+ *                        bf16 [B,C]) = mean * gate (= ECA followed by global average pooling, cnn.py:612-613)
+ *  pose_channel_affine_bf16  Y[b,p,c] = X[b,p,c] * mul[b,c] (fp32, optional) + add[b,c] (bf16, optional)
+ *  pose_coord_pool_bf16 / pose_coord_apply_bf16   CoordAttention (cnn.py:48-98) directional means
+ *                        P [B,H+W,C] and out = x * G[b,h,c] * G[b,H+w,C+c] with G [B,H+W,2C] bf16
+ *  pose_avgpool2x2_bf16  AdaptiveAvgPool2d(8) on a 16x16 map (cnn.py:602)
+ *  pose_sums_to_bf16     out = bf16(sums * scale)
+ * ------------------------------------------------------------------------------------------- */
+int pose_cnn_input_pack(const float *image, const float *depth, const float *kp, int B, int S, int J, float sigma,
+                        void *out, pose_stream_t stream);
+int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, const float *Wd, const float *bias, int stride,
+                        int act, void *Y, float *pool_sum, pose_stream_t stream);
+int pose_pool_sum_bf16(const void *X, int B, int HW, int C, float *sums, pose_stream_t stream);
+int pose_se_gate(const float *pool_sum, float inv_hw, const float *W1, const float *W2, int B, int C, int Cr, int act,
+                 float *gate, pose_stream_t stream);
+int pose_eca_gate(const float *pool_sum, float inv_hw, const float *w, int k, int B, int C, float *gate, void *feat_out,
+                  pose_stream_t stream);
+int pose_channel_affine_bf16(const void *X, const float *mul, const void *add, int B, long HW, int C, void *Y,
+                             pose_stream_t stream);
+int pose_coord_pool_bf16(const void *X, int B, int H, int W, int C, void *P, pose_stream_t stream);
+int pose_coord_apply_bf16(const void *X, const void *G, int B, int H, int W, int C, void *Y, pose_stream_t stream);
+int pose_avgpool2x2_bf16(const void *X, int B, int H, int W, int C, void *Y, pose_stream_t stream);
+int pose_sums_to_bf16(const float *sums, float scale, long n, void *out, pose_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

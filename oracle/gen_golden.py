@@ -172,11 +172,46 @@ def gen_config():
         json.dump(out, f, indent=1, sort_keys=True)
 
 
+SMALL_CNN = dict(image_size=(64, 64), heatmap_size=64, heatmap_sigma=3.0, initial_channels=32,
+                 stage_channels=[64, 128, 256], global_pool_size=2, global_feature_dim=256, regression_dims=[128, 64])
+
+
+def gen_cnn():
+    """State-dict layout of the full-size reference CNN + outputs of a small configuration (eval mode) whose
+    parameters come from oracle.torch_models.fill_state_dict (deterministic, regenerated by the tests)."""
+    import torch
+    from model_config import ModelConfig
+    from models.cnn import CNNPoseEstimation
+    sys.path.insert(0, REPO)
+    from oracle import torch_models as tm
+    full = CNNPoseEstimation(ModelConfig("cnn", image_size=(256, 256), heatmap_size=256))
+    layout = {k: list(v.shape) for k, v in full.state_dict().items()}
+    with open(os.path.join(OUT, "cnn_state_dict_layout.json"), "w") as f:
+        json.dump(layout, f, indent=0, sort_keys=True)
+    cfg = ModelConfig("cnn", **SMALL_CNN)
+    m = CNNPoseEstimation(cfg)
+    sd = tm.fill_state_dict(m.state_dict(), seed=3)
+    m.load_state_dict(sd)
+    m.eval()
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(4, 3, 64, 64, generator=g)
+    dep = torch.rand(4, 1, 64, 64, generator=g)
+    kp = torch.rand(4, 17, 2, generator=g) * 0.9 + 0.05
+    kp[0, 3] = -1.0
+    with torch.no_grad():
+        out = m(img, dep, kp)
+        out_oracle = tm.cnn_forward(sd, cfg, img, dep, kp)
+    assert (out - out_oracle).abs().max() < 1e-3
+    np.savez_compressed(os.path.join(OUT, "cnn_small.npz"), versions=versions(), config=json.dumps(SMALL_CNN),
+                        fill_seed=3, image=img.numpy(), depth=dep.numpy(), kp=kp.numpy(), out=out.numpy(),
+                        n_params=sum(p.numel() for p in m.parameters()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, os.path.join(REF, "src"))
     os.chdir(tempfile.mkdtemp(prefix="pose_golden_"))
-    which = sys.argv[1:] or ["augment", "heatmap", "loss", "config"]
+    which = sys.argv[1:] or ["augment", "heatmap", "loss", "config", "cnn"]
     for w in which:
         globals()["gen_" + w]()
         print("wrote", w)

@@ -41,3 +41,32 @@ def test_loss_module_attributes(pose):
     crit = pose.ComprehensivePoseLoss(l1_weight=0.5, mse_weight=2.0, inter_joint_loss_weight=10.0,
                                       abs_root_loss_weight=3.0)
     assert crit._weights() == (2.0, 0.5, 10.0, 3.0)
+
+
+def test_cnn_state_dict_layout_matches_reference(pose):
+    """Checkpoint compatibility: same keys and shapes as the reference's CNNPoseEstimation."""
+    import json
+    import os
+    from conftest import GOLDEN
+    ref = json.load(open(os.path.join(GOLDEN, "cnn_state_dict_layout.json")))
+    m = pose.CNNPoseEstimation(pose.ModelConfig("cnn", image_size=(256, 256), heatmap_size=256))
+    got = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert got == ref
+    assert sum(p.numel() for p in m.parameters()) == 26920792
+    assert m.config.to_dict()["stage_channels"] == [128, 256, 512]
+
+
+def test_torch_oracle_cnn_matches_reference_golden(golden):
+    """The fp32 model oracle (oracle/torch_models.py) reproduces the live reference on the small configuration."""
+    import json
+    import torch
+    from oracle import torch_models as tm
+    import importlib
+    pose = importlib.import_module("3dhumanposeestimation_b200")
+    g = golden("cnn_small.npz")
+    cfg = pose.ModelConfig("cnn", **json.loads(str(g["config"])))
+    m = pose.CNNPoseEstimation(cfg)
+    assert sum(p.numel() for p in m.parameters()) == int(g["n_params"])
+    sd = tm.fill_state_dict(m.state_dict(), seed=int(g["fill_seed"]))
+    out = tm.cnn_forward(sd, cfg, torch.from_numpy(g["image"]), torch.from_numpy(g["depth"]), torch.from_numpy(g["kp"]))
+    assert np.abs(out.numpy() - g["out"]).max() < 1e-3 * max(1.0, np.abs(g["out"]).max())
