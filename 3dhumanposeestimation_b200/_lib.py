@@ -55,15 +55,16 @@ SIGNATURES = {
                                  c_int, C.POINTER(PoseGemmEpilogue), c_void_p]),
     "pose_cnn_input_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "pose_dwconv3x3_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
-                                    c_void_p, c_void_p]),
-    "pose_pool_sum_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "pose_se_gate": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "pose_eca_gate": (c_int, [c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+                                    c_void_p, c_int, c_void_p]),
+    "pose_pool_sum_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "pose_se_gate": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                             c_void_p]),
+    "pose_eca_gate": (c_int, [c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pose_channel_affine_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, C.c_long, c_int, c_void_p, c_void_p]),
     "pose_coord_pool_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pose_coord_apply_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pose_avgpool2x2_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "pose_sums_to_bf16": (c_int, [c_void_p, c_float, C.c_long, c_void_p, c_void_p]),
+    "pose_sums_to_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -84,8 +84,9 @@ cnn_input_pack_kernel(const float *__restrict__ image, const float *__restrict__
 
 // ---------------------------------------------------------------------------------------------------------
 // Depthwise 3x3 conv (pad 1, stride 1 or 2) + folded BatchNorm + activation, NHWC bf16, 8 channels per thread.
-// Optionally accumulates per-(image, channel) sums of the OUTPUT (the squeeze of SE / ECA, cnn.py:22-23,40-41).
-// grid.x = B * chunks (a CTA stays inside one image), grid.y = channel slabs of CG*8 channels.
+// Optionally emits per-(image, chunk, channel) partial sums of the OUTPUT (the squeeze of SE / ECA,
+// cnn.py:22-23,40-41): pool [B, chunks, C], written (not accumulated) and reduced in a fixed order, so the
+// result is deterministic.  grid.x = B * chunks (a CTA stays inside one image), grid.y = channel slabs.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ Wd, const float *__restrict__ bias,
@@ -102,7 +103,7 @@ dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ 
     __syncthreads();
     const int cg_lane = threadIdx.x % CG, plane = threadIdx.x / CG, planes = 256 / CG;
     const int c0 = slab_c0 + cg_lane * 8;
-    if (c0 >= C || plane >= planes) return;
+    const bool active = c0 < C;
     const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
     const int npx = Ho * Wo;
     const int per = (npx + chunks - 1) / chunks;
@@ -118,7 +119,7 @@ dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ 
         bs[k] = s_w[9 * CG * 8 + cg_lane * 8 + k];
         psum[k] = 0.f;
     }
-    for (int p = p_begin + plane; p < p_end; p += planes) {
+    for (int p = p_begin + plane; active && p < p_end; p += planes) {
         const int oy = p / Wo, ox = p - oy * Wo;
         float acc[8];
 #pragma unroll
@@ -144,14 +145,24 @@ dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ 
         }
         *(uint4 *)(Y + ((long)b * npx + p) * C + c0) = pack8(acc);
     }
-    if (pool != nullptr) {
+    if (pool != nullptr) {  // fixed-order reduction over the pixel planes of the CTA, one write per channel
+        __shared__ float s_part[256 * 8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) atomicAdd(pool + (long)b * C + c0 + k, psum[k]);
+        for (int k = 0; k < 8; ++k) s_part[(plane * CG + cg_lane) * 8 + k] = psum[k];
+        __syncthreads();
+        if (plane == 0 && active) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float t = 0.f;
+                for (int q = 0; q < planes; ++q) t += s_part[(q * CG + cg_lane) * 8 + k];
+                pool[((long)b * chunks + chunk) * C + c0 + k] = t;
+            }
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Channel sums over the pixels of each image: X [B, HW, C] bf16 -> S [B, C] fp32 (+=, S zeroed by the caller)
+// Channel sums over the pixels of each image: X [B, HW, C] bf16 -> partial sums S [B, chunks, C] fp32 (written)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pool_sum_kernel(const __nv_bfloat16 *__restrict__ X, int HW, int C, float *__restrict__ S, int chunks) {
@@ -168,7 +179,7 @@ pool_sum_kernel(const __nv_bfloat16 *__restrict__ X, int HW, int C, float *__res
             for (int k = 0; k < 8; ++k) s[k] += f[k];
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) atomicAdd(S + (long)b * C + cg * 8 + k, s[k]);
+        for (int k = 0; k < 8; ++k) S[((long)b * chunks + chunk) * C + cg * 8 + k] = s[k];
     }
 }
 
@@ -179,12 +190,16 @@ pool_sum_kernel(const __nv_bfloat16 *__restrict__ X, int HW, int C, float *__res
 // global_features tail (ECABlock followed by AdaptiveAvgPool2d(1), cnn.py:612-613) needs nothing else.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-se_gate_kernel(const float *__restrict__ pool, float inv_hw, const float *__restrict__ W1, const float *__restrict__ W2,
-               int C, int Cr, int act, float *__restrict__ gate) {
+se_gate_kernel(const float *__restrict__ pool, int parts, float inv_hw, const float *__restrict__ W1,
+               const float *__restrict__ W2, int C, int Cr, int act, float *__restrict__ gate) {
     extern __shared__ float sm[];  // mean[C] + hidden[Cr]
     float *mean = sm, *hid = sm + C;
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int c = threadIdx.x; c < C; c += 256) mean[c] = pool[(long)b * C + c] * inv_hw;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.f;
+        for (int q = 0; q < parts; ++q) t += pool[((long)b * parts + q) * C + c];
+        mean[c] = t * inv_hw;
+    }
     __syncthreads();
     for (int r = warp; r < Cr; r += 8) {
         float s = 0.f;
@@ -201,19 +216,26 @@ se_gate_kernel(const float *__restrict__ pool, float inv_hw, const float *__rest
 }
 
 __global__ void __launch_bounds__(256)
-eca_gate_kernel(const float *__restrict__ pool, float inv_hw, const float *__restrict__ w, int k, int C,
+eca_gate_kernel(const float *__restrict__ pool, int parts, float inv_hw, const float *__restrict__ w, int k, int C,
                 float *__restrict__ gate, __nv_bfloat16 *__restrict__ feat_out) {
+    extern __shared__ float mean[];  // [C]
     const int b = blockIdx.x;
     const int half = (k - 1) / 2;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.f;
+        for (int q = 0; q < parts; ++q) t += pool[((long)b * parts + q) * C + c];
+        mean[c] = t * inv_hw;
+    }
+    __syncthreads();
     for (int c = threadIdx.x; c < C; c += 256) {
         float s = 0.f;
         for (int t = 0; t < k; ++t) {
             const int cc = c + t - half;
-            if (cc >= 0 && cc < C) s = fmaf(__ldg(w + t), pool[(long)b * C + cc] * inv_hw, s);
+            if (cc >= 0 && cc < C) s = fmaf(__ldg(w + t), mean[cc], s);
         }
         const float g = 1.0f / (1.0f + __expf(-s));
         if (gate != nullptr) gate[(long)b * C + c] = g;
-        if (feat_out != nullptr) feat_out[(long)b * C + c] = __float2bfloat16_rn(pool[(long)b * C + c] * inv_hw * g);
+        if (feat_out != nullptr) feat_out[(long)b * C + c] = __float2bfloat16_rn(mean[c] * g);
     }
 }
 
@@ -318,11 +340,16 @@ avgpool2x2_kernel(const __nv_bfloat16 *__restrict__ X, int H, int W, int C, long
     }
 }
 
-// S [B, C] fp32 sums -> bf16 means (operand of the WASP global-branch GEMM)
+// S [B, parts, C] fp32 partial sums -> bf16 means [B, C] (operand of the WASP global-branch GEMM)
 __global__ void __launch_bounds__(256)
-sums_to_bf16_kernel(const float *__restrict__ S, float scale, long n, __nv_bfloat16 *__restrict__ out) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-        out[i] = __float2bfloat16_rn(S[i] * scale);
+sums_to_bf16_kernel(const float *__restrict__ S, int parts, int C, float scale, long n, __nv_bfloat16 *__restrict__ out) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / C;
+        const int c = (int)(i - b * C);
+        float t = 0.f;
+        for (int q = 0; q < parts; ++q) t += S[(b * parts + q) * C + c];
+        out[i] = __float2bfloat16_rn(t * scale);
+    }
 }
 
 static int grid_for(long items, int per_block = 256, int max_waves = 16) {
@@ -349,7 +376,7 @@ POSE_API int pose_cnn_input_pack(const float *image, const float *depth, const f
 }
 
 POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, const float *Wd, const float *bias, int stride,
-                                 int act, void *Y, float *pool_sum, pose_stream_t stream) {
+                                 int act, void *Y, float *pool_sum, int pool_parts, pose_stream_t stream) {
     if (!X || !Wd || !bias || !Y) return POSE_E_NULL;
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 || (stride != 1 && stride != 2)) return POSE_E_SHAPE;
     if ((uintptr_t)X % 16 || (uintptr_t)Y % 16) return POSE_E_ALIGN;
@@ -363,6 +390,10 @@ POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, cons
     const int npx = Ho * Wo, planes = 256 / CG;
     if (chunks > (npx + planes - 1) / planes) chunks = (npx + planes - 1) / planes;
     if (chunks < 1) chunks = 1;
+    if (pool_sum != nullptr) {
+        if (pool_parts < 1) return POSE_E_SHAPE;
+        chunks = pool_parts;  // the caller sized pool_sum as [B, pool_parts, C]
+    }
     const size_t smem = (size_t)(10 * CG * 8) * sizeof(float);
     dim3 grid(B * chunks, slabs);
     dwconv3x3_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, Wd, bias, H, W, C, stride, act,
@@ -370,29 +401,29 @@ POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, cons
     return launch_status();
 }
 
-POSE_API int pose_pool_sum_bf16(const void *X, int B, int HW, int C, float *sums, pose_stream_t stream) {
+POSE_API int pose_pool_sum_bf16(const void *X, int B, int HW, int C, float *sums, int parts, pose_stream_t stream) {
     if (!X || !sums) return POSE_E_NULL;
-    if (B <= 0 || HW <= 0 || C <= 0 || C % 8) return POSE_E_SHAPE;
-    int chunks = (kNumSMs * 4 + B - 1) / B;
-    if (chunks > HW) chunks = HW;
-    if (chunks < 1) chunks = 1;
+    if (B <= 0 || HW <= 0 || C <= 0 || C % 8 || parts < 1) return POSE_E_SHAPE;
+    const int chunks = parts;
     pool_sum_kernel<<<B * chunks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, HW, C, sums, chunks);
     return launch_status();
 }
 
-POSE_API int pose_se_gate(const float *pool_sum, float inv_hw, const float *W1, const float *W2, int B, int C, int Cr,
-                          int act, float *gate, pose_stream_t stream) {
+POSE_API int pose_se_gate(const float *pool_sum, int parts, float inv_hw, const float *W1, const float *W2, int B, int C,
+                          int Cr, int act, float *gate, pose_stream_t stream) {
     if (!pool_sum || !W1 || !W2 || !gate) return POSE_E_NULL;
-    if (B <= 0 || C <= 0 || Cr <= 0) return POSE_E_SHAPE;
-    se_gate_kernel<<<B, 256, (size_t)(C + Cr) * sizeof(float), (cudaStream_t)stream>>>(pool_sum, inv_hw, W1, W2, C, Cr, act, gate);
+    if (B <= 0 || C <= 0 || Cr <= 0 || parts < 1) return POSE_E_SHAPE;
+    se_gate_kernel<<<B, 256, (size_t)(C + Cr) * sizeof(float), (cudaStream_t)stream>>>(pool_sum, parts, inv_hw, W1, W2, C, Cr,
+                                                                                      act, gate);
     return launch_status();
 }
 
-POSE_API int pose_eca_gate(const float *pool_sum, float inv_hw, const float *w, int k, int B, int C, float *gate,
+POSE_API int pose_eca_gate(const float *pool_sum, int parts, float inv_hw, const float *w, int k, int B, int C, float *gate,
                            void *feat_out, pose_stream_t stream) {
     if (!pool_sum || !w || (!gate && !feat_out)) return POSE_E_NULL;
-    if (B <= 0 || C <= 0 || k <= 0 || !(k & 1)) return POSE_E_SHAPE;
-    eca_gate_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(pool_sum, inv_hw, w, k, C, gate, (__nv_bfloat16 *)feat_out);
+    if (B <= 0 || C <= 0 || k <= 0 || !(k & 1) || parts < 1) return POSE_E_SHAPE;
+    eca_gate_kernel<<<B, 256, (size_t)C * sizeof(float), (cudaStream_t)stream>>>(pool_sum, parts, inv_hw, w, k, C, gate,
+                                                                                (__nv_bfloat16 *)feat_out);
     return launch_status();
 }
 
@@ -432,9 +463,10 @@ POSE_API int pose_avgpool2x2_bf16(const void *X, int B, int H, int W, int C, voi
     return launch_status();
 }
 
-POSE_API int pose_sums_to_bf16(const float *sums, float scale, long n, void *out, pose_stream_t stream) {
+POSE_API int pose_sums_to_bf16(const float *sums, int parts, int B, int C, float scale, void *out, pose_stream_t stream) {
     if (!sums || !out) return POSE_E_NULL;
-    if (n <= 0) return POSE_E_SHAPE;
-    sums_to_bf16_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(sums, scale, n, (__nv_bfloat16 *)out);
+    if (B <= 0 || C <= 0 || parts < 1) return POSE_E_SHAPE;
+    const long n = (long)B * C;
+    sums_to_bf16_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(sums, parts, C, scale, n, (__nv_bfloat16 *)out);
     return launch_status();
 }

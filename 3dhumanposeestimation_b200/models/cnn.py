@@ -252,6 +252,10 @@ class CnnInferencePlan:
         self.keep.append(t)
         return t
 
+    def _parts(self, npx):
+        """Pixel chunks per image for squeeze sums: enough CTAs to fill the chip, at least 8 pixels per chunk."""
+        return max(1, min(npx // 8 if npx >= 8 else 1, (148 * 4 + self.B - 1) // self.B))
+
     def _param_version(self):
         if self._tracked is None:
             self._tracked = list(self.model.parameters()) + list(self.model.buffers())
@@ -327,7 +331,7 @@ class CnnInferencePlan:
                      C.byref(e))
         return out
 
-    def dwconv(self, x, cba, pool=None):
+    def dwconv(self, x, cba, want_pool=False):
         Bn, H, W, ch = x.shape
         conv = cba.conv
         if conv.kernel_size != (3, 3) or conv.padding != (1, 1) or conv.groups != ch:
@@ -344,33 +348,39 @@ class CnnInferencePlan:
         Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
         out = self._buf(Bn, Ho, Wo, ch)
         a = self.act if cba.activation is not None else 0
-        if pool is not None:
-            self.steps.append(pool.zero_)
+        pool = self._buf(Bn, self._parts(Ho * Wo), ch, dtype=torch.float32) if want_pool else None
         self._launch("pose_dwconv3x3_bf16", x.data_ptr(), Bn, H, W, ch, wd.data_ptr(), b32.data_ptr(), stride, a,
-                     out.data_ptr(), pool.data_ptr() if pool is not None else None)
-        return out
+                     out.data_ptr(), pool.data_ptr() if pool is not None else None,
+                     pool.shape[1] if pool is not None else 0)
+        return (out, pool) if want_pool else out
+
+    def pool_sums(self, x):
+        """[B, parts, C] fp32 partial channel sums of x [B,H,W,C]."""
+        Bn, H, W, ch = x.shape
+        pool = self._buf(Bn, self._parts(H * W), ch, dtype=torch.float32)
+        self._launch("pose_pool_sum_bf16", x.data_ptr(), Bn, H * W, ch, pool.data_ptr(), pool.shape[1])
+        return pool
 
     def attention(self, x, att, pool=None):
         """SE / ECA / CoordAttention on x [B,H,W,C]; `pool` = channel sums of x if the producer made them."""
         Bn, H, W, ch = x.shape
         if isinstance(att, (SEBlock, ECABlock)):
             if pool is None:
-                pool = self._buf(Bn, ch, dtype=torch.float32)
-                self.steps.append(pool.zero_)
-                self._launch("pose_pool_sum_bf16", x.data_ptr(), Bn, H * W, ch, pool.data_ptr())
+                pool = self.pool_sums(x)
+            parts = pool.shape[1]
             gate = self._buf(Bn, ch, dtype=torch.float32)
             if isinstance(att, SEBlock):
                 w1, w2 = att.fc[0].weight, att.fc[2].weight
                 w1f, w2f = self._buf(*w1.shape, dtype=torch.float32), self._buf(*w2.shape, dtype=torch.float32)
                 self.weights.append(lambda: (w1f.copy_(w1.detach()), w2f.copy_(w2.detach())))
-                self._launch("pose_se_gate", pool.data_ptr(), 1.0 / (H * W), w1f.data_ptr(), w2f.data_ptr(), Bn, ch,
+                self._launch("pose_se_gate", pool.data_ptr(), parts, 1.0 / (H * W), w1f.data_ptr(), w2f.data_ptr(), Bn, ch,
                              w1.shape[0], activation_id(att.activation), gate.data_ptr())
             else:
                 k = att.conv.weight.shape[-1]
                 wk = self._buf(k, dtype=torch.float32)
                 self.weights.append(lambda: wk.copy_(att.conv.weight.detach().view(-1)))
-                self._launch("pose_eca_gate", pool.data_ptr(), 1.0 / (H * W), wk.data_ptr(), k, Bn, ch, gate.data_ptr(),
-                             None)
+                self._launch("pose_eca_gate", pool.data_ptr(), parts, 1.0 / (H * W), wk.data_ptr(), k, Bn, ch,
+                             gate.data_ptr(), None)
             self._launch("pose_channel_affine_bf16", x.data_ptr(), gate.data_ptr(), None, Bn, H * W, ch, x.data_ptr())
             return x
         if isinstance(att, CoordAttention):
@@ -412,9 +422,11 @@ class CnnInferencePlan:
             y = self.conv1x1(y, cbas[0])
         dw, proj = cbas[-2], cbas[-1]
         att = atts[0] if atts else None
-        ch = dw.conv.out_channels
-        pool = self._buf(x.shape[0], ch, dtype=torch.float32) if isinstance(att, (SEBlock, ECABlock)) else None
-        y = self.dwconv(y, dw, pool)
+        pool = None
+        if isinstance(att, (SEBlock, ECABlock)):
+            y, pool = self.dwconv(y, dw, want_pool=True)
+        else:
+            y = self.dwconv(y, dw)
         if att is not None:
             y = self.attention(y, att, pool)
         if blk.use_residual:   # x + conv(x) * residual_scale
@@ -456,11 +468,9 @@ class CnnInferencePlan:
         for i, br in enumerate(m.atrous_branches):
             self.conv2d(x, br, out=acc, residual=acc, res_scale=1.0)
             scales.append((self.last_epi, i + 1))
-        pool = self._buf(Bn, ch, dtype=torch.float32)
-        self.steps.append(pool.zero_)
-        self._launch("pose_pool_sum_bf16", x.data_ptr(), Bn, H * W, ch, pool.data_ptr())
+        pool = self.pool_sums(x)
         mean16 = self._buf(Bn, ch)
-        self._launch("pose_sums_to_bf16", pool.data_ptr(), 1.0 / (H * W), Bn * ch, mean16.data_ptr())
+        self._launch("pose_sums_to_bf16", pool.data_ptr(), pool.shape[1], Bn, ch, 1.0 / (H * W), mean16.data_ptr())
         g = self.conv1x1(mean16.view(Bn, 1, 1, ch), m.global_branch[1])
         scales.append((self.last_epi, len(m.dilations) + 1))
         # bilinear interpolation of a 1x1 map is a broadcast (cnn.py:465-467)
@@ -496,15 +506,14 @@ class CnnInferencePlan:
             raise NotImplementedError(f"AdaptiveAvgPool2d({gp}) from {H}x{H}: only identity and 2x2 pooling are built")
         x = self.conv1x1(x, m.global_features[1])
         ch = x.shape[-1]
-        pool = self._buf(Bn, ch, dtype=torch.float32)
-        self.steps.append(pool.zero_)
-        self._launch("pose_pool_sum_bf16", x.data_ptr(), Bn, gp * gp, ch, pool.data_ptr())
+        pool = self.pool_sums(x)
         eca = m.global_features[2]
         k = eca.conv.weight.shape[-1]
         wk = self._buf(k, dtype=torch.float32)
         self.weights.append(lambda: wk.copy_(eca.conv.weight.detach().view(-1)))
         feat = self._buf(Bn, ch)
-        self._launch("pose_eca_gate", pool.data_ptr(), 1.0 / (gp * gp), wk.data_ptr(), k, Bn, ch, None, feat.data_ptr())
+        self._launch("pose_eca_gate", pool.data_ptr(), pool.shape[1], 1.0 / (gp * gp), wk.data_ptr(), k, Bn, ch, None,
+                     feat.data_ptr())
         # regression head: Linear + act on the tcgen05 GEMM (dropout is the identity in eval mode)
         lins = [mod[0] if isinstance(mod, nn.Sequential) else mod for mod in m.pose_head.decoder]
         h = feat

@@ -156,8 +156,9 @@ int pose_conv2d_bf16(const void *X, int Nimg, int H, int W, int Cin, const void 
  *  pose_cnn_input_pack   cat([image, depth, heatmaps], 1) (cnn.py:644-648) written as the conv1 operand
  *                        [B,S,S,32] bf16 = {R,G,B,depth, J heat-maps, zero pad}; heat-maps rendered in flight
  *  pose_dwconv3x3_bf16   depthwise 3x3, pad 1, stride 1|2 + per-channel bias (folded BN) + act; Wd [3,3,C]
- *                        fp32; pool_sum [B,C] fp32 (optional, += sums of the OUTPUT: SE/ECA squeeze)
- *  pose_pool_sum_bf16    sums [B,C] fp32 += sum over pixels of X [B,HW,C]
+ *                        fp32; pool_sum [B,pool_parts,C] fp32 (optional): partial sums of the OUTPUT per image
+ *                        chunk (SE/ECA squeeze), written -- consumers add the parts in order (deterministic)
+ *  pose_pool_sum_bf16    sums [B,parts,C] fp32 = partial sums over pixel chunks of X [B,HW,C]
  *  pose_se_gate          SEBlock (cnn.py:9-26): gate = sigmoid(W2 . act(W1 . (pool_sum*inv_hw)))
  *  pose_eca_gate         ECABlock (cnn.py:29-45): gate = sigmoid(conv1d_k(mean)); feat_out (optional,
  *                        bf16 [B,C]) = mean * gate (= ECA followed by global average pooling, cnn.py:612-613)
@@ -165,23 +166,23 @@ int pose_conv2d_bf16(const void *X, int Nimg, int H, int W, int Cin, const void 
  *  pose_coord_pool_bf16 / pose_coord_apply_bf16   CoordAttention (cnn.py:48-98) directional means
  *                        P [B,H+W,C] and out = x * G[b,h,c] * G[b,H+w,C+c] with G [B,H+W,2C] bf16
  *  pose_avgpool2x2_bf16  AdaptiveAvgPool2d(8) on a 16x16 map (cnn.py:602)
- *  pose_sums_to_bf16     out = bf16(sums * scale)
+ *  pose_sums_to_bf16     out [B,C] bf16 = (sum of the parts) * scale
  * ------------------------------------------------------------------------------------------- */
 int pose_cnn_input_pack(const float *image, const float *depth, const float *kp, int B, int S, int J, float sigma,
                         void *out, pose_stream_t stream);
 int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, const float *Wd, const float *bias, int stride,
-                        int act, void *Y, float *pool_sum, pose_stream_t stream);
-int pose_pool_sum_bf16(const void *X, int B, int HW, int C, float *sums, pose_stream_t stream);
-int pose_se_gate(const float *pool_sum, float inv_hw, const float *W1, const float *W2, int B, int C, int Cr, int act,
-                 float *gate, pose_stream_t stream);
-int pose_eca_gate(const float *pool_sum, float inv_hw, const float *w, int k, int B, int C, float *gate, void *feat_out,
-                  pose_stream_t stream);
+                        int act, void *Y, float *pool_sum, int pool_parts, pose_stream_t stream);
+int pose_pool_sum_bf16(const void *X, int B, int HW, int C, float *sums, int parts, pose_stream_t stream);
+int pose_se_gate(const float *pool_sum, int parts, float inv_hw, const float *W1, const float *W2, int B, int C, int Cr,
+                 int act, float *gate, pose_stream_t stream);
+int pose_eca_gate(const float *pool_sum, int parts, float inv_hw, const float *w, int k, int B, int C, float *gate,
+                  void *feat_out, pose_stream_t stream);
 int pose_channel_affine_bf16(const void *X, const float *mul, const void *add, int B, long HW, int C, void *Y,
                              pose_stream_t stream);
 int pose_coord_pool_bf16(const void *X, int B, int H, int W, int C, void *P, pose_stream_t stream);
 int pose_coord_apply_bf16(const void *X, const void *G, int B, int H, int W, int C, void *Y, pose_stream_t stream);
 int pose_avgpool2x2_bf16(const void *X, int B, int H, int W, int C, void *Y, pose_stream_t stream);
-int pose_sums_to_bf16(const float *sums, float scale, long n, void *out, pose_stream_t stream);
+int pose_sums_to_bf16(const float *sums, int parts, int B, int C, float scale, void *out, pose_stream_t stream);
 
 #ifdef __cplusplus
 }

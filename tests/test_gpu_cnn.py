@@ -80,31 +80,39 @@ def test_dwconv_gates_pools_match_fp32_reference(pose):
         ref = F.silu(F.conv2d(x.float().permute(0, 3, 1, 2), wd, bias, stride, 1, groups=Cc)).permute(0, 2, 3, 1)
         Ho = ref.shape[1]
         y = torch.empty(B, Ho, Ho, Cc, device=DEV, dtype=torch.bfloat16)
-        pool = torch.zeros(B, Cc, device=DEV)
+        parts = 5
+        pool = torch.full((B, parts, Cc), float("nan"), device=DEV)    # written, not accumulated
         wk = wd.view(Cc, 9).t().contiguous()
         pose._lib.check(lib.pose_dwconv3x3_bf16(x.data_ptr(), B, H, H, Cc, wk.data_ptr(), bias.data_ptr(), stride, 2,
-                                                y.data_ptr(), pool.data_ptr(), sp()), "dw")
+                                                y.data_ptr(), pool.data_ptr(), parts, sp()), "dw")
         assert torch.allclose(y.float(), ref, rtol=2 ** -7, atol=2e-2)
-        assert torch.allclose(pool, ref.sum((1, 2)), rtol=1e-3, atol=Ho * Ho * 2e-3)
+        assert torch.allclose(pool.sum(1), ref.sum((1, 2)), rtol=1e-3, atol=Ho * Ho * 2e-3)
+        y2 = torch.empty_like(y)                                        # without the squeeze output
+        pose._lib.check(lib.pose_dwconv3x3_bf16(x.data_ptr(), B, H, H, Cc, wk.data_ptr(), bias.data_ptr(), stride, 2,
+                                                y2.data_ptr(), None, 0, sp()), "dw")
+        assert torch.equal(y, y2)
         # pool_sum on its own
-        pool2 = torch.zeros(B, Cc, device=DEV)
-        pose._lib.check(lib.pose_pool_sum_bf16(y.data_ptr(), B, Ho * Ho, Cc, pool2.data_ptr(), sp()), "pool")
-        assert torch.allclose(pool2, y.float().sum((1, 2)), rtol=1e-4, atol=1e-2)
+        pool2 = torch.full((B, 3, Cc), float("nan"), device=DEV)
+        pose._lib.check(lib.pose_pool_sum_bf16(y.data_ptr(), B, Ho * Ho, Cc, pool2.data_ptr(), 3, sp()), "pool")
+        assert torch.allclose(pool2.sum(1), y.float().sum((1, 2)), rtol=1e-4, atol=1e-2)
         # SE gate
         cr = max(2, Cc // 16)
         w1, w2 = (torch.randn(cr, Cc, generator=g) * 0.1).to(DEV), (torch.randn(Cc, cr, generator=g) * 0.1).to(DEV)
         gate = torch.empty(B, Cc, device=DEV)
-        pose._lib.check(lib.pose_se_gate(pool2.data_ptr(), 1.0 / (Ho * Ho), w1.data_ptr(), w2.data_ptr(), B, Cc, cr, 2,
+        pose._lib.check(lib.pose_se_gate(pool2.data_ptr(), 3, 1.0 / (Ho * Ho), w1.data_ptr(), w2.data_ptr(), B, Cc, cr, 2,
                                          gate.data_ptr(), sp()), "se")
-        mean = pool2 / (Ho * Ho)
+        mean = pool2.sum(1) / (Ho * Ho)
         want = torch.sigmoid(F.silu(mean @ w1.t()) @ w2.t())
         assert torch.allclose(gate, want, rtol=1e-4, atol=1e-5)
         # ECA gate (+ fused mean * gate)
         wk5 = torch.randn(5, generator=g).to(DEV)
         gate2 = torch.empty(B, Cc, device=DEV)
         feat = torch.empty(B, Cc, device=DEV, dtype=torch.bfloat16)
-        pose._lib.check(lib.pose_eca_gate(pool2.data_ptr(), 1.0 / (Ho * Ho), wk5.data_ptr(), 5, B, Cc, gate2.data_ptr(),
+        pose._lib.check(lib.pose_eca_gate(pool2.data_ptr(), 3, 1.0 / (Ho * Ho), wk5.data_ptr(), 5, B, Cc, gate2.data_ptr(),
                                           feat.data_ptr(), sp()), "eca")
+        m16 = torch.empty(B, Cc, device=DEV, dtype=torch.bfloat16)
+        pose._lib.check(lib.pose_sums_to_bf16(pool2.data_ptr(), 3, B, Cc, 1.0 / (Ho * Ho), m16.data_ptr(), sp()), "s2b")
+        assert torch.allclose(m16.float(), mean, rtol=2 ** -7, atol=1e-3)
         want2 = torch.sigmoid(F.conv1d(mean[:, None], wk5.view(1, 1, 5), padding=2))[:, 0]
         assert torch.allclose(gate2, want2, rtol=1e-4, atol=1e-5)
         assert torch.allclose(feat.float(), mean * want2, rtol=2 ** -7, atol=1e-3)
@@ -139,12 +147,12 @@ def test_cnn_input_pack_matches_oracle(pose, oracle):
     kp = rng.uniform(0.05, 0.95, (B, J, 2)).astype(np.float32)
     kp[0, 3] = -1
     out = torch.empty(B, S, S, 32, device=DEV, dtype=torch.bfloat16)
-    t = lambda a: torch.from_numpy(a).to(DEV)
-    pose._lib.check(pose._lib.lib().pose_cnn_input_pack(t(img).data_ptr(), t(dep).data_ptr(), t(kp).data_ptr(), B, S, J, 3.0,
+    ti, td, tk = (torch.from_numpy(a).to(DEV) for a in (img, dep, kp))   # keep the device copies alive
+    pose._lib.check(pose._lib.lib().pose_cnn_input_pack(ti.data_ptr(), td.data_ptr(), tk.data_ptr(), B, S, J, 3.0,
                                                         out.data_ptr(), pose._lib.stream_ptr()), "pack")
     o = out.float().cpu().numpy()
     want = np.concatenate([img, dep, oracle.heatmap(kp, S, 3.0)], 1).transpose(0, 2, 3, 1)
-    assert np.allclose(o[..., :21], want, rtol=2 ** -8, atol=1e-30)
+    assert np.allclose(o[..., :21], want, rtol=2 ** -8, atol=1e-37)
     assert (o[..., 21:] == 0).all()
 
 
@@ -191,7 +199,7 @@ def test_cnn_full_size_matches_fp32_oracle(pose, B):
     # second call reuses the plan; parameters changed in place are picked up
     with torch.no_grad():
         out2 = m(img, dep, kp)
-        assert torch.equal(out, out2)
+        assert torch.equal(out, out2)      # no atomics anywhere on the path: bit-reproducible
         m.pose_head.decoder[-1].bias.add_(10.0)
         out3 = m(img, dep, kp)
     assert torch.allclose(out3, out + 10.0, atol=1e-3)
