@@ -189,29 +189,52 @@ pool_sum_kernel(const __nv_bfloat16 *__restrict__ X, int HW, int C, float *__res
 // Both read channel SUMS and scale by inv_hw.  `feat_out` (optional, bf16 [B, C]) receives mean * gate: the
 // global_features tail (ECABlock followed by AdaptiveAvgPool2d(1), cnn.py:612-613) needs nothing else.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kSeSamples = 2;  // images per CTA: every weight row fetched once serves both
+
 __global__ void __launch_bounds__(256)
 se_gate_kernel(const float *__restrict__ pool, int parts, float inv_hw, const float *__restrict__ W1,
-               const float *__restrict__ W2, int C, int Cr, int act, float *__restrict__ gate) {
-    extern __shared__ float sm[];  // mean[C] + hidden[Cr]
-    float *mean = sm, *hid = sm + C;
-    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int c = threadIdx.x; c < C; c += 256) {
+               const float *__restrict__ W2, int B, int C, int Cr, int act, float *__restrict__ gate) {
+    extern __shared__ float sm[];  // mean[kSeSamples][C] + hidden[kSeSamples][Cr]
+    float *mean = sm, *hid = sm + kSeSamples * C;
+    const int b0 = blockIdx.x * kSeSamples, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < kSeSamples * C; i += 256) {
+        const int sb = i / C, c = i - sb * C;
         float t = 0.f;
-        for (int q = 0; q < parts; ++q) t += pool[((long)b * parts + q) * C + c];
-        mean[c] = t * inv_hw;
+        if (b0 + sb < B)
+            for (int q = 0; q < parts; ++q) t += pool[((long)(b0 + sb) * parts + q) * C + c];
+        mean[i] = t * inv_hw;
     }
     __syncthreads();
-    for (int r = warp; r < Cr; r += 8) {
-        float s = 0.f;
-        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(W1 + (long)r * C + c), mean[c], s);
-        s = warp_sum(s);
-        if (lane == 0) hid[r] = act_f(s, act);
+    for (int r = warp; r < Cr; r += 8) {          // a warp per hidden unit: W1 row read once, coalesced
+        float s[kSeSamples];
+#pragma unroll
+        for (int q = 0; q < kSeSamples; ++q) s[q] = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float w = __ldg(W1 + (long)r * C + c);
+#pragma unroll
+            for (int q = 0; q < kSeSamples; ++q) s[q] = fmaf(w, mean[q * C + c], s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < kSeSamples; ++q) {
+            s[q] = warp_sum(s[q]);
+            if (lane == 0) hid[q * Cr + r] = act_f(s[q], act);
+        }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += 256) {
-        float s = 0.f;
-        for (int r = 0; r < Cr; ++r) s = fmaf(__ldg(W2 + (long)c * Cr + r), hid[r], s);
-        gate[(long)b * C + c] = 1.0f / (1.0f + __expf(-s));
+    for (int c = warp; c < C; c += 8) {            // a warp per output channel: W2 row (Cr floats) coalesced
+        float s[kSeSamples];
+#pragma unroll
+        for (int q = 0; q < kSeSamples; ++q) s[q] = 0.f;
+        for (int r = lane; r < Cr; r += 32) {
+            const float w = __ldg(W2 + (long)c * Cr + r);
+#pragma unroll
+            for (int q = 0; q < kSeSamples; ++q) s[q] = fmaf(w, hid[q * Cr + r], s[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < kSeSamples; ++q) {
+            s[q] = warp_sum(s[q]);
+            if (lane == 0 && b0 + q < B) gate[(long)(b0 + q) * C + c] = 1.0f / (1.0f + __expf(-s[q]));
+        }
     }
 }
 
@@ -413,8 +436,10 @@ POSE_API int pose_se_gate(const float *pool_sum, int parts, float inv_hw, const 
                           int Cr, int act, float *gate, pose_stream_t stream) {
     if (!pool_sum || !W1 || !W2 || !gate) return POSE_E_NULL;
     if (B <= 0 || C <= 0 || Cr <= 0 || parts < 1) return POSE_E_SHAPE;
-    se_gate_kernel<<<B, 256, (size_t)(C + Cr) * sizeof(float), (cudaStream_t)stream>>>(pool_sum, parts, inv_hw, W1, W2, C, Cr,
-                                                                                      act, gate);
+    const size_t smem = (size_t)kSeSamples * (C + Cr) * sizeof(float);
+    if (smem > 48 * 1024) return POSE_E_UNSUPPORTED;
+    se_gate_kernel<<<(B + kSeSamples - 1) / kSeSamples, 256, smem, (cudaStream_t)stream>>>(pool_sum, parts, inv_hw, W1, W2, B,
+                                                                                          C, Cr, act, gate);
     return launch_status();
 }
 

@@ -8,13 +8,14 @@
 // convolution once activations are channels-last (NHWC makes a 1x1 conv exactly this GEMM with
 // M = B*H*W: src/models/cnn.py:122-131).
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
-//   warp 0   TMA producer: cp.async.bulk.tensor 2-D loads of A (128 x 64) and W (BN x 64) tiles into
-//            a kStages-deep 128B-swizzled shared-memory ring, completion on `full` mbarriers
-//   warp 1   TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) four
-//            times per stage; tcgen05.commit releases the stage (`empty`) and finally signals `acc_full`
-//   warps 2-5  epilogue: tcgen05.ld the fp32 accumulator (each warp owns its 32-lane TMEM quarter),
-//            bias + activation, convert, store
+// Structure (PERSISTENT: grid = min(tiles, 148), each CTA walks 128 x BN output tiles; 320 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor loads of A (128 x 64) and W (BN x 64) tiles into a kStages-deep
+//            128B-swizzled shared-memory ring (`full` / `empty` mbarriers); runs ahead across tile boundaries
+//   warp 1   TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) four times
+//            per stage; tcgen05.commit releases the stage and, after the last k-block, signals `acc_full[s]`
+//   warps 2-9  epilogue: the accumulator is DOUBLE BUFFERED in TMEM (2 x BN columns): tcgen05.ld the finished
+//            stage (two warps per 32-lane quarter split the column chunks), hand it back (`acc_empty[s]`) and do
+//            bias + activation + residual + convert + 16-byte stores while the next tile's MMAs already run
 // The same kernel is the implicit-GEMM convolution (MODE 1): the A tile of a k-block is one filter tap
 // x one channel chunk, fetched by a 4-D tiled TMA box over the NHWC activation (box = channels x TW x TH
 // output-pixel patch, element strides = conv stride, start = tap offset - padding; out-of-bounds
@@ -28,7 +29,6 @@
 
 namespace pose {
 
-constexpr int kGemmThreads = 192;
 constexpr int BM = 128;   // UMMA M (cta_group::1)
 constexpr int BK = 64;    // 64 bf16 = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
@@ -140,6 +140,7 @@ struct Epilogue {
     const __nv_bfloat16 *residual;   // [M, ldr] bf16 or null
     void *C;
     int ldc, ldr, act, out_bf16;
+    int vec;                         // 16-byte vector path allowed (bases and row pitches aligned; host-checked)
     float out_scale, res_scale;      // C = act(acc + bias) * out_scale + residual * res_scale
 };
 
@@ -161,37 +162,40 @@ struct GemmSmem {
     static_assert(kStageBytes % 1024 == 0, "stage bases must stay 1024 B aligned");
 };
 
+constexpr int kEpiWarps = 8;                              // two per TMEM lane quarter
+constexpr int kGemmThreadsP = 64 + kEpiWarps * 32;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+
+__device__ __forceinline__ float fast_act(float v, int act) {
+    switch (act) {
+        case 1: return fmaxf(v, 0.f);
+        case 2: return __fdividef(v, 1.0f + __expf(-v));
+        case 3: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+        case 4: return __fdividef(1.0f, 1.0f + __expf(-v));
+        default: return v;
+    }
+}
+
+// PERSISTENT kernel: grid = min(tiles, SMs); every CTA walks tiles t = blockIdx.x, += gridDim.x (N fastest so an A
+// tile is reused from L2 by its N neighbours).  The TMA ring runs ahead across tile boundaries, the accumulator is
+// double buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the MMAs of tile i + 1.
 template <int BN, int kStages, int BKC, int MODE>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreadsP, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N,
-                    int K, const Epilogue ep, const ConvGeom cg) {
+                    int K, const Epilogue ep, const ConvGeom cg, int m_tiles, int n_tiles) {
     using S = GemmSmem<BN, kStages, BKC>;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);  // swizzle atoms: 1024 B
     unsigned char *bars = smem + kStages * S::kStageBytes;
     uint64_t *full = (uint64_t *)bars;
     uint64_t *empty = full + kStages;
-    uint64_t *acc_full = empty + kStages;
-    uint32_t *tmem_slot = (uint32_t *)(acc_full + 1);
+    uint64_t *acc_full = empty + kStages;   // [2]
+    uint64_t *acc_empty = acc_full + 2;     // [2]
+    uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
     const int num_kb = (K + BKC - 1) / BKC;
-    constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;  // power of two >= 32
-
-    // M tile -> rows of C.  MODE 0: 128 consecutive rows.  MODE 1: a TH x TW patch of output pixels of one image.
-    int m0 = blockIdx.y * BM;
-    int img = 0, oh0 = 0, ow0 = 0;
-    if (MODE == 1) {
-        const int tiles_w = cg.Wo / cg.TW, tiles_h = cg.Ho / cg.TH;
-        int t = blockIdx.y;
-        const int tw = t % tiles_w;
-        t /= tiles_w;
-        const int th = t % tiles_h;
-        img = (t / tiles_h) * cg.TN;
-        oh0 = th * cg.TH;
-        ow0 = tw * cg.TW;
-    }
+    const int total_tiles = m_tiles * n_tiles;
+    constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // power of two >= 32 (BN in {32, 64, 128})
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -200,7 +204,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mbar_init(full + s, 1);
             mbar_init(empty + s, 1);
         }
-        mbar_init(acc_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(acc_full + s, 1);
+            mbar_init(acc_empty + s, kEpiWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -217,114 +224,162 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(empty + s, ph ^ 1);
-                unsigned char *sa = smem + s * S::kStageBytes, *sb = sa + S::kABytes;
-                mbar_expect_tx(full + s, S::kStageBytes);
-                if (MODE == 0) {
-                    tma_load_2d(sa, &map_a, full + s, kb * BKC, m0);
-                } else {
-                    const int tap = kb / cg.cchunks, cc = kb - tap * cg.cchunks;
-                    const int kh = tap / cg.KW, kw = tap - kh * cg.KW;
-                    tma_load_4d(sa, &map_a, full + s, cc * BKC, ow0 * cg.stride + kw * cg.dil - cg.pad,
-                                oh0 * cg.stride + kh * cg.dil - cg.pad, img);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BN;
+                int img = 0, oh0 = 0, ow0 = 0;
+                if (MODE == 1) {
+                    const int tiles_w = cg.Wo / cg.TW, tiles_h = cg.Ho / cg.TH;
+                    int t = mt;
+                    const int tw = t % tiles_w;
+                    t /= tiles_w;
+                    const int th = t % tiles_h;
+                    img = (t / tiles_h) * cg.TN;
+                    oh0 = th * cg.TH;
+                    ow0 = tw * cg.TW;
                 }
-                tma_load_2d(sb, &map_w, full + s, kb * BKC, n0);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1;
+                    mbar_wait(empty + s, ph ^ 1);
+                    unsigned char *sa = smem + s * S::kStageBytes, *sb = sa + S::kABytes;
+                    mbar_expect_tx(full + s, S::kStageBytes);
+                    if (MODE == 0) {
+                        tma_load_2d(sa, &map_a, full + s, kb * BKC, mt * BM);
+                    } else {
+                        const int tap = kb / cg.cchunks, cc = kb - tap * cg.cchunks;
+                        const int kh = tap / cg.KW, kw = tap - kh * cg.KW;
+                        tma_load_4d(sa, &map_a, full + s, cc * BKC, ow0 * cg.stride + kw * cg.dil - cg.pad,
+                                    oh0 * cg.stride + kh * cg.dil - cg.pad, img);
+                    }
+                    tma_load_2d(sb, &map_w, full + s, kb * BKC, n0);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % kStages;
-            const uint32_t ph = (kb / kStages) & 1;
-            mbar_wait(full + s, ph);
+        uint32_t it = 0, tile_iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+            const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
+            mbar_wait(acc_empty + as, aph ^ 1);   // the epilogue has drained this accumulator stage
             tc_fence_after();
-            if (elect_one()) {
-                const uint32_t sa = smem_u32(smem + s * S::kStageBytes), sb = sa + S::kABytes;
-                const uint64_t da = umma_desc_k<BKC * 2>(sa), db = umma_desc_k<BKC * 2>(sb);
+            const uint32_t tmem_acc = tmem_base + as * BN;
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(full + s, ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(smem + s * S::kStageBytes), sb = sa + S::kABytes;
+                    const uint64_t da = umma_desc_k<BKC * 2>(sa), db = umma_desc_k<BKC * 2>(sb);
 #pragma unroll
-                for (int k = 0; k < BKC / UMMA_K; ++k) {
-                    // advancing K by 16 bf16 = 32 B inside the swizzled row: +2 in the (>>4) address field
-                    tc_mma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < BKC / UMMA_K; ++k) {
+                        // advancing K by 16 bf16 = 32 B inside the swizzled row: +2 in the (>>4) address field
+                        tc_mma_f16(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    }
+                    tc_commit(empty + s);                          // frees the smem stage when these MMAs retire
+                    if (kb == num_kb - 1) tc_commit(acc_full + as);  // accumulator complete
                 }
-                tc_commit(empty + s);                      // frees the smem stage when these MMAs retire
-                if (kb == num_kb - 1) tc_commit(acc_full);  // accumulator complete
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        const int quarter = warp & 3;
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int r = quarter * 32 + lane;
-        long row;
-        bool row_ok;
-        if (MODE == 0) {
-            row = (long)m0 + r;
-            row_ok = row < M;
-        } else {
-            const int per_img = cg.TH * cg.TW;
-            const int dn = r / per_img, rr = r - dn * per_img;
-            const int dh = rr / cg.TW, dw = rr - dh * cg.TW;
-            row = ((long)(img + dn) * cg.Ho + oh0 + dh) * cg.Wo + ow0 + dw;
-            row_ok = img + dn < cg.Nimg;
-        }
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t acc[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), acc);
-            const int col0 = n0 + c * 32;
-            if (!row_ok || col0 >= N) continue;
-            const bool full_chunk = col0 + 32 <= N;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float x = __uint_as_float(acc[j]);
-                if (ep.bias != nullptr && (full_chunk || col0 + j < N)) x += __ldg(ep.bias + col0 + j);
-                v[j] = apply_act(x, ep.act) * ep.out_scale;
+        // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, the two warps of a quarter split the columns =====
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        uint32_t tile_iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+            const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
+            const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BN;
+            const int r = quarter * 32 + lane;
+            long row;
+            bool row_ok;
+            if (MODE == 0) {
+                row = (long)mt * BM + r;
+                row_ok = row < M;
+            } else {
+                const int tiles_w = cg.Wo / cg.TW, tiles_h = cg.Ho / cg.TH;
+                int t = mt;
+                const int tw = t % tiles_w;
+                t /= tiles_w;
+                const int th = t % tiles_h;
+                const int img = (t / tiles_h) * cg.TN;
+                const int per_img = cg.TH * cg.TW;
+                const int dn = r / per_img, rr = r - dn * per_img;
+                const int dh = rr / cg.TW, dw = rr - dh * cg.TW;
+                row = ((long)(img + dn) * cg.Ho + th * cg.TH + dh) * cg.Wo + tw * cg.TW + dw;
+                row_ok = img + dn < cg.Nimg;
             }
-            if (ep.residual != nullptr) {
-                const __nv_bfloat16 *rs = ep.residual + row * ep.ldr + col0;
-                if (full_chunk && (((uintptr_t)rs) & 15) == 0) {
+            mbar_wait(acc_full + as, aph);
+            tc_fence_after();
+            constexpr int kChunks = BN / 32;
+            uint32_t acc[(kChunks + 1) / 2][32];
+            // pull this warp's column chunks out of TMEM first, release the accumulator stage, then do the maths
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        const uint4 pk = __ldg((const uint4 *)(rs + j));
-                        const __nv_bfloat162 *h = (const __nv_bfloat162 *)&pk;
+            for (int ci = 0; ci < (kChunks + 1) / 2; ++ci) {
+                const int c = ci * 2 + half;
+                if (c < kChunks) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(c * 32), acc[ci]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float2 f = __bfloat1622float2(h[q]);
-                            v[j + 2 * q] += f.x * ep.res_scale;
-                            v[j + 2 * q + 1] += f.y * ep.res_scale;
+            for (int ci = 0; ci < (kChunks + 1) / 2; ++ci) {
+                const int c = ci * 2 + half;
+                const int col0 = n0 + c * 32;
+                if (c >= kChunks || !row_ok || col0 >= N) continue;
+                const bool full_chunk = col0 + 32 <= N;
+                if (full_chunk && ep.vec) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ep.bias != nullptr) bz = __ldg((const float4 *)(ep.bias + col0 + j));
+                        v[j] = fast_act(__uint_as_float(acc[ci][j]) + bz.x, ep.act) * ep.out_scale;
+                        v[j + 1] = fast_act(__uint_as_float(acc[ci][j + 1]) + bz.y, ep.act) * ep.out_scale;
+                        v[j + 2] = fast_act(__uint_as_float(acc[ci][j + 2]) + bz.z, ep.act) * ep.out_scale;
+                        v[j + 3] = fast_act(__uint_as_float(acc[ci][j + 3]) + bz.w, ep.act) * ep.out_scale;
+                    }
+                    if (ep.residual != nullptr) {
+                        const __nv_bfloat16 *rs = ep.residual + row * ep.ldr + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const uint4 pk = __ldg((const uint4 *)(rs + j));
+                            const __nv_bfloat162 *h = (const __nv_bfloat162 *)&pk;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 f = __bfloat1622float2(h[q]);
+                                v[j + 2 * q] += f.x * ep.res_scale;
+                                v[j + 2 * q + 1] += f.y * ep.res_scale;
+                            }
                         }
                     }
-                } else {
-                    for (int j = 0; j < 32 && col0 + j < N; ++j) v[j] += __bfloat162float(rs[j]) * ep.res_scale;
-                }
-            }
-            if (ep.out_bf16) {
-                __nv_bfloat16 *dst = (__nv_bfloat16 *)ep.C + row * ep.ldc + col0;
-                if (full_chunk && (((uintptr_t)dst) & 15) == 0) {
+                    if (ep.out_bf16) {
+                        __nv_bfloat16 *dst = (__nv_bfloat16 *)ep.C + row * ep.ldc + col0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                        uint4 pk = make_uint4(*(uint32_t *)&p0, *(uint32_t *)&p1, *(uint32_t *)&p2, *(uint32_t *)&p3);
-                        *(uint4 *)(dst + j) = pk;
+                        for (int j = 0; j < 32; j += 8) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            *(uint4 *)(dst + j) = make_uint4(*(uint32_t *)&p0, *(uint32_t *)&p1, *(uint32_t *)&p2, *(uint32_t *)&p3);
+                        }
+                    } else {
+                        float *dst = (float *)ep.C + row * ep.ldc + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *(float4 *)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     }
                 } else {
-                    for (int j = 0; j < 32 && col0 + j < N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
-                }
-            } else {
-                float *dst = (float *)ep.C + row * ep.ldc + col0;
-                if (full_chunk && (((uintptr_t)dst) & 15) == 0) {
+                    // ragged last chunk (N % 32 != 0) or unaligned rows: element-wise, predicated, fully unrolled
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *(float4 *)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-                    for (int j = 0; j < 32 && col0 + j < N; ++j) dst[j] = v[j];
+                    for (int j = 0; j < 32; ++j) {
+                        if (col0 + j < N) {
+                            float x = __uint_as_float(acc[ci][j]);
+                            if (ep.bias != nullptr) x += __ldg(ep.bias + col0 + j);
+                            x = fast_act(x, ep.act) * ep.out_scale;
+                            if (ep.residual != nullptr) x += __bfloat162float(ep.residual[row * ep.ldr + col0 + j]) * ep.res_scale;
+                            if (ep.out_bf16) ((__nv_bfloat16 *)ep.C)[row * ep.ldc + col0 + j] = __float2bfloat16_rn(x);
+                            else ((float *)ep.C)[row * ep.ldc + col0 + j] = x;
+                        }
+                    }
                 }
             }
         }
@@ -408,8 +463,10 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
         if (ce != cudaSuccess) return (int)ce;
         configured = true;
     }
-    dim3 grid((N + BN - 1) / BN, m_tiles);
-    kern<<<grid, kGemmThreads, S::kTotal, s>>>(ma, mw, M, N, K, ep, cg);
+    const int n_tiles = (N + BN - 1) / BN;
+    const long total = (long)m_tiles * n_tiles;
+    const int grid = (int)(total < kNumSMs ? total : kNumSMs);
+    kern<<<grid, kGemmThreadsP, S::kTotal, s>>>(ma, mw, M, N, K, ep, cg, m_tiles, n_tiles);
     return launch_status();
 }
 
@@ -429,6 +486,10 @@ static int check_epilogue(const pose_gemm_epilogue *e, int N, Epilogue &ep) {
     if (!e || !e->C) return POSE_E_NULL;
     if (e->ldc < N || (e->residual && e->ldr < N)) return POSE_E_SHAPE;
     if (e->act < 0 || e->act > 4 || (e->out_dtype != 0 && e->out_dtype != 1)) return POSE_E_UNSUPPORTED;
+    // the fast epilogue moves 16-byte vectors: needs aligned bases and row pitches, else element-wise stores
+    const int celt = e->out_dtype ? 2 : 4;
+    ep.vec = !((uintptr_t)e->C % 16 || ((long)e->ldc * celt) % 16 ||
+               (e->residual && ((uintptr_t)e->residual % 16 || (e->ldr * 2) % 16)) || (e->bias && (uintptr_t)e->bias % 16));
     ep.bias = e->bias;
     ep.residual = (const __nv_bfloat16 *)e->residual;
     ep.C = e->C;
