@@ -124,19 +124,28 @@ dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ 
         float acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = bs[k];
+        // all nine taps are fetched unconditionally from clamped coordinates (no branches between the loads, so
+        // they are all in flight together); out-of-image taps are zeroed afterwards
+        uint4 tap[9];
+        bool ok[9];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = oy * stride + ky - 1;
-            if (iy < 0 || iy >= H) continue;
+            const int cy = min(max(iy, 0), H - 1);
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const int ix = ox * stride + kx - 1;
-                if (ix < 0 || ix >= W) continue;
-                float f[8];
-                unpack8(__ldg((const uint4 *)(xb + ((long)iy * W + ix) * C + c0)), f);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], w[ky * 3 + kx][k], acc[k]);
+                const int cx = min(max(ix, 0), W - 1);
+                ok[ky * 3 + kx] = iy == cy && ix == cx;
+                tap[ky * 3 + kx] = __ldg((const uint4 *)(xb + ((long)cy * W + cx) * C + c0));
             }
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            float f[8];
+            unpack8(ok[t] ? tap[t] : make_uint4(0u, 0u, 0u, 0u), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], w[t][k], acc[k]);
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {

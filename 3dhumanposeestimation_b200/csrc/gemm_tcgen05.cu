@@ -13,8 +13,8 @@
 //            128B-swizzled shared-memory ring (`full` / `empty` mbarriers); runs ahead across tile boundaries
 //   warp 1   TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) four times
 //            per stage; tcgen05.commit releases the stage and, after the last k-block, signals `acc_full[s]`
-//   warps 2-9  epilogue: the accumulator is DOUBLE BUFFERED in TMEM (2 x BN columns): tcgen05.ld the finished
-//            stage (two warps per 32-lane quarter split the column chunks), hand it back (`acc_empty[s]`) and do
+//   warps 2-17 epilogue: the accumulator is DOUBLE BUFFERED in TMEM (2 x BN columns): tcgen05.ld the finished
+//            stage (four warps per 32-lane quarter split the column chunks), hand it back (`acc_empty[s]`) and do
 //            bias + activation + residual + convert + 16-byte stores while the next tile's MMAs already run
 // The same kernel is the implicit-GEMM convolution (MODE 1): the A tile of a k-block is one filter tap
 // x one channel chunk, fetched by a 4-D tiled TMA box over the NHWC activation (box = channels x TW x TH
@@ -158,20 +158,112 @@ struct GemmSmem {
     static constexpr int kABytes = BM * BKC * 2, kBBytes = BN * BKC * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarrierBytes = 256;
-    static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // + alignment slack
+    static constexpr int kStagePitch = 144;                      // 32 fp32 + 16 B pad: conflict-free 16 B accesses
+    static constexpr int kStagingBytes = 16 * 32 * kStagePitch;  // one 32 x 32 fp32 transpose buffer per epilogue warp
+    static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + kStagingBytes + 1024;  // + alignment slack
     static_assert(kStageBytes % 1024 == 0, "stage bases must stay 1024 B aligned");
 };
 
-constexpr int kEpiWarps = 8;                              // two per TMEM lane quarter
-constexpr int kGemmThreadsP = 64 + kEpiWarps * 32;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiWarps = 16;                             // four per TMEM lane quarter
+constexpr int kGemmThreadsP = 64 + kEpiWarps * 32;        // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 
-__device__ __forceinline__ float fast_act(float v, int act) {
-    switch (act) {
-        case 1: return fmaxf(v, 0.f);
-        case 2: return __fdividef(v, 1.0f + __expf(-v));
-        case 3: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-        case 4: return __fdividef(1.0f, 1.0f + __expf(-v));
-        default: return v;
+// explicit shared-space accesses (the staging pointer is carved out of the raw dynamic buffer, so the compiler
+// would otherwise emit generic LD / ST)
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
+
+// sigmoid(x) = 0.5 (1 + tanh(x / 2)): MUFU.TANH (rel. error ~2^-11, below bf16 resolution) instead of EX2 + RCP --
+// the epilogue of the small-K layers is bound by the 16 MUFU/clk/SM special-function unit
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int ACT>
+__device__ __forceinline__ float fast_act(float v) {
+    if (ACT == 1) return fmaxf(v, 0.f);
+    if (ACT == 2) return 0.5f * v * (1.0f + tanh_approx(0.5f * v));   // silu(x) = x * sigmoid(x), one MUFU
+    if (ACT == 3) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    if (ACT == 4) return 0.5f * (1.0f + tanh_approx(0.5f * v));       // sigmoid
+    return v;
+}
+
+// Phase 2 of the epilogue for one 32 x 32 chunk sitting in the warp's staging buffer (fp32, pitch kPitch):
+// 8 lanes per output row, 4 columns per lane.  The activation is a template parameter so that the loop body
+// stays small (a run-time switch per element made the unrolled epilogue overflow the instruction cache).
+template <int ACT, int kPitch>
+__device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, long row, int lane, int col,
+                                              int N) {
+    const int sub_r = lane >> 3, colq = (lane & 7) * 4;
+    float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.bias != nullptr) bz = __ldg((const float4 *)(ep.bias + col));
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const int tr = g * 4 + sub_r;                       // tile row within the quarter
+        const long grow = __shfl_sync(0xffffffffu, row, tr);
+        float4 x = lds128(stg + tr * kPitch + colq * 4);
+        if (grow < 0) continue;
+        x.x = fast_act<ACT>(x.x + bz.x) * ep.out_scale;
+        x.y = fast_act<ACT>(x.y + bz.y) * ep.out_scale;
+        x.z = fast_act<ACT>(x.z + bz.z) * ep.out_scale;
+        x.w = fast_act<ACT>(x.w + bz.w) * ep.out_scale;
+        if (ep.residual != nullptr) {
+            const uint2 pk = __ldg((const uint2 *)(ep.residual + grow * ep.ldr + col));
+            const float2 f0 = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.x);
+            const float2 f1 = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.y);
+            x.x += f0.x * ep.res_scale; x.y += f0.y * ep.res_scale;
+            x.z += f1.x * ep.res_scale; x.w += f1.y * ep.res_scale;
+        }
+        if (ep.out_bf16) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(x.x, x.y), p1 = __floats2bfloat162_rn(x.z, x.w);
+            *(uint2 *)((__nv_bfloat16 *)ep.C + grow * ep.ldc + col) = make_uint2(*(uint32_t *)&p0, *(uint32_t *)&p1);
+        } else {
+            *(float4 *)((float *)ep.C + grow * ep.ldc + col) = x;
+        }
+    }
+}
+
+// Ragged / unaligned variant (N % 4 != 0 at the edge, or unaligned pitches): element-wise, kept out of line.
+template <int kPitch>
+__device__ __forceinline__ void epilogue_rows_slow(uint32_t stg, const Epilogue &ep, long row, int lane,
+                                                   int col, int N) {
+    // (inlined so that `ep` stays in the constant bank -- taking its address would spill it to local memory --
+    //  but with rolled loops: this path only runs for ragged / unaligned edges)
+    const int sub_r = lane >> 3, colq = (lane & 7) * 4;
+#pragma unroll 1
+    for (int g = 0; g < 8; ++g) {
+        const int tr = g * 4 + sub_r;
+        const long grow = __shfl_sync(0xffffffffu, row, tr);
+        if (grow < 0) continue;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            if (col + q >= N) break;
+            float y = lds32(stg + tr * kPitch + (colq + q) * 4);
+            if (ep.bias != nullptr) y += __ldg(ep.bias + col + q);
+            switch (ep.act) {
+                case 1: y = fast_act<1>(y); break;
+                case 2: y = fast_act<2>(y); break;
+                case 3: y = fast_act<3>(y); break;
+                case 4: y = fast_act<4>(y); break;
+                default: break;
+            }
+            y *= ep.out_scale;
+            if (ep.residual != nullptr) y += __bfloat162float(ep.residual[grow * ep.ldr + col + q]) * ep.res_scale;
+            if (ep.out_bf16) ((__nv_bfloat16 *)ep.C)[grow * ep.ldc + col + q] = __float2bfloat16_rn(y);
+            else ((float *)ep.C)[grow * ep.ldc + col + q] = y;
+        }
     }
 }
 
@@ -191,6 +283,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint64_t *acc_full = empty + kStages;   // [2]
     uint64_t *acc_empty = acc_full + 2;     // [2]
     uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+    unsigned char *staging = bars + S::kBarrierBytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (K + BKC - 1) / BKC;
@@ -285,18 +378,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
     } else {
-        // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, the two warps of a quarter split the columns =====
-        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        // ===== epilogue: warps 2..17; TMEM lane quarter = warp % 4, the two warps of a quarter split the columns =====
+        // A warp's accumulator fragment is row-per-lane; storing that directly scatters every 16 B to a different
+        // 128 B line.  It is transposed through a private shared-memory buffer instead, so that bias / activation /
+        // residual / convert / store all run with 8 lanes per output row (4 full rows per instruction).
+        const int quarter = warp & 3, cgrp = (warp - 2) >> 2;   // cgrp 0..3: which column chunks this warp owns
+        const uint32_t stg = smem_u32(staging + (warp - 2) * 32 * S::kStagePitch);
+        const int colq = (lane & 7) * 4;  // phase-2 mapping: 8 lanes per row, 4 columns per lane
         uint32_t tile_iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
             const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
             const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BN;
             const int r = quarter * 32 + lane;
-            long row;
-            bool row_ok;
+            long row;       // global output row of tile row r (this lane's accumulator row)
             if (MODE == 0) {
                 row = (long)mt * BM + r;
-                row_ok = row < M;
+                if (row >= M) row = -1;
             } else {
                 const int tiles_w = cg.Wo / cg.TW, tiles_h = cg.Ho / cg.TH;
                 int t = mt;
@@ -308,79 +405,43 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int dn = r / per_img, rr = r - dn * per_img;
                 const int dh = rr / cg.TW, dw = rr - dh * cg.TW;
                 row = ((long)(img + dn) * cg.Ho + th * cg.TH + dh) * cg.Wo + tw * cg.TW + dw;
-                row_ok = img + dn < cg.Nimg;
+                if (img + dn >= cg.Nimg) row = -1;
             }
             mbar_wait(acc_full + as, aph);
             tc_fence_after();
             constexpr int kChunks = BN / 32;
-            uint32_t acc[(kChunks + 1) / 2][32];
-            // pull this warp's column chunks out of TMEM first, release the accumulator stage, then do the maths
+            constexpr int kMine = (kChunks + 3) / 4;          // chunks per warp: c = cgrp + 4 * ci
+            uint32_t acc[kMine][32];
 #pragma unroll
-            for (int ci = 0; ci < (kChunks + 1) / 2; ++ci) {
-                const int c = ci * 2 + half;
+            for (int ci = 0; ci < kMine; ++ci) {
+                const int c = cgrp + 4 * ci;
                 if (c < kChunks) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(c * 32), acc[ci]);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
 #pragma unroll
-            for (int ci = 0; ci < (kChunks + 1) / 2; ++ci) {
-                const int c = ci * 2 + half;
+            for (int ci = 0; ci < kMine; ++ci) {
+                const int c = cgrp + 4 * ci;
                 const int col0 = n0 + c * 32;
-                if (c >= kChunks || !row_ok || col0 >= N) continue;
-                const bool full_chunk = col0 + 32 <= N;
-                if (full_chunk && ep.vec) {
-                    float v[32];
+                if (c >= kChunks || col0 >= N) continue;   // warp-uniform
+                // phase 1: raw fp32 accumulators, row-per-lane -> staging
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (ep.bias != nullptr) bz = __ldg((const float4 *)(ep.bias + col0 + j));
-                        v[j] = fast_act(__uint_as_float(acc[ci][j]) + bz.x, ep.act) * ep.out_scale;
-                        v[j + 1] = fast_act(__uint_as_float(acc[ci][j + 1]) + bz.y, ep.act) * ep.out_scale;
-                        v[j + 2] = fast_act(__uint_as_float(acc[ci][j + 2]) + bz.z, ep.act) * ep.out_scale;
-                        v[j + 3] = fast_act(__uint_as_float(acc[ci][j + 3]) + bz.w, ep.act) * ep.out_scale;
-                    }
-                    if (ep.residual != nullptr) {
-                        const __nv_bfloat16 *rs = ep.residual + row * ep.ldr + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            const uint4 pk = __ldg((const uint4 *)(rs + j));
-                            const __nv_bfloat162 *h = (const __nv_bfloat162 *)&pk;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float2 f = __bfloat1622float2(h[q]);
-                                v[j + 2 * q] += f.x * ep.res_scale;
-                                v[j + 2 * q + 1] += f.y * ep.res_scale;
-                            }
-                        }
-                    }
-                    if (ep.out_bf16) {
-                        __nv_bfloat16 *dst = (__nv_bfloat16 *)ep.C + row * ep.ldc + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                            *(uint4 *)(dst + j) = make_uint4(*(uint32_t *)&p0, *(uint32_t *)&p1, *(uint32_t *)&p2, *(uint32_t *)&p3);
-                        }
-                    } else {
-                        float *dst = (float *)ep.C + row * ep.ldc + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) *(float4 *)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    }
-                } else {
-                    // ragged last chunk (N % 32 != 0) or unaligned rows: element-wise, predicated, fully unrolled
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (col0 + j < N) {
-                            float x = __uint_as_float(acc[ci][j]);
-                            if (ep.bias != nullptr) x += __ldg(ep.bias + col0 + j);
-                            x = fast_act(x, ep.act) * ep.out_scale;
-                            if (ep.residual != nullptr) x += __bfloat162float(ep.residual[row * ep.ldr + col0 + j]) * ep.res_scale;
-                            if (ep.out_bf16) ((__nv_bfloat16 *)ep.C)[row * ep.ldc + col0 + j] = __float2bfloat16_rn(x);
-                            else ((float *)ep.C)[row * ep.ldc + col0 + j] = x;
-                        }
-                    }
+                for (int j = 0; j < 32; j += 4)
+                    sts128(stg + lane * S::kStagePitch + j * 4, acc[ci][j], acc[ci][j + 1], acc[ci][j + 2], acc[ci][j + 3]);
+                __syncwarp();
+                // phase 2: 8 lanes per row (warp-uniform dispatch on the activation)
+                const int col = col0 + colq;
+                const bool fast = ep.vec && col0 + 32 <= N;   // warp-uniform
+                if (!fast) epilogue_rows_slow<S::kStagePitch>(stg, ep, row, lane, col, N);
+                else switch (ep.act) {
+                    case 0: epilogue_rows<0, S::kStagePitch>(stg, ep, row, lane, col, N); break;
+                    case 1: epilogue_rows<1, S::kStagePitch>(stg, ep, row, lane, col, N); break;
+                    case 2: epilogue_rows<2, S::kStagePitch>(stg, ep, row, lane, col, N); break;
+                    case 3: epilogue_rows<3, S::kStagePitch>(stg, ep, row, lane, col, N); break;
+                    default: epilogue_rows<4, S::kStagePitch>(stg, ep, row, lane, col, N); break;
                 }
+                __syncwarp();   // staging is rewritten by the next chunk
             }
         }
     }
@@ -477,9 +538,9 @@ static int dispatch_bn(const CUtensorMap &ma, const void *W, int ldw, int M, int
     const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
     int e = make_map_2d(&mw, W, N, K, ldw, bn, BKC);
     if (e) return e;
-    if (bn == 32) return launch_gemm<32, 8, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
-    if (bn == 64) return launch_gemm<64, 8, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
-    return launch_gemm<128, 6, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
+    if (bn == 32) return launch_gemm<32, 6, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
+    if (bn == 64) return launch_gemm<64, 6, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
+    return launch_gemm<128, 4, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
 }
 
 static int check_epilogue(const pose_gemm_epilogue *e, int N, Epilogue &ep) {
