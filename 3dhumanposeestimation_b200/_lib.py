@@ -56,6 +56,7 @@ SIGNATURES = {
     "pose_cnn_input_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "pose_dwconv3x3_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                     c_void_p, c_int, c_void_p]),
+    "pose_dwconv3x3_pool_parts": (c_int, [c_int, c_int, c_int]),
     "pose_pool_sum_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "pose_se_gate": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                              c_void_p]),

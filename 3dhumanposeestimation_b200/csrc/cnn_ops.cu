@@ -83,89 +83,95 @@ cnn_input_pack_kernel(const float *__restrict__ image, const float *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Depthwise 3x3 conv (pad 1, stride 1 or 2) + folded BatchNorm + activation, NHWC bf16, 8 channels per thread.
-// Optionally emits per-(image, chunk, channel) partial sums of the OUTPUT (the squeeze of SE / ECA,
-// cnn.py:22-23,40-41): pool [B, chunks, C], written (not accumulated) and reduced in a fixed order, so the
-// result is deterministic.  grid.x = B * chunks (a CTA stays inside one image), grid.y = channel slabs.
+// Depthwise 3x3 conv (pad 1, stride 1 or 2) + folded BatchNorm + activation, NHWC bf16.
+// A CTA owns an output tile of TH x TW pixels and a slab of 64 channels: the input halo tile is staged in shared
+// memory once with coalesced 16-byte loads (each input element crosses HBM/L2 once per tile instead of nine
+// times), then every thread computes 8 channels of several output pixels from shared memory with its 72 filter
+// taps in registers.  Optionally emits per-(image, tile, channel) partial sums of the OUTPUT (the squeeze of
+// SE / ECA, cnn.py:22-23,40-41): pool [B, tiles_per_image, C], written -- not accumulated -- and reduced by the
+// consumers in a fixed order, so the result is deterministic.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kDwSlab = 64;  // channels per CTA
+
+template <int STRIDE>
+struct DwTile {
+    static constexpr int TH = STRIDE == 1 ? 8 : 4, TW = STRIDE == 1 ? 16 : 8;     // output tile
+    static constexpr int IH = (TH - 1) * STRIDE + 3, IW = (TW - 1) * STRIDE + 3;  // input halo tile
+    static constexpr int kSmem = IH * IW * kDwSlab * 2;
+};
+
+template <int STRIDE>
 __global__ void __launch_bounds__(256)
 dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ Wd, const float *__restrict__ bias,
-                 int H, int W, int C, int stride, int act, __nv_bfloat16 *__restrict__ Y, float *__restrict__ pool,
-                 int Ho, int Wo, int chunks, int CG) {
-    extern __shared__ float s_w[];  // [9][CG*8] weights + [CG*8] bias for this channel slab
-    const int slab_c0 = blockIdx.y * CG * 8;
-    const int slab_c = min(CG * 8, C - slab_c0);
-    for (int i = threadIdx.x; i < 9 * CG * 8; i += 256) {
-        const int t = i / (CG * 8), c = i - t * (CG * 8);
-        s_w[i] = c < slab_c ? __ldg(Wd + (long)t * C + slab_c0 + c) : 0.f;
-    }
-    for (int i = threadIdx.x; i < CG * 8; i += 256) s_w[9 * CG * 8 + i] = i < slab_c ? __ldg(bias + slab_c0 + i) : 0.f;
-    __syncthreads();
-    const int cg_lane = threadIdx.x % CG, plane = threadIdx.x / CG, planes = 256 / CG;
-    const int c0 = slab_c0 + cg_lane * 8;
-    const bool active = c0 < C;
-    const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-    const int npx = Ho * Wo;
-    const int per = (npx + chunks - 1) / chunks;
-    const int p_begin = chunk * per, p_end = min(npx, p_begin + per);
+                 int H, int W, int C, int act, __nv_bfloat16 *__restrict__ Y, float *__restrict__ pool, int Ho, int Wo,
+                 int tiles_x, int tiles_y) {
+    using T = DwTile<STRIDE>;
+    __shared__ __align__(16) unsigned char s_in[T::kSmem];
+    __shared__ float s_part[32][kDwSlab];
+    const int tile = blockIdx.x % (tiles_x * tiles_y), b = blockIdx.x / (tiles_x * tiles_y);
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int oy0 = ty * T::TH, ox0 = tx * T::TW;
+    const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
+    const int c_slab = blockIdx.y * kDwSlab;
+    const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;       // 8 channel groups x 32 pixel lanes
+    const int c0 = c_slab + cg * 8;
+    const bool c_ok = c0 < C;
     const __nv_bfloat16 *xb = X + (long)b * H * W * C;
+    // stage the halo tile: pixel-major, 128 B (64 channels) per pixel, zero outside the image / channel range
+    for (int i = threadIdx.x; i < T::IH * T::IW * 8; i += 256) {
+        const int px = i >> 3, g = i & 7;
+        const int py = px / T::IW, pxx = px - py * T::IW;
+        const int iy = iy0 + py, ix = ix0 + pxx;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W && c_slab + g * 8 < C)
+            v = __ldg((const uint4 *)(xb + ((long)iy * W + ix) * C + c_slab + g * 8));
+        *(uint4 *)(s_in + (px * 8 + g) * 16) = v;
+    }
     float w[9][8], bs[8], psum[8];
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) w[t][k] = s_w[t * CG * 8 + cg_lane * 8 + k];
-#pragma unroll
     for (int k = 0; k < 8; ++k) {
-        bs[k] = s_w[9 * CG * 8 + cg_lane * 8 + k];
+        bs[k] = c_ok ? __ldg(bias + c0 + k) : 0.f;
         psum[k] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w[t][k] = c_ok ? __ldg(Wd + (long)t * C + c0 + k) : 0.f;
     }
-    for (int p = p_begin + plane; active && p < p_end; p += planes) {
-        const int oy = p / Wo, ox = p - oy * Wo;
+    __syncthreads();
+    constexpr int kPix = T::TH * T::TW;
+#pragma unroll
+    for (int q = 0; q < kPix / 32; ++q) {
+        const int p = q * 32 + pl;
+        const int py = p / T::TW, pxx = p - py * T::TW;
+        const int oy = oy0 + py, ox = ox0 + pxx;
         float acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = bs[k];
-        // all nine taps are fetched unconditionally from clamped coordinates (no branches between the loads, so
-        // they are all in flight together); out-of-image taps are zeroed afterwards
-        uint4 tap[9];
-        bool ok[9];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = oy * stride + ky - 1;
-            const int cy = min(max(iy, 0), H - 1);
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const int ix = ox * stride + kx - 1;
-                const int cx = min(max(ix, 0), W - 1);
-                ok[ky * 3 + kx] = iy == cy && ix == cx;
-                tap[ky * 3 + kx] = __ldg((const uint4 *)(xb + ((long)cy * W + cx) * C + c0));
+                float f[8];
+                unpack8(*(const uint4 *)(s_in + (((py * STRIDE + ky) * T::IW + pxx * STRIDE + kx) * 8 + cg) * 16), f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], w[ky * 3 + kx][k], acc[k]);
             }
-        }
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            float f[8];
-            unpack8(ok[t] ? tap[t] : make_uint4(0u, 0u, 0u, 0u), f);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], w[t][k], acc[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            acc[k] = act_f(acc[k], act);
-            psum[k] += acc[k];
-        }
-        *(uint4 *)(Y + ((long)b * npx + p) * C + c0) = pack8(acc);
-    }
-    if (pool != nullptr) {  // fixed-order reduction over the pixel planes of the CTA, one write per channel
-        __shared__ float s_part[256 * 8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s_part[(plane * CG + cg_lane) * 8 + k] = psum[k];
-        __syncthreads();
-        if (plane == 0 && active) {
+        if (oy < Ho && ox < Wo && c_ok) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                float t = 0.f;
-                for (int q = 0; q < planes; ++q) t += s_part[(q * CG + cg_lane) * 8 + k];
-                pool[((long)b * chunks + chunk) * C + c0 + k] = t;
+                acc[k] = act_f(acc[k], act);
+                psum[k] += acc[k];
             }
+            *(uint4 *)(Y + (((long)b * Ho + oy) * Wo + ox) * C + c0) = pack8(acc);
+        }
+    }
+    if (pool != nullptr) {  // fixed-order reduction over the 32 pixel lanes of the CTA, one write per channel
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_part[pl][cg * 8 + k] = psum[k];
+        __syncthreads();
+        if (threadIdx.x < kDwSlab && c_slab + threadIdx.x < C) {
+            float t = 0.f;
+#pragma unroll 8
+            for (int q = 0; q < 32; ++q) t += s_part[q][threadIdx.x];
+            pool[((long)b * (tiles_x * tiles_y) + tile) * C + c_slab + threadIdx.x] = t;
         }
     }
 }
@@ -407,29 +413,31 @@ POSE_API int pose_cnn_input_pack(const float *image, const float *depth, const f
     return launch_status();
 }
 
+POSE_API int pose_dwconv3x3_pool_parts(int H, int W, int stride) {
+    if (H <= 0 || W <= 0 || (stride != 1 && stride != 2)) return POSE_E_SHAPE;
+    const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+    const int th = stride == 1 ? DwTile<1>::TH : DwTile<2>::TH, tw = stride == 1 ? DwTile<1>::TW : DwTile<2>::TW;
+    return ((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
+}
+
 POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, const float *Wd, const float *bias, int stride,
                                  int act, void *Y, float *pool_sum, int pool_parts, pose_stream_t stream) {
     if (!X || !Wd || !bias || !Y) return POSE_E_NULL;
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 || (stride != 1 && stride != 2)) return POSE_E_SHAPE;
     if ((uintptr_t)X % 16 || (uintptr_t)Y % 16) return POSE_E_ALIGN;
     const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-    int CG = C / 8;
-    if (CG > 32) CG = 32;
-    while (256 % CG) --CG;  // channel groups per CTA must divide the CTA
-    const int slabs = (C / 8 + CG - 1) / CG;
-    // enough CTAs to fill the chip, but every CTA stays inside one image (squeeze sums are per image)
-    int chunks = (kNumSMs * 8 + B * slabs - 1) / (B * slabs);
-    const int npx = Ho * Wo, planes = 256 / CG;
-    if (chunks > (npx + planes - 1) / planes) chunks = (npx + planes - 1) / planes;
-    if (chunks < 1) chunks = 1;
-    if (pool_sum != nullptr) {
-        if (pool_parts < 1) return POSE_E_SHAPE;
-        chunks = pool_parts;  // the caller sized pool_sum as [B, pool_parts, C]
-    }
-    const size_t smem = (size_t)(10 * CG * 8) * sizeof(float);
-    dim3 grid(B * chunks, slabs);
-    dwconv3x3_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, Wd, bias, H, W, C, stride, act,
-                                                               (__nv_bfloat16 *)Y, pool_sum, Ho, Wo, chunks, CG);
+    const int parts = pose_dwconv3x3_pool_parts(H, W, stride);
+    if (pool_sum != nullptr && pool_parts != parts) return POSE_E_SHAPE;  // pool_sum is [B, parts, C]
+    const int th = stride == 1 ? DwTile<1>::TH : DwTile<2>::TH, tw = stride == 1 ? DwTile<1>::TW : DwTile<2>::TW;
+    const int tiles_y = (Ho + th - 1) / th, tiles_x = (Wo + tw - 1) / tw;
+    dim3 grid(B * tiles_x * tiles_y, (C + kDwSlab - 1) / kDwSlab);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (stride == 1)
+        dwconv3x3_kernel<1><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)X, Wd, bias, H, W, C, act, (__nv_bfloat16 *)Y, pool_sum,
+                                                 Ho, Wo, tiles_x, tiles_y);
+    else
+        dwconv3x3_kernel<2><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)X, Wd, bias, H, W, C, act, (__nv_bfloat16 *)Y, pool_sum,
+                                                 Ho, Wo, tiles_x, tiles_y);
     return launch_status();
 }
 

@@ -348,7 +348,7 @@ class CnnInferencePlan:
         Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
         out = self._buf(Bn, Ho, Wo, ch)
         a = self.act if cba.activation is not None else 0
-        pool = self._buf(Bn, self._parts(Ho * Wo), ch, dtype=torch.float32) if want_pool else None
+        pool = self._buf(Bn, self.lib.pose_dwconv3x3_pool_parts(H, W, stride), ch, dtype=torch.float32) if want_pool else None
         self._launch("pose_dwconv3x3_bf16", x.data_ptr(), Bn, H, W, ch, wd.data_ptr(), b32.data_ptr(), stride, a,
                      out.data_ptr(), pool.data_ptr() if pool is not None else None,
                      pool.shape[1] if pool is not None else 0)
@@ -370,11 +370,20 @@ class CnnInferencePlan:
             parts = pool.shape[1]
             gate = self._buf(Bn, ch, dtype=torch.float32)
             if isinstance(att, SEBlock):
+                # both Linear layers as tcgen05 GEMMs over the whole batch (M = B): the hidden width is zero-padded
+                # to one 64-wide K block
                 w1, w2 = att.fc[0].weight, att.fc[2].weight
-                w1f, w2f = self._buf(*w1.shape, dtype=torch.float32), self._buf(*w2.shape, dtype=torch.float32)
-                self.weights.append(lambda: (w1f.copy_(w1.detach()), w2f.copy_(w2.detach())))
-                self._launch("pose_se_gate", pool.data_ptr(), parts, 1.0 / (H * W), w1f.data_ptr(), w2f.data_ptr(), Bn, ch,
-                             w1.shape[0], activation_id(att.activation), gate.data_ptr())
+                cr = w1.shape[0]
+                crp = (cr + 63) // 64 * 64
+                w1p, w2p = self._buf(crp, ch, zero=True), self._buf(ch, crp, zero=True)
+                self.weights.append(lambda: (w1p[:cr].copy_(w1.detach()), w2p[:, :cr].copy_(w2.detach())))
+                mean16 = self._buf(Bn, ch)
+                self._launch("pose_sums_to_bf16", pool.data_ptr(), parts, Bn, ch, 1.0 / (H * W), mean16.data_ptr())
+                hid = self._buf(Bn, crp)
+                e1 = self._epi(hid, crp, None, activation_id(att.activation))
+                self._launch("pose_gemm_bf16_ex", mean16.data_ptr(), ch, w1p.data_ptr(), ch, Bn, crp, ch, C.byref(e1))
+                e2 = self._epi(gate, ch, None, 4, fp32=True)
+                self._launch("pose_gemm_bf16_ex", hid.data_ptr(), crp, w2p.data_ptr(), crp, Bn, ch, crp, C.byref(e2))
             else:
                 k = att.conv.weight.shape[-1]
                 wk = self._buf(k, dtype=torch.float32)

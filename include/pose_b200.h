@@ -156,8 +156,9 @@ int pose_conv2d_bf16(const void *X, int Nimg, int H, int W, int Cin, const void 
  *  pose_cnn_input_pack   cat([image, depth, heatmaps], 1) (cnn.py:644-648) written as the conv1 operand
  *                        [B,S,S,32] bf16 = {R,G,B,depth, J heat-maps, zero pad}; heat-maps rendered in flight
  *  pose_dwconv3x3_bf16   depthwise 3x3, pad 1, stride 1|2 + per-channel bias (folded BN) + act; Wd [3,3,C]
- *                        fp32; pool_sum [B,pool_parts,C] fp32 (optional): partial sums of the OUTPUT per image
- *                        chunk (SE/ECA squeeze), written -- consumers add the parts in order (deterministic)
+ *                        fp32; pool_sum [B,pool_parts,C] fp32 (optional): partial sums of the OUTPUT per output
+ *                        tile (SE/ECA squeeze), pool_parts = pose_dwconv3x3_pool_parts(H, W, stride); written,
+ *                        not accumulated -- consumers add the parts in order (deterministic)
  *  pose_pool_sum_bf16    sums [B,parts,C] fp32 = partial sums over pixel chunks of X [B,HW,C]
  *  pose_se_gate          SEBlock (cnn.py:9-26): gate = sigmoid(W2 . act(W1 . (pool_sum*inv_hw)))
  *  pose_eca_gate         ECABlock (cnn.py:29-45): gate = sigmoid(conv1d_k(mean)); feat_out (optional,
@@ -170,6 +171,7 @@ int pose_conv2d_bf16(const void *X, int Nimg, int H, int W, int Cin, const void 
  * ------------------------------------------------------------------------------------------- */
 int pose_cnn_input_pack(const float *image, const float *depth, const float *kp, int B, int S, int J, float sigma,
                         void *out, pose_stream_t stream);
+int pose_dwconv3x3_pool_parts(int H, int W, int stride); /* partial-sum slots per image the kernel writes */
 int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, const float *Wd, const float *bias, int stride,
                         int act, void *Y, float *pool_sum, int pool_parts, pose_stream_t stream);
 int pose_pool_sum_bf16(const void *X, int B, int HW, int C, float *sums, int parts, pose_stream_t stream);

@@ -80,7 +80,7 @@ def test_dwconv_gates_pools_match_fp32_reference(pose):
         ref = F.silu(F.conv2d(x.float().permute(0, 3, 1, 2), wd, bias, stride, 1, groups=Cc)).permute(0, 2, 3, 1)
         Ho = ref.shape[1]
         y = torch.empty(B, Ho, Ho, Cc, device=DEV, dtype=torch.bfloat16)
-        parts = 5
+        parts = lib.pose_dwconv3x3_pool_parts(H, H, stride)
         pool = torch.full((B, parts, Cc), float("nan"), device=DEV)    # written, not accumulated
         wk = wd.view(Cc, 9).t().contiguous()
         pose._lib.check(lib.pose_dwconv3x3_bf16(x.data_ptr(), B, H, H, Cc, wk.data_ptr(), bias.data_ptr(), stride, 2,
