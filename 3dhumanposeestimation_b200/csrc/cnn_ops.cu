@@ -6,7 +6,7 @@
 
 namespace pose {
 
-__device__ __forceinline__ float act_f(float v, int act) {
+__device__ __forceinline__ float act_f(float v, int act) {   // run-time activation (small kernels only)
     switch (act) {
         case 1: return v > 0.f ? v : 0.f;
         case 2: return v / (1.0f + __expf(-v));
@@ -14,6 +14,21 @@ __device__ __forceinline__ float act_f(float v, int act) {
         case 4: return 1.0f / (1.0f + __expf(-v));
         default: return v;
     }
+}
+
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// compile-time activation for the bandwidth kernels: silu / sigmoid through one MUFU.TANH
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+    if (ACT == 1) return fmaxf(v, 0.f);
+    if (ACT == 2) return 0.5f * v * (1.0f + tanh_approx(0.5f * v));
+    if (ACT == 3) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    if (ACT == 4) return 0.5f * (1.0f + tanh_approx(0.5f * v));
+    return v;
 }
 
 __device__ __forceinline__ void unpack8(const uint4 &p, float (&f)[8]) {
@@ -100,10 +115,10 @@ struct DwTile {
     static constexpr int kSmem = IH * IW * kDwSlab * 2;
 };
 
-template <int STRIDE>
+template <int STRIDE, int ACT>
 __global__ void __launch_bounds__(256)
 dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ Wd, const float *__restrict__ bias,
-                 int H, int W, int C, int act, __nv_bfloat16 *__restrict__ Y, float *__restrict__ pool, int Ho, int Wo,
+                 int H, int W, int C, __nv_bfloat16 *__restrict__ Y, float *__restrict__ pool, int Ho, int Wo,
                  int tiles_x, int tiles_y) {
     using T = DwTile<STRIDE>;
     __shared__ __align__(16) unsigned char s_in[T::kSmem];
@@ -157,7 +172,7 @@ dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ 
         if (oy < Ho && ox < Wo && c_ok) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                acc[k] = act_f(acc[k], act);
+                acc[k] = act_t<ACT>(acc[k]);
                 psum[k] += acc[k];
             }
             *(uint4 *)(Y + (((long)b * Ho + oy) * Wo + ox) * C + c0) = pack8(acc);
@@ -432,12 +447,21 @@ POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, cons
     const int tiles_y = (Ho + th - 1) / th, tiles_x = (Wo + tw - 1) / tw;
     dim3 grid(B * tiles_x * tiles_y, (C + kDwSlab - 1) / kDwSlab);
     cudaStream_t s = (cudaStream_t)stream;
-    if (stride == 1)
-        dwconv3x3_kernel<1><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)X, Wd, bias, H, W, C, act, (__nv_bfloat16 *)Y, pool_sum,
-                                                 Ho, Wo, tiles_x, tiles_y);
-    else
-        dwconv3x3_kernel<2><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)X, Wd, bias, H, W, C, act, (__nv_bfloat16 *)Y, pool_sum,
-                                                 Ho, Wo, tiles_x, tiles_y);
+    if (act < 0 || act > 4) return POSE_E_UNSUPPORTED;
+#define DW_LAUNCH(S_, A_)                                                                                             \
+    dwconv3x3_kernel<S_, A_><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)X, Wd, bias, H, W, C, (__nv_bfloat16 *)Y, pool_sum, \
+                                                  Ho, Wo, tiles_x, tiles_y)
+#define DW_ACT(S_)                                                                                                    \
+    switch (act) {                                                                                                    \
+        case 0: DW_LAUNCH(S_, 0); break;                                                                              \
+        case 1: DW_LAUNCH(S_, 1); break;                                                                              \
+        case 2: DW_LAUNCH(S_, 2); break;                                                                              \
+        case 3: DW_LAUNCH(S_, 3); break;                                                                              \
+        default: DW_LAUNCH(S_, 4); break;                                                                             \
+    }
+    if (stride == 1) { DW_ACT(1) } else { DW_ACT(2) }
+#undef DW_ACT
+#undef DW_LAUNCH
     return launch_status();
 }
 

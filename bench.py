@@ -8,6 +8,8 @@ N > 1 is launched by torchrun (one rank per GPU).  Rank 0 prints ONE JSON line.
 Workloads (BASELINE.json configs):
   preproc_b256   configs[1]: PoseAugmentor + heat-map / regression head + composite loss kernels,
                  batch 256 of 256x256 RGB-D per GPU.  One step = one pass of that chain over one batch.
+The same line also carries `cnn_infer`: the eval-mode CNNPoseEstimation forward (configs[4], batch sweep) on the
+tcgen05 path, as measured evidence for rows D/H of SURVEY.md 8a (the training step, configs[2..3], is not built yet).
 """
 from __future__ import annotations
 
@@ -192,7 +194,8 @@ def run_b200(args):
     from importlib import import_module
     ops = import_module("3dhumanposeestimation_b200.ops")
 
-    inp = make_inputs(rank)
+    dutil = import_module("3dhumanposeestimation_b200.dist")
+    inp = make_inputs(rank)          # weak scaling: every rank owns its own B samples, nothing is exchanged
     aug = pose.PoseAugmentor()
     params = draw_params(aug, B)
     crit = pose.ComprehensivePoseLoss()
@@ -246,12 +249,9 @@ def run_b200(args):
     ms_total = t_start.elapsed_time(t_end)
     if aug.kernel_error_flag() != 0:
         raise RuntimeError("augment kernel reported a launch-geometry error")
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    value = dutil.job_throughput(B * args.steps, ms_total, dev)   # all ranks' samples / slowest rank's device time
+    ms_total = dutil.max_over_ranks(ms_total, dev)
     ms_per_step = ms_total / args.steps
-    value = world * B * args.steps / (ms_total * 1e-3)
 
     kern_ms = {k: float(np.mean([v[i][0].elapsed_time(v[i][1]) for i in v])) for k, v in ev.items()}
 
@@ -291,10 +291,9 @@ def run_b200(args):
     e1.record(stream)
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+    e2e_value = dutil.job_throughput(B * args.steps, e2e_ms, dev)
+
+    cnn = measure_cnn_infer(pose, dev, rank) if args.cnn else None
 
     if rank == 0:
         peaks = {}
@@ -303,11 +302,12 @@ def run_b200(args):
         except Exception:
             pass
         hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        # dominant kernel by bytes and time: the heat-map render (J*hs*hs*4 B written + 8*J B read per sample)
-        hm_bytes = B * (J * HS * HS * 4 + J * 8)
-        achieved = hm_bytes / (kern_ms["heatmap"] * 1e-3) / 1e9
+        # dominant kernel group by time: the fused augmentation (pack + tables + cluster kernel).  Algorithmic bytes
+        # (SURVEY.md 8d): 16 B/px fp32 in + 16 B per OUTPUT px + key-points/joints; padding writes are not counted.
         sizes = a["sizes"].cpu().numpy().astype(np.int64)
         aug_bytes = int(B * (16 * H * W) + 16 * int((sizes[:, 0] * sizes[:, 1]).sum()) + B * J * 20 * 2)
+        achieved = aug_bytes / (kern_ms["augment"] * 1e-3) / 1e9
+        hm_bytes = B * (J * HS * HS * 4 + J * 8)
         cpu_n = 256
         cores = os.cpu_count() or 1
         cpu_chain_samples_per_s(32, cores, inp)  # warm-up (page-in, thread pool)
@@ -330,16 +330,82 @@ def run_b200(args):
             "kernel_ms": kern_ms,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 20,
                     "note": "fp32 pinned host batch (reference sample schema) -> device every step, double-buffered"},
-            "roofline": {"kernel": "heatmap_planes_kernel<float>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "others": {"augment(pack+tables+fused)": {"bytes": aug_bytes, "GB/s": aug_bytes / (kern_ms["augment"] * 1e-3) / 1e9},
-                                    "loss": {"bytes": B * 632, "ms": kern_ms["loss"]}, "head": {"ms": kern_ms["head"]}}},
+            "roofline": {"kernel": "pose_augment_batch: aug_pack + aug_tables + aug_fused_kernel<5> (dominant by time)",
+                         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": 67.8e6 + 331.2e6 + 335e6, "traffic_note": "ncu dram bytes r+w per launch: fused 399 MB + pack 335 MB "
+                         "(profiles/r01_*.csv); algorithmic bytes per launch = bytes below",
+                         "bytes_per_launch": aug_bytes, "peak_source": peak_src,
+                         "others": {"heatmap_planes_kernel<float>": {"bytes": hm_bytes, "GB/s": hm_bytes / (kern_ms["heatmap"] * 1e-3) / 1e9,
+                                                                   "frac": hm_bytes / (kern_ms["heatmap"] * 1e-3) / 1e9 / hbm_peak},
+                                    "loss": {"bytes": B * 632, "ms": kern_ms["loss"], "note": "latency bound at B=256"},
+                                    "head (3 tcgen05 GEMMs + cast)": {"ms": kern_ms["head"]}}},
+            "cnn_infer": cnn,
             "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": f"{reps} x the same B=256 batch ({cpu_dt:.1f} s wall, {cpu_dt * cores:.0f} core-s), oracle port (C) on all host threads"},
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_cnn_infer(pose, dev, rank, batches=(1, 8, 32, 128, 256, 512), reps=10):
+    """Eval-mode CNNPoseEstimation forward at 256x256 (BASELINE configs[4]): samples/s per batch size, CUDA events."""
+    import torch
+    cfg = pose.ModelConfig("cnn", image_size=(H, W), heatmap_size=HS)
+    torch.manual_seed(SEED)
+    model = pose.CNNPoseEstimation(cfg).to(dev).eval()
+    out = {"config": "CNNPoseEstimation eval forward, bf16 tensor cores (fp32 accumulate), 256x256, random init, synthetic",
+           "gflop_per_sample": 16.559, "samples_per_s": {}, "ms": {}}
+    g = torch.Generator(device="cpu").manual_seed(SEED + rank)
+    for bs in batches:
+        img = torch.rand(bs, 3, H, W, generator=g).to(dev)
+        dep = torch.rand(bs, 1, H, W, generator=g).to(dev)
+        kp = (torch.rand(bs, J, 2, generator=g) * 0.9 + 0.05).to(dev)
+        with torch.no_grad():
+            for _ in range(3):
+                model(img, dep, kp)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                model(img, dep, kp)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out["ms"][str(bs)] = ms
+        out["samples_per_s"][str(bs)] = bs / ms * 1e3
+        plan = model._plans.pop((bs, dev.index), None)
+        out["launches_per_forward"] = plan.launches + 1 if plan is not None else None
+        del plan, img, dep
+        torch.cuda.empty_cache()
+    best = max(out["samples_per_s"].values())
+    out["tflops_at_best"] = best * 16.559e9 / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    out["tensor_frac_of_measured_sustained"] = out["tflops_at_best"] / peaks.get("bf16_tflops_sustained", 1400.0)
+    if rank == 0:
+        # the reference's CPU path for the same forward (configs[0] flavour): fp32 oracle restatement on the host cores
+        try:
+            from oracle import torch_models as tm
+            torch.set_num_threads(os.cpu_count() or 1)
+            sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+            bs = 8
+            img, dep, kp = torch.rand(bs, 3, H, W), torch.rand(bs, 1, H, W), torch.rand(bs, J, 2) * 0.9 + 0.05
+            with torch.no_grad():
+                tm.cnn_forward(sd, cfg, img, dep, kp)
+                t0 = time.perf_counter()
+                n = 3
+                for _ in range(n):
+                    tm.cnn_forward(sd, cfg, img, dep, kp)
+                dt = (time.perf_counter() - t0) / n
+            out["cpu_baseline"] = {"value": bs / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"fp32 eval forward, B={bs}, {n} repetitions ({dt * n:.1f} s)"}
+        except Exception as exc:  # the checker is optional for the measurement itself
+            out["cpu_baseline"] = {"error": repr(exc)}
+    return out
 
 
 def main():
@@ -349,6 +415,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="preproc_b256")
+    ap.add_argument("--no-cnn", dest="cnn", action="store_false", help="skip the CNN inference sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,51 @@
+"""CPU: the N > 1 host logic on the gloo backend with world_size 2 (no GPU, rendezvous on 127.0.0.1)."""
+import importlib
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = importlib.import_module("3dhumanposeestimation_b200.dist")
+    assert d.world() == (rank, world)
+    lo, hi = d.shard_range(257, rank, world)
+    covered = torch.zeros(257)
+    covered[lo:hi] = 1
+    dist.all_reduce(covered)
+    ms = 10.0 + 5.0 * rank                      # rank 1 is slower
+    out = dict(shard=(lo, hi), covered_once=bool((covered == 1).all()), max_ms=d.max_over_ranks(ms),
+               total=d.sum_over_ranks(hi - lo), thr=d.job_throughput(256.0, ms), seed=d.rank_seed(42, rank))
+    ret[rank] = out
+    dist.destroy_process_group()
+
+
+def test_sharding_and_timing_reductions_world2():
+    world, port = 2, _free_port()
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    r0, r1 = ret[0], ret[1]
+    assert r0["shard"] == (0, 129) and r1["shard"] == (129, 257)
+    assert r0["covered_once"] and r1["covered_once"]
+    assert r0["max_ms"] == r1["max_ms"] == 15.0           # max over ranks, never the local time
+    assert r0["total"] == r1["total"] == 257
+    assert abs(r0["thr"] - 512.0 / 15e-3) < 1e-6          # all units / slowest rank
+    assert r0["seed"] != r1["seed"]
+
+
+def test_single_process_defaults():
+    d = importlib.import_module("3dhumanposeestimation_b200.dist")
+    assert d.world() == (0, 1)
+    assert d.shard_range(10, 0, 1) == (0, 10)
+    assert [d.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert d.max_over_ranks(3.5) == 3.5 and d.job_throughput(100, 50.0) == 2000.0
