@@ -166,6 +166,9 @@ static AugSmemLayout smem_layout(int W, const pose_aug_launch &l) {
 // device: pack
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned q8(float v) { return (unsigned)__float2int_rz(v * 255.0f) & 0xffu; }
+// uint8 input = the decoded pixel BEFORE the reference's u8 / 255 (chunked_dataset.py) and * 255 -> byte
+// (augmentation.py:197) round trip, which is not the identity in fp32 (e.g. 3 -> 2): reproduce it exactly
+__device__ __forceinline__ unsigned q8_u8(unsigned v) { return q8(__fdiv_rn((float)v, 255.0f)); }
 
 template <typename InT>
 __global__ void __launch_bounds__(256)
@@ -190,10 +193,10 @@ aug_pack_kernel(const InT *__restrict__ image, const InT *__restrict__ depth, lo
             const uchar4 g = ((const uchar4 *)(image + (b * 3 + 1) * n_px_per))[q];
             const uchar4 bl = ((const uchar4 *)(image + (b * 3 + 2) * n_px_per))[q];
             const uchar4 d = ((const uchar4 *)(depth + b * n_px_per))[q];
-            o[0] = make_uchar4(r.x, g.x, bl.x, d.x);
-            o[1] = make_uchar4(r.y, g.y, bl.y, d.y);
-            o[2] = make_uchar4(r.z, g.z, bl.z, d.z);
-            o[3] = make_uchar4(r.w, g.w, bl.w, d.w);
+            o[0] = make_uchar4(q8_u8(r.x), q8_u8(g.x), q8_u8(bl.x), q8_u8(d.x));
+            o[1] = make_uchar4(q8_u8(r.y), q8_u8(g.y), q8_u8(bl.y), q8_u8(d.y));
+            o[2] = make_uchar4(q8_u8(r.z), q8_u8(g.z), q8_u8(bl.z), q8_u8(d.z));
+            o[3] = make_uchar4(q8_u8(r.w), q8_u8(g.w), q8_u8(bl.w), q8_u8(d.w));
         }
         ((uint4 *)packed)[i] = *(uint4 *)o;
     }

@@ -118,15 +118,17 @@ class PoseAugmentor:
         nplan = B * _lib.POSE_AUG_PLAN_BYTES
         if self._plan_host is None or self._plan_host.numel() < nplan:
             self._plan_host = torch.empty(nplan, dtype=torch.uint8).pin_memory()
-        if self._plan_copied is not None:
+        capturing = torch.cuda.is_current_stream_capturing()
+        if self._plan_copied is not None and not capturing:
             self._plan_copied.synchronize()  # the pinned buffer is about to be overwritten
         plan_host = self._plan_host[:nplan]
         launch = _lib.PoseAugLaunch()
         _lib.check(lib.pose_augment_plan(params.ctypes.data, B, H, W, flags, plan_host.data_ptr(), C.byref(launch)),
                    "pose_augment_plan")
         plan_dev = plan_host.to(image.device, non_blocking=True)
-        self._plan_copied = torch.cuda.Event()
-        self._plan_copied.record()
+        if not capturing:   # (inside a CUDA-graph capture the copy is a graph node re-reading the pinned buffer)
+            self._plan_copied = torch.cuda.Event()
+            self._plan_copied.record()
 
         PH, PW = launch.max_out_h, (launch.max_out_w + 3) // 4 * 4
         if pad_to is not None:

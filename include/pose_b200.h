@@ -80,7 +80,8 @@ int pose_heatmap_render(const float *kp, int B, int J, int hs, float sigma, void
  *                        the device by the caller.  launch_out: [host] pose_aug_launch.
  *    pose_augment_batch  [device] quantise+pack -> per-sample tables -> fused cluster kernel.
  *      image     [B,3,H,W], depth [B,1,H,W]; in_dtype 0 = fp32 in [0,1] (the reference's sample
- *                schema, chunked_dataset.py:219-231), 1 = uint8
+ *                schema, chunked_dataset.py:219-231), 1 = uint8 decoded pixels p, treated exactly as the
+ *                reference treats the fp32 sample p/255 (its fp32 round trip (p/255)*255 -> byte is reproduced)
  *      kp [B,J,2] fp32, joints [B,J,3] fp32, cam [B,4] fp64 {fx,fy,cx,cy}
  *      plan      device copy of plan_out
  *      image_out [B,3,PH,PW] fp32, depth_out [B,1,PH,PW] fp32: sample i occupies the top-left
