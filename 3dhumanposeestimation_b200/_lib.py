@@ -20,7 +20,7 @@ class PoseGemmEpilogue(C.Structure):
 
     _fields_ = [("bias", C.c_void_p), ("residual", C.c_void_p), ("C", C.c_void_p), ("ldc", C.c_int32),
                 ("ldr", C.c_int32), ("act", C.c_int32), ("out_dtype", C.c_int32), ("out_scale", C.c_float),
-                ("res_scale", C.c_float)]
+                ("res_scale", C.c_float), ("preact", C.c_void_p), ("accumulate", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PoseAugLaunch(C.Structure):
@@ -51,6 +51,8 @@ SIGNATURES = {
     "pose_cast_f32_bf16": (c_int, [c_void_p, c_void_p, C.c_long, c_void_p]),
     "pose_gemm_bf16_ex": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, C.POINTER(PoseGemmEpilogue),
                                   c_void_p]),
+    "pose_gemm_bf16_tr": (c_int, [c_void_p, C.c_long, c_int, c_void_p, C.c_long, c_int, c_int, c_int, c_int, c_int,
+                                  C.POINTER(PoseGemmEpilogue), c_void_p]),
     "pose_conv2d_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_int, C.POINTER(PoseGemmEpilogue), c_void_p]),
     "pose_cnn_input_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
@@ -66,6 +68,13 @@ SIGNATURES = {
     "pose_coord_apply_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pose_avgpool2x2_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pose_sums_to_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "pose_layernorm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_float, C.c_long, c_int, C.c_long, C.c_long, C.c_long,
+                                    C.c_long, c_int, c_void_p, c_void_p]),
+    "pose_token_concat_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                       c_void_p]),
+    "pose_patchify_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pose_attention_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, C.c_long,
+                                    C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, c_float, c_void_p]),
 }
 
 _lib = None

@@ -119,9 +119,23 @@ __device__ __forceinline__ uint64_t umma_desc_k(uint32_t saddr) {
     d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;
     return d;
 }
-// cute::UMMA::InstrDescriptor for kind::f16: D = F32, A = B = BF16, both K-major
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// MN-major operand (the contraction index is the slow one in memory: a transposed view of a row-major matrix),
+// SWIZZLE_128B.  Canonical layout (cute make_umma_desc<Major::MN>): ((64, n), (8, k)) : ((1, LBO), (64, SBO)) elements,
+// i.e. one contraction row = 64 consecutive MN elements (128 B, one TMA box row), 8 rows = one 1024 B swizzle atom
+// (SBO), the next 64 MN elements live LBO bytes further (= the next TMA box of the stage).
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D = F32, A = B = BF16; bit 15 / 16 = A / B is MN-major
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -142,6 +156,8 @@ struct Epilogue {
     int ldc, ldr, act, out_bf16;
     int vec;                         // 16-byte vector path allowed (bases and row pitches aligned; host-checked)
     float out_scale, res_scale;      // C = act(acc + bias) * out_scale + residual * res_scale
+    __nv_bfloat16 *preact;           // [M, ldc] bf16 or null: acc + bias before the activation (saved for backward)
+    int accumulate;                  // fp32 C += acc * out_scale with red.global (split-K weight gradients)
 };
 
 struct ConvGeom {          // MODE 1 only
@@ -199,6 +215,21 @@ __device__ __forceinline__ float fast_act(float v) {
     if (ACT == 4) return 0.5f * (1.0f + tanh_approx(0.5f * v));       // sigmoid
     return v;
 }
+// derivative of the activation at the saved pre-activation u (ACT 5 = gelu', 6 = silu', 7 = relu')
+template <int ACT>
+__device__ __forceinline__ float act_grad(float u) {
+    if (ACT == 5) return 0.5f * (1.0f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+    if (ACT == 6) {
+        const float sg = 0.5f * (1.0f + tanh_approx(0.5f * u));
+        return sg * (1.0f + u * (1.0f - sg));
+    }
+    if (ACT == 7) return u > 0.f ? 1.0f : 0.0f;
+    return 1.0f;
+}
+__device__ __forceinline__ void red_add_f4(float *p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
 
 // Phase 2 of the epilogue for one 32 x 32 chunk sitting in the warp's staging buffer (fp32, pitch kPitch):
 // 8 lanes per output row, 4 columns per lane.  The activation is a template parameter so that the loop body
@@ -215,18 +246,34 @@ __device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, 
         const long grow = __shfl_sync(0xffffffffu, row, tr);
         float4 x = lds128(stg + tr * kPitch + colq * 4);
         if (grow < 0) continue;
-        x.x = fast_act<ACT>(x.x + bz.x) * ep.out_scale;
-        x.y = fast_act<ACT>(x.y + bz.y) * ep.out_scale;
-        x.z = fast_act<ACT>(x.z + bz.z) * ep.out_scale;
-        x.w = fast_act<ACT>(x.w + bz.w) * ep.out_scale;
-        if (ep.residual != nullptr) {
+        if (ACT >= 5) {
+            // backward through an activation: C = acc * act'(u) * out_scale, u = saved pre-activation (`residual`)
             const uint2 pk = __ldg((const uint2 *)(ep.residual + grow * ep.ldr + col));
-            const float2 f0 = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.x);
-            const float2 f1 = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.y);
-            x.x += f0.x * ep.res_scale; x.y += f0.y * ep.res_scale;
-            x.z += f1.x * ep.res_scale; x.w += f1.y * ep.res_scale;
+            const float2 u0 = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.x);
+            const float2 u1 = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.y);
+            x.x *= act_grad<ACT>(u0.x) * ep.out_scale; x.y *= act_grad<ACT>(u0.y) * ep.out_scale;
+            x.z *= act_grad<ACT>(u1.x) * ep.out_scale; x.w *= act_grad<ACT>(u1.y) * ep.out_scale;
+        } else {
+            x.x += bz.x; x.y += bz.y; x.z += bz.z; x.w += bz.w;
+            if (ep.preact != nullptr) {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(x.x, x.y), p1 = __floats2bfloat162_rn(x.z, x.w);
+                *(uint2 *)(ep.preact + grow * ep.ldc + col) = make_uint2(*(uint32_t *)&p0, *(uint32_t *)&p1);
+            }
+            x.x = fast_act<ACT>(x.x) * ep.out_scale;
+            x.y = fast_act<ACT>(x.y) * ep.out_scale;
+            x.z = fast_act<ACT>(x.z) * ep.out_scale;
+            x.w = fast_act<ACT>(x.w) * ep.out_scale;
+            if (ep.residual != nullptr) {
+                const uint2 pk = __ldg((const uint2 *)(ep.residual + grow * ep.ldr + col));
+                const float2 f0 = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.x);
+                const float2 f1 = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.y);
+                x.x += f0.x * ep.res_scale; x.y += f0.y * ep.res_scale;
+                x.z += f1.x * ep.res_scale; x.w += f1.y * ep.res_scale;
+            }
         }
-        if (ep.out_bf16) {
+        if (ep.accumulate) {
+            red_add_f4((float *)ep.C + grow * ep.ldc + col, x);
+        } else if (ep.out_bf16) {
             __nv_bfloat162 p0 = __floats2bfloat162_rn(x.x, x.y), p1 = __floats2bfloat162_rn(x.z, x.w);
             *(uint2 *)((__nv_bfloat16 *)ep.C + grow * ep.ldc + col) = make_uint2(*(uint32_t *)&p0, *(uint32_t *)&p1);
         } else {
@@ -251,17 +298,24 @@ __device__ __forceinline__ void epilogue_rows_slow(uint32_t stg, const Epilogue 
         for (int q = 0; q < 4; ++q) {
             if (col + q >= N) break;
             float y = lds32(stg + tr * kPitch + (colq + q) * 4);
-            if (ep.bias != nullptr) y += __ldg(ep.bias + col + q);
-            switch (ep.act) {
-                case 1: y = fast_act<1>(y); break;
-                case 2: y = fast_act<2>(y); break;
-                case 3: y = fast_act<3>(y); break;
-                case 4: y = fast_act<4>(y); break;
-                default: break;
+            if (ep.act >= 5) {
+                const float u = __bfloat162float(ep.residual[grow * ep.ldr + col + q]);
+                y *= (ep.act == 5 ? act_grad<5>(u) : (ep.act == 6 ? act_grad<6>(u) : act_grad<7>(u))) * ep.out_scale;
+            } else {
+                if (ep.bias != nullptr) y += __ldg(ep.bias + col + q);
+                if (ep.preact != nullptr) ep.preact[grow * ep.ldc + col + q] = __float2bfloat16_rn(y);
+                switch (ep.act) {
+                    case 1: y = fast_act<1>(y); break;
+                    case 2: y = fast_act<2>(y); break;
+                    case 3: y = fast_act<3>(y); break;
+                    case 4: y = fast_act<4>(y); break;
+                    default: break;
+                }
+                y *= ep.out_scale;
+                if (ep.residual != nullptr) y += __bfloat162float(ep.residual[grow * ep.ldr + col + q]) * ep.res_scale;
             }
-            y *= ep.out_scale;
-            if (ep.residual != nullptr) y += __bfloat162float(ep.residual[grow * ep.ldr + col + q]) * ep.res_scale;
-            if (ep.out_bf16) ((__nv_bfloat16 *)ep.C)[grow * ep.ldc + col + q] = __float2bfloat16_rn(y);
+            if (ep.accumulate) atomicAdd((float *)ep.C + grow * ep.ldc + col + q, y);
+            else if (ep.out_bf16) ((__nv_bfloat16 *)ep.C)[grow * ep.ldc + col + q] = __float2bfloat16_rn(y);
             else ((float *)ep.C)[grow * ep.ldc + col + q] = y;
         }
     }
@@ -270,10 +324,14 @@ __device__ __forceinline__ void epilogue_rows_slow(uint32_t stg, const Epilogue 
 // PERSISTENT kernel: grid = min(tiles, SMs); every CTA walks tiles t = blockIdx.x, += gridDim.x (N fastest so an A
 // tile is reused from L2 by its N neighbours).  The TMA ring runs ahead across tile boundaries, the accumulator is
 // double buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the MMAs of tile i + 1.
-template <int BN, int kStages, int BKC, int MODE>
+// A_MN / B_MN: the operand is MN-major (its memory image is the transposed matrix [K, M] resp. [K, N], row-major) --
+// backward GEMMs read activations and weights in place: dX = dY . W (B_MN) and dW = dY^T . X (A_MN and B_MN).
+// Split-K: a work item is (tile, split); split s contracts k-blocks [s * kb_per, (s + 1) * kb_per) and the
+// epilogue accumulates with red.global.add (ep.accumulate).
+template <int BN, int kStages, int BKC, int MODE, int A_MN, int B_MN>
 __global__ void __launch_bounds__(kGemmThreadsP, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N,
-                    int K, const Epilogue ep, const ConvGeom cg, int m_tiles, int n_tiles) {
+                    int K, const Epilogue ep, const ConvGeom cg, int m_tiles, int n_tiles, int kb_per, int k_splits) {
     using S = GemmSmem<BN, kStages, BKC>;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);  // swizzle atoms: 1024 B
@@ -287,7 +345,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (K + BKC - 1) / BKC;
-    const int total_tiles = m_tiles * n_tiles;
+    const int mn_tiles = m_tiles * n_tiles;
+    const int total_tiles = mn_tiles * k_splits;      // work items
     constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // power of two >= 32 (BN in {32, 64, 128})
 
     if (warp == 0 && lane == 0) {
@@ -318,7 +377,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===== TMA producer =====
         if (elect_one()) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+                const int split = item / mn_tiles, tile = item - split * mn_tiles;
+                const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
                 const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BN;
                 int img = 0, oh0 = 0, ow0 = 0;
                 if (MODE == 1) {
@@ -331,13 +392,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     oh0 = th * cg.TH;
                     ow0 = tw * cg.TW;
                 }
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % kStages;
                     const uint32_t ph = (it / kStages) & 1;
                     mbar_wait(empty + s, ph ^ 1);
                     unsigned char *sa = smem + s * S::kStageBytes, *sb = sa + S::kABytes;
                     mbar_expect_tx(full + s, S::kStageBytes);
-                    if (MODE == 0) {
+                    if (MODE == 0 && A_MN) {
+                        // two boxes of 64 MN elements x BKC contraction rows
+                        tma_load_2d(sa, &map_a, full + s, mt * BM, kb * BKC);
+                        tma_load_2d(sa + BKC * 128, &map_a, full + s, mt * BM + 64, kb * BKC);
+                    } else if (MODE == 0) {
                         tma_load_2d(sa, &map_a, full + s, kb * BKC, mt * BM);
                     } else {
                         const int tap = kb / cg.cchunks, cc = kb - tap * cg.cchunks;
@@ -345,34 +410,46 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         tma_load_4d(sa, &map_a, full + s, cc * BKC, ow0 * cg.stride + kw * cg.dil - cg.pad,
                                     oh0 * cg.stride + kh * cg.dil - cg.pad, img);
                     }
-                    tma_load_2d(sb, &map_w, full + s, kb * BKC, n0);
+                    if (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_2d(sb + j * BKC * 128, &map_w, full + s, n0 + j * 64, kb * BKC);
+                    } else {
+                        tma_load_2d(sb, &map_w, full + s, kb * BKC, n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
         uint32_t it = 0, tile_iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++tile_iter) {
+            const int split = item / mn_tiles;
+            const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
             const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
             mbar_wait(acc_empty + as, aph ^ 1);   // the epilogue has drained this accumulator stage
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + as * BN;
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % kStages;
                 const uint32_t ph = (it / kStages) & 1;
                 mbar_wait(full + s, ph);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + s * S::kStageBytes), sb = sa + S::kABytes;
-                    const uint64_t da = umma_desc_k<BKC * 2>(sa), db = umma_desc_k<BKC * 2>(sb);
+                    const uint64_t da = A_MN ? umma_desc_mn(sa, BKC * 128) : umma_desc_k<BKC * 2>(sa);
+                    const uint64_t db = B_MN ? umma_desc_mn(sb, BKC * 128) : umma_desc_k<BKC * 2>(sb);
+                    // advancing K by 16: K-major = 32 B inside the swizzled row (+2 in the >>4 address field);
+                    // MN-major = 16 contraction rows of 128 B (+128)
+                    constexpr uint64_t ka = A_MN ? 128 : 2, kbs = B_MN ? 128 : 2;
 #pragma unroll
                     for (int k = 0; k < BKC / UMMA_K; ++k) {
-                        // advancing K by 16 bf16 = 32 B inside the swizzled row: +2 in the (>>4) address field
-                        tc_mma_f16(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                        tc_mma_f16(tmem_acc, da + (uint64_t)k * ka, db + (uint64_t)k * kbs, idesc,
+                                   ((kb - kb0) | k) ? 1u : 0u);
                     }
                     tc_commit(empty + s);                          // frees the smem stage when these MMAs retire
-                    if (kb == num_kb - 1) tc_commit(acc_full + as);  // accumulator complete
+                    if (kb == kb1 - 1) tc_commit(acc_full + as);   // accumulator complete
                 }
                 __syncwarp();
             }
@@ -386,7 +463,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint32_t stg = smem_u32(staging + (warp - 2) * 32 * S::kStagePitch);
         const int colq = (lane & 7) * 4;  // phase-2 mapping: 8 lanes per row, 4 columns per lane
         uint32_t tile_iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++tile_iter) {
+            const int tile = item % mn_tiles;
             const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
             const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BN;
             const int r = quarter * 32 + lane;
@@ -439,7 +517,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     case 1: epilogue_rows<1, S::kStagePitch>(stg, ep, row, lane, col, N); break;
                     case 2: epilogue_rows<2, S::kStagePitch>(stg, ep, row, lane, col, N); break;
                     case 3: epilogue_rows<3, S::kStagePitch>(stg, ep, row, lane, col, N); break;
-                    default: epilogue_rows<4, S::kStagePitch>(stg, ep, row, lane, col, N); break;
+                    case 4: epilogue_rows<4, S::kStagePitch>(stg, ep, row, lane, col, N); break;
+                    case 5: epilogue_rows<5, S::kStagePitch>(stg, ep, row, lane, col, N); break;
+                    case 6: epilogue_rows<6, S::kStagePitch>(stg, ep, row, lane, col, N); break;
+                    default: epilogue_rows<7, S::kStagePitch>(stg, ep, row, lane, col, N); break;
                 }
                 __syncwarp();   // staging is rewritten by the next chunk
             }
@@ -513,11 +594,11 @@ static int make_map_nhwc(CUtensorMap *map, const void *ptr, int Nimg, int H, int
     return r == CUDA_SUCCESS ? POSE_OK : POSE_E_SHAPE;
 }
 
-template <int BN, int kStages, int BKC, int MODE>
+template <int BN, int kStages, int BKC, int MODE, int A_MN = 0, int B_MN = 0>
 static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int N, int K, const Epilogue &ep,
-                       const ConvGeom &cg, int m_tiles, cudaStream_t s) {
+                       const ConvGeom &cg, int m_tiles, cudaStream_t s, int k_splits = 1) {
     using S = GemmSmem<BN, kStages, BKC>;
-    auto kern = gemm_bf16_tn_kernel<BN, kStages, BKC, MODE>;
+    auto kern = gemm_bf16_tn_kernel<BN, kStages, BKC, MODE, A_MN, B_MN>;
     static bool configured = false;
     if (!configured) {
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -525,9 +606,14 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
         configured = true;
     }
     const int n_tiles = (N + BN - 1) / BN;
-    const long total = (long)m_tiles * n_tiles;
+    const int num_kb = (K + BKC - 1) / BKC;
+    if (k_splits < 1) k_splits = 1;
+    if (k_splits > num_kb) k_splits = num_kb;
+    const int kb_per = (num_kb + k_splits - 1) / k_splits;
+    k_splits = (num_kb + kb_per - 1) / kb_per;            // no empty split
+    const long total = (long)m_tiles * n_tiles * k_splits;
     const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-    kern<<<grid, kGemmThreadsP, S::kTotal, s>>>(ma, mw, M, N, K, ep, cg, m_tiles, n_tiles);
+    kern<<<grid, kGemmThreadsP, S::kTotal, s>>>(ma, mw, M, N, K, ep, cg, m_tiles, n_tiles, kb_per, k_splits);
     return launch_status();
 }
 
@@ -546,11 +632,14 @@ static int dispatch_bn(const CUtensorMap &ma, const void *W, int ldw, int M, int
 static int check_epilogue(const pose_gemm_epilogue *e, int N, Epilogue &ep) {
     if (!e || !e->C) return POSE_E_NULL;
     if (e->ldc < N || (e->residual && e->ldr < N)) return POSE_E_SHAPE;
-    if (e->act < 0 || e->act > 4 || (e->out_dtype != 0 && e->out_dtype != 1)) return POSE_E_UNSUPPORTED;
+    if (e->act < 0 || e->act > 7 || (e->out_dtype != 0 && e->out_dtype != 1)) return POSE_E_UNSUPPORTED;
+    if (e->act >= 5 && !e->residual) return POSE_E_NULL;        // act' needs the saved pre-activation
+    if (e->accumulate && e->out_dtype != 0) return POSE_E_UNSUPPORTED;
     // the fast epilogue moves 16-byte vectors: needs aligned bases and row pitches, else element-wise stores
     const int celt = e->out_dtype ? 2 : 4;
     ep.vec = !((uintptr_t)e->C % 16 || ((long)e->ldc * celt) % 16 ||
-               (e->residual && ((uintptr_t)e->residual % 16 || (e->ldr * 2) % 16)) || (e->bias && (uintptr_t)e->bias % 16));
+               (e->residual && ((uintptr_t)e->residual % 16 || (e->ldr * 2) % 16)) || (e->bias && (uintptr_t)e->bias % 16) ||
+               (e->preact && ((uintptr_t)e->preact % 16 || (e->ldc * 2) % 16)));
     ep.bias = e->bias;
     ep.residual = (const __nv_bfloat16 *)e->residual;
     ep.C = e->C;
@@ -560,6 +649,8 @@ static int check_epilogue(const pose_gemm_epilogue *e, int N, Epilogue &ep) {
     ep.out_bf16 = e->out_dtype;
     ep.out_scale = e->out_scale;
     ep.res_scale = e->res_scale;
+    ep.preact = (__nv_bfloat16 *)e->preact;
+    ep.accumulate = e->accumulate;
     return POSE_OK;
 }
 
@@ -583,9 +674,54 @@ POSE_API int pose_gemm_bf16_ex(const void *A, int lda, const void *W, int ldw, i
     return dispatch_bn<64, 0>(ma, W, ldw, M, N, K, ep, cg, (M + BM - 1) / BM, (cudaStream_t)stream);
 }
 
+// MN-major operand map: memory image [K rows, MN cols] row-major; box = 64 MN elements x bkc contraction rows
+static int make_map_mn(CUtensorMap *map, const void *ptr, long k_rows, long mn_cols, long ld_elems, int bkc) {
+    pose::EncodeTiledFn fn = pose::encode_tiled();
+    if (!fn) return POSE_E_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)mn_cols, (cuuint64_t)k_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)bkc};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? POSE_OK : POSE_E_SHAPE;
+}
+
+POSE_API int pose_gemm_bf16_tr(const void *A, long lda, int a_mn, const void *W, long ldw, int b_mn, int M, int N, int K,
+                               int k_splits, const pose_gemm_epilogue *epilogue, pose_stream_t stream) {
+    using namespace pose;
+    if (!A || !W) return POSE_E_NULL;
+    if (M <= 0 || N <= 0 || K <= 0) return POSE_E_SHAPE;
+    if (lda < (a_mn ? M : K) || ldw < (b_mn ? N : K) || lda % 8 || ldw % 8) return POSE_E_SHAPE;
+    if ((uintptr_t)A % 16 || (uintptr_t)W % 16) return POSE_E_ALIGN;
+    Epilogue ep;
+    int e = check_epilogue(epilogue, N, ep);
+    if (e) return e;
+    if (k_splits > 1 && !ep.accumulate) return POSE_E_UNSUPPORTED;   // partial sums must be accumulated
+    CUtensorMap ma, mw;
+    e = a_mn ? make_map_mn(&ma, A, K, M, lda, 64) : make_map_2d(&ma, A, M, K, lda, BM, 64);
+    if (e) return e;
+    ConvGeom cg = {};
+    const int m_tiles = (M + BM - 1) / BM;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!b_mn) {
+        if (a_mn) return POSE_E_UNSUPPORTED;                          // (A^T, W) is not needed by any backward
+        return dispatch_bn<64, 0>(ma, W, (int)ldw, M, N, K, ep, cg, m_tiles, s);
+    }
+    e = make_map_mn(&mw, W, K, N, ldw, 64);
+    if (e) return e;
+    if (N <= 64) {
+        if (a_mn) return launch_gemm<64, 6, 64, 0, 1, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);
+        return launch_gemm<64, 6, 64, 0, 0, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);
+    }
+    if (a_mn) return launch_gemm<128, 4, 64, 0, 1, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);
+    return launch_gemm<128, 4, 64, 0, 0, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);
+}
+
 POSE_API int pose_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, void *C, int ldc,
                             int M, int N, int K, int act, int out_dtype, pose_stream_t stream) {
-    pose_gemm_epilogue e = {bias, nullptr, C, ldc, 0, act, out_dtype, 1.0f, 0.0f};
+    pose_gemm_epilogue e = {bias, nullptr, C, ldc, 0, act, out_dtype, 1.0f, 0.0f, nullptr, 0, 0};
     return pose_gemm_bf16_ex(A, lda, W, ldw, M, N, K, &e, stream);
 }
 

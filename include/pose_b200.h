@@ -136,10 +136,26 @@ typedef struct pose_gemm_epilogue {
     void *C;
     int32_t ldc, ldr, act, out_dtype;
     float out_scale, res_scale;
+    /* training: */
+    void *preact;       /* [M, ldc] bf16 or NULL: acc + bias BEFORE the activation, saved for the backward pass */
+    int32_t accumulate; /* 1: fp32 C += acc * out_scale (atomic adds; split-K weight gradients accumulate into .grad) */
+    int32_t reserved;
 } pose_gemm_epilogue;
 
 int pose_gemm_bf16_ex(const void *A, int lda, const void *W, int ldw, int M, int N, int K,
                       const pose_gemm_epilogue *epilogue, pose_stream_t stream);
+
+/* Backward contractions of nn.Linear / 1x1 convolutions (autograd of src/train.py:89-92), reading the saved
+ * activations and the weights IN PLACE through MN-major tcgen05 operands (no transposed copies):
+ *    a_mn = 0: A is [M, K] row-major;  a_mn = 1: A's memory image is [K, M] row-major (pitch lda)
+ *    b_mn = 0: W is [N, K] row-major;  b_mn = 1: W's memory image is [K, N] row-major (pitch ldw)
+ *    data gradient    dX[M, Kin] = dY[M, Nout] . W[Nout, Kin]     -> (A = dY, a_mn 0; W = weight, b_mn 1)
+ *    weight gradient  dW[Nout, Kin] = dY^T . X                    -> (A = dY, a_mn 1; W = X, b_mn 1), contraction over
+ *                     the rows, split k_splits ways across CTAs, epilogue->accumulate = 1
+ *    act 5 | 6 | 7 in the epilogue: C = acc * act'(u) * out_scale with u = `residual` (saved pre-activation, bf16)
+ *    for act = gelu | silu | relu. */
+int pose_gemm_bf16_tr(const void *A, long lda, int a_mn, const void *W, long ldw, int b_mn, int M, int N, int K,
+                      int k_splits, const pose_gemm_epilogue *epilogue, pose_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * D. dense nn.Conv2d as implicit GEMM on tcgen05      reference: ConvBnAct, src/models/cnn.py:101-139
@@ -186,6 +202,32 @@ int pose_coord_pool_bf16(const void *X, int B, int H, int W, int C, void *P, pos
 int pose_coord_apply_bf16(const void *X, const void *G, int B, int H, int W, int C, void *Y, pose_stream_t stream);
 int pose_avgpool2x2_bf16(const void *X, int B, int H, int W, int C, void *Y, pose_stream_t stream);
 int pose_sums_to_bf16(const float *sums, int parts, int B, int C, float scale, void *out, pose_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * E. non-GEMM pieces of TransformerPoseEstimation.forward     reference: src/models/transformers.py:326-373
+ *    (+ the timm ViT-B/16 backbone it wraps); all activations bf16 [rows, D], the Linear layers and the
+ *    k16/s16 patch-embedding convolutions run on pose_gemm_bf16_ex.
+ *  pose_layernorm_bf16    nn.LayerNorm over D (256/512/768/1024), fp32 statistics.  Row r = g*rows + i reads input
+ *                         row g*in_group + in_off + i and writes output row g*out_group + out_off + i (drops the cls
+ *                         token of every sample, or normalises only token 0: transformers.py:346, :371)
+ *  pose_token_concat_bf16 dst[b] = [cls (fp32 [D], optional)] ++ src1[b] ++ src2[b] (optional) (+ pos fp32 [T,D]):
+ *                         timm `_pos_embed` and transformers.py:359-366
+ *  pose_patchify_bf16     fp32 NCHW planes (two channel-concatenated sources) -> bf16 [B*(H/P)*(W/P), C*P*P] in
+ *                         flattened-conv-weight column order: Conv2d(kernel = stride = P) becomes one GEMM
+ *  pose_attention_bf16    softmax(Q K^T * scale) V per (batch, head); Q/K/V/O rows with pitches ld* and batch
+ *                         strides bs* (elements), head h in columns [h*head_dim, (h+1)*head_dim); head_dim 48 | 64,
+ *                         Nk <= 288 (whole score row in shared memory).  nn.MultiheadAttention (transformers.py:61-63,
+ *                         :98-106) and timm Attention.
+ * ------------------------------------------------------------------------------------------- */
+int pose_layernorm_bf16(const void *X, const float *gamma, const float *beta, float eps, long M, int rows, long in_group,
+                        long in_off, long out_group, long out_off, int D, void *Y, pose_stream_t stream);
+int pose_token_concat_bf16(void *dst, int B, int T, int D, const float *cls, const void *src1, int N1, const void *src2,
+                           int N2, const float *pos, pose_stream_t stream);
+int pose_patchify_bf16(const float *src0, int C0, const float *src1, int C1, int B, int H, int W, int P, void *out,
+                       pose_stream_t stream);
+int pose_attention_bf16(const void *Q, const void *K, const void *V, void *O, int B, int heads, int Nq, int Nk, int head_dim,
+                        long ldq, long ldk, long ldv, long ldo, long bsq, long bsk, long bsv, long bso, float scale,
+                        pose_stream_t stream);
 
 #ifdef __cplusplus
 }

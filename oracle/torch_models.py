@@ -211,3 +211,120 @@ def fill_state_dict(sd, seed=0, out_scale_mm=300.0):
         k = sorted(last, key=lambda s: int(s.split(".")[2]))[-1]
         out[k] = out[k] * out_scale_mm      # outputs of pose magnitude (hundreds of mm)
     return out
+
+
+# ======================================================================================================
+# ViT: restated timm VisionTransformer backbone + the reference's fusion / final encoder / head
+# ======================================================================================================
+def _ln(x, sd, p, eps):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], eps)
+
+
+def _mha(sd, p, q_in, kv_in, heads):
+    """nn.MultiheadAttention(batch_first=True) forward in eval mode (dropout off): packed in_proj, scaled
+    dot-product attention, out_proj.  The averaged attention weights the reference discards are not computed."""
+    E = q_in.shape[-1]
+    w, b = sd[p + ".in_proj_weight"], sd[p + ".in_proj_bias"]
+    q = F.linear(q_in, w[:E], b[:E])
+    k = F.linear(kv_in, w[E:2 * E], b[E:2 * E])
+    v = F.linear(kv_in, w[2 * E:], b[2 * E:])
+    B, Nq, _ = q.shape
+    Nk = k.shape[1]
+    hd = E // heads
+    q = q.view(B, Nq, heads, hd).transpose(1, 2)
+    k = k.view(B, Nk, heads, hd).transpose(1, 2)
+    v = v.view(B, Nk, heads, hd).transpose(1, 2)
+    a = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), -1)
+    o = (a @ v).transpose(1, 2).reshape(B, Nq, E)
+    return F.linear(o, sd[p + ".out_proj.weight"], sd[p + ".out_proj.bias"])
+
+
+def _mlp2(sd, p, x, i0, i1):
+    return F.linear(F.gelu(F.linear(x, sd[f"{p}.{i0}.weight"], sd[f"{p}.{i0}.bias"])), sd[f"{p}.{i1}.weight"],
+                    sd[f"{p}.{i1}.bias"])
+
+
+def vit_backbone_features(sd, p, x, heads=12, eps=1e-6):
+    """timm 1.0.15 VisionTransformer.forward_features for vit_base_patch16 (published algorithm; timm is not under
+    /root/reference and not installed -- SURVEY.md 8c): conv patch embed -> [cls] + tokens + pos_embed -> pre-LN
+    blocks (LayerNorm eps 1e-6, fused qkv Linear, 12 heads x 64, exact-erf GELU MLP) -> final LayerNorm."""
+    w = sd[p + ".patch_embed.proj.weight"]
+    ps = w.shape[-1]
+    t = F.conv2d(x, w, sd[p + ".patch_embed.proj.bias"], stride=ps).flatten(2).transpose(1, 2)
+    t = torch.cat([sd[p + ".cls_token"].expand(t.shape[0], -1, -1), t], 1) + sd[p + ".pos_embed"]
+    E = t.shape[-1]
+    hd = E // heads
+    i = 0
+    while f"{p}.blocks.{i}.norm1.weight" in sd:
+        bp = f"{p}.blocks.{i}"
+        h = _ln(t, sd, bp + ".norm1", eps)
+        qkv = F.linear(h, sd[bp + ".attn.qkv.weight"], sd[bp + ".attn.qkv.bias"])
+        B, N, _ = qkv.shape
+        q, k, v = qkv.view(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+        a = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), -1)
+        o = (a @ v).transpose(1, 2).reshape(B, N, E)
+        t = t + F.linear(o, sd[bp + ".attn.proj.weight"], sd[bp + ".attn.proj.bias"])
+        h = _ln(t, sd, bp + ".norm2", eps)
+        t = t + F.linear(F.gelu(F.linear(h, sd[bp + ".mlp.fc1.weight"], sd[bp + ".mlp.fc1.bias"])),
+                         sd[bp + ".mlp.fc2.weight"], sd[bp + ".mlp.fc2.bias"])
+        i += 1
+    return _ln(t, sd, p + ".norm", eps)
+
+
+def vit_forward(sd, cfg, image, depth, kp):
+    """TransformerPoseEstimation.forward (reference: src/models/transformers.py:326-373) in eval mode."""
+    g = (lambda k: cfg[k]) if isinstance(cfg, dict) else (lambda k: getattr(cfg, k))
+    heads = g("transformer_heads")
+    tok = vit_backbone_features(sd, "vit_backbone", torch.cat([image, depth], 1))[:, 1:]   # drop the cls prefix token
+    hm = heatmaps(kp, g("heatmap_size"), g("heatmap_sigma"))
+    w = sd["heatmap_patch_embed.proj.weight"]
+    hm_tok = F.conv2d(hm, w, sd["heatmap_patch_embed.proj.bias"], stride=w.shape[-1]).flatten(2).transpose(1, 2)
+    hm_tok = hm_tok + sd["pos_embed_hm"]
+    x_img, x_hm = tok, hm_tok
+    for i in range(g("num_cross_modal_layers")):     # CrossModalFusionBlock, transformers.py:85-137 (LayerNorm eps 1e-5)
+        p = f"cross_modal_fusion_layers.{i}"
+        x_img = x_img + _mha(sd, p + ".cross_attn_img_to_hm", _ln(x_img, sd, p + ".norm_img_q", 1e-5),
+                             _ln(x_hm, sd, p + ".norm_hm_kv", 1e-5), heads)
+        x_hm = x_hm + _mha(sd, p + ".cross_attn_hm_to_img", _ln(x_hm, sd, p + ".norm_hm_q", 1e-5),
+                           _ln(x_img, sd, p + ".norm_img_kv", 1e-5), heads)
+        x_img = x_img + _mlp2(sd, p + ".mlp_img", _ln(x_img, sd, p + ".norm_img_mlp", 1e-5), 0, 3)
+        x_hm = x_hm + _mlp2(sd, p + ".mlp_hm", _ln(x_hm, sd, p + ".norm_hm_mlp", 1e-5), 0, 3)
+    t = torch.cat([sd["final_cls_token"].expand(x_img.shape[0], -1, -1), x_img, x_hm], 1) + sd["final_pos_embed"]
+    for i in range(g("final_encoder_depth")):        # TransformerEncoderBlock, transformers.py:49-82
+        p = f"final_encoder.{i}"
+        h = _ln(t, sd, p + ".norm1", 1e-5)
+        t = t + _mha(sd, p + ".attn", h, h, heads)
+        t = t + _mlp2(sd, p + ".mlp", _ln(t, sd, p + ".norm2", 1e-5), 0, 3)
+    x = _ln(t[:, 0], sd, "norm_out", 1e-5)
+    dims = g("regression_hidden_dims")
+    for i in range(len(dims)):                       # transformers.py:20-26: Linear at decoder.{0,3,6,..}
+        x = F.gelu(F.linear(x, sd[f"pose_head.decoder.{3 * i}.weight"], sd[f"pose_head.decoder.{3 * i}.bias"]))
+    n = 3 * len(dims)
+    x = F.linear(x, sd[f"pose_head.decoder.{n}.weight"], sd[f"pose_head.decoder.{n}.bias"])
+    return x.view(-1, g("num_joints"), 3)
+
+
+def fill_vit_state_dict(sd, seed=0, out_scale_mm=300.0):
+    """Deterministic key-seeded fill for the ViT (same idea as fill_state_dict): trunc-normal-like 0.02 embeddings,
+    xavier-scaled Linear weights, LayerNorm affine parameters perturbed away from (1, 0)."""
+    out = {}
+    for k in sorted(sd):
+        v = sd[k]
+        g = torch.Generator().manual_seed((zlib.crc32(k.encode()) + seed) & 0x7FFFFFFF)
+        if k.endswith("x_grid") or k.endswith("y_grid"):
+            out[k] = v.clone()
+        elif "norm" in (k.split(".") + [""])[-2] and k.endswith("weight") and v.dim() == 1:
+            out[k] = torch.rand(v.shape, generator=g) * 0.4 + 0.8
+        elif v.dim() == 1:
+            out[k] = torch.randn(v.shape, generator=g) * 0.02
+        elif "pos_embed" in k or "cls_token" in k:
+            out[k] = torch.randn(v.shape, generator=g) * 0.02
+        else:
+            fan_in = v[0].numel()
+            fan_out = v.shape[0]
+            out[k] = torch.randn(v.shape, generator=g) * math.sqrt(2.0 / (fan_in + fan_out))
+        out[k] = out[k].to(v.dtype)
+    last = sorted([k for k in out if k.startswith("pose_head.decoder.") and k.endswith("weight")],
+                  key=lambda s: int(s.split(".")[2]))[-1]
+    out[last] = out[last] * out_scale_mm * 10.0
+    return out
