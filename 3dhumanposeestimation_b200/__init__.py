@@ -18,7 +18,9 @@ from .loss import ComprehensivePoseLoss  # noqa: F401
 from .models.common import GaussianHeatmapGenerator, PoseRegressionHead  # noqa: F401
 from .dataset.augmentation import PoseAugmentor  # noqa: F401
 from .models.cnn import CNNPoseEstimation  # noqa: F401
+from .models.transformers import TransformerPoseEstimation  # noqa: F401
+from .optim import AdamW  # noqa: F401
 from . import _lib, ops  # noqa: F401
 
 __all__ = ["ModelConfig", "ComprehensivePoseLoss", "GaussianHeatmapGenerator", "PoseRegressionHead",
-           "PoseAugmentor", "CNNPoseEstimation"]
+           "PoseAugmentor", "CNNPoseEstimation", "TransformerPoseEstimation", "AdamW"]

@@ -74,7 +74,17 @@ SIGNATURES = {
                                        c_void_p]),
     "pose_patchify_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pose_attention_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, C.c_long,
-                                    C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, c_float, c_void_p]),
+                                    C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, c_float, c_void_p,
+                                    c_void_p]),
+    "pose_layernorm_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_float, C.c_long, c_int, C.c_long, C.c_long,
+                                        C.c_long, C.c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pose_colsum_bf16": (c_int, [c_void_p, C.c_long, c_int, C.c_long, c_void_p, c_void_p]),
+    "pose_cast_f32_bf16_2d": (c_int, [c_void_p, C.c_long, C.c_long, c_int, c_void_p, C.c_long, c_void_p]),
+    "pose_batch_rowsum_bf16": (c_int, [c_void_p, c_int, C.c_long, C.c_long, c_int, c_int, c_void_p, c_void_p]),
+    "pose_token_slice_bf16": (c_int, [c_void_p, c_int, C.c_long, C.c_long, c_int, c_int, c_void_p, c_void_p]),
+    "pose_attention_bwd_bf16": (c_int, [c_void_p] * 10 + [c_int] * 5 + [C.c_long] * 16 + [c_float, c_void_p]),
+    "pose_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_long, c_float, c_float, c_float,
+                                c_float, c_float, c_int, c_float, c_int, c_void_p]),
 }
 
 _lib = None

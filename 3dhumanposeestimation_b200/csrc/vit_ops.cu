@@ -141,8 +141,8 @@ patchify_kernel(const float *__restrict__ src0, int C0, const float *__restrict_
 template <int HD>
 __global__ void __launch_bounds__(128)
 attention_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K, const __nv_bfloat16 *__restrict__ V,
-                 __nv_bfloat16 *__restrict__ O, int Nq, int Nk, int Nkp, long ldq, long ldk, long ldv, long ldo, long bsq,
-                 long bsk, long bsv, long bso, float scale) {
+                 __nv_bfloat16 *__restrict__ O, float *__restrict__ lse, int Nq, int Nk, int Nkp, long ldq, long ldk, long ldv,
+                 long ldo, long bsq, long bsk, long bsv, long bso, float scale) {
     extern __shared__ __align__(128) unsigned char smem[];
     __nv_bfloat16 *Qs = (__nv_bfloat16 *)smem;                 // [64][HD]
     __nv_bfloat16 *Ks = Qs + 64 * HD;                           // [Nkp][HD]
@@ -208,7 +208,11 @@ attention_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__res
             P[(size_t)r * Nkp + c] = __float2bfloat16_rn(e);
         }
         sum = warp_sum(sum);
-        if (lane == 0) rowinv[r] = 1.0f / sum;
+        if (lane == 0) {
+            rowinv[r] = 1.0f / sum;
+            // log-sum-exp of the scaled scores: the backward kernels rebuild P = exp(s * scale - lse) from it
+            if (lse != nullptr && q0 + r < Nq) lse[((long)b * gridDim.y + h) * Nq + q0 + r] = m + __logf(sum);
+        }
     }
     __syncwarp();
     // O = P V, normalised on the way out
@@ -235,6 +239,473 @@ attention_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__res
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] = Os[r * HD + c * 8 + k] * inv;
             *((uint4 *)(og + (long)(q0 + r) * ldo) + c) = pack8v(f);
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm backward.  dX = dRes + rstd * (g*dY - mean(g*dY) - xhat * mean(g*dY*xhat)); dgamma += sum dY*xhat,
+// dbeta += sum dY.  Statistics are recomputed from the saved input (one warp per row, rows strided over the
+// grid so that each thread keeps its own columns' dgamma / dbeta partials in registers); row addressing as in
+// the forward: X / dX / dRes use the input addressing, dY the output addressing.
+// ---------------------------------------------------------------------------------------------------------
+template <int D8PL>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__restrict__ dY,
+                     const float *__restrict__ gamma, float eps, long M, int rows, long in_group, long in_off,
+                     long out_group, long out_off, int D, const __nv_bfloat16 *__restrict__ dRes,
+                     __nv_bfloat16 *__restrict__ dX, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    __shared__ float red[8][D8PL * 256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float gacc[D8PL][8], bacc[D8PL][8], gm[D8PL][8];
+#pragma unroll
+    for (int q = 0; q < D8PL; ++q) {
+        const int c = (q * 32 + lane) * 8;
+        const float4 g0 = __ldg((const float4 *)(gamma + c)), g1 = __ldg((const float4 *)(gamma + c) + 1);
+        gm[q][0] = g0.x; gm[q][1] = g0.y; gm[q][2] = g0.z; gm[q][3] = g0.w;
+        gm[q][4] = g1.x; gm[q][5] = g1.y; gm[q][6] = g1.z; gm[q][7] = g1.w;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gacc[q][k] = bacc[q][k] = 0.f;
+    }
+    for (long r = (long)blockIdx.x * 8 + warp; r < M; r += (long)gridDim.x * 8) {
+        const long g = r / rows, i = r - g * rows;
+        const long rin = g * in_group + in_off + i, rout = g * out_group + out_off + i;
+        const __nv_bfloat16 *x = X + rin * D;
+        const __nv_bfloat16 *dy = dY + rout * D;
+        float v[D8PL][8], d[D8PL][8];
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < D8PL; ++q) {
+            unpack8v(__ldg((const uint4 *)x + q * 32 + lane), v[q]);
+            unpack8v(__ldg((const uint4 *)dy + q * 32 + lane), d[q]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += v[q][k];
+        }
+        const float mean = warp_sum(s) / (float)D;
+        float ss = 0.f;
+#pragma unroll
+        for (int q = 0; q < D8PL; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                v[q][k] -= mean;
+                ss += v[q][k] * v[q][k];
+            }
+        const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < D8PL; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                v[q][k] *= rstd;                                // xhat
+                gacc[q][k] += d[q][k] * v[q][k];
+                bacc[q][k] += d[q][k];
+                d[q][k] *= gm[q][k];                            // g * dY
+                s1 += d[q][k];
+                s2 += d[q][k] * v[q][k];
+            }
+        s1 = warp_sum(s1) / (float)D;
+        s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+        for (int q = 0; q < D8PL; ++q) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = rstd * (d[q][k] - s1 - v[q][k] * s2);
+            if (dRes != nullptr) {
+                float rr[8];
+                unpack8v(__ldg((const uint4 *)(dRes + rin * D) + q * 32 + lane), rr);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] += rr[k];
+            }
+            ((uint4 *)(dX + rin * D))[q * 32 + lane] = pack8v(o);
+        }
+    }
+    // fold the 8 warps' partials, then one atomic per column per CTA
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < D8PL; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) red[warp][(q * 32 + lane) * 8 + k] = pass == 0 ? gacc[q][k] : bacc[q][k];
+        __syncthreads();
+        float *dst = pass == 0 ? dgamma : dbeta;
+        if (dst != nullptr)
+            for (int c = threadIdx.x; c < D; c += 256) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) t += red[w][c];
+                atomicAdd(dst + c, t);
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Column sums (bias gradients): out[c] += sum_r X[r, c], X bf16 [M, ld].  Block = 32 column groups of 8 x 8 rows.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16 *__restrict__ X, long M, int N, long ld, float *__restrict__ out) {
+    __shared__ float red[8][256];
+    const int cg = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c0 = (blockIdx.x * 32 + cg) * 8;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    if (c0 < N) {
+        for (long r = (long)blockIdx.y * 8 + ry; r < M; r += (long)gridDim.y * 8) {
+            if (c0 + 8 <= N) {
+                float f[8];
+                unpack8v(__ldg((const uint4 *)(X + r * ld + c0)), f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += f[k];
+            } else {
+                for (int k = 0; c0 + k < N; ++k) acc[k] += __bfloat162float(X[r * ld + c0 + k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[ry][cg * 8 + k] = acc[k];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        atomicAdd(out + c, t);
+    }
+}
+
+// out[t, c] (fp32, accumulated) += sum_b X[(b * T_in + t_off + t) * D + c]: gradients of the positional embeddings and
+// of the class tokens (parameters broadcast over the batch).
+__global__ void __launch_bounds__(256)
+batch_rowsum_kernel(const __nv_bfloat16 *__restrict__ X, int B, long T_in, long t_off, int T_out, int D,
+                    float *__restrict__ out) {
+    const int D8 = D >> 3;
+    const long total = (long)T_out * D8;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % D8);
+        const long t = i / D8;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        for (int b = 0; b < B; ++b) {
+            float f[8];
+            unpack8v(__ldg((const uint4 *)(X + ((long)b * T_in + t_off + t) * D) + c8), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += f[k];
+        }
+        float *o = out + t * D + c8 * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += acc[k];
+    }
+}
+
+// dst[b, i, :] = src[b, t_off + i, :] for i < n   (gradient of torch.cat along the token axis)
+__global__ void __launch_bounds__(256)
+token_slice_kernel(const __nv_bfloat16 *__restrict__ src, long T, long t_off, int n, int D, long total8,
+                   __nv_bfloat16 *__restrict__ dst) {
+    const int D8 = D >> 3;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % D8);
+        const long row = i / D8;
+        const long b = row / n, t = row - b * n;
+        ((uint4 *)dst)[i] = __ldg((const uint4 *)(src + (b * T + t_off + t) * D) + c8);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Attention backward, two kernels with the forward's structure (a 64-row strip against ALL columns in shared
+// memory; probabilities are rebuilt from the saved log-sum-exp, nothing of size Nq x Nk ever reaches HBM):
+//   dq kernel : rows = 64 queries, columns = all keys.   D = rowsum(dO * O); P = exp(S*scale - lse);
+//               dS = P * (dO V^T - D) * scale;  dQ = dS K.   Also writes D for the second kernel.
+//   dkv kernel: rows = 64 keys, columns = all queries.   dV = P^T dO,  dK = dS^T Q.
+// ---------------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(128)
+attention_bwd_dq_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K,
+                        const __nv_bfloat16 *__restrict__ V, const __nv_bfloat16 *__restrict__ O,
+                        const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ lse, __nv_bfloat16 *__restrict__ dQ,
+                        float *__restrict__ Dout, int Nq, int Nk, int Nkp, long ldq, long ldk, long ldv, long ldo, long lddo,
+                        long lddq, long bsq, long bsk, long bsv, long bso, long bsdo, long bsdq, float scale) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __nv_bfloat16 *Qs = (__nv_bfloat16 *)smem;                  // [64][HD]
+    __nv_bfloat16 *dOs = Qs + 64 * HD;                           // [64][HD]
+    __nv_bfloat16 *Ks = dOs + 64 * HD;                           // [Nkp][HD]
+    __nv_bfloat16 *Vs = Ks + (size_t)Nkp * HD;                   // [Nkp][HD]
+    __nv_bfloat16 *dS = Vs + (size_t)Nkp * HD;                   // [64][Nkp]
+    float *Os = (float *)(dS + (size_t)64 * Nkp);                // [64][HD] fp32 staging
+    float *scr = Os + 64 * HD;                                   // [4 warps][2][256]
+    __shared__ float lse_s[64], D_s[64];
+    const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const __nv_bfloat16 *qg = Q + b * bsq + (long)h * HD, *kg = K + b * bsk + (long)h * HD, *vg = V + b * bsv + (long)h * HD;
+    const __nv_bfloat16 *og = O + b * bso + (long)h * HD, *dog = dO + b * bsdo + (long)h * HD;
+    constexpr int C8 = HD / 8;
+    for (int i = threadIdx.x; i < 64 * C8; i += 128) {
+        const int r = i / C8, c = i - r * C8;
+        uint4 qv = make_uint4(0u, 0u, 0u, 0u), dv = qv;
+        if (q0 + r < Nq) {
+            qv = __ldg((const uint4 *)(qg + (long)(q0 + r) * ldq) + c);
+            dv = __ldg((const uint4 *)(dog + (long)(q0 + r) * lddo) + c);
+        }
+        ((uint4 *)Qs)[i] = qv;
+        ((uint4 *)dOs)[i] = dv;
+    }
+    for (int i = threadIdx.x; i < Nkp * C8; i += 128) {
+        const int r = i / C8, c = i - r * C8;
+        uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+        if (r < Nk) {
+            kv = __ldg((const uint4 *)(kg + (long)r * ldk) + c);
+            vv = __ldg((const uint4 *)(vg + (long)r * ldv) + c);
+        }
+        ((uint4 *)Ks)[i] = kv;
+        ((uint4 *)Vs)[i] = vv;
+    }
+    __syncthreads();
+    const int r0 = warp * 16;
+    // D = rowsum(dO * O), lse
+    for (int r = r0; r < r0 + 16; ++r) {
+        float t = 0.f;
+        if (q0 + r < Nq)
+            for (int c = lane; c < HD; c += 32)
+                t += __bfloat162float(dOs[r * HD + c]) * __bfloat162float(og[(long)(q0 + r) * ldo + c]);
+        t = warp_sum(t);
+        if (lane == 0) {
+            D_s[r] = t;
+            const bool ok = q0 + r < Nq;
+            lse_s[r] = ok ? lse[((long)b * gridDim.y + h) * Nq + q0 + r] : 0.f;
+            if (ok) Dout[((long)b * gridDim.y + h) * Nq + q0 + r] = t;
+        }
+    }
+    __syncwarp();
+    float *s0 = scr + warp * 512, *s1 = s0 + 256;
+    {
+        wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> aq[HD / 16], ad[HD / 16];
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+            wmma::load_matrix_sync(aq[k], Qs + r0 * HD + k * 16, HD);
+            wmma::load_matrix_sync(ad[k], dOs + r0 * HD + k * 16, HD);
+        }
+        for (int n = 0; n < Nkp / 16; ++n) {
+            wmma::fragment<wmma::accumulator, 16, 16, 16, float> sa, pa;
+            wmma::fill_fragment(sa, 0.f);
+            wmma::fill_fragment(pa, 0.f);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) {
+                wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> bk, bv;
+                wmma::load_matrix_sync(bk, Ks + (size_t)n * 16 * HD + k * 16, HD);
+                wmma::load_matrix_sync(bv, Vs + (size_t)n * 16 * HD + k * 16, HD);
+                wmma::mma_sync(sa, aq[k], bk, sa);
+                wmma::mma_sync(pa, ad[k], bv, pa);
+            }
+            wmma::store_matrix_sync(s0, sa, 16, wmma::mem_row_major);
+            wmma::store_matrix_sync(s1, pa, 16, wmma::mem_row_major);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = lane + 32 * i, rr = idx >> 4, cc = idx & 15;
+                const int col = n * 16 + cc;
+                float p = col < Nk ? __expf(s0[idx] * scale - lse_s[r0 + rr]) : 0.f;
+                dS[(size_t)(r0 + rr) * Nkp + col] = __float2bfloat16_rn(p * (s1[idx] - D_s[r0 + rr]) * scale);
+            }
+            __syncwarp();
+        }
+    }
+    // dQ = dS K
+#pragma unroll
+    for (int n = 0; n < HD / 16; ++n) {
+        wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
+        wmma::fill_fragment(acc, 0.f);
+        for (int k = 0; k < Nkp / 16; ++k) {
+            wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> a;
+            wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> bf;
+            wmma::load_matrix_sync(a, dS + (size_t)r0 * Nkp + k * 16, Nkp);
+            wmma::load_matrix_sync(bf, Ks + (size_t)k * 16 * HD + n * 16, HD);
+            wmma::mma_sync(acc, a, bf, acc);
+        }
+        wmma::store_matrix_sync(Os + r0 * HD + n * 16, acc, HD, wmma::mem_row_major);
+    }
+    __syncwarp();
+    __nv_bfloat16 *dqg = dQ + b * bsdq + (long)h * HD;
+    for (int i = lane; i < 16 * C8; i += 32) {
+        const int r = r0 + i / C8, c = i % C8;
+        if (q0 + r < Nq) {
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = Os[r * HD + c * 8 + k];
+            *((uint4 *)(dqg + (long)(q0 + r) * lddq) + c) = pack8v(f);
+        }
+    }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128)
+attention_bwd_dkv_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K,
+                         const __nv_bfloat16 *__restrict__ V, const __nv_bfloat16 *__restrict__ dO,
+                         const float *__restrict__ lse, const float *__restrict__ Dg, __nv_bfloat16 *__restrict__ dK,
+                         __nv_bfloat16 *__restrict__ dV, int Nq, int Nk, int Nqp, long ldq, long ldk, long ldv, long lddo,
+                         long lddk, long lddv, long bsq, long bsk, long bsv, long bsdo, long bsdk, long bsdv, float scale) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __nv_bfloat16 *Kt = (__nv_bfloat16 *)smem;                  // [64][HD]
+    __nv_bfloat16 *Vt = Kt + 64 * HD;                            // [64][HD]
+    __nv_bfloat16 *Qs = Vt + 64 * HD;                            // [Nqp][HD]
+    __nv_bfloat16 *dOs = Qs + (size_t)Nqp * HD;                  // [Nqp][HD]
+    __nv_bfloat16 *PT = dOs + (size_t)Nqp * HD;                  // [64][Nqp]
+    __nv_bfloat16 *dST = PT + (size_t)64 * Nqp;                  // [64][Nqp]
+    float *Os = (float *)(dST + (size_t)64 * Nqp);               // [64][HD] fp32 staging
+    float *scr = Os + 64 * HD;                                   // [4][2][256]
+    float *lse_s = scr + 4 * 512;                                // [Nqp]
+    float *D_s = lse_s + Nqp;                                    // [Nqp]
+    const int k0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const __nv_bfloat16 *qg = Q + b * bsq + (long)h * HD, *kg = K + b * bsk + (long)h * HD, *vg = V + b * bsv + (long)h * HD;
+    const __nv_bfloat16 *dog = dO + b * bsdo + (long)h * HD;
+    constexpr int C8 = HD / 8;
+    for (int i = threadIdx.x; i < 64 * C8; i += 128) {
+        const int r = i / C8, c = i - r * C8;
+        uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+        if (k0 + r < Nk) {
+            kv = __ldg((const uint4 *)(kg + (long)(k0 + r) * ldk) + c);
+            vv = __ldg((const uint4 *)(vg + (long)(k0 + r) * ldv) + c);
+        }
+        ((uint4 *)Kt)[i] = kv;
+        ((uint4 *)Vt)[i] = vv;
+    }
+    for (int i = threadIdx.x; i < Nqp * C8; i += 128) {
+        const int r = i / C8, c = i - r * C8;
+        uint4 qv = make_uint4(0u, 0u, 0u, 0u), dv = qv;
+        if (r < Nq) {
+            qv = __ldg((const uint4 *)(qg + (long)r * ldq) + c);
+            dv = __ldg((const uint4 *)(dog + (long)r * lddo) + c);
+        }
+        ((uint4 *)Qs)[i] = qv;
+        ((uint4 *)dOs)[i] = dv;
+    }
+    for (int i = threadIdx.x; i < Nqp; i += 128) {
+        const bool ok = i < Nq;
+        lse_s[i] = ok ? lse[((long)b * gridDim.y + h) * Nq + i] : 0.f;
+        D_s[i] = ok ? Dg[((long)b * gridDim.y + h) * Nq + i] : 0.f;
+    }
+    __syncthreads();
+    const int r0 = warp * 16;
+    float *s0 = scr + warp * 512, *s1 = s0 + 256;
+    {
+        wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> ak[HD / 16], av[HD / 16];
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+            wmma::load_matrix_sync(ak[k], Kt + r0 * HD + k * 16, HD);
+            wmma::load_matrix_sync(av[k], Vt + r0 * HD + k * 16, HD);
+        }
+        for (int n = 0; n < Nqp / 16; ++n) {
+            wmma::fragment<wmma::accumulator, 16, 16, 16, float> sa, pa;
+            wmma::fill_fragment(sa, 0.f);
+            wmma::fill_fragment(pa, 0.f);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) {
+                wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> bq, bd;
+                wmma::load_matrix_sync(bq, Qs + (size_t)n * 16 * HD + k * 16, HD);
+                wmma::load_matrix_sync(bd, dOs + (size_t)n * 16 * HD + k * 16, HD);
+                wmma::mma_sync(sa, ak[k], bq, sa);     // S^T tile = K Q^T
+                wmma::mma_sync(pa, av[k], bd, pa);     // dP^T tile = V dO^T
+            }
+            wmma::store_matrix_sync(s0, sa, 16, wmma::mem_row_major);
+            wmma::store_matrix_sync(s1, pa, 16, wmma::mem_row_major);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = lane + 32 * i, rr = idx >> 4, cc = idx & 15;
+                const int col = n * 16 + cc;
+                const bool ok = col < Nq && k0 + r0 + rr < Nk;
+                const float p = ok ? __expf(s0[idx] * scale - lse_s[col]) : 0.f;
+                PT[(size_t)(r0 + rr) * Nqp + col] = __float2bfloat16_rn(p);
+                dST[(size_t)(r0 + rr) * Nqp + col] = __float2bfloat16_rn(p * (s1[idx] - D_s[col]) * scale);
+            }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {      // 0: dV = P^T dO, 1: dK = dS^T Q
+        const __nv_bfloat16 *Am = which == 0 ? PT : dST, *Bm = which == 0 ? dOs : Qs;
+#pragma unroll
+        for (int n = 0; n < HD / 16; ++n) {
+            wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
+            wmma::fill_fragment(acc, 0.f);
+            for (int k = 0; k < Nqp / 16; ++k) {
+                wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> a;
+                wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> bf;
+                wmma::load_matrix_sync(a, Am + (size_t)r0 * Nqp + k * 16, Nqp);
+                wmma::load_matrix_sync(bf, Bm + (size_t)k * 16 * HD + n * 16, HD);
+                wmma::mma_sync(acc, a, bf, acc);
+            }
+            wmma::store_matrix_sync(Os + r0 * HD + n * 16, acc, HD, wmma::mem_row_major);
+        }
+        __syncwarp();
+        __nv_bfloat16 *og = which == 0 ? dV + b * bsdv + (long)h * HD : dK + b * bsdk + (long)h * HD;
+        const long ldo = which == 0 ? lddv : lddk;
+        for (int i = lane; i < 16 * C8; i += 32) {
+            const int r = r0 + i / C8, c = i % C8;
+            if (k0 + r < Nk) {
+                float f[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = Os[r * HD + c * 8 + k];
+                *((uint4 *)(og + (long)(k0 + r) * ldo) + c) = pack8v(f);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// fp32 [rows, cols] (pitch ld_in) -> bf16 [rows, ld_out], columns >= cols zero-filled: gradients whose width is not a
+// multiple of 8 (the 51-wide pose output) become TMA-addressable GEMM operands
+__global__ void __launch_bounds__(256)
+cast_pad_kernel(const float *__restrict__ in, long ld_in, int cols, __nv_bfloat16 *__restrict__ out, long ld_out, long total) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / ld_out;
+        const int c = (int)(i - r * ld_out);
+        out[i] = __float2bfloat16_rn(c < cols ? in[r * ld_in + c] : 0.f);
+    }
+}
+
+template <int HD>
+static size_t attn_dq_smem(int Nkp) {
+    return (size_t)2 * 64 * HD * 2 + (size_t)2 * Nkp * HD * 2 + (size_t)64 * Nkp * 2 + (size_t)64 * HD * 4 + 4 * 512 * 4;
+}
+template <int HD>
+static size_t attn_dkv_smem(int Nqp) {
+    return (size_t)2 * 64 * HD * 2 + (size_t)2 * Nqp * HD * 2 + (size_t)2 * 64 * Nqp * 2 + (size_t)64 * HD * 4 + 4 * 512 * 4 +
+           (size_t)2 * Nqp * 4;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// AdamW over one flat fp32 parameter buffer (torch.optim.AdamW semantics: decoupled weight decay, bias
+// correction, eps added after the sqrt), fused with: gradient scaling (loss scale / world size), refresh of the
+// bf16 shadow weights the GEMMs read, and zeroing of the gradient for the next accumulation window.
+// 28 B/param of HBM traffic (+ 2 B for the shadow): 16 B loads, 16 + 2 B stores per 4 parameters x 4.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adamw_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+             __nv_bfloat16 *__restrict__ shadow, long n, float lr, float beta1, float beta2, float eps, float wd,
+             float bc1, float bc2_sqrt, float grad_scale, int zero_grad) {
+    const long n4 = n >> 2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 pp = ((float4 *)p)[i], gg = ((const float4 *)g)[i], mm = ((float4 *)m)[i], vv = ((float4 *)v)[i];
+        float *pa = (float *)&pp, *ga = (float *)&gg, *ma = (float *)&mm, *va = (float *)&vv;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gr = ga[k] * grad_scale;
+            pa[k] *= 1.0f - lr * wd;
+            ma[k] = beta1 * ma[k] + (1.0f - beta1) * gr;
+            va[k] = beta2 * va[k] + (1.0f - beta2) * gr * gr;
+            const float denom = sqrtf(va[k]) / bc2_sqrt + eps;
+            pa[k] -= (lr / bc1) * (ma[k] / denom);
+        }
+        ((float4 *)p)[i] = pp;
+        ((float4 *)m)[i] = mm;
+        ((float4 *)v)[i] = vv;
+        if (zero_grad) ((float4 *)g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (shadow != nullptr) {
+            __nv_bfloat162 s0 = __floats2bfloat162_rn(pa[0], pa[1]), s1 = __floats2bfloat162_rn(pa[2], pa[3]);
+            ((uint2 *)shadow)[i] = make_uint2(*(uint32_t *)&s0, *(uint32_t *)&s1);
         }
     }
 }
@@ -298,7 +769,7 @@ POSE_API int pose_patchify_bf16(const float *src0, int C0, const float *src1, in
 
 POSE_API int pose_attention_bf16(const void *Q, const void *K, const void *V, void *O, int B, int heads, int Nq, int Nk,
                                  int head_dim, long ldq, long ldk, long ldv, long ldo, long bsq, long bsk, long bsv, long bso,
-                                 float scale, pose_stream_t stream) {
+                                 float scale, float *lse, pose_stream_t stream) {
     if (!Q || !K || !V || !O) return POSE_E_NULL;
     if (B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return POSE_E_SHAPE;
     if (head_dim != 48 && head_dim != 64) return POSE_E_UNSUPPORTED;
@@ -314,12 +785,132 @@ POSE_API int pose_attention_bf16(const void *Q, const void *K, const void *V, vo
         e = cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attention_kernel<64><<<grid, 128, smem, s>>>((const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V,
-                                                     (__nv_bfloat16 *)O, Nq, Nk, Nkp, ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale);
+                                                     (__nv_bfloat16 *)O, lse, Nq, Nk, Nkp, ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale);
     } else {
         e = cudaFuncSetAttribute(attention_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attention_kernel<48><<<grid, 128, smem, s>>>((const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V,
-                                                     (__nv_bfloat16 *)O, Nq, Nk, Nkp, ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale);
+                                                     (__nv_bfloat16 *)O, lse, Nq, Nk, Nkp, ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale);
     }
+    return launch_status();
+}
+
+POSE_API int pose_layernorm_bwd_bf16(const void *X, const void *dY, const float *gamma, float eps, long M, int rows,
+                                     long in_group, long in_off, long out_group, long out_off, int D, const void *dRes,
+                                     void *dX, float *dgamma, float *dbeta, pose_stream_t stream) {
+    if (!X || !dY || !gamma || !dX) return POSE_E_NULL;
+    if (M <= 0 || rows <= 0 || D <= 0) return POSE_E_SHAPE;
+    if ((uintptr_t)X % 16 || (uintptr_t)dY % 16 || (uintptr_t)dX % 16 || (uintptr_t)gamma % 16 || (dRes && (uintptr_t)dRes % 16))
+        return POSE_E_ALIGN;
+    long blocks = (M + 7) / 8;
+    const int grid = (int)(blocks < kNumSMs * 2 ? blocks : kNumSMs * 2);
+    cudaStream_t s = (cudaStream_t)stream;
+#define LNB_LAUNCH(N_)                                                                                                  \
+    layernorm_bwd_kernel<N_><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)X, (const __nv_bfloat16 *)dY, gamma, eps, M,   \
+                                                  rows, in_group, in_off, out_group, out_off, D,                        \
+                                                  (const __nv_bfloat16 *)dRes, (__nv_bfloat16 *)dX, dgamma, dbeta)
+    if (D == 256) LNB_LAUNCH(1);
+    else if (D == 512) LNB_LAUNCH(2);
+    else if (D == 768) LNB_LAUNCH(3);
+    else if (D == 1024) LNB_LAUNCH(4);
+    else return POSE_E_UNSUPPORTED;
+#undef LNB_LAUNCH
+    return launch_status();
+}
+
+POSE_API int pose_colsum_bf16(const void *X, long M, int N, long ld, float *out, pose_stream_t stream) {
+    if (!X || !out) return POSE_E_NULL;
+    if (M <= 0 || N <= 0 || ld < N) return POSE_E_SHAPE;
+    if ((uintptr_t)X % 16 || ld % 8) return POSE_E_ALIGN;
+    const int gx = (N + 255) / 256;
+    long gy = (M + 63) / 64;                       // >= 8 rows per thread row
+    const long cap = (kNumSMs * 4 + gx - 1) / gx;
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, M, N, ld, out);
+    return launch_status();
+}
+
+POSE_API int pose_batch_rowsum_bf16(const void *X, int B, long T_in, long t_off, int T_out, int D, float *out,
+                                    pose_stream_t stream) {
+    if (!X || !out) return POSE_E_NULL;
+    if (B <= 0 || T_in <= 0 || t_off < 0 || T_out <= 0 || t_off + T_out > T_in || D <= 0 || D % 8) return POSE_E_SHAPE;
+    if ((uintptr_t)X % 16) return POSE_E_ALIGN;
+    batch_rowsum_kernel<<<grid_cap((long)T_out * (D / 8)), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, B, T_in,
+                                                                                         t_off, T_out, D, out);
+    return launch_status();
+}
+
+POSE_API int pose_token_slice_bf16(const void *src, int B, long T, long t_off, int n, int D, void *dst, pose_stream_t stream) {
+    if (!src || !dst) return POSE_E_NULL;
+    if (B <= 0 || T <= 0 || t_off < 0 || n <= 0 || t_off + n > T || D <= 0 || D % 8) return POSE_E_SHAPE;
+    if ((uintptr_t)src % 16 || (uintptr_t)dst % 16) return POSE_E_ALIGN;
+    const long total8 = (long)B * n * (D / 8);
+    token_slice_kernel<<<grid_cap(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)src, T, t_off, n, D, total8,
+                                                                          (__nv_bfloat16 *)dst);
+    return launch_status();
+}
+
+POSE_API int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V, const void *O, const void *dO,
+                                     const float *lse, void *dQ, void *dK, void *dV, float *Dws, int B, int heads, int Nq,
+                                     int Nk, int head_dim, long ldq, long ldk, long ldv, long ldo, long lddo, long lddq,
+                                     long lddk, long lddv, long bsq, long bsk, long bsv, long bso, long bsdo, long bsdq,
+                                     long bsdk, long bsdv, float scale, pose_stream_t stream) {
+    if (!Q || !K || !V || !O || !dO || !lse || !dQ || !dK || !dV || !Dws) return POSE_E_NULL;
+    if (B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return POSE_E_SHAPE;
+    if (head_dim != 48 && head_dim != 64) return POSE_E_UNSUPPORTED;
+    const long al[] = {ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv};
+    for (long a : al)
+        if (a % 8) return POSE_E_ALIGN;
+    const void *ptrs[] = {Q, K, V, O, dO, dQ, dK, dV};
+    for (const void *q : ptrs)
+        if ((uintptr_t)q % 16) return POSE_E_ALIGN;
+    const int Nkp = (Nk + 15) / 16 * 16, Nqp = (Nq + 15) / 16 * 16;
+    const size_t s1 = head_dim == 64 ? attn_dq_smem<64>(Nkp) : attn_dq_smem<48>(Nkp);
+    const size_t s2 = head_dim == 64 ? attn_dkv_smem<64>(Nqp) : attn_dkv_smem<48>(Nqp);
+    if (s1 > 227 * 1024 - 1024 || s2 > 227 * 1024 - 1024) return POSE_E_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    const dim3 g1((Nq + 63) / 64, heads, B), g2((Nk + 63) / 64, heads, B);
+    cudaError_t e;
+#define BWD_LAUNCH(HD_)                                                                                                \
+    e = cudaFuncSetAttribute(attention_bwd_dq_kernel<HD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);      \
+    if (e != cudaSuccess) return (int)e;                                                                               \
+    e = cudaFuncSetAttribute(attention_bwd_dkv_kernel<HD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);     \
+    if (e != cudaSuccess) return (int)e;                                                                               \
+    attention_bwd_dq_kernel<HD_><<<g1, 128, s1, s>>>(                                                                  \
+        (const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V, (const __nv_bfloat16 *)O,        \
+        (const __nv_bfloat16 *)dO, lse, (__nv_bfloat16 *)dQ, Dws, Nq, Nk, Nkp, ldq, ldk, ldv, ldo, lddo, lddq, bsq, bsk,  \
+        bsv, bso, bsdo, bsdq, scale);                                                                                  \
+    attention_bwd_dkv_kernel<HD_><<<g2, 128, s2, s>>>(                                                                 \
+        (const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V, (const __nv_bfloat16 *)dO, lse,  \
+        Dws, (__nv_bfloat16 *)dK, (__nv_bfloat16 *)dV, Nq, Nk, Nqp, ldq, ldk, ldv, lddo, lddk, lddv, bsq, bsk, bsv,     \
+        bsdo, bsdk, bsdv, scale)
+    if (head_dim == 64) { BWD_LAUNCH(64); } else { BWD_LAUNCH(48); }
+#undef BWD_LAUNCH
+    return launch_status();
+}
+
+POSE_API int pose_adamw_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, void *shadow_bf16, long n,
+                             float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                             float grad_scale, int zero_grad, pose_stream_t stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq) return POSE_E_NULL;
+    if (n <= 0 || n % 4 || step < 1) return POSE_E_SHAPE;
+    if ((uintptr_t)param % 16 || (uintptr_t)grad % 16 || (uintptr_t)exp_avg % 16 || (uintptr_t)exp_avg_sq % 16 ||
+        (shadow_bf16 && (uintptr_t)shadow_bf16 % 8))
+        return POSE_E_ALIGN;
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
+    adamw_kernel<<<grid_cap(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq,
+                                                                        (__nv_bfloat16 *)shadow_bf16, n, lr, beta1, beta2,
+                                                                        eps, weight_decay, bc1, bc2s, grad_scale, zero_grad);
+    return launch_status();
+}
+
+POSE_API int pose_cast_f32_bf16_2d(const float *in, long ld_in, long rows, int cols, void *out, long ld_out,
+                                   pose_stream_t stream) {
+    if (!in || !out) return POSE_E_NULL;
+    if (rows <= 0 || cols <= 0 || ld_in < cols || ld_out < cols) return POSE_E_SHAPE;
+    const long total = rows * ld_out;
+    cast_pad_kernel<<<grid_cap(total), 256, 0, (cudaStream_t)stream>>>(in, ld_in, cols, (__nv_bfloat16 *)out, ld_out, total);
     return launch_status();
 }

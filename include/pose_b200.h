@@ -227,7 +227,42 @@ int pose_patchify_bf16(const float *src0, int C0, const float *src1, int C1, int
                        pose_stream_t stream);
 int pose_attention_bf16(const void *Q, const void *K, const void *V, void *O, int B, int heads, int Nq, int Nk, int head_dim,
                         long ldq, long ldk, long ldv, long ldo, long bsq, long bsk, long bsv, long bso, float scale,
+                        float *lse /* [B, heads, Nq] fp32 or NULL: log-sum-exp of the scaled scores, saved for backward */,
                         pose_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * E/G. backward of the non-GEMM transformer pieces           reference: autograd of src/train.py:89-92 over
+ *      src/models/transformers.py:33-137, 326-373.  Parameter gradients are ACCUMULATED (+=, fp32) like torch's .grad.
+ *  pose_layernorm_bwd_bf16  dX = dRes + LayerNorm'(dY); dgamma += , dbeta += ; X / dX / dRes use the forward's input row
+ *                           addressing, dY the output addressing; statistics are recomputed from the saved input X
+ *  pose_colsum_bf16         out[c] += sum_r X[r, c]                      (bias gradients)
+ *  pose_batch_rowsum_bf16   out[t, :] += sum_b X[b, t_off + t, :]        (positional-embedding / class-token gradients)
+ *  pose_token_slice_bf16    dst[b, i, :] = src[b, t_off + i, :], i < n   (gradient of the token concatenation)
+ *  pose_attention_bwd_bf16  dQ, dK, dV from Q, K, V, O, dO and the forward's lse; Dws [B, heads, Nq] fp32 scratch
+ * ------------------------------------------------------------------------------------------- */
+int pose_layernorm_bwd_bf16(const void *X, const void *dY, const float *gamma, float eps, long M, int rows, long in_group,
+                            long in_off, long out_group, long out_off, int D, const void *dRes, void *dX, float *dgamma,
+                            float *dbeta, pose_stream_t stream);
+int pose_colsum_bf16(const void *X, long M, int N, long ld, float *out, pose_stream_t stream);
+/* out[r, c] (bf16, pitch ld_out) = in[r, c] (fp32, pitch ld_in) for c < cols, 0 for cols <= c < ld_out */
+int pose_cast_f32_bf16_2d(const float *in, long ld_in, long rows, int cols, void *out, long ld_out, pose_stream_t stream);
+int pose_batch_rowsum_bf16(const void *X, int B, long T_in, long t_off, int T_out, int D, float *out, pose_stream_t stream);
+int pose_token_slice_bf16(const void *src, int B, long T, long t_off, int n, int D, void *dst, pose_stream_t stream);
+int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V, const void *O, const void *dO, const float *lse,
+                            void *dQ, void *dK, void *dV, float *Dws, int B, int heads, int Nq, int Nk, int head_dim,
+                            long ldq, long ldk, long ldv, long ldo, long lddo, long lddq, long lddk, long lddv, long bsq,
+                            long bsk, long bsv, long bso, long bsdo, long bsdq, long bsdk, long bsdv, float scale,
+                            pose_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * G. optimizer step                       reference: torch.optim.AdamW(lr 1e-3, weight_decay 0.01), main.py:154-156,
+ *    src/train.py:117-119.  One launch over a flat fp32 parameter buffer (n % 4 == 0): p, exp_avg, exp_avg_sq updated
+ *    in place from grad * grad_scale; shadow_bf16 (optional) receives the bf16 copy of the new parameters (the GEMM
+ *    operands); zero_grad = 1 clears grad for the next accumulation window (optimizer.zero_grad()).
+ * ------------------------------------------------------------------------------------------- */
+int pose_adamw_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, void *shadow_bf16, long n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, int zero_grad,
+                    pose_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -207,11 +207,156 @@ def gen_cnn():
                         n_params=sum(p.numel() for p in m.parameters()))
 
 
+def _install_timm_stub():
+    """timm is a third-party dependency of src/models/transformers.py:5 that is not under /root/reference and not
+    installed here.  This stub restates timm 1.0.15's `VisionTransformer` (vit_base_patch16: conv
+    patch embed, cls token + pos_embed, 12 pre-LN blocks with LayerNorm eps 1e-6, fused qkv, 12 heads, exact GELU MLP,
+    final LayerNorm; `forward_features` returns all 1 + N tokens) with the attribute surface the reference touches,
+    so that the reference's OWN TransformerPoseEstimation (patch-embed surgery, fusion blocks, final encoder, head)
+    runs live on top of it."""
+    import types
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    class Attention(nn.Module):
+        def __init__(self, dim, heads):
+            super().__init__()
+            self.num_heads = heads
+            self.qkv = nn.Linear(dim, dim * 3)
+            self.proj = nn.Linear(dim, dim)
+
+        def forward(self, x):
+            B, N, C = x.shape
+            qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+            x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
+            return self.proj(x.transpose(1, 2).reshape(B, N, C))
+
+    class Mlp(nn.Module):
+        def __init__(self, dim):
+            super().__init__()
+            self.fc1 = nn.Linear(dim, dim * 4)
+            self.act = nn.GELU()
+            self.fc2 = nn.Linear(dim * 4, dim)
+
+        def forward(self, x):
+            return self.fc2(self.act(self.fc1(x)))
+
+    class Block(nn.Module):
+        def __init__(self, dim, heads):
+            super().__init__()
+            self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+            self.attn = Attention(dim, heads)
+            self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+            self.mlp = Mlp(dim)
+
+        def forward(self, x):
+            x = x + self.attn(self.norm1(x))
+            return x + self.mlp(self.norm2(x))
+
+    class PatchEmbed(nn.Module):
+        def __init__(self, img_size, patch, dim):
+            super().__init__()
+            self.num_patches = (img_size[0] // patch) * (img_size[1] // patch)
+            self.proj = nn.Conv2d(3, dim, patch, patch)
+
+        def forward(self, x):
+            return self.proj(x).flatten(2).transpose(1, 2)
+
+    class VisionTransformer(nn.Module):
+        default_cfg = {}          # no "embed_dim" key: the reference falls into its except branch (:164-170)
+
+        def __init__(self, img_size, dim=768, depth=12, heads=12, patch=16):
+            super().__init__()
+            self.num_prefix_tokens = 1
+            self.patch_embed = PatchEmbed(img_size, patch, dim)
+            self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+            self.pos_embed = nn.Parameter(torch.zeros(1, self.patch_embed.num_patches + 1, dim))
+            self.blocks = nn.Sequential(*[Block(dim, heads) for _ in range(depth)])
+            self.norm = nn.LayerNorm(dim, eps=1e-6)
+
+        def forward_features(self, x):
+            x = self.patch_embed(x)
+            x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], 1) + self.pos_embed
+            return self.norm(self.blocks(x))
+
+    def create_model(name, pretrained=False, num_classes=0, img_size=None, **kw):
+        assert name.startswith("vit_base_patch16") and not pretrained
+        return VisionTransformer(tuple(img_size) if img_size is not None else (384, 384))
+
+    mod = types.ModuleType("timm")
+    mod.create_model = create_model
+    sys.modules["timm"] = mod
+
+
+VIT_CFG = dict(image_size=(256, 256), vit_pretrained=False)
+VIT_TRAIN_CFG = dict(image_size=(256, 256), vit_pretrained=False, transformer_dropout_rate=0.0,
+                     transformer_attention_dropout_rate=0.0, regression_dropout=0.0)
+
+
+def gen_vit():
+    """Reference TransformerPoseEstimation (live, over the timm stub) at 256x256: eval-mode outputs, and one training
+    step's loss + per-parameter gradient norms (dropout rates 0 so that the step is deterministic).  Parameters come from
+    oracle.torch_models.fill_vit_state_dict (regenerated by the tests from the same seed)."""
+    import contextlib
+    import io
+    import torch
+    _install_timm_stub()
+    from model_config import ModelConfig
+    from models.transformers import TransformerPoseEstimation
+    from loss import ComprehensivePoseLoss
+    sys.path.insert(0, REPO)
+    from oracle import torch_models as tm
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = TransformerPoseEstimation(ModelConfig("transformer", **VIT_CFG))
+    layout = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(OUT, "vit_state_dict_layout.json"), "w") as f:
+        json.dump(layout, f, indent=0, sort_keys=True)
+    sd = tm.fill_vit_state_dict(m.state_dict(), seed=7)
+    m.load_state_dict(sd)
+    m.eval()
+    g = torch.Generator().manual_seed(9)
+    img = torch.rand(2, 3, 256, 256, generator=g)
+    dep = torch.rand(2, 1, 256, 256, generator=g)
+    kp = torch.rand(2, 17, 2, generator=g) * 0.9 + 0.05
+    kp[1, 5] = -1.0
+    with torch.no_grad():
+        out = m(img, dep, kp)
+        out_oracle = tm.vit_forward(sd, m.config, img, dep, kp)
+    assert (out - out_oracle).abs().max() < 2e-3 * out.abs().max(), (out - out_oracle).abs().max()
+    # one training step (dropout 0): loss and gradient norms
+    with contextlib.redirect_stdout(io.StringIO()):
+        mt = TransformerPoseEstimation(ModelConfig("transformer", **VIT_TRAIN_CFG))
+    mt.load_state_dict(sd)
+    mt.train()
+    gt = torch.randn(2, 17, 3, generator=g) * 300
+    pred = mt(img, dep, kp)
+    total, comps = ComprehensivePoseLoss()(pred, gt)
+    total.backward()
+    names = [n for n, _ in mt.named_parameters()]
+    gnorm = np.array([p.grad.double().norm().item() for _, p in mt.named_parameters()])
+    # the restated functional oracle must give the same gradients (it is what the GPU tests differentiate)
+    sdg = {k: (v.clone().requires_grad_() if v.is_floating_point() and "grid" not in k else v) for k, v in sd.items()}
+    po = tm.vit_forward(sdg, mt.config, img, dep, kp)
+    to, _ = ComprehensivePoseLoss()(po, gt)
+    to.backward()
+    gn_o = np.array([sdg[n].grad.double().norm().item() for n in names])
+    assert np.allclose(gn_o, gnorm, rtol=2e-3, atol=1e-6), np.abs(gn_o / np.maximum(gnorm, 1e-12) - 1).max()
+    np.savez_compressed(os.path.join(OUT, "vit_256.npz"), versions=versions(), fill_seed=7, image_seed=9, kp=kp.numpy(),
+                        out=out.numpy(), gt=gt.numpy(), train_pred=pred.detach().numpy(),
+                        train_loss=np.float32(total.item()), grad_names=np.array(names), grad_norms=gnorm,
+                        grad_final_cls=mt.final_cls_token.grad.numpy().reshape(-1),
+                        grad_head_last_bias=mt.pose_head.decoder[-1].bias.grad.numpy(),
+                        note="reference TransformerPoseEstimation over a restated timm ViT-B/16 stub; inputs torch.rand "
+                             "with Generator(9): image, depth, kp, gt in that order")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, os.path.join(REF, "src"))
     os.chdir(tempfile.mkdtemp(prefix="pose_golden_"))
-    which = sys.argv[1:] or ["augment", "heatmap", "loss", "config", "cnn"]
+    which = sys.argv[1:] or ["augment", "heatmap", "loss", "config", "cnn", "vit"]
     for w in which:
         globals()["gen_" + w]()
         print("wrote", w)
