@@ -541,8 +541,10 @@ class VitPlan:
         self.layernorm_bwd(x_img, dimg_q, blk.norm_img_q, Mi, d_img, d_img)
         self.layernorm_bwd(x_hm, dhm_kv, blk.norm_hm_kv, Mh, d_hm, d_hm)
 
-    def backward(self, dout):
-        """dout: gradient of the [B, J, 3] output (fp32).  Accumulates into the flat .grad buffer."""
+    def backward(self, dout, section_done=None):
+        """dout: gradient of the [B, J, 3] output (fp32).  Accumulates into the flat .grad buffer.
+        section_done(flat, lo, hi) is called as soon as every kernel writing flat.grad[lo:hi) has been enqueued
+        (the data-parallel trainer all-reduces that range while the rest of the backward runs)."""
         if not getattr(self, "saved", False):
             raise RuntimeError("backward needs a training-mode forward on this plan first")
         m, B, E, b = self.model, self.B, self.E, self.bufs
@@ -553,6 +555,13 @@ class VitPlan:
             flat.grad.zero_()
             flat.attach_grads()
         _lib.require_cuda(dout, "grad_output", torch.float32)
+        hi = [flat.numel]
+
+        def done(first_param):
+            if section_done is not None:
+                lo = flat.index[id(first_param)] if first_param is not None else 0
+                section_done(flat, lo, hi[0])
+                hi[0] = lo
         n_out = self.J * 3
         ld = (n_out + 7) // 8 * 8
         dy = self.buf("d.out", B, ld)
@@ -567,12 +576,14 @@ class VitPlan:
             ld = dy.shape[1]
         dt = self.buf("d.fin", B * Tf, E, zero=True)
         self.layernorm_bwd(self.fin_out, dy, m.norm_out, B, None, dt, rows=1, in_group=Tf, in_off=0)
+        done(m.norm_out.weight)
         # ---- final encoder ---------------------------------------------------------------------------------
         for i in range(len(m.final_encoder) - 1, -1, -1):
             blk = m.final_encoder[i]
             dt = self.encoder_block_bwd(f"fe{i}.", dt, Tf, blk.norm1, blk.attn.in_proj_weight, blk.attn.in_proj_bias,
                                         blk.attn.out_proj.weight, blk.attn.out_proj.bias, blk.norm2, blk.mlp[0],
                                         blk.mlp[3], c.transformer_heads)
+            done(blk.norm1.weight)
         self.call("pose_batch_rowsum_bf16", dt.data_ptr(), B, Tf, 0, Tf, E, flat.g32(m.final_pos_embed).data_ptr())
         self.call("pose_batch_rowsum_bf16", dt.data_ptr(), B, Tf, 0, 1, E, flat.g32(m.final_cls_token).data_ptr())
         d_img, d_hm = self.buf("d.img", B * Ti, E), self.buf("d.hm", B * Th, E)
@@ -584,10 +595,12 @@ class VitPlan:
             x_img = b[f"cm{i - 1}.mi.y"] if i > 0 else b["x_img"]
             x_hm = b[f"cm{i - 1}.mh.y"] if i > 0 else b["x_hm"]
             self.cross_block_bwd(f"cm{i}.", m.cross_modal_fusion_layers[i], x_img, x_hm, d_img, d_hm)
+            done(m.cross_modal_fusion_layers[i].norm_img_q.weight)
         # ---- heat-map stream: pos_embed_hm and the patch embedding (key-points carry no gradient) -----------
         self.call("pose_batch_rowsum_bf16", d_hm.data_ptr(), B, Th, 0, Th, E, flat.g32(m.pos_embed_hm).data_ptr())
         hpe = m.heatmap_patch_embed.proj
         self.linear_bwd(d_hm, E, B * Th, b["phm"], hpe.weight, hpe.bias)
+        done(hpe.weight)
         # ---- backbone --------------------------------------------------------------------------------------
         bb = m.vit_backbone
         dx = self.buf("d.bb", B * (Ti + 1), E, zero=True)
@@ -597,11 +610,14 @@ class VitPlan:
             dx = self.encoder_block_bwd(f"bb{i}.", dx, Ti + 1, blk.norm1, blk.attn.qkv.weight, blk.attn.qkv.bias,
                                         blk.attn.proj.weight, blk.attn.proj.bias, blk.norm2, blk.mlp.fc1, blk.mlp.fc2,
                                         bb.num_heads)
+            if i % 3 == 0:
+                done(blk.norm1.weight)
         self.call("pose_batch_rowsum_bf16", dx.data_ptr(), B, Ti + 1, 0, Ti + 1, E, flat.g32(bb.pos_embed).data_ptr())
         self.call("pose_batch_rowsum_bf16", dx.data_ptr(), B, Ti + 1, 0, 1, E, flat.g32(bb.cls_token).data_ptr())
         dtok = self.buf("d.tok", B * Ti, E)
         self.call("pose_token_slice_bf16", dx.data_ptr(), B, Ti + 1, 1, Ti, E, dtok.data_ptr())
         self.linear_bwd(dtok, E, B * Ti, b["pimg"], bb.patch_embed.proj.weight, bb.patch_embed.proj.bias)
+        done(None)
 
     @property
     def _block_input(self):

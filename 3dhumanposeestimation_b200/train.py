@@ -1,0 +1,88 @@
+"""The per-batch training step on B200 (reference: src/train.py:76-119, optimizer main.py:154-156).
+
+``Trainer.step`` is the body of the reference's batch loop -- forward, composite loss, backward, (every
+``accumulation_steps`` batches) AdamW step + zero_grad -- with the reference's six ``.item()`` syncs replaced by
+one 5-float device buffer.  It drives the model's launch plan directly (the same kernels ``loss.backward()``
+reaches through autograd; the autograd route stays available for drop-in use).
+
+Data parallelism: one process per GPU, every rank owns its own samples and a full replica; the only
+exchange is the gradient all-reduce.  The flat fp32 gradient buffer is reduced in a few large buckets in the
+order the backward pass completes them (model tail first), each bucket on a communication stream as soon as its
+section of the backward has been enqueued, so NCCL over NVLink overlaps the remaining backward kernels.
+BatchNorm statistics stay per replica (the reference has no SyncBN).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .loss import pose_loss_fwd_bwd
+from .optim import AdamW
+
+
+class Trainer:
+    def __init__(self, model, criterion, optimizer=None, accumulation_steps=1, lr=1e-3, weight_decay=0.01,
+                 process_group=None, bucket_bytes=64 << 20):
+        self.model, self.crit = model, criterion
+        self.opt = optimizer if optimizer is not None else AdamW(model.parameters(), lr=lr, weight_decay=weight_decay)
+        self.accum = int(accumulation_steps)
+        self.micro = 0
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.pg = process_group
+        self.bucket_bytes = bucket_bytes
+        self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
+        self._pending = []
+        self.out5 = None
+
+    # ---- gradient exchange ---------------------------------------------------------------------------
+    def _section_done(self, flat, lo, hi):
+        """Gradients in flat[lo:hi) are final: all-reduce them on the communication stream (bucketed)."""
+        if self.world == 1 or hi <= lo:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        step = max(1, self.bucket_bytes // 4)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            pos = hi
+            while pos > lo:
+                a = max(lo, pos - step)
+                dist.all_reduce(flat.grad[a:pos], op=dist.ReduceOp.SUM, group=self.pg)
+                pos = a
+
+    def _wait_comm(self):
+        if self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    # ---- one batch -----------------------------------------------------------------------------------
+    def step(self, images, depths, keypoints_2d, gt_joints):
+        """Returns the device tensor [mse, l1, inter_joint, abs_root, total] of this batch (no host sync)."""
+        m = self.model
+        B = images.shape[0]
+        plan = m.plan(B, images.device)
+        last = (self.micro + 1) % self.accum == 0
+        out = plan.forward(images, depths, keypoints_2d, save=True)
+        pred = out.view(B, -1, 3)
+        # loss forward + d(total / accum)/d(pred) in one kernel (src/train.py:86-92)
+        out5, grad = pose_loss_fwd_bwd(pred, gt_joints, self.crit._weights(), want_grad=True, grad_scale=1.0 / self.accum)
+        hook = self._section_done if (last and self.world > 1) else None
+        plan.backward(grad.view(B, -1), section_done=hook)
+        self.micro += 1
+        if last:
+            self._wait_comm()
+            self.opt.grad_scale = 1.0 / self.world          # all-reduce(sum) / world = mean over replicas
+            self.opt.step()                                  # also clears the flat gradient buffer
+        self.out5 = out5
+        return out5
+
+
+def broadcast_parameters(model, src=0, process_group=None):
+    """Replicas start from rank `src`'s parameters and buffers (one flat broadcast)."""
+    from .params import FlatParams
+    flat = FlatParams.of(model.parameters())
+    dist.broadcast(flat.master, src, group=process_group)
+    for b in model.buffers():
+        dist.broadcast(b, src, group=process_group)
+    flat.refresh_shadow(force=True)
+    return flat
