@@ -23,6 +23,13 @@ class PoseGemmEpilogue(C.Structure):
                 ("res_scale", C.c_float), ("preact", C.c_void_p), ("accumulate", C.c_int32), ("reserved", C.c_int32)]
 
 
+class PoseRepackEntry(C.Structure):
+    """Mirror of `pose_repack_entry` in include/pose_b200.h."""
+
+    _fields_ = [("src", C.c_int64), ("dst", C.c_int64), ("kind", C.c_int32), ("d0", C.c_int32), ("d1", C.c_int32),
+                ("d2", C.c_int32), ("d3", C.c_int32), ("pad", C.c_int32)]
+
+
 class PoseAugLaunch(C.Structure):
     """Mirror of `pose_aug_launch` in include/pose_b200.h."""
 
@@ -83,6 +90,33 @@ SIGNATURES = {
     "pose_batch_rowsum_bf16": (c_int, [c_void_p, c_int, C.c_long, C.c_long, c_int, c_int, c_void_p, c_void_p]),
     "pose_token_slice_bf16": (c_int, [c_void_p, c_int, C.c_long, C.c_long, c_int, c_int, c_void_p, c_void_p]),
     "pose_attention_bwd_bf16": (c_int, [c_void_p] * 10 + [c_int] * 5 + [C.c_long] * 16 + [c_float, c_void_p]),
+    "pose_cnn_input_pack_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "pose_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [c_void_p, c_int, c_void_p]),
+    "pose_bn_stats_bf16": (c_int, [c_void_p, C.c_long, c_int, C.c_long, c_void_p, c_void_p]),
+    "pose_bn_finalize": (c_int, [c_void_p, C.c_long, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
+    "pose_bn_apply_bf16": (c_int, [c_void_p, C.c_long, c_int, c_void_p, c_int, c_float, c_void_p, C.c_long, c_void_p, C.c_long,
+                                   c_void_p]),
+    "pose_bn_bwd_bf16": (c_int, [c_void_p, C.c_long, c_void_p, C.c_long, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pose_dwconv3x3_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
+    "pose_gate_bwd_reduce_bf16": (c_int, [c_void_p, c_void_p, c_int, C.c_long, c_int, c_void_p, c_void_p]),
+    "pose_gate_bwd_apply_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, C.c_long, c_int, c_void_p, c_void_p,
+                                         c_void_p]),
+    "pose_sigmoid_bwd": (c_int, [c_void_p, c_void_p, C.c_long, c_void_p, c_void_p]),
+    "pose_eca_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int, c_int,
+                             c_void_p, c_void_p, c_void_p]),
+    "pose_coord_bwd_reduce_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pose_coord_bwd_apply_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pose_wasp_mix_bf16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, C.c_long, c_int, c_void_p, c_void_p]),
+    "pose_wasp_mix_bwd_bf16": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, C.c_long, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p]),
+    "pose_avgpool2x2_bwd_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pose_scatter_strided_add_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pose_add_bf16": (c_int, [c_void_p, c_void_p, C.c_long, c_void_p, c_void_p]),
+    "pose_dropout_bf16": (c_int, [c_void_p, C.c_long, c_float, C.c_uint64, c_void_p, c_void_p]),
+    "pose_param_repack": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pose_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_long, c_float, c_float, c_float,
                                 c_float, c_float, c_int, c_float, c_int, c_void_p]),
 }

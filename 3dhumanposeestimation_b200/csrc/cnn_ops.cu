@@ -54,7 +54,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 cnn_input_pack_kernel(const float *__restrict__ image, const float *__restrict__ depth, const float *__restrict__ kp,
-                      int B, int S, int J, float scale, float denom, float rcp, __nv_bfloat16 *__restrict__ out) {
+                      int B, int S, int J, float scale, float denom, float rcp, int c_stride, __nv_bfloat16 *__restrict__ out) {
     __shared__ float s_mu[32][2];
     __shared__ float s_valid[32];
     const long npx = (long)S * S;
@@ -87,7 +87,7 @@ cnn_input_pack_kernel(const float *__restrict__ image, const float *__restrict__
         }
         v[4 + j] = r;
     }
-    uint4 *dst = (uint4 *)(out + ((long)b * npx + px) * 32);
+    uint4 *dst = (uint4 *)(out + ((long)b * npx + px) * c_stride);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         float f[8];
@@ -417,14 +417,19 @@ using namespace pose;
 
 POSE_API int pose_cnn_input_pack(const float *image, const float *depth, const float *kp, int B, int S, int J,
                                  float sigma, void *out, pose_stream_t stream) {
+    return pose_cnn_input_pack_ex(image, depth, kp, B, S, J, sigma, 32, out, stream);
+}
+
+POSE_API int pose_cnn_input_pack_ex(const float *image, const float *depth, const float *kp, int B, int S, int J,
+                                    float sigma, int c_stride, void *out, pose_stream_t stream) {
     if (!image || !depth || !kp || !out) return POSE_E_NULL;
-    if (B <= 0 || S <= 0 || J <= 0 || J > 28 || !(sigma > 0.f)) return POSE_E_SHAPE;
+    if (B <= 0 || S <= 0 || J <= 0 || J > 28 || !(sigma > 0.f) || c_stride < 32 || c_stride % 8) return POSE_E_SHAPE;
     if ((uintptr_t)out % 16) return POSE_E_ALIGN;
     const float denom = (float)(2.0 * (double)sigma * (double)sigma);
     const long npx = (long)S * S;
     const int blocks_per_img = (int)((npx + 255) / 256);
     cnn_input_pack_kernel<<<B * blocks_per_img, 256, 0, (cudaStream_t)stream>>>(
-        image, depth, kp, B, S, J, (float)(S - 1), denom, (float)(1.0 / (double)denom), (__nv_bfloat16 *)out);
+        image, depth, kp, B, S, J, (float)(S - 1), denom, (float)(1.0 / (double)denom), c_stride, (__nv_bfloat16 *)out);
     return launch_status();
 }
 

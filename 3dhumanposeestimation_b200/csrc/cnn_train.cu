@@ -1,0 +1,900 @@
+// cnn_train.cu -- the bandwidth-bound kernels of the CNN TRAINING step (reference: loss.backward() over
+// src/models/cnn.py; src/train.py:83-92): batch-statistics BatchNorm forward / backward fused with the activation,
+// the residual add and the channel concatenation; depthwise 3x3 convolution backward (data and weights); the
+// backward of the SE / ECA / CoordAttention gates, of the WASP branch mix and of the pooling layers; dropout; and
+// the per-step re-layout of the parameters the tensor-core kernels read (one table-driven launch).
+// Channels-last bf16 activations, fp32 statistics and parameter gradients (accumulated like torch's .grad).
+#include "common.cuh"
+
+namespace pose {
+
+__device__ __forceinline__ void up8(const uint4 &p, float (&f)[8]) {
+    const __nv_bfloat162 *h = (const __nv_bfloat162 *)&p;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 t = __bfloat1622float2(h[q]);
+        f[2 * q] = t.x;
+        f[2 * q + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pk8(const float (&f)[8]) {
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+    return *(uint4 *)h;
+}
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float act_fwd(float z, int act) {
+    switch (act) {
+        case 1: return z > 0.f ? z : 0.f;
+        case 2: return z * sigmoid_f(z);
+        case 3: return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f));
+        case 4: return sigmoid_f(z);
+        default: return z;
+    }
+}
+__device__ __forceinline__ float act_bwd(float z, int act) {   // d act / dz
+    switch (act) {
+        case 1: return z > 0.f ? 1.f : 0.f;
+        case 2: { const float s = sigmoid_f(z); return s * (1.0f + z * (1.0f - s)); }
+        case 3: return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
+        case 4: { const float s = sigmoid_f(z); return s * (1.0f - s); }
+        default: return 1.f;
+    }
+}
+
+static int grid_for(long items, int per_block = 256, int max_waves = 16) {
+    long blocks = (items + per_block - 1) / per_block;
+    long cap = (long)kNumSMs * max_waves;
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-channel reduction over the rows of an [M, C] channels-last matrix: K quantities per channel, produced by a
+// functor for 8 consecutive channels of one row.  A CTA owns a slab of up to 256 channels (32 groups of 8); when the
+// matrix has fewer groups than a warp has lanes, the spare lanes take further rows.  Per-thread fp32 partials ->
+// shuffle across the lanes that share a channel group -> shared memory across the 8 warps -> one atomicAdd per
+// channel per CTA into out[k * C + c].
+// ---------------------------------------------------------------------------------------------------------
+template <int K, class F>
+__device__ __forceinline__ void col_reduce(long M, int C, float *__restrict__ out, F f) {
+    __shared__ float red[8][K][256];
+    const int C8 = C >> 3;
+    const int slab = blockIdx.x;
+    const int ng = min(32, C8 - slab * 32);
+    int gpr = 1;
+    while (gpr < ng) gpr <<= 1;                      // groups per row slot (power of two <= 32)
+    const int R = 32 / gpr;                          // rows per warp iteration
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane % gpr, rsub = lane / gpr;
+    const bool active = g < ng;
+    const int c0 = (slab * 32 + g) * 8;
+    float acc[K][8];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+    if (active)
+        for (long r = ((long)blockIdx.y * 8 + warp) * R + rsub; r < M; r += (long)gridDim.y * 8 * R) {
+            float v[K][8];
+            f(r, c0, v);
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[k][j] += v[k][j];
+        }
+    for (int o = gpr; o < 32; o <<= 1)
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[k][j] += __shfl_xor_sync(0xffffffffu, acc[k][j], o);
+    if (rsub == 0 && active)
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) red[warp][k][g * 8 + j] = acc[k][j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * ng * 8; i += 256) {
+        const int k = i / (ng * 8), c = i - k * ng * 8;
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][k][c];
+        atomicAdd(out + (long)k * C + slab * 256 + c, t);
+    }
+}
+
+static dim3 col_reduce_grid(long M, int C) {
+    const int gx = (C / 8 + 31) / 32;
+    long gy = (M + 255) / 256;
+    const long cap = (kNumSMs * 4 + gx - 1) / gx;
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    return dim3(gx, (unsigned)gy);
+}
+
+// ---- BatchNorm (training mode) ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const __nv_bfloat16 *__restrict__ Y, long M, int C, long ld, float *__restrict__ sums) {
+    col_reduce<2>(M, C, sums, [&](long r, int c0, float (&v)[2][8]) {
+        up8(__ldg((const uint4 *)(Y + r * ld + c0)), v[0]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[1][j] = v[0][j] * v[0][j];
+    });
+}
+
+// sums [2, C] -> mean_rstd [2, C], scale_shift [2, C] (z = y * scale + shift), running statistics (momentum, unbiased var)
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float *__restrict__ sums, float count, const float *__restrict__ gamma, const float *__restrict__ beta,
+                   float eps, float momentum, int C, float *__restrict__ mean_rstd, float *__restrict__ scale_shift,
+                   float *__restrict__ running_mean, float *__restrict__ running_var) {
+    for (int c = blockIdx.x * 256 + threadIdx.x; c < C; c += gridDim.x * 256) {
+        const float mean = sums[c] / count;
+        const float var = fmaxf(sums[C + c] / count - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        mean_rstd[c] = mean;
+        mean_rstd[C + c] = rstd;
+        const float a = gamma[c] * rstd;
+        scale_shift[c] = a;
+        scale_shift[C + c] = beta[c] - mean * a;
+        if (running_mean != nullptr) {
+            running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean;
+            running_var[c] = (1.0f - momentum) * running_var[c] + momentum * var * (count / fmaxf(count - 1.0f, 1.0f));
+        }
+    }
+}
+
+// out[r, :] (pitch ld_out) = residual[r, :] + out_scale * act(y * scale + shift)
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16 *__restrict__ Y, long total8, int C, const float *__restrict__ scale_shift, int act,
+                float out_scale, const __nv_bfloat16 *__restrict__ residual, long ld_res, __nv_bfloat16 *__restrict__ out,
+                long ld_out) {
+    const int C8 = C >> 3;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        const long r = i / C8;
+        const int c0 = cg * 8;
+        float y[8];
+        up8(__ldg((const uint4 *)Y + i), y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            y[j] = out_scale * act_fwd(fmaf(y[j], __ldg(scale_shift + c0 + j), __ldg(scale_shift + C + c0 + j)), act);
+        if (residual != nullptr) {
+            float q[8];
+            up8(__ldg((const uint4 *)(residual + r * ld_res + c0)), q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] += q[j];
+        }
+        *(uint4 *)(out + r * ld_out + c0) = pk8(y);
+    }
+}
+
+// pass 1 of the backward: sums2[c] += dz, sums2[C + c] += dz * xhat, dz = dA * out_scale * act'(z)
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dA, long ld_da, const __nv_bfloat16 *__restrict__ Y, long M, int C,
+                     const float *__restrict__ scale_shift, const float *__restrict__ mean_rstd, int act, float out_scale,
+                     float *__restrict__ sums2) {
+    col_reduce<2>(M, C, sums2, [&](long r, int c0, float (&v)[2][8]) {
+        float y[8], d[8];
+        up8(__ldg((const uint4 *)(Y + r * C + c0)), y);
+        up8(__ldg((const uint4 *)(dA + r * ld_da + c0)), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(y[j], __ldg(scale_shift + c0 + j), __ldg(scale_shift + C + c0 + j));
+            const float dz = d[j] * out_scale * act_bwd(z, act);
+            v[0][j] = dz;
+            v[1][j] = dz * (y[j] - __ldg(mean_rstd + c0 + j)) * __ldg(mean_rstd + C + c0 + j);
+        }
+    });
+}
+
+// pass 2: dY = gamma * rstd * (dz - s1 / M - xhat * s2 / M); block 0 also accumulates dgamma += s2, dbeta += s1
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dA, long ld_da, const __nv_bfloat16 *__restrict__ Y, long total8, int C,
+                    const float *__restrict__ scale_shift, const float *__restrict__ mean_rstd, int act, float out_scale,
+                    const float *__restrict__ sums2, float inv_m, __nv_bfloat16 *__restrict__ dY, float *__restrict__ dgamma,
+                    float *__restrict__ dbeta) {
+    const int C8 = C >> 3;
+    if (blockIdx.x == 0)
+        for (int c = threadIdx.x; c < C; c += 256) {
+            dgamma[c] += sums2[C + c];
+            dbeta[c] += sums2[c];
+        }
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        const long r = i / C8;
+        const int c0 = cg * 8;
+        float y[8], d[8];
+        up8(__ldg((const uint4 *)Y + i), y);
+        up8(__ldg((const uint4 *)(dA + r * ld_da + c0)), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float a = __ldg(scale_shift + c0 + j);                 // gamma * rstd
+            const float z = fmaf(y[j], a, __ldg(scale_shift + C + c0 + j));
+            const float dz = d[j] * out_scale * act_bwd(z, act);
+            const float xhat = (y[j] - __ldg(mean_rstd + c0 + j)) * __ldg(mean_rstd + C + c0 + j);
+            d[j] = a * (dz - __ldg(sums2 + c0 + j) * inv_m - xhat * __ldg(sums2 + C + c0 + j) * inv_m);
+        }
+        ((uint4 *)dY)[i] = pk8(d);
+    }
+}
+
+// ---- depthwise 3x3 backward ---------------------------------------------------------------------------------
+// dX[b, iy, ix, c] = add + sum_{ky,kx} dY[b, oy, ox, c] * w[ky*3+kx][c], oy * s + ky - 1 = iy (likewise x)
+__global__ void __launch_bounds__(256)
+dwconv_bwd_data_kernel(const __nv_bfloat16 *__restrict__ dY, const float *__restrict__ Wd, int H, int W, int C, int Ho,
+                       int Wo, int stride, const __nv_bfloat16 *__restrict__ add, long total8, __nv_bfloat16 *__restrict__ dX) {
+    const int C8 = C >> 3;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        long p = i / C8;
+        const int ix = (int)(p % W);
+        p /= W;
+        const int iy = (int)(p % H);
+        const long b = p / H;
+        float acc[8];
+        if (add != nullptr) up8(__ldg((const uint4 *)add + i), acc);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ty = iy + 1 - ky;
+            if (ty < 0 || (ty % stride) != 0) continue;
+            const int oy = ty / stride;
+            if (oy >= Ho) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int tx = ix + 1 - kx;
+                if (tx < 0 || (tx % stride) != 0) continue;
+                const int ox = tx / stride;
+                if (ox >= Wo) continue;
+                float d[8];
+                up8(__ldg((const uint4 *)(dY + ((b * Ho + oy) * Wo + ox) * C + cg * 8)), d);
+                const float *w = Wd + (long)(ky * 3 + kx) * C + cg * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(d[j], __ldg(w + j), acc[j]);
+            }
+        }
+        ((uint4 *)dX)[i] = pk8(acc);
+    }
+}
+
+// dW[c * 9 + k] += sum_{b,oy,ox} dY[b,oy,ox,c] * X[b, oy*s+ky-1, ox*s+kx-1, c]   (parameter layout [C,1,3,3])
+// CTA = 64 channels (8 groups) x 32 pixel lanes; each lane walks output pixels with 72 fp32 partials in registers.
+__global__ void __launch_bounds__(256)
+dwconv_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ dY, const __nv_bfloat16 *__restrict__ X, int B, int H, int W, int C,
+                         int Ho, int Wo, int stride, float *__restrict__ dW) {
+    __shared__ float red[32][65];
+    const int cgi = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    const int c0 = blockIdx.y * 64 + cgi * 8;
+    const bool c_ok = c0 < C;
+    float acc[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+    const long npx = (long)B * Ho * Wo;
+    if (c_ok)
+        for (long p = (long)blockIdx.x * 32 + pl; p < npx; p += (long)gridDim.x * 32) {
+            const int ox = (int)(p % Wo);
+            const long q = p / Wo;
+            const int oy = (int)(q % Ho);
+            const long b = q / Ho;
+            float d[8];
+            up8(__ldg((const uint4 *)(dY + p * C + c0)), d);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = oy * stride + ky - 1;
+                if (iy < 0 || iy >= H) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = ox * stride + kx - 1;
+                    if (ix < 0 || ix >= W) continue;
+                    float x[8];
+                    up8(__ldg((const uint4 *)(X + ((b * H + iy) * W + ix) * C + c0)), x);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(d[j], x[j], acc[ky * 3 + kx][j]);
+                }
+            }
+        }
+#pragma unroll 1
+    for (int t = 0; t < 9; ++t) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[pl][cgi * 8 + j] = acc[t][j];
+        __syncthreads();
+        if (threadIdx.x < 64 && blockIdx.y * 64 + threadIdx.x < C) {
+            float s = 0.f;
+#pragma unroll 8
+            for (int q = 0; q < 32; ++q) s += red[q][threadIdx.x];
+            atomicAdd(dW + (long)(blockIdx.y * 64 + threadIdx.x) * 9 + t, s);
+        }
+    }
+}
+
+// ---- SE / ECA gates -------------------------------------------------------------------------------------------
+// out[b, c] += sum_p dOut[b, p, c] * X[b, p, c]   (gradient reaching the gate); grid (chunks, B)
+__global__ void __launch_bounds__(256)
+gate_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dO, const __nv_bfloat16 *__restrict__ X, long HW, int C, int chunks,
+                       float *__restrict__ out) {
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int C8 = C >> 3;
+    const long per = (HW + chunks - 1) / chunks;
+    const long p0 = chunk * per, p1 = min(HW, p0 + per);
+    for (int cg = threadIdx.x; cg < C8; cg += 256) {
+        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (long p = p0; p < p1; ++p) {
+            float d[8], x[8];
+            up8(__ldg((const uint4 *)(dO + ((long)b * HW + p) * C + cg * 8)), d);
+            up8(__ldg((const uint4 *)(X + ((long)b * HW + p) * C + cg * 8)), x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = fmaf(d[j], x[j], s[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(out + (long)b * C + cg * 8 + j, s[j]);
+    }
+}
+
+// dX[b,p,c] = add + dOut[b,p,c] * gate[b,c] + dmean[b,c] * inv_hw
+__global__ void __launch_bounds__(256)
+gate_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ gate, const __nv_bfloat16 *__restrict__ dmean,
+                      float inv_hw, long HW, int C, const __nv_bfloat16 *__restrict__ add, long total8,
+                      __nv_bfloat16 *__restrict__ dX) {
+    const int C8 = C >> 3;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        const long b = (i / C8) / HW;
+        float d[8], m[8];
+        if (dO != nullptr) up8(__ldg((const uint4 *)dO + i), d);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] = 0.f;
+        }
+        if (dmean != nullptr) up8(__ldg((const uint4 *)(dmean + b * C + cg * 8)), m);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            d[j] *= gate != nullptr ? __ldg(gate + b * C + cg * 8 + j) : 1.0f;
+            if (dmean != nullptr) d[j] = fmaf(m[j], inv_hw, d[j]);
+        }
+        if (add != nullptr) {
+            float a[8];
+            up8(__ldg((const uint4 *)add + i), a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] += a[j];
+        }
+        ((uint4 *)dX)[i] = pk8(d);
+    }
+}
+
+// dz[b,c] (bf16) = dgate[b,c] * g (1 - g)     (through the sigmoid of the SE gate; operand of the SE backward GEMMs)
+__global__ void __launch_bounds__(256)
+sigmoid_bwd_kernel(const float *__restrict__ dgate, const float *__restrict__ gate, long n, __nv_bfloat16 *__restrict__ dz) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float g = gate[i];
+        dz[i] = __float2bfloat16_rn(dgate[i] * g * (1.0f - g));
+    }
+}
+
+// ECA backward, one CTA per image.  mode 0: gate multiplies a map (dgate given);  mode 1: feat = mean * gate (the
+// global_features tail): dgate = dfeat * mean and dmean gets the direct term dfeat * gate.
+__global__ void __launch_bounds__(256)
+eca_bwd_kernel(const float *__restrict__ dgate_in, const __nv_bfloat16 *__restrict__ dfeat, const float *__restrict__ gate,
+               const float *__restrict__ pool, int parts, float inv_hw, const float *__restrict__ w, int k, int C, int mode,
+               __nv_bfloat16 *__restrict__ dmean_out, float *__restrict__ dw) {
+    extern __shared__ float sm[];   // mean[C], dz[C]
+    float *mean = sm, *dz = sm + C;
+    __shared__ float wred[8];
+    const int b = blockIdx.x, half = (k - 1) / 2;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.f;
+        for (int q = 0; q < parts; ++q) t += pool[((long)b * parts + q) * C + c];
+        mean[c] = t * inv_hw;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const float g = gate[(long)b * C + c];
+        const float dg = mode == 0 ? dgate_in[(long)b * C + c] : __bfloat162float(dfeat[(long)b * C + c]) * mean[c];
+        dz[c] = dg * g * (1.0f - g);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float s = 0.f;                            // z[c'] = sum_t w[t] mean[c' + t - half]  ->  dmean[c] = sum_t w[t] dz[c - t + half]
+        for (int t = 0; t < k; ++t) {
+            const int cc = c - t + half;
+            if (cc >= 0 && cc < C) s = fmaf(__ldg(w + t), dz[cc], s);
+        }
+        if (mode == 1) s += __bfloat162float(dfeat[(long)b * C + c]) * gate[(long)b * C + c];
+        dmean_out[(long)b * C + c] = __float2bfloat16_rn(s);
+    }
+    for (int t = 0; t < k; ++t) {                 // dw[t] += sum_c dz[c] * mean[c + t - half]
+        float s = 0.f;
+        for (int c = threadIdx.x; c < C; c += 256) {
+            const int cc = c + t - half;
+            if (cc >= 0 && cc < C) s = fmaf(dz[c], mean[cc], s);
+        }
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tt = 0.f;
+            for (int q = 0; q < 8; ++q) tt += wred[q];
+            atomicAdd(dw + t, tt);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- CoordAttention backward ------------------------------------------------------------------------------
+// dZ [B, H+W, 2C] bf16 = gradient at the INPUT of the sigmoids of G (zero in the halves the forward does not use):
+//   rows h < H, cols c      : (sum_w dOut * X * a_w) * a_h (1 - a_h)
+//   rows H + w, cols C + c  : (sum_h dOut * X * a_h) * a_w (1 - a_w)
+__global__ void __launch_bounds__(256)
+coord_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dO, const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__restrict__ G,
+                        int H, int W, int C, __nv_bfloat16 *__restrict__ dZ) {
+    const int b = blockIdx.x, C8 = C >> 3;
+    const int n_rows = H + W;
+    for (int i = threadIdx.x; i < n_rows * C8; i += 256) {
+        const int r = i / C8, cg = i - r * C8;
+        const bool is_h = r < H;
+        const int n = is_h ? W : H;
+        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int q = 0; q < n; ++q) {
+            const int y = is_h ? r : q, x = is_h ? q : r - H;
+            float d[8], xv[8], go[8];
+            const long off = (((long)b * H + y) * W + x) * C + cg * 8;
+            up8(__ldg((const uint4 *)(dO + off)), d);
+            up8(__ldg((const uint4 *)(X + off)), xv);
+            // the OTHER direction's gate at this pixel
+            const long grow = is_h ? ((long)b * n_rows + H + x) * 2L * C + C : ((long)b * n_rows + y) * 2L * C;
+            up8(__ldg((const uint4 *)(G + grow + cg * 8)), go);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = fmaf(d[j] * xv[j], go[j], s[j]);
+        }
+        float gs[8], z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const long row = ((long)b * n_rows + r) * 2L * C;
+        up8(__ldg((const uint4 *)(G + row + (is_h ? 0 : C) + cg * 8)), gs);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] *= gs[j] * (1.0f - gs[j]);
+        *(uint4 *)(dZ + row + (is_h ? 0 : C) + cg * 8) = pk8(s);
+        *(uint4 *)(dZ + row + (is_h ? C : 0) + cg * 8) = pk8(z);
+    }
+}
+
+// dX = dOut * a_h * a_w + dP[b, h, c] / W + dP[b, H + w, c] / H
+__global__ void __launch_bounds__(256)
+coord_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dO, const __nv_bfloat16 *__restrict__ G, const __nv_bfloat16 *__restrict__ dP,
+                       int H, int W, int C, long total8, __nv_bfloat16 *__restrict__ dX) {
+    const int C8 = C >> 3;
+    const float iw = 1.0f / (float)W, ih = 1.0f / (float)H;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        long p = i / C8;
+        const int x = (int)(p % W);
+        p /= W;
+        const int y = (int)(p % H);
+        const long b = p / H;
+        float d[8], gh[8], gw[8], ph[8], pw[8];
+        up8(__ldg((const uint4 *)dO + i), d);
+        up8(__ldg((const uint4 *)(G + ((b * (H + W) + y) * 2L * C) + cg * 8)), gh);
+        up8(__ldg((const uint4 *)(G + ((b * (H + W) + H + x) * 2L * C) + C + cg * 8)), gw);
+        up8(__ldg((const uint4 *)(dP + (b * (H + W) + y) * (long)C + cg * 8)), ph);
+        up8(__ldg((const uint4 *)(dP + (b * (H + W) + H + x) * (long)C + cg * 8)), pw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = d[j] * gh[j] * gw[j] + ph[j] * iw + pw[j] * ih;
+        ((uint4 *)dX)[i] = pk8(d);
+    }
+}
+
+// ---- WASP branch mix (cnn.py:451-479) -----------------------------------------------------------------------
+// out = sum_i w_i * branch_i + w_last * global[b, c],  w = softmax(raw); branches [nb, B*HW, C] contiguous
+__global__ void __launch_bounds__(256)
+wasp_mix_kernel(const __nv_bfloat16 *__restrict__ branches, int nb, long branch_stride, const __nv_bfloat16 *__restrict__ glob,
+                const float *__restrict__ raw, long HW, int C, long total8, __nv_bfloat16 *__restrict__ out) {
+    __shared__ float w[8];
+    if (threadIdx.x == 0) {
+        float m = -1e30f, s = 0.f;
+        for (int i = 0; i <= nb; ++i) m = fmaxf(m, raw[i]);
+        for (int i = 0; i <= nb; ++i) s += __expf(raw[i] - m);
+        for (int i = 0; i <= nb; ++i) w[i] = __expf(raw[i] - m) / s;
+    }
+    __syncthreads();
+    const int C8 = C >> 3;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        const long b = (i / C8) / HW;
+        float acc[8], f[8];
+        up8(__ldg((const uint4 *)(glob + b * C + cg * 8)), acc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= w[nb];
+        for (int q = 0; q < nb; ++q) {
+            up8(__ldg((const uint4 *)(branches + q * branch_stride) + i), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(w[q], f[j], acc[j]);
+        }
+        ((uint4 *)out)[i] = pk8(acc);
+    }
+}
+
+// backward: dbranch_i = w_i * dOut (written), dglob[b,c] = w_last * sum_p dOut (atomic, fp32 [B,C]),
+// dots[i] += <dOut, branch_i> (i < nb), dots[nb] += <dOut, glob broadcast>   (fp32 [nb+1], zeroed by the caller)
+__global__ void __launch_bounds__(256)
+wasp_mix_bwd_kernel(const __nv_bfloat16 *__restrict__ dO, const __nv_bfloat16 *__restrict__ branches, int nb, long branch_stride,
+                    const __nv_bfloat16 *__restrict__ glob, const float *__restrict__ raw, long HW, int C, long total8,
+                    __nv_bfloat16 *__restrict__ dbranches, float *__restrict__ dglob, float *__restrict__ dots) {
+    __shared__ float w[8];
+    __shared__ float sdots[8];
+    if (threadIdx.x == 0) {
+        float m = -1e30f, s = 0.f;
+        for (int i = 0; i <= nb; ++i) m = fmaxf(m, raw[i]);
+        for (int i = 0; i <= nb; ++i) s += __expf(raw[i] - m);
+        for (int i = 0; i <= nb; ++i) w[i] = __expf(raw[i] - m) / s;
+    }
+    if (threadIdx.x < 8) sdots[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int C8 = C >> 3;
+    float dot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        const long b = (i / C8) / HW;
+        float d[8], f[8], o[8];
+        up8(__ldg((const uint4 *)dO + i), d);
+        up8(__ldg((const uint4 *)(glob + b * C + cg * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            dot[nb] = fmaf(d[j], f[j], dot[nb]);
+            atomicAdd(dglob + b * C + cg * 8 + j, w[nb] * d[j]);
+        }
+        for (int q = 0; q < nb; ++q) {
+            up8(__ldg((const uint4 *)(branches + q * branch_stride) + i), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                dot[q] = fmaf(d[j], f[j], dot[q]);
+                o[j] = w[q] * d[j];
+            }
+            ((uint4 *)(dbranches + q * branch_stride))[i] = pk8(o);
+        }
+    }
+    for (int q = 0; q <= nb; ++q) {
+        const float s = warp_sum(dot[q]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sdots[q], s);
+    }
+    __syncthreads();
+    if (threadIdx.x <= nb) atomicAdd(dots + threadIdx.x, sdots[threadIdx.x]);
+}
+
+// softmax backward for the nb+1 raw mixing weights: draw[i] += w_i * (dots[i] - sum_j w_j dots[j])
+__global__ void wasp_weights_bwd_kernel(const float *__restrict__ raw, const float *__restrict__ dots, int n, float *__restrict__ draw) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float w[8], m = -1e30f, s = 0.f, t = 0.f;
+        for (int i = 0; i < n; ++i) m = fmaxf(m, raw[i]);
+        for (int i = 0; i < n; ++i) s += __expf(raw[i] - m);
+        for (int i = 0; i < n; ++i) {
+            w[i] = __expf(raw[i] - m) / s;
+            t += w[i] * dots[i];
+        }
+        for (int i = 0; i < n; ++i) draw[i] += w[i] * (dots[i] - t);
+    }
+}
+
+// ---- pooling / striding / elementwise ---------------------------------------------------------------------
+// dX[b, 2y+dy, 2x+dx, c] = 0.25 * dY[b, y, x, c]
+__global__ void __launch_bounds__(256)
+avgpool2x2_bwd_kernel(const __nv_bfloat16 *__restrict__ dY, int H, int W, int C, long total8, __nv_bfloat16 *__restrict__ dX) {
+    const int C8 = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        long p = i / C8;
+        const int x = (int)(p % W);
+        p /= W;
+        const int y = (int)(p % H);
+        const long b = p / H;
+        float f[8];
+        up8(__ldg((const uint4 *)(dY + ((b * Ho + (y >> 1)) * Wo + (x >> 1)) * C + cg * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= 0.25f;
+        ((uint4 *)dX)[i] = pk8(f);
+    }
+}
+
+// dX[b, s*i, s*j, c] += dXs[b, i, j, c]   (data gradient of a strided 1x1 convolution, added into the full-size map)
+__global__ void __launch_bounds__(256)
+scatter_strided_add_kernel(const __nv_bfloat16 *__restrict__ dXs, int Ho, int Wo, int H, int W, int C, int stride, long total8,
+                           __nv_bfloat16 *__restrict__ dX) {
+    const int C8 = C >> 3;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        long p = i / C8;
+        const int x = (int)(p % Wo);
+        p /= Wo;
+        const int y = (int)(p % Ho);
+        const long b = p / Ho;
+        float a[8], d[8];
+        uint4 *dst = (uint4 *)(dX + ((b * H + (long)y * stride) * W + (long)x * stride) * C + cg * 8);
+        up8(*dst, a);
+        up8(__ldg((const uint4 *)dXs + i), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += d[j];
+        *dst = pk8(a);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+add_kernel(const __nv_bfloat16 *__restrict__ a, const __nv_bfloat16 *__restrict__ b, long n8, __nv_bfloat16 *__restrict__ out) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+        float x[8], y[8];
+        up8(__ldg((const uint4 *)a + i), x);
+        up8(__ldg((const uint4 *)b + i), y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += y[j];
+        ((uint4 *)out)[i] = pk8(x);
+    }
+}
+
+// counter-based dropout mask: element i of call `seed` is kept iff hash(seed, i) >= p * 2^32 (same mask in backward)
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return (uint32_t)x;
+}
+__global__ void __launch_bounds__(256)
+dropout_kernel(const __nv_bfloat16 *__restrict__ x, long n, uint32_t thresh, float keep_scale, uint64_t seed,
+               __nv_bfloat16 *__restrict__ out) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const bool keep = mix32(seed * 0x9E3779B97F4A7C15ULL + (uint64_t)i) >= thresh;
+        out[i] = __float2bfloat16_rn(keep ? __bfloat162float(x[i]) * keep_scale : 0.f);
+    }
+}
+
+// ---- table-driven parameter re-layout (one launch per step) --------------------------------------------------
+// kind 0: depthwise weight [C,1,3,3] fp32 -> fp32 [9, C]                                     (d0 = C)
+// kind 1: dense conv weight [Co,Ci,K,K] fp32 -> bf16 KRSC [Co, K, K, Cp]                       (d0 Co, d1 Ci, d2 K, d3 Cp)
+// kind 2: dense conv weight -> bf16 [Ci, K, K, Co] spatially flipped (the data-gradient conv)  (same dims, Cp ignored)
+// kind 3: matrix [R, Cc] fp32 -> bf16 [.., ld d2] top-left block (zero padding is never touched) (d0 R, d1 Cc, d2 ld)
+// kind 4: fp32 vector copy (d0 = n)
+// kind 5: (gradient, reverse of 1) fp32 KRSC [Co,K,K,Cp] workspace -> += into fp32 [Co,Ci,K,K]   (src = workspace)
+struct RepackEntry {
+    long src, dst;
+    int kind, d0, d1, d2, d3, pad;
+};
+__global__ void __launch_bounds__(256)
+repack_kernel(const RepackEntry *__restrict__ table, const float *__restrict__ src_f32, float *__restrict__ dst_f32,
+              __nv_bfloat16 *__restrict__ dst_bf16) {
+    const RepackEntry e = table[blockIdx.y];
+    const float *s = src_f32 + e.src;
+    long n;
+    switch (e.kind) {
+        case 0: n = (long)e.d0 * 9; break;
+        case 1: case 2: case 5: n = (long)e.d0 * e.d1 * e.d2 * e.d2; break;
+        case 3: n = (long)e.d0 * e.d1; break;
+        default: n = e.d0; break;
+    }
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+        if (e.kind == 0) {
+            const long c = i / 9, k = i - c * 9;
+            dst_f32[e.dst + k * e.d0 + c] = s[i];
+        } else if (e.kind == 1 || e.kind == 2 || e.kind == 5) {
+            const int K = e.d2, Ci = e.d1, Co = e.d0;
+            long t = i;
+            const int kw = (int)(t % K); t /= K;
+            const int kh = (int)(t % K); t /= K;
+            const int ci = (int)(t % Ci);
+            const int co = (int)(t / Ci);
+            if (e.kind == 1) dst_bf16[e.dst + (((long)co * K + kh) * K + kw) * e.d3 + ci] = __float2bfloat16_rn(s[i]);
+            else if (e.kind == 2)
+                dst_bf16[e.dst + (((long)ci * K + (K - 1 - kh)) * K + (K - 1 - kw)) * Co + co] = __float2bfloat16_rn(s[i]);
+            else dst_f32[e.dst + i] += s[(((long)co * K + kh) * K + kw) * e.d3 + ci];
+        } else if (e.kind == 3) {
+            const long r = i / e.d1, c = i - r * e.d1;
+            dst_bf16[e.dst + r * e.d2 + c] = __float2bfloat16_rn(s[i]);
+        } else {
+            dst_f32[e.dst + i] = s[i];
+        }
+    }
+}
+
+}  // namespace pose
+
+using namespace pose;
+
+#define REQ(c, e) do { if (!(c)) return (e); } while (0)
+
+POSE_API int pose_bn_stats_bf16(const void *Y, long M, int C, long ld, float *sums, pose_stream_t stream) {
+    REQ(Y && sums, POSE_E_NULL);
+    REQ(M > 0 && C > 0 && C % 8 == 0 && ld >= C && ld % 8 == 0, POSE_E_SHAPE);
+    REQ((uintptr_t)Y % 16 == 0, POSE_E_ALIGN);
+    bn_stats_kernel<<<col_reduce_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Y, M, C, ld, sums);
+    return launch_status();
+}
+
+POSE_API int pose_bn_finalize(const float *sums, long count, const float *gamma, const float *beta, float eps, float momentum,
+                              int C, float *mean_rstd, float *scale_shift, float *running_mean, float *running_var,
+                              pose_stream_t stream) {
+    REQ(sums && gamma && beta && mean_rstd && scale_shift, POSE_E_NULL);
+    REQ(count > 0 && C > 0, POSE_E_SHAPE);
+    bn_finalize_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, (float)count, gamma, beta, eps, momentum, C,
+                                                                         mean_rstd, scale_shift, running_mean, running_var);
+    return launch_status();
+}
+
+POSE_API int pose_bn_apply_bf16(const void *Y, long M, int C, const float *scale_shift, int act, float out_scale,
+                                const void *residual, long ld_res, void *out, long ld_out, pose_stream_t stream) {
+    REQ(Y && scale_shift && out, POSE_E_NULL);
+    REQ(M > 0 && C > 0 && C % 8 == 0 && ld_out >= C && ld_out % 8 == 0 && (!residual || (ld_res >= C && ld_res % 8 == 0)),
+        POSE_E_SHAPE);
+    REQ((uintptr_t)Y % 16 == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)residual % 16 == 0, POSE_E_ALIGN);
+    const long total8 = M * (C / 8);
+    bn_apply_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Y, total8, C, scale_shift, act,
+                                                                       out_scale, (const __nv_bfloat16 *)residual, ld_res,
+                                                                       (__nv_bfloat16 *)out, ld_out);
+    return launch_status();
+}
+
+POSE_API int pose_bn_bwd_bf16(const void *dA, long ld_da, const void *Y, long M, int C, const float *scale_shift,
+                              const float *mean_rstd, int act, float out_scale, float *sums2, void *dY, float *dgamma,
+                              float *dbeta, pose_stream_t stream) {
+    REQ(dA && Y && scale_shift && mean_rstd && sums2 && dY && dgamma && dbeta, POSE_E_NULL);
+    REQ(M > 0 && C > 0 && C % 8 == 0 && ld_da >= C && ld_da % 8 == 0, POSE_E_SHAPE);
+    REQ((uintptr_t)dA % 16 == 0 && (uintptr_t)Y % 16 == 0 && (uintptr_t)dY % 16 == 0, POSE_E_ALIGN);
+    cudaStream_t s = (cudaStream_t)stream;
+    bn_bwd_reduce_kernel<<<col_reduce_grid(M, C), 256, 0, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, M, C,
+                                                              scale_shift, mean_rstd, act, out_scale, sums2);
+    const long total8 = M * (C / 8);
+    bn_bwd_apply_kernel<<<grid_for(total8), 256, 0, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, total8, C,
+                                                        scale_shift, mean_rstd, act, out_scale, sums2, 1.0f / (float)M,
+                                                        (__nv_bfloat16 *)dY, dgamma, dbeta);
+    return launch_status();
+}
+
+POSE_API int pose_dwconv3x3_bwd_bf16(const void *dY, const void *X, const float *Wd, int B, int H, int W, int C, int stride,
+                                     const void *add, void *dX, float *dW, pose_stream_t stream) {
+    REQ(dY && Wd && (dX || dW) && (!dW || X), POSE_E_NULL);
+    REQ(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2), POSE_E_SHAPE);
+    const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dX) {
+        const long total8 = (long)B * H * W * (C / 8);
+        dwconv_bwd_data_kernel<<<grid_for(total8), 256, 0, s>>>((const __nv_bfloat16 *)dY, Wd, H, W, C, Ho, Wo, stride,
+                                                               (const __nv_bfloat16 *)add, total8, (__nv_bfloat16 *)dX);
+    }
+    if (dW) {
+        const long npx = (long)B * Ho * Wo;
+        const int gy = (C + 63) / 64;
+        long gx = (npx + 32 * 16 - 1) / (32 * 16);
+        const long cap = (kNumSMs * 8 + gy - 1) / gy;
+        if (gx > cap) gx = cap;
+        if (gx < 1) gx = 1;
+        dwconv_bwd_weight_kernel<<<dim3((unsigned)gx, gy), 256, 0, s>>>((const __nv_bfloat16 *)dY, (const __nv_bfloat16 *)X, B, H, W,
+                                                                       C, Ho, Wo, stride, dW);
+    }
+    return launch_status();
+}
+
+POSE_API int pose_gate_bwd_reduce_bf16(const void *dOut, const void *X, int B, long HW, int C, float *dgate, pose_stream_t stream) {
+    REQ(dOut && X && dgate, POSE_E_NULL);
+    REQ(B > 0 && HW > 0 && C > 0 && C % 8 == 0, POSE_E_SHAPE);
+    long chunks = (kNumSMs * 4 + B - 1) / B;
+    if (chunks > HW / 8) chunks = HW / 8;
+    if (chunks < 1) chunks = 1;
+    gate_bwd_reduce_kernel<<<dim3((unsigned)chunks, B), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dOut,
+                                                                                       (const __nv_bfloat16 *)X, HW, C, (int)chunks, dgate);
+    return launch_status();
+}
+
+POSE_API int pose_gate_bwd_apply_bf16(const void *dOut, const float *gate, const void *dmean, float inv_hw, int B, long HW, int C,
+                                      const void *add, void *dX, pose_stream_t stream) {
+    REQ((dOut || dmean) && dX, POSE_E_NULL);      /* dOut NULL: dX = dmean / HW broadcast (gradient of a global average) */
+    REQ(B > 0 && HW > 0 && C > 0 && C % 8 == 0, POSE_E_SHAPE);
+    const long total8 = (long)B * HW * (C / 8);
+    gate_bwd_apply_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dOut, gate,
+                                                                             (const __nv_bfloat16 *)dmean, inv_hw, HW, C,
+                                                                             (const __nv_bfloat16 *)add, total8, (__nv_bfloat16 *)dX);
+    return launch_status();
+}
+
+POSE_API int pose_sigmoid_bwd(const float *dgate, const float *gate, long n, void *dz, pose_stream_t stream) {
+    REQ(dgate && gate && dz, POSE_E_NULL);
+    REQ(n > 0, POSE_E_SHAPE);
+    sigmoid_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dgate, gate, n, (__nv_bfloat16 *)dz);
+    return launch_status();
+}
+
+POSE_API int pose_eca_bwd(const float *dgate, const void *dfeat, const float *gate, const float *pool_sum, int parts, float inv_hw,
+                          const float *w, int k, int B, int C, int mode, void *dmean, float *dw, pose_stream_t stream) {
+    REQ(gate && pool_sum && w && dmean && dw && (mode == 0 ? (const void *)dgate : dfeat), POSE_E_NULL);
+    REQ(B > 0 && C > 0 && k > 0 && (k & 1) && parts >= 1, POSE_E_SHAPE);
+    eca_bwd_kernel<<<B, 256, (size_t)2 * C * sizeof(float), (cudaStream_t)stream>>>(dgate, (const __nv_bfloat16 *)dfeat, gate, pool_sum,
+                                                                                   parts, inv_hw, w, k, C, mode,
+                                                                                   (__nv_bfloat16 *)dmean, dw);
+    return launch_status();
+}
+
+POSE_API int pose_coord_bwd_reduce_bf16(const void *dOut, const void *X, const void *G, int B, int H, int W, int C, void *dZ,
+                                        pose_stream_t stream) {
+    REQ(dOut && X && G && dZ, POSE_E_NULL);
+    REQ(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, POSE_E_SHAPE);
+    coord_bwd_reduce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dOut, (const __nv_bfloat16 *)X,
+                                                                (const __nv_bfloat16 *)G, H, W, C, (__nv_bfloat16 *)dZ);
+    return launch_status();
+}
+
+POSE_API int pose_coord_bwd_apply_bf16(const void *dOut, const void *G, const void *dP, int B, int H, int W, int C, void *dX,
+                                       pose_stream_t stream) {
+    REQ(dOut && G && dP && dX, POSE_E_NULL);
+    REQ(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, POSE_E_SHAPE);
+    const long total8 = (long)B * H * W * (C / 8);
+    coord_bwd_apply_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dOut, (const __nv_bfloat16 *)G,
+                                                                              (const __nv_bfloat16 *)dP, H, W, C, total8,
+                                                                              (__nv_bfloat16 *)dX);
+    return launch_status();
+}
+
+POSE_API int pose_wasp_mix_bf16(const void *branches, int nb, const void *glob, const float *raw_weights, int B, long HW, int C,
+                                void *out, pose_stream_t stream) {
+    REQ(branches && glob && raw_weights && out, POSE_E_NULL);
+    REQ(nb > 0 && nb < 8 && B > 0 && HW > 0 && C > 0 && C % 8 == 0, POSE_E_SHAPE);
+    const long total8 = (long)B * HW * (C / 8);
+    wasp_mix_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)branches, nb, (long)B * HW * C,
+                                                                       (const __nv_bfloat16 *)glob, raw_weights, HW, C, total8,
+                                                                       (__nv_bfloat16 *)out);
+    return launch_status();
+}
+
+POSE_API int pose_wasp_mix_bwd_bf16(const void *dOut, const void *branches, int nb, const void *glob, const float *raw_weights,
+                                    int B, long HW, int C, void *dbranches, float *dglob, float *dots, float *draw,
+                                    pose_stream_t stream) {
+    REQ(dOut && branches && glob && raw_weights && dbranches && dglob && dots && draw, POSE_E_NULL);
+    REQ(nb > 0 && nb < 8 && B > 0 && HW > 0 && C > 0 && C % 8 == 0, POSE_E_SHAPE);
+    const long total8 = (long)B * HW * (C / 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    wasp_mix_bwd_kernel<<<grid_for(total8, 256, 4), 256, 0, s>>>((const __nv_bfloat16 *)dOut, (const __nv_bfloat16 *)branches, nb,
+                                                                (long)B * HW * C, (const __nv_bfloat16 *)glob, raw_weights, HW, C,
+                                                                total8, (__nv_bfloat16 *)dbranches, dglob, dots);
+    wasp_weights_bwd_kernel<<<1, 32, 0, s>>>(raw_weights, dots, nb + 1, draw);
+    return launch_status();
+}
+
+POSE_API int pose_avgpool2x2_bwd_bf16(const void *dY, int B, int H, int W, int C, void *dX, pose_stream_t stream) {
+    REQ(dY && dX, POSE_E_NULL);
+    REQ(B > 0 && H > 0 && W > 0 && !(H & 1) && !(W & 1) && C > 0 && C % 8 == 0, POSE_E_SHAPE);
+    const long total8 = (long)B * H * W * (C / 8);
+    avgpool2x2_bwd_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dY, H, W, C, total8,
+                                                                             (__nv_bfloat16 *)dX);
+    return launch_status();
+}
+
+POSE_API int pose_scatter_strided_add_bf16(const void *dXs, int B, int Ho, int Wo, int H, int W, int C, int stride, void *dX,
+                                           pose_stream_t stream) {
+    REQ(dXs && dX, POSE_E_NULL);
+    REQ(B > 0 && Ho > 0 && Wo > 0 && C > 0 && C % 8 == 0 && stride >= 1 && (Ho - 1) * stride < H && (Wo - 1) * stride < W,
+        POSE_E_SHAPE);
+    const long total8 = (long)B * Ho * Wo * (C / 8);
+    scatter_strided_add_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dXs, Ho, Wo, H, W, C, stride,
+                                                                                  total8, (__nv_bfloat16 *)dX);
+    return launch_status();
+}
+
+POSE_API int pose_add_bf16(const void *a, const void *b, long n, void *out, pose_stream_t stream) {
+    REQ(a && b && out, POSE_E_NULL);
+    REQ(n > 0 && n % 8 == 0, POSE_E_SHAPE);
+    add_kernel<<<grid_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a, (const __nv_bfloat16 *)b, n / 8,
+                                                                 (__nv_bfloat16 *)out);
+    return launch_status();
+}
+
+POSE_API int pose_dropout_bf16(const void *x, long n, float p, uint64_t seed, void *out, pose_stream_t stream) {
+    REQ(x && out, POSE_E_NULL);
+    REQ(n > 0 && p >= 0.f && p < 1.f, POSE_E_SHAPE);
+    const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+    dropout_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x, n, thresh, 1.0f / (1.0f - p), seed,
+                                                                 (__nv_bfloat16 *)out);
+    return launch_status();
+}
+
+POSE_API int pose_param_repack(const void *table, int n_entries, const float *src_f32, float *dst_f32, void *dst_bf16,
+                               pose_stream_t stream) {
+    REQ(table && src_f32, POSE_E_NULL);
+    REQ(n_entries > 0, POSE_E_SHAPE);
+    repack_kernel<<<dim3(32, n_entries), 256, 0, (cudaStream_t)stream>>>((const RepackEntry *)table, src_f32, dst_f32,
+                                                                        (__nv_bfloat16 *)dst_bf16);
+    return launch_status();
+}

@@ -398,7 +398,29 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     mbar_wait(empty + s, ph ^ 1);
                     unsigned char *sa = smem + s * S::kStageBytes, *sb = sa + S::kABytes;
                     mbar_expect_tx(full + s, S::kStageBytes);
-                    if (MODE == 0 && A_MN) {
+                    if (MODE == 2) {
+                        // convolution weight gradient: the contraction block is a patch of 64 OUTPUT PIXELS; A = dY^T
+                        // (two boxes of 64 output channels), B = the input activation at one filter tap per 64-column
+                        // block (4-D boxes, zero fill outside the image = the convolution padding)
+                        const int tiles_w = cg.Wo / cg.TW, tiles_h = cg.Ho / cg.TH;
+                        int t = kb;
+                        const int tw = t % tiles_w;
+                        t /= tiles_w;
+                        const int th = t % tiles_h;
+                        const int pimg = (t / tiles_h) * cg.TN, poh = th * cg.TH, pow_ = tw * cg.TW;
+                        tma_load_4d(sa, &map_a, full + s, mt * BM, pow_, poh, pimg);
+                        tma_load_4d(sa + 64 * 128, &map_a, full + s, mt * BM + 64, pow_, poh, pimg);
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) {
+                            const int jb = n0 / 64 + j;
+                            const int tap = jb / cg.cchunks, cc = jb - tap * cg.cchunks;
+                            const int kh = tap / cg.KW, kw = tap - kh * cg.KW;
+                            // past the last tap: a box that is entirely out of bounds (zero filled, full byte count)
+                            const int c0 = tap < cg.taps ? cc * 64 : cg.cchunks * 64;
+                            tma_load_4d(sb + j * 64 * 128, &map_w, full + s, c0, pow_ * cg.stride + kw * cg.dil - cg.pad,
+                                        poh * cg.stride + kh * cg.dil - cg.pad, pimg);
+                        }
+                    } else if (MODE == 0 && A_MN) {
                         // two boxes of 64 MN elements x BKC contraction rows
                         tma_load_2d(sa, &map_a, full + s, mt * BM, kb * BKC);
                         tma_load_2d(sa + BKC * 128, &map_a, full + s, mt * BM + 64, kb * BKC);
@@ -410,7 +432,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         tma_load_4d(sa, &map_a, full + s, cc * BKC, ow0 * cg.stride + kw * cg.dil - cg.pad,
                                     oh0 * cg.stride + kh * cg.dil - cg.pad, img);
                     }
-                    if (B_MN) {
+                    if (MODE == 2) {
+                    } else if (B_MN) {
 #pragma unroll
                         for (int j = 0; j < BN / 64; ++j)
                             tma_load_2d(sb + j * BKC * 128, &map_w, full + s, n0 + j * 64, kb * BKC);
@@ -469,7 +492,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BN;
             const int r = quarter * 32 + lane;
             long row;       // global output row of tile row r (this lane's accumulator row)
-            if (MODE == 0) {
+            if (MODE != 1) {
                 row = (long)mt * BM + r;
                 if (row >= M) row = -1;
             } else {
@@ -758,6 +781,40 @@ POSE_API int pose_conv2d_bf16(const void *X, int Nimg, int H, int Wd, int Cin, c
     cudaStream_t s = (cudaStream_t)stream;
     if (bkc == 64) return dispatch_bn<64, 1>(ma, Wt, K, M, N, K, ep, cg, m_tiles, s);
     return dispatch_bn<32, 1>(ma, Wt, K, M, N, K, ep, cg, m_tiles, s);
+}
+
+POSE_API int pose_conv2d_wgrad_bf16(const void *dY, const void *X, int Nimg, int H, int Wd, int Cin, int Cout, int KH, int KW,
+                                    int stride, int dil, int pad, float *dWk, int k_splits, pose_stream_t stream) {
+    using namespace pose;
+    if (!dY || !X || !dWk) return POSE_E_NULL;
+    if (Nimg <= 0 || H <= 0 || Wd <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || stride <= 0 || dil <= 0 || pad < 0)
+        return POSE_E_SHAPE;
+    if (Cin % 64 || Cout % 8) return POSE_E_UNSUPPORTED;       // 128-byte channel chunks (the training input is padded)
+    if ((uintptr_t)dY % 16 || (uintptr_t)X % 16 || (uintptr_t)dWk % 16) return POSE_E_ALIGN;
+    const int Ho = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, Wo = (Wd + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+    int TW = 64;
+    while (TW > 1 && (Wo % TW)) TW >>= 1;
+    int TH = 64 / TW, TN = 1;
+    if (TH > Ho) {
+        if ((TH % Ho) || TW != Wo) return POSE_E_UNSUPPORTED;
+        TN = TH / Ho;
+        TH = Ho;
+    }
+    if (TW * TH * TN != 64 || Ho % TH || Wo % TW) return POSE_E_UNSUPPORTED;
+    const int patches = ((Nimg + TN - 1) / TN) * (Ho / TH) * (Wo / TW);
+    const int M = Cout, N = KH * KW * Cin, K = patches * 64;
+    pose_gemm_epilogue pe = {nullptr, nullptr, dWk, N, 0, 0, 0, 1.0f, 0.0f, nullptr, 1, 0};
+    Epilogue ep;
+    int e = check_epilogue(&pe, N, ep);
+    if (e) return e;
+    CUtensorMap ma, mw;
+    e = make_map_nhwc(&ma, dY, Nimg, Ho, Wo, Cout, 64, TW, TH, TN, 1);
+    if (e) return e;
+    e = make_map_nhwc(&mw, X, Nimg, H, Wd, Cin, 64, TW, TH, TN, stride);
+    if (e) return e;
+    ConvGeom cg = {Ho, Wo, TH, TW, TN, Nimg, KW, KH * KW, stride, dil, pad, Cin / 64};
+    const int m_tiles = (M + BM - 1) / BM;
+    return launch_gemm<128, 4, 64, 2, 1, 1>(ma, mw, M, N, K, ep, cg, m_tiles, (cudaStream_t)stream, k_splits);
 }
 
 POSE_API int pose_cast_f32_bf16(const float *in, void *out, long n, pose_stream_t stream) {

@@ -196,10 +196,12 @@ class CNNPoseEstimation(nn.Module):  # cnn.py:482-665
 
     def forward(self, image, depth, keypoints_2d):
         """image [B,3,S,S], depth [B,1,S,S], keypoints_2d [B,J,2] (fp32, CUDA) -> joints [B,J,3] fp32."""
+        if self.training and torch.is_grad_enabled():
+            plan = self.plan(image.shape[0], image.device)
+            return _CnnTrainFn.apply(plan, image, depth, keypoints_2d, self.wasp.weights)
         if self.training:
-            raise NotImplementedError(
-                "the training-mode (batch-statistics BatchNorm + autograd) path of the B200 CNN is not built yet; "
-                "call model.eval() (SURVEY.md 8a row H) -- see DESIGN.md section 1")
+            raise NotImplementedError("training-mode forward under no_grad (batch statistics without backward): "
+                                      "call model.eval() for inference")
         B = image.shape[0]
         key = (B, image.device.index)
         plan = self._plans.get(key)
@@ -207,6 +209,32 @@ class CNNPoseEstimation(nn.Module):  # cnn.py:482-665
             plan = CnnInferencePlan(self, B, image.device)
             self._plans[key] = plan
         return plan.run(image, depth, keypoints_2d)
+
+    def plan(self, B, device):
+        """Training launch plan (forward with batch statistics + backward) at batch size B."""
+        from .cnn_train import CnnTrainPlan
+        key = ("train", B, device.index)
+        p = self._plans.get(key)
+        if p is None or not p.flat.intact():
+            p = CnnTrainPlan(self, B, device)
+            self._plans[key] = p
+        return p
+
+
+class _CnnTrainFn(torch.autograd.Function):
+    """Autograd node of the whole model: backward runs the plan's reverse pass, which accumulates straight into the
+    parameters' flat ``.grad`` views (the `anchor` parameter only ties the node into the graph)."""
+
+    @staticmethod
+    def forward(ctx, plan, image, depth, kp, anchor):
+        ctx.plan = plan
+        out = plan.forward(image, depth, kp, save=True)
+        return out.view(-1, plan.J, 3).clone()
+
+    @staticmethod
+    def backward(ctx, dout):
+        ctx.plan.backward(dout.contiguous().view(dout.shape[0], -1))
+        return None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------------

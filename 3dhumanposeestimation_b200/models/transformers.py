@@ -460,7 +460,7 @@ class VitPlan:
         if dx_name is None:
             return None
         dx = self.buf(dx_name, M, K)
-        e = self._epi(dx, K, act=(self.act + 3) if act_u is not None else 0, residual=act_u, ldr=K)
+        e = self._epi(dx, K, act={2: 6, 3: 5}[self.act] if act_u is not None else 0, residual=act_u, ldr=K)
         self.call("pose_gemm_bf16_tr", dy.data_ptr(), ldy, 0, w16.data_ptr(), K, 1, M, K, N, 1, C.byref(e))
         return dx
 

@@ -188,6 +188,10 @@ int pose_conv2d_bf16(const void *X, int Nimg, int H, int W, int Cin, const void 
  * ------------------------------------------------------------------------------------------- */
 int pose_cnn_input_pack(const float *image, const float *depth, const float *kp, int B, int S, int J, float sigma,
                         void *out, pose_stream_t stream);
+/* same, pixel pitch c_stride >= 32 channels (channels 32.. are left untouched: zero them once); the training step pads
+ * the conv1 operand to 64 channels so that its weight gradient reads 128-byte channel chunks */
+int pose_cnn_input_pack_ex(const float *image, const float *depth, const float *kp, int B, int S, int J, float sigma,
+                           int c_stride, void *out, pose_stream_t stream);
 int pose_dwconv3x3_pool_parts(int H, int W, int stride); /* partial-sum slots per image the kernel writes */
 int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, const float *Wd, const float *bias, int stride,
                         int act, void *Y, float *pool_sum, int pool_parts, pose_stream_t stream);
@@ -263,6 +267,66 @@ int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V, const v
 int pose_adamw_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, void *shadow_bf16, long n, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, int zero_grad,
                     pose_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * D/G. CNN training step                reference: loss.backward() over src/models/cnn.py (src/train.py:83-92)
+ *  pose_conv2d_wgrad_bf16   weight gradient of a dense convolution as an implicit GEMM on tcgen05: dWk[Cout, KH*KW*Cin]
+ *                           (fp32, KRSC, ACCUMULATED) += sum over output pixels of dY[pixel, co] * X[pixel @ tap, ci];
+ *                           the contraction runs over patches of 64 output pixels fetched by 4-D TMA boxes (zero fill =
+ *                           padding), split k_splits ways.  Cin % 64 == 0.  The data gradient of a stride-1 convolution is
+ *                           pose_conv2d_bf16 over dY with the flipped / transposed weights (pose_param_repack kind 2).
+ *  BatchNorm2d in training mode (batch statistics, cnn.py:135-139), fused with activation, residual add and concat:
+ *   pose_bn_stats_bf16      sums[c] += sum_r y, sums[C + c] += sum_r y^2          (sums zeroed by the caller)
+ *   pose_bn_finalize        mean / rstd, the affine (scale, shift) that normalises, running statistics (momentum,
+ *                           unbiased variance) -- nn.BatchNorm2d semantics
+ *   pose_bn_apply_bf16      out[r, :ld_out] = residual + out_scale * act(y * scale + shift)
+ *   pose_bn_bwd_bf16        dY from dA (pitch ld_da: a column slice of a concatenation) -- two passes (per-channel sums, then
+ *                           the gradient); dgamma, dbeta accumulated; sums2 [2, C] zeroed by the caller
+ *  pose_dwconv3x3_bwd_bf16  depthwise 3x3 backward: dX (+ add) and / or dW (parameter layout [C,1,3,3], accumulated)
+ *  pose_gate_bwd_*          x * gate[b, c] (SE / ECA): dgate[b,c] += sum_p dOut * x;  dX = add + dOut * gate + dmean / HW
+ *  pose_sigmoid_bwd, pose_eca_bwd, pose_coord_bwd_*, pose_wasp_mix_*: see csrc/cnn_train.cu
+ *  pose_avgpool2x2_bwd_bf16, pose_scatter_strided_add_bf16 (data gradient of a strided 1x1 conv), pose_add_bf16
+ *  pose_dropout_bf16        counter-based mask hash(seed, i) -- the same call on the gradient is the backward
+ *  pose_param_repack        one launch re-lays-out every parameter the kernels read in another layout / precision
+ *                           (table of pose_repack_entry on the device; kinds documented in csrc/cnn_train.cu)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pose_repack_entry {
+    int64_t src, dst;
+    int32_t kind, d0, d1, d2, d3, pad;
+} pose_repack_entry;
+
+int pose_conv2d_wgrad_bf16(const void *dY, const void *X, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
+                           int dil, int pad, float *dWk, int k_splits, pose_stream_t stream);
+int pose_bn_stats_bf16(const void *Y, long M, int C, long ld, float *sums, pose_stream_t stream);
+int pose_bn_finalize(const float *sums, long count, const float *gamma, const float *beta, float eps, float momentum, int C,
+                     float *mean_rstd, float *scale_shift, float *running_mean, float *running_var, pose_stream_t stream);
+int pose_bn_apply_bf16(const void *Y, long M, int C, const float *scale_shift, int act, float out_scale, const void *residual,
+                       long ld_res, void *out, long ld_out, pose_stream_t stream);
+int pose_bn_bwd_bf16(const void *dA, long ld_da, const void *Y, long M, int C, const float *scale_shift, const float *mean_rstd,
+                     int act, float out_scale, float *sums2, void *dY, float *dgamma, float *dbeta, pose_stream_t stream);
+int pose_dwconv3x3_bwd_bf16(const void *dY, const void *X, const float *Wd, int B, int H, int W, int C, int stride,
+                            const void *add, void *dX, float *dW, pose_stream_t stream);
+int pose_gate_bwd_reduce_bf16(const void *dOut, const void *X, int B, long HW, int C, float *dgate, pose_stream_t stream);
+int pose_gate_bwd_apply_bf16(const void *dOut, const float *gate, const void *dmean, float inv_hw, int B, long HW, int C,
+                             const void *add, void *dX, pose_stream_t stream);
+int pose_sigmoid_bwd(const float *dgate, const float *gate, long n, void *dz, pose_stream_t stream);
+int pose_eca_bwd(const float *dgate, const void *dfeat, const float *gate, const float *pool_sum, int parts, float inv_hw,
+                 const float *w, int k, int B, int C, int mode, void *dmean, float *dw, pose_stream_t stream);
+int pose_coord_bwd_reduce_bf16(const void *dOut, const void *X, const void *G, int B, int H, int W, int C, void *dZ,
+                               pose_stream_t stream);
+int pose_coord_bwd_apply_bf16(const void *dOut, const void *G, const void *dP, int B, int H, int W, int C, void *dX,
+                              pose_stream_t stream);
+int pose_wasp_mix_bf16(const void *branches, int nb, const void *glob, const float *raw_weights, int B, long HW, int C, void *out,
+                       pose_stream_t stream);
+int pose_wasp_mix_bwd_bf16(const void *dOut, const void *branches, int nb, const void *glob, const float *raw_weights, int B,
+                           long HW, int C, void *dbranches, float *dglob, float *dots, float *draw, pose_stream_t stream);
+int pose_avgpool2x2_bwd_bf16(const void *dY, int B, int H, int W, int C, void *dX, pose_stream_t stream);
+int pose_scatter_strided_add_bf16(const void *dXs, int B, int Ho, int Wo, int H, int W, int C, int stride, void *dX,
+                                  pose_stream_t stream);
+int pose_add_bf16(const void *a, const void *b, long n, void *out, pose_stream_t stream);
+int pose_dropout_bf16(const void *x, long n, float p, uint64_t seed, void *out, pose_stream_t stream);
+int pose_param_repack(const void *table, int n_entries, const float *src_f32, float *dst_f32, void *dst_bf16,
+                      pose_stream_t stream);
 
 #ifdef __cplusplus
 }

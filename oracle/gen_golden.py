@@ -352,11 +352,62 @@ def gen_vit():
                              "with Generator(9): image, depth, kp, gt in that order")
 
 
+CNN_TRAIN_CFG = dict(image_size=(256, 256), heatmap_size=256, regression_dropout=0.0)
+
+
+def gen_cnn_train():
+    """One training step of the live reference CNN (model.train(): batch-statistics BatchNorm; dropout 0 so that the step
+    is deterministic) at 256x256, batch 4: predictions, loss, per-parameter gradient norms and the updated BatchNorm
+    running statistics.  The functional oracle (oracle.torch_models.cnn_forward(train=True)) must reproduce them: it is
+    what the GPU tests differentiate."""
+    import torch
+    from model_config import ModelConfig
+    from models.cnn import CNNPoseEstimation
+    from loss import ComprehensivePoseLoss
+    sys.path.insert(0, REPO)
+    from oracle import torch_models as tm
+    cfg = ModelConfig("cnn", **CNN_TRAIN_CFG)
+    m = CNNPoseEstimation(cfg)
+    sd = tm.fill_state_dict(m.state_dict(), seed=5)
+    m.load_state_dict(sd)
+    m.train()
+    g = torch.Generator().manual_seed(21)
+    B = 4
+    img = torch.rand(B, 3, 256, 256, generator=g)
+    dep = torch.rand(B, 1, 256, 256, generator=g)
+    kp = torch.rand(B, 17, 2, generator=g) * 0.9 + 0.05
+    kp[2, 7] = -1.0
+    gt = torch.randn(B, 17, 3, generator=g) * 300
+    pred = m(img, dep, kp)
+    total, _ = ComprehensivePoseLoss()(pred, gt)
+    total.backward()
+    names = [n for n, _ in m.named_parameters()]
+    gnorm = np.array([p.grad.double().norm().item() for _, p in m.named_parameters()])
+    sdg = {k: (v.clone().requires_grad_() if v.is_floating_point() and k in names else v.clone()) for k, v in sd.items()}
+    po, new_stats = tm.cnn_forward(sdg, cfg, img, dep, kp, train=True, return_stats=True)
+    to, _ = ComprehensivePoseLoss()(po, gt)
+    to.backward()
+    gn_o = np.array([sdg[n].grad.double().norm().item() for n in names])
+    # parameters whose gradient is analytically zero (an affine shift that the next BatchNorm removes) hold rounding
+    # noise six orders of magnitude below the real gradients: compare with an absolute floor
+    assert np.allclose(gn_o, gnorm, rtol=5e-3, atol=2e-6 * gnorm.max()), np.abs(gn_o - gnorm).max()
+    after = m.state_dict()
+    for k, v in new_stats.items():
+        assert torch.allclose(v, after[k], rtol=1e-4, atol=1e-5), k
+    rm = np.array([after[k].double().sum().item() for k in sorted(after) if k.endswith("running_mean")])
+    rv = np.array([after[k].double().sum().item() for k in sorted(after) if k.endswith("running_var")])
+    np.savez_compressed(os.path.join(OUT, "cnn_train_256.npz"), versions=versions(), fill_seed=5, input_seed=21,
+                        kp=kp.numpy(), gt=gt.numpy(), pred=pred.detach().numpy(), loss=np.float32(total.item()),
+                        grad_names=np.array(names), grad_norms=gnorm, running_mean_sums=rm, running_var_sums=rv,
+                        note="live reference CNNPoseEstimation.train() step, B=4, inputs torch.rand with Generator(21): "
+                             "image, depth, kp, gt in that order")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, os.path.join(REF, "src"))
     os.chdir(tempfile.mkdtemp(prefix="pose_golden_"))
-    which = sys.argv[1:] or ["augment", "heatmap", "loss", "config", "cnn", "vit"]
+    which = sys.argv[1:] or ["augment", "heatmap", "loss", "config", "cnn", "vit", "cnn_train"]
     for w in which:
         globals()["gen_" + w]()
         print("wrote", w)

@@ -34,8 +34,8 @@ class _Ctx:
     """Walks a state_dict by prefix; in train mode batch statistics are used and the updated running
     statistics are collected in ``new_stats`` (momentum 0.1, unbiased variance -- nn.BatchNorm2d)."""
 
-    def __init__(self, sd, train, act):
-        self.sd, self.train, self.act, self.new_stats = sd, train, act, {}
+    def __init__(self, sd, train, act, trace=None):
+        self.sd, self.train, self.act, self.new_stats, self.trace = sd, train, act, {}, trace
 
     def bn(self, x, p):
         w, b = self.sd[p + ".weight"], self.sd[p + ".bias"]
@@ -54,7 +54,10 @@ class _Ctx:
         pad = (k - 1) // 2 * dilation
         x = F.conv2d(x, w, None, stride, pad, dilation, groups)
         x = self.bn(x, p + ".norm")
-        return _act(x, self.act if act == "default" else act)
+        x = _act(x, self.act if act == "default" else act)
+        if self.trace is not None:
+            self.trace[p] = x.detach()
+        return x
 
     def dw(self, x, p, stride=1):
         return self.conv_bn_act(x, p, stride=stride, groups=x.shape[1])
@@ -146,10 +149,11 @@ def heatmaps(kp, hs, sigma):  # common.py:23-51
     return hm * (kp > 0).all(-1)[..., None, None]
 
 
-def cnn_forward(sd, cfg, image, depth, kp, train=False, return_stats=False):
-    """cfg: an object / dict with the reference ModelConfig('cnn') attributes."""
+def cnn_forward(sd, cfg, image, depth, kp, train=False, return_stats=False, trace=None):
+    """cfg: an object / dict with the reference ModelConfig('cnn') attributes.  `trace` (dict) collects the output of
+    every ConvBnAct by state-dict prefix (layer-by-layer comparisons in the tests)."""
     g = (lambda k: cfg[k]) if isinstance(cfg, dict) else (lambda k: getattr(cfg, k))
-    c = _Ctx(sd, train, g("activation"))
+    c = _Ctx(sd, train, g("activation"), trace)
     x = torch.cat([image, depth, heatmaps(kp, g("heatmap_size"), g("heatmap_sigma"))], 1)
     x = c.conv_bn_act(x, "conv1.0", stride=g("initial_stride"))
     x = c.conv_bn_act(x, "conv1.1")
