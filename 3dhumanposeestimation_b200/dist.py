@@ -53,3 +53,21 @@ def job_throughput(units_this_rank: float, elapsed_ms_this_rank: float, device=N
     total = sum_over_ranks(units_this_rank, device)
     slowest = max_over_ranks(elapsed_ms_this_rank, device)
     return total / (slowest * 1e-3)
+
+
+def bucket_ranges(lo: int, hi: int, bucket_elems: int):
+    """[lo, hi) cut into buckets of at most bucket_elems elements, LAST bucket first: the order in which the backward
+    pass finishes the flat gradient buffer (model tail first)."""
+    out, pos = [], hi
+    step = max(1, int(bucket_elems))
+    while pos > lo:
+        a = max(lo, pos - step)
+        out.append((a, pos))
+        pos = a
+    return out
+
+
+def allreduce_range(flat_grad: torch.Tensor, lo: int, hi: int, bucket_elems: int, group=None):
+    """Sum-all-reduce flat_grad[lo:hi) in buckets (the data-parallel gradient exchange)."""
+    for a, b in bucket_ranges(lo, hi, bucket_elems):
+        dist.all_reduce(flat_grad[a:b], op=dist.ReduceOp.SUM, group=group)

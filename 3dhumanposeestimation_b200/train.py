@@ -16,7 +16,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib  # noqa: F401
+from .dist import allreduce_range
 from .loss import pose_loss_fwd_bwd
 from .optim import AdamW
 
@@ -42,14 +43,9 @@ class Trainer:
             return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
-        step = max(1, self.bucket_bytes // 4)
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ev)
-            pos = hi
-            while pos > lo:
-                a = max(lo, pos - step)
-                dist.all_reduce(flat.grad[a:pos], op=dist.ReduceOp.SUM, group=self.pg)
-                pos = a
+            allreduce_range(flat.grad, lo, hi, self.bucket_bytes // 4, self.pg)
 
     def _wait_comm(self):
         if self.world > 1:

@@ -8,8 +8,11 @@ N > 1 is launched by torchrun (one rank per GPU).  Rank 0 prints ONE JSON line.
 Workloads (BASELINE.json configs):
   preproc_b256   configs[1]: PoseAugmentor + heat-map / regression head + composite loss kernels,
                  batch 256 of 256x256 RGB-D per GPU.  One step = one pass of that chain over one batch.
-The same line also carries `cnn_infer`: the eval-mode CNNPoseEstimation forward (configs[4], batch sweep) on the
-tcgen05 path, as measured evidence for rows D/H of SURVEY.md 8a (the training step, configs[2..3], is not built yet).
+  cnn_train      configs[2]: CNNPoseEstimation full training step (forward, composite loss, backward, AdamW), bf16
+                 tensor cores, batch 128 per GPU, data parallel (gradient all-reduce over NCCL overlapped with backward).
+  vit_train      configs[3]: TransformerPoseEstimation full training step, batch 64 per GPU, data parallel.
+The default line (preproc_b256) also carries `train` (both training steps at this N, so the 1/2/4/8-GPU runs record
+their scaling) and `cnn_infer` (configs[4]: eval-mode CNN forward, batch sweep).
 """
 from __future__ import annotations
 
@@ -311,6 +314,9 @@ def run_b200(args):
     e2e_value = dutil.job_throughput(B * args.steps, e2e_ms, dev)
 
     cnn = measure_cnn_infer(pose, dev, rank) if args.cnn else None
+    train_res = None
+    if args.train:
+        train_res = {k: measure_train(pose, dev, rank, world, k, max(3, min(args.steps, 10)), 3) for k in ("cnn", "vit")}
 
     # ---- the same end-to-end loop fed with uint8 host pixels (4x fewer PCIe bytes; augment_batch's uint8 input is
     #      defined to reproduce the reference's fp32 sample p/255 bit for bit, tests/test_gpu_parity.py) -------------
@@ -394,9 +400,190 @@ def run_b200(args):
                                     "loss": {"bytes": B * 632, "ms": kern_ms["loss"], "note": "latency bound at B=256"},
                                     "head (3 tcgen05 GEMMs + cast)": {"ms": kern_ms["head"]}}},
             "cnn_infer": cnn,
+            "train": train_res,
             "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": f"{reps} x the same B=256 batch ({cpu_dt:.1f} s wall, {cpu_dt * cores:.0f} core-s), oracle port (C) on all host threads"},
         }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+# training step (configs[2], configs[3]): forward + loss + backward + AdamW, data parallel
+# ----------------------------------------------------------------------------------------------------
+TRAIN_CFG = {
+    "cnn": dict(batch=128, gflop_per_sample=49.68, params=26_920_792),
+    "vit": dict(batch=64, gflop_per_sample=212.2, params=147_774_515),
+}
+
+
+def build_train_model(pose, kind, dev):
+    import torch
+    torch.manual_seed(SEED)
+    if kind == "cnn":
+        cfg = pose.ModelConfig("cnn", image_size=(H, W), heatmap_size=HS)     # reference defaults incl. dropout 0.2
+        return pose.CNNPoseEstimation(cfg).to(dev).train(), cfg
+    # dropout rates 0: the ViT dropout kernels are not built yet; everything else is the reference default
+    cfg = pose.ModelConfig("transformer", image_size=(H, W), vit_pretrained=False, transformer_dropout_rate=0.0,
+                           transformer_attention_dropout_rate=0.0, regression_dropout=0.0)
+    return pose.TransformerPoseEstimation(cfg).to(dev).train(), cfg
+
+
+def measure_train(pose, dev, rank, world, kind, steps, warmup, cpu_baseline=True):
+    """One rank's share of the data-parallel training step; returns the whole-job numbers (max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from importlib import import_module
+    train = import_module("3dhumanposeestimation_b200.train")
+    dutil = import_module("3dhumanposeestimation_b200.dist")
+    spec = TRAIN_CFG[kind]
+    Bn = spec["batch"]
+    model, cfg = build_train_model(pose, kind, dev)
+    if world > 1:
+        train.broadcast_parameters(model)
+    g = torch.Generator().manual_seed(SEED + rank)
+    host = dict(image=torch.rand(Bn, 3, H, W, generator=g).pin_memory(), depth=torch.rand(Bn, 1, H, W, generator=g).pin_memory(),
+                kp=(torch.rand(Bn, J, 2, generator=g) * 0.9 + 0.05).pin_memory(),
+                gt=(torch.randn(Bn, J, 3, generator=g) * 300).pin_memory())
+    d = {k: v.to(dev) for k, v in host.items()}
+    tr = train.Trainer(model, pose.ComprehensivePoseLoss(), lr=1e-3, weight_decay=0.01)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        o5 = tr.step(d["image"], d["depth"], d["kp"], d["gt"])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev.index) as clocks:
+        e0.record()
+        for _ in range(steps):
+            o5 = tr.step(d["image"], d["depth"], d["kp"], d["gt"])
+        e1.record()
+        barrier()
+    ms = dutil.max_over_ranks(e0.elapsed_time(e1), dev)
+    value = world * Bn * steps / ms * 1e3
+    plan = model.plan(Bn, dev)
+    launches = plan.launches + 3          # forward + backward kernels of the last step, loss, AdamW, workspace clear
+    # end to end: the batch comes from pinned host memory every step, the 5 loss scalars go back
+    res_host = torch.empty(5, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    stream = torch.cuda.current_stream()
+    bufs = [{k: torch.empty_like(d[k]) for k in host} for _ in range(2)]
+    ready, free = [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_steps(n):
+        for f in free:
+            f.record(stream)
+        for i in range(n + 1):
+            if i < n:
+                sidx = i & 1
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(free[sidx])
+                    for k in host:
+                        bufs[sidx][k].copy_(host[k], non_blocking=True)
+                    ready[sidx].record(copy_stream)
+            if i > 0:
+                sidx = (i - 1) & 1
+                stream.wait_event(ready[sidx])
+                o = tr.step(bufs[sidx]["image"], bufs[sidx]["depth"], bufs[sidx]["kp"], bufs[sidx]["gt"])
+                res_host.copy_(o, non_blocking=True)
+                free[sidx].record(stream)
+        torch.cuda.synchronize()
+
+    e2e_steps(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps(steps)
+    barrier()
+    e2e_ms = dutil.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf = value * spec["gflop_per_sample"] / 1e3
+    out = {"model": kind, "batch_per_gpu": Bn, "n_gpus": world, "samples_per_s": value, "ms_per_step": ms / steps,
+           "tflops": tf, "tensor_frac_of_measured_sustained": tf / world / peaks.get("bf16_tflops_sustained", 1344.7),
+           "gflop_per_sample_train": spec["gflop_per_sample"], "launches_per_step": launches,
+           "loss_total": float(o5[4].item()), "clocks": clocks.summary(),
+           "e2e": {"value": world * Bn * steps / e2e_ms * 1e3, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": 20},
+           "dtype": "bf16 activations / weights on the tensor cores, fp32 accumulate, fp32 master weights + AdamW state",
+           "data": "synthetic", "parallelism": f"dp{world}" if world > 1 else "single GPU",
+           "optimizer": "fused AdamW lr 1e-3 wd 0.01 (main.py:154-156), accumulation_steps 1"}
+    if kind == "vit":
+        out["note"] = "dropout rates 0 (ViT dropout kernels not built yet); CNN runs the reference defaults (head dropout 0.2)"
+    if rank == 0 and cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_train_baseline(pose, kind, cfg)
+    del tr, model, plan, d, bufs
+    torch.cuda.empty_cache()
+    return out
+
+
+def cpu_train_baseline(pose, kind, cfg):
+    """The reference's CPU path of the same training step (fp32 PyTorch on the host cores): the oracle restatement, pinned
+    to the live reference by tests/golden (the reference itself cannot travel to the GPU box)."""
+    import torch
+    try:
+        from oracle import torch_models as tm
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        bs = 8 if kind == "cnn" else 2
+        model = (pose.CNNPoseEstimation(cfg) if kind == "cnn" else pose.TransformerPoseEstimation(cfg))
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        names = [n for n, _ in model.named_parameters()]
+        g = torch.Generator().manual_seed(SEED)
+        img, dep = torch.rand(bs, 3, H, W, generator=g), torch.rand(bs, 1, H, W, generator=g)
+        kp, gt = torch.rand(bs, J, 2, generator=g) * 0.9 + 0.05, torch.randn(bs, J, 3, generator=g) * 300
+        iu = torch.triu_indices(J, J, 1)
+        pd = lambda t: torch.linalg.norm(t[:, :, None] - t[:, None], dim=-1)[:, iu[0], iu[1]]   # noqa: E731
+
+        def step():
+            sdg = {k: (v.clone().requires_grad_() if k in names else v) for k, v in sd.items()}
+            po = tm.cnn_forward(sdg, cfg, img, dep, kp, train=True) if kind == "cnn" else tm.vit_forward(sdg, cfg, img, dep, kp)
+            d = po - gt
+            ((d ** 2).mean() + d.abs().mean() + 100.0 * (pd(po) - pd(gt)).abs().mean() + d[:, 0].abs().mean()).backward()
+        step()
+        t0 = time.perf_counter()
+        n = 2
+        for _ in range(n):
+            step()
+        dt = (time.perf_counter() - t0) / n
+        return {"value": bs / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+                "sample": f"fp32 forward + loss + backward, B={bs}, {n} repetitions ({dt * n:.1f} s); optimizer step not included"}
+    except Exception as exc:
+        return {"error": repr(exc)}
+
+
+def run_train(args, kind):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    importlib.import_module("3dhumanposeestimation_b200.build").build()
+    pose = importlib.import_module("3dhumanposeestimation_b200")
+    r = measure_train(pose, dev, rank, world, kind, args.steps, args.warmup)
+    if rank == 0:
+        line = {"metric": "train samples/sec", "value": r["samples_per_s"], "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{kind}_train", "batch_per_gpu": r["batch_per_gpu"], "image": [H, W],
+                           "parallelism": r["parallelism"], "l2": "activations of one step (GBs) exceed the 126 MB L2"},
+                "clocks": r["clocks"], "gpu_launches": r["launches_per_step"] * args.steps, "e2e": r["e2e"],
+                "roofline": {"bound": "tensor", "achieved": r["tflops"] / world, "peak": 1344.7, "unit": "TFLOP/s",
+                             "frac": r["tensor_frac_of_measured_sustained"], "traffic": None,
+                             "note": "whole step: nominal training FLOPs (SURVEY.md 8d) / step time, per GPU"},
+                "cpu_baseline": r.get("cpu_baseline"), "train": r}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -470,9 +657,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="preproc_b256")
     ap.add_argument("--no-cnn", dest="cnn", action="store_false", help="skip the CNN inference sweep")
+    ap.add_argument("--no-train", dest="train", action="store_false", help="skip the training-step measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in ("cnn_train", "vit_train"):
+        run_train(args, args.workload.split("_")[0])
     else:
         run_b200(args)
 

@@ -26,6 +26,12 @@ def _worker(rank, world, port, ret):
     ms = 10.0 + 5.0 * rank                      # rank 1 is slower
     out = dict(shard=(lo, hi), covered_once=bool((covered == 1).all()), max_ms=d.max_over_ranks(ms),
                total=d.sum_over_ranks(hi - lo), thr=d.job_throughput(256.0, ms), seed=d.rank_seed(42, rank))
+    # the data-parallel gradient exchange: bucketed all-reduce of a range of the flat gradient buffer, tail first
+    grad = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    d.allreduce_range(grad, 100, 900, 256)
+    want = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    want[100:900] = torch.arange(100, 900, dtype=torch.float32) * 3          # 1x + 2x over the two ranks
+    out["allreduce_ok"] = bool(torch.equal(grad, want))
     ret[rank] = out
     dist.destroy_process_group()
 
@@ -41,6 +47,7 @@ def test_sharding_and_timing_reductions_world2():
     assert r0["total"] == r1["total"] == 257
     assert abs(r0["thr"] - 512.0 / 15e-3) < 1e-6          # all units / slowest rank
     assert r0["seed"] != r1["seed"]
+    assert r0["allreduce_ok"] and r1["allreduce_ok"]
 
 
 def test_single_process_defaults():
@@ -49,3 +56,5 @@ def test_single_process_defaults():
     assert d.shard_range(10, 0, 1) == (0, 10)
     assert [d.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert d.max_over_ranks(3.5) == 3.5 and d.job_throughput(100, 50.0) == 2000.0
+    assert d.bucket_ranges(10, 100, 40) == [(60, 100), (20, 60), (10, 20)]      # model tail first
+    assert d.bucket_ranges(5, 5, 8) == []

@@ -203,5 +203,5 @@ def test_cnn_full_size_matches_fp32_oracle(pose, B):
         m.pose_head.decoder[-1].bias.add_(10.0)
         out3 = m(img, dep, kp)
     assert torch.allclose(out3, out + 10.0, atol=1e-3)
-    with pytest.raises(NotImplementedError):
-        m.train()(img, dep, kp)
+    with pytest.raises(NotImplementedError), torch.no_grad():
+        m.train()(img, dep, kp)            # batch statistics without a backward: eval() is the inference mode
