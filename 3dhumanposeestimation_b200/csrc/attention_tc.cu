@@ -1,0 +1,509 @@
+// attention_tc.cu -- scaled dot-product attention, forward and backward, on the tcgen05 tensor cores with the score
+// matrix resident in TMEM (reference: nn.MultiheadAttention in src/models/transformers.py:61-63, :98-106 and the timm
+// ViT attention it wraps; sequences of this model: 257 / 273 tokens self-attention, 256 x 16 and 16 x 256 cross-attention;
+// head_dim 64 | 48).
+//
+// Forward (one CTA per (sample, head), 128 threads, query tiles of 128 rows):
+//   Q tile, K, V are staged in shared memory in the 128-byte-swizzled UMMA image (one row = one token's head slice); K
+//   is the K-major B operand of S = Q K^T and the very same image of V is the MN-major B operand of O = P V.
+//   S (128 x Nk fp32) is accumulated in TMEM; each thread owns one query row (tcgen05.ld 32x32b): row max, exp2,
+//   row sum with no shuffles; P goes to shared memory as the K-major A operand (bf16); O accumulates in TMEM and is
+//   normalised on the way out.  The log-sum-exp of every row is saved for the backward pass.
+// Backward (probabilities rebuilt from the saved log-sum-exp, nothing of size Nq x Nk reaches HBM):
+//   dq kernel : per (sample, head): for every query tile and key chunk of 128: S, dP = dO V^T in TMEM ->
+//               dS = P (dP - D) scale -> shared memory -> dQ += dS K (K image read as an MN-major operand).
+//   dkv kernel: per (sample, head, 128-key tile): for every query tile: S^T = K Q^T, dP^T = V dO^T in TMEM -> P^T, dS^T
+//               -> shared memory -> dV += P^T dO, dK += dS^T Q (Q / dO images read as MN-major operands).
+#include "tc_common.cuh"
+
+namespace pose {
+
+constexpr int kAttnThreads = 128;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// rows of 128 B (one token's head slice, zero padded to 64 elements), 16-byte chunks XOR-swizzled by (row & 7):
+// the SWIZZLE_128B image both the K-major and the MN-major UMMA descriptors read
+template <int HD>
+__device__ __forceinline__ void load_rows_sw128(unsigned char *smem, const __nv_bfloat16 *g, long ld, int rows_valid,
+                                                int rows_total) {
+    for (int i = threadIdx.x; i < rows_total * 8; i += kAttnThreads) {
+        const int r = i >> 3, c = i & 7;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rows_valid && c < HD / 8) v = __ldg((const uint4 *)(g + (long)r * ld) + c);
+        *(uint4 *)(smem + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+    }
+}
+
+// 8 consecutive bf16 of row r, columns [col8 * 8, col8 * 8 + 8) of a K-major [128 x 64k] operand made of 16 KB blocks
+__device__ __forceinline__ void store_chunk_kmajor(unsigned char *base, int r, int col8, uint4 v) {
+    const int blk = col8 >> 3, c = col8 & 7;
+    *(uint4 *)(base + blk * 16384 + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *(uint32_t *)&h;
+}
+
+struct AttnSync {
+    uint64_t *bar;
+    uint32_t phase;
+    __device__ __forceinline__ void commit_and_wait() {     // thread 0 commits the MMAs issued so far; everybody waits
+        if (threadIdx.x == 0) tc_commit(bar);
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+    }
+};
+
+__device__ __forceinline__ uint32_t attn_prologue(unsigned char *&smem, uint64_t *&bar) {
+    extern __shared__ unsigned char smem_dyn[];
+    smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    bar = &s_bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return s_tmem;
+}
+
+__device__ __forceinline__ void attn_epilogue(uint32_t tmem_base) {
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K, const __nv_bfloat16 *__restrict__ V,
+                   __nv_bfloat16 *__restrict__ O, float *__restrict__ lse, int Nq, int Nk, int Nkp, long ldq, long ldk, long ldv,
+                   long ldo, long bsq, long bsk, long bsv, long bso, float scale) {
+    unsigned char *smem;
+    uint64_t *bar;
+    const uint32_t tmem = attn_prologue(smem, bar);
+    AttnSync sync{bar, 0};
+    unsigned char *Qs = smem, *Ks = Qs + 16384, *Vs = Ks + 288 * 128, *Ps = Vs + 288 * 128;   // P: 5 blocks of 16 KB
+    const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
+    const int warp = threadIdx.x >> 5;
+    const __nv_bfloat16 *qg = Q + b * bsq + (long)h * HD, *kg = K + b * bsk + (long)h * HD, *vg = V + b * bsv + (long)h * HD;
+    __nv_bfloat16 *og = O + b * bso + (long)h * HD;
+    load_rows_sw128<HD>(Ks, kg, ldk, Nk, Nkp);
+    load_rows_sw128<HD>(Vs, vg, ldv, Nk, Nkp);
+    const float sl2 = scale * kLog2e;
+    const uint32_t tO = tmem + 320;
+    const int nch = (Nkp + 31) / 32;
+    for (int q0 = 0; q0 < Nq; q0 += 128) {
+        const int rows = min(128, Nq - q0);
+        load_rows_sw128<HD>(Qs, qg + (long)q0 * ldq, ldq, rows, 128);
+        fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            const uint64_t da = umma_desc_k<128>(smem_u32(Qs));
+            for (int kc0 = 0; kc0 < Nkp; kc0 += 256) {
+                const int n = min(256, Nkp - kc0);
+                const uint32_t idesc = umma_idesc_bf16(128, n);
+                const uint64_t db = umma_desc_k<128>(smem_u32(Ks + kc0 * 128));
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tmem + kc0, da + 2 * k, db + 2 * k, idesc, k ? 1u : 0u);
+            }
+        }
+        sync.commit_and_wait();
+        const int r = threadIdx.x;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        float inv = 0.f;
+        if (q0 + warp * 32 < Nq) {                       // warps whose 32 rows are all padding skip the softmax
+            float m = -INFINITY;
+            for (int c = 0; c < nch; ++c) {
+                uint32_t v[32];
+                tmem_ld32(trow + c * 32, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c * 32 + j < Nk) m = fmaxf(m, __uint_as_float(v[j]));
+            }
+            const float ms = m * sl2;
+            float sum = 0.f;
+            for (int c = 0; c < nch; ++c) {
+                uint32_t v[32];
+                tmem_ld32(trow + c * 32, v);
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    float p[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = c * 32 + j8 * 8 + j;
+                        p[j] = col < Nk ? exp2f(fmaf(__uint_as_float(v[j8 * 8 + j]), sl2, -ms)) : 0.f;
+                        sum += p[j];
+                    }
+                    const int col8 = c * 4 + j8;
+                    if (col8 * 8 < Nkp)
+                        store_chunk_kmajor(Ps, r, col8, make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
+                                                                  pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7])));
+                }
+            }
+            inv = 1.0f / sum;
+            if (lse != nullptr && q0 + r < Nq) lse[((long)b * heads + h) * Nq + q0 + r] = m * scale + __logf(sum);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            constexpr uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
+            for (int ks = 0; ks < Nkp / 16; ++ks) {
+                const uint64_t da = umma_desc_k<128>(smem_u32(Ps + (ks >> 2) * 16384)) + 2 * (ks & 3);
+                const uint64_t db = umma_desc_mn(smem_u32(Vs + ks * 2048), 1024);
+                tc_mma_f16(tO, da, db, idesc, ks ? 1u : 0u);
+            }
+        }
+        sync.commit_and_wait();
+        if (q0 + warp * 32 < Nq) {                       // warp-uniform: tcgen05.ld is a warp-collective instruction
+            uint32_t v[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                tmem_ld32(tO + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+                if (q0 + r < Nq)
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        if (c * 32 + j8 * 8 >= HD) break;
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(v[j8 * 8]) * inv, __uint_as_float(v[j8 * 8 + 1]) * inv);
+                        o.y = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) * inv, __uint_as_float(v[j8 * 8 + 3]) * inv);
+                        o.z = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) * inv, __uint_as_float(v[j8 * 8 + 5]) * inv);
+                        o.w = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) * inv, __uint_as_float(v[j8 * 8 + 7]) * inv);
+                        *((uint4 *)(og + (long)(q0 + r) * ldo) + c * 4 + j8) = o;
+                    }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    attn_epilogue(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dQ (and D = rowsum(dO * O)) per (sample, head)
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_bwd_dq_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K, const __nv_bfloat16 *__restrict__ V,
+                      const __nv_bfloat16 *__restrict__ O, const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ lse,
+                      __nv_bfloat16 *__restrict__ dQ, float *__restrict__ Dout, int Nq, int Nk, int Nkp, long ldq, long ldk,
+                      long ldv, long ldo, long lddo, long lddq, long bsq, long bsk, long bsv, long bso, long bsdo, long bsdq,
+                      float scale) {
+    unsigned char *smem;
+    uint64_t *bar;
+    const uint32_t tmem = attn_prologue(smem, bar);
+    AttnSync sync{bar, 0};
+    unsigned char *Qs = smem, *dOs = Qs + 16384, *Ks = dOs + 16384, *Vs = Ks + 288 * 128, *dSs = Vs + 288 * 128;  // dS: 2 blocks
+    const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
+    const int warp = threadIdx.x >> 5, r = threadIdx.x;
+    const __nv_bfloat16 *qg = Q + b * bsq + (long)h * HD, *kg = K + b * bsk + (long)h * HD, *vg = V + b * bsv + (long)h * HD;
+    const __nv_bfloat16 *og = O + b * bso + (long)h * HD, *dog = dO + b * bsdo + (long)h * HD;
+    __nv_bfloat16 *dqg = dQ + b * bsdq + (long)h * HD;
+    load_rows_sw128<HD>(Ks, kg, ldk, Nk, Nkp);
+    load_rows_sw128<HD>(Vs, vg, ldv, Nk, Nkp);
+    const float sl2 = scale * kLog2e;
+    const uint32_t tS = tmem, tP = tmem + 128, tQ = tmem + 256;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    for (int q0 = 0; q0 < Nq; q0 += 128) {
+        const int rows = min(128, Nq - q0);
+        load_rows_sw128<HD>(Qs, qg + (long)q0 * ldq, ldq, rows, 128);
+        load_rows_sw128<HD>(dOs, dog + (long)q0 * lddo, lddo, rows, 128);
+        // D = rowsum(dO * O), log-sum-exp (in exp2 units) of this thread's row
+        float Dr = 0.f, l2 = 0.f;
+        const bool row_ok = q0 + r < Nq;
+        if (row_ok) {
+            const uint4 *po = (const uint4 *)(og + (long)(q0 + r) * ldo), *pd = (const uint4 *)(dog + (long)(q0 + r) * lddo);
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c) {
+                const uint4 a = __ldg(po + c), d = __ldg(pd + c);
+                const __nv_bfloat162 *ha = (const __nv_bfloat162 *)&a, *hd = (const __nv_bfloat162 *)&d;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 fa = __bfloat1622float2(ha[j]), fd = __bfloat1622float2(hd[j]);
+                    Dr = fmaf(fa.x, fd.x, fmaf(fa.y, fd.y, Dr));
+                }
+            }
+            const long idx = ((long)b * heads + h) * Nq + q0 + r;
+            Dout[idx] = Dr;
+            l2 = lse[idx] * kLog2e;
+        }
+        for (int kc0 = 0; kc0 < Nkp; kc0 += 128) {
+            const int n = min(128, Nkp - kc0);
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                tc_fence_after();
+                const uint32_t idesc = umma_idesc_bf16(128, n);
+                const uint64_t dq = umma_desc_k<128>(smem_u32(Qs)), dd = umma_desc_k<128>(smem_u32(dOs));
+                const uint64_t dk = umma_desc_k<128>(smem_u32(Ks + kc0 * 128)), dv = umma_desc_k<128>(smem_u32(Vs + kc0 * 128));
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tS, dq + 2 * k, dk + 2 * k, idesc, k ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tP, dd + 2 * k, dv + 2 * k, idesc, k ? 1u : 0u);
+            }
+            sync.commit_and_wait();
+            if (q0 + warp * 32 < Nq) {
+                for (int c = 0; c < (n + 31) / 32; ++c) {
+                    uint32_t s[32], p[32];
+                    tmem_ld32(tS + lane_off + c * 32, s);
+                    tmem_ld32(tP + lane_off + c * 32, p);
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        float ds[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int col = kc0 + c * 32 + j8 * 8 + j;
+                            const float pr = (col < Nk && row_ok) ? exp2f(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -l2)) : 0.f;
+                            ds[j] = pr * (__uint_as_float(p[j8 * 8 + j]) - Dr) * scale;
+                        }
+                        const int col8 = c * 4 + j8;
+                        if (col8 * 8 < n)
+                            store_chunk_kmajor(dSs, r, col8, make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]),
+                                                                        pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7])));
+                    }
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                tc_fence_after();
+                constexpr uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
+                for (int ks = 0; ks < n / 16; ++ks) {
+                    const uint64_t da = umma_desc_k<128>(smem_u32(dSs + (ks >> 2) * 16384)) + 2 * (ks & 3);
+                    const uint64_t db = umma_desc_mn(smem_u32(Ks + (kc0 + ks * 16) * 128), 1024);
+                    tc_mma_f16(tQ, da, db, idesc, (kc0 | ks) ? 1u : 0u);
+                }
+            }
+            sync.commit_and_wait();
+        }
+        if (q0 + warp * 32 < Nq) {
+            uint32_t v[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                tmem_ld32(tQ + lane_off + c * 32, v);
+                if (row_ok)
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        if (c * 32 + j8 * 8 >= HD) break;
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(v[j8 * 8]), __uint_as_float(v[j8 * 8 + 1]));
+                        o.y = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]), __uint_as_float(v[j8 * 8 + 3]));
+                        o.z = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]), __uint_as_float(v[j8 * 8 + 5]));
+                        o.w = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]), __uint_as_float(v[j8 * 8 + 7]));
+                        *((uint4 *)(dqg + (long)(q0 + r) * lddq) + c * 4 + j8) = o;
+                    }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    attn_epilogue(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dK, dV per (128-key tile, head, sample)
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_bwd_dkv_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K, const __nv_bfloat16 *__restrict__ V,
+                       const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ lse, const float *__restrict__ Dg,
+                       __nv_bfloat16 *__restrict__ dK, __nv_bfloat16 *__restrict__ dV, int Nq, int Nk, long ldq, long ldk, long ldv,
+                       long lddo, long lddk, long lddv, long bsq, long bsk, long bsv, long bsdo, long bsdk, long bsdv, float scale) {
+    unsigned char *smem;
+    uint64_t *bar;
+    const uint32_t tmem = attn_prologue(smem, bar);
+    AttnSync sync{bar, 0};
+    unsigned char *Kt = smem, *Vt = Kt + 16384, *Qs = Vt + 16384, *dOs = Qs + 16384, *PT = dOs + 16384, *dST = PT + 32768;
+    __shared__ float lse_s[128], D_s[128];
+    const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z, heads = gridDim.y;
+    const int warp = threadIdx.x >> 5, r = threadIdx.x;
+    const __nv_bfloat16 *qg = Q + b * bsq + (long)h * HD, *kg = K + b * bsk + (long)h * HD, *vg = V + b * bsv + (long)h * HD;
+    const __nv_bfloat16 *dog = dO + b * bsdo + (long)h * HD;
+    const int krows = min(128, Nk - k0);
+    load_rows_sw128<HD>(Kt, kg + (long)k0 * ldk, ldk, krows, 128);
+    load_rows_sw128<HD>(Vt, vg + (long)k0 * ldv, ldv, krows, 128);
+    const float sl2 = scale * kLog2e;
+    const uint32_t tS = tmem, tP = tmem + 128, tV = tmem + 256, tK = tmem + 320;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const bool warp_ok = k0 + warp * 32 < Nk;
+    for (int q0 = 0; q0 < Nq; q0 += 128) {
+        const int rows = min(128, Nq - q0);
+        const int np = (rows + 15) / 16 * 16;            // query columns of this tile, padded to the UMMA N / K granularity
+        load_rows_sw128<HD>(Qs, qg + (long)q0 * ldq, ldq, rows, 128);
+        load_rows_sw128<HD>(dOs, dog + (long)q0 * lddo, lddo, rows, 128);
+        {
+            const bool ok = q0 + r < Nq;
+            const long idx = ((long)b * heads + h) * Nq + q0 + r;
+            lse_s[r] = ok ? lse[idx] * kLog2e : 0.f;
+            D_s[r] = ok ? Dg[idx] : 0.f;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            const uint32_t idesc = umma_idesc_bf16(128, np);
+            const uint64_t dk = umma_desc_k<128>(smem_u32(Kt)), dv = umma_desc_k<128>(smem_u32(Vt));
+            const uint64_t dq = umma_desc_k<128>(smem_u32(Qs)), dd = umma_desc_k<128>(smem_u32(dOs));
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tS, dk + 2 * k, dq + 2 * k, idesc, k ? 1u : 0u);     // S^T = K Q^T
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tP, dv + 2 * k, dd + 2 * k, idesc, k ? 1u : 0u);     // dP^T = V dO^T
+        }
+        sync.commit_and_wait();
+        if (warp_ok) {
+            for (int c = 0; c < (np + 31) / 32; ++c) {
+                uint32_t s[32], p[32];
+                tmem_ld32(tS + lane_off + c * 32, s);
+                tmem_ld32(tP + lane_off + c * 32, p);
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    float pv[8], ds[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = c * 32 + j8 * 8 + j;                  // query within the tile
+                        const float pr = col < rows ? exp2f(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -lse_s[col])) : 0.f;
+                        pv[j] = pr;
+                        ds[j] = pr * (__uint_as_float(p[j8 * 8 + j]) - D_s[col]) * scale;
+                    }
+                    const int col8 = c * 4 + j8;
+                    if (col8 * 8 < np) {
+                        store_chunk_kmajor(PT, r, col8, make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]),
+                                                                   pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7])));
+                        store_chunk_kmajor(dST, r, col8, make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]),
+                                                                    pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7])));
+                    }
+                }
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            constexpr uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
+            for (int ks = 0; ks < np / 16; ++ks) {
+                const uint64_t dp = umma_desc_k<128>(smem_u32(PT + (ks >> 2) * 16384)) + 2 * (ks & 3);
+                const uint64_t ds = umma_desc_k<128>(smem_u32(dST + (ks >> 2) * 16384)) + 2 * (ks & 3);
+                const uint64_t bo = umma_desc_mn(smem_u32(dOs + ks * 2048), 1024);
+                const uint64_t bq = umma_desc_mn(smem_u32(Qs + ks * 2048), 1024);
+                tc_mma_f16(tV, dp, bo, idesc, (q0 | ks) ? 1u : 0u);      // dV += P^T dO
+                tc_mma_f16(tK, ds, bq, idesc, (q0 | ks) ? 1u : 0u);      // dK += dS^T Q
+            }
+        }
+        sync.commit_and_wait();      // the Q / dO / P^T / dS^T images are overwritten by the next query tile
+    }
+    if (warp_ok) {
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            __nv_bfloat16 *og = which == 0 ? dV + b * bsdv + (long)h * HD : dK + b * bsdk + (long)h * HD;
+            const long ldo = which == 0 ? lddv : lddk;
+            const uint32_t t = (which == 0 ? tV : tK) + lane_off;
+            uint32_t v[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                tmem_ld32(t + c * 32, v);
+                if (k0 + r < Nk)
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        if (c * 32 + j8 * 8 >= HD) break;
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(v[j8 * 8]), __uint_as_float(v[j8 * 8 + 1]));
+                        o.y = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]), __uint_as_float(v[j8 * 8 + 3]));
+                        o.z = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]), __uint_as_float(v[j8 * 8 + 5]));
+                        o.w = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]), __uint_as_float(v[j8 * 8 + 7]));
+                        *((uint4 *)(og + (long)(k0 + r) * ldo) + c * 4 + j8) = o;
+                    }
+            }
+        }
+    }
+    attn_epilogue(tmem);
+}
+
+constexpr int kFwdSmem = 16384 + 2 * 288 * 128 + 5 * 16384 + 1024;
+constexpr int kDqSmem = 2 * 16384 + 2 * 288 * 128 + 2 * 16384 + 1024;
+constexpr int kDkvSmem = 4 * 16384 + 2 * 32768 + 1024;
+
+template <class Kern>
+static int set_smem(Kern kern, int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e == cudaSuccess ? POSE_OK : (int)e;
+}
+
+}  // namespace pose
+
+using namespace pose;
+
+POSE_API int pose_attention_bf16(const void *Q, const void *K, const void *V, void *O, int B, int heads, int Nq, int Nk,
+                                 int head_dim, long ldq, long ldk, long ldv, long ldo, long bsq, long bsk, long bsv, long bso,
+                                 float scale, float *lse, pose_stream_t stream) {
+    if (!Q || !K || !V || !O) return POSE_E_NULL;
+    if (B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return POSE_E_SHAPE;
+    if (head_dim != 48 && head_dim != 64) return POSE_E_UNSUPPORTED;
+    if (Nk > 288) return POSE_E_UNSUPPORTED;              // the whole score row lives in TMEM (<= 288 columns)
+    if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || bsq % 8 || bsk % 8 || bsv % 8 || bso % 8) return POSE_E_ALIGN;
+    if ((uintptr_t)Q % 16 || (uintptr_t)K % 16 || (uintptr_t)V % 16 || (uintptr_t)O % 16) return POSE_E_ALIGN;
+    const int Nkp = (Nk + 15) / 16 * 16;
+    const dim3 grid(heads, B);
+    cudaStream_t s = (cudaStream_t)stream;
+    int e;
+#define FWD(HD_)                                                                                                       \
+    if ((e = set_smem(attn_fwd_tc_kernel<HD_>, kFwdSmem))) return e;                                                    \
+    attn_fwd_tc_kernel<HD_><<<grid, kAttnThreads, kFwdSmem, s>>>((const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K,     \
+                                                                (const __nv_bfloat16 *)V, (__nv_bfloat16 *)O, lse, Nq, Nk, Nkp, \
+                                                                ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale)
+    if (head_dim == 64) { FWD(64); } else { FWD(48); }
+#undef FWD
+    return launch_status();
+}
+
+POSE_API int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V, const void *O, const void *dO,
+                                     const float *lse, void *dQ, void *dK, void *dV, float *Dws, int B, int heads, int Nq,
+                                     int Nk, int head_dim, long ldq, long ldk, long ldv, long ldo, long lddo, long lddq,
+                                     long lddk, long lddv, long bsq, long bsk, long bsv, long bso, long bsdo, long bsdq,
+                                     long bsdk, long bsdv, float scale, pose_stream_t stream) {
+    if (!Q || !K || !V || !O || !dO || !lse || !dQ || !dK || !dV || !Dws) return POSE_E_NULL;
+    if (B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return POSE_E_SHAPE;
+    if (head_dim != 48 && head_dim != 64) return POSE_E_UNSUPPORTED;
+    if (Nk > 288) return POSE_E_UNSUPPORTED;
+    const long al[] = {ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv};
+    for (long a : al)
+        if (a % 8) return POSE_E_ALIGN;
+    const void *ptrs[] = {Q, K, V, O, dO, dQ, dK, dV};
+    for (const void *q : ptrs)
+        if ((uintptr_t)q % 16) return POSE_E_ALIGN;
+    const int Nkp = (Nk + 15) / 16 * 16;
+    cudaStream_t s = (cudaStream_t)stream;
+    const dim3 g1(heads, B), g2((Nk + 127) / 128, heads, B);
+    int e;
+#define BWD(HD_)                                                                                                       \
+    if ((e = set_smem(attn_bwd_dq_tc_kernel<HD_>, kDqSmem))) return e;                                                  \
+    if ((e = set_smem(attn_bwd_dkv_tc_kernel<HD_>, kDkvSmem))) return e;                                                \
+    attn_bwd_dq_tc_kernel<HD_><<<g1, kAttnThreads, kDqSmem, s>>>(                                                       \
+        (const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V, (const __nv_bfloat16 *)O,        \
+        (const __nv_bfloat16 *)dO, lse, (__nv_bfloat16 *)dQ, Dws, Nq, Nk, Nkp, ldq, ldk, ldv, ldo, lddo, lddq, bsq, bsk,  \
+        bsv, bso, bsdo, bsdq, scale);                                                                                  \
+    attn_bwd_dkv_tc_kernel<HD_><<<g2, kAttnThreads, kDkvSmem, s>>>(                                                     \
+        (const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V, (const __nv_bfloat16 *)dO, lse,  \
+        Dws, (__nv_bfloat16 *)dK, (__nv_bfloat16 *)dV, Nq, Nk, ldq, ldk, ldv, lddo, lddk, lddv, bsq, bsk, bsv, bsdo,    \
+        bsdk, bsdv, scale)
+    if (head_dim == 64) { BWD(64); } else { BWD(48); }
+#undef BWD
+    return launch_status();
+}

@@ -1,17 +1,12 @@
 // vit_ops.cu -- the non-GEMM pieces of TransformerPoseEstimation.forward (src/models/transformers.py:326-373 and the
 // timm ViT-B/16 backbone it wraps): LayerNorm, token assembly (cls + tokens + positional embedding), patch
 // extraction for the k16/s16 patch-embedding convolutions (which then run as plain tcgen05 GEMMs), and scaled
-// dot-product attention for the short sequences of this model (<= 288 keys: 257 backbone, 273 final encoder,
-// 16 / 256 cross-modal), with the whole score row resident in shared memory.
+// the backward of those pieces, and the fused AdamW step.
 //
-// Attention uses warp-level bf16 tensor-core MMAs (nvcuda::wmma, mma.sync) -- a first correct version; the
-// tcgen05/TMEM flash-attention kernel is the planned replacement.  It is ~6 % of the model's FLOPs.
-#include <mma.h>
+// Attention itself runs on the tcgen05 tensor cores: attention_tc.cu.
 #include "common.cuh"
 
 namespace pose {
-
-using namespace nvcuda;
 
 __device__ __forceinline__ void unpack8v(const uint4 &p, float (&f)[8]) {
     const __nv_bfloat162 *h = (const __nv_bfloat162 *)&p;
@@ -132,117 +127,6 @@ patchify_kernel(const float *__restrict__ src0, int C0, const float *__restrict_
         out[i] = __float2bfloat16_rn(v);
     }
 }
-
-// ---------------------------------------------------------------------------------------------------------
-// Attention: O[b, q, h*HD:(h+1)*HD] = softmax(Q K^T * scale) V for one (64-query tile, head, batch) per CTA.
-// Q/K/V rows have arbitrary pitches (packed qkv or separate projections); the whole score strip (64 x Nk) lives
-// in shared memory, so there is no online rescaling.  4 warps, 16 query rows each.
-// ---------------------------------------------------------------------------------------------------------
-template <int HD>
-__global__ void __launch_bounds__(128)
-attention_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K, const __nv_bfloat16 *__restrict__ V,
-                 __nv_bfloat16 *__restrict__ O, float *__restrict__ lse, int Nq, int Nk, int Nkp, long ldq, long ldk, long ldv,
-                 long ldo, long bsq, long bsk, long bsv, long bso, float scale) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __nv_bfloat16 *Qs = (__nv_bfloat16 *)smem;                 // [64][HD]
-    __nv_bfloat16 *Ks = Qs + 64 * HD;                           // [Nkp][HD]
-    __nv_bfloat16 *Vs = Ks + (size_t)Nkp * HD;                  // [Nkp][HD]
-    float *S = (float *)(Vs + (size_t)Nkp * HD);                // [64][Nkp]
-    __nv_bfloat16 *P = (__nv_bfloat16 *)(S + (size_t)64 * Nkp); // [64][Nkp]
-    float *Os = (float *)(P + (size_t)64 * Nkp);                // [64][HD] output staging
-    __shared__ float rowinv[64];
-    const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const __nv_bfloat16 *qg = Q + b * bsq + (long)h * HD, *kg = K + b * bsk + (long)h * HD, *vg = V + b * bsv + (long)h * HD;
-    constexpr int C8 = HD / 8;
-    for (int i = threadIdx.x; i < 64 * C8; i += 128) {
-        const int r = i / C8, c = i - r * C8;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (q0 + r < Nq) v = __ldg((const uint4 *)(qg + (long)(q0 + r) * ldq) + c);
-        ((uint4 *)Qs)[i] = v;
-    }
-    for (int i = threadIdx.x; i < Nkp * C8; i += 128) {
-        const int r = i / C8, c = i - r * C8;
-        uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
-        if (r < Nk) {
-            kv = __ldg((const uint4 *)(kg + (long)r * ldk) + c);
-            vv = __ldg((const uint4 *)(vg + (long)r * ldv) + c);
-        }
-        ((uint4 *)Ks)[i] = kv;
-        ((uint4 *)Vs)[i] = vv;
-    }
-    __syncthreads();
-    // S = Q K^T for this warp's 16 rows
-    const int r0 = warp * 16;
-    {
-        wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> a[HD / 16];
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) wmma::load_matrix_sync(a[k], Qs + r0 * HD + k * 16, HD);
-        for (int n = 0; n < Nkp / 16; ++n) {
-            wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
-            wmma::fill_fragment(acc, 0.f);
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) {
-                wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> bf;  // B(k, n) = K[n][k]
-                wmma::load_matrix_sync(bf, Ks + (size_t)n * 16 * HD + k * 16, HD);
-                wmma::mma_sync(acc, a[k], bf, acc);
-            }
-            wmma::store_matrix_sync(S + (size_t)r0 * Nkp + n * 16, acc, Nkp, wmma::mem_row_major);
-        }
-    }
-    __syncwarp();
-    // softmax over the Nk real keys of each of the warp's rows (fp32), P unnormalised in bf16
-    for (int r = r0; r < r0 + 16; ++r) {
-        float *srow = S + (size_t)r * Nkp;
-        float m = -INFINITY;
-        for (int c = lane; c < Nk; c += 32) m = fmaxf(m, srow[c] * scale);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        float sum = 0.f;
-        for (int c = lane; c < Nkp; c += 32) {
-            float e = 0.f;
-            if (c < Nk) {
-                e = __expf(srow[c] * scale - m);
-                sum += e;
-            }
-            P[(size_t)r * Nkp + c] = __float2bfloat16_rn(e);
-        }
-        sum = warp_sum(sum);
-        if (lane == 0) {
-            rowinv[r] = 1.0f / sum;
-            // log-sum-exp of the scaled scores: the backward kernels rebuild P = exp(s * scale - lse) from it
-            if (lse != nullptr && q0 + r < Nq) lse[((long)b * gridDim.y + h) * Nq + q0 + r] = m + __logf(sum);
-        }
-    }
-    __syncwarp();
-    // O = P V, normalised on the way out
-#pragma unroll
-    for (int n = 0; n < HD / 16; ++n) {
-        wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
-        wmma::fill_fragment(acc, 0.f);
-        for (int k = 0; k < Nkp / 16; ++k) {
-            wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> a;
-            wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> bf;
-            wmma::load_matrix_sync(a, P + (size_t)r0 * Nkp + k * 16, Nkp);
-            wmma::load_matrix_sync(bf, Vs + (size_t)k * 16 * HD + n * 16, HD);
-            wmma::mma_sync(acc, a, bf, acc);
-        }
-        wmma::store_matrix_sync(Os + r0 * HD + n * 16, acc, HD, wmma::mem_row_major);
-    }
-    __syncwarp();
-    __nv_bfloat16 *og = O + b * bso + (long)h * HD;
-    for (int i = lane; i < 16 * C8; i += 32) {
-        const int r = r0 + i / C8, c = i % C8;
-        if (q0 + r < Nq) {
-            const float inv = rowinv[r];
-            float f[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = Os[r * HD + c * 8 + k] * inv;
-            *((uint4 *)(og + (long)(q0 + r) * ldo) + c) = pack8v(f);
-        }
-    }
-}
-
 
 // ---------------------------------------------------------------------------------------------------------
 // LayerNorm backward.  dX = dRes + rstd * (g*dY - mean(g*dY) - xhat * mean(g*dY*xhat)); dgamma += sum dY*xhat,
@@ -413,248 +297,6 @@ token_slice_kernel(const __nv_bfloat16 *__restrict__ src, long T, long t_off, in
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Attention backward, two kernels with the forward's structure (a 64-row strip against ALL columns in shared
-// memory; probabilities are rebuilt from the saved log-sum-exp, nothing of size Nq x Nk ever reaches HBM):
-//   dq kernel : rows = 64 queries, columns = all keys.   D = rowsum(dO * O); P = exp(S*scale - lse);
-//               dS = P * (dO V^T - D) * scale;  dQ = dS K.   Also writes D for the second kernel.
-//   dkv kernel: rows = 64 keys, columns = all queries.   dV = P^T dO,  dK = dS^T Q.
-// ---------------------------------------------------------------------------------------------------------
-template <int HD>
-__global__ void __launch_bounds__(128)
-attention_bwd_dq_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K,
-                        const __nv_bfloat16 *__restrict__ V, const __nv_bfloat16 *__restrict__ O,
-                        const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ lse, __nv_bfloat16 *__restrict__ dQ,
-                        float *__restrict__ Dout, int Nq, int Nk, int Nkp, long ldq, long ldk, long ldv, long ldo, long lddo,
-                        long lddq, long bsq, long bsk, long bsv, long bso, long bsdo, long bsdq, float scale) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __nv_bfloat16 *Qs = (__nv_bfloat16 *)smem;                  // [64][HD]
-    __nv_bfloat16 *dOs = Qs + 64 * HD;                           // [64][HD]
-    __nv_bfloat16 *Ks = dOs + 64 * HD;                           // [Nkp][HD]
-    __nv_bfloat16 *Vs = Ks + (size_t)Nkp * HD;                   // [Nkp][HD]
-    __nv_bfloat16 *dS = Vs + (size_t)Nkp * HD;                   // [64][Nkp]
-    float *Os = (float *)(dS + (size_t)64 * Nkp);                // [64][HD] fp32 staging
-    float *scr = Os + 64 * HD;                                   // [4 warps][2][256]
-    __shared__ float lse_s[64], D_s[64];
-    const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const __nv_bfloat16 *qg = Q + b * bsq + (long)h * HD, *kg = K + b * bsk + (long)h * HD, *vg = V + b * bsv + (long)h * HD;
-    const __nv_bfloat16 *og = O + b * bso + (long)h * HD, *dog = dO + b * bsdo + (long)h * HD;
-    constexpr int C8 = HD / 8;
-    for (int i = threadIdx.x; i < 64 * C8; i += 128) {
-        const int r = i / C8, c = i - r * C8;
-        uint4 qv = make_uint4(0u, 0u, 0u, 0u), dv = qv;
-        if (q0 + r < Nq) {
-            qv = __ldg((const uint4 *)(qg + (long)(q0 + r) * ldq) + c);
-            dv = __ldg((const uint4 *)(dog + (long)(q0 + r) * lddo) + c);
-        }
-        ((uint4 *)Qs)[i] = qv;
-        ((uint4 *)dOs)[i] = dv;
-    }
-    for (int i = threadIdx.x; i < Nkp * C8; i += 128) {
-        const int r = i / C8, c = i - r * C8;
-        uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
-        if (r < Nk) {
-            kv = __ldg((const uint4 *)(kg + (long)r * ldk) + c);
-            vv = __ldg((const uint4 *)(vg + (long)r * ldv) + c);
-        }
-        ((uint4 *)Ks)[i] = kv;
-        ((uint4 *)Vs)[i] = vv;
-    }
-    __syncthreads();
-    const int r0 = warp * 16;
-    // D = rowsum(dO * O), lse
-    for (int r = r0; r < r0 + 16; ++r) {
-        float t = 0.f;
-        if (q0 + r < Nq)
-            for (int c = lane; c < HD; c += 32)
-                t += __bfloat162float(dOs[r * HD + c]) * __bfloat162float(og[(long)(q0 + r) * ldo + c]);
-        t = warp_sum(t);
-        if (lane == 0) {
-            D_s[r] = t;
-            const bool ok = q0 + r < Nq;
-            lse_s[r] = ok ? lse[((long)b * gridDim.y + h) * Nq + q0 + r] : 0.f;
-            if (ok) Dout[((long)b * gridDim.y + h) * Nq + q0 + r] = t;
-        }
-    }
-    __syncwarp();
-    float *s0 = scr + warp * 512, *s1 = s0 + 256;
-    {
-        wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> aq[HD / 16], ad[HD / 16];
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-            wmma::load_matrix_sync(aq[k], Qs + r0 * HD + k * 16, HD);
-            wmma::load_matrix_sync(ad[k], dOs + r0 * HD + k * 16, HD);
-        }
-        for (int n = 0; n < Nkp / 16; ++n) {
-            wmma::fragment<wmma::accumulator, 16, 16, 16, float> sa, pa;
-            wmma::fill_fragment(sa, 0.f);
-            wmma::fill_fragment(pa, 0.f);
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) {
-                wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> bk, bv;
-                wmma::load_matrix_sync(bk, Ks + (size_t)n * 16 * HD + k * 16, HD);
-                wmma::load_matrix_sync(bv, Vs + (size_t)n * 16 * HD + k * 16, HD);
-                wmma::mma_sync(sa, aq[k], bk, sa);
-                wmma::mma_sync(pa, ad[k], bv, pa);
-            }
-            wmma::store_matrix_sync(s0, sa, 16, wmma::mem_row_major);
-            wmma::store_matrix_sync(s1, pa, 16, wmma::mem_row_major);
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int idx = lane + 32 * i, rr = idx >> 4, cc = idx & 15;
-                const int col = n * 16 + cc;
-                float p = col < Nk ? __expf(s0[idx] * scale - lse_s[r0 + rr]) : 0.f;
-                dS[(size_t)(r0 + rr) * Nkp + col] = __float2bfloat16_rn(p * (s1[idx] - D_s[r0 + rr]) * scale);
-            }
-            __syncwarp();
-        }
-    }
-    // dQ = dS K
-#pragma unroll
-    for (int n = 0; n < HD / 16; ++n) {
-        wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
-        wmma::fill_fragment(acc, 0.f);
-        for (int k = 0; k < Nkp / 16; ++k) {
-            wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> a;
-            wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> bf;
-            wmma::load_matrix_sync(a, dS + (size_t)r0 * Nkp + k * 16, Nkp);
-            wmma::load_matrix_sync(bf, Ks + (size_t)k * 16 * HD + n * 16, HD);
-            wmma::mma_sync(acc, a, bf, acc);
-        }
-        wmma::store_matrix_sync(Os + r0 * HD + n * 16, acc, HD, wmma::mem_row_major);
-    }
-    __syncwarp();
-    __nv_bfloat16 *dqg = dQ + b * bsdq + (long)h * HD;
-    for (int i = lane; i < 16 * C8; i += 32) {
-        const int r = r0 + i / C8, c = i % C8;
-        if (q0 + r < Nq) {
-            float f[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = Os[r * HD + c * 8 + k];
-            *((uint4 *)(dqg + (long)(q0 + r) * lddq) + c) = pack8v(f);
-        }
-    }
-}
-
-template <int HD>
-__global__ void __launch_bounds__(128)
-attention_bwd_dkv_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K,
-                         const __nv_bfloat16 *__restrict__ V, const __nv_bfloat16 *__restrict__ dO,
-                         const float *__restrict__ lse, const float *__restrict__ Dg, __nv_bfloat16 *__restrict__ dK,
-                         __nv_bfloat16 *__restrict__ dV, int Nq, int Nk, int Nqp, long ldq, long ldk, long ldv, long lddo,
-                         long lddk, long lddv, long bsq, long bsk, long bsv, long bsdo, long bsdk, long bsdv, float scale) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __nv_bfloat16 *Kt = (__nv_bfloat16 *)smem;                  // [64][HD]
-    __nv_bfloat16 *Vt = Kt + 64 * HD;                            // [64][HD]
-    __nv_bfloat16 *Qs = Vt + 64 * HD;                            // [Nqp][HD]
-    __nv_bfloat16 *dOs = Qs + (size_t)Nqp * HD;                  // [Nqp][HD]
-    __nv_bfloat16 *PT = dOs + (size_t)Nqp * HD;                  // [64][Nqp]
-    __nv_bfloat16 *dST = PT + (size_t)64 * Nqp;                  // [64][Nqp]
-    float *Os = (float *)(dST + (size_t)64 * Nqp);               // [64][HD] fp32 staging
-    float *scr = Os + 64 * HD;                                   // [4][2][256]
-    float *lse_s = scr + 4 * 512;                                // [Nqp]
-    float *D_s = lse_s + Nqp;                                    // [Nqp]
-    const int k0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const __nv_bfloat16 *qg = Q + b * bsq + (long)h * HD, *kg = K + b * bsk + (long)h * HD, *vg = V + b * bsv + (long)h * HD;
-    const __nv_bfloat16 *dog = dO + b * bsdo + (long)h * HD;
-    constexpr int C8 = HD / 8;
-    for (int i = threadIdx.x; i < 64 * C8; i += 128) {
-        const int r = i / C8, c = i - r * C8;
-        uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
-        if (k0 + r < Nk) {
-            kv = __ldg((const uint4 *)(kg + (long)(k0 + r) * ldk) + c);
-            vv = __ldg((const uint4 *)(vg + (long)(k0 + r) * ldv) + c);
-        }
-        ((uint4 *)Kt)[i] = kv;
-        ((uint4 *)Vt)[i] = vv;
-    }
-    for (int i = threadIdx.x; i < Nqp * C8; i += 128) {
-        const int r = i / C8, c = i - r * C8;
-        uint4 qv = make_uint4(0u, 0u, 0u, 0u), dv = qv;
-        if (r < Nq) {
-            qv = __ldg((const uint4 *)(qg + (long)r * ldq) + c);
-            dv = __ldg((const uint4 *)(dog + (long)r * lddo) + c);
-        }
-        ((uint4 *)Qs)[i] = qv;
-        ((uint4 *)dOs)[i] = dv;
-    }
-    for (int i = threadIdx.x; i < Nqp; i += 128) {
-        const bool ok = i < Nq;
-        lse_s[i] = ok ? lse[((long)b * gridDim.y + h) * Nq + i] : 0.f;
-        D_s[i] = ok ? Dg[((long)b * gridDim.y + h) * Nq + i] : 0.f;
-    }
-    __syncthreads();
-    const int r0 = warp * 16;
-    float *s0 = scr + warp * 512, *s1 = s0 + 256;
-    {
-        wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> ak[HD / 16], av[HD / 16];
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-            wmma::load_matrix_sync(ak[k], Kt + r0 * HD + k * 16, HD);
-            wmma::load_matrix_sync(av[k], Vt + r0 * HD + k * 16, HD);
-        }
-        for (int n = 0; n < Nqp / 16; ++n) {
-            wmma::fragment<wmma::accumulator, 16, 16, 16, float> sa, pa;
-            wmma::fill_fragment(sa, 0.f);
-            wmma::fill_fragment(pa, 0.f);
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) {
-                wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> bq, bd;
-                wmma::load_matrix_sync(bq, Qs + (size_t)n * 16 * HD + k * 16, HD);
-                wmma::load_matrix_sync(bd, dOs + (size_t)n * 16 * HD + k * 16, HD);
-                wmma::mma_sync(sa, ak[k], bq, sa);     // S^T tile = K Q^T
-                wmma::mma_sync(pa, av[k], bd, pa);     // dP^T tile = V dO^T
-            }
-            wmma::store_matrix_sync(s0, sa, 16, wmma::mem_row_major);
-            wmma::store_matrix_sync(s1, pa, 16, wmma::mem_row_major);
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int idx = lane + 32 * i, rr = idx >> 4, cc = idx & 15;
-                const int col = n * 16 + cc;
-                const bool ok = col < Nq && k0 + r0 + rr < Nk;
-                const float p = ok ? __expf(s0[idx] * scale - lse_s[col]) : 0.f;
-                PT[(size_t)(r0 + rr) * Nqp + col] = __float2bfloat16_rn(p);
-                dST[(size_t)(r0 + rr) * Nqp + col] = __float2bfloat16_rn(p * (s1[idx] - D_s[col]) * scale);
-            }
-            __syncwarp();
-        }
-    }
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {      // 0: dV = P^T dO, 1: dK = dS^T Q
-        const __nv_bfloat16 *Am = which == 0 ? PT : dST, *Bm = which == 0 ? dOs : Qs;
-#pragma unroll
-        for (int n = 0; n < HD / 16; ++n) {
-            wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
-            wmma::fill_fragment(acc, 0.f);
-            for (int k = 0; k < Nqp / 16; ++k) {
-                wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> a;
-                wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> bf;
-                wmma::load_matrix_sync(a, Am + (size_t)r0 * Nqp + k * 16, Nqp);
-                wmma::load_matrix_sync(bf, Bm + (size_t)k * 16 * HD + n * 16, HD);
-                wmma::mma_sync(acc, a, bf, acc);
-            }
-            wmma::store_matrix_sync(Os + r0 * HD + n * 16, acc, HD, wmma::mem_row_major);
-        }
-        __syncwarp();
-        __nv_bfloat16 *og = which == 0 ? dV + b * bsdv + (long)h * HD : dK + b * bsdk + (long)h * HD;
-        const long ldo = which == 0 ? lddv : lddk;
-        for (int i = lane; i < 16 * C8; i += 32) {
-            const int r = r0 + i / C8, c = i % C8;
-            if (k0 + r < Nk) {
-                float f[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) f[k] = Os[r * HD + c * 8 + k];
-                *((uint4 *)(og + (long)(k0 + r) * ldo) + c) = pack8v(f);
-            }
-        }
-        __syncwarp();
-    }
-}
-
 // fp32 [rows, cols] (pitch ld_in) -> bf16 [rows, ld_out], columns >= cols zero-filled: gradients whose width is not a
 // multiple of 8 (the 51-wide pose output) become TMA-addressable GEMM operands
 __global__ void __launch_bounds__(256)
@@ -664,16 +306,6 @@ cast_pad_kernel(const float *__restrict__ in, long ld_in, int cols, __nv_bfloat1
         const int c = (int)(i - r * ld_out);
         out[i] = __float2bfloat16_rn(c < cols ? in[r * ld_in + c] : 0.f);
     }
-}
-
-template <int HD>
-static size_t attn_dq_smem(int Nkp) {
-    return (size_t)2 * 64 * HD * 2 + (size_t)2 * Nkp * HD * 2 + (size_t)64 * Nkp * 2 + (size_t)64 * HD * 4 + 4 * 512 * 4;
-}
-template <int HD>
-static size_t attn_dkv_smem(int Nqp) {
-    return (size_t)2 * 64 * HD * 2 + (size_t)2 * Nqp * HD * 2 + (size_t)2 * 64 * Nqp * 2 + (size_t)64 * HD * 4 + 4 * 512 * 4 +
-           (size_t)2 * Nqp * 4;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -708,11 +340,6 @@ adamw_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m
             ((uint2 *)shadow)[i] = make_uint2(*(uint32_t *)&s0, *(uint32_t *)&s1);
         }
     }
-}
-
-template <int HD>
-static size_t attn_smem(int Nkp) {
-    return (size_t)64 * HD * 2 + (size_t)Nkp * HD * 2 * 2 + (size_t)64 * Nkp * 4 + (size_t)64 * Nkp * 2 + (size_t)64 * HD * 4;
 }
 
 static int grid_cap(long items, int per_block = 256) {
@@ -764,34 +391,6 @@ POSE_API int pose_patchify_bf16(const float *src0, int C0, const float *src1, in
     const long total = (long)B * (H / P) * (W / P) * (C0 + C1) * P * P;
     patchify_kernel<<<grid_cap(total), 256, 0, (cudaStream_t)stream>>>(src0, C0, src1, C1, H, W, P, total,
                                                                       (__nv_bfloat16 *)out);
-    return launch_status();
-}
-
-POSE_API int pose_attention_bf16(const void *Q, const void *K, const void *V, void *O, int B, int heads, int Nq, int Nk,
-                                 int head_dim, long ldq, long ldk, long ldv, long ldo, long bsq, long bsk, long bsv, long bso,
-                                 float scale, float *lse, pose_stream_t stream) {
-    if (!Q || !K || !V || !O) return POSE_E_NULL;
-    if (B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return POSE_E_SHAPE;
-    if (head_dim != 48 && head_dim != 64) return POSE_E_UNSUPPORTED;
-    if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || bsq % 8 || bsk % 8 || bsv % 8 || bso % 8) return POSE_E_ALIGN;
-    if ((uintptr_t)Q % 16 || (uintptr_t)K % 16 || (uintptr_t)V % 16 || (uintptr_t)O % 16) return POSE_E_ALIGN;
-    const int Nkp = (Nk + 15) / 16 * 16;
-    const size_t smem = head_dim == 64 ? attn_smem<64>(Nkp) : attn_smem<48>(Nkp);
-    if (smem > 227 * 1024 - 1024) return POSE_E_UNSUPPORTED;  // whole-row scores: up to ~288 keys
-    dim3 grid((Nq + 63) / 64, heads, B);
-    cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e;
-    if (head_dim == 64) {
-        e = cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attention_kernel<64><<<grid, 128, smem, s>>>((const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V,
-                                                     (__nv_bfloat16 *)O, lse, Nq, Nk, Nkp, ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale);
-    } else {
-        e = cudaFuncSetAttribute(attention_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        attention_kernel<48><<<grid, 128, smem, s>>>((const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V,
-                                                     (__nv_bfloat16 *)O, lse, Nq, Nk, Nkp, ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale);
-    }
     return launch_status();
 }
 
@@ -848,45 +447,6 @@ POSE_API int pose_token_slice_bf16(const void *src, int B, long T, long t_off, i
     const long total8 = (long)B * n * (D / 8);
     token_slice_kernel<<<grid_cap(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)src, T, t_off, n, D, total8,
                                                                           (__nv_bfloat16 *)dst);
-    return launch_status();
-}
-
-POSE_API int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V, const void *O, const void *dO,
-                                     const float *lse, void *dQ, void *dK, void *dV, float *Dws, int B, int heads, int Nq,
-                                     int Nk, int head_dim, long ldq, long ldk, long ldv, long ldo, long lddo, long lddq,
-                                     long lddk, long lddv, long bsq, long bsk, long bsv, long bso, long bsdo, long bsdq,
-                                     long bsdk, long bsdv, float scale, pose_stream_t stream) {
-    if (!Q || !K || !V || !O || !dO || !lse || !dQ || !dK || !dV || !Dws) return POSE_E_NULL;
-    if (B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return POSE_E_SHAPE;
-    if (head_dim != 48 && head_dim != 64) return POSE_E_UNSUPPORTED;
-    const long al[] = {ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv};
-    for (long a : al)
-        if (a % 8) return POSE_E_ALIGN;
-    const void *ptrs[] = {Q, K, V, O, dO, dQ, dK, dV};
-    for (const void *q : ptrs)
-        if ((uintptr_t)q % 16) return POSE_E_ALIGN;
-    const int Nkp = (Nk + 15) / 16 * 16, Nqp = (Nq + 15) / 16 * 16;
-    const size_t s1 = head_dim == 64 ? attn_dq_smem<64>(Nkp) : attn_dq_smem<48>(Nkp);
-    const size_t s2 = head_dim == 64 ? attn_dkv_smem<64>(Nqp) : attn_dkv_smem<48>(Nqp);
-    if (s1 > 227 * 1024 - 1024 || s2 > 227 * 1024 - 1024) return POSE_E_UNSUPPORTED;
-    cudaStream_t s = (cudaStream_t)stream;
-    const dim3 g1((Nq + 63) / 64, heads, B), g2((Nk + 63) / 64, heads, B);
-    cudaError_t e;
-#define BWD_LAUNCH(HD_)                                                                                                \
-    e = cudaFuncSetAttribute(attention_bwd_dq_kernel<HD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);      \
-    if (e != cudaSuccess) return (int)e;                                                                               \
-    e = cudaFuncSetAttribute(attention_bwd_dkv_kernel<HD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);     \
-    if (e != cudaSuccess) return (int)e;                                                                               \
-    attention_bwd_dq_kernel<HD_><<<g1, 128, s1, s>>>(                                                                  \
-        (const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V, (const __nv_bfloat16 *)O,        \
-        (const __nv_bfloat16 *)dO, lse, (__nv_bfloat16 *)dQ, Dws, Nq, Nk, Nkp, ldq, ldk, ldv, ldo, lddo, lddq, bsq, bsk,  \
-        bsv, bso, bsdo, bsdq, scale);                                                                                  \
-    attention_bwd_dkv_kernel<HD_><<<g2, 128, s2, s>>>(                                                                 \
-        (const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V, (const __nv_bfloat16 *)dO, lse,  \
-        Dws, (__nv_bfloat16 *)dK, (__nv_bfloat16 *)dV, Nq, Nk, Nqp, ldq, ldk, ldv, lddo, lddk, lddv, bsq, bsk, bsv,     \
-        bsdo, bsdk, bsdv, scale)
-    if (head_dim == 64) { BWD_LAUNCH(64); } else { BWD_LAUNCH(48); }
-#undef BWD_LAUNCH
     return launch_status();
 }
 
