@@ -92,13 +92,13 @@ SIGNATURES = {
     "pose_attention_bwd_bf16": (c_int, [c_void_p] * 10 + [c_int] * 5 + [C.c_long] * 16 + [c_float, c_void_p]),
     "pose_cnn_input_pack_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     "pose_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [c_void_p, c_int, c_void_p]),
-    "pose_bn_stats_bf16": (c_int, [c_void_p, C.c_long, c_int, C.c_long, c_void_p, c_void_p]),
-    "pose_bn_finalize": (c_int, [c_void_p, C.c_long, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_void_p]),
+    "pose_bn_stats_bf16": (c_int, [c_void_p, C.c_long, c_int, C.c_long, c_void_p, C.c_long, c_void_p]),
+    "pose_bn_finalize": (c_int, [c_void_p, C.c_long, C.c_long, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
     "pose_bn_apply_bf16": (c_int, [c_void_p, C.c_long, c_int, c_void_p, c_int, c_float, c_void_p, C.c_long, c_void_p, C.c_long,
                                    c_void_p]),
     "pose_bn_bwd_bf16": (c_int, [c_void_p, C.c_long, c_void_p, C.c_long, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p,
-                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 C.c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pose_dwconv3x3_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
     "pose_gate_bwd_reduce_bf16": (c_int, [c_void_p, c_void_p, c_int, C.c_long, c_int, c_void_p, c_void_p]),

@@ -49,87 +49,143 @@ static int grid_for(long items, int per_block = 256, int max_waves = 16) {
     return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Per-channel reduction over the rows of an [M, C] channels-last matrix: K quantities per channel, produced by a
-// functor for 8 consecutive channels of one row.  A CTA owns a slab of up to 256 channels (32 groups of 8); when the
-// matrix has fewer groups than a warp has lanes, the spare lanes take further rows.  Per-thread fp32 partials ->
-// shuffle across the lanes that share a channel group -> shared memory across the 8 warps -> one atomicAdd per
-// channel per CTA into out[k * C + c].
-// ---------------------------------------------------------------------------------------------------------
-template <int K, class F>
-__device__ __forceinline__ void col_reduce(long M, int C, float *__restrict__ out, F f) {
-    __shared__ float red[8][K][256];
-    const int C8 = C >> 3;
-    const int slab = blockIdx.x;
-    const int ng = min(32, C8 - slab * 32);
-    int gpr = 1;
-    while (gpr < ng) gpr <<= 1;                      // groups per row slot (power of two <= 32)
-    const int R = 32 / gpr;                          // rows per warp iteration
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane % gpr, rsub = lane / gpr;
-    const bool active = g < ng;
-    const int c0 = (slab * 32 + g) * 8;
-    float acc[K][8];
+// ---- BatchNorm (training mode) ------------------------------------------------------------------------------
+// Thread mapping of the row-streaming kernels: a thread owns ONE group of 8 channels for its whole life (its per-channel
+// coefficients live in registers) and walks rows; block = G * k threads (G = C / 8 groups, k rows side by side), so
+// consecutive threads read consecutive 16-byte chunks of a row.
+struct RowMap {
+    int g, rsub, rpb, c0;
+    __device__ __forceinline__ RowMap(int C) {
+        const int G = C >> 3;
+        g = threadIdx.x % G;
+        rsub = threadIdx.x / G;
+        rpb = blockDim.x / G;
+        c0 = g * 8;
+    }
+};
+static int rowmap_threads(int C) {
+    const int G = C / 8;
+    const int k = 256 / G > 0 ? 256 / G : 1;
+    return G * k;
+}
+static int rowmap_grid(long M, int C, int rows_per_thread = 8) {
+    const int rpb = rowmap_threads(C) / (C / 8);
+    long blocks = (M + (long)rpb * rows_per_thread - 1) / ((long)rpb * rows_per_thread);
+    const long cap = (long)kNumSMs * 8;
+    return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+__device__ __forceinline__ void ld8f(const float *p, float (&f)[8]) {
+    const float4 a = __ldg((const float4 *)p), b = __ldg((const float4 *)p + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// activation and its derivative, template-selected (silu through one MUFU.TANH)
+template <int ACT>
+__device__ __forceinline__ float actf(float z) {
+    if (ACT == 1) return fmaxf(z, 0.f);
+    if (ACT == 2) return 0.5f * z * (1.0f + tanh_fast(0.5f * z));
+    return z;
+}
+template <int ACT>
+__device__ __forceinline__ float dactf(float z) {
+    if (ACT == 1) return z > 0.f ? 1.f : 0.f;
+    if (ACT == 2) {
+        const float sg = 0.5f * (1.0f + tanh_fast(0.5f * z));
+        return sg * (1.0f + z * (1.0f - sg));
+    }
+    return 1.f;
+}
+// block-level fold of K * 8 per-thread partials over the rsub lanes that share a channel group; the block's result is
+// either WRITTEN to its own slot (deterministic two-stage reductions: out_off = blockIdx * K * C) or added atomically
+template <int K, bool ATOMIC = true>
+__device__ __forceinline__ void rowmap_fold(const RowMap &rm, int C, float (&acc)[K][8], float *__restrict__ out, long out_off) {
+    __shared__ float red[384 * 8 * K];
+    const int G = C >> 3;
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
-    if (active)
-        for (long r = ((long)blockIdx.y * 8 + warp) * R + rsub; r < M; r += (long)gridDim.y * 8 * R) {
-            float v[K][8];
-            f(r, c0, v);
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[k][j] += v[k][j];
-        }
-    for (int o = gpr; o < 32; o <<= 1)
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[k][j] += __shfl_xor_sync(0xffffffffu, acc[k][j], o);
-    if (rsub == 0 && active)
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) red[warp][k][g * 8 + j] = acc[k][j];
+        for (int j = 0; j < 8; ++j) red[(k * 8 + j) * blockDim.x + threadIdx.x] = acc[k][j];
     __syncthreads();
-    for (int i = threadIdx.x; i < K * ng * 8; i += 256) {
-        const int k = i / (ng * 8), c = i - k * ng * 8;
-        float t = 0.f;
+    if (rm.rsub == 0) {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += red[w][k][c];
-        atomicAdd(out + (long)k * C + slab * 256 + c, t);
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float t = 0.f;
+                for (int q = 0; q < rm.rpb; ++q) t += red[(k * 8 + j) * blockDim.x + q * G + rm.g];
+                if (ATOMIC) atomicAdd(out + out_off + (long)k * C + rm.c0 + j, t);
+                else out[out_off + (long)k * C + rm.c0 + j] = t;
+            }
     }
 }
 
-static dim3 col_reduce_grid(long M, int C) {
-    const int gx = (C / 8 + 31) / 32;
-    long gy = (M + 255) / 256;
-    const long cap = (kNumSMs * 4 + gx - 1) / gx;
-    if (gy > cap) gy = cap;
-    if (gy < 1) gy = 1;
-    return dim3(gx, (unsigned)gy);
-}
-
-// ---- BatchNorm (training mode) ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-bn_stats_kernel(const __nv_bfloat16 *__restrict__ Y, long M, int C, long ld, float *__restrict__ sums) {
-    col_reduce<2>(M, C, sums, [&](long r, int c0, float (&v)[2][8]) {
-        up8(__ldg((const uint4 *)(Y + r * ld + c0)), v[0]);
+__global__ void __launch_bounds__(384)
+bn_stats_kernel(const __nv_bfloat16 *__restrict__ Y, long M, int C, long ld, float *__restrict__ partials) {
+    const RowMap rm(C);
+    float acc[2][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[1][j] = v[0][j] * v[0][j];
-    });
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+    for (long r = (long)blockIdx.x * rm.rpb + rm.rsub; r < M; r += (long)gridDim.x * rm.rpb) {
+        float y[8];
+        up8(__ldg((const uint4 *)(Y + r * ld + rm.c0)), y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            acc[0][j] += y[j];
+            acc[1][j] = fmaf(y[j], y[j], acc[1][j]);
+        }
+    }
+    rowmap_fold<2, false>(rm, C, acc, partials, (long)blockIdx.x * 2 * C);
 }
 
-// sums [2, C] -> mean_rstd [2, C], scale_shift [2, C] (z = y * scale + shift), running statistics (momentum, unbiased var)
+// Second stage of the two-stage reductions: block = 32 channels x 8 part lanes; every lane adds its share of the
+// per-block partials in a fixed order (4 independent accumulators), shared memory folds the 8 lanes in a fixed order.
+// Returns the two totals to the threads with part lane 0 (tid < 32).
+__device__ __forceinline__ void fold_parts(const float *__restrict__ partials, int parts, int C, int c, float &s1, float &s2) {
+    __shared__ float red[2][8][33];
+    const int pl = threadIdx.x >> 5, cl = threadIdx.x & 31;
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < C) {
+        int q = pl;
+        for (; q + 24 < parts; q += 32) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a[u] += partials[(long)(q + 8 * u) * 2 * C + c];
+                b[u] += partials[(long)(q + 8 * u) * 2 * C + C + c];
+            }
+        }
+        for (; q < parts; q += 8) {
+            a[0] += partials[(long)q * 2 * C + c];
+            b[0] += partials[(long)q * 2 * C + C + c];
+        }
+    }
+    red[0][pl][cl] = (a[0] + a[1]) + (a[2] + a[3]);
+    red[1][pl][cl] = (b[0] + b[1]) + (b[2] + b[3]);
+    __syncthreads();
+    s1 = s2 = 0.f;
+    if (pl == 0)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            s1 += red[0][q][cl];
+            s2 += red[1][q][cl];
+        }
+}
+
+// partials [parts, 2, C] -> mean_rstd [2, C], scale_shift [2, C] (z = y * scale + shift), running statistics (momentum,
+// unbiased variance).  grid = ceil(C / 32), 256 threads.
 __global__ void __launch_bounds__(256)
-bn_finalize_kernel(const float *__restrict__ sums, float count, const float *__restrict__ gamma, const float *__restrict__ beta,
-                   float eps, float momentum, int C, float *__restrict__ mean_rstd, float *__restrict__ scale_shift,
-                   float *__restrict__ running_mean, float *__restrict__ running_var) {
-    for (int c = blockIdx.x * 256 + threadIdx.x; c < C; c += gridDim.x * 256) {
-        const float mean = sums[c] / count;
-        const float var = fmaxf(sums[C + c] / count - mean * mean, 0.f);
+bn_finalize_kernel(const float *__restrict__ partials, int parts, float count, const float *__restrict__ gamma,
+                   const float *__restrict__ beta, float eps, float momentum, int C, float *__restrict__ mean_rstd,
+                   float *__restrict__ scale_shift, float *__restrict__ running_mean, float *__restrict__ running_var) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    float s1, s2;
+    fold_parts(partials, parts, C, c, s1, s2);
+    if (threadIdx.x < 32 && c < C) {
+        const float mean = s1 / count;
+        const float var = fmaxf(s2 / count - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
         mean_rstd[c] = mean;
         mean_rstd[C + c] = rstd;
@@ -144,77 +200,101 @@ bn_finalize_kernel(const float *__restrict__ sums, float count, const float *__r
 }
 
 // out[r, :] (pitch ld_out) = residual[r, :] + out_scale * act(y * scale + shift)
-__global__ void __launch_bounds__(256)
-bn_apply_kernel(const __nv_bfloat16 *__restrict__ Y, long total8, int C, const float *__restrict__ scale_shift, int act,
-                float out_scale, const __nv_bfloat16 *__restrict__ residual, long ld_res, __nv_bfloat16 *__restrict__ out,
-                long ld_out) {
-    const int C8 = C >> 3;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(i % C8);
-        const long r = i / C8;
-        const int c0 = cg * 8;
+template <int ACT>
+__global__ void __launch_bounds__(384)
+bn_apply_kernel(const __nv_bfloat16 *__restrict__ Y, long M, int C, const float *__restrict__ scale_shift, float out_scale,
+                const __nv_bfloat16 *__restrict__ residual, long ld_res, __nv_bfloat16 *__restrict__ out, long ld_out) {
+    const RowMap rm(C);
+    float a[8], b[8];
+    ld8f(scale_shift + rm.c0, a);
+    ld8f(scale_shift + C + rm.c0, b);
+    for (long r = (long)blockIdx.x * rm.rpb + rm.rsub; r < M; r += (long)gridDim.x * rm.rpb) {
         float y[8];
-        up8(__ldg((const uint4 *)Y + i), y);
+        up8(__ldg((const uint4 *)(Y + r * C + rm.c0)), y);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            y[j] = out_scale * act_fwd(fmaf(y[j], __ldg(scale_shift + c0 + j), __ldg(scale_shift + C + c0 + j)), act);
+        for (int j = 0; j < 8; ++j) y[j] = out_scale * actf<ACT>(fmaf(y[j], a[j], b[j]));
         if (residual != nullptr) {
             float q[8];
-            up8(__ldg((const uint4 *)(residual + r * ld_res + c0)), q);
+            up8(__ldg((const uint4 *)(residual + r * ld_res + rm.c0)), q);
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] += q[j];
         }
-        *(uint4 *)(out + r * ld_out + c0) = pk8(y);
+        *(uint4 *)(out + r * ld_out + rm.c0) = pk8(y);
     }
 }
 
 // pass 1 of the backward: sums2[c] += dz, sums2[C + c] += dz * xhat, dz = dA * out_scale * act'(z)
-__global__ void __launch_bounds__(256)
+template <int ACT>
+__global__ void __launch_bounds__(384)
 bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dA, long ld_da, const __nv_bfloat16 *__restrict__ Y, long M, int C,
-                     const float *__restrict__ scale_shift, const float *__restrict__ mean_rstd, int act, float out_scale,
-                     float *__restrict__ sums2) {
-    col_reduce<2>(M, C, sums2, [&](long r, int c0, float (&v)[2][8]) {
+                     const float *__restrict__ scale_shift, const float *__restrict__ mean_rstd, float out_scale,
+                     float *__restrict__ partials) {
+    const RowMap rm(C);
+    float a[8], b[8], rs[8], mr[8];
+    ld8f(scale_shift + rm.c0, a);
+    ld8f(scale_shift + C + rm.c0, b);
+    ld8f(mean_rstd + rm.c0, mr);
+    ld8f(mean_rstd + C + rm.c0, rs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mr[j] *= rs[j];              // xhat = y * rstd - mean * rstd
+    float acc[2][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+    for (long r = (long)blockIdx.x * rm.rpb + rm.rsub; r < M; r += (long)gridDim.x * rm.rpb) {
         float y[8], d[8];
-        up8(__ldg((const uint4 *)(Y + r * C + c0)), y);
-        up8(__ldg((const uint4 *)(dA + r * ld_da + c0)), d);
+        up8(__ldg((const uint4 *)(Y + r * C + rm.c0)), y);
+        up8(__ldg((const uint4 *)(dA + r * ld_da + rm.c0)), d);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float z = fmaf(y[j], __ldg(scale_shift + c0 + j), __ldg(scale_shift + C + c0 + j));
-            const float dz = d[j] * out_scale * act_bwd(z, act);
-            v[0][j] = dz;
-            v[1][j] = dz * (y[j] - __ldg(mean_rstd + c0 + j)) * __ldg(mean_rstd + C + c0 + j);
+            const float dz = d[j] * out_scale * dactf<ACT>(fmaf(y[j], a[j], b[j]));
+            acc[0][j] += dz;
+            acc[1][j] = fmaf(dz, fmaf(y[j], rs[j], -mr[j]), acc[1][j]);
         }
-    });
+    }
+    rowmap_fold<2, false>(rm, C, acc, partials, (long)blockIdx.x * 2 * C);
 }
 
-// pass 2: dY = gamma * rstd * (dz - s1 / M - xhat * s2 / M); block 0 also accumulates dgamma += s2, dbeta += s1
+// between the passes: fold the per-block partials in a fixed order, accumulate dgamma += s2, dbeta += s1, and emit the two
+// per-channel coefficients of pass 2 (dy = a dz - k2 y - k3)
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dA, long ld_da, const __nv_bfloat16 *__restrict__ Y, long total8, int C,
-                    const float *__restrict__ scale_shift, const float *__restrict__ mean_rstd, int act, float out_scale,
-                    const float *__restrict__ sums2, float inv_m, __nv_bfloat16 *__restrict__ dY, float *__restrict__ dgamma,
-                    float *__restrict__ dbeta) {
-    const int C8 = C >> 3;
-    if (blockIdx.x == 0)
-        for (int c = threadIdx.x; c < C; c += 256) {
-            dgamma[c] += sums2[C + c];
-            dbeta[c] += sums2[c];
-        }
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(i % C8);
-        const long r = i / C8;
-        const int c0 = cg * 8;
+bn_bwd_coef_kernel(const float *__restrict__ partials, int parts, float inv_m, const float *__restrict__ scale_shift,
+                   const float *__restrict__ mean_rstd, int C, float *__restrict__ coef, float *__restrict__ dgamma,
+                   float *__restrict__ dbeta) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    float s1, s2;
+    fold_parts(partials, parts, C, c, s1, s2);
+    if (threadIdx.x < 32 && c < C) {
+        dgamma[c] += s2;
+        dbeta[c] += s1;
+        const float a = scale_shift[c], mean = mean_rstd[c], rstd = mean_rstd[C + c];
+        const float c1 = s1 * inv_m, c2 = s2 * inv_m;
+        coef[c] = a * c2 * rstd;
+        coef[C + c] = a * (c1 - c2 * mean * rstd);
+    }
+}
+
+// pass 2: dY = gamma * rstd * (dz - s1 / M - xhat * s2 / M) = a dz - k2 y - k3
+template <int ACT>
+__global__ void __launch_bounds__(384)
+bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dA, long ld_da, const __nv_bfloat16 *__restrict__ Y, long M, int C,
+                    const float *__restrict__ scale_shift, const float *__restrict__ coef, float out_scale,
+                    __nv_bfloat16 *__restrict__ dY) {
+    const RowMap rm(C);
+    float a[8], b[8], k2[8], k3[8];
+    ld8f(scale_shift + rm.c0, a);
+    ld8f(scale_shift + C + rm.c0, b);
+    ld8f(coef + rm.c0, k2);
+    ld8f(coef + C + rm.c0, k3);
+    for (long r = (long)blockIdx.x * rm.rpb + rm.rsub; r < M; r += (long)gridDim.x * rm.rpb) {
         float y[8], d[8];
-        up8(__ldg((const uint4 *)Y + i), y);
-        up8(__ldg((const uint4 *)(dA + r * ld_da + c0)), d);
+        up8(__ldg((const uint4 *)(Y + r * C + rm.c0)), y);
+        up8(__ldg((const uint4 *)(dA + r * ld_da + rm.c0)), d);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float a = __ldg(scale_shift + c0 + j);                 // gamma * rstd
-            const float z = fmaf(y[j], a, __ldg(scale_shift + C + c0 + j));
-            const float dz = d[j] * out_scale * act_bwd(z, act);
-            const float xhat = (y[j] - __ldg(mean_rstd + c0 + j)) * __ldg(mean_rstd + C + c0 + j);
-            d[j] = a * (dz - __ldg(sums2 + c0 + j) * inv_m - xhat * __ldg(sums2 + C + c0 + j) * inv_m);
+            const float dz = d[j] * out_scale * dactf<ACT>(fmaf(y[j], a[j], b[j]));
+            d[j] = fmaf(a[j], dz, -fmaf(k2[j], y[j], k3[j]));
         }
-        ((uint4 *)dY)[i] = pk8(d);
+        *(uint4 *)(dY + r * C + rm.c0) = pk8(d);
     }
 }
 
@@ -261,79 +341,103 @@ dwconv_bwd_data_kernel(const __nv_bfloat16 *__restrict__ dY, const float *__rest
 }
 
 // dW[c * 9 + k] += sum_{b,oy,ox} dY[b,oy,ox,c] * X[b, oy*s+ky-1, ox*s+kx-1, c]   (parameter layout [C,1,3,3])
-// CTA = 64 channels (8 groups) x 32 pixel lanes; each lane walks output pixels with 72 fp32 partials in registers.
+// Same tiling as the forward kernel: a CTA walks output tiles (TH x TW pixels x 64 channels), stages the input halo
+// tile in shared memory once, and every thread keeps 9 x 8 fp32 partials in registers across all its tiles; one fold
+// and 576 atomics per CTA at the end.
+template <int STRIDE>
+struct DwT {
+    static constexpr int TH = STRIDE == 1 ? 8 : 4, TW = STRIDE == 1 ? 16 : 8;
+    static constexpr int IH = (TH - 1) * STRIDE + 3, IW = (TW - 1) * STRIDE + 3;
+};
+template <int STRIDE>
 __global__ void __launch_bounds__(256)
 dwconv_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ dY, const __nv_bfloat16 *__restrict__ X, int B, int H, int W, int C,
-                         int Ho, int Wo, int stride, float *__restrict__ dW) {
+                         int Ho, int Wo, int tiles_x, int tiles_y, float *__restrict__ dW) {
+    using T = DwT<STRIDE>;
+    __shared__ __align__(16) unsigned char s_in[T::IH * T::IW * 128];
     __shared__ float red[32][65];
     const int cgi = threadIdx.x & 7, pl = threadIdx.x >> 3;
-    const int c0 = blockIdx.y * 64 + cgi * 8;
+    const int c_slab = blockIdx.y * 64;
+    const int c0 = c_slab + cgi * 8;
     const bool c_ok = c0 < C;
     float acc[9][8];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
-    const long npx = (long)B * Ho * Wo;
-    if (c_ok)
-        for (long p = (long)blockIdx.x * 32 + pl; p < npx; p += (long)gridDim.x * 32) {
-            const int ox = (int)(p % Wo);
-            const long q = p / Wo;
-            const int oy = (int)(q % Ho);
-            const long b = q / Ho;
-            float d[8];
-            up8(__ldg((const uint4 *)(dY + p * C + c0)), d);
+    const int per_img = tiles_x * tiles_y;
+    const long n_tiles = (long)B * per_img;
+    for (long tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+        const int b = (int)(tile_id / per_img), tile = (int)(tile_id - (long)b * per_img);
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int oy0 = ty * T::TH, ox0 = tx * T::TW;
+        const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
+        const __nv_bfloat16 *xb = X + (long)b * H * W * C;
+        __syncthreads();
+        for (int i = threadIdx.x; i < T::IH * T::IW * 8; i += 256) {
+            const int px = i >> 3, g = i & 7;
+            const int py = px / T::IW, pxx = px - py * T::IW;
+            const int iy = iy0 + py, ix = ix0 + pxx;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W && c_slab + g * 8 < C)
+                v = __ldg((const uint4 *)(xb + ((long)iy * W + ix) * C + c_slab + g * 8));
+            *(uint4 *)(s_in + (px * 8 + g) * 16) = v;
+        }
+        __syncthreads();
+        constexpr int kPix = T::TH * T::TW;
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int iy = oy * stride + ky - 1;
-                if (iy < 0 || iy >= H) continue;
+        for (int q = 0; q < kPix / 32; ++q) {
+            const int p = q * 32 + pl;
+            const int py = p / T::TW, pxx = p - py * T::TW;
+            const int oy = oy0 + py, ox = ox0 + pxx;
+            if (oy < Ho && ox < Wo && c_ok) {
+                float d[8];
+                up8(__ldg((const uint4 *)(dY + (((long)b * Ho + oy) * Wo + ox) * C + c0)), d);
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int ix = ox * stride + kx - 1;
-                    if (ix < 0 || ix >= W) continue;
-                    float x[8];
-                    up8(__ldg((const uint4 *)(X + ((b * H + iy) * W + ix) * C + c0)), x);
+                for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(d[j], x[j], acc[ky * 3 + kx][j]);
-                }
+                    for (int kx = 0; kx < 3; ++kx) {
+                        float x[8];
+                        up8(*(const uint4 *)(s_in + (((py * STRIDE + ky) * T::IW + pxx * STRIDE + kx) * 8 + cgi) * 16), x);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(d[j], x[j], acc[ky * 3 + kx][j]);
+                    }
             }
         }
+    }
 #pragma unroll 1
     for (int t = 0; t < 9; ++t) {
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < 8; ++j) red[pl][cgi * 8 + j] = acc[t][j];
         __syncthreads();
-        if (threadIdx.x < 64 && blockIdx.y * 64 + threadIdx.x < C) {
-            float s = 0.f;
+        if (threadIdx.x < 64 && c_slab + threadIdx.x < C) {
+            float sacc = 0.f;
 #pragma unroll 8
-            for (int q = 0; q < 32; ++q) s += red[q][threadIdx.x];
-            atomicAdd(dW + (long)(blockIdx.y * 64 + threadIdx.x) * 9 + t, s);
+            for (int q = 0; q < 32; ++q) sacc += red[q][threadIdx.x];
+            atomicAdd(dW + (long)(c_slab + threadIdx.x) * 9 + t, sacc);
         }
     }
 }
 
 // ---- SE / ECA gates -------------------------------------------------------------------------------------------
-// out[b, c] += sum_p dOut[b, p, c] * X[b, p, c]   (gradient reaching the gate); grid (chunks, B)
-__global__ void __launch_bounds__(256)
-gate_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dO, const __nv_bfloat16 *__restrict__ X, long HW, int C, int chunks,
+// out[b, c] += sum_p dOut[b, p, c] * X[b, p, c]   (gradient reaching the gate); grid (row blocks, B)
+__global__ void __launch_bounds__(384)
+gate_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dO, const __nv_bfloat16 *__restrict__ X, long HW, int C,
                        float *__restrict__ out) {
-    const int b = blockIdx.y, chunk = blockIdx.x;
-    const int C8 = C >> 3;
-    const long per = (HW + chunks - 1) / chunks;
-    const long p0 = chunk * per, p1 = min(HW, p0 + per);
-    for (int cg = threadIdx.x; cg < C8; cg += 256) {
-        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (long p = p0; p < p1; ++p) {
-            float d[8], x[8];
-            up8(__ldg((const uint4 *)(dO + ((long)b * HW + p) * C + cg * 8)), d);
-            up8(__ldg((const uint4 *)(X + ((long)b * HW + p) * C + cg * 8)), x);
+    const RowMap rm(C);
+    const long base = (long)blockIdx.y * HW;
+    float acc[1][8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s[j] = fmaf(d[j], x[j], s[j]);
-        }
+    for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+    for (long r = (long)blockIdx.x * rm.rpb + rm.rsub; r < HW; r += (long)gridDim.x * rm.rpb) {
+        float d[8], x[8];
+        up8(__ldg((const uint4 *)(dO + (base + r) * C + rm.c0)), d);
+        up8(__ldg((const uint4 *)(X + (base + r) * C + rm.c0)), x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(out + (long)b * C + cg * 8 + j, s[j]);
+        for (int j = 0; j < 8; ++j) acc[0][j] = fmaf(d[j], x[j], acc[0][j]);
     }
+    rowmap_fold<1>(rm, C, acc, out, (long)blockIdx.y * C);
 }
 
 // dX[b,p,c] = add + dOut[b,p,c] * gate[b,c] + dmean[b,c] * inv_hw
@@ -652,6 +756,7 @@ dropout_kernel(const __nv_bfloat16 *__restrict__ x, long n, uint32_t thresh, flo
 // kind 3: matrix [R, Cc] fp32 -> bf16 [.., ld d2] top-left block (zero padding is never touched) (d0 R, d1 Cc, d2 ld)
 // kind 4: fp32 vector copy (d0 = n)
 // kind 5: (gradient, reverse of 1) fp32 KRSC [Co,K,K,Cp] workspace -> += into fp32 [Co,Ci,K,K]   (src = workspace)
+// kind 6: depthwise weight [C,1,3,3] fp32 -> fp32 [9, C] with the taps flipped (data gradient = forward kernel over dY)
 struct RepackEntry {
     long src, dst;
     int kind, d0, d1, d2, d3, pad;
@@ -663,15 +768,15 @@ repack_kernel(const RepackEntry *__restrict__ table, const float *__restrict__ s
     const float *s = src_f32 + e.src;
     long n;
     switch (e.kind) {
-        case 0: n = (long)e.d0 * 9; break;
+        case 0: case 6: n = (long)e.d0 * 9; break;
         case 1: case 2: case 5: n = (long)e.d0 * e.d1 * e.d2 * e.d2; break;
         case 3: n = (long)e.d0 * e.d1; break;
         default: n = e.d0; break;
     }
     for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
-        if (e.kind == 0) {
+        if (e.kind == 0 || e.kind == 6) {
             const long c = i / 9, k = i - c * 9;
-            dst_f32[e.dst + k * e.d0 + c] = s[i];
+            dst_f32[e.dst + (e.kind == 0 ? k : 8 - k) * e.d0 + c] = s[i];
         } else if (e.kind == 1 || e.kind == 2 || e.kind == 5) {
             const int K = e.d2, Ci = e.d1, Co = e.d0;
             long t = i;
@@ -698,21 +803,34 @@ using namespace pose;
 
 #define REQ(c, e) do { if (!(c)) return (e); } while (0)
 
-POSE_API int pose_bn_stats_bf16(const void *Y, long M, int C, long ld, float *sums, pose_stream_t stream) {
-    REQ(Y && sums, POSE_E_NULL);
+// number of per-block partial slots a row reduction over [M, C] uses, given a scratch capacity in floats
+static int bn_parts(long M, int C, long cap_floats) {
+    long parts = rowmap_grid(M, C, 8);
+    if (parts > kNumSMs * 4) parts = kNumSMs * 4;      // 4 CTAs per SM saturate HBM; fewer partials to fold
+    const long fit = cap_floats / (2L * C);
+    if (parts > fit) parts = fit;
+    return (int)(parts < 1 ? 1 : parts);
+}
+
+POSE_API int pose_bn_stats_bf16(const void *Y, long M, int C, long ld, float *partials, long cap_floats, pose_stream_t stream) {
+    REQ(Y && partials, POSE_E_NULL);
     REQ(M > 0 && C > 0 && C % 8 == 0 && ld >= C && ld % 8 == 0, POSE_E_SHAPE);
     REQ((uintptr_t)Y % 16 == 0, POSE_E_ALIGN);
-    bn_stats_kernel<<<col_reduce_grid(M, C), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Y, M, C, ld, sums);
+    REQ(C <= 3072, POSE_E_UNSUPPORTED);
+    REQ(cap_floats >= 2L * C, POSE_E_WORKSPACE);
+    bn_stats_kernel<<<bn_parts(M, C, cap_floats), rowmap_threads(C), 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Y, M, C, ld,
+                                                                                               partials);
     return launch_status();
 }
 
-POSE_API int pose_bn_finalize(const float *sums, long count, const float *gamma, const float *beta, float eps, float momentum,
-                              int C, float *mean_rstd, float *scale_shift, float *running_mean, float *running_var,
-                              pose_stream_t stream) {
-    REQ(sums && gamma && beta && mean_rstd && scale_shift, POSE_E_NULL);
+POSE_API int pose_bn_finalize(const float *partials, long cap_floats, long count, const float *gamma, const float *beta,
+                              float eps, float momentum, int C, float *mean_rstd, float *scale_shift, float *running_mean,
+                              float *running_var, pose_stream_t stream) {
+    REQ(partials && gamma && beta && mean_rstd && scale_shift, POSE_E_NULL);
     REQ(count > 0 && C > 0, POSE_E_SHAPE);
-    bn_finalize_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, (float)count, gamma, beta, eps, momentum, C,
-                                                                         mean_rstd, scale_shift, running_mean, running_var);
+    bn_finalize_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, bn_parts(count, C, cap_floats), (float)count,
+                                                                         gamma, beta, eps, momentum, C, mean_rstd, scale_shift,
+                                                                         running_mean, running_var);
     return launch_status();
 }
 
@@ -722,26 +840,36 @@ POSE_API int pose_bn_apply_bf16(const void *Y, long M, int C, const float *scale
     REQ(M > 0 && C > 0 && C % 8 == 0 && ld_out >= C && ld_out % 8 == 0 && (!residual || (ld_res >= C && ld_res % 8 == 0)),
         POSE_E_SHAPE);
     REQ((uintptr_t)Y % 16 == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)residual % 16 == 0, POSE_E_ALIGN);
-    const long total8 = M * (C / 8);
-    bn_apply_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Y, total8, C, scale_shift, act,
-                                                                       out_scale, (const __nv_bfloat16 *)residual, ld_res,
-                                                                       (__nv_bfloat16 *)out, ld_out);
+    REQ(C <= 3072 && act >= 0 && act <= 2, POSE_E_UNSUPPORTED);
+    const int grid = rowmap_grid(M, C, 4), thr = rowmap_threads(C);
+    cudaStream_t s = (cudaStream_t)stream;
+#define BN_APPLY(A_)                                                                                                   \
+    bn_apply_kernel<A_><<<grid, thr, 0, s>>>((const __nv_bfloat16 *)Y, M, C, scale_shift, out_scale,                    \
+                                             (const __nv_bfloat16 *)residual, ld_res, (__nv_bfloat16 *)out, ld_out)
+    if (act == 0) BN_APPLY(0); else if (act == 1) BN_APPLY(1); else BN_APPLY(2);
+#undef BN_APPLY
     return launch_status();
 }
 
 POSE_API int pose_bn_bwd_bf16(const void *dA, long ld_da, const void *Y, long M, int C, const float *scale_shift,
-                              const float *mean_rstd, int act, float out_scale, float *sums2, void *dY, float *dgamma,
-                              float *dbeta, pose_stream_t stream) {
-    REQ(dA && Y && scale_shift && mean_rstd && sums2 && dY && dgamma && dbeta, POSE_E_NULL);
+                              const float *mean_rstd, int act, float out_scale, float *partials, long cap_floats, float *coef,
+                              void *dY, float *dgamma, float *dbeta, pose_stream_t stream) {
+    REQ(dA && Y && scale_shift && mean_rstd && partials && coef && dY && dgamma && dbeta, POSE_E_NULL);
     REQ(M > 0 && C > 0 && C % 8 == 0 && ld_da >= C && ld_da % 8 == 0, POSE_E_SHAPE);
     REQ((uintptr_t)dA % 16 == 0 && (uintptr_t)Y % 16 == 0 && (uintptr_t)dY % 16 == 0, POSE_E_ALIGN);
+    REQ(C <= 3072 && act >= 0 && act <= 2, POSE_E_UNSUPPORTED);
+    REQ(cap_floats >= 2L * C, POSE_E_WORKSPACE);
     cudaStream_t s = (cudaStream_t)stream;
-    bn_bwd_reduce_kernel<<<col_reduce_grid(M, C), 256, 0, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, M, C,
-                                                              scale_shift, mean_rstd, act, out_scale, sums2);
-    const long total8 = M * (C / 8);
-    bn_bwd_apply_kernel<<<grid_for(total8), 256, 0, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, total8, C,
-                                                        scale_shift, mean_rstd, act, out_scale, sums2, 1.0f / (float)M,
-                                                        (__nv_bfloat16 *)dY, dgamma, dbeta);
+    const int thr = rowmap_threads(C), parts = bn_parts(M, C, cap_floats);
+#define BN_BWD(A_)                                                                                                     \
+    bn_bwd_reduce_kernel<A_><<<parts, thr, 0, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, M, C,     \
+                                                  scale_shift, mean_rstd, out_scale, partials);                        \
+    bn_bwd_coef_kernel<<<(C + 31) / 32, 256, 0, s>>>(partials, parts, 1.0f / (float)M, scale_shift, mean_rstd, C, coef,    \
+                                                      dgamma, dbeta);                                                  \
+    bn_bwd_apply_kernel<A_><<<rowmap_grid(M, C, 4), thr, 0, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, M, \
+                                                                C, scale_shift, coef, out_scale, (__nv_bfloat16 *)dY)
+    if (act == 0) { BN_BWD(0); } else if (act == 1) { BN_BWD(1); } else { BN_BWD(2); }
+#undef BN_BWD
     return launch_status();
 }
 
@@ -757,14 +885,18 @@ POSE_API int pose_dwconv3x3_bwd_bf16(const void *dY, const void *X, const float 
                                                                (const __nv_bfloat16 *)add, total8, (__nv_bfloat16 *)dX);
     }
     if (dW) {
-        const long npx = (long)B * Ho * Wo;
+        const int th = stride == 1 ? DwT<1>::TH : DwT<2>::TH, tw = stride == 1 ? DwT<1>::TW : DwT<2>::TW;
+        const int tiles_y = (Ho + th - 1) / th, tiles_x = (Wo + tw - 1) / tw;
         const int gy = (C + 63) / 64;
-        long gx = (npx + 32 * 16 - 1) / (32 * 16);
-        const long cap = (kNumSMs * 8 + gy - 1) / gy;
+        long gx = (long)B * tiles_x * tiles_y;
+        const long cap = (kNumSMs * 6 + gy - 1) / gy;
         if (gx > cap) gx = cap;
-        if (gx < 1) gx = 1;
-        dwconv_bwd_weight_kernel<<<dim3((unsigned)gx, gy), 256, 0, s>>>((const __nv_bfloat16 *)dY, (const __nv_bfloat16 *)X, B, H, W,
-                                                                       C, Ho, Wo, stride, dW);
+        if (stride == 1)
+            dwconv_bwd_weight_kernel<1><<<dim3((unsigned)gx, gy), 256, 0, s>>>((const __nv_bfloat16 *)dY, (const __nv_bfloat16 *)X, B,
+                                                                              H, W, C, Ho, Wo, tiles_x, tiles_y, dW);
+        else
+            dwconv_bwd_weight_kernel<2><<<dim3((unsigned)gx, gy), 256, 0, s>>>((const __nv_bfloat16 *)dY, (const __nv_bfloat16 *)X, B,
+                                                                              H, W, C, Ho, Wo, tiles_x, tiles_y, dW);
     }
     return launch_status();
 }
@@ -772,11 +904,14 @@ POSE_API int pose_dwconv3x3_bwd_bf16(const void *dY, const void *X, const float 
 POSE_API int pose_gate_bwd_reduce_bf16(const void *dOut, const void *X, int B, long HW, int C, float *dgate, pose_stream_t stream) {
     REQ(dOut && X && dgate, POSE_E_NULL);
     REQ(B > 0 && HW > 0 && C > 0 && C % 8 == 0, POSE_E_SHAPE);
-    long chunks = (kNumSMs * 4 + B - 1) / B;
-    if (chunks > HW / 8) chunks = HW / 8;
-    if (chunks < 1) chunks = 1;
-    gate_bwd_reduce_kernel<<<dim3((unsigned)chunks, B), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dOut,
-                                                                                       (const __nv_bfloat16 *)X, HW, C, (int)chunks, dgate);
+    REQ(C <= 3072, POSE_E_UNSUPPORTED);
+    const int rpb = rowmap_threads(C) / (C / 8);
+    long gx = (HW + (long)rpb * 8 - 1) / ((long)rpb * 8);
+    const long cap = (kNumSMs * 8 + B - 1) / B;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    gate_bwd_reduce_kernel<<<dim3((unsigned)gx, B), rowmap_threads(C), 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dOut,
+                                                                                                 (const __nv_bfloat16 *)X, HW, C, dgate);
     return launch_status();
 }
 
@@ -894,7 +1029,7 @@ POSE_API int pose_param_repack(const void *table, int n_entries, const float *sr
                                pose_stream_t stream) {
     REQ(table && src_f32, POSE_E_NULL);
     REQ(n_entries > 0, POSE_E_SHAPE);
-    repack_kernel<<<dim3(32, n_entries), 256, 0, (cudaStream_t)stream>>>((const RepackEntry *)table, src_f32, dst_f32,
+    repack_kernel<<<dim3(n_entries >= 8 ? 64 : 296, n_entries), 256, 0, (cudaStream_t)stream>>>((const RepackEntry *)table, src_f32, dst_f32,
                                                                         (__nv_bfloat16 *)dst_bf16);
     return launch_status();
 }

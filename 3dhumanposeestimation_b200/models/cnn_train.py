@@ -78,9 +78,11 @@ class CnnTrainPlan:
                 co, ci, kh, kw = conv.weight.shape
                 src = flat.index[id(conv.weight)]
                 if conv.groups > 1:
-                    self.pk[name] = ("dw", self._pk32_off)
+                    n9 = (9 * co + 63) // 64 * 64
+                    self.pk[name] = ("dw", self._pk32_off, self._pk32_off + n9)
                     self._repack.append((src, self._pk32_off, 0, co, 0, 0, 0))
-                    self._pk32_off += (9 * co + 63) // 64 * 64
+                    self._repack.append((src, self._pk32_off + n9, 6, co, 0, 0, 0))     # flipped taps: data gradient
+                    self._pk32_off += 2 * n9
                 elif kh > 1 or conv.stride[0] > 1:
                     cp = (ci + 63) // 64 * 64
                     fwd = self._pk16_off
@@ -192,11 +194,11 @@ class CnnTrainPlan:
             self.gemm(x.data_ptr(), cin, w16.data_ptr(), cin, Bn * H * W, co, cin, self._epi(y, co))
             kind = "1x1"
         M = Bn * Ho * Wo
-        sums = self.ws(name + ".sums", 2 * co)
-        self.call("pose_bn_stats_bf16", y.data_ptr(), M, co, co, sums.data_ptr())
+        part = self.partials()
+        self.call("pose_bn_stats_bf16", y.data_ptr(), M, co, co, part.data_ptr(), part.numel())
         mr = self.buf(name + ".mr", 2 * co, dtype=torch.float32)
         ss = self.buf(name + ".ss", 2 * co, dtype=torch.float32)
-        self.call("pose_bn_finalize", sums.data_ptr(), M, flat.f32(bn.weight).data_ptr(), flat.f32(bn.bias).data_ptr(),
+        self.call("pose_bn_finalize", part.data_ptr(), part.numel(), M, flat.f32(bn.weight).data_ptr(), flat.f32(bn.bias).data_ptr(),
                   float(bn.eps), float(bn.momentum), co, mr.data_ptr(), ss.data_ptr(), bn.running_mean.data_ptr(),
                   bn.running_var.data_ptr())
         if out is None:
@@ -208,6 +210,15 @@ class CnnTrainPlan:
         self.rec[name] = dict(kind=kind, x=x, shape=shape, y=y, mr=mr, ss=ss, act=a_id, M=M, co=co, cin=cin,
                               oshape=(Bn, Ho, Wo, co), cba=cba)
         return out, (Bn, Ho, Wo, co)
+
+    def partials(self):
+        """Scratch for the two-stage per-channel reductions (stream-ordered reuse by every BatchNorm)."""
+        t = self.bufs.get("bn.partials")
+        if t is None:
+            t = torch.empty(8 << 20, dtype=torch.float32, device=self.dev)
+            self.bufs["bn.partials"] = t
+            self.bufs["bn.coef"] = torch.empty(2 * 3072, dtype=torch.float32, device=self.dev)
+        return t
 
     def zero_bias(self, n):
         t = self.bufs.get("zero_bias")
@@ -226,21 +237,31 @@ class CnnTrainPlan:
         Bn, H, W, _ = r["shape"]
         _, Ho, Wo, _ = r["oshape"]
         dy = self.buf(name + ".dy", M, co)
-        sums2 = self.ws(name + ".sums2", 2 * co)
+        part = self.partials()
         self.call("pose_bn_bwd_bf16", dA.data_ptr() + 2 * da_off, ld_da, r["y"].data_ptr(), M, co, r["ss"].data_ptr(),
-                  r["mr"].data_ptr(), r["act"], 1.0, sums2.data_ptr(), dy.data_ptr(), flat.g32(bn.weight).data_ptr(),
-                  flat.g32(bn.bias).data_ptr())
+                  r["mr"].data_ptr(), r["act"], 1.0, part.data_ptr(), part.numel(), self.bufs["bn.coef"].data_ptr(),
+                  dy.data_ptr(), flat.g32(bn.weight).data_ptr(), flat.g32(bn.bias).data_ptr())
         x = r["x"]
         kh = conv.kernel_size[0]
         stride, dil, pad = conv.stride[0], conv.dilation[0], conv.padding[0]
         add_ptr = dx_add.data_ptr() if dx_add is not None else None
         if r["kind"] == "dw":
             wd = self.pk32[self.pk[name][1]:]
-            dx = self.buf(name + ".dx", Bn * H * W, co) if need_dx else None
-            self.call("pose_dwconv3x3_bwd_bf16", dy.data_ptr(), x.data_ptr(), wd.data_ptr(), Bn, H, W, co, stride, add_ptr,
-                      dx.data_ptr() if need_dx else None, flat.g32(conv.weight).data_ptr())
             if dx_add is not None and ld_add not in (0, co):
                 raise RuntimeError("depthwise dx_add must be compact")
+            dx = self.buf(name + ".dx", Bn * H * W, co) if need_dx else None
+            if need_dx and stride == 1:
+                # stride 1: the data gradient is the forward (shared-memory tiled) kernel over dY with flipped taps
+                wf = self.pk32[self.pk[name][2]:]
+                self.call("pose_dwconv3x3_bf16", dy.data_ptr(), Bn, Ho, Wo, co, wf.data_ptr(), self.zero_bias(co).data_ptr(), 1,
+                          0, dx.data_ptr(), None, 0)
+                if dx_add is not None:
+                    self.call("pose_add_bf16", dx.data_ptr(), add_ptr, dx.numel(), dx.data_ptr())
+                self.call("pose_dwconv3x3_bwd_bf16", dy.data_ptr(), x.data_ptr(), wd.data_ptr(), Bn, H, W, co, stride, None,
+                          None, flat.g32(conv.weight).data_ptr())
+            else:
+                self.call("pose_dwconv3x3_bwd_bf16", dy.data_ptr(), x.data_ptr(), wd.data_ptr(), Bn, H, W, co, stride, add_ptr,
+                          dx.data_ptr() if need_dx else None, flat.g32(conv.weight).data_ptr())
             return dx
         if r["kind"] == "conv":
             _, fwd, bwd, cp, stage, ui = self.pk[name]
@@ -326,11 +347,11 @@ class CnnTrainPlan:
         e = self._epi(y1, mid, bias=flat.f32(att.conv1.bias))
         self.gemm(P.data_ptr(), ch, flat.w16(att.conv1.weight).data_ptr(), ch, rows, mid, ch, e)
         bn = att.bn1
-        sums = self.ws(name + ".sums", 2 * mid)
-        self.call("pose_bn_stats_bf16", y1.data_ptr(), rows, mid, mid, sums.data_ptr())
+        part = self.partials()
+        self.call("pose_bn_stats_bf16", y1.data_ptr(), rows, mid, mid, part.data_ptr(), part.numel())
         mr = self.buf(name + ".mr", 2 * mid, dtype=torch.float32)
         ss = self.buf(name + ".ss", 2 * mid, dtype=torch.float32)
-        self.call("pose_bn_finalize", sums.data_ptr(), rows, flat.f32(bn.weight).data_ptr(), flat.f32(bn.bias).data_ptr(),
+        self.call("pose_bn_finalize", part.data_ptr(), part.numel(), rows, flat.f32(bn.weight).data_ptr(), flat.f32(bn.bias).data_ptr(),
                   float(bn.eps), float(bn.momentum), mid, mr.data_ptr(), ss.data_ptr(), bn.running_mean.data_ptr(),
                   bn.running_var.data_ptr())
         a1 = self.buf(name + ".a1", rows, mid)
@@ -397,9 +418,10 @@ class CnnTrainPlan:
             self.gemm_tr(zp, 2 * ch, 0, flat.w16(cv.weight).data_ptr(), mid, 1, rows, mid, ch, e)
         bn = att.bn1
         dy1 = self.buf(name + ".dy1", rows, mid)
-        sums2 = self.ws(name + ".sums2", 2 * mid)
+        part = self.partials()
         self.call("pose_bn_bwd_bf16", da1.data_ptr(), mid, y1.data_ptr(), rows, mid, r["ss"].data_ptr(), r["mr"].data_ptr(), 2,
-                  1.0, sums2.data_ptr(), dy1.data_ptr(), flat.g32(bn.weight).data_ptr(), flat.g32(bn.bias).data_ptr())
+                  1.0, part.data_ptr(), part.numel(), self.bufs["bn.coef"].data_ptr(), dy1.data_ptr(),
+                  flat.g32(bn.weight).data_ptr(), flat.g32(bn.bias).data_ptr())
         self.gemm_tr(dy1.data_ptr(), mid, 1, P.data_ptr(), ch, 1, mid, ch, rows,
                      self._epi(flat.g32(att.conv1.weight).view(mid, ch), ch, accumulate=1), self._splits(mid, ch, rows))
         self.call("pose_colsum_bf16", dy1.data_ptr(), rows, mid, mid, flat.g32(att.conv1.bias).data_ptr())

@@ -276,12 +276,14 @@ int pose_adamw_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq
  *                           padding), split k_splits ways.  Cin % 64 == 0.  The data gradient of a stride-1 convolution is
  *                           pose_conv2d_bf16 over dY with the flipped / transposed weights (pose_param_repack kind 2).
  *  BatchNorm2d in training mode (batch statistics, cnn.py:135-139), fused with activation, residual add and concat:
- *   pose_bn_stats_bf16      sums[c] += sum_r y, sums[C + c] += sum_r y^2          (sums zeroed by the caller)
- *   pose_bn_finalize        mean / rstd, the affine (scale, shift) that normalises, running statistics (momentum,
- *                           unbiased variance) -- nn.BatchNorm2d semantics
+ *   pose_bn_stats_bf16      per-block partial sums of y and y^2 into `partials` (scratch of cap_floats floats, shared by
+ *                           all layers: consumers run before the next producer on the stream); no atomics
+ *   pose_bn_finalize        folds the partials in a fixed order (deterministic statistics): mean / rstd, the affine
+ *                           (scale, shift) that normalises, running statistics (momentum, unbiased variance) --
+ *                           nn.BatchNorm2d semantics.  Pass the same (count = M, C, cap_floats) as to pose_bn_stats_bf16
  *   pose_bn_apply_bf16      out[r, :ld_out] = residual + out_scale * act(y * scale + shift)
- *   pose_bn_bwd_bf16        dY from dA (pitch ld_da: a column slice of a concatenation) -- two passes (per-channel sums, then
- *                           the gradient); dgamma, dbeta accumulated; sums2 [2, C] zeroed by the caller
+ *   pose_bn_bwd_bf16        dY from dA (pitch ld_da: a column slice of a concatenation) -- per-channel partial sums, a
+ *                           fixed-order fold (dgamma, dbeta accumulated; coef [2, C] scratch), then the gradient
  *  pose_dwconv3x3_bwd_bf16  depthwise 3x3 backward: dX (+ add) and / or dW (parameter layout [C,1,3,3], accumulated)
  *  pose_gate_bwd_*          x * gate[b, c] (SE / ECA): dgate[b,c] += sum_p dOut * x;  dX = add + dOut * gate + dmean / HW
  *  pose_sigmoid_bwd, pose_eca_bwd, pose_coord_bwd_*, pose_wasp_mix_*: see csrc/cnn_train.cu
@@ -297,13 +299,15 @@ typedef struct pose_repack_entry {
 
 int pose_conv2d_wgrad_bf16(const void *dY, const void *X, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
                            int dil, int pad, float *dWk, int k_splits, pose_stream_t stream);
-int pose_bn_stats_bf16(const void *Y, long M, int C, long ld, float *sums, pose_stream_t stream);
-int pose_bn_finalize(const float *sums, long count, const float *gamma, const float *beta, float eps, float momentum, int C,
-                     float *mean_rstd, float *scale_shift, float *running_mean, float *running_var, pose_stream_t stream);
+int pose_bn_stats_bf16(const void *Y, long M, int C, long ld, float *partials, long cap_floats, pose_stream_t stream);
+int pose_bn_finalize(const float *partials, long cap_floats, long count, const float *gamma, const float *beta, float eps,
+                     float momentum, int C, float *mean_rstd, float *scale_shift, float *running_mean, float *running_var,
+                     pose_stream_t stream);
 int pose_bn_apply_bf16(const void *Y, long M, int C, const float *scale_shift, int act, float out_scale, const void *residual,
                        long ld_res, void *out, long ld_out, pose_stream_t stream);
 int pose_bn_bwd_bf16(const void *dA, long ld_da, const void *Y, long M, int C, const float *scale_shift, const float *mean_rstd,
-                     int act, float out_scale, float *sums2, void *dY, float *dgamma, float *dbeta, pose_stream_t stream);
+                     int act, float out_scale, float *partials, long cap_floats, float *coef, void *dY, float *dgamma,
+                     float *dbeta, pose_stream_t stream);
 int pose_dwconv3x3_bwd_bf16(const void *dY, const void *X, const float *Wd, int B, int H, int W, int C, int stride,
                             const void *add, void *dX, float *dW, pose_stream_t stream);
 int pose_gate_bwd_reduce_bf16(const void *dOut, const void *X, int B, long HW, int C, float *dgate, pose_stream_t stream);

@@ -26,12 +26,12 @@ def test_batchnorm_training_forward_backward(pose, M, Cc, act):
     rm, rv = torch.zeros(Cc, device=DEV), torch.ones(Cc, device=DEV)
     res = torch.randn(M, Cc, generator=g).to(DEV).bfloat16()
     da = torch.randn(M, Cc + 8, generator=g).to(DEV).bfloat16()          # column slice of a wider gradient
-    sums = torch.zeros(2 * Cc, device=DEV)
+    part = torch.empty(1 << 20, device=DEV)                  # per-block partial sums (no atomics, fixed-order fold)
     mr, ss = torch.empty(2 * Cc, device=DEV), torch.empty(2 * Cc, device=DEV)
     out = torch.empty(M, Cc, device=DEV, dtype=torch.bfloat16)
-    check(lib.pose_bn_stats_bf16(y.data_ptr(), M, Cc, Cc, sums.data_ptr(), sp()), "stats")
-    check(lib.pose_bn_finalize(sums.data_ptr(), M, gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1, Cc, mr.data_ptr(), ss.data_ptr(),
-                               rm.data_ptr(), rv.data_ptr(), sp()), "finalize")
+    check(lib.pose_bn_stats_bf16(y.data_ptr(), M, Cc, Cc, part.data_ptr(), part.numel(), sp()), "stats")
+    check(lib.pose_bn_finalize(part.data_ptr(), part.numel(), M, gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1, Cc, mr.data_ptr(),
+                               ss.data_ptr(), rm.data_ptr(), rv.data_ptr(), sp()), "finalize")
     check(lib.pose_bn_apply_bf16(y.data_ptr(), M, Cc, ss.data_ptr(), act, 1.0, res.data_ptr(), Cc, out.data_ptr(), Cc, sp()), "apply")
     yr = y.float().requires_grad_()
     gr, br = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
@@ -42,10 +42,11 @@ def test_batchnorm_training_forward_backward(pose, M, Cc, act):
     assert torch.allclose(rm, rm2, rtol=1e-3, atol=1e-4) and torch.allclose(rv, rv2, rtol=1e-3, atol=1e-4)
     a.backward(da[:, 8:].float())
     dy = torch.empty(M, Cc, device=DEV, dtype=torch.bfloat16)
-    sums2 = torch.zeros(2 * Cc, device=DEV)
+    coef = torch.empty(2 * Cc, device=DEV)
     dg, db = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
     check(lib.pose_bn_bwd_bf16(da.data_ptr() + 16, Cc + 8, y.data_ptr(), M, Cc, ss.data_ptr(), mr.data_ptr(), act, 1.0,
-                               sums2.data_ptr(), dy.data_ptr(), dg.data_ptr(), db.data_ptr(), sp()), "bn_bwd")
+                               part.data_ptr(), part.numel(), coef.data_ptr(), dy.data_ptr(), dg.data_ptr(), db.data_ptr(),
+                               sp()), "bn_bwd")
     scale = yr.grad.abs().max().item()
     assert (dy.float() - yr.grad).abs().max().item() < 2e-2 * scale + 1e-3
     assert torch.allclose(dg, gr.grad, rtol=2e-2, atol=2e-2 * M ** 0.5)
