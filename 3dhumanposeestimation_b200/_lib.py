@@ -20,7 +20,8 @@ class PoseGemmEpilogue(C.Structure):
 
     _fields_ = [("bias", C.c_void_p), ("residual", C.c_void_p), ("C", C.c_void_p), ("ldc", C.c_int32),
                 ("ldr", C.c_int32), ("act", C.c_int32), ("out_dtype", C.c_int32), ("out_scale", C.c_float),
-                ("res_scale", C.c_float), ("preact", C.c_void_p), ("accumulate", C.c_int32), ("reserved", C.c_int32)]
+                ("res_scale", C.c_float), ("preact", C.c_void_p), ("accumulate", C.c_int32), ("reserved", C.c_int32),
+                ("drop_seed", C.c_uint64), ("drop_p", C.c_float), ("reserved2", C.c_int32)]
 
 
 class PoseRepackEntry(C.Structure):
@@ -82,14 +83,15 @@ SIGNATURES = {
     "pose_patchify_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pose_attention_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, C.c_long,
                                     C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, c_float, c_void_p,
-                                    c_void_p]),
+                                    c_float, C.c_uint64, c_void_p]),
     "pose_layernorm_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_float, C.c_long, c_int, C.c_long, C.c_long,
                                         C.c_long, C.c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pose_colsum_bf16": (c_int, [c_void_p, C.c_long, c_int, C.c_long, c_void_p, c_void_p]),
     "pose_cast_f32_bf16_2d": (c_int, [c_void_p, C.c_long, C.c_long, c_int, c_void_p, C.c_long, c_void_p]),
     "pose_batch_rowsum_bf16": (c_int, [c_void_p, c_int, C.c_long, C.c_long, c_int, c_int, c_void_p, c_void_p]),
     "pose_token_slice_bf16": (c_int, [c_void_p, c_int, C.c_long, C.c_long, c_int, c_int, c_void_p, c_void_p]),
-    "pose_attention_bwd_bf16": (c_int, [c_void_p] * 10 + [c_int] * 5 + [C.c_long] * 16 + [c_float, c_void_p]),
+    "pose_attention_bwd_bf16": (c_int, [c_void_p] * 10 + [c_int] * 5 + [C.c_long] * 16 + [c_float, c_float, C.c_uint64,
+                                                                                            c_void_p]),
     "pose_cnn_input_pack_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     "pose_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [c_void_p, c_int, c_void_p]),
     "pose_bn_stats_bf16": (c_int, [c_void_p, C.c_long, c_int, C.c_long, c_void_p, C.c_long, c_void_p]),

@@ -91,7 +91,8 @@ template <int HD>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K, const __nv_bfloat16 *__restrict__ V,
                    __nv_bfloat16 *__restrict__ O, float *__restrict__ lse, int Nq, int Nk, int Nkp, long ldq, long ldk, long ldv,
-                   long ldo, long bsq, long bsk, long bsv, long bso, float scale) {
+                   long ldo, long bsq, long bsk, long bsv, long bso, float scale, uint32_t drop_thresh, float drop_scale,
+                   unsigned long long drop_seed) {
     unsigned char *smem;
     uint64_t *bar;
     const uint32_t tmem = attn_prologue(smem, bar);
@@ -148,6 +149,10 @@ attn_fwd_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__r
                         const int col = c * 32 + j8 * 8 + j;
                         p[j] = col < Nk ? exp2f(fmaf(__uint_as_float(v[j8 * 8 + j]), sl2, -ms)) : 0.f;
                         sum += p[j];
+                        // attention-weight dropout (nn.MultiheadAttention(dropout=p)): the row still normalises by the full sum
+                        if (drop_thresh)
+                            p[j] = drop_keep(drop_seed, (((unsigned long long)b * heads + h) * Nq + q0 + r) * Nk + col, drop_thresh)
+                                       ? p[j] * drop_scale : 0.f;
                     }
                     const int col8 = c * 4 + j8;
                     if (col8 * 8 < Nkp)
@@ -203,7 +208,7 @@ attn_bwd_dq_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *
                       const __nv_bfloat16 *__restrict__ O, const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ lse,
                       __nv_bfloat16 *__restrict__ dQ, float *__restrict__ Dout, int Nq, int Nk, int Nkp, long ldq, long ldk,
                       long ldv, long ldo, long lddo, long lddq, long bsq, long bsk, long bsv, long bso, long bsdo, long bsdq,
-                      float scale) {
+                      float scale, uint32_t drop_thresh, float drop_scale, unsigned long long drop_seed) {
     unsigned char *smem;
     uint64_t *bar;
     const uint32_t tmem = attn_prologue(smem, bar);
@@ -270,7 +275,11 @@ attn_bwd_dq_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *
                         for (int j = 0; j < 8; ++j) {
                             const int col = kc0 + c * 32 + j8 * 8 + j;
                             const float pr = (col < Nk && row_ok) ? exp2f(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -l2)) : 0.f;
-                            ds[j] = pr * (__uint_as_float(p[j8 * 8 + j]) - Dr) * scale;
+                            float dp = __uint_as_float(p[j8 * 8 + j]);
+                            if (drop_thresh)
+                                dp = drop_keep(drop_seed, (((unsigned long long)b * heads + h) * Nq + q0 + r) * Nk + col, drop_thresh)
+                                         ? dp * drop_scale : 0.f;
+                            ds[j] = pr * (dp - Dr) * scale;
                         }
                         const int col8 = c * 4 + j8;
                         if (col8 * 8 < n)
@@ -324,7 +333,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_dkv_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K, const __nv_bfloat16 *__restrict__ V,
                        const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ lse, const float *__restrict__ Dg,
                        __nv_bfloat16 *__restrict__ dK, __nv_bfloat16 *__restrict__ dV, int Nq, int Nk, long ldq, long ldk, long ldv,
-                       long lddo, long lddk, long lddv, long bsq, long bsk, long bsv, long bsdo, long bsdk, long bsdv, float scale) {
+                       long lddo, long lddk, long lddv, long bsq, long bsk, long bsv, long bsdo, long bsdk, long bsdv, float scale,
+                       uint32_t drop_thresh, float drop_scale, unsigned long long drop_seed) {
     unsigned char *smem;
     uint64_t *bar;
     const uint32_t tmem = attn_prologue(smem, bar);
@@ -379,8 +389,12 @@ attn_bwd_dkv_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 
                     for (int j = 0; j < 8; ++j) {
                         const int col = c * 32 + j8 * 8 + j;                  // query within the tile
                         const float pr = col < rows ? exp2f(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -lse_s[col])) : 0.f;
-                        pv[j] = pr;
-                        ds[j] = pr * (__uint_as_float(p[j8 * 8 + j]) - D_s[col]) * scale;
+                        float keep = 1.0f;
+                        if (drop_thresh)
+                            keep = drop_keep(drop_seed, (((unsigned long long)b * heads + h) * Nq + q0 + col) * Nk + k0 + r, drop_thresh)
+                                       ? drop_scale : 0.f;
+                        pv[j] = pr * keep;                                    // dV sees the dropped probabilities
+                        ds[j] = pr * (__uint_as_float(p[j8 * 8 + j]) * keep - D_s[col]) * scale;
                     }
                     const int col8 = c * 4 + j8;
                     if (col8 * 8 < np) {
@@ -452,8 +466,11 @@ using namespace pose;
 
 POSE_API int pose_attention_bf16(const void *Q, const void *K, const void *V, void *O, int B, int heads, int Nq, int Nk,
                                  int head_dim, long ldq, long ldk, long ldv, long ldo, long bsq, long bsk, long bsv, long bso,
-                                 float scale, float *lse, pose_stream_t stream) {
+                                 float scale, float *lse, float drop_p, uint64_t drop_seed, pose_stream_t stream) {
     if (!Q || !K || !V || !O) return POSE_E_NULL;
+    if (drop_p < 0.f || drop_p >= 1.f) return POSE_E_SHAPE;
+    const uint32_t dth = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
+    const float dsc = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     if (B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return POSE_E_SHAPE;
     if (head_dim != 48 && head_dim != 64) return POSE_E_UNSUPPORTED;
     if (Nk > 288) return POSE_E_UNSUPPORTED;              // the whole score row lives in TMEM (<= 288 columns)
@@ -467,7 +484,7 @@ POSE_API int pose_attention_bf16(const void *Q, const void *K, const void *V, vo
     if ((e = set_smem(attn_fwd_tc_kernel<HD_>, kFwdSmem))) return e;                                                    \
     attn_fwd_tc_kernel<HD_><<<grid, kAttnThreads, kFwdSmem, s>>>((const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K,     \
                                                                 (const __nv_bfloat16 *)V, (__nv_bfloat16 *)O, lse, Nq, Nk, Nkp, \
-                                                                ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale)
+                                                                ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale, dth, dsc, drop_seed)
     if (head_dim == 64) { FWD(64); } else { FWD(48); }
 #undef FWD
     return launch_status();
@@ -477,8 +494,11 @@ POSE_API int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V
                                      const float *lse, void *dQ, void *dK, void *dV, float *Dws, int B, int heads, int Nq,
                                      int Nk, int head_dim, long ldq, long ldk, long ldv, long ldo, long lddo, long lddq,
                                      long lddk, long lddv, long bsq, long bsk, long bsv, long bso, long bsdo, long bsdq,
-                                     long bsdk, long bsdv, float scale, pose_stream_t stream) {
+                                     long bsdk, long bsdv, float scale, float drop_p, uint64_t drop_seed, pose_stream_t stream) {
     if (!Q || !K || !V || !O || !dO || !lse || !dQ || !dK || !dV || !Dws) return POSE_E_NULL;
+    if (drop_p < 0.f || drop_p >= 1.f) return POSE_E_SHAPE;
+    const uint32_t dth = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
+    const float dsc = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     if (B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return POSE_E_SHAPE;
     if (head_dim != 48 && head_dim != 64) return POSE_E_UNSUPPORTED;
     if (Nk > 288) return POSE_E_UNSUPPORTED;
@@ -498,11 +518,11 @@ POSE_API int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V
     attn_bwd_dq_tc_kernel<HD_><<<g1, kAttnThreads, kDqSmem, s>>>(                                                       \
         (const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V, (const __nv_bfloat16 *)O,        \
         (const __nv_bfloat16 *)dO, lse, (__nv_bfloat16 *)dQ, Dws, Nq, Nk, Nkp, ldq, ldk, ldv, ldo, lddo, lddq, bsq, bsk,  \
-        bsv, bso, bsdo, bsdq, scale);                                                                                  \
+        bsv, bso, bsdo, bsdq, scale, dth, dsc, drop_seed);                                                             \
     attn_bwd_dkv_tc_kernel<HD_><<<g2, kAttnThreads, kDkvSmem, s>>>(                                                     \
         (const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V, (const __nv_bfloat16 *)dO, lse,  \
         Dws, (__nv_bfloat16 *)dK, (__nv_bfloat16 *)dV, Nq, Nk, ldq, ldk, ldv, lddo, lddk, lddv, bsq, bsk, bsv, bsdo,    \
-        bsdk, bsdv, scale)
+        bsdk, bsdv, scale, dth, dsc, drop_seed)
     if (head_dim == 64) { BWD(64); } else { BWD(48); }
 #undef BWD
     return launch_status();

@@ -736,15 +736,11 @@ add_kernel(const __nv_bfloat16 *__restrict__ a, const __nv_bfloat16 *__restrict_
 }
 
 // counter-based dropout mask: element i of call `seed` is kept iff hash(seed, i) >= p * 2^32 (same mask in backward)
-__device__ __forceinline__ uint32_t mix32(uint64_t x) {
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
-    return (uint32_t)x;
-}
 __global__ void __launch_bounds__(256)
 dropout_kernel(const __nv_bfloat16 *__restrict__ x, long n, uint32_t thresh, float keep_scale, uint64_t seed,
                __nv_bfloat16 *__restrict__ out) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        const bool keep = mix32(seed * 0x9E3779B97F4A7C15ULL + (uint64_t)i) >= thresh;
+        const bool keep = drop_keep(seed, (uint64_t)i, thresh);
         out[i] = __float2bfloat16_rn(keep ? __bfloat162float(x[i]) * keep_scale : 0.f);
     }
 }
@@ -1019,7 +1015,7 @@ POSE_API int pose_add_bf16(const void *a, const void *b, long n, void *out, pose
 POSE_API int pose_dropout_bf16(const void *x, long n, float p, uint64_t seed, void *out, pose_stream_t stream) {
     REQ(x && out, POSE_E_NULL);
     REQ(n > 0 && p >= 0.f && p < 1.f, POSE_E_SHAPE);
-    const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+    const uint32_t thresh = drop_threshold(p);
     dropout_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x, n, thresh, 1.0f / (1.0f - p), seed,
                                                                  (__nv_bfloat16 *)out);
     return launch_status();

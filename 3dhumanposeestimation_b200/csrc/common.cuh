@@ -27,6 +27,17 @@ __device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
     return v;
 }
 
+// Counter-based dropout mask shared by every kernel that applies or re-applies dropout: element `i` of the tensor that
+// call `seed` drops is kept iff hash(seed, i) >= p * 2^32.  The backward pass regenerates the same mask from (seed, i).
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return (uint32_t)x;
+}
+__device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t i, uint32_t thresh) {
+    return mix32(seed * 0x9E3779B97F4A7C15ULL + i) >= thresh;
+}
+inline uint32_t drop_threshold(float p) { return (uint32_t)((double)p * 4294967296.0); }
+
 // streaming 128-bit store: outputs are written once and not re-read by the producing kernel
 __device__ __forceinline__ void st_stream_f4(float *p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)

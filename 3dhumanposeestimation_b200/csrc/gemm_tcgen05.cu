@@ -53,6 +53,9 @@ struct Epilogue {
     float out_scale, res_scale;      // C = act(acc + bias) * out_scale + residual * res_scale
     __nv_bfloat16 *preact;           // [M, ldc] bf16 or null: acc + bias before the activation (saved for backward)
     int accumulate;                  // fp32 C += acc * out_scale with red.global (split-K weight gradients)
+    uint32_t drop_thresh;            // dropout after the activation (before the residual): keep iff hash >= thresh
+    float drop_scale;                // 1 / (1 - p)
+    unsigned long long drop_seed;    // element index = row * ldc + col (common.cuh: drop_keep)
 };
 
 struct ConvGeom {          // MODE 1 only
@@ -148,6 +151,13 @@ __device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, 
             const float2 u1 = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.y);
             x.x *= act_grad<ACT>(u0.x) * ep.out_scale; x.y *= act_grad<ACT>(u0.y) * ep.out_scale;
             x.z *= act_grad<ACT>(u1.x) * ep.out_scale; x.w *= act_grad<ACT>(u1.y) * ep.out_scale;
+            if (ep.drop_thresh) {     // the forward dropped act(u): the same mask gates the gradient
+                const unsigned long long i0 = (unsigned long long)grow * ep.ldc + col;
+                x.x = drop_keep(ep.drop_seed, i0, ep.drop_thresh) ? x.x * ep.drop_scale : 0.f;
+                x.y = drop_keep(ep.drop_seed, i0 + 1, ep.drop_thresh) ? x.y * ep.drop_scale : 0.f;
+                x.z = drop_keep(ep.drop_seed, i0 + 2, ep.drop_thresh) ? x.z * ep.drop_scale : 0.f;
+                x.w = drop_keep(ep.drop_seed, i0 + 3, ep.drop_thresh) ? x.w * ep.drop_scale : 0.f;
+            }
         } else {
             x.x += bz.x; x.y += bz.y; x.z += bz.z; x.w += bz.w;
             if (ep.preact != nullptr) {
@@ -158,6 +168,13 @@ __device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, 
             x.y = fast_act<ACT>(x.y) * ep.out_scale;
             x.z = fast_act<ACT>(x.z) * ep.out_scale;
             x.w = fast_act<ACT>(x.w) * ep.out_scale;
+            if (ep.drop_thresh) {
+                const unsigned long long i0 = (unsigned long long)grow * ep.ldc + col;
+                x.x = drop_keep(ep.drop_seed, i0, ep.drop_thresh) ? x.x * ep.drop_scale : 0.f;
+                x.y = drop_keep(ep.drop_seed, i0 + 1, ep.drop_thresh) ? x.y * ep.drop_scale : 0.f;
+                x.z = drop_keep(ep.drop_seed, i0 + 2, ep.drop_thresh) ? x.z * ep.drop_scale : 0.f;
+                x.w = drop_keep(ep.drop_seed, i0 + 3, ep.drop_thresh) ? x.w * ep.drop_scale : 0.f;
+            }
             if (ep.residual != nullptr) {
                 const uint2 pk = __ldg((const uint2 *)(ep.residual + grow * ep.ldr + col));
                 const float2 f0 = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.x);
@@ -196,6 +213,8 @@ __device__ __forceinline__ void epilogue_rows_slow(uint32_t stg, const Epilogue 
             if (ep.act >= 5) {
                 const float u = __bfloat162float(ep.residual[grow * ep.ldr + col + q]);
                 y *= (ep.act == 5 ? act_grad<5>(u) : (ep.act == 6 ? act_grad<6>(u) : act_grad<7>(u))) * ep.out_scale;
+                if (ep.drop_thresh)
+                    y = drop_keep(ep.drop_seed, (unsigned long long)grow * ep.ldc + col + q, ep.drop_thresh) ? y * ep.drop_scale : 0.f;
             } else {
                 if (ep.bias != nullptr) y += __ldg(ep.bias + col + q);
                 if (ep.preact != nullptr) ep.preact[grow * ep.ldc + col + q] = __float2bfloat16_rn(y);
@@ -207,6 +226,8 @@ __device__ __forceinline__ void epilogue_rows_slow(uint32_t stg, const Epilogue 
                     default: break;
                 }
                 y *= ep.out_scale;
+                if (ep.drop_thresh)
+                    y = drop_keep(ep.drop_seed, (unsigned long long)grow * ep.ldc + col + q, ep.drop_thresh) ? y * ep.drop_scale : 0.f;
                 if (ep.residual != nullptr) y += __bfloat162float(ep.residual[grow * ep.ldr + col + q]) * ep.res_scale;
             }
             if (ep.accumulate) atomicAdd((float *)ep.C + grow * ep.ldc + col + q, y);
@@ -569,6 +590,10 @@ static int check_epilogue(const pose_gemm_epilogue *e, int N, Epilogue &ep) {
     ep.res_scale = e->res_scale;
     ep.preact = (__nv_bfloat16 *)e->preact;
     ep.accumulate = e->accumulate;
+    if (e->drop_p < 0.f || e->drop_p >= 1.f) return POSE_E_SHAPE;
+    ep.drop_thresh = e->drop_p > 0.f ? drop_threshold(e->drop_p) : 0u;
+    ep.drop_scale = e->drop_p > 0.f ? 1.0f / (1.0f - e->drop_p) : 1.0f;
+    ep.drop_seed = e->drop_seed;
     return POSE_OK;
 }
 
@@ -639,7 +664,7 @@ POSE_API int pose_gemm_bf16_tr(const void *A, long lda, int a_mn, const void *W,
 
 POSE_API int pose_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, void *C, int ldc,
                             int M, int N, int K, int act, int out_dtype, pose_stream_t stream) {
-    pose_gemm_epilogue e = {bias, nullptr, C, ldc, 0, act, out_dtype, 1.0f, 0.0f, nullptr, 0, 0};
+    pose_gemm_epilogue e = {bias, nullptr, C, ldc, 0, act, out_dtype, 1.0f, 0.0f, nullptr, 0, 0, 0ull, 0.0f, 0};
     return pose_gemm_bf16_ex(A, lda, W, ldw, M, N, K, &e, stream);
 }
 
@@ -698,7 +723,7 @@ POSE_API int pose_conv2d_wgrad_bf16(const void *dY, const void *X, int Nimg, int
     if (TW * TH * TN != 64 || Ho % TH || Wo % TW) return POSE_E_UNSUPPORTED;
     const int patches = ((Nimg + TN - 1) / TN) * (Ho / TH) * (Wo / TW);
     const int M = Cout, N = KH * KW * Cin, K = patches * 64;
-    pose_gemm_epilogue pe = {nullptr, nullptr, dWk, N, 0, 0, 0, 1.0f, 0.0f, nullptr, 1, 0};
+    pose_gemm_epilogue pe = {nullptr, nullptr, dWk, N, 0, 0, 0, 1.0f, 0.0f, nullptr, 1, 0, 0ull, 0.0f, 0};
     Epilogue ep;
     int e = check_epilogue(&pe, N, ep);
     if (e) return e;

@@ -259,10 +259,14 @@ class VitPlan:
             raise NotImplementedError(
                 f"{self.T_fin} tokens: the attention kernels keep a whole score row on chip (<= 288 keys; 256x256 "
                 "inputs).  A streaming (flash) variant is the planned extension for 512x512.")
-        if c.transformer_dropout_rate or c.transformer_attention_dropout_rate or c.regression_dropout:
-            self.dropout = True     # training-mode forward raises (see forward)
-        else:
-            self.dropout = False
+        # nn.Dropout sites of the reference (transformers.py:24,61-72,98-124,363): active in training mode only; the timm
+        # backbone has no dropout (all its drop rates default to 0)
+        self.p_drop = float(c.transformer_dropout_rate)
+        self.p_attn = float(c.transformer_attention_dropout_rate)
+        self.p_head = float(c.regression_dropout)
+        self.step_count = 0
+        self.seeds = {}
+        self.training = False
         self.flat = FlatParams.of(model.parameters())
         self.bufs = {}
         self.launches = 0
@@ -282,8 +286,19 @@ class VitPlan:
         _lib.check(getattr(self.lib, name)(*args, _lib.stream_ptr()), name)
         self.launches += 1
 
+    def seed(self, site):
+        """Dropout seed of a site for the current step (the backward pass regenerates the mask from it)."""
+        idx = self.seeds.get(site)
+        if idx is None:
+            idx = self.seeds[site] = len(self.seeds) + 1
+        return self.step_count * 4096 + idx
+
+    def drop(self, site, p):
+        """(p, seed) for a dropout site, or None when dropout is off (eval mode / p = 0)."""
+        return (p, self.seed(site)) if (self.training and p > 0.0) else None
+
     def _epi(self, out, ldc, bias=None, act=0, residual=None, ldr=0, preact=None, accumulate=0, out_scale=1.0,
-             res_scale=1.0):
+             res_scale=1.0, drop=None):
         e = _lib.PoseGemmEpilogue()
         e.bias = bias.data_ptr() if bias is not None else None
         e.residual = residual.data_ptr() if residual is not None else None
@@ -293,10 +308,12 @@ class VitPlan:
         e.out_scale, e.res_scale = out_scale, res_scale
         e.preact = preact.data_ptr() if preact is not None else None
         e.accumulate = accumulate
+        if drop is not None:
+            e.drop_p, e.drop_seed = drop
         return e
 
     # ---- forward ops ---------------------------------------------------------------------------------
-    def linear(self, name, x, M, weight, bias, rows=None, act=0, residual=None, preact=False, fp32=False):
+    def linear(self, name, x, M, weight, bias, rows=None, act=0, residual=None, preact=False, fp32=False, drop=None):
         """y = act(x @ W[rows]^T + b[rows]) (+ residual); returns y (and keeps the pre-activation when asked)."""
         w16 = self.flat.w16(weight, rows)
         N, K = w16.shape
@@ -305,7 +322,7 @@ class VitPlan:
             b = b[rows[0]:rows[1]]
         y = self.buf(name, M, N, dtype=torch.float32 if fp32 else torch.bfloat16)
         u = self.buf(name + ".u", M, N) if preact else None
-        e = self._epi(y, N, b, act, residual, N if residual is not None else 0, u)
+        e = self._epi(y, N, b, act, residual, N if residual is not None else 0, u, drop=drop)
         self.call("pose_gemm_bf16_ex", x.data_ptr(), K, w16.data_ptr(), K, M, N, K, C.byref(e))
         return (y, u) if preact else y
 
@@ -319,36 +336,40 @@ class VitPlan:
                   self.flat.f32(ln.bias).data_ptr(), float(ln.eps), M, rows, in_group, in_off, rows, 0, D, y.data_ptr())
         return y
 
-    def attention(self, name, q, k, v, Nq, Nk, heads, ldq, ldk, ldv, save):
+    def attention(self, name, q, k, v, Nq, Nk, heads, ldq, ldk, ldv, save, drop=None):
         """softmax(q k^T / sqrt(hd)) v per (sample, head); q/k/v are column offsets into row-major buffers."""
         E, B = self.E, self.B
         hd = E // heads
         o = self.buf(name, B * Nq, E)
         lse = self.buf(name + ".lse", B, heads, Nq, dtype=torch.float32) if save else None
         self.call("pose_attention_bf16", q, k, v, o.data_ptr(), B, heads, Nq, Nk, hd, ldq, ldk, ldv, E, Nq * ldq,
-                  Nk * ldk, Nk * ldv, Nq * E, 1.0 / math.sqrt(hd), lse.data_ptr() if save else None)
+                  Nk * ldk, Nk * ldv, Nq * E, 1.0 / math.sqrt(hd), lse.data_ptr() if save else None,
+                  drop[0] if drop else 0.0, drop[1] if drop else 0)
         return o
 
-    def encoder_block(self, pre, x, T, norm1, wqkv, bqkv, wo, bo, norm2, fc1, fc2, heads, save):
-        """pre-LN transformer block (timm Block and TransformerEncoderBlock, transformers.py:75-82)."""
+    def encoder_block(self, pre, x, T, norm1, wqkv, bqkv, wo, bo, norm2, fc1, fc2, heads, save, p_drop=0.0, p_attn=0.0):
+        """pre-LN transformer block (timm Block and TransformerEncoderBlock, transformers.py:75-82); dropout on the
+        attention weights, on the projected attention output, after the activation and after fc2 (transformers.py:61-72)."""
         M, E = self.B * T, self.E
         h = self.layernorm(pre + "h", x, norm1, M)
         qkv = self.linear(pre + "qkv", h, M, wqkv, bqkv)
         p = qkv.data_ptr()
-        o = self.attention(pre + "o", p, p + 2 * E, p + 4 * E, T, T, heads, 3 * E, 3 * E, 3 * E, save)
-        x1 = self.linear(pre + "x1", o, M, wo, bo, residual=x)
+        o = self.attention(pre + "o", p, p + 2 * E, p + 4 * E, T, T, heads, 3 * E, 3 * E, 3 * E, save,
+                           drop=self.drop(pre + "attn", p_attn))
+        x1 = self.linear(pre + "x1", o, M, wo, bo, residual=x, drop=self.drop(pre + "proj", p_drop))
         h2 = self.layernorm(pre + "h2", x1, norm2, M)
-        g = self.linear(pre + "g", h2, M, fc1.weight, fc1.bias, act=self.act, preact=save)
+        g = self.linear(pre + "g", h2, M, fc1.weight, fc1.bias, act=self.act, preact=save, drop=self.drop(pre + "act", p_drop))
         if save:
             g = g[0]
-        return self.linear(pre + "x2", g, M, fc2.weight, fc2.bias, residual=x1)
+        return self.linear(pre + "x2", g, M, fc2.weight, fc2.bias, residual=x1, drop=self.drop(pre + "fc2", p_drop))
 
     def mlp_residual(self, pre, x, M, norm, mlp, save):
         h = self.layernorm(pre + "h", x, norm, M)
-        g = self.linear(pre + "g", h, M, mlp[0].weight, mlp[0].bias, act=self.act, preact=save)
+        g = self.linear(pre + "g", h, M, mlp[0].weight, mlp[0].bias, act=self.act, preact=save,
+                        drop=self.drop(pre + "act", self.p_drop))
         if save:
             g = g[0]
-        return self.linear(pre + "y", g, M, mlp[3].weight, mlp[3].bias, residual=x)
+        return self.linear(pre + "y", g, M, mlp[3].weight, mlp[3].bias, residual=x, drop=self.drop(pre + "fc2", self.p_drop))
 
     def cross_block(self, pre, blk, x_img, x_hm, save):
         B, E, Ti, Th = self.B, self.E, self.T_img, self.T_hm
@@ -360,15 +381,17 @@ class VitPlan:
         q1 = self.linear(pre + "q1", img_q, Mi, a1.in_proj_weight, a1.in_proj_bias, rows=(0, E))
         kv1 = self.linear(pre + "kv1", hm_kv, Mh, a1.in_proj_weight, a1.in_proj_bias, rows=(E, 3 * E))
         o1 = self.attention(pre + "o1", q1.data_ptr(), kv1.data_ptr(), kv1.data_ptr() + 2 * E, Ti, Th, heads, E, 2 * E,
-                            2 * E, save)
-        x_img1 = self.linear(pre + "x_img1", o1, Mi, a1.out_proj.weight, a1.out_proj.bias, residual=x_img)
+                            2 * E, save, drop=self.drop(pre + "attn1", self.p_attn))
+        x_img1 = self.linear(pre + "x_img1", o1, Mi, a1.out_proj.weight, a1.out_proj.bias, residual=x_img,
+                             drop=self.drop(pre + "proj1", self.p_drop))
         hm_q = self.layernorm(pre + "hm_q", x_hm, blk.norm_hm_q, Mh)
         img_kv = self.layernorm(pre + "img_kv", x_img1, blk.norm_img_kv, Mi)
         q2 = self.linear(pre + "q2", hm_q, Mh, a2.in_proj_weight, a2.in_proj_bias, rows=(0, E))
         kv2 = self.linear(pre + "kv2", img_kv, Mi, a2.in_proj_weight, a2.in_proj_bias, rows=(E, 3 * E))
         o2 = self.attention(pre + "o2", q2.data_ptr(), kv2.data_ptr(), kv2.data_ptr() + 2 * E, Th, Ti, heads, E, 2 * E,
-                            2 * E, save)
-        x_hm1 = self.linear(pre + "x_hm1", o2, Mh, a2.out_proj.weight, a2.out_proj.bias, residual=x_hm)
+                            2 * E, save, drop=self.drop(pre + "attn2", self.p_attn))
+        x_hm1 = self.linear(pre + "x_hm1", o2, Mh, a2.out_proj.weight, a2.out_proj.bias, residual=x_hm,
+                            drop=self.drop(pre + "proj2", self.p_drop))
         x_img2 = self.mlp_residual(pre + "mi.", x_img1, Mi, blk.norm_img_mlp, blk.mlp_img, save)
         x_hm2 = self.mlp_residual(pre + "mh.", x_hm1, Mh, blk.norm_hm_mlp, blk.mlp_hm, save)
         return x_img2, x_hm2
@@ -383,10 +406,9 @@ class VitPlan:
                 tuple(kp.shape) != (B, self.J, 2) or c.image_in_channels != 4:
             raise ValueError(f"expected image [{B},3,{self.H},{self.W}], depth [{B},1,{self.H},{self.W}], "
                              f"keypoints [{B},{self.J},2]")
-        if save and self.dropout:
-            raise NotImplementedError(
-                "training-mode dropout is not built yet: construct the config with transformer_dropout_rate=0, "
-                "transformer_attention_dropout_rate=0, regression_dropout=0 (DESIGN.md section 1)")
+        self.training = bool(save)
+        if save:
+            self.step_count += 1
         self.flat.refresh_shadow()
         self.launches = 0
         self.saved = save
@@ -425,17 +447,20 @@ class VitPlan:
         t = self.buf("fin.x0", B * Tf, E)
         self.call("pose_token_concat_bf16", t.data_ptr(), B, Tf, E, self.flat.f32(m.final_cls_token).data_ptr(),
                   x_img.data_ptr(), Ti, x_hm.data_ptr(), Th, self.flat.f32(m.final_pos_embed).data_ptr())
+        d = self.drop("final_pos_drop", self.p_drop)              # final_pos_drop (transformers.py:363)
+        if d is not None:
+            self.call("pose_dropout_bf16", t.data_ptr(), t.numel(), d[0], d[1], t.data_ptr())
         for i, blk in enumerate(m.final_encoder):
             t = self.encoder_block(f"fe{i}.", t, Tf, blk.norm1, blk.attn.in_proj_weight, blk.attn.in_proj_bias,
                                    blk.attn.out_proj.weight, blk.attn.out_proj.bias, blk.norm2, blk.mlp[0], blk.mlp[3],
-                                   c.transformer_heads, save)
+                                   c.transformer_heads, save, self.p_drop, self.p_attn)
         self.fin_out = t
         h = self.layernorm("cls_out", t, m.norm_out, B, rows=1, in_group=Tf, in_off=0)
         lins = m.pose_head.linears()
         for i, lin in enumerate(lins):
             last = i == len(lins) - 1
             h = self.linear(f"head{i}", h, B, lin.weight, lin.bias, act=0 if last else self.act,
-                            preact=save and not last, fp32=last)
+                            preact=save and not last, fp32=last, drop=None if last else self.drop(f"head{i}", self.p_head))
             if save and not last:
                 h = h[0]
         return h
@@ -446,9 +471,18 @@ class VitPlan:
         kb = (m_rows + 63) // 64
         return max(1, min((148 * 2 + tiles - 1) // tiles, kb // 4 if kb >= 4 else 1))
 
-    def linear_bwd(self, dy, ldy, M, x, weight, bias, rows=None, dx_name=None, act_u=None):
+    def drop_grad(self, name, d, site, p):
+        """Gradient entering a dropout site: the forward's mask (same seed) applied to d -> a new buffer."""
+        dd = self.drop(site, p)
+        if dd is None:
+            return d
+        out = self.buf(name, *d.shape)
+        self.call("pose_dropout_bf16", d.data_ptr(), d.numel(), dd[0], dd[1], out.data_ptr())
+        return out
+
+    def linear_bwd(self, dy, ldy, M, x, weight, bias, rows=None, dx_name=None, act_u=None, act_drop=None):
         """Backward of y = x @ W[rows]^T + b[rows] given dy [M, N] (pitch ldy): accumulates dW and db, returns
-        dx = dy @ W (times act'(u) when the layer's INPUT x was act(u)) or None."""
+        dx = dy @ W (times act'(u), and the dropout mask `act_drop`, when the layer's INPUT x was drop(act(u))) or None."""
         w16 = self.flat.w16(weight, rows)
         N, K = w16.shape
         gw = self.flat.g32(weight, rows).view(N, K)
@@ -460,7 +494,7 @@ class VitPlan:
         if dx_name is None:
             return None
         dx = self.buf(dx_name, M, K)
-        e = self._epi(dx, K, act={2: 6, 3: 5}[self.act] if act_u is not None else 0, residual=act_u, ldr=K)
+        e = self._epi(dx, K, act={2: 6, 3: 5}[self.act] if act_u is not None else 0, residual=act_u, ldr=K, drop=act_drop)
         self.call("pose_gemm_bf16_tr", dy.data_ptr(), ldy, 0, w16.data_ptr(), K, 1, M, K, N, 1, C.byref(e))
         return dx
 
@@ -473,35 +507,40 @@ class VitPlan:
                   self.flat.g32(ln.bias).data_ptr())
         return dx
 
-    def attention_bwd(self, name, q, k, v, o, do, dq, dk, dv, Nq, Nk, heads, ldq, ldk, ldv, lddq, lddk, lddv):
+    def attention_bwd(self, name, q, k, v, o, do, dq, dk, dv, Nq, Nk, heads, ldq, ldk, ldv, lddq, lddk, lddv, drop=None):
         E, B = self.E, self.B
         hd = E // heads
         lse = self.bufs[name + ".lse"]
         dws = self.buf(f"attn.D{heads}", B, heads, max(self.T_fin, self.T_img + 1), dtype=torch.float32)
         self.call("pose_attention_bwd_bf16", q, k, v, o.data_ptr(), do.data_ptr(), lse.data_ptr(), dq, dk, dv,
                   dws.data_ptr(), B, heads, Nq, Nk, hd, ldq, ldk, ldv, E, E, lddq, lddk, lddv, Nq * ldq, Nk * ldk,
-                  Nk * ldv, Nq * E, Nq * E, Nq * lddq, Nk * lddk, Nk * lddv, 1.0 / math.sqrt(hd))
+                  Nk * ldv, Nq * E, Nq * E, Nq * lddq, Nk * lddk, Nk * lddv, 1.0 / math.sqrt(hd),
+                  drop[0] if drop else 0.0, drop[1] if drop else 0)
 
-    def encoder_block_bwd(self, pre, dx2, T, norm1, wqkv, bqkv, wo, bo, norm2, fc1, fc2, heads):
+    def encoder_block_bwd(self, pre, dx2, T, norm1, wqkv, bqkv, wo, bo, norm2, fc1, fc2, heads, p_drop=0.0, p_attn=0.0):
         """dx2 = gradient of the block output; returns the gradient of the block input (written in place)."""
         M, E, b = self.B * T, self.E, self.bufs
-        du = self.linear_bwd(dx2, E, M, b[pre + "g"], fc2.weight, fc2.bias, dx_name=f"d.u{M}", act_u=b[pre + "g.u"])
+        dyf = self.drop_grad(f"d.m{M}", dx2, pre + "fc2", p_drop)
+        du = self.linear_bwd(dyf, E, M, b[pre + "g"], fc2.weight, fc2.bias, dx_name=f"d.u{M}", act_u=b[pre + "g.u"],
+                             act_drop=self.drop(pre + "act", p_drop))
         dh2 = self.linear_bwd(du, du.shape[1], M, b[pre + "h2"], fc1.weight, fc1.bias, dx_name=f"d.e{M}")
         dx1 = self.layernorm_bwd(b[pre + "x1"], dh2, norm2, M, dx2, dx2)
-        do = self.linear_bwd(dx1, E, M, b[pre + "o"], wo, bo, dx_name=f"d.e{M}")
+        dya = self.drop_grad(f"d.m{M}", dx1, pre + "proj", p_drop)
+        do = self.linear_bwd(dya, E, M, b[pre + "o"], wo, bo, dx_name=f"d.e{M}")
         qkv = b[pre + "qkv"]
         dqkv = self.buf(f"d.qkv{M}", M, 3 * E)
         p, dp = qkv.data_ptr(), dqkv.data_ptr()
         self.attention_bwd(pre + "o", p, p + 2 * E, p + 4 * E, b[pre + "o"], do, dp, dp + 2 * E, dp + 4 * E, T, T, heads,
-                           3 * E, 3 * E, 3 * E, 3 * E, 3 * E, 3 * E)
+                           3 * E, 3 * E, 3 * E, 3 * E, 3 * E, 3 * E, drop=self.drop(pre + "attn", p_attn))
         dh = self.linear_bwd(dqkv, 3 * E, M, b[pre + "h"], wqkv, bqkv, dx_name=f"d.e{M}")
         x_in = b[self._block_input[pre]]
         return self.layernorm_bwd(x_in, dh, norm1, M, dx1, dx1)
 
     def mlp_residual_bwd(self, pre, dy, M, x_in, norm, mlp):
         b = self.bufs
-        du = self.linear_bwd(dy, self.E, M, b[pre + "g"], mlp[3].weight, mlp[3].bias, dx_name=f"d.u{M}",
-                             act_u=b[pre + "g.u"])
+        dyf = self.drop_grad(f"d.m{M}", dy, pre + "fc2", self.p_drop)
+        du = self.linear_bwd(dyf, self.E, M, b[pre + "g"], mlp[3].weight, mlp[3].bias, dx_name=f"d.u{M}",
+                             act_u=b[pre + "g.u"], act_drop=self.drop(pre + "act", self.p_drop))
         dh = self.linear_bwd(du, du.shape[1], M, b[pre + "h"], mlp[0].weight, mlp[0].bias, dx_name=f"d.e{M}")
         return self.layernorm_bwd(x_in, dh, norm, M, dy, dy)
 
@@ -515,12 +554,13 @@ class VitPlan:
         self.mlp_residual_bwd(pre + "mh.", d_hm, Mh, x_hm1, blk.norm_hm_mlp, blk.mlp_hm)
         self.mlp_residual_bwd(pre + "mi.", d_img, Mi, x_img1, blk.norm_img_mlp, blk.mlp_img)
         # x_hm1 = x_hm + out_proj(attn(q2 = hm_q, kv2 = img_kv))
-        do2 = self.linear_bwd(d_hm, E, Mh, b[pre + "o2"], a2.out_proj.weight, a2.out_proj.bias, dx_name=f"d.e{Mh}")
+        dy2 = self.drop_grad(f"d.m{Mh}", d_hm, pre + "proj2", self.p_drop)
+        do2 = self.linear_bwd(dy2, E, Mh, b[pre + "o2"], a2.out_proj.weight, a2.out_proj.bias, dx_name=f"d.e{Mh}")
         q2, kv2 = b[pre + "q2"], b[pre + "kv2"]
         dq2, dkv2 = self.buf(f"d.q{Mh}", Mh, E), self.buf(f"d.kv{Mi}", Mi, 2 * E)
         self.attention_bwd(pre + "o2", q2.data_ptr(), kv2.data_ptr(), kv2.data_ptr() + 2 * E, b[pre + "o2"], do2,
                            dq2.data_ptr(), dkv2.data_ptr(), dkv2.data_ptr() + 2 * E, Th, Ti, heads, E, 2 * E, 2 * E, E,
-                           2 * E, 2 * E)
+                           2 * E, 2 * E, drop=self.drop(pre + "attn2", self.p_attn))
         dhm_q = self.linear_bwd(dq2, E, Mh, b[pre + "hm_q"], a2.in_proj_weight, a2.in_proj_bias, rows=(0, E),
                                 dx_name=f"d.e{Mh}")
         dimg_kv = self.linear_bwd(dkv2, 2 * E, Mi, b[pre + "img_kv"], a2.in_proj_weight, a2.in_proj_bias,
@@ -528,12 +568,13 @@ class VitPlan:
         self.layernorm_bwd(x_hm, dhm_q, blk.norm_hm_q, Mh, d_hm, d_hm)
         self.layernorm_bwd(x_img1, dimg_kv, blk.norm_img_kv, Mi, d_img, d_img)
         # x_img1 = x_img + out_proj(attn(q1 = img_q, kv1 = hm_kv))
-        do1 = self.linear_bwd(d_img, E, Mi, b[pre + "o1"], a1.out_proj.weight, a1.out_proj.bias, dx_name=f"d.e{Mi}")
+        dy1 = self.drop_grad(f"d.m{Mi}", d_img, pre + "proj1", self.p_drop)
+        do1 = self.linear_bwd(dy1, E, Mi, b[pre + "o1"], a1.out_proj.weight, a1.out_proj.bias, dx_name=f"d.e{Mi}")
         q1, kv1 = b[pre + "q1"], b[pre + "kv1"]
         dq1, dkv1 = self.buf(f"d.q{Mi}", Mi, E), self.buf(f"d.kv{Mh}", Mh, 2 * E)
         self.attention_bwd(pre + "o1", q1.data_ptr(), kv1.data_ptr(), kv1.data_ptr() + 2 * E, b[pre + "o1"], do1,
                            dq1.data_ptr(), dkv1.data_ptr(), dkv1.data_ptr() + 2 * E, Ti, Th, heads, E, 2 * E, 2 * E, E,
-                           2 * E, 2 * E)
+                           2 * E, 2 * E, drop=self.drop(pre + "attn1", self.p_attn))
         dimg_q = self.linear_bwd(dq1, E, Mi, b[pre + "img_q"], a1.in_proj_weight, a1.in_proj_bias, rows=(0, E),
                                  dx_name=f"d.e{Mi}")
         dhm_kv = self.linear_bwd(dkv1, 2 * E, Mh, b[pre + "hm_kv"], a1.in_proj_weight, a1.in_proj_bias,
@@ -572,7 +613,8 @@ class VitPlan:
             lin = lins[i]
             x = b[f"head{i - 1}"] if i > 0 else b["cls_out"]
             u = b[f"head{i - 1}.u"] if i > 0 else None
-            dy = self.linear_bwd(dy, ld, B, x, lin.weight, lin.bias, dx_name=f"d.head{i}", act_u=u)
+            dy = self.linear_bwd(dy, ld, B, x, lin.weight, lin.bias, dx_name=f"d.head{i}", act_u=u,
+                                 act_drop=self.drop(f"head{i - 1}", self.p_head) if i > 0 else None)
             ld = dy.shape[1]
         dt = self.buf("d.fin", B * Tf, E, zero=True)
         self.layernorm_bwd(self.fin_out, dy, m.norm_out, B, None, dt, rows=1, in_group=Tf, in_off=0)
@@ -582,8 +624,11 @@ class VitPlan:
             blk = m.final_encoder[i]
             dt = self.encoder_block_bwd(f"fe{i}.", dt, Tf, blk.norm1, blk.attn.in_proj_weight, blk.attn.in_proj_bias,
                                         blk.attn.out_proj.weight, blk.attn.out_proj.bias, blk.norm2, blk.mlp[0],
-                                        blk.mlp[3], c.transformer_heads)
+                                        blk.mlp[3], c.transformer_heads, self.p_drop, self.p_attn)
             done(blk.norm1.weight)
+        d = self.drop("final_pos_drop", self.p_drop)
+        if d is not None:
+            self.call("pose_dropout_bf16", dt.data_ptr(), dt.numel(), d[0], d[1], dt.data_ptr())
         self.call("pose_batch_rowsum_bf16", dt.data_ptr(), B, Tf, 0, Tf, E, flat.g32(m.final_pos_embed).data_ptr())
         self.call("pose_batch_rowsum_bf16", dt.data_ptr(), B, Tf, 0, 1, E, flat.g32(m.final_cls_token).data_ptr())
         d_img, d_hm = self.buf("d.img", B * Ti, E), self.buf("d.hm", B * Th, E)

@@ -424,9 +424,8 @@ def build_train_model(pose, kind, dev):
     if kind == "cnn":
         cfg = pose.ModelConfig("cnn", image_size=(H, W), heatmap_size=HS)     # reference defaults incl. dropout 0.2
         return pose.CNNPoseEstimation(cfg).to(dev).train(), cfg
-    # dropout rates 0: the ViT dropout kernels are not built yet; everything else is the reference default
-    cfg = pose.ModelConfig("transformer", image_size=(H, W), vit_pretrained=False, transformer_dropout_rate=0.0,
-                           transformer_attention_dropout_rate=0.0, regression_dropout=0.0)
+    # reference defaults (dropout 0.1 / attention dropout 0.1 / head dropout 0.25); random init instead of timm weights
+    cfg = pose.ModelConfig("transformer", image_size=(H, W), vit_pretrained=False)
     return pose.TransformerPoseEstimation(cfg).to(dev).train(), cfg
 
 
@@ -516,8 +515,7 @@ def measure_train(pose, dev, rank, world, kind, steps, warmup, cpu_baseline=True
            "dtype": "bf16 activations / weights on the tensor cores, fp32 accumulate, fp32 master weights + AdamW state",
            "data": "synthetic", "parallelism": f"dp{world}" if world > 1 else "single GPU",
            "optimizer": "fused AdamW lr 1e-3 wd 0.01 (main.py:154-156), accumulation_steps 1"}
-    if kind == "vit":
-        out["note"] = "dropout rates 0 (ViT dropout kernels not built yet); CNN runs the reference defaults (head dropout 0.2)"
+    out["note"] = "reference default configuration incl. dropout (CNN head 0.2; ViT 0.1 / attention 0.1 / head 0.25)"
     if rank == 0 and cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_train_baseline(pose, kind, cfg)
     del tr, model, plan, d, bufs

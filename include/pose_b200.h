@@ -140,6 +140,12 @@ typedef struct pose_gemm_epilogue {
     void *preact;       /* [M, ldc] bf16 or NULL: acc + bias BEFORE the activation, saved for the backward pass */
     int32_t accumulate; /* 1: fp32 C += acc * out_scale (atomic adds; split-K weight gradients accumulate into .grad) */
     int32_t reserved;
+    /* nn.Dropout fused after the activation and before the residual add: element (row, col) is kept iff
+     * hash(drop_seed, row * ldc + col) >= drop_p * 2^32 and scaled by 1 / (1 - drop_p); with act 5..7 the same mask gates
+     * the gradient.  pose_dropout_bf16 over the compact [M, ldc] tensor with the same seed reproduces the mask. */
+    uint64_t drop_seed;
+    float drop_p;
+    int32_t reserved2;
 } pose_gemm_epilogue;
 
 int pose_gemm_bf16_ex(const void *A, int lda, const void *W, int ldw, int M, int N, int K,
@@ -220,8 +226,8 @@ int pose_sums_to_bf16(const float *sums, int parts, int B, int C, float scale, v
  *                         flattened-conv-weight column order: Conv2d(kernel = stride = P) becomes one GEMM
  *  pose_attention_bf16    softmax(Q K^T * scale) V per (batch, head); Q/K/V/O rows with pitches ld* and batch
  *                         strides bs* (elements), head h in columns [h*head_dim, (h+1)*head_dim); head_dim 48 | 64,
- *                         Nk <= 288 (whole score row in shared memory).  nn.MultiheadAttention (transformers.py:61-63,
- *                         :98-106) and timm Attention.
+ *                         Nk <= 288 (the whole score row lives in TMEM; tcgen05 kernels in csrc/attention_tc.cu).
+ *                         nn.MultiheadAttention (transformers.py:61-63, :98-106) and timm Attention.
  * ------------------------------------------------------------------------------------------- */
 int pose_layernorm_bf16(const void *X, const float *gamma, const float *beta, float eps, long M, int rows, long in_group,
                         long in_off, long out_group, long out_off, int D, void *Y, pose_stream_t stream);
@@ -232,6 +238,7 @@ int pose_patchify_bf16(const float *src0, int C0, const float *src1, int C1, int
 int pose_attention_bf16(const void *Q, const void *K, const void *V, void *O, int B, int heads, int Nq, int Nk, int head_dim,
                         long ldq, long ldk, long ldv, long ldo, long bsq, long bsk, long bsv, long bso, float scale,
                         float *lse /* [B, heads, Nq] fp32 or NULL: log-sum-exp of the scaled scores, saved for backward */,
+                        float drop_p, uint64_t drop_seed /* attention-weight dropout (MultiheadAttention(dropout=p)); 0 = off */,
                         pose_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -256,7 +263,7 @@ int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V, const v
                             void *dQ, void *dK, void *dV, float *Dws, int B, int heads, int Nq, int Nk, int head_dim,
                             long ldq, long ldk, long ldv, long ldo, long lddo, long lddq, long lddk, long lddv, long bsq,
                             long bsk, long bsv, long bso, long bsdo, long bsdq, long bsdk, long bsdv, float scale,
-                            pose_stream_t stream);
+                            float drop_p, uint64_t drop_seed, pose_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * G. optimizer step                       reference: torch.optim.AdamW(lr 1e-3, weight_decay 0.01), main.py:154-156,

@@ -77,7 +77,7 @@ def test_attention_forward_backward(pose, hd, heads, Nq, Nk):
     scale = 1.0 / math.sqrt(hd)
     k_ptr, v_ptr = kv.data_ptr(), kv.data_ptr() + 2 * E
     check(lib.pose_attention_bf16(q.data_ptr(), k_ptr, v_ptr, o.data_ptr(), B, heads, Nq, Nk, hd, E, 2 * E, 2 * E, E,
-                                  Nq * E, Nk * 2 * E, Nk * 2 * E, Nq * E, scale, lse.data_ptr(), sp()), "attn")
+                                  Nq * E, Nk * 2 * E, Nk * 2 * E, Nq * E, scale, lse.data_ptr(), 0.0, 0, sp()), "attn")
     qr = q.float().requires_grad_()
     kvr = kv.float().requires_grad_()
     qh = qr.view(B, Nq, heads, hd).transpose(1, 2)
@@ -94,10 +94,74 @@ def test_attention_forward_backward(pose, hd, heads, Nq, Nk):
     check(lib.pose_attention_bwd_bf16(q.data_ptr(), k_ptr, v_ptr, o.data_ptr(), do.data_ptr(), lse.data_ptr(),
                                       dq.data_ptr(), dkv.data_ptr(), dkv.data_ptr() + 2 * E, dws.data_ptr(), B, heads, Nq,
                                       Nk, hd, E, 2 * E, 2 * E, E, E, E, 2 * E, 2 * E, Nq * E, Nk * 2 * E, Nk * 2 * E,
-                                      Nq * E, Nq * E, Nq * E, Nk * 2 * E, Nk * 2 * E, scale, sp()), "attn_bwd")
+                                      Nq * E, Nq * E, Nq * E, Nk * 2 * E, Nk * 2 * E, scale, 0.0, 0, sp()), "attn_bwd")
     tol = dict(rtol=3e-2, atol=3e-2)
     assert torch.allclose(dq.float(), qr.grad, **tol), (dq.float() - qr.grad).abs().max().item()
     assert torch.allclose(dkv.float(), kvr.grad, **tol), (dkv.float() - kvr.grad).abs().max().item()
+
+
+@pytest.mark.parametrize("hd,heads,Nq,Nk", [(48, 16, 273, 273), (64, 12, 257, 257), (48, 16, 16, 256)])
+def test_attention_weight_dropout_forward_backward(pose, hd, heads, Nq, Nk):
+    """nn.MultiheadAttention(dropout=p): the mask is a counter-based hash of (seed, element); pose_dropout_bf16 over a
+    tensor of ones with the same seed exposes it, so the fused kernels can be checked against plain PyTorch."""
+    lib, sp, check = _lib(pose)
+    B, E, p, seed = 2, hd * heads, 0.1, 1234567
+    g = torch.Generator().manual_seed(Nq + Nk)
+    q = torch.randn(B, Nq, E, generator=g).to(DEV).bfloat16()
+    kv = torch.randn(B, Nk, 2 * E, generator=g).to(DEV).bfloat16()
+    do = torch.randn(B, Nq, E, generator=g).to(DEV).bfloat16()
+    ones = torch.ones(B, heads, Nq, Nk, device=DEV, dtype=torch.bfloat16)
+    mask = torch.empty_like(ones)
+    check(lib.pose_dropout_bf16(ones.data_ptr(), ones.numel(), p, seed, mask.data_ptr(), sp()), "dropout")
+    keep = (mask != 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 0.01 and abs(mask.float().max().item() - 1 / (1 - p)) < 0.01
+    o = torch.empty(B, Nq, E, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B, heads, Nq, device=DEV)
+    scale = 1.0 / math.sqrt(hd)
+    k_ptr, v_ptr = kv.data_ptr(), kv.data_ptr() + 2 * E
+    check(lib.pose_attention_bf16(q.data_ptr(), k_ptr, v_ptr, o.data_ptr(), B, heads, Nq, Nk, hd, E, 2 * E, 2 * E, E,
+                                  Nq * E, Nk * 2 * E, Nk * 2 * E, Nq * E, scale, lse.data_ptr(), p, seed, sp()), "attn")
+    qr, kvr = q.float().requires_grad_(), kv.float().requires_grad_()
+    qh = qr.view(B, Nq, heads, hd).transpose(1, 2)
+    kh = kvr[..., :E].reshape(B, Nk, heads, hd).transpose(1, 2)
+    vh = kvr[..., E:].reshape(B, Nk, heads, hd).transpose(1, 2)
+    pr = torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1) * mask.float()
+    orf = (pr @ vh).transpose(1, 2).reshape(B, Nq, E)
+    assert torch.allclose(o.float(), orf, rtol=2e-2, atol=2e-2), (o.float() - orf).abs().max().item()
+    orf.backward(do.float())
+    dq, dkv, dws = torch.empty_like(q), torch.empty_like(kv), torch.empty(B, heads, Nq, device=DEV)
+    check(lib.pose_attention_bwd_bf16(q.data_ptr(), k_ptr, v_ptr, o.data_ptr(), do.data_ptr(), lse.data_ptr(),
+                                      dq.data_ptr(), dkv.data_ptr(), dkv.data_ptr() + 2 * E, dws.data_ptr(), B, heads, Nq,
+                                      Nk, hd, E, 2 * E, 2 * E, E, E, E, 2 * E, 2 * E, Nq * E, Nk * 2 * E, Nk * 2 * E,
+                                      Nq * E, Nq * E, Nq * E, Nk * 2 * E, Nk * 2 * E, scale, p, seed, sp()), "attn_bwd")
+    tol = dict(rtol=3e-2, atol=3e-2)
+    assert torch.allclose(dq.float(), qr.grad, **tol), (dq.float() - qr.grad).abs().max().item()
+    assert torch.allclose(dkv.float(), kvr.grad, **tol), (dkv.float() - kvr.grad).abs().max().item()
+
+
+def test_gemm_epilogue_dropout_matches_the_elementwise_mask(pose):
+    import ctypes as C
+    lib, sp, check = _lib(pose)
+    g = torch.Generator().manual_seed(5)
+    M, K, N, p, seed = 300, 256, 768, 0.25, 99
+    a = torch.randn(M, K, generator=g).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).bfloat16()
+    res = torch.randn(M, N, generator=g).to(DEV).bfloat16()
+
+    def run(drop_p):
+        out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+        e = pose._lib.PoseGemmEpilogue()
+        e.C, e.ldc, e.act, e.out_dtype, e.out_scale = out.data_ptr(), N, 3, 0, 1.0
+        e.residual, e.ldr, e.res_scale = res.data_ptr(), N, 1.0
+        e.drop_p, e.drop_seed = drop_p, seed
+        check(lib.pose_gemm_bf16_ex(a.data_ptr(), K, w.data_ptr(), K, M, N, K, C.byref(e), sp()), "gemm")
+        return out
+    plain, dropped = run(0.0), run(p)
+    ones = torch.ones(M, N, device=DEV, dtype=torch.bfloat16)
+    mask = torch.empty_like(ones)
+    check(lib.pose_dropout_bf16(ones.data_ptr(), ones.numel(), p, seed, mask.data_ptr(), sp()), "dropout")
+    want = (plain - res.float()) * (mask != 0).float() / (1 - p) + res.float()       # x + drop(gelu(a w^T))
+    assert torch.allclose(dropped, want, rtol=1e-4, atol=1e-4)
 
 
 def test_sums_slices_and_padded_cast(pose):
@@ -218,6 +282,29 @@ def test_training_step_gradients_match_fp32_autograd(pose, golden):
     worst.sort(reverse=True)
     assert worst[0][0] < 0.08, worst[:8]        # bf16 activations / weights end to end vs fp32
     assert sum(r for r, _ in worst) / len(worst) < 0.04, worst[:8]
+
+
+def test_training_with_the_reference_dropout_rates(pose, golden):
+    """Default config (transformer dropout 0.1, attention dropout 0.1, head dropout 0.25): the step runs, eval ignores
+    dropout, training forwards differ from step to step (fresh masks) and the loss goes down."""
+    gd, img, dep, kp = _inputs(golden)
+    m, sd, tm = _model(pose)
+    gt = torch.from_numpy(gd["gt"]).to(DEV)
+    m.eval()
+    with torch.no_grad():
+        e1, e2 = m(img, dep, kp), m(img, dep, kp)
+    assert torch.equal(e1, e2)
+    m.train()
+    train = __import__("importlib").import_module("3dhumanposeestimation_b200.train")
+    tr = train.Trainer(m, pose.ComprehensivePoseLoss(), lr=1e-4)
+    plan = m.plan(2, img.device)
+    a = plan.forward(img, dep, kp, save=True).clone()
+    b = plan.forward(img, dep, kp, save=True).clone()
+    assert not torch.equal(a, b) and torch.isfinite(a).all()
+    losses = [tr.step(img, dep, kp, gt)[4].item() for _ in range(6)]
+    assert all(np.isfinite(losses)) and min(losses[3:]) < losses[0], losses
+    for p_ in m.parameters():
+        assert torch.isfinite(p_).all()
 
 
 def test_fused_optimizer_step_changes_the_next_forward(pose, golden):
