@@ -7,12 +7,13 @@ train = importlib.import_module("3dhumanposeestimation_b200.train")
 ap = argparse.ArgumentParser()
 ap.add_argument("--model", default="vit"); ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--steps", type=int, default=5); ap.add_argument("--profile", action="store_true")
+ap.add_argument("--warmup", type=int, default=3); ap.add_argument("--dropout0", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda")
 torch.manual_seed(0)
 if a.model == "vit":
-    cfg = pose.ModelConfig("transformer", image_size=(256, 256), vit_pretrained=False, transformer_dropout_rate=0.0,
-                           transformer_attention_dropout_rate=0.0, regression_dropout=0.0)
+    kw = dict(transformer_dropout_rate=0.0, transformer_attention_dropout_rate=0.0, regression_dropout=0.0) if a.dropout0 else {}
+    cfg = pose.ModelConfig("transformer", image_size=(256, 256), vit_pretrained=False, **kw)
     model = pose.TransformerPoseEstimation(cfg).to(dev).train()
 else:
     cfg = pose.ModelConfig("cnn", image_size=(256, 256), heatmap_size=256)
@@ -22,7 +23,7 @@ img, dep = torch.rand(B, 3, 256, 256, device=dev), torch.rand(B, 1, 256, 256, de
 kp = torch.rand(B, 17, 2, device=dev) * 0.9 + 0.05
 gt = torch.randn(B, 17, 3, device=dev) * 300
 tr = train.Trainer(model, pose.ComprehensivePoseLoss(), lr=1e-4)
-for _ in range(3):
+for _ in range(a.warmup):
     o5 = tr.step(img, dep, kp, gt)
 torch.cuda.synchronize()
 print("loss", o5.tolist())
