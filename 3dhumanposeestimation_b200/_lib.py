@@ -10,7 +10,7 @@ import os
 import torch  # noqa: F401  (loads the CUDA runtime the library links against)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpose_b200.so")
+LIB_PATH = os.environ.get("POSE_B200_LIB") or os.path.join(_HERE, "libpose_b200.so")   # override: A/B measurements only
 
 c_int, c_float, c_size_t, c_void_p = C.c_int, C.c_float, C.c_size_t, C.c_void_p
 

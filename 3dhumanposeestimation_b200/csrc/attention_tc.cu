@@ -48,24 +48,39 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 
 struct AttnSync {
-    uint64_t *bar;
-    uint32_t phase;
+    uint64_t *bar;       // [0]: MMA completion (tcgen05.commit), [1]: TMA operand loads (complete_tx)
+    uint32_t phase, lphase;
     __device__ __forceinline__ void commit_and_wait() {     // thread 0 commits the MMAs issued so far; everybody waits
         if (threadIdx.x == 0) tc_commit(bar);
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
     }
+    __device__ __forceinline__ void wait_loads() {
+        mbar_wait(bar + 1, lphase);
+        lphase ^= 1;
+    }
 };
+
+// Operand staging by TMA: every operand is a [B, T, cols] bf16 tensor (pitch ld, batch stride bs); one box = 64 columns
+// (one head slice, 128 B: the SWIZZLE_128B row) x 32 tokens.  Rows past T and columns past `cols` are zero filled.
+// Called by ONE thread; the bytes land on bar[1].
+constexpr int kBoxRows = 32;
+__device__ __forceinline__ void tma_rows(unsigned char *smem, const CUtensorMap *map, uint64_t *lbar, int col0, int row0, int b,
+                                         int rows_padded) {
+    for (int r = 0; r < rows_padded; r += kBoxRows) tma_load_3d(smem + r * 128, map, lbar, col0, row0 + r, b);
+}
+__device__ __forceinline__ int box_bytes(int rows) { return (rows + kBoxRows - 1) / kBoxRows * kBoxRows * 128; }
 
 __device__ __forceinline__ uint32_t attn_prologue(unsigned char *&smem, uint64_t *&bar) {
     extern __shared__ unsigned char smem_dyn[];
     smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t s_bar;
+    __shared__ uint64_t s_bar[2];
     __shared__ uint32_t s_tmem;
-    bar = &s_bar;
+    bar = s_bar;
     if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) {
@@ -89,31 +104,32 @@ __device__ __forceinline__ void attn_epilogue(uint32_t tmem_base) {
 // ---------------------------------------------------------------------------------------------------------
 template <int HD>
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attn_fwd_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K, const __nv_bfloat16 *__restrict__ V,
-                   __nv_bfloat16 *__restrict__ O, float *__restrict__ lse, int Nq, int Nk, int Nkp, long ldq, long ldk, long ldv,
-                   long ldo, long bsq, long bsk, long bsv, long bso, float scale, uint32_t drop_thresh, float drop_scale,
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                   const __grid_constant__ CUtensorMap mapV, __nv_bfloat16 *__restrict__ O, float *__restrict__ lse, int Nq, int Nk,
+                   int Nkp, long ldo, long bso, float scale, uint32_t drop_thresh, float drop_scale,
                    unsigned long long drop_seed) {
     unsigned char *smem;
     uint64_t *bar;
     const uint32_t tmem = attn_prologue(smem, bar);
-    AttnSync sync{bar, 0};
+    AttnSync sync{bar, 0, 0};
     unsigned char *Qs = smem, *Ks = Qs + 16384, *Vs = Ks + 288 * 128, *Ps = Vs + 288 * 128;   // P: 5 blocks of 16 KB
     const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
     const int warp = threadIdx.x >> 5;
-    const __nv_bfloat16 *qg = Q + b * bsq + (long)h * HD, *kg = K + b * bsk + (long)h * HD, *vg = V + b * bsv + (long)h * HD;
     __nv_bfloat16 *og = O + b * bso + (long)h * HD;
-    load_rows_sw128<HD>(Ks, kg, ldk, Nk, Nkp);
-    load_rows_sw128<HD>(Vs, vg, ldv, Nk, Nkp);
     const float sl2 = scale * kLog2e;
     const uint32_t tO = tmem + 320;
     const int nch = (Nkp + 31) / 32;
     for (int q0 = 0; q0 < Nq; q0 += 128) {
-        const int rows = min(128, Nq - q0);
-        load_rows_sw128<HD>(Qs, qg + (long)q0 * ldq, ldq, rows, 128);
-        fence_async_smem();
-        __syncthreads();
         if (threadIdx.x == 0) {
-            tc_fence_after();
+            mbar_expect_tx(bar + 1, 4 * kBoxRows * 128 + (q0 == 0 ? 2 * box_bytes(Nkp) : 0));
+            if (q0 == 0) {
+                tma_rows(Ks, &mapK, bar + 1, h * HD, 0, b, Nkp);
+                tma_rows(Vs, &mapV, bar + 1, h * HD, 0, b, Nkp);
+            }
+            tma_rows(Qs, &mapQ, bar + 1, h * HD, q0, b, 128);
+        }
+        sync.wait_loads();
+        if (threadIdx.x == 0) {
             const uint64_t da = umma_desc_k<128>(smem_u32(Qs));
             for (int kc0 = 0; kc0 < Nkp; kc0 += 256) {
                 const int n = min(256, Nkp - kc0);
@@ -204,30 +220,34 @@ attn_fwd_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__r
 // dQ (and D = rowsum(dO * O)) per (sample, head)
 template <int HD>
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attn_bwd_dq_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K, const __nv_bfloat16 *__restrict__ V,
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
                       const __nv_bfloat16 *__restrict__ O, const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ lse,
-                      __nv_bfloat16 *__restrict__ dQ, float *__restrict__ Dout, int Nq, int Nk, int Nkp, long ldq, long ldk,
-                      long ldv, long ldo, long lddo, long lddq, long bsq, long bsk, long bsv, long bso, long bsdo, long bsdq,
-                      float scale, uint32_t drop_thresh, float drop_scale, unsigned long long drop_seed) {
+                      __nv_bfloat16 *__restrict__ dQ, float *__restrict__ Dout, int Nq, int Nk, int Nkp, long ldo, long lddo,
+                      long lddq, long bso, long bsdo, long bsdq, float scale, uint32_t drop_thresh, float drop_scale,
+                      unsigned long long drop_seed) {
     unsigned char *smem;
     uint64_t *bar;
     const uint32_t tmem = attn_prologue(smem, bar);
-    AttnSync sync{bar, 0};
+    AttnSync sync{bar, 0, 0};
     unsigned char *Qs = smem, *dOs = Qs + 16384, *Ks = dOs + 16384, *Vs = Ks + 288 * 128, *dSs = Vs + 288 * 128;  // dS: 2 blocks
     const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
     const int warp = threadIdx.x >> 5, r = threadIdx.x;
-    const __nv_bfloat16 *qg = Q + b * bsq + (long)h * HD, *kg = K + b * bsk + (long)h * HD, *vg = V + b * bsv + (long)h * HD;
     const __nv_bfloat16 *og = O + b * bso + (long)h * HD, *dog = dO + b * bsdo + (long)h * HD;
     __nv_bfloat16 *dqg = dQ + b * bsdq + (long)h * HD;
-    load_rows_sw128<HD>(Ks, kg, ldk, Nk, Nkp);
-    load_rows_sw128<HD>(Vs, vg, ldv, Nk, Nkp);
     const float sl2 = scale * kLog2e;
     const uint32_t tS = tmem, tP = tmem + 128, tQ = tmem + 256;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     for (int q0 = 0; q0 < Nq; q0 += 128) {
-        const int rows = min(128, Nq - q0);
-        load_rows_sw128<HD>(Qs, qg + (long)q0 * ldq, ldq, rows, 128);
-        load_rows_sw128<HD>(dOs, dog + (long)q0 * lddo, lddo, rows, 128);
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar + 1, 2 * 4 * kBoxRows * 128 + (q0 == 0 ? 2 * box_bytes(Nkp) : 0));
+            if (q0 == 0) {
+                tma_rows(Ks, &mapK, bar + 1, h * HD, 0, b, Nkp);
+                tma_rows(Vs, &mapV, bar + 1, h * HD, 0, b, Nkp);
+            }
+            tma_rows(Qs, &mapQ, bar + 1, h * HD, q0, b, 128);
+            tma_rows(dOs, &mapdO, bar + 1, h * HD, q0, b, 128);
+        }
         // D = rowsum(dO * O), log-sum-exp (in exp2 units) of this thread's row
         float Dr = 0.f, l2 = 0.f;
         const bool row_ok = q0 + r < Nq;
@@ -247,6 +267,7 @@ attn_bwd_dq_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *
             Dout[idx] = Dr;
             l2 = lse[idx] * kLog2e;
         }
+        sync.wait_loads();
         for (int kc0 = 0; kc0 < Nkp; kc0 += 128) {
             const int n = min(128, Nkp - kc0);
             fence_async_smem();
@@ -330,24 +351,19 @@ attn_bwd_dq_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *
 // dK, dV per (128-key tile, head, sample)
 template <int HD>
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attn_bwd_dkv_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 *__restrict__ K, const __nv_bfloat16 *__restrict__ V,
-                       const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ lse, const float *__restrict__ Dg,
-                       __nv_bfloat16 *__restrict__ dK, __nv_bfloat16 *__restrict__ dV, int Nq, int Nk, long ldq, long ldk, long ldv,
-                       long lddo, long lddk, long lddv, long bsq, long bsk, long bsv, long bsdo, long bsdk, long bsdv, float scale,
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
+                       const float *__restrict__ lse, const float *__restrict__ Dg, __nv_bfloat16 *__restrict__ dK,
+                       __nv_bfloat16 *__restrict__ dV, int Nq, int Nk, long lddk, long lddv, long bsdk, long bsdv, float scale,
                        uint32_t drop_thresh, float drop_scale, unsigned long long drop_seed) {
     unsigned char *smem;
     uint64_t *bar;
     const uint32_t tmem = attn_prologue(smem, bar);
-    AttnSync sync{bar, 0};
+    AttnSync sync{bar, 0, 0};
     unsigned char *Kt = smem, *Vt = Kt + 16384, *Qs = Vt + 16384, *dOs = Qs + 16384, *PT = dOs + 16384, *dST = PT + 32768;
     __shared__ float lse_s[128], D_s[128];
     const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z, heads = gridDim.y;
     const int warp = threadIdx.x >> 5, r = threadIdx.x;
-    const __nv_bfloat16 *qg = Q + b * bsq + (long)h * HD, *kg = K + b * bsk + (long)h * HD, *vg = V + b * bsv + (long)h * HD;
-    const __nv_bfloat16 *dog = dO + b * bsdo + (long)h * HD;
-    const int krows = min(128, Nk - k0);
-    load_rows_sw128<HD>(Kt, kg + (long)k0 * ldk, ldk, krows, 128);
-    load_rows_sw128<HD>(Vt, vg + (long)k0 * ldv, ldv, krows, 128);
     const float sl2 = scale * kLog2e;
     const uint32_t tS = tmem, tP = tmem + 128, tV = tmem + 256, tK = tmem + 320;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
@@ -355,15 +371,22 @@ attn_bwd_dkv_tc_kernel(const __nv_bfloat16 *__restrict__ Q, const __nv_bfloat16 
     for (int q0 = 0; q0 < Nq; q0 += 128) {
         const int rows = min(128, Nq - q0);
         const int np = (rows + 15) / 16 * 16;            // query columns of this tile, padded to the UMMA N / K granularity
-        load_rows_sw128<HD>(Qs, qg + (long)q0 * ldq, ldq, rows, 128);
-        load_rows_sw128<HD>(dOs, dog + (long)q0 * lddo, lddo, rows, 128);
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar + 1, (q0 == 0 ? 4 : 2) * 4 * kBoxRows * 128);
+            if (q0 == 0) {
+                tma_rows(Kt, &mapK, bar + 1, h * HD, k0, b, 128);
+                tma_rows(Vt, &mapV, bar + 1, h * HD, k0, b, 128);
+            }
+            tma_rows(Qs, &mapQ, bar + 1, h * HD, q0, b, 128);
+            tma_rows(dOs, &mapdO, bar + 1, h * HD, q0, b, 128);
+        }
         {
             const bool ok = q0 + r < Nq;
             const long idx = ((long)b * heads + h) * Nq + q0 + r;
             lse_s[r] = ok ? lse[idx] * kLog2e : 0.f;
             D_s[r] = ok ? Dg[idx] : 0.f;
         }
-        fence_async_smem();
+        sync.wait_loads();
         tc_fence_before();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -454,6 +477,20 @@ constexpr int kFwdSmem = 16384 + 2 * 288 * 128 + 5 * 16384 + 1024;
 constexpr int kDqSmem = 2 * 16384 + 2 * 288 * 128 + 2 * 16384 + 1024;
 constexpr int kDkvSmem = 4 * 16384 + 2 * 32768 + 1024;
 
+// [B, T, cols] bf16 operand (pitch ld, batch stride bs, in elements); box = 64 columns x kBoxRows tokens, 128-byte swizzle
+static int make_map_tokens(CUtensorMap *map, const void *ptr, int cols, int T, int B, long ld, long bs) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return POSE_E_UNSUPPORTED;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bs * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)kBoxRows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? POSE_OK : POSE_E_SHAPE;
+}
+
 template <class Kern>
 static int set_smem(Kern kern, int bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -479,12 +516,17 @@ POSE_API int pose_attention_bf16(const void *Q, const void *K, const void *V, vo
     const int Nkp = (Nk + 15) / 16 * 16;
     const dim3 grid(heads, B);
     cudaStream_t s = (cudaStream_t)stream;
+    const int cols = heads * head_dim;
+    if (ldq < cols || ldk < cols || ldv < cols || ldo < cols) return POSE_E_SHAPE;
+    CUtensorMap mq, mk, mv;
     int e;
+    if ((e = make_map_tokens(&mq, Q, cols, Nq, B, ldq, bsq))) return e;
+    if ((e = make_map_tokens(&mk, K, cols, Nk, B, ldk, bsk))) return e;
+    if ((e = make_map_tokens(&mv, V, cols, Nk, B, ldv, bsv))) return e;
 #define FWD(HD_)                                                                                                       \
     if ((e = set_smem(attn_fwd_tc_kernel<HD_>, kFwdSmem))) return e;                                                    \
-    attn_fwd_tc_kernel<HD_><<<grid, kAttnThreads, kFwdSmem, s>>>((const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K,     \
-                                                                (const __nv_bfloat16 *)V, (__nv_bfloat16 *)O, lse, Nq, Nk, Nkp, \
-                                                                ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale, dth, dsc, drop_seed)
+    attn_fwd_tc_kernel<HD_><<<grid, kAttnThreads, kFwdSmem, s>>>(mq, mk, mv, (__nv_bfloat16 *)O, lse, Nq, Nk, Nkp, ldo, bso, \
+                                                                scale, dth, dsc, drop_seed)
     if (head_dim == 64) { FWD(64); } else { FWD(48); }
 #undef FWD
     return launch_status();
@@ -511,18 +553,24 @@ POSE_API int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V
     const int Nkp = (Nk + 15) / 16 * 16;
     cudaStream_t s = (cudaStream_t)stream;
     const dim3 g1(heads, B), g2((Nk + 127) / 128, heads, B);
+    const int cols = heads * head_dim;
+    if (ldq < cols || ldk < cols || ldv < cols || ldo < cols || lddo < cols) return POSE_E_SHAPE;
+    CUtensorMap mq, mk, mv, md;
     int e;
+    if ((e = make_map_tokens(&mq, Q, cols, Nq, B, ldq, bsq))) return e;
+    if ((e = make_map_tokens(&mk, K, cols, Nk, B, ldk, bsk))) return e;
+    if ((e = make_map_tokens(&mv, V, cols, Nk, B, ldv, bsv))) return e;
+    if ((e = make_map_tokens(&md, dO, cols, Nq, B, lddo, bsdo))) return e;
 #define BWD(HD_)                                                                                                       \
     if ((e = set_smem(attn_bwd_dq_tc_kernel<HD_>, kDqSmem))) return e;                                                  \
     if ((e = set_smem(attn_bwd_dkv_tc_kernel<HD_>, kDkvSmem))) return e;                                                \
-    attn_bwd_dq_tc_kernel<HD_><<<g1, kAttnThreads, kDqSmem, s>>>(                                                       \
-        (const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V, (const __nv_bfloat16 *)O,        \
-        (const __nv_bfloat16 *)dO, lse, (__nv_bfloat16 *)dQ, Dws, Nq, Nk, Nkp, ldq, ldk, ldv, ldo, lddo, lddq, bsq, bsk,  \
-        bsv, bso, bsdo, bsdq, scale, dth, dsc, drop_seed);                                                             \
-    attn_bwd_dkv_tc_kernel<HD_><<<g2, kAttnThreads, kDkvSmem, s>>>(                                                     \
-        (const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V, (const __nv_bfloat16 *)dO, lse,  \
-        Dws, (__nv_bfloat16 *)dK, (__nv_bfloat16 *)dV, Nq, Nk, ldq, ldk, ldv, lddo, lddk, lddv, bsq, bsk, bsv, bsdo,    \
-        bsdk, bsdv, scale, dth, dsc, drop_seed)
+    attn_bwd_dq_tc_kernel<HD_><<<g1, kAttnThreads, kDqSmem, s>>>(mq, mk, mv, md, (const __nv_bfloat16 *)O,              \
+                                                                (const __nv_bfloat16 *)dO, lse, (__nv_bfloat16 *)dQ, Dws, Nq, \
+                                                                Nk, Nkp, ldo, lddo, lddq, bso, bsdo, bsdq, scale, dth, dsc, \
+                                                                drop_seed);                                           \
+    attn_bwd_dkv_tc_kernel<HD_><<<g2, kAttnThreads, kDkvSmem, s>>>(mq, mk, mv, md, lse, Dws, (__nv_bfloat16 *)dK,        \
+                                                                  (__nv_bfloat16 *)dV, Nq, Nk, lddk, lddv, bsdk, bsdv, scale, \
+                                                                  dth, dsc, drop_seed)
     if (head_dim == 64) { BWD(64); } else { BWD(48); }
 #undef BWD
     return launch_status();

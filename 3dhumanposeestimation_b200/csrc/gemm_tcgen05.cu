@@ -24,7 +24,7 @@
 // strided convolutions of src/models/cnn.py:122-131 never materialise an im2col matrix.
 // All mbarrier waits are bounded (trap instead of hanging the GPU if a descriptor is wrong).
 #include <cuda.h>
-#include <mutex>
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace pose {
@@ -53,6 +53,7 @@ struct Epilogue {
     float out_scale, res_scale;      // C = act(acc + bias) * out_scale + residual * res_scale
     __nv_bfloat16 *preact;           // [M, ldc] bf16 or null: acc + bias before the activation (saved for backward)
     int accumulate;                  // fp32 C += acc * out_scale with red.global (split-K weight gradients)
+    int tma;                         // bf16 output tiles leave through TMA stores (row-per-lane epilogue, no transpose)
     uint32_t drop_thresh;            // dropout after the activation (before the residual): keep iff hash >= thresh
     float drop_scale;                // 1 / (1 - p)
     unsigned long long drop_seed;    // element index = row * ldc + col (common.cuh: drop_keep)
@@ -71,9 +72,11 @@ template <int BN, int kStages, int BKC>
 struct GemmSmem {
     static constexpr int kABytes = BM * BKC * 2, kBBytes = BN * BKC * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarrierBytes = 256;
+    static constexpr int kBarrierBytes = 1024;                   // keeps the staging buffers 1024 B aligned (TMA swizzle)
     static constexpr int kStagePitch = 144;                      // 32 fp32 + 16 B pad: conflict-free 16 B accesses
-    static constexpr int kStagingBytes = 16 * 32 * kStagePitch;  // one 32 x 32 fp32 transpose buffer per epilogue warp
+    static constexpr int kWarpStaging = 5120;                    // per epilogue warp: 32 x 32 fp32 transpose buffer (4608 B), or
+                                                                 // two 32 x 32 bf16 TMA tiles (output at +0, auxiliary at +2048)
+    static constexpr int kStagingBytes = 16 * kWarpStaging;
     static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + kStagingBytes + 1024;  // + alignment slack
     static_assert(kStageBytes % 1024 == 0, "stage bases must stay 1024 B aligned");
 };
@@ -105,18 +108,64 @@ __device__ __forceinline__ float tanh_approx(float x) {
     return y;
 }
 
+// erf(|x|) and exp(-x^2) in one go, branch-free (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7: two MUFU ops -- rcp and
+// ex2 -- and six FMAs instead of the two-range libdevice erff; the exact-GELU epilogues were instruction bound on it).
+// The same exponential is the Gaussian density of gelu'.
+__device__ __forceinline__ float erf_abs_exp(float ax, float &e) {
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+    e = __expf(-ax * ax);
+    const float p = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
+    return fmaf(-p, e, 1.0f);
+}
+__device__ __forceinline__ float gelu_erf(float v) {     // nn.GELU() (exact, erf form)
+    float e;
+    const float x = v * 0.70710678118654752f;
+    const float er = copysignf(erf_abs_exp(fabsf(x), e), x);
+    return 0.5f * v * (1.0f + er);
+}
+
 template <int ACT>
 __device__ __forceinline__ float fast_act(float v) {
     if (ACT == 1) return fmaxf(v, 0.f);
     if (ACT == 2) return 0.5f * v * (1.0f + tanh_approx(0.5f * v));   // silu(x) = x * sigmoid(x), one MUFU
-    if (ACT == 3) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    if (ACT == 3) return gelu_erf(v);
     if (ACT == 4) return 0.5f * (1.0f + tanh_approx(0.5f * v));       // sigmoid
     return v;
 }
-// derivative of the activation at the saved pre-activation u (ACT 5 = gelu', 6 = silu', 7 = relu')
+// activation and its derivative in one evaluation (the forward pass of a training step stores act'(u) for the backward
+// data-gradient GEMM, whose epilogue then only multiplies: the erf / exp / tanh are paid once)
+template <int ACT>
+__device__ __forceinline__ float act_with_grad(float v, float &g) {
+    if (ACT == 1) {
+        g = v > 0.f ? 1.f : 0.f;
+        return fmaxf(v, 0.f);
+    }
+    if (ACT == 2) {
+        const float sg = 0.5f * (1.0f + tanh_approx(0.5f * v));
+        g = sg * (1.0f + v * (1.0f - sg));
+        return v * sg;
+    }
+    if (ACT == 3) {
+        float e;
+        const float x = v * 0.70710678118654752f;
+        const float phi = 0.5f * (1.0f + copysignf(erf_abs_exp(fabsf(x), e), x));
+        g = fmaf(v * 0.3989422804014327f, e, phi);
+        return v * phi;
+    }
+    if (ACT == 4) {
+        const float sg = 0.5f * (1.0f + tanh_approx(0.5f * v));
+        g = sg * (1.0f - sg);
+        return sg;
+    }
+    g = 1.f;
+    return v;
+}
+
+// derivative of the activation at a saved pre-activation u (ACT 6 = silu', 7 = relu'; ACT 5 multiplies by a SAVED derivative)
 template <int ACT>
 __device__ __forceinline__ float act_grad(float u) {
-    if (ACT == 5) return 0.5f * (1.0f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+    if (ACT == 5) return u;
     if (ACT == 6) {
         const float sg = 0.5f * (1.0f + tanh_approx(0.5f * u));
         return sg * (1.0f + u * (1.0f - sg));
@@ -145,7 +194,7 @@ __device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, 
         float4 x = lds128(stg + tr * kPitch + colq * 4);
         if (grow < 0) continue;
         if (ACT >= 5) {
-            // backward through an activation: C = acc * act'(u) * out_scale, u = saved pre-activation (`residual`)
+            // backward through an activation: C = acc * act'(u) * out_scale (saved derivative or pre-activation: `residual`)
             const uint2 pk = __ldg((const uint2 *)(ep.residual + grow * ep.ldr + col));
             const float2 u0 = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.x);
             const float2 u1 = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.y);
@@ -160,14 +209,20 @@ __device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, 
             }
         } else {
             x.x += bz.x; x.y += bz.y; x.z += bz.z; x.w += bz.w;
-            if (ep.preact != nullptr) {
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(x.x, x.y), p1 = __floats2bfloat162_rn(x.z, x.w);
+            if (ep.preact != nullptr) {          // training: keep act'(u) (bf16) for the backward data-gradient GEMM
+                float4 g;
+                x.x = act_with_grad<ACT>(x.x, g.x) * ep.out_scale;
+                x.y = act_with_grad<ACT>(x.y, g.y) * ep.out_scale;
+                x.z = act_with_grad<ACT>(x.z, g.z) * ep.out_scale;
+                x.w = act_with_grad<ACT>(x.w, g.w) * ep.out_scale;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(g.x, g.y), p1 = __floats2bfloat162_rn(g.z, g.w);
                 *(uint2 *)(ep.preact + grow * ep.ldc + col) = make_uint2(*(uint32_t *)&p0, *(uint32_t *)&p1);
+            } else {
+                x.x = fast_act<ACT>(x.x) * ep.out_scale;
+                x.y = fast_act<ACT>(x.y) * ep.out_scale;
+                x.z = fast_act<ACT>(x.z) * ep.out_scale;
+                x.w = fast_act<ACT>(x.w) * ep.out_scale;
             }
-            x.x = fast_act<ACT>(x.x) * ep.out_scale;
-            x.y = fast_act<ACT>(x.y) * ep.out_scale;
-            x.z = fast_act<ACT>(x.z) * ep.out_scale;
-            x.w = fast_act<ACT>(x.w) * ep.out_scale;
             if (ep.drop_thresh) {
                 const unsigned long long i0 = (unsigned long long)grow * ep.ldc + col;
                 x.x = drop_keep(ep.drop_seed, i0, ep.drop_thresh) ? x.x * ep.drop_scale : 0.f;
@@ -217,14 +272,15 @@ __device__ __forceinline__ void epilogue_rows_slow(uint32_t stg, const Epilogue 
                     y = drop_keep(ep.drop_seed, (unsigned long long)grow * ep.ldc + col + q, ep.drop_thresh) ? y * ep.drop_scale : 0.f;
             } else {
                 if (ep.bias != nullptr) y += __ldg(ep.bias + col + q);
-                if (ep.preact != nullptr) ep.preact[grow * ep.ldc + col + q] = __float2bfloat16_rn(y);
+                float gq = 1.f;
                 switch (ep.act) {
-                    case 1: y = fast_act<1>(y); break;
-                    case 2: y = fast_act<2>(y); break;
-                    case 3: y = fast_act<3>(y); break;
-                    case 4: y = fast_act<4>(y); break;
+                    case 1: y = act_with_grad<1>(y, gq); break;
+                    case 2: y = act_with_grad<2>(y, gq); break;
+                    case 3: y = act_with_grad<3>(y, gq); break;
+                    case 4: y = act_with_grad<4>(y, gq); break;
                     default: break;
                 }
+                if (ep.preact != nullptr) ep.preact[grow * ep.ldc + col + q] = __float2bfloat16_rn(gq);
                 y *= ep.out_scale;
                 if (ep.drop_thresh)
                     y = drop_keep(ep.drop_seed, (unsigned long long)grow * ep.ldc + col + q, ep.drop_thresh) ? y * ep.drop_scale : 0.f;
@@ -237,6 +293,97 @@ __device__ __forceinline__ void epilogue_rows_slow(uint32_t stg, const Epilogue 
     }
 }
 
+// ---- TMA epilogue --------------------------------------------------------------------------------------------------
+// Row-per-lane epilogue for bf16 outputs (MODE 0): a lane keeps its accumulator row (32 columns) in registers, reads the
+// auxiliary operand (residual / saved derivative) from a 32 x 32 bf16 tile the TMA unit prefetched while the main loop
+// was still running, and writes its 64 output bytes into a 64-byte-swizzled shared-memory tile that one
+// cp.async.bulk.tensor store sends to HBM: ~70 instructions per 32 x 32 chunk instead of ~190 (+ per-element math) for
+// the transposing epilogue, which was issue bound on the K = 768 layers.  TMA clips rows >= M.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_src),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+// byte offset of 16-byte chunk c of row r in a [32 x 64 B] SWIZZLE_64B tile
+__device__ __forceinline__ uint32_t sw64(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
+
+template <int ACT>
+__device__ __forceinline__ void epilogue_tma(const uint32_t (&acc)[32], const Epilogue &ep, const CUtensorMap *map_c,
+                                             const CUtensorMap *map_pre, uint32_t out_stg, uint32_t aux_stg, uint64_t *auxbar,
+                                             uint32_t &aux_phase, long row0, int lane, int col0) {
+    const long grow = row0 + lane;
+    if (ep.residual != nullptr) {
+        mbar_wait(auxbar, aux_phase);
+        aux_phase ^= 1;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {                      // 8 columns at a time keeps the live registers low
+        float x[8], g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(acc[c * 8 + j]);
+        float a[8];
+        if (ep.residual != nullptr) {
+            const uint4 pk = lds128u(aux_stg + sw64(lane, c));
+            const __nv_bfloat162 *h = (const __nv_bfloat162 *)&pk;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 t = __bfloat1622float2(h[q]);
+                a[2 * q] = t.x;
+                a[2 * q + 1] = t.y;
+            }
+        }
+        if (ACT >= 5) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] *= act_grad<ACT>(a[j]) * ep.out_scale;
+        } else {
+            if (ep.bias != nullptr) {
+                const float4 b0 = __ldg((const float4 *)(ep.bias + col0 + c * 8)), b1 = __ldg((const float4 *)(ep.bias + col0 + c * 8) + 1);
+                x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+                x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+            }
+            if (ep.preact != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = act_with_grad<ACT>(x[j], g[j]) * ep.out_scale;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = fast_act<ACT>(x[j]) * ep.out_scale;
+            }
+        }
+        if (ep.drop_thresh) {
+            const unsigned long long i0 = (unsigned long long)grow * ep.ldc + col0 + c * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = drop_keep(ep.drop_seed, i0 + j, ep.drop_thresh) ? x[j] * ep.drop_scale : 0.f;
+        }
+        if (ACT < 5 && ep.residual != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = fmaf(a[j], ep.res_scale, x[j]);
+        }
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(x[0], x[1]), p1 = __floats2bfloat162_rn(x[2], x[3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(x[4], x[5]), p3 = __floats2bfloat162_rn(x[6], x[7]);
+        sts128(out_stg + sw64(lane, c), *(uint32_t *)&p0, *(uint32_t *)&p1, *(uint32_t *)&p2, *(uint32_t *)&p3);
+        if (ACT < 5 && ep.preact != nullptr) {          // the derivative tile reuses this lane's own row of the aux tile
+            p0 = __floats2bfloat162_rn(g[0], g[1]); p1 = __floats2bfloat162_rn(g[2], g[3]);
+            p2 = __floats2bfloat162_rn(g[4], g[5]); p3 = __floats2bfloat162_rn(g[6], g[7]);
+            sts128(aux_stg + sw64(lane, c), *(uint32_t *)&p0, *(uint32_t *)&p1, *(uint32_t *)&p2, *(uint32_t *)&p3);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(map_c, out_stg, col0, (int)row0);
+        if (ACT < 5 && ep.preact != nullptr) tma_store_2d(map_pre, aux_stg, col0, (int)row0);
+        tma_store_commit();
+    }
+}
+
 // PERSISTENT kernel: grid = min(tiles, SMs); every CTA walks tiles t = blockIdx.x, += gridDim.x (N fastest so an A
 // tile is reused from L2 by its N neighbours).  The TMA ring runs ahead across tile boundaries, the accumulator is
 // double buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the MMAs of tile i + 1.
@@ -244,10 +391,14 @@ __device__ __forceinline__ void epilogue_rows_slow(uint32_t stg, const Epilogue 
 // backward GEMMs read activations and weights in place: dX = dY . W (B_MN) and dW = dY^T . X (A_MN and B_MN).
 // Split-K: a work item is (tile, split); split s contracts k-blocks [s * kb_per, (s + 1) * kb_per) and the
 // epilogue accumulates with red.global.add (ep.accumulate).
-template <int BN, int kStages, int BKC, int MODE, int A_MN, int B_MN>
+// TMA_EPI selects the epilogue at compile time (each instantiation carries only one of the two: the combined kernel was
+// 28 K instructions and measurably slower on every path).
+template <int BN, int kStages, int BKC, int MODE, int A_MN, int B_MN, int TMA_EPI>
 __global__ void __launch_bounds__(kGemmThreadsP, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N,
-                    int K, const Epilogue ep, const ConvGeom cg, int m_tiles, int n_tiles, int kb_per, int k_splits) {
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_aux,
+                    const __grid_constant__ CUtensorMap map_pre, int M, int N, int K, const Epilogue ep, const ConvGeom cg,
+                    int m_tiles, int n_tiles, int kb_per, int k_splits) {
     using S = GemmSmem<BN, kStages, BKC>;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);  // swizzle atoms: 1024 B
@@ -256,7 +407,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint64_t *empty = full + kStages;
     uint64_t *acc_full = empty + kStages;   // [2]
     uint64_t *acc_empty = acc_full + 2;     // [2]
-    uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+    uint64_t *aux_bar = acc_empty + 2;      // [16]: auxiliary-tile TMA loads of the epilogue warps
+    uint32_t *tmem_slot = (uint32_t *)(aux_bar + 16);
     unsigned char *staging = bars + S::kBarrierBytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -276,6 +428,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mbar_init(acc_full + s, 1);
             mbar_init(acc_empty + s, kEpiWarps);
         }
+        for (int s = 0; s < 16; ++s) mbar_init(aux_bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -399,14 +552,44 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // 128 B line.  It is transposed through a private shared-memory buffer instead, so that bias / activation /
         // residual / convert / store all run with 8 lanes per output row (4 full rows per instruction).
         const int quarter = warp & 3, cgrp = (warp - 2) >> 2;   // cgrp 0..3: which column chunks this warp owns
-        const uint32_t stg = smem_u32(staging + (warp - 2) * 32 * S::kStagePitch);
+        const uint32_t stg = smem_u32(staging + (warp - 2) * S::kWarpStaging);
         const int colq = (lane & 7) * 4;  // phase-2 mapping: 8 lanes per row, 4 columns per lane
-        uint32_t tile_iter = 0;
+        uint32_t tile_iter = 0, aux_phase = 0;
         for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++tile_iter) {
             const int tile = item % mn_tiles;
             const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
             const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BN;
             const int r = quarter * 32 + lane;
+            if constexpr (TMA_EPI != 0) {
+                // ---- row-per-lane epilogue with TMA stores (one 32 x 32 chunk per warp: BN <= 128) ----
+                const int col0 = n0 + cgrp * 32;
+                const bool mine = cgrp < BN / 32 && col0 < N;       // warp-uniform
+                const long row0 = (long)mt * BM + quarter * 32;
+                if (lane == 0 && mine) {
+                    tma_store_wait_read();                          // the previous tile's stores have left both staging tiles
+                    if (ep.residual != nullptr) {
+                        mbar_expect_tx(aux_bar + (warp - 2), 32 * 64);
+                        tma_load_2d((void *)(staging + (warp - 2) * S::kWarpStaging + 2048), &map_aux, aux_bar + (warp - 2), col0,
+                                    (int)row0);
+                    }
+                }
+                __syncwarp();
+                mbar_wait(acc_full + as, aph);
+                tc_fence_after();
+                uint32_t acc1[32];
+                if (mine) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(cgrp * 32), acc1);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
+                if (mine) {
+                    switch (ep.act) {
+#define EPI_TMA(A_) case A_: epilogue_tma<A_>(acc1, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
+                        EPI_TMA(0) EPI_TMA(1) EPI_TMA(2) EPI_TMA(3) EPI_TMA(4) EPI_TMA(5) EPI_TMA(6)
+                        default: epilogue_tma<7>(acc1, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
+#undef EPI_TMA
+                    }
+                }
+            } else {
             long row;       // global output row of tile row r (this lane's accumulator row)
             if (MODE != 1) {
                 row = (long)mt * BM + r;
@@ -463,8 +646,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
                 __syncwarp();   // staging is rewritten by the next chunk
             }
+            }   // !TMA_EPI
         }
     }
+    if (TMA_EPI != 0 && warp >= 2 && lane == 0) tma_store_wait_all();      // bulk stores of this thread have completed
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -486,23 +671,6 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float *__restr
 }
 
 // -------------------------------------------------------------------------------------------- host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    });
-    return fn;
-}
-
 // 2-D bf16 row-major [rows, cols] tensor, box = box_rows x bkc columns, swizzle = row bytes, OOB reads give zeros
 static int make_map_2d(CUtensorMap *map, const void *ptr, long rows, long cols, long ld_elems, int box_rows, int bkc) {
     EncodeTiledFn fn = encode_tiled();
@@ -533,17 +701,49 @@ static int make_map_nhwc(CUtensorMap *map, const void *ptr, int Nimg, int H, int
     return r == CUDA_SUCCESS ? POSE_OK : POSE_E_SHAPE;
 }
 
+// bf16 [rows, cols] tensor (pitch ld elements), box = 32 x 32, 64-byte swizzle: the epilogue's output / auxiliary tiles
+static int make_map_tile32(CUtensorMap *map, const void *ptr, long rows, long cols, long ld) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return POSE_E_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? POSE_OK : POSE_E_SHAPE;
+}
+
 template <int BN, int kStages, int BKC, int MODE, int A_MN = 0, int B_MN = 0>
-static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int N, int K, const Epilogue &ep,
+static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int N, int K, const Epilogue &ep_in,
                        const ConvGeom &cg, int m_tiles, cudaStream_t s, int k_splits = 1) {
+    Epilogue ep = ep_in;
+    CUtensorMap mc = {}, maux = {}, mpre = {};
+    // Epilogue choice (measured on the ViT shapes, same box): the row-per-lane TMA epilogue wins whenever the epilogue has
+    // real per-element work -- exact GELU (103 vs 111 us), saving the activation derivative (109 vs 117 us), multiplying
+    // by a saved derivative (105 vs 212 us) -- and loses ~10 % on plain / SiLU / residual-only epilogues, whose 64-byte
+    // row stores compete with the operand loads for the TMA / L2 path that already bounds the 128 x 128 main loop.
+    ep.tma = 0;
+    static const bool tma_off = getenv("POSE_NO_TMA_EPILOGUE") != nullptr;     // A/B switch for measurements
+    const bool heavy = ep.act == 3 || ep.act >= 5 || ep.preact != nullptr;
+    if (MODE == 0 && BN <= 128 && ep.out_bf16 && !ep.accumulate && ep.vec && N % 32 == 0 && heavy && !tma_off) {
+        int e = make_map_tile32(&mc, ep.C, M, N, ep.ldc);
+        if (!e && ep.residual) e = make_map_tile32(&maux, ep.residual, M, N, ep.ldr);
+        if (!e && ep.preact) e = make_map_tile32(&mpre, ep.preact, M, N, ep.ldc);
+        ep.tma = e ? 0 : 1;
+    }
     using S = GemmSmem<BN, kStages, BKC>;
-    auto kern = gemm_bf16_tn_kernel<BN, kStages, BKC, MODE, A_MN, B_MN>;
+    auto kern_plain = gemm_bf16_tn_kernel<BN, kStages, BKC, MODE, A_MN, B_MN, 0>;
+    auto kern_tma = gemm_bf16_tn_kernel<BN, kStages, BKC, MODE, A_MN, B_MN, (MODE == 0 && BN <= 128) ? 1 : 0>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        cudaError_t ce = cudaFuncSetAttribute(kern_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
         if (ce != cudaSuccess) return (int)ce;
         configured = true;
     }
+    auto kern = ep.tma ? kern_tma : kern_plain;
     const int n_tiles = (N + BN - 1) / BN;
     const int num_kb = (K + BKC - 1) / BKC;
     if (k_splits < 1) k_splits = 1;
@@ -552,7 +752,7 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
     k_splits = (num_kb + kb_per - 1) / kb_per;            // no empty split
     const long total = (long)m_tiles * n_tiles * k_splits;
     const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-    kern<<<grid, kGemmThreadsP, S::kTotal, s>>>(ma, mw, M, N, K, ep, cg, m_tiles, n_tiles, kb_per, k_splits);
+    kern<<<grid, kGemmThreadsP, S::kTotal, s>>>(ma, mw, mc, maux, mpre, M, N, K, ep, cg, m_tiles, n_tiles, kb_per, k_splits);
     return launch_status();
 }
 

@@ -26,8 +26,9 @@ def _ceil8(n):
     return (n + 7) // 8 * 8
 
 
-# forward activation id -> id of the "multiply by act'(saved pre-activation)" GEMM epilogue (csrc/gemm_tcgen05.cu)
-ACT_GRAD = {1: 7, 2: 6, 3: 5}
+# GEMM epilogue id "multiply by the activation derivative the forward GEMM saved" (csrc/gemm_tcgen05.cu); the table is kept
+# so that call sites read as act -> act'
+ACT_GRAD = {1: 5, 2: 5, 3: 5}
 
 
 class CnnTrainPlan:

@@ -482,7 +482,8 @@ class VitPlan:
 
     def linear_bwd(self, dy, ldy, M, x, weight, bias, rows=None, dx_name=None, act_u=None, act_drop=None):
         """Backward of y = x @ W[rows]^T + b[rows] given dy [M, N] (pitch ldy): accumulates dW and db, returns
-        dx = dy @ W (times act'(u), and the dropout mask `act_drop`, when the layer's INPUT x was drop(act(u))) or None."""
+        dx = dy @ W (times the saved derivative act'(u) `act_u`, and the dropout mask `act_drop`, when the layer's INPUT x
+        was drop(act(u))) or None."""
         w16 = self.flat.w16(weight, rows)
         N, K = w16.shape
         gw = self.flat.g32(weight, rows).view(N, K)
@@ -494,7 +495,7 @@ class VitPlan:
         if dx_name is None:
             return None
         dx = self.buf(dx_name, M, K)
-        e = self._epi(dx, K, act={2: 6, 3: 5}[self.act] if act_u is not None else 0, residual=act_u, ldr=K, drop=act_drop)
+        e = self._epi(dx, K, act=5 if act_u is not None else 0, residual=act_u, ldr=K, drop=act_drop)
         self.call("pose_gemm_bf16_tr", dy.data_ptr(), ldy, 0, w16.data_ptr(), K, 1, M, K, N, 1, C.byref(e))
         return dx
 

@@ -137,7 +137,7 @@ typedef struct pose_gemm_epilogue {
     int32_t ldc, ldr, act, out_dtype;
     float out_scale, res_scale;
     /* training: */
-    void *preact;       /* [M, ldc] bf16 or NULL: acc + bias BEFORE the activation, saved for the backward pass */
+    void *preact;       /* [M, ldc] bf16 or NULL: act'(acc + bias), the activation's derivative, saved for the backward pass */
     int32_t accumulate; /* 1: fp32 C += acc * out_scale (atomic adds; split-K weight gradients accumulate into .grad) */
     int32_t reserved;
     /* nn.Dropout fused after the activation and before the residual add: element (row, col) is kept iff
@@ -158,8 +158,8 @@ int pose_gemm_bf16_ex(const void *A, int lda, const void *W, int ldw, int M, int
  *    data gradient    dX[M, Kin] = dY[M, Nout] . W[Nout, Kin]     -> (A = dY, a_mn 0; W = weight, b_mn 1)
  *    weight gradient  dW[Nout, Kin] = dY^T . X                    -> (A = dY, a_mn 1; W = X, b_mn 1), contraction over
  *                     the rows, split k_splits ways across CTAs, epilogue->accumulate = 1
- *    act 5 | 6 | 7 in the epilogue: C = acc * act'(u) * out_scale with u = `residual` (saved pre-activation, bf16)
- *    for act = gelu | silu | relu. */
+ *    act 5 in the epilogue: C = acc * g * out_scale with g = `residual` = the derivative act'(u) the forward GEMM saved
+ *    through `preact` (bf16); act 6 | 7: C = acc * silu'(u) | relu'(u) with u = `residual` a saved PRE-activation. */
 int pose_gemm_bf16_tr(const void *A, long lda, int a_mn, const void *W, long ldw, int b_mn, int M, int N, int K,
                       int k_splits, const pose_gemm_epilogue *epilogue, pose_stream_t stream);
 

@@ -44,14 +44,20 @@ def test_data_gradient_gemm_reads_the_weight_in_place(pose, M, Nout, Kin):
     _tr(pose, dy, 0, w, 1, M, Kin, Nout, 1, _epi(pose, dx))
     want = dy[:, :Nout].float() @ w.float()
     assert torch.allclose(dx, want, rtol=1e-3, atol=1e-3), (dx - want).abs().max().item()
-    # fused activation derivative: dU = (dH . W) * gelu'(u) / silu'(u)
+    # fused activation derivative: dU = (dH . W) * act'(u); act 5 multiplies by the derivative the forward GEMM saved,
+    # act 6 recomputes silu' from a saved pre-activation
     u = torch.randn(M, Kin, generator=g).to(DEV).bfloat16()
-    for act, fn in ((5, F.gelu), (6, F.silu)):
-        du = torch.empty(M, Kin, device=DEV, dtype=torch.bfloat16)
-        _tr(pose, dy, 0, w, 1, M, Kin, Nout, 1, _epi(pose, du, act=act, residual=u))
-        uu = u.float().requires_grad_()
-        fn(uu).backward(want)
-        assert torch.allclose(du.float(), uu.grad, rtol=2e-2, atol=2e-2), (du.float() - uu.grad).abs().max().item()
+    uu = u.float().requires_grad_()
+    F.gelu(uu).backward(torch.ones_like(uu))
+    gp = uu.grad.bfloat16()
+    du = torch.empty(M, Kin, device=DEV, dtype=torch.bfloat16)
+    _tr(pose, dy, 0, w, 1, M, Kin, Nout, 1, _epi(pose, du, act=5, residual=gp))
+    assert torch.allclose(du.float(), want * gp.float(), rtol=2e-2, atol=2e-2)
+    du = torch.empty(M, Kin, device=DEV, dtype=torch.bfloat16)
+    _tr(pose, dy, 0, w, 1, M, Kin, Nout, 1, _epi(pose, du, act=6, residual=u))
+    uu = u.float().requires_grad_()
+    F.silu(uu).backward(want)
+    assert torch.allclose(du.float(), uu.grad, rtol=2e-2, atol=2e-2), (du.float() - uu.grad).abs().max().item()
 
 
 @pytest.mark.parametrize("M,Nout,Kin,splits", [(257 * 8, 768, 768, 4), (1000, 51, 256, 3), (4096, 3072, 768, 1),
@@ -70,7 +76,7 @@ def test_weight_gradient_gemm_split_k_accumulates(pose, M, Nout, Kin, splits):
     assert torch.allclose(dw, want, rtol=1e-3, atol=tol), (dw - want).abs().max().item()
 
 
-def test_forward_gemm_saves_the_pre_activation(pose):
+def test_forward_gemm_saves_the_activation_derivative(pose):
     g = torch.Generator().manual_seed(3)
     M, K, N = 500, 768, 3072
     a = torch.randn(M, K, generator=g).to(DEV).bfloat16()
@@ -81,6 +87,15 @@ def test_forward_gemm_saves_the_pre_activation(pose):
     e = _epi(pose, h, bias=b, act=3, preact=u)
     pose._lib.check(pose._lib.lib().pose_gemm_bf16_ex(a.data_ptr(), K, w.data_ptr(), K, M, N, K, C.byref(e),
                                                       pose._lib.stream_ptr()), "gemm")
-    want_u = a.float() @ w.float().t() + b
-    assert torch.allclose(u.float(), want_u, rtol=2 ** -7, atol=2e-2)
-    assert torch.allclose(h.float(), F.gelu(want_u), rtol=2 ** -7, atol=2e-2)
+    want_u = (a.float() @ w.float().t() + b).requires_grad_()
+    F.gelu(want_u).backward(torch.ones_like(want_u))
+    assert torch.allclose(u.float(), want_u.grad, rtol=2 ** -7, atol=2e-2)          # gelu'(a w^T + b), exact-erf form
+    assert torch.allclose(h.float(), F.gelu(want_u.detach()), rtol=2 ** -7, atol=2e-2)
+    for act, fn in ((2, F.silu), (1, F.relu)):
+        e = _epi(pose, h, bias=b, act=act, preact=u)
+        pose._lib.check(pose._lib.lib().pose_gemm_bf16_ex(a.data_ptr(), K, w.data_ptr(), K, M, N, K, C.byref(e),
+                                                          pose._lib.stream_ptr()), "gemm")
+        wu = want_u.detach().clone().requires_grad_()
+        fn(wu).backward(torch.ones_like(wu))
+        far = (wu.detach().abs() > 0.05)          # relu' is discontinuous at 0: compare away from it
+        assert torch.allclose(u.float()[far], wu.grad[far], rtol=2e-2, atol=2e-2)
