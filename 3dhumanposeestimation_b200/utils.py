@@ -32,8 +32,29 @@ def get_activation(name):
     return nn.ReLU(inplace=True)
 
 
+def eval_metrics(predicted_joints, ground_truth_joints):
+    """(means [2], per_sample [2, B]) fp32 device tensors: row 0 MPJPE, row 1 PA-MPJPE -- one launch for both metrics
+    (src/utils.py:55-165; the reference loops over samples in Python with a 3x3 SVD each)."""
+    from . import _lib
+    if predicted_joints.shape != ground_truth_joints.shape:
+        raise AssertionError(f"Shape mismatch: pred {predicted_joints.shape}, gt {ground_truth_joints.shape}")
+    pred = _lib.require_cuda(predicted_joints.detach().float().contiguous(), "predicted_joints", torch.float32)
+    gt = _lib.require_cuda(ground_truth_joints.detach().float().contiguous(), "ground_truth_joints", torch.float32)
+    if pred.dim() != 3 or pred.shape[2] != 3:
+        raise ValueError(f"expected [N, num_joints, 3], got {tuple(pred.shape)}")
+    B, J = pred.shape[0], pred.shape[1]
+    per = torch.empty(2, B, dtype=torch.float32, device=pred.device)
+    means = torch.empty(2, dtype=torch.float32, device=pred.device)
+    _lib.check(_lib.lib().pose_eval_metrics(pred.data_ptr(), gt.data_ptr(), B, J, per.data_ptr(), means.data_ptr(),
+                                            _lib.stream_ptr()), "pose_eval_metrics")
+    return means, per
+
+
 def compute_mpjpe(predicted_joints, ground_truth_joints):
-    """Mean per-joint position error (src/utils.py:55-69); plain tensor ops, used as the parity metric."""
-    assert predicted_joints.shape == ground_truth_joints.shape
-    errors = torch.linalg.norm(predicted_joints - ground_truth_joints, dim=2)
-    return errors.mean(dim=1).mean()
+    """Mean per-joint position error (src/utils.py:55-69): 0-dim device tensor."""
+    return eval_metrics(predicted_joints, ground_truth_joints)[0][0]
+
+
+def compute_pa_mpjpe(predicted_joints, ground_truth_joints):
+    """Procrustes-aligned MPJPE (src/utils.py:72-165, including its rotation convention): 0-dim device tensor."""
+    return eval_metrics(predicted_joints, ground_truth_joints)[0][1]

@@ -339,6 +339,14 @@ int pose_dropout_bf16(const void *x, long n, float p, uint64_t seed, void *out, 
 int pose_param_repack(const void *table, int n_entries, const float *src_f32, float *dst_f32, void *dst_bf16,
                       pose_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * next row: validation metrics     reference: src/utils.py:55-69 compute_mpjpe, :72-165
+ *    compute_pa_mpjpe (per-sample Python loop + 3x3 SVD in the reference; src/train.py:249-254).
+ *    pred, gt [B, J, 3] fp32; per_sample [2, B] fp32 = {MPJPE_b}, {PA-MPJPE_b}; means [2] fp32 = batch means
+ *    (what the reference functions return).  The reference's rotation convention (Pc @ V U^T) is reproduced.
+ * ------------------------------------------------------------------------------------------- */
+int pose_eval_metrics(const float *pred, const float *gt, int B, int J, float *per_sample, float *means, pose_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,7 @@ def lib() -> C.CDLL:
         build()
         _lib = C.CDLL(_SO)
         _lib.oracle_mpjpe.restype = C.c_float
+        _lib.oracle_pa_mpjpe.restype = C.c_float
         _lib.oracle_rotate_matrix.restype = C.c_int
         _lib.oracle_grey_mean_u8.restype = C.c_int
     return _lib
@@ -185,3 +186,11 @@ def pose_loss(pred, gt, weights=(1.0, 1.0, 100.0, 1.0), want_grad: bool = True):
 def mpjpe(pred, gt) -> float:
     pred, gt = _f32(pred), _f32(gt)
     return float(lib().oracle_mpjpe(_p(pred), _p(gt), pred.shape[0], pred.shape[1]))
+
+
+def pa_mpjpe(pred, gt, per_sample: bool = False):
+    """utils.py:72-165 compute_pa_mpjpe (the reference's rotation convention included)."""
+    pred, gt = _f32(pred), _f32(gt)
+    out = np.empty(pred.shape[0], np.float32)
+    m = float(lib().oracle_pa_mpjpe(_p(pred), _p(gt), pred.shape[0], pred.shape[1], _p(out)))
+    return (m, out) if per_sample else m

@@ -403,11 +403,34 @@ def gen_cnn_train():
                              "image, depth, kp, gt in that order")
 
 
+def gen_metrics():
+    """compute_mpjpe / compute_pa_mpjpe of the live reference (src/utils.py:55-165) on seeded poses incl. a mirrored pose
+    (reflection branch), a pure similarity transform, identical poses and a collapsed prediction (variance <= 1e-9)."""
+    import torch
+    import utils
+    rng = np.random.default_rng(17)
+    B = 24
+    gt = rng.normal(0, 300, (B, 17, 3)).astype(np.float32)
+    pred = (gt + rng.normal(0, 60, (B, 17, 3))).astype(np.float32)
+    pred[1] = gt[1] * np.array([-1, 1, 1], np.float32)                       # mirrored: det < 0 branch
+    th = 0.7
+    Rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32)
+    pred[2] = (1.3 * gt[2] @ Rz + np.array([50, -20, 10], np.float32)).astype(np.float32)   # similarity transform
+    pred[3] = gt[3]                                                           # identical
+    pred[4] = np.float32(7.0)                                                 # collapsed: scale falls back to 1
+    pred[5] = gt[5] @ Rz.T                                                    # pure rotation the other way
+    tp, tg = torch.from_numpy(pred), torch.from_numpy(gt)
+    per = np.array([utils.compute_pa_mpjpe(tp[i:i + 1], tg[i:i + 1]).item() for i in range(B)], np.float32)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), versions=versions(), pred=pred, gt=gt,
+                        mpjpe=np.float32(utils.compute_mpjpe(tp, tg).item()),
+                        pa_mpjpe=np.float32(utils.compute_pa_mpjpe(tp, tg).item()), pa_per_sample=per)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, os.path.join(REF, "src"))
     os.chdir(tempfile.mkdtemp(prefix="pose_golden_"))
-    which = sys.argv[1:] or ["augment", "heatmap", "loss", "config", "cnn", "vit", "cnn_train"]
+    which = sys.argv[1:] or ["augment", "heatmap", "loss", "config", "cnn", "vit", "cnn_train", "metrics"]
     for w in which:
         globals()["gen_" + w]()
         print("wrote", w)

@@ -623,3 +623,120 @@ ORACLE_API float oracle_mpjpe(const float *pred, const float *gt, int B, int J) 
     }
     return (float)(s / ((double)B * J));
 }
+
+/* utils.py:72-165 compute_pa_mpjpe: per sample centre both point sets, M = Pc^T Gc, SVD M = U S V^T, R = V U^T (the
+ * reference applies it as Pc @ R, i.e. the transpose of the optimal Procrustes rotation: mirrored, not fixed), reflection
+ * fix on the last right-singular vector, scale = sum(S') / |Pc|^2 (1 if |Pc|^2 <= 1e-9), error = mean |s Pc R + mu_g - G|.
+ * The 3x3 SVD is a cyclic Jacobi eigen-decomposition of M^T M in double precision (torch.linalg.svd = LAPACK gesdd). */
+static void jacobi_eig3(double a[3][3], double v[3][3]) {
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) v[i][j] = i == j;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (fabs(a[p][q]) < 1e-300) continue;
+                double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; ++k) {
+                    double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - sn * akq;
+                    a[k][q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - sn * aqk;
+                    a[q][k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = c * vkp - sn * vkq;
+                    v[k][q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+}
+
+static void cross3(const double a[3], const double b[3], double c[3]) {
+    c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+static double det3(double m[3][3]) {
+    return m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+           m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+}
+
+ORACLE_API float oracle_pa_mpjpe(const float *pred, const float *gt, int B, int J, float *per_sample) {
+    double total = 0;
+    for (int b = 0; b < B; ++b) {
+        const float *P = pred + (long)b * J * 3, *G = gt + (long)b * J * 3;
+        double mp[3] = {0, 0, 0}, mg[3] = {0, 0, 0};
+        for (int j = 0; j < J; ++j) for (int d = 0; d < 3; ++d) { mp[d] += P[j * 3 + d]; mg[d] += G[j * 3 + d]; }
+        for (int d = 0; d < 3; ++d) { mp[d] = (float)(mp[d] / J); mg[d] = (float)(mg[d] / J); }
+        double M[3][3] = {{0}}, var = 0;
+        for (int j = 0; j < J; ++j)
+            for (int r = 0; r < 3; ++r) {
+                double pc = (float)(P[j * 3 + r] - mp[r]);
+                var += pc * pc;
+                for (int c = 0; c < 3; ++c) M[r][c] += pc * (double)(float)(G[j * 3 + c] - mg[c]);
+            }
+        double A[3][3], V[3][3];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { A[r][c] = 0; for (int k = 0; k < 3; ++k) A[r][c] += M[k][r] * M[k][c]; }
+        jacobi_eig3(A, V);
+        int idx[3] = {0, 1, 2};                                  /* sort eigenvalues descending */
+        for (int i = 0; i < 2; ++i) for (int k = i + 1; k < 3; ++k) if (A[idx[k]][idx[k]] > A[idx[i]][idx[i]]) { int t = idx[i]; idx[i] = idx[k]; idx[k] = t; }
+        double S[3], Vs[3][3], U[3][3];
+        for (int i = 0; i < 3; ++i) {
+            S[i] = sqrt(fmax(A[idx[i]][idx[i]], 0.0));
+            for (int r = 0; r < 3; ++r) Vs[r][i] = V[r][idx[i]];
+        }
+        double vc[3]; { double c0[3] = {Vs[0][0], Vs[1][0], Vs[2][0]}, c1[3] = {Vs[0][1], Vs[1][1], Vs[2][1]}; cross3(c0, c1, vc); }
+        if (vc[0] * Vs[0][2] + vc[1] * Vs[1][2] + vc[2] * Vs[2][2] < 0) for (int r = 0; r < 3; ++r) Vs[r][2] = -Vs[r][2];   /* det V = +1 */
+        const double tiny = 1e-12 * (S[0] > 0 ? S[0] : 1.0);
+        int rank = 0;
+        for (int i = 0; i < 3; ++i) {
+            if (S[i] > tiny) {
+                for (int r = 0; r < 3; ++r) { U[r][i] = 0; for (int k = 0; k < 3; ++k) U[r][i] += M[r][k] * Vs[k][i]; U[r][i] /= S[i]; }
+                rank = i + 1;
+            }
+        }
+        if (rank == 0) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) U[r][c] = Vs[r][c]; }   /* M = 0: any U; R = I */
+        else if (rank == 1) {                                   /* complete an orthonormal basis */
+            double u0[3] = {U[0][0], U[1][0], U[2][0]}, e[3] = {0, 0, 0}, u1[3], u2[3];
+            int m = fabs(u0[0]) < fabs(u0[1]) ? (fabs(u0[0]) < fabs(u0[2]) ? 0 : 2) : (fabs(u0[1]) < fabs(u0[2]) ? 1 : 2);
+            e[m] = 1; cross3(u0, e, u1);
+            double n = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+            for (int r = 0; r < 3; ++r) u1[r] /= n;
+            cross3(u0, u1, u2);
+            for (int r = 0; r < 3; ++r) { U[r][1] = u1[r]; U[r][2] = u2[r]; }
+        } else if (rank == 2) {
+            double u0[3] = {U[0][0], U[1][0], U[2][0]}, u1[3] = {U[0][1], U[1][1], U[2][1]}, u2[3];
+            cross3(u0, u1, u2);
+            for (int r = 0; r < 3; ++r) U[r][2] = u2[r];
+        }
+        double R[3][3];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { R[r][c] = 0; for (int k = 0; k < 3; ++k) R[r][c] += Vs[r][k] * U[c][k]; }
+        double s_sum = S[0] + S[1] + S[2];
+        if (det3(R) < 0) {
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r][c] -= 2.0 * Vs[r][2] * U[c][2];
+            s_sum = S[0] + S[1] - S[2];
+        }
+        const double sc = var > 1e-9 ? s_sum / var : 1.0;
+        double err = 0;
+        for (int j = 0; j < J; ++j) {
+            double d2 = 0;
+            for (int c = 0; c < 3; ++c) {
+                double a = 0;
+                for (int k = 0; k < 3; ++k) a += (double)(float)(P[j * 3 + k] - mp[k]) * R[k][c];
+                double diff = sc * a + mg[c] - G[j * 3 + c];
+                d2 += diff * diff;
+            }
+            err += sqrt(d2);
+        }
+        err /= J;
+        if (per_sample) per_sample[b] = (float)err;
+        total += err;
+    }
+    return (float)(total / B);
+}

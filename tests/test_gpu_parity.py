@@ -376,3 +376,23 @@ def test_regression_head_matches_fp32_reference(pose):
         assert got.shape == (256, 17, 3) and got.dtype == torch.float32
         err = (got - ref).abs().max().item()
         assert err < 3e-2 * max(1.0, ref.abs().max().item()), err
+
+
+def test_eval_metrics_match_the_reference(pose, oracle, golden):
+    """MPJPE / PA-MPJPE on the device (one thread per sample, closed-form 3x3 SVD) vs the live reference's values and the
+    C oracle, incl. the reflection, similarity-transform, identical-pose and collapsed-prediction cases; 1e-3 relative."""
+    d = golden("metrics.npz")
+    pred, gt = torch.from_numpy(d["pred"]).cuda(), torch.from_numpy(d["gt"]).cuda()
+    means, per = pose.utils.eval_metrics(pred, gt)
+    assert abs(means[0].item() - float(d["mpjpe"])) < 1e-3 * float(d["mpjpe"])
+    assert abs(means[1].item() - float(d["pa_mpjpe"])) < 1e-3 * float(d["pa_mpjpe"])
+    assert np.allclose(per[1].cpu().numpy(), d["pa_per_sample"], rtol=1e-4, atol=2e-3)
+    assert abs(pose.utils.compute_pa_mpjpe(pred, gt).item() - oracle.pa_mpjpe(d["pred"], d["gt"])) < 1e-2
+    # a large seeded batch against the oracle
+    rng = np.random.default_rng(3)
+    g2 = rng.normal(0, 300, (4096, 17, 3)).astype(np.float32)
+    p2 = (g2 + rng.normal(0, 80, g2.shape)).astype(np.float32)
+    m2, per2 = pose.utils.eval_metrics(torch.from_numpy(p2).cuda(), torch.from_numpy(g2).cuda())
+    mo, pero = oracle.pa_mpjpe(p2, g2, per_sample=True)
+    assert np.allclose(per2[1].cpu().numpy(), pero, rtol=1e-4, atol=1e-3)
+    assert abs(m2[0].item() - oracle.mpjpe(p2, g2)) < 1e-3 and abs(m2[1].item() - mo) < 1e-3

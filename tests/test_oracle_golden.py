@@ -101,3 +101,14 @@ def test_model_config_defaults_match_reference(golden):
     import pytest
     with pytest.raises(ValueError):
         mc.ModelConfig("rnn")
+
+
+def test_metrics_oracle_matches_live_reference(oracle, golden):
+    """compute_mpjpe / compute_pa_mpjpe (src/utils.py:55-165) incl. the mirrored, similarity, identical and collapsed poses."""
+    d = golden("metrics.npz")
+    assert abs(oracle.mpjpe(d["pred"], d["gt"]) - float(d["mpjpe"])) < 1e-3
+    m, per = oracle.pa_mpjpe(d["pred"], d["gt"], per_sample=True)
+    assert abs(m - float(d["pa_mpjpe"])) < 1e-3
+    assert np.allclose(per, d["pa_per_sample"], rtol=1e-5, atol=1e-3)
+    # the reference's rotation convention: a pose rotated about z by +0.7 rad (sample 2) is NOT perfectly re-aligned
+    assert per[2] > 100.0 and per[3] < 1e-3
