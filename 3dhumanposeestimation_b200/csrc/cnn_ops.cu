@@ -115,79 +115,153 @@ struct DwTile {
     static constexpr int kSmem = IH * IW * kDwSlab * 2;
 };
 
-template <int STRIDE, int ACT>
-__global__ void __launch_bounds__(256)
-dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ Wd, const float *__restrict__ bias,
-                 int H, int W, int C, __nv_bfloat16 *__restrict__ Y, float *__restrict__ pool, int Ho, int Wo,
-                 int tiles_x, int tiles_y) {
+// Stages the halo tile of (image b, tile) x 64-channel slab with 16-byte asynchronous copies (zero fill outside the image
+// or the channel range); one commit group per tile.
+template <int STRIDE>
+__device__ __forceinline__ void dw_stage_tile(unsigned char *buf, const __nv_bfloat16 *__restrict__ X, int H, int W, int C,
+                                              int b, int tile, int tiles_x, int c_slab) {
     using T = DwTile<STRIDE>;
-    __shared__ __align__(16) unsigned char s_in[T::kSmem];
-    __shared__ float s_part[32][kDwSlab];
-    const int tile = blockIdx.x % (tiles_x * tiles_y), b = blockIdx.x / (tiles_x * tiles_y);
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    const int oy0 = ty * T::TH, ox0 = tx * T::TW;
-    const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
-    const int c_slab = blockIdx.y * kDwSlab;
-    const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;       // 8 channel groups x 32 pixel lanes
-    const int c0 = c_slab + cg * 8;
-    const bool c_ok = c0 < C;
+    const int iy0 = ty * T::TH * STRIDE - 1, ix0 = tx * T::TW * STRIDE - 1;
     const __nv_bfloat16 *xb = X + (long)b * H * W * C;
-    // stage the halo tile: pixel-major, 128 B (64 channels) per pixel, zero outside the image / channel range
     for (int i = threadIdx.x; i < T::IH * T::IW * 8; i += 256) {
         const int px = i >> 3, g = i & 7;
         const int py = px / T::IW, pxx = px - py * T::IW;
         const int iy = iy0 + py, ix = ix0 + pxx;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W && c_slab + g * 8 < C)
-            v = __ldg((const uint4 *)(xb + ((long)iy * W + ix) * C + c_slab + g * 8));
-        *(uint4 *)(s_in + (px * 8 + g) * 16) = v;
+        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W && c_slab + g * 8 < C;
+        cp_async16(buf + (px * 8 + g) * 16, ok ? (const void *)(xb + ((long)iy * W + ix) * C + c_slab + g * 8) : (const void *)X, ok);
     }
-    float w[9][8], bs[8], psum[8];
+    cp_async_commit();
+}
+
+// PERSISTENT: a CTA walks (image, tile) pairs of its 64-channel slab; the next tile's halo is in flight (cp.async, second
+// buffer) while the current one is computed -- the one-tile-per-CTA version left every global-load latency exposed at
+// two CTAs per SM.
+template <int STRIDE, int ACT>
+__global__ void __launch_bounds__(256)
+dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ Wd, const float *__restrict__ bias,
+                 int B, int H, int W, int C, __nv_bfloat16 *__restrict__ Y, float *__restrict__ pool, int Ho, int Wo,
+                 int tiles_x, int tiles_y) {
+    using T = DwTile<STRIDE>;
+    extern __shared__ __align__(16) unsigned char s_dyn[];      // 2 halo buffers, then the pooled-sum scratch
+    unsigned char *bufs[2] = {s_dyn, s_dyn + T::kSmem};
+    float(*s_part)[kDwSlab] = (float(*)[kDwSlab])(s_dyn + 2 * T::kSmem);
+    const int per_img = tiles_x * tiles_y;
+    const long n_items = (long)B * per_img;
+    const int c_slab = blockIdx.y * kDwSlab;
+    const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;       // 8 channel groups x 32 pixel lanes
+    const int c0 = c_slab + cg * 8;
+    const bool c_ok = c0 < C;
+    float w[9][8], bs[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         bs[k] = c_ok ? __ldg(bias + c0 + k) : 0.f;
-        psum[k] = 0.f;
 #pragma unroll
         for (int t = 0; t < 9; ++t) w[t][k] = c_ok ? __ldg(Wd + (long)t * C + c0 + k) : 0.f;
     }
-    __syncthreads();
-    constexpr int kPix = T::TH * T::TW;
-#pragma unroll
-    for (int q = 0; q < kPix / 32; ++q) {
-        const int p = q * 32 + pl;
-        const int py = p / T::TW, pxx = p - py * T::TW;
-        const int oy = oy0 + py, ox = ox0 + pxx;
-        float acc[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = bs[k];
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                float f[8];
-                unpack8(*(const uint4 *)(s_in + (((py * STRIDE + ky) * T::IW + pxx * STRIDE + kx) * 8 + cg) * 16), f);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], w[ky * 3 + kx][k], acc[k]);
-            }
-        if (oy < Ho && ox < Wo && c_ok) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                acc[k] = act_t<ACT>(acc[k]);
-                psum[k] += acc[k];
-            }
-            *(uint4 *)(Y + (((long)b * Ho + oy) * Wo + ox) * C + c0) = pack8(acc);
-        }
-    }
-    if (pool != nullptr) {  // fixed-order reduction over the 32 pixel lanes of the CTA, one write per channel
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s_part[pl][cg * 8 + k] = psum[k];
+    long item = blockIdx.x;
+    if (item < n_items) dw_stage_tile<STRIDE>(bufs[0], X, H, W, C, (int)(item / per_img), (int)(item % per_img), tiles_x, c_slab);
+    for (int it = 0; item < n_items; item += gridDim.x, ++it) {
+        const long next = item + gridDim.x;
+        if (next < n_items)
+            dw_stage_tile<STRIDE>(bufs[(it + 1) & 1], X, H, W, C, (int)(next / per_img), (int)(next % per_img), tiles_x, c_slab);
+        else
+            cp_async_commit();
+        cp_async_wait<1>();
         __syncthreads();
-        if (threadIdx.x < kDwSlab && c_slab + threadIdx.x < C) {
-            float t = 0.f;
-#pragma unroll 8
-            for (int q = 0; q < 32; ++q) t += s_part[q][threadIdx.x];
-            pool[((long)b * (tiles_x * tiles_y) + tile) * C + c_slab + threadIdx.x] = t;
+        const unsigned char *s_in = bufs[it & 1];
+        const int b = (int)(item / per_img), tile = (int)(item - (long)b * per_img);
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int oy0 = ty * T::TH, ox0 = tx * T::TW;
+        float psum[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) psum[k] = 0.f;
+        constexpr int kPix = T::TH * T::TW;
+        if (STRIDE == 1) {
+            // a thread owns a column of 4 output rows, two at a time: the 4 x 3 input vectors of a pair are read once and
+            // feed both outputs (24 shared-memory loads per 4 outputs instead of 36: the kernel is shared-memory bound)
+            const int pxx = pl & (T::TW - 1), rb = pl / T::TW;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int r0 = rb * 4 + q * 2;
+                float a0[8], a1[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a0[k] = a1[k] = bs[k];
+#pragma unroll
+                for (int ir = 0; ir < 4; ++ir)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        float f[8];
+                        unpack8(*(const uint4 *)(s_in + (((r0 + ir) * T::IW + pxx + kx) * 8 + cg) * 16), f);
+                        if (ir < 3) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) a0[k] = fmaf(f[k], w[ir * 3 + kx][k], a0[k]);
+                        }
+                        if (ir > 0) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) a1[k] = fmaf(f[k], w[(ir - 1) * 3 + kx][k], a1[k]);
+                        }
+                    }
+                const int ox = ox0 + pxx;
+                if (ox < Wo && c_ok) {
+                    if (oy0 + r0 < Ho) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            a0[k] = act_t<ACT>(a0[k]);
+                            psum[k] += a0[k];
+                        }
+                        *(uint4 *)(Y + (((long)b * Ho + oy0 + r0) * Wo + ox) * C + c0) = pack8(a0);
+                    }
+                    if (oy0 + r0 + 1 < Ho) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            a1[k] = act_t<ACT>(a1[k]);
+                            psum[k] += a1[k];
+                        }
+                        *(uint4 *)(Y + (((long)b * Ho + oy0 + r0 + 1) * Wo + ox) * C + c0) = pack8(a1);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+        for (int q = 0; q < kPix / 32; ++q) {
+            const int p = q * 32 + pl;
+            const int py = p / T::TW, pxx = p - py * T::TW;
+            const int oy = oy0 + py, ox = ox0 + pxx;
+            float acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = bs[k];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    float f[8];
+                    unpack8(*(const uint4 *)(s_in + (((py * STRIDE + ky) * T::IW + pxx * STRIDE + kx) * 8 + cg) * 16), f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], w[ky * 3 + kx][k], acc[k]);
+                }
+            if (oy < Ho && ox < Wo && c_ok) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    acc[k] = act_t<ACT>(acc[k]);
+                    psum[k] += acc[k];
+                }
+                *(uint4 *)(Y + (((long)b * Ho + oy) * Wo + ox) * C + c0) = pack8(acc);
+            }
         }
+        }
+        if (pool != nullptr) {  // fixed-order reduction over the 32 pixel lanes of the CTA, one write per channel
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s_part[pl][cg * 8 + k] = psum[k];
+            __syncthreads();
+            if (threadIdx.x < kDwSlab && c_slab + threadIdx.x < C) {
+                float t = 0.f;
+#pragma unroll 8
+                for (int q = 0; q < 32; ++q) t += s_part[q][threadIdx.x];
+                pool[((long)b * per_img + tile) * C + c_slab + threadIdx.x] = t;
+            }
+        }
+        __syncthreads();     // the buffer just read is the target of the copies issued in the next iteration
     }
 }
 
@@ -450,12 +524,25 @@ POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, cons
     if (pool_sum != nullptr && pool_parts != parts) return POSE_E_SHAPE;  // pool_sum is [B, parts, C]
     const int th = stride == 1 ? DwTile<1>::TH : DwTile<2>::TH, tw = stride == 1 ? DwTile<1>::TW : DwTile<2>::TW;
     const int tiles_y = (Ho + th - 1) / th, tiles_x = (Wo + tw - 1) / tw;
-    dim3 grid(B * tiles_x * tiles_y, (C + kDwSlab - 1) / kDwSlab);
+    const int gy = (C + kDwSlab - 1) / kDwSlab;
+    long gx = (long)B * tiles_x * tiles_y;
+    const long cap = ((long)kNumSMs * 4 + gy - 1) / gy;           // ~4 resident CTAs per SM over all channel slabs
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, gy);
     cudaStream_t s = (cudaStream_t)stream;
     if (act < 0 || act > 4) return POSE_E_UNSUPPORTED;
+    const int smem = 2 * (stride == 1 ? DwTile<1>::kSmem : DwTile<2>::kSmem) + 32 * kDwSlab * 4;
 #define DW_LAUNCH(S_, A_)                                                                                             \
-    dwconv3x3_kernel<S_, A_><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)X, Wd, bias, H, W, C, (__nv_bfloat16 *)Y, pool_sum, \
-                                                  Ho, Wo, tiles_x, tiles_y)
+    {                                                                                                                 \
+        static bool cfg = false;                                                                                      \
+        if (!cfg) {                                                                                                   \
+            cudaError_t ce = cudaFuncSetAttribute(dwconv3x3_kernel<S_, A_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+            if (ce != cudaSuccess) return (int)ce;                                                                    \
+            cfg = true;                                                                                               \
+        }                                                                                                             \
+        dwconv3x3_kernel<S_, A_><<<grid, 256, smem, s>>>((const __nv_bfloat16 *)X, Wd, bias, B, H, W, C, (__nv_bfloat16 *)Y, \
+                                                         pool_sum, Ho, Wo, tiles_x, tiles_y);                         \
+    }
 #define DW_ACT(S_)                                                                                                    \
     switch (act) {                                                                                                    \
         case 0: DW_LAUNCH(S_, 0); break;                                                                              \

@@ -38,6 +38,16 @@ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t i, uint32_t th
 }
 inline uint32_t drop_threshold(float p) { return (uint32_t)((double)p * 4294967296.0); }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); `valid == false` writes zeros (padding) without touching memory
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // streaming 128-bit store: outputs are written once and not re-read by the producing kernel
 __device__ __forceinline__ void st_stream_f4(float *p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
