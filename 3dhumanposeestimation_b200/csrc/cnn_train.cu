@@ -129,7 +129,24 @@ bn_stats_kernel(const __nv_bfloat16 *__restrict__ Y, long M, int C, long ld, flo
     float acc[2][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
-    for (long r = (long)blockIdx.x * rm.rpb + rm.rsub; r < M; r += (long)gridDim.x * rm.rpb) {
+    const long step = (long)gridDim.x * rm.rpb;
+    long r = (long)blockIdx.x * rm.rpb + rm.rsub;
+    for (; r + 3 * step < M; r += 4 * step) {           // four independent 16-byte loads in flight per thread
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg((const uint4 *)(Y + (r + u * step) * ld + rm.c0));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float y[8];
+            up8(v[u], y);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[0][j] += y[j];
+                acc[1][j] = fmaf(y[j], y[j], acc[1][j]);
+            }
+        }
+    }
+    for (; r < M; r += step) {
         float y[8];
         up8(__ldg((const uint4 *)(Y + r * ld + rm.c0)), y);
 #pragma unroll
@@ -141,23 +158,23 @@ bn_stats_kernel(const __nv_bfloat16 *__restrict__ Y, long M, int C, long ld, flo
     rowmap_fold<2, false>(rm, C, acc, partials, (long)blockIdx.x * 2 * C);
 }
 
-// Second stage of the two-stage reductions: block = 32 channels x 8 part lanes; every lane adds its share of the
-// per-block partials in a fixed order (4 independent accumulators), shared memory folds the 8 lanes in a fixed order.
-// Returns the two totals to the threads with part lane 0 (tid < 32).
+// Second stage of the two-stage reductions: block = 8 channels x 32 part lanes; every lane adds its share of the
+// per-block partials in a fixed order (4 independent accumulators), shared memory folds the 32 lanes in a fixed order.
+// Returns the two totals to the threads with part lane 0 (tid < 8).
 __device__ __forceinline__ void fold_parts(const float *__restrict__ partials, int parts, int C, int c, float &s1, float &s2) {
-    __shared__ float red[2][8][33];
-    const int pl = threadIdx.x >> 5, cl = threadIdx.x & 31;
+    __shared__ float red[2][32][9];
+    const int pl = threadIdx.x >> 3, cl = threadIdx.x & 7;      // 32 part lanes x 8 channels
     float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < C) {
         int q = pl;
-        for (; q + 24 < parts; q += 32) {
+        for (; q + 96 < parts; q += 128) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                a[u] += partials[(long)(q + 8 * u) * 2 * C + c];
-                b[u] += partials[(long)(q + 8 * u) * 2 * C + C + c];
+                a[u] += partials[(long)(q + 32 * u) * 2 * C + c];
+                b[u] += partials[(long)(q + 32 * u) * 2 * C + C + c];
             }
         }
-        for (; q < parts; q += 8) {
+        for (; q < parts; q += 32) {
             a[0] += partials[(long)q * 2 * C + c];
             b[0] += partials[(long)q * 2 * C + C + c];
         }
@@ -168,22 +185,22 @@ __device__ __forceinline__ void fold_parts(const float *__restrict__ partials, i
     s1 = s2 = 0.f;
     if (pl == 0)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 32; ++q) {
             s1 += red[0][q][cl];
             s2 += red[1][q][cl];
         }
 }
 
 // partials [parts, 2, C] -> mean_rstd [2, C], scale_shift [2, C] (z = y * scale + shift), running statistics (momentum,
-// unbiased variance).  grid = ceil(C / 32), 256 threads.
+// unbiased variance).  grid = ceil(C / 8), 256 threads.
 __global__ void __launch_bounds__(256)
 bn_finalize_kernel(const float *__restrict__ partials, int parts, float count, const float *__restrict__ gamma,
                    const float *__restrict__ beta, float eps, float momentum, int C, float *__restrict__ mean_rstd,
                    float *__restrict__ scale_shift, float *__restrict__ running_mean, float *__restrict__ running_var) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int c = blockIdx.x * 8 + (threadIdx.x & 7);
     float s1, s2;
     fold_parts(partials, parts, C, c, s1, s2);
-    if (threadIdx.x < 32 && c < C) {
+    if (threadIdx.x < 8 && c < C) {
         const float mean = s1 / count;
         const float var = fmaxf(s2 / count - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
@@ -240,16 +257,28 @@ bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dA, long ld_da, const __n
     float acc[2][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
-    for (long r = (long)blockIdx.x * rm.rpb + rm.rsub; r < M; r += (long)gridDim.x * rm.rpb) {
+    const long step = (long)gridDim.x * rm.rpb;
+    long r = (long)blockIdx.x * rm.rpb + rm.rsub;
+    auto body = [&](const uint4 &vy, const uint4 &vd) {
         float y[8], d[8];
-        up8(__ldg((const uint4 *)(Y + r * C + rm.c0)), y);
-        up8(__ldg((const uint4 *)(dA + r * ld_da + rm.c0)), d);
+        up8(vy, y);
+        up8(vd, d);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float dz = d[j] * out_scale * dactf<ACT>(fmaf(y[j], a[j], b[j]));
             acc[0][j] += dz;
             acc[1][j] = fmaf(dz, fmaf(y[j], rs[j], -mr[j]), acc[1][j]);
         }
+    };
+    for (; r + step < M; r += 2 * step) {               // two rows = four independent 16-byte loads in flight per thread
+        const uint4 y0 = __ldg((const uint4 *)(Y + r * C + rm.c0)), d0 = __ldg((const uint4 *)(dA + r * ld_da + rm.c0));
+        const uint4 y1 = __ldg((const uint4 *)(Y + (r + step) * C + rm.c0)), d1 = __ldg((const uint4 *)(dA + (r + step) * ld_da + rm.c0));
+        body(y0, d0);
+        body(y1, d1);
+    }
+    for (; r < M; r += step) {
+        const uint4 y0 = __ldg((const uint4 *)(Y + r * C + rm.c0)), d0 = __ldg((const uint4 *)(dA + r * ld_da + rm.c0));
+        body(y0, d0);
     }
     rowmap_fold<2, false>(rm, C, acc, partials, (long)blockIdx.x * 2 * C);
 }
@@ -260,10 +289,10 @@ __global__ void __launch_bounds__(256)
 bn_bwd_coef_kernel(const float *__restrict__ partials, int parts, float inv_m, const float *__restrict__ scale_shift,
                    const float *__restrict__ mean_rstd, int C, float *__restrict__ coef, float *__restrict__ dgamma,
                    float *__restrict__ dbeta) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int c = blockIdx.x * 8 + (threadIdx.x & 7);
     float s1, s2;
     fold_parts(partials, parts, C, c, s1, s2);
-    if (threadIdx.x < 32 && c < C) {
+    if (threadIdx.x < 8 && c < C) {
         dgamma[c] += s2;
         dbeta[c] += s1;
         const float a = scale_shift[c], mean = mean_rstd[c], rstd = mean_rstd[C + c];
@@ -871,7 +900,7 @@ POSE_API int pose_bn_finalize(const float *partials, long cap_floats, long count
                               float *running_var, pose_stream_t stream) {
     REQ(partials && gamma && beta && mean_rstd && scale_shift, POSE_E_NULL);
     REQ(count > 0 && C > 0, POSE_E_SHAPE);
-    bn_finalize_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, bn_parts(count, C, cap_floats), (float)count,
+    bn_finalize_kernel<<<(C + 7) / 8, 256, 0, (cudaStream_t)stream>>>(partials, bn_parts(count, C, cap_floats), (float)count,
                                                                          gamma, beta, eps, momentum, C, mean_rstd, scale_shift,
                                                                          running_mean, running_var);
     return launch_status();
@@ -907,7 +936,7 @@ POSE_API int pose_bn_bwd_bf16(const void *dA, long ld_da, const void *Y, long M,
 #define BN_BWD(A_)                                                                                                     \
     bn_bwd_reduce_kernel<A_><<<parts, thr, 0, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, M, C,     \
                                                   scale_shift, mean_rstd, out_scale, partials);                        \
-    bn_bwd_coef_kernel<<<(C + 31) / 32, 256, 0, s>>>(partials, parts, 1.0f / (float)M, scale_shift, mean_rstd, C, coef,    \
+    bn_bwd_coef_kernel<<<(C + 7) / 8, 256, 0, s>>>  (partials, parts, 1.0f / (float)M, scale_shift, mean_rstd, C, coef,    \
                                                       dgamma, dbeta);                                                  \
     bn_bwd_apply_kernel<A_><<<rowmap_grid(M, C, 4), thr, 0, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, M, \
                                                                 C, scale_shift, coef, out_scale, (__nv_bfloat16 *)dY)
