@@ -21,6 +21,12 @@ namespace pose {
 constexpr int kAttnThreads = 128;
 constexpr float kLog2e = 1.4426950408889634f;
 
+__device__ __forceinline__ float ex2_approx(float x) {      // one MUFU.EX2 (exp2f without -use_fast_math is a multi-instruction sequence)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // rows of 128 B (one token's head slice, zero padded to 64 elements), 16-byte chunks XOR-swizzled by (row & 7):
@@ -112,48 +118,61 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     uint64_t *bar;
     const uint32_t tmem = attn_prologue(smem, bar);
     AttnSync sync{bar, 0, 0};
-    unsigned char *Qs = smem, *Ks = Qs + 16384, *Vs = Ks + 288 * 128, *Ps = Vs + 288 * 128;   // P: 5 blocks of 16 KB
+    unsigned char *Qb[2] = {smem, smem + 16384};                                  // double-buffered query tiles
+    unsigned char *Ks = smem + 32768, *Vs = Ks + 288 * 128, *Ps = Vs + 288 * 128;  // P: 5 blocks of 16 KB
     const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
-    const int warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5, r = threadIdx.x;
     __nv_bfloat16 *og = O + b * bso + (long)h * HD;
     const float sl2 = scale * kLog2e;
     const uint32_t tO = tmem + 320;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const int nch = (Nkp + 31) / 32;
-    for (int q0 = 0; q0 < Nq; q0 += 128) {
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(bar + 1, 4 * kBoxRows * 128 + (q0 == 0 ? 2 * box_bytes(Nkp) : 0));
-            if (q0 == 0) {
-                tma_rows(Ks, &mapK, bar + 1, h * HD, 0, b, Nkp);
-                tma_rows(Vs, &mapV, bar + 1, h * HD, 0, b, Nkp);
-            }
-            tma_rows(Qs, &mapQ, bar + 1, h * HD, q0, b, 128);
-        }
-        sync.wait_loads();
-        if (threadIdx.x == 0) {
-            const uint64_t da = umma_desc_k<128>(smem_u32(Qs));
-            for (int kc0 = 0; kc0 < Nkp; kc0 += 256) {
-                const int n = min(256, Nkp - kc0);
-                const uint32_t idesc = umma_idesc_bf16(128, n);
-                const uint64_t db = umma_desc_k<128>(smem_u32(Ks + kc0 * 128));
+
+    auto issue_s = [&](const unsigned char *Qs) {      // S = Q K^T into TMEM columns [0, Nkp)   (thread 0)
+        const uint64_t da = umma_desc_k<128>(smem_u32(Qs));
+        for (int kc0 = 0; kc0 < Nkp; kc0 += 256) {
+            const int n = min(256, Nkp - kc0);
+            const uint32_t idesc = umma_idesc_bf16(128, n);
+            const uint64_t db = umma_desc_k<128>(smem_u32(Ks + kc0 * 128));
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tmem + kc0, da + 2 * k, db + 2 * k, idesc, k ? 1u : 0u);
-            }
+            for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tmem + kc0, da + 2 * k, db + 2 * k, idesc, k ? 1u : 0u);
         }
-        sync.commit_and_wait();
-        const int r = threadIdx.x;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    };
+
+    // prologue: K, V and the first query tile; S(0)
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar + 1, 4 * kBoxRows * 128 + 2 * box_bytes(Nkp));
+        tma_rows(Ks, &mapK, bar + 1, h * HD, 0, b, Nkp);
+        tma_rows(Vs, &mapV, bar + 1, h * HD, 0, b, Nkp);
+        tma_rows(Qb[0], &mapQ, bar + 1, h * HD, 0, b, 128);
+    }
+    sync.wait_loads();
+    if (threadIdx.x == 0) issue_s(Qb[0]);
+    sync.commit_and_wait();
+
+    // steady state, ONE tensor-core round trip per query tile: after the softmax of tile i, O(i) = P V and S(i+1) are issued
+    // together; the next query tile streams in (TMA) during the softmax
+    for (int i = 0, q0 = 0; q0 < Nq; ++i, q0 += 128) {
+        const bool has_next = q0 + 128 < Nq;
+        if (threadIdx.x == 0 && has_next) {
+            mbar_expect_tx(bar + 1, 4 * kBoxRows * 128);
+            tma_rows(Qb[(i + 1) & 1], &mapQ, bar + 1, h * HD, q0 + 128, b, 128);
+        }
         float inv = 0.f;
         if (q0 + warp * 32 < Nq) {                       // warps whose 32 rows are all padding skip the softmax
-            float m = -INFINITY;
-            for (int c = 0; c < nch; ++c) {
+            // A thread owns one row and there is one warp per scheduler: every dependent chain is exposed, so the row
+            // maximum and the row sum run on four independent accumulators and only the last (partial) chunk is masked.
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            for (int c = 0; c < nch; ++c) {              // (kept compact: one warp per scheduler also exposes i-cache misses)
                 uint32_t v[32];
                 tmem_ld32(trow + c * 32, v);
+                const int lim = Nk - c * 32;             // columns of this chunk that are real keys
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c * 32 + j < Nk) m = fmaxf(m, __uint_as_float(v[j]));
+                for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], j < lim ? __uint_as_float(v[j]) : -INFINITY);
             }
+            const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             const float ms = m * sl2;
-            float sum = 0.f;
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
             for (int c = 0; c < nch; ++c) {
                 uint32_t v[32];
                 tmem_ld32(trow + c * 32, v);
@@ -163,8 +182,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int col = c * 32 + j8 * 8 + j;
-                        p[j] = col < Nk ? exp2f(fmaf(__uint_as_float(v[j8 * 8 + j]), sl2, -ms)) : 0.f;
-                        sum += p[j];
+                        p[j] = col < Nk ? ex2_approx(fmaf(__uint_as_float(v[j8 * 8 + j]), sl2, -ms)) : 0.f;
+                        s4[j & 3] += p[j];
                         // attention-weight dropout (nn.MultiheadAttention(dropout=p)): the row still normalises by the full sum
                         if (drop_thresh)
                             p[j] = drop_keep(drop_seed, (((unsigned long long)b * heads + h) * Nq + q0 + r) * Nk + col, drop_thresh)
@@ -176,12 +195,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
                                                                   pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7])));
                 }
             }
+            const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
             inv = 1.0f / sum;
             if (lse != nullptr && q0 + r < Nq) lse[((long)b * heads + h) * Nq + q0 + r] = m * scale + __logf(sum);
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        if (has_next) sync.wait_loads();
         if (threadIdx.x == 0) {
             tc_fence_after();
             constexpr uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
@@ -190,6 +211,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
                 const uint64_t db = umma_desc_mn(smem_u32(Vs + ks * 2048), 1024);
                 tc_mma_f16(tO, da, db, idesc, ks ? 1u : 0u);
             }
+            if (has_next) issue_s(Qb[(i + 1) & 1]);
         }
         sync.commit_and_wait();
         if (q0 + warp * 32 < Nq) {                       // warp-uniform: tcgen05.ld is a warp-collective instruction
@@ -295,7 +317,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int col = kc0 + c * 32 + j8 * 8 + j;
-                            const float pr = (col < Nk && row_ok) ? exp2f(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -l2)) : 0.f;
+                            const float pr = (col < Nk && row_ok) ? ex2_approx(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -l2)) : 0.f;
                             float dp = __uint_as_float(p[j8 * 8 + j]);
                             if (drop_thresh)
                                 dp = drop_keep(drop_seed, (((unsigned long long)b * heads + h) * Nq + q0 + r) * Nk + col, drop_thresh)
@@ -411,7 +433,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int col = c * 32 + j8 * 8 + j;                  // query within the tile
-                        const float pr = col < rows ? exp2f(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -lse_s[col])) : 0.f;
+                        const float pr = col < rows ? ex2_approx(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -lse_s[col])) : 0.f;
                         float keep = 1.0f;
                         if (drop_thresh)
                             keep = drop_keep(drop_seed, (((unsigned long long)b * heads + h) * Nq + q0 + col) * Nk + k0 + r, drop_thresh)
@@ -473,7 +495,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
     attn_epilogue(tmem);
 }
 
-constexpr int kFwdSmem = 16384 + 2 * 288 * 128 + 5 * 16384 + 1024;
+constexpr int kFwdSmem = 2 * 16384 + 2 * 288 * 128 + 5 * 16384 + 1024;
 constexpr int kDqSmem = 2 * 16384 + 2 * 288 * 128 + 2 * 16384 + 1024;
 constexpr int kDkvSmem = 4 * 16384 + 2 * 32768 + 1024;
 

@@ -68,14 +68,15 @@ struct ConvGeom {          // MODE 1 only
     int cchunks;           // Cin_pad / BKC
 };
 
-template <int BN, int kStages, int BKC>
+template <int BN, int kStages, int BKC, int TMA_EPI = 0>
 struct GemmSmem {
     static constexpr int kABytes = BM * BKC * 2, kBBytes = BN * BKC * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarrierBytes = 1024;                   // keeps the staging buffers 1024 B aligned (TMA swizzle)
     static constexpr int kStagePitch = 144;                      // 32 fp32 + 16 B pad: conflict-free 16 B accesses
-    static constexpr int kWarpStaging = 5120;                    // per epilogue warp: 32 x 32 fp32 transpose buffer (4608 B), or
-                                                                 // two 32 x 32 bf16 TMA tiles (output at +0, auxiliary at +2048)
+    // per epilogue warp: a 32 x 32 fp32 transpose buffer (4608 B), or two 32 x 32 bf16 TMA tiles (output at +0,
+    // auxiliary at +2048); the smaller TMA staging leaves room for one more pipeline stage
+    static constexpr int kWarpStaging = TMA_EPI ? 4096 : 5120;
     static constexpr int kStagingBytes = 16 * kWarpStaging;
     static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + kStagingBytes + 1024;  // + alignment slack
     static_assert(kStageBytes % 1024 == 0, "stage bases must stay 1024 B aligned");
@@ -399,7 +400,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_aux,
                     const __grid_constant__ CUtensorMap map_pre, int M, int N, int K, const Epilogue ep, const ConvGeom cg,
                     int m_tiles, int n_tiles, int kb_per, int k_splits) {
-    using S = GemmSmem<BN, kStages, BKC>;
+    using S = GemmSmem<BN, kStages, BKC, TMA_EPI>;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);  // swizzle atoms: 1024 B
     unsigned char *bars = smem + kStages * S::kStageBytes;
@@ -726,24 +727,30 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
     // row stores compete with the operand loads for the TMA / L2 path that already bounds the 128 x 128 main loop.
     ep.tma = 0;
     static const bool tma_off = getenv("POSE_NO_TMA_EPILOGUE") != nullptr;     // A/B switch for measurements
-    const bool heavy = ep.act == 3 || ep.act >= 5 || ep.preact != nullptr;
+    static const bool tma_all = getenv("POSE_TMA_EPILOGUE_ALL") != nullptr;    // measurements: TMA path for every bf16 GEMM
+    const bool heavy = ep.act == 3 || ep.act >= 5 || ep.preact != nullptr || tma_all;
     if (MODE == 0 && BN <= 128 && ep.out_bf16 && !ep.accumulate && ep.vec && N % 32 == 0 && heavy && !tma_off) {
         int e = make_map_tile32(&mc, ep.C, M, N, ep.ldc);
         if (!e && ep.residual) e = make_map_tile32(&maux, ep.residual, M, N, ep.ldr);
         if (!e && ep.preact) e = make_map_tile32(&mpre, ep.preact, M, N, ep.ldc);
         ep.tma = e ? 0 : 1;
     }
-    using S = GemmSmem<BN, kStages, BKC>;
+    constexpr int kTma = (MODE == 0 && BN <= 128) ? 1 : 0;
+    constexpr int kStagesT = (kTma && BN == 128) ? kStages + 1 : kStages;      // 5 x 32 KB stages fit beside the TMA staging
+    using S0 = GemmSmem<BN, kStages, BKC, 0>;
+    using S1 = GemmSmem<BN, kStagesT, BKC, kTma>;
+    static_assert(S0::kTotal <= 232448 && S1::kTotal <= 232448, "shared memory budget");
     auto kern_plain = gemm_bf16_tn_kernel<BN, kStages, BKC, MODE, A_MN, B_MN, 0>;
-    auto kern_tma = gemm_bf16_tn_kernel<BN, kStages, BKC, MODE, A_MN, B_MN, (MODE == 0 && BN <= 128) ? 1 : 0>;
+    auto kern_tma = gemm_bf16_tn_kernel<BN, kStagesT, BKC, MODE, A_MN, B_MN, kTma>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t ce = cudaFuncSetAttribute(kern_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+        cudaError_t ce = cudaFuncSetAttribute(kern_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, S0::kTotal);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, S1::kTotal);
         if (ce != cudaSuccess) return (int)ce;
         configured = true;
     }
     auto kern = ep.tma ? kern_tma : kern_plain;
+    const int smem_bytes = ep.tma ? S1::kTotal : S0::kTotal;
     const int n_tiles = (N + BN - 1) / BN;
     const int num_kb = (K + BKC - 1) / BKC;
     if (k_splits < 1) k_splits = 1;
@@ -752,7 +759,7 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
     k_splits = (num_kb + kb_per - 1) / kb_per;            // no empty split
     const long total = (long)m_tiles * n_tiles * k_splits;
     const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-    kern<<<grid, kGemmThreadsP, S::kTotal, s>>>(ma, mw, mc, maux, mpre, M, N, K, ep, cg, m_tiles, n_tiles, kb_per, k_splits);
+    kern<<<grid, kGemmThreadsP, smem_bytes, s>>>(ma, mw, mc, maux, mpre, M, N, K, ep, cg, m_tiles, n_tiles, kb_per, k_splits);
     return launch_status();
 }
 
