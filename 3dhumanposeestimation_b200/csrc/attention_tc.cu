@@ -18,7 +18,7 @@
 
 namespace pose {
 
-constexpr int kAttnThreads = 128;
+constexpr int kAttnThreads = 256;     // two warps per TMEM lane quarter: they split the column chunks of the elementwise phases
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {      // one MUFU.EX2 (exp2f without -use_fast_math is a multi-instruction sequence)
@@ -121,11 +121,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     unsigned char *Qb[2] = {smem, smem + 16384};                                  // double-buffered query tiles
     unsigned char *Ks = smem + 32768, *Vs = Ks + 288 * 128, *Ps = Vs + 288 * 128;  // P: 5 blocks of 16 KB
     const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
-    const int warp = threadIdx.x >> 5, r = threadIdx.x;
+    const int warp = threadIdx.x >> 5, quarter = warp & 3, grp = warp >> 2;
+    const int r = quarter * 32 + (threadIdx.x & 31);              // this thread's query row (shared by its twin in the other group)
+    __shared__ float red_m[2][128], red_s[2][128];
     __nv_bfloat16 *og = O + b * bso + (long)h * HD;
     const float sl2 = scale * kLog2e;
     const uint32_t tO = tmem + 320;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
     const int nch = (Nkp + 31) / 32;
 
     auto issue_s = [&](const unsigned char *Qs) {      // S = Q K^T into TMEM columns [0, Nkp)   (thread 0)
@@ -158,22 +160,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
             mbar_expect_tx(bar + 1, 4 * kBoxRows * 128);
             tma_rows(Qb[(i + 1) & 1], &mapQ, bar + 1, h * HD, q0 + 128, b, 128);
         }
-        float inv = 0.f;
-        if (q0 + warp * 32 < Nq) {                       // warps whose 32 rows are all padding skip the softmax
-            // A thread owns one row and there is one warp per scheduler: every dependent chain is exposed, so the row
-            // maximum and the row sum run on four independent accumulators and only the last (partial) chunk is masked.
-            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            for (int c = 0; c < nch; ++c) {              // (kept compact: one warp per scheduler also exposes i-cache misses)
+        const bool live = q0 + quarter * 32 < Nq;        // warps whose 32 rows are all padding skip the softmax
+        // A thread owns one row and there are two warps per scheduler: every dependent chain is exposed, so the row maximum
+        // and the row sum run on four independent accumulators; the two warps of a lane quarter take alternate 32-column
+        // chunks and meet through shared memory.  (Kept compact: i-cache misses are exposed too.)
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (live)
+            for (int c = grp; c < nch; c += 2) {
                 uint32_t v[32];
                 tmem_ld32(trow + c * 32, v);
                 const int lim = Nk - c * 32;             // columns of this chunk that are real keys
 #pragma unroll
                 for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], j < lim ? __uint_as_float(v[j]) : -INFINITY);
             }
-            const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-            const float ms = m * sl2;
-            float s4[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int c = 0; c < nch; ++c) {
+        red_m[grp][r] = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        __syncthreads();
+        const float m = fmaxf(red_m[0][r], red_m[1][r]);
+        const float ms = m * sl2;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (live)
+            for (int c = grp; c < nch; c += 2) {
                 uint32_t v[32];
                 tmem_ld32(trow + c * 32, v);
 #pragma unroll
@@ -195,10 +201,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
                                                                   pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7])));
                 }
             }
-            const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-            inv = 1.0f / sum;
-            if (lse != nullptr && q0 + r < Nq) lse[((long)b * heads + h) * Nq + q0 + r] = m * scale + __logf(sum);
-        }
+        red_s[grp][r] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -214,11 +217,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
             if (has_next) issue_s(Qb[(i + 1) & 1]);
         }
         sync.commit_and_wait();
-        if (q0 + warp * 32 < Nq) {                       // warp-uniform: tcgen05.ld is a warp-collective instruction
+        if (live) {                                      // warp-uniform: tcgen05.ld is a warp-collective instruction
+            const float sum = red_s[0][r] + red_s[1][r];         // (written before the barrier that preceded the MMAs)
+            const float inv = 1.0f / sum;
+            if (grp == 0 && lse != nullptr && q0 + r < Nq) lse[((long)b * heads + h) * Nq + q0 + r] = m * scale + __logf(sum);
             uint32_t v[32];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                tmem_ld32(tO + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+            {
+                const int c = grp;                       // each group stores one 32-column half of the output row
+                tmem_ld32(tO + ((uint32_t)(quarter * 32) << 16) + c * 32, v);
                 if (q0 + r < Nq)
 #pragma unroll
                     for (int j8 = 0; j8 < 4; ++j8) {
@@ -254,12 +260,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     AttnSync sync{bar, 0, 0};
     unsigned char *Qs = smem, *dOs = Qs + 16384, *Ks = dOs + 16384, *Vs = Ks + 288 * 128, *dSs = Vs + 288 * 128;  // dS: 2 blocks
     const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
-    const int warp = threadIdx.x >> 5, r = threadIdx.x;
+    const int warp = threadIdx.x >> 5, quarter = warp & 3, grp = warp >> 2;
+    const int r = quarter * 32 + (threadIdx.x & 31);
     const __nv_bfloat16 *og = O + b * bso + (long)h * HD, *dog = dO + b * bsdo + (long)h * HD;
     __nv_bfloat16 *dqg = dQ + b * bsdq + (long)h * HD;
     const float sl2 = scale * kLog2e;
     const uint32_t tS = tmem, tP = tmem + 128, tQ = tmem + 256;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     for (int q0 = 0; q0 < Nq; q0 += 128) {
         if (threadIdx.x == 0) {
             mbar_expect_tx(bar + 1, 2 * 4 * kBoxRows * 128 + (q0 == 0 ? 2 * box_bytes(Nkp) : 0));
@@ -286,7 +293,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
                 }
             }
             const long idx = ((long)b * heads + h) * Nq + q0 + r;
-            Dout[idx] = Dr;
+            if (grp == 0) Dout[idx] = Dr;
             l2 = lse[idx] * kLog2e;
         }
         sync.wait_loads();
@@ -306,11 +313,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
                 for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tP, dd + 2 * k, dv + 2 * k, idesc, k ? 1u : 0u);
             }
             sync.commit_and_wait();
-            if (q0 + warp * 32 < Nq) {
-                for (int c = 0; c < (n + 31) / 32; ++c) {
+            if (q0 + quarter * 32 < Nq) {
+                for (int c = grp; c < (n + 31) / 32; c += 2) {   // the two warps of a lane quarter take alternate chunks
                     uint32_t s[32], p[32];
-                    tmem_ld32(tS + lane_off + c * 32, s);
-                    tmem_ld32(tP + lane_off + c * 32, p);
+                    tmem_ld32_nowait(tS + lane_off + c * 32, s);
+                    tmem_ld32_nowait(tP + lane_off + c * 32, p);
+                    tmem_wait_ld();
 #pragma unroll
                     for (int j8 = 0; j8 < 4; ++j8) {
                         float ds[8];
@@ -345,10 +353,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
             }
             sync.commit_and_wait();
         }
-        if (q0 + warp * 32 < Nq) {
+        if (q0 + quarter * 32 < Nq) {
             uint32_t v[32];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            {
+                const int c = grp;
                 tmem_ld32(tQ + lane_off + c * 32, v);
                 if (row_ok)
 #pragma unroll
@@ -382,51 +390,72 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
     uint64_t *bar;
     const uint32_t tmem = attn_prologue(smem, bar);
     AttnSync sync{bar, 0, 0};
-    unsigned char *Kt = smem, *Vt = Kt + 16384, *Qs = Vt + 16384, *dOs = Qs + 16384, *PT = dOs + 16384, *dST = PT + 32768;
-    __shared__ float lse_s[128], D_s[128];
+    unsigned char *Kt = smem, *Vt = Kt + 16384, *PT = Vt + 16384, *dST = PT + 32768;
+    unsigned char *Qb[2] = {dST + 32768, dST + 32768 + 32768}, *dOb[2] = {dST + 32768 + 16384, dST + 32768 + 32768 + 16384};
+    __shared__ float lse_b[2][128], D_b[2][128];          // double buffered with the query / dO tiles
     const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z, heads = gridDim.y;
-    const int warp = threadIdx.x >> 5, r = threadIdx.x;
+    const int warp = threadIdx.x >> 5, quarter = warp & 3, grp = warp >> 2;
+    const int r = quarter * 32 + (threadIdx.x & 31);
     const float sl2 = scale * kLog2e;
     const uint32_t tS = tmem, tP = tmem + 128, tV = tmem + 256, tK = tmem + 320;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const bool warp_ok = k0 + warp * 32 < Nk;
-    for (int q0 = 0; q0 < Nq; q0 += 128) {
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const bool warp_ok = k0 + quarter * 32 < Nk;
+
+    auto load_stats = [&](int buf, int q0) {               // log-sum-exp (exp2 units) and D of a query tile
+        if (threadIdx.x < 128) {
+            const int t = threadIdx.x;
+            const bool ok = q0 + t < Nq;
+            const long idx = ((long)b * heads + h) * Nq + q0 + t;
+            lse_b[buf][t] = ok ? lse[idx] * kLog2e : 0.f;
+            D_b[buf][t] = ok ? Dg[idx] : 0.f;
+        }
+    };
+    auto issue_st = [&](int buf, int np) {                 // S^T = K Q^T, dP^T = V dO^T   (thread 0)
+        const uint32_t idesc = umma_idesc_bf16(128, np);
+        const uint64_t dk = umma_desc_k<128>(smem_u32(Kt)), dv = umma_desc_k<128>(smem_u32(Vt));
+        const uint64_t dq = umma_desc_k<128>(smem_u32(Qb[buf])), dd = umma_desc_k<128>(smem_u32(dOb[buf]));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tS, dk + 2 * k, dq + 2 * k, idesc, k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tP, dv + 2 * k, dd + 2 * k, idesc, k ? 1u : 0u);
+    };
+
+    // prologue: this CTA's key / value tile, the first query / dO tile and its statistics; S^T(0), dP^T(0)
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar + 1, 4 * 4 * kBoxRows * 128);
+        tma_rows(Kt, &mapK, bar + 1, h * HD, k0, b, 128);
+        tma_rows(Vt, &mapV, bar + 1, h * HD, k0, b, 128);
+        tma_rows(Qb[0], &mapQ, bar + 1, h * HD, 0, b, 128);
+        tma_rows(dOb[0], &mapdO, bar + 1, h * HD, 0, b, 128);
+    }
+    load_stats(0, 0);
+    sync.wait_loads();
+    if (threadIdx.x == 0) issue_st(0, (min(128, Nq) + 15) / 16 * 16);
+    sync.commit_and_wait();
+
+    // steady state, ONE tensor-core round trip per query tile: dV / dK of tile i are issued together with S^T / dP^T of
+    // tile i + 1, whose operands streamed in (TMA) during the elementwise phase
+    for (int i = 0, q0 = 0; q0 < Nq; ++i, q0 += 128) {
         const int rows = min(128, Nq - q0);
         const int np = (rows + 15) / 16 * 16;            // query columns of this tile, padded to the UMMA N / K granularity
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(bar + 1, (q0 == 0 ? 4 : 2) * 4 * kBoxRows * 128);
-            if (q0 == 0) {
-                tma_rows(Kt, &mapK, bar + 1, h * HD, k0, b, 128);
-                tma_rows(Vt, &mapV, bar + 1, h * HD, k0, b, 128);
+        const bool has_next = q0 + 128 < Nq;
+        const int cur = i & 1;
+        if (has_next) {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar + 1, 2 * 4 * kBoxRows * 128);
+                tma_rows(Qb[cur ^ 1], &mapQ, bar + 1, h * HD, q0 + 128, b, 128);
+                tma_rows(dOb[cur ^ 1], &mapdO, bar + 1, h * HD, q0 + 128, b, 128);
             }
-            tma_rows(Qs, &mapQ, bar + 1, h * HD, q0, b, 128);
-            tma_rows(dOs, &mapdO, bar + 1, h * HD, q0, b, 128);
+            load_stats(cur ^ 1, q0 + 128);
         }
-        {
-            const bool ok = q0 + r < Nq;
-            const long idx = ((long)b * heads + h) * Nq + q0 + r;
-            lse_s[r] = ok ? lse[idx] * kLog2e : 0.f;
-            D_s[r] = ok ? Dg[idx] : 0.f;
-        }
-        sync.wait_loads();
-        tc_fence_before();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            tc_fence_after();
-            const uint32_t idesc = umma_idesc_bf16(128, np);
-            const uint64_t dk = umma_desc_k<128>(smem_u32(Kt)), dv = umma_desc_k<128>(smem_u32(Vt));
-            const uint64_t dq = umma_desc_k<128>(smem_u32(Qs)), dd = umma_desc_k<128>(smem_u32(dOs));
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tS, dk + 2 * k, dq + 2 * k, idesc, k ? 1u : 0u);     // S^T = K Q^T
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tP, dv + 2 * k, dd + 2 * k, idesc, k ? 1u : 0u);     // dP^T = V dO^T
-        }
-        sync.commit_and_wait();
+        __syncthreads();                                  // lse / D of the current tile are visible (prologue or previous iteration)
         if (warp_ok) {
-            for (int c = 0; c < (np + 31) / 32; ++c) {
+            const float *lse_s = lse_b[cur], *D_s = D_b[cur];
+            for (int c = grp; c < (np + 31) / 32; c += 2) {      // the two warps of a lane quarter take alternate chunks
                 uint32_t s[32], p[32];
-                tmem_ld32(tS + lane_off + c * 32, s);
-                tmem_ld32(tP + lane_off + c * 32, p);
+                tmem_ld32_nowait(tS + lane_off + c * 32, s);
+                tmem_ld32_nowait(tP + lane_off + c * 32, p);
+                tmem_wait_ld();
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) {
                     float pv[8], ds[8];
@@ -454,19 +483,21 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        if (has_next) sync.wait_loads();
         if (threadIdx.x == 0) {
             tc_fence_after();
             constexpr uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
             for (int ks = 0; ks < np / 16; ++ks) {
                 const uint64_t dp = umma_desc_k<128>(smem_u32(PT + (ks >> 2) * 16384)) + 2 * (ks & 3);
                 const uint64_t ds = umma_desc_k<128>(smem_u32(dST + (ks >> 2) * 16384)) + 2 * (ks & 3);
-                const uint64_t bo = umma_desc_mn(smem_u32(dOs + ks * 2048), 1024);
-                const uint64_t bq = umma_desc_mn(smem_u32(Qs + ks * 2048), 1024);
+                const uint64_t bo = umma_desc_mn(smem_u32(dOb[cur] + ks * 2048), 1024);
+                const uint64_t bq = umma_desc_mn(smem_u32(Qb[cur] + ks * 2048), 1024);
                 tc_mma_f16(tV, dp, bo, idesc, (q0 | ks) ? 1u : 0u);      // dV += P^T dO
                 tc_mma_f16(tK, ds, bq, idesc, (q0 | ks) ? 1u : 0u);      // dK += dS^T Q
             }
+            if (has_next) issue_st(cur ^ 1, (min(128, Nq - q0 - 128) + 15) / 16 * 16);
         }
-        sync.commit_and_wait();      // the Q / dO / P^T / dS^T images are overwritten by the next query tile
+        sync.commit_and_wait();      // P^T / dS^T and the S^T / dP^T accumulators are free again
     }
     if (warp_ok) {
 #pragma unroll
@@ -475,8 +506,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
             const long ldo = which == 0 ? lddv : lddk;
             const uint32_t t = (which == 0 ? tV : tK) + lane_off;
             uint32_t v[32];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            {
+                const int c = grp;
                 tmem_ld32(t + c * 32, v);
                 if (k0 + r < Nk)
 #pragma unroll
@@ -497,7 +528,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
 
 constexpr int kFwdSmem = 2 * 16384 + 2 * 288 * 128 + 5 * 16384 + 1024;
 constexpr int kDqSmem = 2 * 16384 + 2 * 288 * 128 + 2 * 16384 + 1024;
-constexpr int kDkvSmem = 4 * 16384 + 2 * 32768 + 1024;
+constexpr int kDkvSmem = 2 * 16384 + 2 * 32768 + 4 * 16384 + 1024;
 
 // [B, T, cols] bf16 operand (pitch ld, batch stride bs, in elements); box = 64 columns x kBoxRows tokens, 128-byte swizzle
 static int make_map_tokens(CUtensorMap *map, const void *ptr, int cols, int T, int B, long ld, long bs) {
