@@ -314,6 +314,7 @@ def run_b200(args):
     e2e_value = dutil.job_throughput(B * args.steps, e2e_ms, dev)
 
     cnn = measure_cnn_infer(pose, dev, rank) if args.cnn else None
+    vit_inf = measure_vit_infer(pose, dev, rank) if args.cnn else None
     train_res = None
     if args.train:
         train_res = {k: measure_train(pose, dev, rank, world, k, max(3, min(args.steps, 10)), 3) for k in ("cnn", "vit")}
@@ -400,6 +401,7 @@ def run_b200(args):
                                     "loss": {"bytes": B * 632, "ms": kern_ms["loss"], "note": "latency bound at B=256"},
                                     "head (3 tcgen05 GEMMs + cast)": {"ms": kern_ms["head"]}}},
             "cnn_infer": cnn,
+            "vit_infer": vit_inf,
             "train": train_res,
             "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": f"{reps} x the same B=256 batch ({cpu_dt:.1f} s wall, {cpu_dt * cores:.0f} core-s), oracle port (C) on all host threads"},
@@ -644,6 +646,38 @@ def measure_cnn_infer(pose, dev, rank, batches=(1, 8, 32, 128, 256, 512), reps=1
                                    "sample": f"fp32 eval forward, B={bs}, {n} repetitions ({dt * n:.1f} s)"}
         except Exception as exc:  # the checker is optional for the measurement itself
             out["cpu_baseline"] = {"error": repr(exc)}
+    return out
+
+
+def measure_vit_infer(pose, dev, rank, batches=(1, 8, 64, 256), reps=5):
+    """Eval-mode TransformerPoseEstimation forward at 256x256 (row H for the ViT): samples/s per batch size, CUDA events."""
+    import torch
+    cfg = pose.ModelConfig("transformer", image_size=(H, W), vit_pretrained=False)
+    torch.manual_seed(SEED)
+    model = pose.TransformerPoseEstimation(cfg).to(dev).eval()
+    out = {"config": "TransformerPoseEstimation eval forward, bf16 tensor cores (fp32 accumulate), 256x256, random init, synthetic",
+           "gflop_per_sample": 70.73, "samples_per_s": {}, "ms": {}}
+    g = torch.Generator(device="cpu").manual_seed(SEED + rank)
+    for bs in batches:
+        img = torch.rand(bs, 3, H, W, generator=g).to(dev)
+        dep = torch.rand(bs, 1, H, W, generator=g).to(dev)
+        kp = (torch.rand(bs, J, 2, generator=g) * 0.9 + 0.05).to(dev)
+        with torch.no_grad():
+            for _ in range(2):
+                model(img, dep, kp)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                model(img, dep, kp)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out["ms"][str(bs)] = ms
+        out["samples_per_s"][str(bs)] = bs / ms * 1e3
+        model._plans.clear()
+        torch.cuda.empty_cache()
+    out["tflops_at_best"] = max(out["samples_per_s"].values()) * 70.73e9 / 1e12
     return out
 
 
