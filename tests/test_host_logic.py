@@ -70,3 +70,35 @@ def test_torch_oracle_cnn_matches_reference_golden(golden):
     sd = tm.fill_state_dict(m.state_dict(), seed=int(g["fill_seed"]))
     out = tm.cnn_forward(sd, cfg, torch.from_numpy(g["image"]), torch.from_numpy(g["depth"]), torch.from_numpy(g["kp"]))
     assert np.abs(out.numpy() - g["out"]).max() < 1e-3 * max(1.0, np.abs(g["out"]).max())
+
+
+def test_checkpoint_round_trip_in_the_reference_format(tmp_path):
+    """src/train.py:300-309 layout out, infer.py:73-131 semantics in (bare state dict, 'module.' prefixes, model_args)."""
+    import importlib
+    import torch
+    pose = importlib.import_module("3dhumanposeestimation_b200")
+    ck = importlib.import_module("3dhumanposeestimation_b200.checkpoint")
+    cfg = pose.ModelConfig("cnn", image_size=(64, 64), heatmap_size=64, initial_channels=32, stage_channels=[64, 128, 256],
+                           global_pool_size=2, global_feature_dim=256, regression_dims=[128, 64])
+    m = pose.CNNPoseEstimation(cfg)
+    path = str(tmp_path / "ckpt_cnn_step_5.pth")
+    ck.save_checkpoint(path, m, "cnn", step=5)
+    raw = torch.load(path, weights_only=False)
+    assert set(raw) == {"step", "model_state_dict", "optimizer_state_dict", "model_args", "model_type"}
+    assert raw["model_type"] == "cnn" and raw["model_args"]["stage_channels"] == [64, 128, 256]
+    m2 = ck.load_pose_model(path, "transformer", device="cpu")          # model_type comes from the file
+    assert type(m2).__name__ == "CNNPoseEstimation" and not m2.training
+    sd, sd2 = m.state_dict(), m2.state_dict()
+    assert set(sd) == set(sd2) and all(torch.equal(sd[k], sd2[k]) for k in sd)
+    # DataParallel-style "module." prefixes are stripped (infer.py:95-98)
+    raw["model_state_dict"] = {"module." + k: v for k, v in sd.items()}
+    torch.save(raw, path)
+    m3 = ck.load_pose_model(path, "cnn", device="cpu")
+    assert all(torch.equal(sd[k], v) for k, v in m3.state_dict().items())
+    # a file that is neither a state dict nor a checkpoint dictionary is rejected like the reference does
+    torch.save([1, 2, 3], path)
+    try:
+        ck.load_pose_model(path, "cnn", device="cpu")
+        raise AssertionError("expected ValueError")
+    except ValueError:
+        pass
