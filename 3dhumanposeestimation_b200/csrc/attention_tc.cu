@@ -78,6 +78,7 @@ __device__ __forceinline__ void tma_rows(unsigned char *smem, const CUtensorMap 
 }
 __device__ __forceinline__ int box_bytes(int rows) { return (rows + kBoxRows - 1) / kBoxRows * kBoxRows * 128; }
 
+template <uint32_t TCOLS = 512>
 __device__ __forceinline__ uint32_t attn_prologue(unsigned char *&smem, uint64_t *&bar) {
     extern __shared__ unsigned char smem_dyn[];
     smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
@@ -90,7 +91,7 @@ __device__ __forceinline__ uint32_t attn_prologue(unsigned char *&smem, uint64_t
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TCOLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -100,11 +101,12 @@ __device__ __forceinline__ uint32_t attn_prologue(unsigned char *&smem, uint64_t
     return s_tmem;
 }
 
+template <uint32_t TCOLS = 512>
 __device__ __forceinline__ void attn_epilogue(uint32_t tmem_base) {
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -245,41 +247,68 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// dQ (and D = rowsum(dO * O)) per (sample, head)
+// dQ (and D = rowsum(dO * O)) per (sample, head).  Keys stream through shared memory in double-buffered chunks of 64
+// (256 TMEM columns, 81 KB of shared memory: TWO CTAs per SM), and the loop is software pipelined over the flattened
+// (query tile, key chunk) steps: dQ += dS K of step t is issued together with S / dP of step t + 1, whose operands
+// (next key chunk, and at a tile boundary the next Q / dO tile) arrive by TMA during the elementwise phase of step t.
+constexpr int kDqKC = 64;
 template <int HD>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
                       const __nv_bfloat16 *__restrict__ O, const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ lse,
                       __nv_bfloat16 *__restrict__ dQ, float *__restrict__ Dout, int Nq, int Nk, int Nkp, long ldo, long lddo,
                       long lddq, long bso, long bsdo, long bsdq, float scale, uint32_t drop_thresh, float drop_scale,
                       unsigned long long drop_seed) {
+    constexpr int KC = kDqKC, KB = KC * 128;
     unsigned char *smem;
     uint64_t *bar;
-    const uint32_t tmem = attn_prologue(smem, bar);
+    const uint32_t tmem = attn_prologue<256>(smem, bar);
     AttnSync sync{bar, 0, 0};
-    unsigned char *Qs = smem, *dOs = Qs + 16384, *Ks = dOs + 16384, *Vs = Ks + 288 * 128, *dSs = Vs + 288 * 128;  // dS: 2 blocks
+    unsigned char *Qs = smem, *dOs = Qs + 16384, *dSs = dOs + 16384;
+    unsigned char *Kc[2] = {dSs + 16384, dSs + 16384 + 2 * KB}, *Vc[2] = {dSs + 16384 + KB, dSs + 16384 + 3 * KB};
     const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
     const int warp = threadIdx.x >> 5, quarter = warp & 3, grp = warp >> 2;
     const int r = quarter * 32 + (threadIdx.x & 31);
     const __nv_bfloat16 *og = O + b * bso + (long)h * HD, *dog = dO + b * bsdo + (long)h * HD;
     __nv_bfloat16 *dqg = dQ + b * bsdq + (long)h * HD;
     const float sl2 = scale * kLog2e;
-    const uint32_t tS = tmem, tP = tmem + 128, tQ = tmem + 256;
+    const uint32_t tS = tmem, tP = tmem + 64, tQ = tmem + 128;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    for (int q0 = 0; q0 < Nq; q0 += 128) {
+    const int nch = (Nkp + KC - 1) / KC;
+
+    auto issue_s = [&](int buf, int n) {                   // S = Q K^T, dP = dO V^T for one key chunk   (thread 0)
+        const uint32_t idesc = umma_idesc_bf16(128, n);
+        const uint64_t dq = umma_desc_k<128>(smem_u32(Qs)), dd = umma_desc_k<128>(smem_u32(dOs));
+        const uint64_t dk = umma_desc_k<128>(smem_u32(Kc[buf])), dv = umma_desc_k<128>(smem_u32(Vc[buf]));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tS, dq + 2 * k, dk + 2 * k, idesc, k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tP, dd + 2 * k, dv + 2 * k, idesc, k ? 1u : 0u);
+    };
+
+    // prologue: first Q / dO tile, first key chunk; S(0), dP(0)
+    {
+        const int n0 = min(KC, Nkp);
         if (threadIdx.x == 0) {
-            mbar_expect_tx(bar + 1, 2 * 4 * kBoxRows * 128 + (q0 == 0 ? 2 * box_bytes(Nkp) : 0));
-            if (q0 == 0) {
-                tma_rows(Ks, &mapK, bar + 1, h * HD, 0, b, Nkp);
-                tma_rows(Vs, &mapV, bar + 1, h * HD, 0, b, Nkp);
-            }
-            tma_rows(Qs, &mapQ, bar + 1, h * HD, q0, b, 128);
-            tma_rows(dOs, &mapdO, bar + 1, h * HD, q0, b, 128);
+            mbar_expect_tx(bar + 1, 2 * 16384 + 2 * box_bytes(n0));
+            tma_rows(Qs, &mapQ, bar + 1, h * HD, 0, b, 128);
+            tma_rows(dOs, &mapdO, bar + 1, h * HD, 0, b, 128);
+            tma_rows(Kc[0], &mapK, bar + 1, h * HD, 0, b, n0);
+            tma_rows(Vc[0], &mapV, bar + 1, h * HD, 0, b, n0);
         }
+        sync.wait_loads();
+        if (threadIdx.x == 0) issue_s(0, n0);
+        sync.commit_and_wait();
+    }
+
+    int t = 0;
+    for (int q0 = 0; q0 < Nq; q0 += 128) {
+        const bool last_tile = q0 + 128 >= Nq;
+        const bool row_ok = q0 + r < Nq;
+        const bool live = q0 + quarter * 32 < Nq;
         // D = rowsum(dO * O), log-sum-exp (in exp2 units) of this thread's row
         float Dr = 0.f, l2 = 0.f;
-        const bool row_ok = q0 + r < Nq;
         if (row_ok) {
             const uint4 *po = (const uint4 *)(og + (long)(q0 + r) * ldo), *pd = (const uint4 *)(dog + (long)(q0 + r) * lddo);
 #pragma unroll
@@ -296,113 +325,112 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
             if (grp == 0) Dout[idx] = Dr;
             l2 = lse[idx] * kLog2e;
         }
-        sync.wait_loads();
-        for (int kc0 = 0; kc0 < Nkp; kc0 += 128) {
-            const int n = min(128, Nkp - kc0);
-            fence_async_smem();
-            tc_fence_before();
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                tc_fence_after();
-                const uint32_t idesc = umma_idesc_bf16(128, n);
-                const uint64_t dq = umma_desc_k<128>(smem_u32(Qs)), dd = umma_desc_k<128>(smem_u32(dOs));
-                const uint64_t dk = umma_desc_k<128>(smem_u32(Ks + kc0 * 128)), dv = umma_desc_k<128>(smem_u32(Vs + kc0 * 128));
-#pragma unroll
-                for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tS, dq + 2 * k, dk + 2 * k, idesc, k ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tP, dd + 2 * k, dv + 2 * k, idesc, k ? 1u : 0u);
+        for (int c = 0; c < nch; ++c, ++t) {
+            const int kc0 = c * KC, n = min(KC, Nkp - kc0);
+            const bool last_c = c == nch - 1;
+            const bool has_next = !(last_c && last_tile);
+            const int cn = last_c ? 0 : c + 1, n_next = min(KC, Nkp - cn * KC);
+            const int cur = t & 1;
+            if (threadIdx.x == 0 && has_next) {           // operands of step t + 1 (their buffers were released by the last commit)
+                mbar_expect_tx(bar + 1, 2 * box_bytes(n_next) + (last_c ? 2 * 16384 : 0));
+                tma_rows(Kc[cur ^ 1], &mapK, bar + 1, h * HD, cn * KC, b, n_next);
+                tma_rows(Vc[cur ^ 1], &mapV, bar + 1, h * HD, cn * KC, b, n_next);
+                if (last_c) {
+                    tma_rows(Qs, &mapQ, bar + 1, h * HD, q0 + 128, b, 128);
+                    tma_rows(dOs, &mapdO, bar + 1, h * HD, q0 + 128, b, 128);
+                }
             }
-            sync.commit_and_wait();
-            if (q0 + quarter * 32 < Nq) {
-                for (int c = grp; c < (n + 31) / 32; c += 2) {   // the two warps of a lane quarter take alternate chunks
-                    uint32_t s[32], p[32];
-                    tmem_ld32_nowait(tS + lane_off + c * 32, s);
-                    tmem_ld32_nowait(tP + lane_off + c * 32, p);
-                    tmem_wait_ld();
+            if (live && grp * 32 < n) {                   // the two warps of a lane quarter take one 32-column chunk each
+                const int sc = grp;
+                uint32_t s[32], p[32];
+                tmem_ld32_nowait(tS + lane_off + sc * 32, s);
+                tmem_ld32_nowait(tP + lane_off + sc * 32, p);
+                tmem_wait_ld();
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        float ds[8];
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    float ds[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int col = kc0 + c * 32 + j8 * 8 + j;
-                            const float pr = (col < Nk && row_ok) ? ex2_approx(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -l2)) : 0.f;
-                            float dp = __uint_as_float(p[j8 * 8 + j]);
-                            if (drop_thresh)
-                                dp = drop_keep(drop_seed, (((unsigned long long)b * heads + h) * Nq + q0 + r) * Nk + col, drop_thresh)
-                                         ? dp * drop_scale : 0.f;
-                            ds[j] = pr * (dp - Dr) * scale;
-                        }
-                        const int col8 = c * 4 + j8;
-                        if (col8 * 8 < n)
-                            store_chunk_kmajor(dSs, r, col8, make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]),
-                                                                        pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7])));
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = kc0 + sc * 32 + j8 * 8 + j;
+                        const float pr = (col < Nk && row_ok) ? ex2_approx(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -l2)) : 0.f;
+                        float dp = __uint_as_float(p[j8 * 8 + j]);
+                        if (drop_thresh)
+                            dp = drop_keep(drop_seed, (((unsigned long long)b * heads + h) * Nq + q0 + r) * Nk + col, drop_thresh)
+                                     ? dp * drop_scale : 0.f;
+                        ds[j] = pr * (dp - Dr) * scale;
                     }
+                    const int col8 = sc * 4 + j8;
+                    if (col8 * 8 < n)
+                        store_chunk_kmajor(dSs, r, col8, make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]),
+                                                                    pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7])));
                 }
             }
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
+            if (has_next) sync.wait_loads();
             if (threadIdx.x == 0) {
                 tc_fence_after();
                 constexpr uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
                 for (int ks = 0; ks < n / 16; ++ks) {
-                    const uint64_t da = umma_desc_k<128>(smem_u32(dSs + (ks >> 2) * 16384)) + 2 * (ks & 3);
-                    const uint64_t db = umma_desc_mn(smem_u32(Ks + (kc0 + ks * 16) * 128), 1024);
-                    tc_mma_f16(tQ, da, db, idesc, (kc0 | ks) ? 1u : 0u);
+                    const uint64_t da = umma_desc_k<128>(smem_u32(dSs)) + 2 * ks;
+                    const uint64_t db = umma_desc_mn(smem_u32(Kc[cur] + ks * 2048), 1024);
+                    tc_mma_f16(tQ, da, db, idesc, (c | ks) ? 1u : 0u);       // dQ += dS K
                 }
+                if (has_next) issue_s(cur ^ 1, n_next);
             }
             sync.commit_and_wait();
         }
-        if (q0 + quarter * 32 < Nq) {
+        if (live) {
             uint32_t v[32];
-            {
-                const int c = grp;
-                tmem_ld32(tQ + lane_off + c * 32, v);
-                if (row_ok)
+            const int c = grp;
+            tmem_ld32(tQ + lane_off + c * 32, v);
+            if (row_ok)
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        if (c * 32 + j8 * 8 >= HD) break;
-                        uint4 o;
-                        o.x = pack_bf16x2(__uint_as_float(v[j8 * 8]), __uint_as_float(v[j8 * 8 + 1]));
-                        o.y = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]), __uint_as_float(v[j8 * 8 + 3]));
-                        o.z = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]), __uint_as_float(v[j8 * 8 + 5]));
-                        o.w = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]), __uint_as_float(v[j8 * 8 + 7]));
-                        *((uint4 *)(dqg + (long)(q0 + r) * lddq) + c * 4 + j8) = o;
-                    }
-            }
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    if (c * 32 + j8 * 8 >= HD) break;
+                    uint4 o;
+                    o.x = pack_bf16x2(__uint_as_float(v[j8 * 8]), __uint_as_float(v[j8 * 8 + 1]));
+                    o.y = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]), __uint_as_float(v[j8 * 8 + 3]));
+                    o.z = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]), __uint_as_float(v[j8 * 8 + 5]));
+                    o.w = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]), __uint_as_float(v[j8 * 8 + 7]));
+                    *((uint4 *)(dqg + (long)(q0 + r) * lddq) + c * 4 + j8) = o;
+                }
         }
-        tc_fence_before();
-        __syncthreads();
     }
-    attn_epilogue(tmem);
+    attn_epilogue<256>(tmem);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// dK, dV per (128-key tile, head, sample)
+// dK, dV per (128-key tile, head, sample).  Query tiles of 64 columns keep the CTA at 256 TMEM columns and 97 KB of shared
+// memory, so TWO CTAs share an SM: one's elementwise phase covers the other's tensor-core / TMA round trips, and the
+// mostly-padding CTA of the last key tile (257 = 2 * 128 + 1 tokens) no longer holds an SM on its own.
+constexpr int kDkvQT = 64;
 template <int HD>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                        const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
                        const float *__restrict__ lse, const float *__restrict__ Dg, __nv_bfloat16 *__restrict__ dK,
                        __nv_bfloat16 *__restrict__ dV, int Nq, int Nk, long lddk, long lddv, long bsdk, long bsdv, float scale,
                        uint32_t drop_thresh, float drop_scale, unsigned long long drop_seed) {
+    constexpr int QT = kDkvQT, QB = QT * 128;             // query rows per tile, bytes of one tile image
     unsigned char *smem;
     uint64_t *bar;
-    const uint32_t tmem = attn_prologue(smem, bar);
+    const uint32_t tmem = attn_prologue<256>(smem, bar);
     AttnSync sync{bar, 0, 0};
-    unsigned char *Kt = smem, *Vt = Kt + 16384, *PT = Vt + 16384, *dST = PT + 32768;
-    unsigned char *Qb[2] = {dST + 32768, dST + 32768 + 32768}, *dOb[2] = {dST + 32768 + 16384, dST + 32768 + 32768 + 16384};
-    __shared__ float lse_b[2][128], D_b[2][128];          // double buffered with the query / dO tiles
+    unsigned char *Kt = smem, *Vt = Kt + 16384, *PT = Vt + 16384, *dST = PT + 16384;
+    unsigned char *Qb[2] = {dST + 16384, dST + 16384 + 2 * QB}, *dOb[2] = {dST + 16384 + QB, dST + 16384 + 3 * QB};
+    __shared__ float lse_b[2][QT], D_b[2][QT];            // double buffered with the query / dO tiles
     const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z, heads = gridDim.y;
     const int warp = threadIdx.x >> 5, quarter = warp & 3, grp = warp >> 2;
     const int r = quarter * 32 + (threadIdx.x & 31);
     const float sl2 = scale * kLog2e;
-    const uint32_t tS = tmem, tP = tmem + 128, tV = tmem + 256, tK = tmem + 320;
+    const uint32_t tS = tmem, tP = tmem + 64, tV = tmem + 128, tK = tmem + 192;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const bool warp_ok = k0 + quarter * 32 < Nk;
 
     auto load_stats = [&](int buf, int q0) {               // log-sum-exp (exp2 units) and D of a query tile
-        if (threadIdx.x < 128) {
+        if (threadIdx.x < QT) {
             const int t = threadIdx.x;
             const bool ok = q0 + t < Nq;
             const long idx = ((long)b * heads + h) * Nq + q0 + t;
@@ -422,61 +450,60 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
 
     // prologue: this CTA's key / value tile, the first query / dO tile and its statistics; S^T(0), dP^T(0)
     if (threadIdx.x == 0) {
-        mbar_expect_tx(bar + 1, 4 * 4 * kBoxRows * 128);
+        mbar_expect_tx(bar + 1, 2 * 16384 + 2 * QB);
         tma_rows(Kt, &mapK, bar + 1, h * HD, k0, b, 128);
         tma_rows(Vt, &mapV, bar + 1, h * HD, k0, b, 128);
-        tma_rows(Qb[0], &mapQ, bar + 1, h * HD, 0, b, 128);
-        tma_rows(dOb[0], &mapdO, bar + 1, h * HD, 0, b, 128);
+        tma_rows(Qb[0], &mapQ, bar + 1, h * HD, 0, b, QT);
+        tma_rows(dOb[0], &mapdO, bar + 1, h * HD, 0, b, QT);
     }
     load_stats(0, 0);
     sync.wait_loads();
-    if (threadIdx.x == 0) issue_st(0, (min(128, Nq) + 15) / 16 * 16);
+    if (threadIdx.x == 0) issue_st(0, (min(QT, Nq) + 15) / 16 * 16);
     sync.commit_and_wait();
 
     // steady state, ONE tensor-core round trip per query tile: dV / dK of tile i are issued together with S^T / dP^T of
     // tile i + 1, whose operands streamed in (TMA) during the elementwise phase
-    for (int i = 0, q0 = 0; q0 < Nq; ++i, q0 += 128) {
-        const int rows = min(128, Nq - q0);
+    for (int i = 0, q0 = 0; q0 < Nq; ++i, q0 += QT) {
+        const int rows = min(QT, Nq - q0);
         const int np = (rows + 15) / 16 * 16;            // query columns of this tile, padded to the UMMA N / K granularity
-        const bool has_next = q0 + 128 < Nq;
+        const bool has_next = q0 + QT < Nq;
         const int cur = i & 1;
         if (has_next) {
             if (threadIdx.x == 0) {
-                mbar_expect_tx(bar + 1, 2 * 4 * kBoxRows * 128);
-                tma_rows(Qb[cur ^ 1], &mapQ, bar + 1, h * HD, q0 + 128, b, 128);
-                tma_rows(dOb[cur ^ 1], &mapdO, bar + 1, h * HD, q0 + 128, b, 128);
+                mbar_expect_tx(bar + 1, 2 * QB);
+                tma_rows(Qb[cur ^ 1], &mapQ, bar + 1, h * HD, q0 + QT, b, QT);
+                tma_rows(dOb[cur ^ 1], &mapdO, bar + 1, h * HD, q0 + QT, b, QT);
             }
-            load_stats(cur ^ 1, q0 + 128);
+            load_stats(cur ^ 1, q0 + QT);
         }
         __syncthreads();                                  // lse / D of the current tile are visible (prologue or previous iteration)
-        if (warp_ok) {
+        if (warp_ok && grp * 32 < np) {                   // the two warps of a lane quarter take one 32-column chunk each
             const float *lse_s = lse_b[cur], *D_s = D_b[cur];
-            for (int c = grp; c < (np + 31) / 32; c += 2) {      // the two warps of a lane quarter take alternate chunks
-                uint32_t s[32], p[32];
-                tmem_ld32_nowait(tS + lane_off + c * 32, s);
-                tmem_ld32_nowait(tP + lane_off + c * 32, p);
-                tmem_wait_ld();
+            const int c = grp;
+            uint32_t s[32], p[32];
+            tmem_ld32_nowait(tS + lane_off + c * 32, s);
+            tmem_ld32_nowait(tP + lane_off + c * 32, p);
+            tmem_wait_ld();
 #pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) {
-                    float pv[8], ds[8];
+            for (int j8 = 0; j8 < 4; ++j8) {
+                float pv[8], ds[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int col = c * 32 + j8 * 8 + j;                  // query within the tile
-                        const float pr = col < rows ? ex2_approx(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -lse_s[col])) : 0.f;
-                        float keep = 1.0f;
-                        if (drop_thresh)
-                            keep = drop_keep(drop_seed, (((unsigned long long)b * heads + h) * Nq + q0 + col) * Nk + k0 + r, drop_thresh)
-                                       ? drop_scale : 0.f;
-                        pv[j] = pr * keep;                                    // dV sees the dropped probabilities
-                        ds[j] = pr * (__uint_as_float(p[j8 * 8 + j]) * keep - D_s[col]) * scale;
-                    }
-                    const int col8 = c * 4 + j8;
-                    if (col8 * 8 < np) {
-                        store_chunk_kmajor(PT, r, col8, make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]),
-                                                                   pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7])));
-                        store_chunk_kmajor(dST, r, col8, make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]),
-                                                                    pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7])));
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const int col = c * 32 + j8 * 8 + j;                  // query within the tile
+                    const float pr = col < rows ? ex2_approx(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -lse_s[col])) : 0.f;
+                    float keep = 1.0f;
+                    if (drop_thresh)
+                        keep = drop_keep(drop_seed, (((unsigned long long)b * heads + h) * Nq + q0 + col) * Nk + k0 + r, drop_thresh)
+                                   ? drop_scale : 0.f;
+                    pv[j] = pr * keep;                                    // dV sees the dropped probabilities
+                    ds[j] = pr * (__uint_as_float(p[j8 * 8 + j]) * keep - D_s[col]) * scale;
+                }
+                const int col8 = c * 4 + j8;
+                if (col8 * 8 < np) {
+                    store_chunk_kmajor(PT, r, col8, make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]),
+                                                               pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7])));
+                    store_chunk_kmajor(dST, r, col8, make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]),
+                                                                pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7])));
                 }
             }
         }
@@ -488,14 +515,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
             tc_fence_after();
             constexpr uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
             for (int ks = 0; ks < np / 16; ++ks) {
-                const uint64_t dp = umma_desc_k<128>(smem_u32(PT + (ks >> 2) * 16384)) + 2 * (ks & 3);
-                const uint64_t ds = umma_desc_k<128>(smem_u32(dST + (ks >> 2) * 16384)) + 2 * (ks & 3);
+                const uint64_t dp = umma_desc_k<128>(smem_u32(PT)) + 2 * ks;
+                const uint64_t ds = umma_desc_k<128>(smem_u32(dST)) + 2 * ks;
                 const uint64_t bo = umma_desc_mn(smem_u32(dOb[cur] + ks * 2048), 1024);
                 const uint64_t bq = umma_desc_mn(smem_u32(Qb[cur] + ks * 2048), 1024);
                 tc_mma_f16(tV, dp, bo, idesc, (q0 | ks) ? 1u : 0u);      // dV += P^T dO
                 tc_mma_f16(tK, ds, bq, idesc, (q0 | ks) ? 1u : 0u);      // dK += dS^T Q
             }
-            if (has_next) issue_st(cur ^ 1, (min(128, Nq - q0 - 128) + 15) / 16 * 16);
+            if (has_next) issue_st(cur ^ 1, (min(QT, Nq - q0 - QT) + 15) / 16 * 16);
         }
         sync.commit_and_wait();      // P^T / dS^T and the S^T / dP^T accumulators are free again
     }
@@ -523,12 +550,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
             }
         }
     }
-    attn_epilogue(tmem);
+    attn_epilogue<256>(tmem);
 }
 
 constexpr int kFwdSmem = 2 * 16384 + 2 * 288 * 128 + 5 * 16384 + 1024;
-constexpr int kDqSmem = 2 * 16384 + 2 * 288 * 128 + 2 * 16384 + 1024;
-constexpr int kDkvSmem = 2 * 16384 + 2 * 32768 + 4 * 16384 + 1024;
+constexpr int kDqSmem = 3 * 16384 + 4 * kDqKC * 128 + 1024;
+constexpr int kDkvSmem = 4 * 16384 + 4 * kDkvQT * 128 + 1024;
 
 // [B, T, cols] bf16 operand (pitch ld, batch stride bs, in elements); box = 64 columns x kBoxRows tokens, 128-byte swizzle
 static int make_map_tokens(CUtensorMap *map, const void *ptr, int cols, int T, int B, long ld, long bs) {
