@@ -115,12 +115,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, __nv_bfloat16 *__restrict__ O, float *__restrict__ lse, int Nq, int Nk,
                    int Nkp, long ldo, long bso, float scale, uint32_t drop_thresh, float drop_scale,
-                   unsigned long long drop_seed) {
+                   const DropSeed drop_seed) {
     unsigned char *smem;
     uint64_t *bar;
     const uint32_t tmem = attn_prologue(smem, bar);
     AttnSync sync{bar, 0, 0};
-    unsigned char *Qb[2] = {smem, smem + 16384};                                  // double-buffered query tiles
+    auto Qb = [&](int i) { return smem + i * 16384; };                             // double-buffered query tiles
     unsigned char *Ks = smem + 32768, *Vs = Ks + 288 * 128, *Ps = Vs + 288 * 128;  // P: 5 blocks of 16 KB
     const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
     const int warp = threadIdx.x >> 5, quarter = warp & 3, grp = warp >> 2;
@@ -148,10 +148,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         mbar_expect_tx(bar + 1, 4 * kBoxRows * 128 + 2 * box_bytes(Nkp));
         tma_rows(Ks, &mapK, bar + 1, h * HD, 0, b, Nkp);
         tma_rows(Vs, &mapV, bar + 1, h * HD, 0, b, Nkp);
-        tma_rows(Qb[0], &mapQ, bar + 1, h * HD, 0, b, 128);
+        tma_rows(Qb(0), &mapQ, bar + 1, h * HD, 0, b, 128);
     }
     sync.wait_loads();
-    if (threadIdx.x == 0) issue_s(Qb[0]);
+    if (threadIdx.x == 0) issue_s(Qb(0));
     sync.commit_and_wait();
 
     // steady state, ONE tensor-core round trip per query tile: after the softmax of tile i, O(i) = P V and S(i+1) are issued
@@ -160,9 +160,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         const bool has_next = q0 + 128 < Nq;
         if (threadIdx.x == 0 && has_next) {
             mbar_expect_tx(bar + 1, 4 * kBoxRows * 128);
-            tma_rows(Qb[(i + 1) & 1], &mapQ, bar + 1, h * HD, q0 + 128, b, 128);
+            tma_rows(Qb((i + 1) & 1), &mapQ, bar + 1, h * HD, q0 + 128, b, 128);
         }
         const bool live = q0 + quarter * 32 < Nq;        // warps whose 32 rows are all padding skip the softmax
+        const uint32_t drop_row = (uint32_t)(((b * heads + h) * Nq + q0 + r) * Nk);   // mask index of (row, key 0); < 2^32 (host check)
         // A thread owns one row and there are two warps per scheduler: every dependent chain is exposed, so the row maximum
         // and the row sum run on four independent accumulators; the two warps of a lane quarter take alternate 32-column
         // chunks and meet through shared memory.  (Kept compact: i-cache misses are exposed too.)
@@ -193,9 +194,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
                         p[j] = col < Nk ? ex2_approx(fmaf(__uint_as_float(v[j8 * 8 + j]), sl2, -ms)) : 0.f;
                         s4[j & 3] += p[j];
                         // attention-weight dropout (nn.MultiheadAttention(dropout=p)): the row still normalises by the full sum
-                        if (drop_thresh)
-                            p[j] = drop_keep(drop_seed, (((unsigned long long)b * heads + h) * Nq + q0 + r) * Nk + col, drop_thresh)
-                                       ? p[j] * drop_scale : 0.f;
+                        if (drop_thresh) p[j] = drop_keep32(drop_seed.key0, drop_row + col, drop_thresh) ? p[j] * drop_scale : 0.f;
                     }
                     const int col8 = c * 4 + j8;
                     if (col8 * 8 < Nkp)
@@ -216,7 +215,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
                 const uint64_t db = umma_desc_mn(smem_u32(Vs + ks * 2048), 1024);
                 tc_mma_f16(tO, da, db, idesc, ks ? 1u : 0u);
             }
-            if (has_next) issue_s(Qb[(i + 1) & 1]);
+            if (has_next) issue_s(Qb((i + 1) & 1));
         }
         sync.commit_and_wait();
         if (live) {                                      // warp-uniform: tcgen05.ld is a warp-collective instruction
@@ -259,14 +258,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
                       const __nv_bfloat16 *__restrict__ O, const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ lse,
                       __nv_bfloat16 *__restrict__ dQ, float *__restrict__ Dout, int Nq, int Nk, int Nkp, long ldo, long lddo,
                       long lddq, long bso, long bsdo, long bsdq, float scale, uint32_t drop_thresh, float drop_scale,
-                      unsigned long long drop_seed) {
+                      const DropSeed drop_seed) {
     constexpr int KC = kDqKC, KB = KC * 128;
     unsigned char *smem;
     uint64_t *bar;
     const uint32_t tmem = attn_prologue<256>(smem, bar);
     AttnSync sync{bar, 0, 0};
     unsigned char *Qs = smem, *dOs = Qs + 16384, *dSs = dOs + 16384;
-    unsigned char *Kc[2] = {dSs + 16384, dSs + 16384 + 2 * KB}, *Vc[2] = {dSs + 16384 + KB, dSs + 16384 + 3 * KB};
+    auto Kc = [&](int i) { return dSs + 16384 + i * 2 * KB; };      // double-buffered key / value chunks
+    auto Vc = [&](int i) { return dSs + 16384 + KB + i * 2 * KB; };
     const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
     const int warp = threadIdx.x >> 5, quarter = warp & 3, grp = warp >> 2;
     const int r = quarter * 32 + (threadIdx.x & 31);
@@ -280,7 +280,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     auto issue_s = [&](int buf, int n) {                   // S = Q K^T, dP = dO V^T for one key chunk   (thread 0)
         const uint32_t idesc = umma_idesc_bf16(128, n);
         const uint64_t dq = umma_desc_k<128>(smem_u32(Qs)), dd = umma_desc_k<128>(smem_u32(dOs));
-        const uint64_t dk = umma_desc_k<128>(smem_u32(Kc[buf])), dv = umma_desc_k<128>(smem_u32(Vc[buf]));
+        const uint64_t dk = umma_desc_k<128>(smem_u32(Kc(buf))), dv = umma_desc_k<128>(smem_u32(Vc(buf)));
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tS, dq + 2 * k, dk + 2 * k, idesc, k ? 1u : 0u);
 #pragma unroll
@@ -294,8 +294,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
             mbar_expect_tx(bar + 1, 2 * 16384 + 2 * box_bytes(n0));
             tma_rows(Qs, &mapQ, bar + 1, h * HD, 0, b, 128);
             tma_rows(dOs, &mapdO, bar + 1, h * HD, 0, b, 128);
-            tma_rows(Kc[0], &mapK, bar + 1, h * HD, 0, b, n0);
-            tma_rows(Vc[0], &mapV, bar + 1, h * HD, 0, b, n0);
+            tma_rows(Kc(0), &mapK, bar + 1, h * HD, 0, b, n0);
+            tma_rows(Vc(0), &mapV, bar + 1, h * HD, 0, b, n0);
         }
         sync.wait_loads();
         if (threadIdx.x == 0) issue_s(0, n0);
@@ -307,6 +307,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         const bool last_tile = q0 + 128 >= Nq;
         const bool row_ok = q0 + r < Nq;
         const bool live = q0 + quarter * 32 < Nq;
+        const uint32_t drop_row = (uint32_t)(((b * heads + h) * Nq + q0 + r) * Nk);   // mask index of (row, key 0); < 2^32 (host check)
         // D = rowsum(dO * O), log-sum-exp (in exp2 units) of this thread's row
         float Dr = 0.f, l2 = 0.f;
         if (row_ok) {
@@ -333,8 +334,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
             const int cur = t & 1;
             if (threadIdx.x == 0 && has_next) {           // operands of step t + 1 (their buffers were released by the last commit)
                 mbar_expect_tx(bar + 1, 2 * box_bytes(n_next) + (last_c ? 2 * 16384 : 0));
-                tma_rows(Kc[cur ^ 1], &mapK, bar + 1, h * HD, cn * KC, b, n_next);
-                tma_rows(Vc[cur ^ 1], &mapV, bar + 1, h * HD, cn * KC, b, n_next);
+                tma_rows(Kc(cur ^ 1), &mapK, bar + 1, h * HD, cn * KC, b, n_next);
+                tma_rows(Vc(cur ^ 1), &mapV, bar + 1, h * HD, cn * KC, b, n_next);
                 if (last_c) {
                     tma_rows(Qs, &mapQ, bar + 1, h * HD, q0 + 128, b, 128);
                     tma_rows(dOs, &mapdO, bar + 1, h * HD, q0 + 128, b, 128);
@@ -354,9 +355,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
                         const int col = kc0 + sc * 32 + j8 * 8 + j;
                         const float pr = (col < Nk && row_ok) ? ex2_approx(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -l2)) : 0.f;
                         float dp = __uint_as_float(p[j8 * 8 + j]);
-                        if (drop_thresh)
-                            dp = drop_keep(drop_seed, (((unsigned long long)b * heads + h) * Nq + q0 + r) * Nk + col, drop_thresh)
-                                     ? dp * drop_scale : 0.f;
+                        if (drop_thresh) dp = drop_keep32(drop_seed.key0, drop_row + col, drop_thresh) ? dp * drop_scale : 0.f;
                         ds[j] = pr * (dp - Dr) * scale;
                     }
                     const int col8 = sc * 4 + j8;
@@ -374,7 +373,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
                 constexpr uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
                 for (int ks = 0; ks < n / 16; ++ks) {
                     const uint64_t da = umma_desc_k<128>(smem_u32(dSs)) + 2 * ks;
-                    const uint64_t db = umma_desc_mn(smem_u32(Kc[cur] + ks * 2048), 1024);
+                    const uint64_t db = umma_desc_mn(smem_u32(Kc(cur) + ks * 2048), 1024);
                     tc_mma_f16(tQ, da, db, idesc, (c | ks) ? 1u : 0u);       // dQ += dS K
                 }
                 if (has_next) issue_s(cur ^ 1, n_next);
@@ -412,14 +411,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
                        const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
                        const float *__restrict__ lse, const float *__restrict__ Dg, __nv_bfloat16 *__restrict__ dK,
                        __nv_bfloat16 *__restrict__ dV, int Nq, int Nk, long lddk, long lddv, long bsdk, long bsdv, float scale,
-                       uint32_t drop_thresh, float drop_scale, unsigned long long drop_seed) {
+                       uint32_t drop_thresh, float drop_scale, const DropSeed drop_seed) {
     constexpr int QT = kDkvQT, QB = QT * 128;             // query rows per tile, bytes of one tile image
     unsigned char *smem;
     uint64_t *bar;
     const uint32_t tmem = attn_prologue<256>(smem, bar);
     AttnSync sync{bar, 0, 0};
     unsigned char *Kt = smem, *Vt = Kt + 16384, *PT = Vt + 16384, *dST = PT + 16384;
-    unsigned char *Qb[2] = {dST + 16384, dST + 16384 + 2 * QB}, *dOb[2] = {dST + 16384 + QB, dST + 16384 + 3 * QB};
+    auto Qb = [&](int i) { return dST + 16384 + i * 2 * QB; };      // double-buffered query / dO tiles
+    auto dOb = [&](int i) { return dST + 16384 + QB + i * 2 * QB; };
     __shared__ float lse_b[2][QT], D_b[2][QT];            // double buffered with the query / dO tiles
     const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z, heads = gridDim.y;
     const int warp = threadIdx.x >> 5, quarter = warp & 3, grp = warp >> 2;
@@ -441,7 +441,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
     auto issue_st = [&](int buf, int np) {                 // S^T = K Q^T, dP^T = V dO^T   (thread 0)
         const uint32_t idesc = umma_idesc_bf16(128, np);
         const uint64_t dk = umma_desc_k<128>(smem_u32(Kt)), dv = umma_desc_k<128>(smem_u32(Vt));
-        const uint64_t dq = umma_desc_k<128>(smem_u32(Qb[buf])), dd = umma_desc_k<128>(smem_u32(dOb[buf]));
+        const uint64_t dq = umma_desc_k<128>(smem_u32(Qb(buf))), dd = umma_desc_k<128>(smem_u32(dOb(buf)));
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tS, dk + 2 * k, dq + 2 * k, idesc, k ? 1u : 0u);
 #pragma unroll
@@ -453,8 +453,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
         mbar_expect_tx(bar + 1, 2 * 16384 + 2 * QB);
         tma_rows(Kt, &mapK, bar + 1, h * HD, k0, b, 128);
         tma_rows(Vt, &mapV, bar + 1, h * HD, k0, b, 128);
-        tma_rows(Qb[0], &mapQ, bar + 1, h * HD, 0, b, QT);
-        tma_rows(dOb[0], &mapdO, bar + 1, h * HD, 0, b, QT);
+        tma_rows(Qb(0), &mapQ, bar + 1, h * HD, 0, b, QT);
+        tma_rows(dOb(0), &mapdO, bar + 1, h * HD, 0, b, QT);
     }
     load_stats(0, 0);
     sync.wait_loads();
@@ -468,11 +468,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
         const int np = (rows + 15) / 16 * 16;            // query columns of this tile, padded to the UMMA N / K granularity
         const bool has_next = q0 + QT < Nq;
         const int cur = i & 1;
+        const uint32_t drop_col = (uint32_t)(((b * heads + h) * Nq + q0) * Nk + k0 + r);   // mask index of (query q0, this key); < 2^32 (host check)
         if (has_next) {
             if (threadIdx.x == 0) {
                 mbar_expect_tx(bar + 1, 2 * QB);
-                tma_rows(Qb[cur ^ 1], &mapQ, bar + 1, h * HD, q0 + QT, b, QT);
-                tma_rows(dOb[cur ^ 1], &mapdO, bar + 1, h * HD, q0 + QT, b, QT);
+                tma_rows(Qb(cur ^ 1), &mapQ, bar + 1, h * HD, q0 + QT, b, QT);
+                tma_rows(dOb(cur ^ 1), &mapdO, bar + 1, h * HD, q0 + QT, b, QT);
             }
             load_stats(cur ^ 1, q0 + QT);
         }
@@ -492,9 +493,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
                     const int col = c * 32 + j8 * 8 + j;                  // query within the tile
                     const float pr = col < rows ? ex2_approx(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -lse_s[col])) : 0.f;
                     float keep = 1.0f;
-                    if (drop_thresh)
-                        keep = drop_keep(drop_seed, (((unsigned long long)b * heads + h) * Nq + q0 + col) * Nk + k0 + r, drop_thresh)
-                                   ? drop_scale : 0.f;
+                    if (drop_thresh) keep = drop_keep32(drop_seed.key0, drop_col + (unsigned)(col * Nk), drop_thresh) ? drop_scale : 0.f;
                     pv[j] = pr * keep;                                    // dV sees the dropped probabilities
                     ds[j] = pr * (__uint_as_float(p[j8 * 8 + j]) * keep - D_s[col]) * scale;
                 }
@@ -517,8 +516,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
             for (int ks = 0; ks < np / 16; ++ks) {
                 const uint64_t dp = umma_desc_k<128>(smem_u32(PT)) + 2 * ks;
                 const uint64_t ds = umma_desc_k<128>(smem_u32(dST)) + 2 * ks;
-                const uint64_t bo = umma_desc_mn(smem_u32(dOb[cur] + ks * 2048), 1024);
-                const uint64_t bq = umma_desc_mn(smem_u32(Qb[cur] + ks * 2048), 1024);
+                const uint64_t bo = umma_desc_mn(smem_u32(dOb(cur) + ks * 2048), 1024);
+                const uint64_t bq = umma_desc_mn(smem_u32(Qb(cur) + ks * 2048), 1024);
                 tc_mma_f16(tV, dp, bo, idesc, (q0 | ks) ? 1u : 0u);      // dV += P^T dO
                 tc_mma_f16(tK, ds, bq, idesc, (q0 | ks) ? 1u : 0u);      // dK += dS^T Q
             }
@@ -591,6 +590,7 @@ POSE_API int pose_attention_bf16(const void *Q, const void *K, const void *V, vo
     if (B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return POSE_E_SHAPE;
     if (head_dim != 48 && head_dim != 64) return POSE_E_UNSUPPORTED;
     if (Nk > 288) return POSE_E_UNSUPPORTED;              // the whole score row lives in TMEM (<= 288 columns)
+    if (drop_p > 0.f && (double)B * heads * Nq * Nk >= 4294967296.0) return POSE_E_UNSUPPORTED;   // 32-bit mask counter
     if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || bsq % 8 || bsk % 8 || bsv % 8 || bso % 8) return POSE_E_ALIGN;
     if ((uintptr_t)Q % 16 || (uintptr_t)K % 16 || (uintptr_t)V % 16 || (uintptr_t)O % 16) return POSE_E_ALIGN;
     const int Nkp = (Nk + 15) / 16 * 16;
@@ -606,7 +606,7 @@ POSE_API int pose_attention_bf16(const void *Q, const void *K, const void *V, vo
 #define FWD(HD_)                                                                                                       \
     if ((e = set_smem(attn_fwd_tc_kernel<HD_>, kFwdSmem))) return e;                                                    \
     attn_fwd_tc_kernel<HD_><<<grid, kAttnThreads, kFwdSmem, s>>>(mq, mk, mv, (__nv_bfloat16 *)O, lse, Nq, Nk, Nkp, ldo, bso, \
-                                                                scale, dth, dsc, drop_seed)
+                                                                scale, dth, dsc, make_drop_seed(drop_seed))
     if (head_dim == 64) { FWD(64); } else { FWD(48); }
 #undef FWD
     return launch_status();
@@ -624,6 +624,7 @@ POSE_API int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V
     if (B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return POSE_E_SHAPE;
     if (head_dim != 48 && head_dim != 64) return POSE_E_UNSUPPORTED;
     if (Nk > 288) return POSE_E_UNSUPPORTED;
+    if (drop_p > 0.f && (double)B * heads * Nq * Nk >= 4294967296.0) return POSE_E_UNSUPPORTED;   // 32-bit mask counter
     const long al[] = {ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv};
     for (long a : al)
         if (a % 8) return POSE_E_ALIGN;
@@ -647,10 +648,10 @@ POSE_API int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V
     attn_bwd_dq_tc_kernel<HD_><<<g1, kAttnThreads, kDqSmem, s>>>(mq, mk, mv, md, (const __nv_bfloat16 *)O,              \
                                                                 (const __nv_bfloat16 *)dO, lse, (__nv_bfloat16 *)dQ, Dws, Nq, \
                                                                 Nk, Nkp, ldo, lddo, lddq, bso, bsdo, bsdq, scale, dth, dsc, \
-                                                                drop_seed);                                           \
+                                                                make_drop_seed(drop_seed));                                           \
     attn_bwd_dkv_tc_kernel<HD_><<<g2, kAttnThreads, kDkvSmem, s>>>(mq, mk, mv, md, lse, Dws, (__nv_bfloat16 *)dK,        \
                                                                   (__nv_bfloat16 *)dV, Nq, Nk, lddk, lddv, bsdk, bsdv, scale, \
-                                                                  dth, dsc, drop_seed)
+                                                                  dth, dsc, make_drop_seed(drop_seed))
     if (head_dim == 64) { BWD(64); } else { BWD(48); }
 #undef BWD
     return launch_status();

@@ -811,14 +811,21 @@ add_kernel(const __nv_bfloat16 *__restrict__ a, const __nv_bfloat16 *__restrict_
     }
 }
 
-// counter-based dropout mask: element i of call `seed` is kept iff hash(seed, i) >= p * 2^32 (same mask in backward)
+// counter-based dropout mask (common.cuh: drop_keep), 8 elements per thread; the same mask is regenerated in backward
 __global__ void __launch_bounds__(256)
-dropout_kernel(const __nv_bfloat16 *__restrict__ x, long n, uint32_t thresh, float keep_scale, uint64_t seed,
+dropout_kernel(const __nv_bfloat16 *__restrict__ x, long n, uint32_t thresh, float keep_scale, DropSeed seed,
                __nv_bfloat16 *__restrict__ out) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        const bool keep = drop_keep(seed, (uint64_t)i, thresh);
-        out[i] = __float2bfloat16_rn(keep ? __bfloat162float(x[i]) * keep_scale : 0.f);
+    const long n8 = n >> 3;
+    const bool vec = (((uintptr_t)x | (uintptr_t)out) & 15) == 0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; vec && i < n8; i += (long)gridDim.x * blockDim.x) {
+        float v[8];
+        up8(__ldg((const uint4 *)x + i), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = drop_keep(seed, (uint64_t)(i * 8 + j), thresh) ? v[j] * keep_scale : 0.f;
+        ((uint4 *)out)[i] = pk8(v);
     }
+    for (long i = (vec ? n8 * 8 : 0) + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        out[i] = __float2bfloat16_rn(drop_keep(seed, (uint64_t)i, thresh) ? __bfloat162float(x[i]) * keep_scale : 0.f);
 }
 
 // ---- table-driven parameter re-layout (one launch per step) --------------------------------------------------
@@ -1102,7 +1109,7 @@ POSE_API int pose_dropout_bf16(const void *x, long n, float p, uint64_t seed, vo
     REQ(x && out, POSE_E_NULL);
     REQ(n > 0 && p >= 0.f && p < 1.f, POSE_E_SHAPE);
     const uint32_t thresh = drop_threshold(p);
-    dropout_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x, n, thresh, 1.0f / (1.0f - p), seed,
+    dropout_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x, n, thresh, 1.0f / (1.0f - p), make_drop_seed(seed),
                                                                  (__nv_bfloat16 *)out);
     return launch_status();
 }

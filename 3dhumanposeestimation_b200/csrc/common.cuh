@@ -28,13 +28,33 @@ __device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
 }
 
 // Counter-based dropout mask shared by every kernel that applies or re-applies dropout: element `i` of the tensor that
-// call `seed` drops is kept iff hash(seed, i) >= p * 2^32.  The backward pass regenerates the same mask from (seed, i).
-__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+// call `seed` drops is kept iff lowbias32(lo32(i) ^ key(seed, hi32(i))) >= p * 2^32, key = a 64-bit murmur finaliser of
+// (seed, hi32(i)).  The key of hi32 == 0 (every tensor of this model) is computed once on the host (`DropSeed`), so the
+// per-element cost is one 32-bit hash (2 multiplies) instead of a 64-bit one.  Backward regenerates the same mask.
+__host__ __device__ __forceinline__ uint32_t mix32(uint64_t x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return (uint32_t)x;
 }
-__device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t i, uint32_t thresh) {
-    return mix32(seed * 0x9E3779B97F4A7C15ULL + i) >= thresh;
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+struct DropSeed {
+    unsigned long long s;      // seed * golden ratio
+    uint32_t key0;             // mix32(s): the key of elements below 2^32
+};
+inline DropSeed make_drop_seed(unsigned long long seed) {
+    DropSeed d;
+    d.s = seed * 0x9E3779B97F4A7C15ULL;
+    d.key0 = mix32(d.s);
+    return d;
+}
+__device__ __forceinline__ uint32_t drop_key(const DropSeed &d, uint32_t hi) { return hi ? mix32(d.s + hi) : d.key0; }
+// element `lo` (< 2^32) under a key: branch-free, 2 multiplies -- the form the fused kernels use (their hosts reject
+// tensors of 2^32 elements or more, so the key is always DropSeed::key0)
+__device__ __forceinline__ bool drop_keep32(uint32_t key, uint32_t lo, uint32_t thresh) { return lowbias32(lo ^ key) >= thresh; }
+__device__ __forceinline__ bool drop_keep(const DropSeed &d, uint64_t i, uint32_t thresh) {
+    return drop_keep32(drop_key(d, (uint32_t)(i >> 32)), (uint32_t)i, thresh);
 }
 inline uint32_t drop_threshold(float p) { return (uint32_t)((double)p * 4294967296.0); }
 

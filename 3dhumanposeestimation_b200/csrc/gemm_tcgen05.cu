@@ -56,7 +56,7 @@ struct Epilogue {
     int tma;                         // bf16 output tiles leave through TMA stores (row-per-lane epilogue, no transpose)
     uint32_t drop_thresh;            // dropout after the activation (before the residual): keep iff hash >= thresh
     float drop_scale;                // 1 / (1 - p)
-    unsigned long long drop_seed;    // element index = row * ldc + col (common.cuh: drop_keep)
+    DropSeed drop_seed;              // element index = row * ldc + col (common.cuh: drop_keep)
 };
 
 struct ConvGeom {          // MODE 1 only
@@ -202,11 +202,11 @@ __device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, 
             x.x *= act_grad<ACT>(u0.x) * ep.out_scale; x.y *= act_grad<ACT>(u0.y) * ep.out_scale;
             x.z *= act_grad<ACT>(u1.x) * ep.out_scale; x.w *= act_grad<ACT>(u1.y) * ep.out_scale;
             if (ep.drop_thresh) {     // the forward dropped act(u): the same mask gates the gradient
-                const unsigned long long i0 = (unsigned long long)grow * ep.ldc + col;
-                x.x = drop_keep(ep.drop_seed, i0, ep.drop_thresh) ? x.x * ep.drop_scale : 0.f;
-                x.y = drop_keep(ep.drop_seed, i0 + 1, ep.drop_thresh) ? x.y * ep.drop_scale : 0.f;
-                x.z = drop_keep(ep.drop_seed, i0 + 2, ep.drop_thresh) ? x.z * ep.drop_scale : 0.f;
-                x.w = drop_keep(ep.drop_seed, i0 + 3, ep.drop_thresh) ? x.w * ep.drop_scale : 0.f;
+                const uint32_t i0 = (uint32_t)(grow * ep.ldc + col);   // < 2^32 (host check)
+                x.x = drop_keep32(ep.drop_seed.key0, i0, ep.drop_thresh) ? x.x * ep.drop_scale : 0.f;
+                x.y = drop_keep32(ep.drop_seed.key0, i0 + 1, ep.drop_thresh) ? x.y * ep.drop_scale : 0.f;
+                x.z = drop_keep32(ep.drop_seed.key0, i0 + 2, ep.drop_thresh) ? x.z * ep.drop_scale : 0.f;
+                x.w = drop_keep32(ep.drop_seed.key0, i0 + 3, ep.drop_thresh) ? x.w * ep.drop_scale : 0.f;
             }
         } else {
             x.x += bz.x; x.y += bz.y; x.z += bz.z; x.w += bz.w;
@@ -225,11 +225,11 @@ __device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, 
                 x.w = fast_act<ACT>(x.w) * ep.out_scale;
             }
             if (ep.drop_thresh) {
-                const unsigned long long i0 = (unsigned long long)grow * ep.ldc + col;
-                x.x = drop_keep(ep.drop_seed, i0, ep.drop_thresh) ? x.x * ep.drop_scale : 0.f;
-                x.y = drop_keep(ep.drop_seed, i0 + 1, ep.drop_thresh) ? x.y * ep.drop_scale : 0.f;
-                x.z = drop_keep(ep.drop_seed, i0 + 2, ep.drop_thresh) ? x.z * ep.drop_scale : 0.f;
-                x.w = drop_keep(ep.drop_seed, i0 + 3, ep.drop_thresh) ? x.w * ep.drop_scale : 0.f;
+                const uint32_t i0 = (uint32_t)(grow * ep.ldc + col);   // < 2^32 (host check)
+                x.x = drop_keep32(ep.drop_seed.key0, i0, ep.drop_thresh) ? x.x * ep.drop_scale : 0.f;
+                x.y = drop_keep32(ep.drop_seed.key0, i0 + 1, ep.drop_thresh) ? x.y * ep.drop_scale : 0.f;
+                x.z = drop_keep32(ep.drop_seed.key0, i0 + 2, ep.drop_thresh) ? x.z * ep.drop_scale : 0.f;
+                x.w = drop_keep32(ep.drop_seed.key0, i0 + 3, ep.drop_thresh) ? x.w * ep.drop_scale : 0.f;
             }
             if (ep.residual != nullptr) {
                 const uint2 pk = __ldg((const uint2 *)(ep.residual + grow * ep.ldr + col));
@@ -270,7 +270,7 @@ __device__ __forceinline__ void epilogue_rows_slow(uint32_t stg, const Epilogue 
                 const float u = __bfloat162float(ep.residual[grow * ep.ldr + col + q]);
                 y *= (ep.act == 5 ? act_grad<5>(u) : (ep.act == 6 ? act_grad<6>(u) : act_grad<7>(u))) * ep.out_scale;
                 if (ep.drop_thresh)
-                    y = drop_keep(ep.drop_seed, (unsigned long long)grow * ep.ldc + col + q, ep.drop_thresh) ? y * ep.drop_scale : 0.f;
+                    y = drop_keep32(ep.drop_seed.key0, (uint32_t)(grow * ep.ldc + col + q), ep.drop_thresh) ? y * ep.drop_scale : 0.f;
             } else {
                 if (ep.bias != nullptr) y += __ldg(ep.bias + col + q);
                 float gq = 1.f;
@@ -284,7 +284,7 @@ __device__ __forceinline__ void epilogue_rows_slow(uint32_t stg, const Epilogue 
                 if (ep.preact != nullptr) ep.preact[grow * ep.ldc + col + q] = __float2bfloat16_rn(gq);
                 y *= ep.out_scale;
                 if (ep.drop_thresh)
-                    y = drop_keep(ep.drop_seed, (unsigned long long)grow * ep.ldc + col + q, ep.drop_thresh) ? y * ep.drop_scale : 0.f;
+                    y = drop_keep32(ep.drop_seed.key0, (uint32_t)(grow * ep.ldc + col + q), ep.drop_thresh) ? y * ep.drop_scale : 0.f;
                 if (ep.residual != nullptr) y += __bfloat162float(ep.residual[grow * ep.ldr + col + q]) * ep.res_scale;
             }
             if (ep.accumulate) atomicAdd((float *)ep.C + grow * ep.ldc + col + q, y);
@@ -359,9 +359,9 @@ __device__ __forceinline__ void epilogue_tma(const uint32_t (&acc)[32], const Ep
             }
         }
         if (ep.drop_thresh) {
-            const unsigned long long i0 = (unsigned long long)grow * ep.ldc + col0 + c * 8;
+            const uint32_t i0 = (uint32_t)(grow * ep.ldc + col0 + c * 8);   // < 2^32 (host check)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = drop_keep(ep.drop_seed, i0 + j, ep.drop_thresh) ? x[j] * ep.drop_scale : 0.f;
+            for (int j = 0; j < 8; ++j) x[j] = drop_keep32(ep.drop_seed.key0, i0 + j, ep.drop_thresh) ? x[j] * ep.drop_scale : 0.f;
         }
         if (ACT < 5 && ep.residual != nullptr) {
 #pragma unroll
@@ -775,8 +775,9 @@ static int dispatch_bn(const CUtensorMap &ma, const void *W, int ldw, int M, int
     return launch_gemm<128, 4, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
 }
 
-static int check_epilogue(const pose_gemm_epilogue *e, int N, Epilogue &ep) {
+static int check_epilogue(const pose_gemm_epilogue *e, long M, int N, Epilogue &ep) {
     if (!e || !e->C) return POSE_E_NULL;
+    if (e->drop_p > 0.f && (double)M * (double)e->ldc >= 4294967296.0) return POSE_E_UNSUPPORTED;   // 32-bit mask counter
     if (e->ldc < N || (e->residual && e->ldr < N)) return POSE_E_SHAPE;
     if (e->act < 0 || e->act > 7 || (e->out_dtype != 0 && e->out_dtype != 1)) return POSE_E_UNSUPPORTED;
     if (e->act >= 5 && !e->residual) return POSE_E_NULL;        // act' needs the saved pre-activation
@@ -800,7 +801,7 @@ static int check_epilogue(const pose_gemm_epilogue *e, int N, Epilogue &ep) {
     if (e->drop_p < 0.f || e->drop_p >= 1.f) return POSE_E_SHAPE;
     ep.drop_thresh = e->drop_p > 0.f ? drop_threshold(e->drop_p) : 0u;
     ep.drop_scale = e->drop_p > 0.f ? 1.0f / (1.0f - e->drop_p) : 1.0f;
-    ep.drop_seed = e->drop_seed;
+    ep.drop_seed = make_drop_seed(e->drop_seed);
     return POSE_OK;
 }
 
@@ -815,7 +816,7 @@ POSE_API int pose_gemm_bf16_ex(const void *A, int lda, const void *W, int ldw, i
     if (lda % 8 || ldw % 8) return POSE_E_SHAPE;  // TMA: row pitch must be a multiple of 16 bytes
     if ((uintptr_t)A % 16 || (uintptr_t)W % 16) return POSE_E_ALIGN;
     Epilogue ep;
-    int e = check_epilogue(epilogue, N, ep);
+    int e = check_epilogue(epilogue, M, N, ep);
     if (e) return e;
     CUtensorMap ma;
     e = make_map_2d(&ma, A, M, K, lda, BM, 64);
@@ -846,7 +847,7 @@ POSE_API int pose_gemm_bf16_tr(const void *A, long lda, int a_mn, const void *W,
     if (lda < (a_mn ? M : K) || ldw < (b_mn ? N : K) || lda % 8 || ldw % 8) return POSE_E_SHAPE;
     if ((uintptr_t)A % 16 || (uintptr_t)W % 16) return POSE_E_ALIGN;
     Epilogue ep;
-    int e = check_epilogue(epilogue, N, ep);
+    int e = check_epilogue(epilogue, M, N, ep);
     if (e) return e;
     if (k_splits > 1 && !ep.accumulate) return POSE_E_UNSUPPORTED;   // partial sums must be accumulated
     CUtensorMap ma, mw;
@@ -897,7 +898,7 @@ POSE_API int pose_conv2d_bf16(const void *X, int Nimg, int H, int Wd, int Cin, c
     if (TW * TH * TN != BM || Ho % TH || Wo % TW) return POSE_E_UNSUPPORTED;
     const int K = KH * KW * Cin, N = Cout;
     Epilogue ep;
-    int e = check_epilogue(epilogue, N, ep);
+    int e = check_epilogue(epilogue, (long)Nimg * Ho * Wo, N, ep);
     if (e) return e;
     CUtensorMap ma;
     e = make_map_nhwc(&ma, X, Nimg, H, Wd, Cin, bkc, TW, TH, TN, stride);
@@ -932,7 +933,7 @@ POSE_API int pose_conv2d_wgrad_bf16(const void *dY, const void *X, int Nimg, int
     const int M = Cout, N = KH * KW * Cin, K = patches * 64;
     pose_gemm_epilogue pe = {nullptr, nullptr, dWk, N, 0, 0, 0, 1.0f, 0.0f, nullptr, 1, 0, 0ull, 0.0f, 0};
     Epilogue ep;
-    int e = check_epilogue(&pe, N, ep);
+    int e = check_epilogue(&pe, M, N, ep);
     if (e) return e;
     CUtensorMap ma, mw;
     e = make_map_nhwc(&ma, dY, Nimg, Ho, Wo, Cout, 64, TW, TH, TN, 1);
