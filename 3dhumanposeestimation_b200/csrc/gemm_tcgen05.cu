@@ -763,13 +763,34 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
     return launch_status();
 }
 
+// 128 x 256 tiles (3 stages of 48 KB): the 128 x 128 main loop reads 32 KB of operands per 256 tensor-core cycles, which is
+// the whole 128 B/clk shared-memory read bandwidth of the SM; the wide tile needs 96 B/clk.  Used for plain epilogues
+// (the TMA-store epilogue of the GELU / derivative GEMMs is a 128-column design) when there are enough tiles to go round.
+static bool wide_tile_ok(const Epilogue &ep, int N, int K, int m_tiles, int k_splits) {
+    static const bool off = getenv("POSE_GEMM_NO_BN256") != nullptr;      // A/B switch for measurements
+    if (off || N % 256 || K < 512) return false;          // short contractions are output-write bound: nothing to gain
+    const bool heavy = ep.act == 3 || ep.act >= 5 || ep.preact != nullptr;
+    if (heavy && ep.out_bf16 && !ep.accumulate && ep.vec) return false;  // those take the TMA-store epilogue
+    return (long)m_tiles * (N / 256) * k_splits >= kNumSMs;
+}
+// short contractions with per-element epilogue work (activation, residual read) are epilogue bound: two 32-column chunks
+// per epilogue warp lose to the 128-column tile there (measured: 37.0 vs 34.4 us at K = 768 with a residual)
+static bool wide_tile_fwd_ok(const Epilogue &ep, int N, int K, int m_tiles) {
+    if ((ep.act != 0 || ep.residual != nullptr) && K < 1024) return false;
+    return wide_tile_ok(ep, N, K, m_tiles, 1);
+}
+
 template <int BKC, int MODE>
 static int dispatch_bn(const CUtensorMap &ma, const void *W, int ldw, int M, int N, int K, const Epilogue &ep,
                        const ConvGeom &cg, int m_tiles, cudaStream_t s) {
     CUtensorMap mw;
-    const int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+    int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+    if (MODE == 0 && BKC == 64 && wide_tile_fwd_ok(ep, N, K, m_tiles)) bn = 256;
     int e = make_map_2d(&mw, W, N, K, ldw, bn, BKC);
     if (e) return e;
+    if constexpr (MODE == 0 && BKC == 64) {
+        if (bn == 256) return launch_gemm<256, 3, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
+    }
     if (bn == 32) return launch_gemm<32, 6, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
     if (bn == 64) return launch_gemm<64, 6, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
     return launch_gemm<128, 4, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
@@ -865,6 +886,11 @@ POSE_API int pose_gemm_bf16_tr(const void *A, long lda, int a_mn, const void *W,
     if (N <= 64) {
         if (a_mn) return launch_gemm<64, 6, 64, 0, 1, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);
         return launch_gemm<64, 6, 64, 0, 0, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);
+    }
+    if (wide_tile_ok(ep, N, K / (k_splits > 1 ? k_splits : 1), m_tiles, k_splits > 1 ? 2 * k_splits : 1)) {
+        if (k_splits > 1) k_splits *= 2;                 // the caller sized the splits for 128-column tiles
+        if (a_mn) return launch_gemm<256, 3, 64, 0, 1, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);
+        return launch_gemm<256, 3, 64, 0, 0, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);
     }
     if (a_mn) return launch_gemm<128, 4, 64, 0, 1, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);
     return launch_gemm<128, 4, 64, 0, 0, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);

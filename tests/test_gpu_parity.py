@@ -341,7 +341,9 @@ def _ref_linear(a_bf16, w_bf16, bias, act):
 
 @pytest.mark.parametrize("M,N,K,act", [(256, 1024, 1024, "silu"), (128, 128, 64, None), (1, 51, 512, None),
                                        (300, 200, 136, "gelu"), (257, 768, 3072, "relu"), (4096, 64, 64, None),
-                                       (130, 16, 512, None), (1000, 3072, 768, "gelu")])
+                                       (130, 16, 512, None), (1000, 3072, 768, "gelu"),
+                                       # 128 x 256 tiles (N % 256 == 0 and >= 148 tiles), ragged last M tile
+                                       (16448, 768, 768, "silu"), (6500, 2304, 320, None)])
 def test_gemm_tcgen05_matches_fp32_reference(pose, M, N, K, act):
     g = torch.Generator(device="cpu").manual_seed(M * 31 + N)
     a = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()

@@ -32,7 +32,7 @@ def _tr(pose, A, a_mn, W, b_mn, M, N, K, splits, e):
 
 
 @pytest.mark.parametrize("M,Nout,Kin", [(257 * 3, 768, 768), (300, 51, 256), (1000, 3072, 768), (64, 256, 512),
-                                        (130, 64, 128)])
+                                        (130, 64, 128), (16448, 768, 768), (8200, 3072, 768)])   # the last two: 128 x 256 tiles
 def test_data_gradient_gemm_reads_the_weight_in_place(pose, M, Nout, Kin):
     g = torch.Generator().manual_seed(M + Nout)
     ldy = (Nout + 7) // 8 * 8
@@ -61,7 +61,8 @@ def test_data_gradient_gemm_reads_the_weight_in_place(pose, M, Nout, Kin):
 
 
 @pytest.mark.parametrize("M,Nout,Kin,splits", [(257 * 8, 768, 768, 4), (1000, 51, 256, 3), (4096, 3072, 768, 1),
-                                               (64, 1024, 768, 1), (333, 200, 72, 2)])
+                                               (64, 1024, 768, 1), (333, 200, 72, 2),
+                                               (4096, 3072, 768, 4), (16448, 768, 3072, 6)])   # the last two: 128 x 256 tiles
 def test_weight_gradient_gemm_split_k_accumulates(pose, M, Nout, Kin, splits):
     g = torch.Generator().manual_seed(M + Nout + 1)
     ldy = (Nout + 7) // 8 * 8
