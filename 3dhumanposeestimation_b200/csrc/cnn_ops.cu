@@ -137,127 +137,139 @@ __device__ __forceinline__ void dw_stage_tile(unsigned char *buf, const __nv_bfl
 // PERSISTENT: a CTA walks (image, tile) pairs of its 64-channel slab; the next tile's halo is in flight (cp.async, second
 // buffer) while the current one is computed -- the one-tile-per-CTA version left every global-load latency exposed at
 // two CTAs per SM.
+__device__ __forceinline__ void unpack4(const uint2 &p, float (&f)[4]) {
+    const float2 t0 = __bfloat1622float2(*(const __nv_bfloat162 *)&p.x), t1 = __bfloat1622float2(*(const __nv_bfloat162 *)&p.y);
+    f[0] = t0.x; f[1] = t0.y; f[2] = t1.x; f[3] = t1.y;
+}
+__device__ __forceinline__ uint2 pack4(const float (&f)[4]) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+    return make_uint2(*(uint32_t *)&p0, *(uint32_t *)&p1);
+}
+
+// A thread owns FOUR channels (16 channel groups x 16 pixel lanes): 36 filter taps in registers instead of 72 keeps the
+// kernel under 85 registers, so three CTAs (24 warps, three halo tiles in flight) share an SM; with eight channels per
+// thread it ran one CTA per SM at 20 % of the HBM roofline.
 template <int STRIDE, int ACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ Wd, const float *__restrict__ bias,
                  int B, int H, int W, int C, __nv_bfloat16 *__restrict__ Y, float *__restrict__ pool, int Ho, int Wo,
                  int tiles_x, int tiles_y) {
     using T = DwTile<STRIDE>;
     extern __shared__ __align__(16) unsigned char s_dyn[];      // 2 halo buffers, then the pooled-sum scratch
-    unsigned char *bufs[2] = {s_dyn, s_dyn + T::kSmem};
     float(*s_part)[kDwSlab] = (float(*)[kDwSlab])(s_dyn + 2 * T::kSmem);
     const int per_img = tiles_x * tiles_y;
     const long n_items = (long)B * per_img;
     const int c_slab = blockIdx.y * kDwSlab;
-    const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;       // 8 channel groups x 32 pixel lanes
-    const int c0 = c_slab + cg * 8;
+    const int cg = threadIdx.x & 15, pl = threadIdx.x >> 4;      // 16 channel groups of 4 x 16 pixel lanes
+    const int c0 = c_slab + cg * 4;
     const bool c_ok = c0 < C;
-    float w[9][8], bs[8];
+    float w[9][4], bs[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 4; ++k) {
         bs[k] = c_ok ? __ldg(bias + c0 + k) : 0.f;
 #pragma unroll
         for (int t = 0; t < 9; ++t) w[t][k] = c_ok ? __ldg(Wd + (long)t * C + c0 + k) : 0.f;
     }
     long item = blockIdx.x;
-    if (item < n_items) dw_stage_tile<STRIDE>(bufs[0], X, H, W, C, (int)(item / per_img), (int)(item % per_img), tiles_x, c_slab);
+    if (item < n_items) dw_stage_tile<STRIDE>(s_dyn, X, H, W, C, (int)(item / per_img), (int)(item % per_img), tiles_x, c_slab);
     for (int it = 0; item < n_items; item += gridDim.x, ++it) {
         const long next = item + gridDim.x;
         if (next < n_items)
-            dw_stage_tile<STRIDE>(bufs[(it + 1) & 1], X, H, W, C, (int)(next / per_img), (int)(next % per_img), tiles_x, c_slab);
+            dw_stage_tile<STRIDE>(s_dyn + ((it + 1) & 1) * T::kSmem, X, H, W, C, (int)(next / per_img), (int)(next % per_img),
+                                  tiles_x, c_slab);
         else
             cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const unsigned char *s_in = bufs[it & 1];
+        const unsigned char *s_in = s_dyn + (it & 1) * T::kSmem + cg * 8;      // this thread's channels of pixel 0
         const int b = (int)(item / per_img), tile = (int)(item - (long)b * per_img);
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         const int oy0 = ty * T::TH, ox0 = tx * T::TW;
-        float psum[8];
+        float psum[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) psum[k] = 0.f;
+        for (int k = 0; k < 4; ++k) psum[k] = 0.f;
         constexpr int kPix = T::TH * T::TW;
         if (STRIDE == 1) {
-            // a thread owns a column of 4 output rows, two at a time: the 4 x 3 input vectors of a pair are read once and
-            // feed both outputs (24 shared-memory loads per 4 outputs instead of 36: the kernel is shared-memory bound)
-            const int pxx = pl & (T::TW - 1), rb = pl / T::TW;
+            // a thread owns one column of the 8 x 16 tile, two output rows at a time: the 4 x 3 input vectors of a pair are
+            // read once and feed both outputs (24 shared-memory loads per 4 outputs instead of 36)
+            static_assert(STRIDE != 1 || T::TW == 16, "one pixel lane per tile column");
+            const int pxx = pl;
+            const int ox = ox0 + pxx;
+#pragma unroll 1
+            for (int r0 = 0; r0 < T::TH; r0 += 2) {
+                float a0[4], a1[4];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int r0 = rb * 4 + q * 2;
-                float a0[8], a1[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) a0[k] = a1[k] = bs[k];
+                for (int k = 0; k < 4; ++k) a0[k] = a1[k] = bs[k];
 #pragma unroll
                 for (int ir = 0; ir < 4; ++ir)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
-                        float f[8];
-                        unpack8(*(const uint4 *)(s_in + (((r0 + ir) * T::IW + pxx + kx) * 8 + cg) * 16), f);
+                        float f[4];
+                        unpack4(*(const uint2 *)(s_in + ((r0 + ir) * T::IW + pxx + kx) * 128), f);
                         if (ir < 3) {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) a0[k] = fmaf(f[k], w[ir * 3 + kx][k], a0[k]);
+                            for (int k = 0; k < 4; ++k) a0[k] = fmaf(f[k], w[ir * 3 + kx][k], a0[k]);
                         }
                         if (ir > 0) {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) a1[k] = fmaf(f[k], w[(ir - 1) * 3 + kx][k], a1[k]);
+                            for (int k = 0; k < 4; ++k) a1[k] = fmaf(f[k], w[(ir - 1) * 3 + kx][k], a1[k]);
                         }
                     }
-                const int ox = ox0 + pxx;
                 if (ox < Wo && c_ok) {
                     if (oy0 + r0 < Ho) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
+                        for (int k = 0; k < 4; ++k) {
                             a0[k] = act_t<ACT>(a0[k]);
                             psum[k] += a0[k];
                         }
-                        *(uint4 *)(Y + (((long)b * Ho + oy0 + r0) * Wo + ox) * C + c0) = pack8(a0);
+                        *(uint2 *)(Y + (((long)b * Ho + oy0 + r0) * Wo + ox) * C + c0) = pack4(a0);
                     }
                     if (oy0 + r0 + 1 < Ho) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
+                        for (int k = 0; k < 4; ++k) {
                             a1[k] = act_t<ACT>(a1[k]);
                             psum[k] += a1[k];
                         }
-                        *(uint4 *)(Y + (((long)b * Ho + oy0 + r0 + 1) * Wo + ox) * C + c0) = pack8(a1);
+                        *(uint2 *)(Y + (((long)b * Ho + oy0 + r0 + 1) * Wo + ox) * C + c0) = pack4(a1);
                     }
                 }
             }
         } else {
+#pragma unroll 1
+            for (int q = 0; q < kPix / 16; ++q) {
+                const int p = q * 16 + pl;
+                const int py = p / T::TW, pxx = p - py * T::TW;
+                const int oy = oy0 + py, ox = ox0 + pxx;
+                float acc[4];
 #pragma unroll
-        for (int q = 0; q < kPix / 32; ++q) {
-            const int p = q * 32 + pl;
-            const int py = p / T::TW, pxx = p - py * T::TW;
-            const int oy = oy0 + py, ox = ox0 + pxx;
-            float acc[8];
+                for (int k = 0; k < 4; ++k) acc[k] = bs[k];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = bs[k];
+                for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+                    for (int kx = 0; kx < 3; ++kx) {
+                        float f[4];
+                        unpack4(*(const uint2 *)(s_in + ((py * STRIDE + ky) * T::IW + pxx * STRIDE + kx) * 128), f);
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    float f[8];
-                    unpack8(*(const uint4 *)(s_in + (((py * STRIDE + ky) * T::IW + pxx * STRIDE + kx) * 8 + cg) * 16), f);
+                        for (int k = 0; k < 4; ++k) acc[k] = fmaf(f[k], w[ky * 3 + kx][k], acc[k]);
+                    }
+                if (oy < Ho && ox < Wo && c_ok) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[k] = fmaf(f[k], w[ky * 3 + kx][k], acc[k]);
+                    for (int k = 0; k < 4; ++k) {
+                        acc[k] = act_t<ACT>(acc[k]);
+                        psum[k] += acc[k];
+                    }
+                    *(uint2 *)(Y + (((long)b * Ho + oy) * Wo + ox) * C + c0) = pack4(acc);
                 }
-            if (oy < Ho && ox < Wo && c_ok) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    acc[k] = act_t<ACT>(acc[k]);
-                    psum[k] += acc[k];
-                }
-                *(uint4 *)(Y + (((long)b * Ho + oy) * Wo + ox) * C + c0) = pack8(acc);
             }
         }
-        }
-        if (pool != nullptr) {  // fixed-order reduction over the 32 pixel lanes of the CTA, one write per channel
+        if (pool != nullptr) {  // fixed-order reduction over the 16 pixel lanes of the CTA, one write per channel
 #pragma unroll
-            for (int k = 0; k < 8; ++k) s_part[pl][cg * 8 + k] = psum[k];
+            for (int k = 0; k < 4; ++k) s_part[pl][cg * 4 + k] = psum[k];
             __syncthreads();
             if (threadIdx.x < kDwSlab && c_slab + threadIdx.x < C) {
                 float t = 0.f;
 #pragma unroll 8
-                for (int q = 0; q < 32; ++q) t += s_part[q][threadIdx.x];
+                for (int q = 0; q < 16; ++q) t += s_part[q][threadIdx.x];
                 pool[((long)b * per_img + tile) * C + c_slab + threadIdx.x] = t;
             }
         }
@@ -526,12 +538,12 @@ POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, cons
     const int tiles_y = (Ho + th - 1) / th, tiles_x = (Wo + tw - 1) / tw;
     const int gy = (C + kDwSlab - 1) / kDwSlab;
     long gx = (long)B * tiles_x * tiles_y;
-    const long cap = ((long)kNumSMs * 4 + gy - 1) / gy;           // ~4 resident CTAs per SM over all channel slabs
+    const long cap = ((long)kNumSMs * 3 + gy - 1) / gy;           // 3 resident CTAs per SM over all channel slabs
     if (gx > cap) gx = cap;
     dim3 grid((unsigned)gx, gy);
     cudaStream_t s = (cudaStream_t)stream;
     if (act < 0 || act > 4) return POSE_E_UNSUPPORTED;
-    const int smem = 2 * (stride == 1 ? DwTile<1>::kSmem : DwTile<2>::kSmem) + 32 * kDwSlab * 4;
+    const int smem = 2 * (stride == 1 ? DwTile<1>::kSmem : DwTile<2>::kSmem) + 16 * kDwSlab * 4;
 #define DW_LAUNCH(S_, A_)                                                                                             \
     {                                                                                                                 \
         static bool cfg = false;                                                                                      \

@@ -379,14 +379,12 @@ struct DwT {
     static constexpr int IH = (TH - 1) * STRIDE + 3, IW = (TW - 1) * STRIDE + 3;
 };
 template <int STRIDE>
-__device__ __forceinline__ void dww_stage(unsigned char *xbuf, unsigned char *ybuf, const __nv_bfloat16 *__restrict__ X,
-                                          const __nv_bfloat16 *__restrict__ dY, int H, int W, int C, int Ho, int Wo, int b,
+__device__ __forceinline__ void dww_stage(unsigned char *xbuf, const __nv_bfloat16 *__restrict__ X, int H, int W, int C, int b,
                                           int tile, int tiles_x, int c_slab) {
     using T = DwT<STRIDE>;
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    const int oy0 = ty * T::TH, ox0 = tx * T::TW;
-    const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
-    const __nv_bfloat16 *xb = X + (long)b * H * W * C, *yb = dY + (long)b * Ho * Wo * C;
+    const int iy0 = ty * T::TH * STRIDE - 1, ix0 = tx * T::TW * STRIDE - 1;
+    const __nv_bfloat16 *xb = X + (long)b * H * W * C;
     for (int i = threadIdx.x; i < T::IH * T::IW * 8; i += 256) {
         const int px = i >> 3, g = i & 7;
         const int py = px / T::IW, pxx = px - py * T::IW;
@@ -394,103 +392,113 @@ __device__ __forceinline__ void dww_stage(unsigned char *xbuf, unsigned char *yb
         const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W && c_slab + g * 8 < C;
         cp_async16(xbuf + (px * 8 + g) * 16, ok ? (const void *)(xb + ((long)iy * W + ix) * C + c_slab + g * 8) : (const void *)X, ok);
     }
-    for (int i = threadIdx.x; i < T::TH * T::TW * 8; i += 256) {
-        const int p = i >> 3, g = i & 7;
-        const int py = p / T::TW, pxx = p - py * T::TW;
-        const int oy = oy0 + py, ox = ox0 + pxx;
-        const bool ok = oy < Ho && ox < Wo && c_slab + g * 8 < C;      // zero gradient outside: contributes nothing
-        cp_async16(ybuf + (p * 8 + g) * 16, ok ? (const void *)(yb + ((long)oy * Wo + ox) * C + c_slab + g * 8) : (const void *)dY, ok);
-    }
     cp_async_commit();
 }
-
+__device__ __forceinline__ void up4(const uint2 &p, float (&f)[4]) {
+    const float2 t0 = __bfloat1622float2(*(const __nv_bfloat162 *)&p.x), t1 = __bfloat1622float2(*(const __nv_bfloat162 *)&p.y);
+    f[0] = t0.x; f[1] = t0.y; f[2] = t1.x; f[3] = t1.y;
+}
+// A thread owns FOUR channels of one tile column (16 channel groups x 16 pixel lanes): 36 fp32 partials instead of 72, and
+// the output gradients -- each used by exactly one thread -- come straight from global memory into registers while the
+// halo tile is in flight, so three CTAs share an SM (was one, at 136 registers and 79 KB of shared memory).
 template <int STRIDE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 dwconv_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ dY, const __nv_bfloat16 *__restrict__ X, int B, int H, int W, int C,
                          int Ho, int Wo, int tiles_x, int tiles_y, float *__restrict__ dW) {
     using T = DwT<STRIDE>;
-    constexpr int kX = T::IH * T::IW * 128, kY = T::TH * T::TW * 128;
-    extern __shared__ __align__(16) unsigned char s_dyn[];      // 2 x (input halo tile + gradient tile); the fold reuses it
-    unsigned char *xb[2] = {s_dyn, s_dyn + kX + kY}, *yb[2] = {s_dyn + kX, s_dyn + 2 * kX + kY};
-    const int cgi = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    constexpr int kX = T::IH * T::IW * 128;
+    constexpr int kPix = T::TH * T::TW, kMine = kPix / 16;      // output pixels per thread
+    extern __shared__ __align__(16) unsigned char s_dyn[];      // 2 input halo tiles; the fold reuses them
+    const int cgi = threadIdx.x & 15, pl = threadIdx.x >> 4;
     const int c_slab = blockIdx.y * 64;
-    float acc[9][8];
+    const int c0 = c_slab + cgi * 4;
+    float acc[9][4];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
     const int per_img = tiles_x * tiles_y;
     const long n_tiles = (long)B * per_img;
     long item = blockIdx.x;
-    if (item < n_tiles)
-        dww_stage<STRIDE>(xb[0], yb[0], X, dY, H, W, C, Ho, Wo, (int)(item / per_img), (int)(item % per_img), tiles_x, c_slab);
+    if (item < n_tiles) dww_stage<STRIDE>(s_dyn, X, H, W, C, (int)(item / per_img), (int)(item % per_img), tiles_x, c_slab);
     for (int it = 0; item < n_tiles; item += gridDim.x, ++it) {
         const long next = item + gridDim.x;
         if (next < n_tiles)
-            dww_stage<STRIDE>(xb[(it + 1) & 1], yb[(it + 1) & 1], X, dY, H, W, C, Ho, Wo, (int)(next / per_img),
-                              (int)(next % per_img), tiles_x, c_slab);
+            dww_stage<STRIDE>(s_dyn + ((it + 1) & 1) * kX, X, H, W, C, (int)(next / per_img), (int)(next % per_img), tiles_x, c_slab);
         else
             cp_async_commit();
+        // this thread's output gradients (zero outside the image / channel range: they contribute nothing)
+        const int b = (int)(item / per_img), tile = (int)(item - (long)b * per_img);
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int oy0 = ty * T::TH, ox0 = tx * T::TW;
+        uint2 dyr[kMine];
+#pragma unroll
+        for (int q = 0; q < kMine; ++q) {
+            const int p = STRIDE == 1 ? q * T::TW + pl : q * 16 + pl;     // stride 1: column pl, row q
+            const int py = p / T::TW, pxx = p - py * T::TW;
+            const int oy = oy0 + py, ox = ox0 + pxx;
+            dyr[q] = make_uint2(0u, 0u);
+            if (oy < Ho && ox < Wo && c0 < C) dyr[q] = __ldg((const uint2 *)(dY + (((long)b * Ho + oy) * Wo + ox) * C + c0));
+        }
         cp_async_wait<1>();
         __syncthreads();
-        const unsigned char *s_in = xb[it & 1], *s_dy = yb[it & 1];
-        constexpr int kPix = T::TH * T::TW;
+        const unsigned char *s_in = s_dyn + (it & 1) * kX + cgi * 8;
         if (STRIDE == 1) {
-            // two vertically adjacent outputs share their 4 x 3 input vectors (12 + 2 loads instead of 18 + 2)
-            const int pxx = pl & (T::TW - 1), rb = pl / T::TW;
+            // two vertically adjacent outputs share their 4 x 3 input vectors (12 loads instead of 18)
+            const int pxx = pl;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int r0 = rb * 4 + q * 2;
-                float d0[8], d1[8];
-                up8(*(const uint4 *)(s_dy + ((r0 * T::TW + pxx) * 8 + cgi) * 16), d0);
-                up8(*(const uint4 *)(s_dy + (((r0 + 1) * T::TW + pxx) * 8 + cgi) * 16), d1);
+            for (int q = 0; q < kMine / 2; ++q) {
+                const int r0 = q * 2;
+                float d0[4], d1[4];
+                up4(dyr[r0], d0);
+                up4(dyr[r0 + 1], d1);
 #pragma unroll
                 for (int ir = 0; ir < 4; ++ir)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
-                        float x[8];
-                        up8(*(const uint4 *)(s_in + (((r0 + ir) * T::IW + pxx + kx) * 8 + cgi) * 16), x);
+                        float x[4];
+                        up4(*(const uint2 *)(s_in + ((r0 + ir) * T::IW + pxx + kx) * 128), x);
                         if (ir < 3) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) acc[ir * 3 + kx][j] = fmaf(d0[j], x[j], acc[ir * 3 + kx][j]);
+                            for (int j = 0; j < 4; ++j) acc[ir * 3 + kx][j] = fmaf(d0[j], x[j], acc[ir * 3 + kx][j]);
                         }
                         if (ir > 0) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) acc[(ir - 1) * 3 + kx][j] = fmaf(d1[j], x[j], acc[(ir - 1) * 3 + kx][j]);
+                            for (int j = 0; j < 4; ++j) acc[(ir - 1) * 3 + kx][j] = fmaf(d1[j], x[j], acc[(ir - 1) * 3 + kx][j]);
                         }
                     }
             }
         } else {
 #pragma unroll
-        for (int q = 0; q < kPix / 32; ++q) {
-            const int p = q * 32 + pl;
-            const int py = p / T::TW, pxx = p - py * T::TW;
-            float d[8];
-            up8(*(const uint4 *)(s_dy + (p * 8 + cgi) * 16), d);
+            for (int q = 0; q < kMine; ++q) {
+                const int p = q * 16 + pl;
+                const int py = p / T::TW, pxx = p - py * T::TW;
+                float d[4];
+                up4(dyr[q], d);
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+                for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    float x[8];
-                    up8(*(const uint4 *)(s_in + (((py * STRIDE + ky) * T::IW + pxx * STRIDE + kx) * 8 + cgi) * 16), x);
+                    for (int kx = 0; kx < 3; ++kx) {
+                        float x[4];
+                        up4(*(const uint2 *)(s_in + ((py * STRIDE + ky) * T::IW + pxx * STRIDE + kx) * 128), x);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(d[j], x[j], acc[ky * 3 + kx][j]);
-                }
-        }
+                        for (int j = 0; j < 4; ++j) acc[ky * 3 + kx][j] = fmaf(d[j], x[j], acc[ky * 3 + kx][j]);
+                    }
+            }
         }
         __syncthreads();
     }
     float(*red)[65] = (float(*)[65])s_dyn;
-#pragma unroll 1
+#pragma unroll                        // (a rolled loop would index acc dynamically and push it to local memory)
     for (int t = 0; t < 9; ++t) {
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[pl][cgi * 8 + j] = acc[t][j];
+        for (int j = 0; j < 4; ++j) red[pl][cgi * 4 + j] = acc[t][j];
         __syncthreads();
         if (threadIdx.x < 64 && c_slab + threadIdx.x < C) {
             float sacc = 0.f;
 #pragma unroll 8
-            for (int q = 0; q < 32; ++q) sacc += red[q][threadIdx.x];
+            for (int q = 0; q < 16; ++q) sacc += red[q][threadIdx.x];
             atomicAdd(dW + (long)(c_slab + threadIdx.x) * 9 + t, sacc);
         }
     }
@@ -970,8 +978,8 @@ POSE_API int pose_dwconv3x3_bwd_bf16(const void *dY, const void *X, const float 
         long gx = (long)B * tiles_x * tiles_y;
         const long cap = (kNumSMs * 3 + gy - 1) / gy;
         if (gx > cap) gx = cap;
-        const int smem1 = 2 * (DwT<1>::IH * DwT<1>::IW + DwT<1>::TH * DwT<1>::TW) * 128;
-        const int smem2 = 2 * (DwT<2>::IH * DwT<2>::IW + DwT<2>::TH * DwT<2>::TW) * 128;
+        const int smem1 = 2 * DwT<1>::IH * DwT<1>::IW * 128;
+        const int smem2 = 2 * DwT<2>::IH * DwT<2>::IW * 128;
         static bool cfg = false;
         if (!cfg) {
             cudaError_t ce = cudaFuncSetAttribute(dwconv_bwd_weight_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);

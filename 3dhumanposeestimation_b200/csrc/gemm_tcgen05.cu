@@ -316,20 +316,31 @@ __device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
 // byte offset of 16-byte chunk c of row r in a [32 x 64 B] SWIZZLE_64B tile
 __device__ __forceinline__ uint32_t sw64(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
+// The accumulator chunk is read 8 columns at a time (a 576-thread CTA caps the kernel at 96 registers: with all 32
+// accumulators live the exact-GELU / derivative epilogues kept ~58 words per thread in local memory); the TMEM stage is
+// released after the last load.
 template <int ACT>
-__device__ __forceinline__ void epilogue_tma(const uint32_t (&acc)[32], const Epilogue &ep, const CUtensorMap *map_c,
-                                             const CUtensorMap *map_pre, uint32_t out_stg, uint32_t aux_stg, uint64_t *auxbar,
-                                             uint32_t &aux_phase, long row0, int lane, int col0) {
+__device__ __forceinline__ void epilogue_tma(uint32_t tmem_chunk, uint64_t *acc_empty_bar, const Epilogue &ep,
+                                             const CUtensorMap *map_c, const CUtensorMap *map_pre, uint32_t out_stg,
+                                             uint32_t aux_stg, uint64_t *auxbar, uint32_t &aux_phase, long row0, int lane,
+                                             int col0) {
     const long grow = row0 + lane;
     if (ep.residual != nullptr) {
         mbar_wait(auxbar, aux_phase);
         aux_phase ^= 1;
     }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {                      // 8 columns at a time keeps the live registers low
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {                      // 8 columns at a time, rolled: low register pressure, 4x less code
+        uint32_t acc[8];
+        tmem_ld8(tmem_chunk + c * 8, acc);
+        if (c == 3) {                                  // the whole chunk has left TMEM: release the accumulator stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty_bar)) : "memory");
+        }
         float x[8], g[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(acc[c * 8 + j]);
+        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(acc[j]);
         float a[8];
         if (ep.residual != nullptr) {
             const uint4 pk = lds128u(aux_stg + sw64(lane, c));
@@ -577,18 +588,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 __syncwarp();
                 mbar_wait(acc_full + as, aph);
                 tc_fence_after();
-                uint32_t acc1[32];
-                if (mine) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(cgrp * 32), acc1);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
+                const uint32_t chunk = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(cgrp * 32);
                 if (mine) {
                     switch (ep.act) {
-#define EPI_TMA(A_) case A_: epilogue_tma<A_>(acc1, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
+#define EPI_TMA(A_) case A_: epilogue_tma<A_>(chunk, acc_empty + as, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
                         EPI_TMA(0) EPI_TMA(1) EPI_TMA(2) EPI_TMA(3) EPI_TMA(4) EPI_TMA(5) EPI_TMA(6)
-                        default: epilogue_tma<7>(acc1, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
+                        default: epilogue_tma<7>(chunk, acc_empty + as, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
 #undef EPI_TMA
                     }
+                } else {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
                 }
             } else {
             long row;       // global output row of tile row r (this lane's accumulator row)

@@ -135,7 +135,7 @@ patchify_kernel(const float *__restrict__ src0, int C0, const float *__restrict_
 // the forward: X / dX / dRes use the input addressing, dY the output addressing.
 // ---------------------------------------------------------------------------------------------------------
 template <int D8PL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__restrict__ dY,
                      const float *__restrict__ gamma, float eps, long M, int rows, long in_group, long in_off,
                      long out_group, long out_off, int D, const __nv_bfloat16 *__restrict__ dRes,
