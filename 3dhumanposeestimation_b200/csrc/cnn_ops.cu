@@ -137,9 +137,10 @@ __device__ __forceinline__ void dw_stage_tile(unsigned char *buf, const __nv_bfl
 // PERSISTENT: a CTA walks (image, tile) pairs of its 64-channel slab; the next tile's halo is in flight (cp.async, second
 // buffer) while the current one is computed -- the one-tile-per-CTA version left every global-load latency exposed at
 // two CTAs per SM.
-__device__ __forceinline__ void unpack4(const uint2 &p, float (&f)[4]) {
-    const float2 t0 = __bfloat1622float2(*(const __nv_bfloat162 *)&p.x), t1 = __bfloat1622float2(*(const __nv_bfloat162 *)&p.y);
-    f[0] = t0.x; f[1] = t0.y; f[2] = t1.x; f[3] = t1.y;
+// four bf16 channels as two fp32 pairs (the operands of the packed FFMA2 of sm_100: two fused multiply-adds per issue slot)
+__device__ __forceinline__ void unpack4(const uint2 &p, float2 (&f)[2]) {
+    f[0] = make_float2(__uint_as_float(p.x << 16), __uint_as_float(p.x & 0xffff0000u));
+    f[1] = make_float2(__uint_as_float(p.y << 16), __uint_as_float(p.y & 0xffff0000u));
 }
 __device__ __forceinline__ uint2 pack4(const float (&f)[4]) {
     __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
@@ -163,12 +164,12 @@ dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ 
     const int cg = threadIdx.x & 15, pl = threadIdx.x >> 4;      // 16 channel groups of 4 x 16 pixel lanes
     const int c0 = c_slab + cg * 4;
     const bool c_ok = c0 < C;
-    float w[9][4], bs[4];
+    float2 w[9][2], bs[2];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        bs[k] = c_ok ? __ldg(bias + c0 + k) : 0.f;
+    for (int k = 0; k < 2; ++k) {
+        bs[k] = c_ok ? __ldg((const float2 *)(bias + c0) + k) : make_float2(0.f, 0.f);
 #pragma unroll
-        for (int t = 0; t < 9; ++t) w[t][k] = c_ok ? __ldg(Wd + (long)t * C + c0 + k) : 0.f;
+        for (int t = 0; t < 9; ++t) w[t][k] = c_ok ? __ldg((const float2 *)(Wd + (long)t * C + c0) + k) : make_float2(0.f, 0.f);
     }
     long item = blockIdx.x;
     if (item < n_items) dw_stage_tile<STRIDE>(s_dyn, X, H, W, C, (int)(item / per_img), (int)(item % per_img), tiles_x, c_slab);
@@ -197,24 +198,23 @@ dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ 
             const int ox = ox0 + pxx;
 #pragma unroll 1
             for (int r0 = 0; r0 < T::TH; r0 += 2) {
-                float a0[4], a1[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) a0[k] = a1[k] = bs[k];
+                float2 v0[2] = {bs[0], bs[1]}, v1[2] = {bs[0], bs[1]};
 #pragma unroll
                 for (int ir = 0; ir < 4; ++ir)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
-                        float f[4];
+                        float2 f[2];
                         unpack4(*(const uint2 *)(s_in + ((r0 + ir) * T::IW + pxx + kx) * 128), f);
                         if (ir < 3) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) a0[k] = fmaf(f[k], w[ir * 3 + kx][k], a0[k]);
+                            for (int k = 0; k < 2; ++k) v0[k] = __ffma2_rn(f[k], w[ir * 3 + kx][k], v0[k]);
                         }
                         if (ir > 0) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) a1[k] = fmaf(f[k], w[(ir - 1) * 3 + kx][k], a1[k]);
+                            for (int k = 0; k < 2; ++k) v1[k] = __ffma2_rn(f[k], w[(ir - 1) * 3 + kx][k], v1[k]);
                         }
                     }
+                float a0[4] = {v0[0].x, v0[0].y, v0[1].x, v0[1].y}, a1[4] = {v1[0].x, v1[0].y, v1[1].x, v1[1].y};
                 if (ox < Wo && c_ok) {
                     if (oy0 + r0 < Ho) {
 #pragma unroll
@@ -240,18 +240,17 @@ dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ 
                 const int p = q * 16 + pl;
                 const int py = p / T::TW, pxx = p - py * T::TW;
                 const int oy = oy0 + py, ox = ox0 + pxx;
-                float acc[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc[k] = bs[k];
+                float2 v[2] = {bs[0], bs[1]};
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
-                        float f[4];
+                        float2 f[2];
                         unpack4(*(const uint2 *)(s_in + ((py * STRIDE + ky) * T::IW + pxx * STRIDE + kx) * 128), f);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) acc[k] = fmaf(f[k], w[ky * 3 + kx][k], acc[k]);
+                        for (int k = 0; k < 2; ++k) v[k] = __ffma2_rn(f[k], w[ky * 3 + kx][k], v[k]);
                     }
+                float acc[4] = {v[0].x, v[0].y, v[1].x, v[1].y};
                 if (oy < Ho && ox < Wo && c_ok) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {

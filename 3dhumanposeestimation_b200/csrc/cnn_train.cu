@@ -394,9 +394,10 @@ __device__ __forceinline__ void dww_stage(unsigned char *xbuf, const __nv_bfloat
     }
     cp_async_commit();
 }
-__device__ __forceinline__ void up4(const uint2 &p, float (&f)[4]) {
-    const float2 t0 = __bfloat1622float2(*(const __nv_bfloat162 *)&p.x), t1 = __bfloat1622float2(*(const __nv_bfloat162 *)&p.y);
-    f[0] = t0.x; f[1] = t0.y; f[2] = t1.x; f[3] = t1.y;
+// four bf16 channels as two fp32 pairs (operands of the packed FFMA2: two fused multiply-adds per issue slot)
+__device__ __forceinline__ void up4(const uint2 &p, float2 (&f)[2]) {
+    f[0] = make_float2(__uint_as_float(p.x << 16), __uint_as_float(p.x & 0xffff0000u));
+    f[1] = make_float2(__uint_as_float(p.y << 16), __uint_as_float(p.y & 0xffff0000u));
 }
 // A thread owns FOUR channels of one tile column (16 channel groups x 16 pixel lanes): 36 fp32 partials instead of 72, and
 // the output gradients -- each used by exactly one thread -- come straight from global memory into registers while the
@@ -412,11 +413,11 @@ dwconv_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ dY, const __nv_bfloat
     const int cgi = threadIdx.x & 15, pl = threadIdx.x >> 4;
     const int c_slab = blockIdx.y * 64;
     const int c0 = c_slab + cgi * 4;
-    float acc[9][4];
+    float2 acc[9][2];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+        for (int j = 0; j < 2; ++j) acc[t][j] = make_float2(0.f, 0.f);
     const int per_img = tiles_x * tiles_y;
     const long n_tiles = (long)B * per_img;
     long item = blockIdx.x;
@@ -449,22 +450,22 @@ dwconv_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ dY, const __nv_bfloat
 #pragma unroll
             for (int q = 0; q < kMine / 2; ++q) {
                 const int r0 = q * 2;
-                float d0[4], d1[4];
+                float2 d0[2], d1[2];
                 up4(dyr[r0], d0);
                 up4(dyr[r0 + 1], d1);
 #pragma unroll
                 for (int ir = 0; ir < 4; ++ir)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
-                        float x[4];
+                        float2 x[2];
                         up4(*(const uint2 *)(s_in + ((r0 + ir) * T::IW + pxx + kx) * 128), x);
                         if (ir < 3) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) acc[ir * 3 + kx][j] = fmaf(d0[j], x[j], acc[ir * 3 + kx][j]);
+                            for (int j = 0; j < 2; ++j) acc[ir * 3 + kx][j] = __ffma2_rn(d0[j], x[j], acc[ir * 3 + kx][j]);
                         }
                         if (ir > 0) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) acc[(ir - 1) * 3 + kx][j] = fmaf(d1[j], x[j], acc[(ir - 1) * 3 + kx][j]);
+                            for (int j = 0; j < 2; ++j) acc[(ir - 1) * 3 + kx][j] = __ffma2_rn(d1[j], x[j], acc[(ir - 1) * 3 + kx][j]);
                         }
                     }
             }
@@ -473,16 +474,16 @@ dwconv_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ dY, const __nv_bfloat
             for (int q = 0; q < kMine; ++q) {
                 const int p = q * 16 + pl;
                 const int py = p / T::TW, pxx = p - py * T::TW;
-                float d[4];
+                float2 d[2];
                 up4(dyr[q], d);
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
-                        float x[4];
+                        float2 x[2];
                         up4(*(const uint2 *)(s_in + ((py * STRIDE + ky) * T::IW + pxx * STRIDE + kx) * 128), x);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[ky * 3 + kx][j] = fmaf(d[j], x[j], acc[ky * 3 + kx][j]);
+                        for (int j = 0; j < 2; ++j) acc[ky * 3 + kx][j] = __ffma2_rn(d[j], x[j], acc[ky * 3 + kx][j]);
                     }
             }
         }
@@ -492,8 +493,8 @@ dwconv_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ dY, const __nv_bfloat
 #pragma unroll                        // (a rolled loop would index acc dynamically and push it to local memory)
     for (int t = 0; t < 9; ++t) {
         __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) red[pl][cgi * 4 + j] = acc[t][j];
+        red[pl][cgi * 4 + 0] = acc[t][0].x; red[pl][cgi * 4 + 1] = acc[t][0].y;
+        red[pl][cgi * 4 + 2] = acc[t][1].x; red[pl][cgi * 4 + 3] = acc[t][1].y;
         __syncthreads();
         if (threadIdx.x < 64 && c_slab + threadIdx.x < C) {
             float sacc = 0.f;
