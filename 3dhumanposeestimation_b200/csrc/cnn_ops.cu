@@ -2,7 +2,7 @@
 // bf16: fused input assembly (heat-map render + concat + cast), depthwise 3x3 + BN + SiLU (+ squeeze sums),
 // SE / ECA / CoordAttention gates, pooling.  The dense convolutions and Linear layers run on the tcgen05
 // GEMM (gemm_tcgen05.cu); everything here moves each activation through HBM exactly once per op.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace pose {
 
@@ -115,23 +115,17 @@ struct DwTile {
     static constexpr int kSmem = IH * IW * kDwSlab * 2;
 };
 
-// Stages the halo tile of (image b, tile) x 64-channel slab with 16-byte asynchronous copies (zero fill outside the image
-// or the channel range); one commit group per tile.
+// The halo tile of (image b, tile) x 64-channel slab is ONE 4-D TMA box {64 channels, IW, IH, 1} over the NHWC tensor:
+// the box starts one pixel above / left of the tile, and everything outside the image or the channel range is zero
+// filled by the copy engine (= the convolution padding).  The per-thread cp.async version spent 27 % of the kernel's
+// instructions on halo index arithmetic.  Called by one thread; the bytes land on `bar`.
 template <int STRIDE>
-__device__ __forceinline__ void dw_stage_tile(unsigned char *buf, const __nv_bfloat16 *__restrict__ X, int H, int W, int C,
-                                              int b, int tile, int tiles_x, int c_slab) {
+__device__ __forceinline__ void dw_stage_tile(unsigned char *buf, const CUtensorMap *map, uint64_t *bar, int b, int tile,
+                                              int tiles_x, int c_slab) {
     using T = DwTile<STRIDE>;
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    const int iy0 = ty * T::TH * STRIDE - 1, ix0 = tx * T::TW * STRIDE - 1;
-    const __nv_bfloat16 *xb = X + (long)b * H * W * C;
-    for (int i = threadIdx.x; i < T::IH * T::IW * 8; i += 256) {
-        const int px = i >> 3, g = i & 7;
-        const int py = px / T::IW, pxx = px - py * T::IW;
-        const int iy = iy0 + py, ix = ix0 + pxx;
-        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W && c_slab + g * 8 < C;
-        cp_async16(buf + (px * 8 + g) * 16, ok ? (const void *)(xb + ((long)iy * W + ix) * C + c_slab + g * 8) : (const void *)X, ok);
-    }
-    cp_async_commit();
+    mbar_expect_tx(bar, T::kSmem);
+    tma_load_4d(buf, map, bar, c_slab, tx * T::TW * STRIDE - 1, ty * T::TH * STRIDE - 1, b);
 }
 
 // PERSISTENT: a CTA walks (image, tile) pairs of its 64-channel slab; the next tile's halo is in flight (cp.async, second
@@ -152,12 +146,19 @@ __device__ __forceinline__ uint2 pack4(const float (&f)[4]) {
 // thread it ran one CTA per SM at 20 % of the HBM roofline.
 template <int STRIDE, int ACT>
 __global__ void __launch_bounds__(256, 3)
-dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ Wd, const float *__restrict__ bias,
+dwconv3x3_kernel(const __grid_constant__ CUtensorMap mapX, const float *__restrict__ Wd, const float *__restrict__ bias,
                  int B, int H, int W, int C, __nv_bfloat16 *__restrict__ Y, float *__restrict__ pool, int Ho, int Wo,
                  int tiles_x, int tiles_y) {
     using T = DwTile<STRIDE>;
-    extern __shared__ __align__(16) unsigned char s_dyn[];      // 2 halo buffers, then the pooled-sum scratch
+    extern __shared__ __align__(128) unsigned char s_dyn[];     // 2 halo buffers, then the pooled-sum scratch
     float(*s_part)[kDwSlab] = (float(*)[kDwSlab])(s_dyn + 2 * T::kSmem);
+    __shared__ uint64_t s_bar[2];                                // one per halo buffer (TMA completion)
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     const int per_img = tiles_x * tiles_y;
     const long n_items = (long)B * per_img;
     const int c_slab = blockIdx.y * kDwSlab;
@@ -172,16 +173,14 @@ dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ 
         for (int t = 0; t < 9; ++t) w[t][k] = c_ok ? __ldg((const float2 *)(Wd + (long)t * C + c0) + k) : make_float2(0.f, 0.f);
     }
     long item = blockIdx.x;
-    if (item < n_items) dw_stage_tile<STRIDE>(s_dyn, X, H, W, C, (int)(item / per_img), (int)(item % per_img), tiles_x, c_slab);
+    if (item < n_items && threadIdx.x == 0)
+        dw_stage_tile<STRIDE>(s_dyn, &mapX, &s_bar[0], (int)(item / per_img), (int)(item % per_img), tiles_x, c_slab);
     for (int it = 0; item < n_items; item += gridDim.x, ++it) {
         const long next = item + gridDim.x;
-        if (next < n_items)
-            dw_stage_tile<STRIDE>(s_dyn + ((it + 1) & 1) * T::kSmem, X, H, W, C, (int)(next / per_img), (int)(next % per_img),
-                                  tiles_x, c_slab);
-        else
-            cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
+        if (next < n_items && threadIdx.x == 0)     // (the buffer was released by the barrier that ended the previous iteration)
+            dw_stage_tile<STRIDE>(s_dyn + ((it + 1) & 1) * T::kSmem, &mapX, &s_bar[(it + 1) & 1], (int)(next / per_img),
+                                  (int)(next % per_img), tiles_x, c_slab);
+        mbar_wait(&s_bar[it & 1], (it >> 1) & 1);
         const unsigned char *s_in = s_dyn + (it & 1) * T::kSmem + cg * 8;      // this thread's channels of pixel 0
         const int b = (int)(item / per_img), tile = (int)(item - (long)b * per_img);
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
@@ -272,7 +271,7 @@ dwconv3x3_kernel(const __nv_bfloat16 *__restrict__ X, const float *__restrict__ 
                 pool[((long)b * per_img + tile) * C + c_slab + threadIdx.x] = t;
             }
         }
-        __syncthreads();     // the buffer just read is the target of the copies issued in the next iteration
+        __syncthreads();     // the buffer just read is the target of the copy issued in the next iteration
     }
 }
 
@@ -543,6 +542,12 @@ POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, cons
     cudaStream_t s = (cudaStream_t)stream;
     if (act < 0 || act > 4) return POSE_E_UNSUPPORTED;
     const int smem = 2 * (stride == 1 ? DwTile<1>::kSmem : DwTile<2>::kSmem) + 16 * kDwSlab * 4;
+    CUtensorMap mapX;
+    {
+        const int e = make_map_dw_halo(&mapX, X, B, H, W, C, stride == 1 ? DwTile<1>::IW : DwTile<2>::IW,
+                                       stride == 1 ? DwTile<1>::IH : DwTile<2>::IH);
+        if (e) return e;
+    }
 #define DW_LAUNCH(S_, A_)                                                                                             \
     {                                                                                                                 \
         static bool cfg = false;                                                                                      \
@@ -551,7 +556,7 @@ POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, cons
             if (ce != cudaSuccess) return (int)ce;                                                                    \
             cfg = true;                                                                                               \
         }                                                                                                             \
-        dwconv3x3_kernel<S_, A_><<<grid, 256, smem, s>>>((const __nv_bfloat16 *)X, Wd, bias, B, H, W, C, (__nv_bfloat16 *)Y, \
+        dwconv3x3_kernel<S_, A_><<<grid, 256, smem, s>>>(mapX, Wd, bias, B, H, W, C, (__nv_bfloat16 *)Y, \
                                                          pool_sum, Ho, Wo, tiles_x, tiles_y);                         \
     }
 #define DW_ACT(S_)                                                                                                    \

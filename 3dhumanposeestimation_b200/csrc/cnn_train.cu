@@ -4,7 +4,7 @@
 // backward of the SE / ECA / CoordAttention gates, of the WASP branch mix and of the pooling layers; dropout; and
 // the per-step re-layout of the parameters the tensor-core kernels read (one table-driven launch).
 // Channels-last bf16 activations, fp32 statistics and parameter gradients (accumulated like torch's .grad).
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace pose {
 
@@ -378,21 +378,14 @@ struct DwT {
     static constexpr int TH = STRIDE == 1 ? 8 : 4, TW = STRIDE == 1 ? 16 : 8;
     static constexpr int IH = (TH - 1) * STRIDE + 3, IW = (TW - 1) * STRIDE + 3;
 };
+// the input halo tile is one 4-D TMA box (zero fill outside the image = the padding), as in the forward kernel
 template <int STRIDE>
-__device__ __forceinline__ void dww_stage(unsigned char *xbuf, const __nv_bfloat16 *__restrict__ X, int H, int W, int C, int b,
-                                          int tile, int tiles_x, int c_slab) {
+__device__ __forceinline__ void dww_stage(unsigned char *xbuf, const CUtensorMap *map, uint64_t *bar, int b, int tile, int tiles_x,
+                                          int c_slab) {
     using T = DwT<STRIDE>;
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    const int iy0 = ty * T::TH * STRIDE - 1, ix0 = tx * T::TW * STRIDE - 1;
-    const __nv_bfloat16 *xb = X + (long)b * H * W * C;
-    for (int i = threadIdx.x; i < T::IH * T::IW * 8; i += 256) {
-        const int px = i >> 3, g = i & 7;
-        const int py = px / T::IW, pxx = px - py * T::IW;
-        const int iy = iy0 + py, ix = ix0 + pxx;
-        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W && c_slab + g * 8 < C;
-        cp_async16(xbuf + (px * 8 + g) * 16, ok ? (const void *)(xb + ((long)iy * W + ix) * C + c_slab + g * 8) : (const void *)X, ok);
-    }
-    cp_async_commit();
+    mbar_expect_tx(bar, T::IH * T::IW * 128);
+    tma_load_4d(xbuf, map, bar, c_slab, tx * T::TW * STRIDE - 1, ty * T::TH * STRIDE - 1, b);
 }
 // four bf16 channels as two fp32 pairs (operands of the packed FFMA2: two fused multiply-adds per issue slot)
 __device__ __forceinline__ void up4(const uint2 &p, float2 (&f)[2]) {
@@ -404,12 +397,19 @@ __device__ __forceinline__ void up4(const uint2 &p, float2 (&f)[2]) {
 // halo tile is in flight, so three CTAs share an SM (was one, at 136 registers and 79 KB of shared memory).
 template <int STRIDE>
 __global__ void __launch_bounds__(256, 3)
-dwconv_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ dY, const __nv_bfloat16 *__restrict__ X, int B, int H, int W, int C,
+dwconv_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ dY, const __grid_constant__ CUtensorMap mapX, int B, int H, int W, int C,
                          int Ho, int Wo, int tiles_x, int tiles_y, float *__restrict__ dW) {
     using T = DwT<STRIDE>;
     constexpr int kX = T::IH * T::IW * 128;
     constexpr int kPix = T::TH * T::TW, kMine = kPix / 16;      // output pixels per thread
-    extern __shared__ __align__(16) unsigned char s_dyn[];      // 2 input halo tiles; the fold reuses them
+    extern __shared__ __align__(128) unsigned char s_dyn[];     // 2 input halo tiles; the fold reuses them
+    __shared__ uint64_t s_bar[2];
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     const int cgi = threadIdx.x & 15, pl = threadIdx.x >> 4;
     const int c_slab = blockIdx.y * 64;
     const int c0 = c_slab + cgi * 4;
@@ -421,13 +421,13 @@ dwconv_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ dY, const __nv_bfloat
     const int per_img = tiles_x * tiles_y;
     const long n_tiles = (long)B * per_img;
     long item = blockIdx.x;
-    if (item < n_tiles) dww_stage<STRIDE>(s_dyn, X, H, W, C, (int)(item / per_img), (int)(item % per_img), tiles_x, c_slab);
+    if (item < n_tiles && threadIdx.x == 0)
+        dww_stage<STRIDE>(s_dyn, &mapX, &s_bar[0], (int)(item / per_img), (int)(item % per_img), tiles_x, c_slab);
     for (int it = 0; item < n_tiles; item += gridDim.x, ++it) {
         const long next = item + gridDim.x;
-        if (next < n_tiles)
-            dww_stage<STRIDE>(s_dyn + ((it + 1) & 1) * kX, X, H, W, C, (int)(next / per_img), (int)(next % per_img), tiles_x, c_slab);
-        else
-            cp_async_commit();
+        if (next < n_tiles && threadIdx.x == 0)
+            dww_stage<STRIDE>(s_dyn + ((it + 1) & 1) * kX, &mapX, &s_bar[(it + 1) & 1], (int)(next / per_img), (int)(next % per_img),
+                              tiles_x, c_slab);
         // this thread's output gradients (zero outside the image / channel range: they contribute nothing)
         const int b = (int)(item / per_img), tile = (int)(item - (long)b * per_img);
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
@@ -441,8 +441,7 @@ dwconv_bwd_weight_kernel(const __nv_bfloat16 *__restrict__ dY, const __nv_bfloat
             dyr[q] = make_uint2(0u, 0u);
             if (oy < Ho && ox < Wo && c0 < C) dyr[q] = __ldg((const uint2 *)(dY + (((long)b * Ho + oy) * Wo + ox) * C + c0));
         }
-        cp_async_wait<1>();
-        __syncthreads();
+        mbar_wait(&s_bar[it & 1], (it >> 1) & 1);
         const unsigned char *s_in = s_dyn + (it & 1) * kX + cgi * 8;
         if (STRIDE == 1) {
             // two vertically adjacent outputs share their 4 x 3 input vectors (12 loads instead of 18)
@@ -981,6 +980,12 @@ POSE_API int pose_dwconv3x3_bwd_bf16(const void *dY, const void *X, const float 
         if (gx > cap) gx = cap;
         const int smem1 = 2 * DwT<1>::IH * DwT<1>::IW * 128;
         const int smem2 = 2 * DwT<2>::IH * DwT<2>::IW * 128;
+        CUtensorMap mapX;
+        {
+            const int e = make_map_dw_halo(&mapX, X, B, H, W, C, stride == 1 ? DwT<1>::IW : DwT<2>::IW,
+                                           stride == 1 ? DwT<1>::IH : DwT<2>::IH);
+            if (e) return e;
+        }
         static bool cfg = false;
         if (!cfg) {
             cudaError_t ce = cudaFuncSetAttribute(dwconv_bwd_weight_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
@@ -990,10 +995,10 @@ POSE_API int pose_dwconv3x3_bwd_bf16(const void *dY, const void *X, const float 
             cfg = true;
         }
         if (stride == 1)
-            dwconv_bwd_weight_kernel<1><<<dim3((unsigned)gx, gy), 256, smem1, s>>>((const __nv_bfloat16 *)dY, (const __nv_bfloat16 *)X,
+            dwconv_bwd_weight_kernel<1><<<dim3((unsigned)gx, gy), 256, smem1, s>>>((const __nv_bfloat16 *)dY, mapX,
                                                                                   B, H, W, C, Ho, Wo, tiles_x, tiles_y, dW);
         else
-            dwconv_bwd_weight_kernel<2><<<dim3((unsigned)gx, gy), 256, smem2, s>>>((const __nv_bfloat16 *)dY, (const __nv_bfloat16 *)X,
+            dwconv_bwd_weight_kernel<2><<<dim3((unsigned)gx, gy), 256, smem2, s>>>((const __nv_bfloat16 *)dY, mapX,
                                                                                   B, H, W, C, Ho, Wo, tiles_x, tiles_y, dW);
     }
     return launch_status();

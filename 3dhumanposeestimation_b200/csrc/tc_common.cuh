@@ -168,5 +168,19 @@ inline EncodeTiledFn encode_tiled() {
     return fn;
 }
 
+// NHWC bf16 activation [B, H, W, C] as a 4-D tensor; box = {64 channels, iw, ih, 1 image}, no swizzle: the halo tile of the
+// depthwise kernels (rows / columns / channels outside the tensor are zero filled = the convolution padding)
+inline int make_map_dw_halo(CUtensorMap *map, const void *ptr, int B, int H, int W, int C, int iw, int ih) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return POSE_E_UNSUPPORTED;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)iw, (cuuint32_t)ih, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? POSE_OK : POSE_E_SHAPE;
+}
 
 }  // namespace pose
