@@ -54,17 +54,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 
 struct AttnSync {
-    uint64_t *bar;       // [0]: MMA completion (tcgen05.commit), [1]: TMA operand loads (complete_tx)
-    uint32_t phase, lphase;
+    uint64_t *bar;       // [0]: MMA completion (tcgen05.commit); [1], [2]: TMA operand loads (complete_tx), used alternately
+    uint32_t phase, lwait, lissue;
     __device__ __forceinline__ void commit_and_wait() {     // thread 0 commits the MMAs issued so far; everybody waits
         if (threadIdx.x == 0) tc_commit(bar);
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
     }
+    // Load group k lands on barrier 1 + (k & 1) with parity (k >> 1) & 1.  Two alternating barriers mean that the issuing
+    // thread re-arms a barrier only two groups later -- with a __syncthreads in between -- so no thread can still be
+    // polling the phase that is being re-armed (with ONE barrier a thread that had not yet observed phase P could miss it
+    // once phase P + 1 completed as well: a parity alias, i.e. a hang).
+    __device__ __forceinline__ uint64_t *load_bar() { return bar + 1 + (lissue++ & 1); }     // issuing thread only
     __device__ __forceinline__ void wait_loads() {
-        mbar_wait(bar + 1, lphase);
-        lphase ^= 1;
+        mbar_wait(bar + 1 + (lwait & 1), (lwait >> 1) & 1);
+        ++lwait;
     }
 };
 
@@ -82,12 +87,13 @@ template <uint32_t TCOLS = 512>
 __device__ __forceinline__ uint32_t attn_prologue(unsigned char *&smem, uint64_t *&bar) {
     extern __shared__ unsigned char smem_dyn[];
     smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t s_bar[2];
+    __shared__ uint64_t s_bar[3];
     __shared__ uint32_t s_tmem;
     bar = s_bar;
     if (threadIdx.x == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) {
@@ -110,139 +116,161 @@ __device__ __forceinline__ void attn_epilogue(uint32_t tmem_base) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Forward, one CTA per (sample, head): query tiles of 128 rows x key chunks of 64 streamed through double-buffered shared
+// memory, ONLINE softmax (running row maximum / sum, the O accumulator in TMEM rescaled when the maximum moves), so the
+// sequence length is unbounded (the 512 x 512 default of the reference: 1025 tokens) and the CTA needs only 128 TMEM
+// columns and 65 KB of shared memory: several CTAs share an SM and cover each other's tensor / TMA round trips.  The loop
+// is software pipelined over the flattened (query tile, key chunk) steps: O += P V of step t is issued together with
+// S = Q K^T of step t + 1, whose operands arrive by TMA during the softmax of step t.
+constexpr int kFwdKC = 64;
 template <int HD>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, __nv_bfloat16 *__restrict__ O, float *__restrict__ lse, int Nq, int Nk,
                    int Nkp, long ldo, long bso, float scale, uint32_t drop_thresh, float drop_scale,
                    const DropSeed drop_seed) {
+    constexpr int KC = kFwdKC, KB = KC * 128;
     unsigned char *smem;
     uint64_t *bar;
-    const uint32_t tmem = attn_prologue(smem, bar);
-    AttnSync sync{bar, 0, 0};
-    auto Qb = [&](int i) { return smem + i * 16384; };                             // double-buffered query tiles
-    unsigned char *Ks = smem + 32768, *Vs = Ks + 288 * 128, *Ps = Vs + 288 * 128;  // P: 5 blocks of 16 KB
+    const uint32_t tmem = attn_prologue<128>(smem, bar);
+    AttnSync sync{bar, 0, 0, 0};
+    unsigned char *Qs = smem, *Ps = Qs + 16384;
+    auto Kc = [&](int i) { return Ps + 16384 + i * 2 * KB; };       // double-buffered key / value chunks
+    auto Vc = [&](int i) { return Ps + 16384 + KB + i * 2 * KB; };
     const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
     const int warp = threadIdx.x >> 5, quarter = warp & 3, grp = warp >> 2;
     const int r = quarter * 32 + (threadIdx.x & 31);              // this thread's query row (shared by its twin in the other group)
     __shared__ float red_m[2][128], red_s[2][128];
     __nv_bfloat16 *og = O + b * bso + (long)h * HD;
     const float sl2 = scale * kLog2e;
-    const uint32_t tO = tmem + 320;
-    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
-    const int nch = (Nkp + 31) / 32;
+    const uint32_t tS = tmem, tO = tmem + 64;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int nch = (Nkp + KC - 1) / KC;
 
-    auto issue_s = [&](const unsigned char *Qs) {      // S = Q K^T into TMEM columns [0, Nkp)   (thread 0)
-        const uint64_t da = umma_desc_k<128>(smem_u32(Qs));
-        for (int kc0 = 0; kc0 < Nkp; kc0 += 256) {
-            const int n = min(256, Nkp - kc0);
-            const uint32_t idesc = umma_idesc_bf16(128, n);
-            const uint64_t db = umma_desc_k<128>(smem_u32(Ks + kc0 * 128));
+    auto issue_s = [&](int buf, int n) {                // S = Q K^T for one key chunk   (thread 0)
+        const uint32_t idesc = umma_idesc_bf16(128, n);
+        const uint64_t da = umma_desc_k<128>(smem_u32(Qs)), db = umma_desc_k<128>(smem_u32(Kc(buf)));
 #pragma unroll
-            for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tmem + kc0, da + 2 * k, db + 2 * k, idesc, k ? 1u : 0u);
-        }
+        for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tS, da + 2 * k, db + 2 * k, idesc, k ? 1u : 0u);
     };
 
-    // prologue: K, V and the first query tile; S(0)
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(bar + 1, 4 * kBoxRows * 128 + 2 * box_bytes(Nkp));
-        tma_rows(Ks, &mapK, bar + 1, h * HD, 0, b, Nkp);
-        tma_rows(Vs, &mapV, bar + 1, h * HD, 0, b, Nkp);
-        tma_rows(Qb(0), &mapQ, bar + 1, h * HD, 0, b, 128);
-    }
-    sync.wait_loads();
-    if (threadIdx.x == 0) issue_s(Qb(0));
-    sync.commit_and_wait();
-
-    // steady state, ONE tensor-core round trip per query tile: after the softmax of tile i, O(i) = P V and S(i+1) are issued
-    // together; the next query tile streams in (TMA) during the softmax
-    for (int i = 0, q0 = 0; q0 < Nq; ++i, q0 += 128) {
-        const bool has_next = q0 + 128 < Nq;
-        if (threadIdx.x == 0 && has_next) {
-            mbar_expect_tx(bar + 1, 4 * kBoxRows * 128);
-            tma_rows(Qb((i + 1) & 1), &mapQ, bar + 1, h * HD, q0 + 128, b, 128);
+    {   // prologue: first query tile, first key / value chunk; S(0)
+        const int n0 = min(KC, Nkp);
+        if (threadIdx.x == 0) {
+            uint64_t *lb = sync.load_bar();
+            mbar_expect_tx(lb, 16384 + 2 * box_bytes(n0));
+            tma_rows(Qs, &mapQ, lb, h * HD, 0, b, 128);
+            tma_rows(Kc(0), &mapK, lb, h * HD, 0, b, n0);
+            tma_rows(Vc(0), &mapV, lb, h * HD, 0, b, n0);
         }
+        sync.wait_loads();
+        if (threadIdx.x == 0) issue_s(0, n0);
+        sync.commit_and_wait();
+    }
+
+    int t = 0;
+    for (int q0 = 0; q0 < Nq; q0 += 128) {
+        const bool last_tile = q0 + 128 >= Nq;
         const bool live = q0 + quarter * 32 < Nq;        // warps whose 32 rows are all padding skip the softmax
         const uint32_t drop_row = (uint32_t)(((b * heads + h) * Nq + q0 + r) * Nk);   // mask index of (row, key 0); < 2^32 (host check)
-        // A thread owns one row and there are two warps per scheduler: every dependent chain is exposed, so the row maximum
-        // and the row sum run on four independent accumulators; the two warps of a lane quarter take alternate 32-column
-        // chunks and meet through shared memory.  (Kept compact: i-cache misses are exposed too.)
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if (live)
-            for (int c = grp; c < nch; c += 2) {
-                uint32_t v[32];
-                tmem_ld32(trow + c * 32, v);
-                const int lim = Nk - c * 32;             // columns of this chunk that are real keys
+        float m = -INFINITY, l = 0.f;                    // running row maximum (raw scores) and this thread's share of the row sum
+        for (int c = 0; c < nch; ++c, ++t) {
+            const int kc0 = c * KC, n = min(KC, Nkp - kc0);
+            const bool last_c = c == nch - 1;
+            const bool has_next = !(last_c && last_tile);
+            const int cn = last_c ? 0 : c + 1, n_next = min(KC, Nkp - cn * KC);
+            const int cur = t & 1;
+            if (threadIdx.x == 0 && has_next) {           // operands of step t + 1 (their buffers were released by the last commit)
+                uint64_t *lb = sync.load_bar();
+                mbar_expect_tx(lb, 2 * box_bytes(n_next) + (last_c ? 16384 : 0));
+                tma_rows(Kc(cur ^ 1), &mapK, lb, h * HD, cn * KC, b, n_next);
+                tma_rows(Vc(cur ^ 1), &mapV, lb, h * HD, cn * KC, b, n_next);
+                if (last_c) tma_rows(Qs, &mapQ, lb, h * HD, q0 + 128, b, 128);
+            }
+            // the two warps of a lane quarter take one 32-column half of the chunk each and meet through shared memory
+            const bool mine = live && grp * 32 < n;
+            uint32_t v[32];
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (mine) {
+                tmem_ld32(tS + lane_off + grp * 32, v);
+                const int lim = Nk - kc0 - grp * 32;     // columns of this half that are real keys
 #pragma unroll
                 for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], j < lim ? __uint_as_float(v[j]) : -INFINITY);
             }
-        red_m[grp][r] = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        __syncthreads();
-        const float m = fmaxf(red_m[0][r], red_m[1][r]);
-        const float ms = m * sl2;
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (live)
-            for (int c = grp; c < nch; c += 2) {
-                uint32_t v[32];
-                tmem_ld32(trow + c * 32, v);
+            red_m[grp][r] = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            __syncthreads();
+            const float m_new = fmaxf(m, fmaxf(red_m[0][r], red_m[1][r]));
+            const float alpha = ex2_approx((m - m_new) * sl2);      // exp2(-inf) = 0 on the first chunk
+            const float ms = m_new * sl2;
+            m = m_new;
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (mine) {
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) {
                     float p[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int col = c * 32 + j8 * 8 + j;
+                        const int col = kc0 + grp * 32 + j8 * 8 + j;
                         p[j] = col < Nk ? ex2_approx(fmaf(__uint_as_float(v[j8 * 8 + j]), sl2, -ms)) : 0.f;
                         s4[j & 3] += p[j];
                         // attention-weight dropout (nn.MultiheadAttention(dropout=p)): the row still normalises by the full sum
                         if (drop_thresh) p[j] = drop_keep32(drop_seed.key0, drop_row + col, drop_thresh) ? p[j] * drop_scale : 0.f;
                     }
-                    const int col8 = c * 4 + j8;
-                    if (col8 * 8 < Nkp)
+                    const int col8 = grp * 4 + j8;
+                    if (col8 * 8 < n)
                         store_chunk_kmajor(Ps, r, col8, make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]),
                                                                   pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7])));
                 }
             }
-        red_s[grp][r] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (has_next) sync.wait_loads();
-        if (threadIdx.x == 0) {
-            tc_fence_after();
-            constexpr uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
-            for (int ks = 0; ks < Nkp / 16; ++ks) {
-                const uint64_t da = umma_desc_k<128>(smem_u32(Ps + (ks >> 2) * 16384)) + 2 * (ks & 3);
-                const uint64_t db = umma_desc_mn(smem_u32(Vs + ks * 2048), 1024);
-                tc_mma_f16(tO, da, db, idesc, ks ? 1u : 0u);
+            l = fmaf(l, alpha, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+            // the maximum moved: rescale this warp's 32-column half of the O accumulator (complete since the last commit)
+            if (c > 0 && live && !__all_sync(0xffffffffu, alpha == 1.0f)) {
+                uint32_t o[32];
+                tmem_ld32(tO + lane_off + grp * 32, o);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+                tmem_st32(tO + lane_off + grp * 32, o);
             }
-            if (has_next) issue_s(Qb((i + 1) & 1));
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (has_next) sync.wait_loads();
+            if (threadIdx.x == 0) {
+                tc_fence_after();
+                constexpr uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
+                for (int ks = 0; ks < n / 16; ++ks) {
+                    const uint64_t da = umma_desc_k<128>(smem_u32(Ps)) + 2 * ks;
+                    const uint64_t db = umma_desc_mn(smem_u32(Vc(cur) + ks * 2048), 1024);
+                    tc_mma_f16(tO, da, db, idesc, (c | ks) ? 1u : 0u);           // O += P V
+                }
+                if (has_next) issue_s(cur ^ 1, n_next);
+            }
+            sync.commit_and_wait();
         }
-        sync.commit_and_wait();
+        // end of the query tile: normalise and store; log-sum-exp for the backward pass
+        red_s[grp][r] = l;
+        __syncthreads();
         if (live) {                                      // warp-uniform: tcgen05.ld is a warp-collective instruction
-            const float sum = red_s[0][r] + red_s[1][r];         // (written before the barrier that preceded the MMAs)
+            const float sum = red_s[0][r] + red_s[1][r];
             const float inv = 1.0f / sum;
             if (grp == 0 && lse != nullptr && q0 + r < Nq) lse[((long)b * heads + h) * Nq + q0 + r] = m * scale + __logf(sum);
             uint32_t v[32];
-            {
-                const int c = grp;                       // each group stores one 32-column half of the output row
-                tmem_ld32(tO + ((uint32_t)(quarter * 32) << 16) + c * 32, v);
-                if (q0 + r < Nq)
+            const int c = grp;                           // each group stores one 32-column half of the output row
+            tmem_ld32(tO + lane_off + c * 32, v);
+            if (q0 + r < Nq)
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        if (c * 32 + j8 * 8 >= HD) break;
-                        uint4 o;
-                        o.x = pack_bf16x2(__uint_as_float(v[j8 * 8]) * inv, __uint_as_float(v[j8 * 8 + 1]) * inv);
-                        o.y = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) * inv, __uint_as_float(v[j8 * 8 + 3]) * inv);
-                        o.z = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) * inv, __uint_as_float(v[j8 * 8 + 5]) * inv);
-                        o.w = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) * inv, __uint_as_float(v[j8 * 8 + 7]) * inv);
-                        *((uint4 *)(og + (long)(q0 + r) * ldo) + c * 4 + j8) = o;
-                    }
-            }
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    if (c * 32 + j8 * 8 >= HD) break;
+                    uint4 o;
+                    o.x = pack_bf16x2(__uint_as_float(v[j8 * 8]) * inv, __uint_as_float(v[j8 * 8 + 1]) * inv);
+                    o.y = pack_bf16x2(__uint_as_float(v[j8 * 8 + 2]) * inv, __uint_as_float(v[j8 * 8 + 3]) * inv);
+                    o.z = pack_bf16x2(__uint_as_float(v[j8 * 8 + 4]) * inv, __uint_as_float(v[j8 * 8 + 5]) * inv);
+                    o.w = pack_bf16x2(__uint_as_float(v[j8 * 8 + 6]) * inv, __uint_as_float(v[j8 * 8 + 7]) * inv);
+                    *((uint4 *)(og + (long)(q0 + r) * ldo) + c * 4 + j8) = o;
+                }
         }
-        tc_fence_before();
-        __syncthreads();
     }
-    attn_epilogue(tmem);
+    attn_epilogue<128>(tmem);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -263,7 +291,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     unsigned char *smem;
     uint64_t *bar;
     const uint32_t tmem = attn_prologue<256>(smem, bar);
-    AttnSync sync{bar, 0, 0};
+    AttnSync sync{bar, 0, 0, 0};
     unsigned char *Qs = smem, *dOs = Qs + 16384, *dSs = dOs + 16384;
     auto Kc = [&](int i) { return dSs + 16384 + i * 2 * KB; };      // double-buffered key / value chunks
     auto Vc = [&](int i) { return dSs + 16384 + KB + i * 2 * KB; };
@@ -291,11 +319,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     {
         const int n0 = min(KC, Nkp);
         if (threadIdx.x == 0) {
-            mbar_expect_tx(bar + 1, 2 * 16384 + 2 * box_bytes(n0));
-            tma_rows(Qs, &mapQ, bar + 1, h * HD, 0, b, 128);
-            tma_rows(dOs, &mapdO, bar + 1, h * HD, 0, b, 128);
-            tma_rows(Kc(0), &mapK, bar + 1, h * HD, 0, b, n0);
-            tma_rows(Vc(0), &mapV, bar + 1, h * HD, 0, b, n0);
+            uint64_t *lb = sync.load_bar();
+            mbar_expect_tx(lb, 2 * 16384 + 2 * box_bytes(n0));
+            tma_rows(Qs, &mapQ, lb, h * HD, 0, b, 128);
+            tma_rows(dOs, &mapdO, lb, h * HD, 0, b, 128);
+            tma_rows(Kc(0), &mapK, lb, h * HD, 0, b, n0);
+            tma_rows(Vc(0), &mapV, lb, h * HD, 0, b, n0);
         }
         sync.wait_loads();
         if (threadIdx.x == 0) issue_s(0, n0);
@@ -333,12 +362,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
             const int cn = last_c ? 0 : c + 1, n_next = min(KC, Nkp - cn * KC);
             const int cur = t & 1;
             if (threadIdx.x == 0 && has_next) {           // operands of step t + 1 (their buffers were released by the last commit)
-                mbar_expect_tx(bar + 1, 2 * box_bytes(n_next) + (last_c ? 2 * 16384 : 0));
-                tma_rows(Kc(cur ^ 1), &mapK, bar + 1, h * HD, cn * KC, b, n_next);
-                tma_rows(Vc(cur ^ 1), &mapV, bar + 1, h * HD, cn * KC, b, n_next);
+                uint64_t *lb = sync.load_bar();
+                mbar_expect_tx(lb, 2 * box_bytes(n_next) + (last_c ? 2 * 16384 : 0));
+                tma_rows(Kc(cur ^ 1), &mapK, lb, h * HD, cn * KC, b, n_next);
+                tma_rows(Vc(cur ^ 1), &mapV, lb, h * HD, cn * KC, b, n_next);
                 if (last_c) {
-                    tma_rows(Qs, &mapQ, bar + 1, h * HD, q0 + 128, b, 128);
-                    tma_rows(dOs, &mapdO, bar + 1, h * HD, q0 + 128, b, 128);
+                    tma_rows(Qs, &mapQ, lb, h * HD, q0 + 128, b, 128);
+                    tma_rows(dOs, &mapdO, lb, h * HD, q0 + 128, b, 128);
                 }
             }
             if (live && grp * 32 < n) {                   // the two warps of a lane quarter take one 32-column chunk each
@@ -416,7 +446,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
     unsigned char *smem;
     uint64_t *bar;
     const uint32_t tmem = attn_prologue<256>(smem, bar);
-    AttnSync sync{bar, 0, 0};
+    AttnSync sync{bar, 0, 0, 0};
     unsigned char *Kt = smem, *Vt = Kt + 16384, *PT = Vt + 16384, *dST = PT + 16384;
     auto Qb = [&](int i) { return dST + 16384 + i * 2 * QB; };      // double-buffered query / dO tiles
     auto dOb = [&](int i) { return dST + 16384 + QB + i * 2 * QB; };
@@ -450,11 +480,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
 
     // prologue: this CTA's key / value tile, the first query / dO tile and its statistics; S^T(0), dP^T(0)
     if (threadIdx.x == 0) {
-        mbar_expect_tx(bar + 1, 2 * 16384 + 2 * QB);
-        tma_rows(Kt, &mapK, bar + 1, h * HD, k0, b, 128);
-        tma_rows(Vt, &mapV, bar + 1, h * HD, k0, b, 128);
-        tma_rows(Qb(0), &mapQ, bar + 1, h * HD, 0, b, QT);
-        tma_rows(dOb(0), &mapdO, bar + 1, h * HD, 0, b, QT);
+        uint64_t *lb = sync.load_bar();
+        mbar_expect_tx(lb, 2 * 16384 + 2 * QB);
+        tma_rows(Kt, &mapK, lb, h * HD, k0, b, 128);
+        tma_rows(Vt, &mapV, lb, h * HD, k0, b, 128);
+        tma_rows(Qb(0), &mapQ, lb, h * HD, 0, b, QT);
+        tma_rows(dOb(0), &mapdO, lb, h * HD, 0, b, QT);
     }
     load_stats(0, 0);
     sync.wait_loads();
@@ -471,9 +502,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
         const uint32_t drop_col = (uint32_t)(((b * heads + h) * Nq + q0) * Nk + k0 + r);   // mask index of (query q0, this key); < 2^32 (host check)
         if (has_next) {
             if (threadIdx.x == 0) {
-                mbar_expect_tx(bar + 1, 2 * QB);
-                tma_rows(Qb(cur ^ 1), &mapQ, bar + 1, h * HD, q0 + QT, b, QT);
-                tma_rows(dOb(cur ^ 1), &mapdO, bar + 1, h * HD, q0 + QT, b, QT);
+                uint64_t *lb = sync.load_bar();
+                mbar_expect_tx(lb, 2 * QB);
+                tma_rows(Qb(cur ^ 1), &mapQ, lb, h * HD, q0 + QT, b, QT);
+                tma_rows(dOb(cur ^ 1), &mapdO, lb, h * HD, q0 + QT, b, QT);
             }
             load_stats(cur ^ 1, q0 + QT);
         }
@@ -552,7 +584,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
     attn_epilogue<256>(tmem);
 }
 
-constexpr int kFwdSmem = 2 * 16384 + 2 * 288 * 128 + 5 * 16384 + 1024;
+constexpr int kFwdSmem = 2 * 16384 + 4 * kFwdKC * 128 + 1024;
 constexpr int kDqSmem = 3 * 16384 + 4 * kDqKC * 128 + 1024;
 constexpr int kDkvSmem = 4 * 16384 + 4 * kDkvQT * 128 + 1024;
 
@@ -589,7 +621,6 @@ POSE_API int pose_attention_bf16(const void *Q, const void *K, const void *V, vo
     const float dsc = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     if (B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return POSE_E_SHAPE;
     if (head_dim != 48 && head_dim != 64) return POSE_E_UNSUPPORTED;
-    if (Nk > 288) return POSE_E_UNSUPPORTED;              // the whole score row lives in TMEM (<= 288 columns)
     if (drop_p > 0.f && (double)B * heads * Nq * Nk >= 4294967296.0) return POSE_E_UNSUPPORTED;   // 32-bit mask counter
     if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || bsq % 8 || bsk % 8 || bsv % 8 || bso % 8) return POSE_E_ALIGN;
     if ((uintptr_t)Q % 16 || (uintptr_t)K % 16 || (uintptr_t)V % 16 || (uintptr_t)O % 16) return POSE_E_ALIGN;
@@ -623,7 +654,6 @@ POSE_API int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V
     const float dsc = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     if (B <= 0 || heads <= 0 || Nq <= 0 || Nk <= 0) return POSE_E_SHAPE;
     if (head_dim != 48 && head_dim != 64) return POSE_E_UNSUPPORTED;
-    if (Nk > 288) return POSE_E_UNSUPPORTED;
     if (drop_p > 0.f && (double)B * heads * Nq * Nk >= 4294967296.0) return POSE_E_UNSUPPORTED;   // 32-bit mask counter
     const long al[] = {ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv};
     for (long a : al)

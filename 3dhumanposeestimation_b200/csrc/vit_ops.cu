@@ -236,15 +236,30 @@ colsum_kernel(const __nv_bfloat16 *__restrict__ X, long M, int N, long ld, float
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
     if (c0 < N) {
-        for (long r = (long)blockIdx.y * 8 + ry; r < M; r += (long)gridDim.y * 8) {
-            if (c0 + 8 <= N) {
+        const long step = (long)gridDim.y * 8;
+        long r = (long)blockIdx.y * 8 + ry;
+        if (c0 + 8 <= N) {
+            for (; r + 3 * step < M; r += 4 * step) {          // four independent 16-byte loads in flight per thread
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldg((const uint4 *)(X + (r + u * step) * ld + c0));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float f[8];
+                    unpack8v(v[u], f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] += f[k];
+                }
+            }
+            for (; r < M; r += step) {
                 float f[8];
                 unpack8v(__ldg((const uint4 *)(X + r * ld + c0)), f);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) acc[k] += f[k];
-            } else {
-                for (int k = 0; c0 + k < N; ++k) acc[k] += __bfloat162float(X[r * ld + c0 + k]);
             }
+        } else {
+            for (; r < M; r += step)
+                for (int k = 0; c0 + k < N; ++k) acc[k] += __bfloat162float(X[r * ld + c0 + k]);
         }
     }
 #pragma unroll
@@ -423,7 +438,7 @@ POSE_API int pose_colsum_bf16(const void *X, long M, int N, long ld, float *out,
     if ((uintptr_t)X % 16 || ld % 8) return POSE_E_ALIGN;
     const int gx = (N + 255) / 256;
     long gy = (M + 63) / 64;                       // >= 8 rows per thread row
-    const long cap = (kNumSMs * 4 + gx - 1) / gx;
+    const long cap = (kNumSMs * 6 + gx - 1) / gx;
     if (gy > cap) gy = cap;
     if (gy < 1) gy = 1;
     colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, M, N, ld, out);

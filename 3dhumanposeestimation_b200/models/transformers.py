@@ -255,10 +255,6 @@ class VitPlan:
         self.act = activation_id(c.activation)
         if self.act not in (2, 3):
             raise NotImplementedError("transformer activation: gelu or silu")
-        if max(self.T_img + 1, self.T_fin) > 288:
-            raise NotImplementedError(
-                f"{self.T_fin} tokens: the attention kernels keep a whole score row on chip (<= 288 keys; 256x256 "
-                "inputs).  A streaming (flash) variant is the planned extension for 512x512.")
         # nn.Dropout sites of the reference (transformers.py:24,61-72,98-124,363): active in training mode only; the timm
         # backbone has no dropout (all its drop rates default to 0)
         self.p_drop = float(c.transformer_dropout_rate)

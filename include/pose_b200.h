@@ -226,7 +226,8 @@ int pose_sums_to_bf16(const float *sums, int parts, int B, int C, float scale, v
  *                         flattened-conv-weight column order: Conv2d(kernel = stride = P) becomes one GEMM
  *  pose_attention_bf16    softmax(Q K^T * scale) V per (batch, head); Q/K/V/O rows with pitches ld* and batch
  *                         strides bs* (elements), head h in columns [h*head_dim, (h+1)*head_dim); head_dim 48 | 64,
- *                         Nk <= 288 (the whole score row lives in TMEM; tcgen05 kernels in csrc/attention_tc.cu).
+ *                         any sequence length (key chunks of 64 stream through shared memory, online softmax with the
+ *                         O accumulator in TMEM; tcgen05 kernels in csrc/attention_tc.cu).
  *                         nn.MultiheadAttention (transformers.py:61-63, :98-106) and timm Attention.
  * ------------------------------------------------------------------------------------------- */
 int pose_layernorm_bf16(const void *X, const float *gamma, const float *beta, float eps, long M, int rows, long in_group,

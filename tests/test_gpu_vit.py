@@ -64,7 +64,9 @@ def test_layernorm_token_subrange_addressing(pose):
 
 
 @pytest.mark.parametrize("hd,heads,Nq,Nk", [(64, 12, 257, 257), (48, 16, 273, 273), (48, 16, 256, 16), (48, 16, 16, 256),
-                                            (64, 2, 70, 33)])
+                                            (64, 2, 70, 33),
+                                            # the reference's default 512 x 512 input: 1025 backbone tokens, 1024 + 64 + 1 final
+                                            (64, 12, 1025, 1025), (48, 16, 1089, 1089), (48, 4, 1024, 64), (48, 4, 64, 1024)])
 def test_attention_forward_backward(pose, hd, heads, Nq, Nk):
     lib, sp, check = _lib(pose)
     B, E = 2, hd * heads
@@ -100,7 +102,7 @@ def test_attention_forward_backward(pose, hd, heads, Nq, Nk):
     assert torch.allclose(dkv.float(), kvr.grad, **tol), (dkv.float() - kvr.grad).abs().max().item()
 
 
-@pytest.mark.parametrize("hd,heads,Nq,Nk", [(48, 16, 273, 273), (64, 12, 257, 257), (48, 16, 16, 256)])
+@pytest.mark.parametrize("hd,heads,Nq,Nk", [(48, 16, 273, 273), (64, 12, 257, 257), (48, 16, 16, 256), (64, 3, 1025, 1025)])
 def test_attention_weight_dropout_forward_backward(pose, hd, heads, Nq, Nk):
     """nn.MultiheadAttention(dropout=p): the mask is a counter-based hash of (seed, element); pose_dropout_bf16 over a
     tensor of ones with the same seed exposes it, so the fused kernels can be checked against plain PyTorch."""
@@ -282,6 +284,47 @@ def test_training_step_gradients_match_fp32_autograd(pose, golden):
     worst.sort(reverse=True)
     assert worst[0][0] < 0.08, worst[:8]        # bf16 activations / weights end to end vs fp32
     assert sum(r for r, _ in worst) / len(worst) < 0.04, worst[:8]
+
+
+def test_default_512x512_configuration_forward_and_gradients(pose):
+    """ModelConfig("transformer") defaults to 512 x 512 (model_config.py): 1025 backbone tokens, 1024 + 64 + 1 tokens in
+    the final encoder -- the streaming attention kernels.  Eval forward and every gradient against fp32 autograd over
+    the oracle restatement (pinned to the live reference at 256 x 256 by the tests above)."""
+    from oracle import torch_models as tm
+    cfg = pose.ModelConfig("transformer", vit_pretrained=False, transformer_dropout_rate=0.0,
+                           transformer_attention_dropout_rate=0.0, regression_dropout=0.0)
+    assert tuple(cfg.image_size) == (512, 512)
+    m = pose.TransformerPoseEstimation(cfg)
+    sd = tm.fill_vit_state_dict(m.state_dict(), seed=11)
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    sd = {k: v.to(DEV) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(5)
+    img, dep = torch.rand(1, 3, 512, 512, generator=g).to(DEV), torch.rand(1, 1, 512, 512, generator=g).to(DEV)
+    kp = (torch.rand(1, 17, 2, generator=g) * 0.9 + 0.05).to(DEV)
+    gt = (torch.randn(1, 17, 3, generator=g) * 300).to(DEV)
+    m.eval()
+    with torch.no_grad():
+        out = m(img, dep, kp)
+        ref = tm.vit_forward(sd, cfg, img, dep, kp)
+    mpjpe = pose.utils.compute_mpjpe(out, ref).item()
+    assert mpjpe < 0.5, f"MPJPE vs the fp32 oracle {mpjpe:.3f} mm"
+    m.train()
+    total, _ = pose.ComprehensivePoseLoss()(m(img, dep, kp), gt)
+    total.backward()
+    sdg = {k: (v.clone().requires_grad_() if v.is_floating_point() and "grid" not in k else v) for k, v in sd.items()}
+    po = tm.vit_forward(sdg, cfg, img, dep, kp)
+    d = po - gt
+    iu = torch.triu_indices(17, 17, 1, device=DEV)
+    pd = lambda t: torch.linalg.norm(t[:, :, None] - t[:, None], dim=-1)[:, iu[0], iu[1]]   # noqa: E731
+    lo = (d ** 2).mean() + d.abs().mean() + 100.0 * (pd(po) - pd(gt)).abs().mean() + d[:, 0].abs().mean()
+    lo.backward()
+    assert abs(total.item() - lo.item()) < 2e-2 * lo.item()
+    norms = {n: sdg[n].grad.double().norm().item() for n, _ in m.named_parameters()}
+    floor = 1e-6 * max(norms.values())
+    worst = sorted(((p.grad.double() - sdg[n].grad.double()).norm().item() / (norms[n] + floor), n) for n, p in m.named_parameters())
+    assert worst[-1][0] < 0.08, worst[-8:]
+    assert sum(r for r, _ in worst) / len(worst) < 0.04, worst[-8:]
 
 
 def test_training_with_the_reference_dropout_rates(pose, golden):
