@@ -348,6 +348,16 @@ int pose_param_repack(const void *table, int n_entries, const float *src_f32, fl
  * ------------------------------------------------------------------------------------------- */
 int pose_eval_metrics(const float *pred, const float *gt, int B, int J, float *per_sample, float *means, pose_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * next row: model-input preparation of the inference path     reference: infer.py:319-380
+ *    depth [B, h, w] fp32 -> depth_out [B, H, W] = F.interpolate(mode="bilinear", align_corners=False) (infer.py:362-367,
+ *    ATen's source-index rule, evaluated without contraction: equal to the CPU path bit for bit);
+ *    kpts_px_conf [B, K, 3] = (x_pixel, y_pixel, confidence) -> kp_norm [B, K, 2] = (x / img_w, y / img_h) (infer.py:217-221)
+ *    and, optionally, kp_norm_conf [B, K, 3] (the visualisation copy).  kpts_px_conf may be NULL (depth only).
+ * ------------------------------------------------------------------------------------------- */
+int pose_infer_prep(const float *depth, int B, int h, int w, int H, int W, float *depth_out, const float *kpts_px_conf, int K,
+                    float img_w, float img_h, float *kp_norm, float *kp_norm_conf, pose_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

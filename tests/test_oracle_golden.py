@@ -112,3 +112,20 @@ def test_metrics_oracle_matches_live_reference(oracle, golden):
     assert np.allclose(per, d["pa_per_sample"], rtol=1e-5, atol=1e-3)
     # the reference's rotation convention: a pose rotated about z by +0.7 rad (sample 2) is NOT perfectly re-aligned
     assert per[2] > 100.0 and per[3] < 1e-3
+
+
+def test_infer_prep_oracle_matches_the_live_torch_call():
+    """infer.py:362-367 calls F.interpolate(mode="bilinear", align_corners=False) directly: the numpy restatement is pinned
+    against that live call (up- and down-sampling, non-square, odd sizes, 1-pixel axes)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import infer_ref
+    rng = np.random.default_rng(3)
+    for (h, w, H, W) in ((37, 53, 256, 256), (480, 640, 256, 256), (256, 256, 256, 256), (1, 7, 5, 9), (300, 200, 512, 512)):
+        d = rng.random((2, h, w), dtype=np.float32) * 10.0
+        want = F.interpolate(torch.from_numpy(d)[:, None], size=(H, W), mode="bilinear", align_corners=False)[:, 0].numpy()
+        got = infer_ref.depth_resize(d, H, W)
+        assert np.allclose(got, want, rtol=2e-6, atol=2e-6), (h, w, H, W, np.abs(got - want).max())
+    k = rng.random((2, 17, 3), dtype=np.float32) * np.float32(640.0)
+    kp2, kp3 = infer_ref.normalise_keypoints(k, 640, 480)
+    assert np.array_equal(kp2[..., 0], k[..., 0] / np.float32(640)) and np.array_equal(kp3[..., 2], k[..., 2])
