@@ -97,6 +97,10 @@ SIGNATURES = {
     "pose_bn_stats_bf16": (c_int, [c_void_p, C.c_long, c_int, C.c_long, c_void_p, C.c_long, c_void_p]),
     "pose_bn_finalize": (c_int, [c_void_p, C.c_long, C.c_long, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
+    "pose_bn_finalize_parts": (c_int, [c_void_p, c_int, C.c_long, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pose_dwconv3x3_bn_stats_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                             C.c_long, c_void_p]),
     "pose_bn_apply_bf16": (c_int, [c_void_p, C.c_long, c_int, c_void_p, c_int, c_float, c_void_p, C.c_long, c_void_p, C.c_long,
                                    c_void_p]),
     "pose_bn_bwd_bf16": (c_int, [c_void_p, C.c_long, c_void_p, C.c_long, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p,

@@ -141,17 +141,40 @@ __device__ __forceinline__ uint2 pack4(const float (&f)[4]) {
     return make_uint2(*(uint32_t *)&p0, *(uint32_t *)&p1);
 }
 
+// activation, store (bf16) and the per-thread partial sums of one 4-channel output (see `pool` / `stats` of the kernel)
+template <int ACT>
+__device__ __forceinline__ void dw_emit(float (&a)[4], int stats, float (&psum)[4], float (&psq)[4], __nv_bfloat16 *dst) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = act_t<ACT>(a[k]);
+    const uint2 pk = pack4(a);
+    *(uint2 *)dst = pk;
+    if (stats) {          // BatchNorm statistics are those of the tensor the next kernel will read: the rounded values
+        float2 r[2];
+        unpack4(pk, r);
+        psum[0] += r[0].x; psum[1] += r[0].y; psum[2] += r[1].x; psum[3] += r[1].y;
+        psq[0] = fmaf(r[0].x, r[0].x, psq[0]); psq[1] = fmaf(r[0].y, r[0].y, psq[1]);
+        psq[2] = fmaf(r[1].x, r[1].x, psq[2]); psq[3] = fmaf(r[1].y, r[1].y, psq[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) psum[k] += a[k];
+    }
+}
+
 // A thread owns FOUR channels (16 channel groups x 16 pixel lanes): 36 filter taps in registers instead of 72 keeps the
 // kernel under 85 registers, so three CTAs (24 warps, three halo tiles in flight) share an SM; with eight channels per
 // thread it ran one CTA per SM at 20 % of the HBM roofline.
 template <int STRIDE, int ACT>
 __global__ void __launch_bounds__(256, 3)
 dwconv3x3_kernel(const __grid_constant__ CUtensorMap mapX, const float *__restrict__ Wd, const float *__restrict__ bias,
-                 int B, int H, int W, int C, __nv_bfloat16 *__restrict__ Y, float *__restrict__ pool, int Ho, int Wo,
+                 int B, int H, int W, int C, __nv_bfloat16 *__restrict__ Y, float *__restrict__ pool, int stats, int Ho, int Wo,
                  int tiles_x, int tiles_y) {
+    // pool (optional): stats == 0: [B * tiles, C] sums of the activated outputs (SE / ECA squeeze);
+    //                  stats == 1: [B * tiles, 2, C] sums of y and y^2 of the bf16-ROUNDED outputs = the first stage of
+    //                  the BatchNorm batch statistics (the separate pass over the conv output disappears)
     using T = DwTile<STRIDE>;
     extern __shared__ __align__(128) unsigned char s_dyn[];     // 2 halo buffers, then the pooled-sum scratch
     float(*s_part)[kDwSlab] = (float(*)[kDwSlab])(s_dyn + 2 * T::kSmem);
+    float(*s_part2)[kDwSlab] = s_part + 16;
     __shared__ uint64_t s_bar[2];                                // one per halo buffer (TMA completion)
     if (threadIdx.x == 0) {
         mbar_init(&s_bar[0], 1);
@@ -168,7 +191,7 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap mapX, const float *__restri
     float2 w[9][2], bs[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        bs[k] = c_ok ? __ldg((const float2 *)(bias + c0) + k) : make_float2(0.f, 0.f);
+        bs[k] = (c_ok && bias != nullptr) ? __ldg((const float2 *)(bias + c0) + k) : make_float2(0.f, 0.f);
 #pragma unroll
         for (int t = 0; t < 9; ++t) w[t][k] = c_ok ? __ldg((const float2 *)(Wd + (long)t * C + c0) + k) : make_float2(0.f, 0.f);
     }
@@ -185,9 +208,9 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap mapX, const float *__restri
         const int b = (int)(item / per_img), tile = (int)(item - (long)b * per_img);
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         const int oy0 = ty * T::TH, ox0 = tx * T::TW;
-        float psum[4];
+        float psum[4], psq[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) psum[k] = 0.f;
+        for (int k = 0; k < 4; ++k) psum[k] = psq[k] = 0.f;
         constexpr int kPix = T::TH * T::TW;
         if (STRIDE == 1) {
             // a thread owns one column of the 8 x 16 tile, two output rows at a time: the 4 x 3 input vectors of a pair are
@@ -215,22 +238,8 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap mapX, const float *__restri
                     }
                 float a0[4] = {v0[0].x, v0[0].y, v0[1].x, v0[1].y}, a1[4] = {v1[0].x, v1[0].y, v1[1].x, v1[1].y};
                 if (ox < Wo && c_ok) {
-                    if (oy0 + r0 < Ho) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            a0[k] = act_t<ACT>(a0[k]);
-                            psum[k] += a0[k];
-                        }
-                        *(uint2 *)(Y + (((long)b * Ho + oy0 + r0) * Wo + ox) * C + c0) = pack4(a0);
-                    }
-                    if (oy0 + r0 + 1 < Ho) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            a1[k] = act_t<ACT>(a1[k]);
-                            psum[k] += a1[k];
-                        }
-                        *(uint2 *)(Y + (((long)b * Ho + oy0 + r0 + 1) * Wo + ox) * C + c0) = pack4(a1);
-                    }
+                    if (oy0 + r0 < Ho) dw_emit<ACT>(a0, stats, psum, psq, Y + (((long)b * Ho + oy0 + r0) * Wo + ox) * C + c0);
+                    if (oy0 + r0 + 1 < Ho) dw_emit<ACT>(a1, stats, psum, psq, Y + (((long)b * Ho + oy0 + r0 + 1) * Wo + ox) * C + c0);
                 }
             }
         } else {
@@ -250,25 +259,24 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap mapX, const float *__restri
                         for (int k = 0; k < 2; ++k) v[k] = __ffma2_rn(f[k], w[ky * 3 + kx][k], v[k]);
                     }
                 float acc[4] = {v[0].x, v[0].y, v[1].x, v[1].y};
-                if (oy < Ho && ox < Wo && c_ok) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        acc[k] = act_t<ACT>(acc[k]);
-                        psum[k] += acc[k];
-                    }
-                    *(uint2 *)(Y + (((long)b * Ho + oy) * Wo + ox) * C + c0) = pack4(acc);
-                }
+                if (oy < Ho && ox < Wo && c_ok) dw_emit<ACT>(acc, stats, psum, psq, Y + (((long)b * Ho + oy) * Wo + ox) * C + c0);
             }
         }
         if (pool != nullptr) {  // fixed-order reduction over the 16 pixel lanes of the CTA, one write per channel
 #pragma unroll
-            for (int k = 0; k < 4; ++k) s_part[pl][cg * 4 + k] = psum[k];
+            for (int k = 0; k < 4; ++k) {
+                s_part[pl][cg * 4 + k] = psum[k];
+                s_part2[pl][cg * 4 + k] = psq[k];
+            }
             __syncthreads();
-            if (threadIdx.x < kDwSlab && c_slab + threadIdx.x < C) {
+            const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;      // threads 0..63: sums, 64..127: sums of squares
+            if (which <= stats && c_slab + ch < C) {
+                const float(*src)[kDwSlab] = which ? s_part2 : s_part;
                 float t = 0.f;
 #pragma unroll 8
-                for (int q = 0; q < 16; ++q) t += s_part[q][threadIdx.x];
-                pool[((long)b * per_img + tile) * C + c_slab + threadIdx.x] = t;
+                for (int q = 0; q < 16; ++q) t += src[q][ch];
+                const long part = (long)b * per_img + tile;
+                pool[(stats ? part * 2 + which : part) * C + c_slab + ch] = t;
             }
         }
         __syncthreads();     // the buffer just read is the target of the copy issued in the next iteration
@@ -524,9 +532,26 @@ POSE_API int pose_dwconv3x3_pool_parts(int H, int W, int stride) {
     return ((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
 }
 
+static int dwconv3x3_launch(const void *X, int B, int H, int W, int C, const float *Wd, const float *bias, int stride, int act,
+                            void *Y, float *pool_sum, int pool_parts, int stats, pose_stream_t stream);
+
 POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, const float *Wd, const float *bias, int stride,
                                  int act, void *Y, float *pool_sum, int pool_parts, pose_stream_t stream) {
-    if (!X || !Wd || !bias || !Y) return POSE_E_NULL;
+    return dwconv3x3_launch(X, B, H, W, C, Wd, bias, stride, act, Y, pool_sum, pool_parts, 0, stream);
+}
+
+POSE_API int pose_dwconv3x3_bn_stats_bf16(const void *X, int B, int H, int W, int C, const float *Wd, int stride, void *Y,
+                                          float *partials, long cap_floats, pose_stream_t stream) {
+    if (!partials) return POSE_E_NULL;
+    if (H <= 0 || W <= 0 || (stride != 1 && stride != 2)) return POSE_E_SHAPE;
+    const int parts = pose_dwconv3x3_pool_parts(H, W, stride);
+    if ((long)B * parts * 2 * C > cap_floats) return POSE_E_WORKSPACE;
+    return dwconv3x3_launch(X, B, H, W, C, Wd, nullptr, stride, 0, Y, partials, parts, 1, stream);
+}
+
+static int dwconv3x3_launch(const void *X, int B, int H, int W, int C, const float *Wd, const float *bias, int stride, int act,
+                            void *Y, float *pool_sum, int pool_parts, int stats, pose_stream_t stream) {
+    if (!X || !Wd || (!bias && !stats) || !Y) return POSE_E_NULL;
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 || (stride != 1 && stride != 2)) return POSE_E_SHAPE;
     if ((uintptr_t)X % 16 || (uintptr_t)Y % 16) return POSE_E_ALIGN;
     const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
@@ -541,7 +566,7 @@ POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, cons
     dim3 grid((unsigned)gx, gy);
     cudaStream_t s = (cudaStream_t)stream;
     if (act < 0 || act > 4) return POSE_E_UNSUPPORTED;
-    const int smem = 2 * (stride == 1 ? DwTile<1>::kSmem : DwTile<2>::kSmem) + 16 * kDwSlab * 4;
+    const int smem = 2 * (stride == 1 ? DwTile<1>::kSmem : DwTile<2>::kSmem) + 2 * 16 * kDwSlab * 4;
     CUtensorMap mapX;
     {
         const int e = make_map_dw_halo(&mapX, X, B, H, W, C, stride == 1 ? DwTile<1>::IW : DwTile<2>::IW,
@@ -557,7 +582,7 @@ POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, cons
             cfg = true;                                                                                               \
         }                                                                                                             \
         dwconv3x3_kernel<S_, A_><<<grid, 256, smem, s>>>(mapX, Wd, bias, B, H, W, C, (__nv_bfloat16 *)Y, \
-                                                         pool_sum, Ho, Wo, tiles_x, tiles_y);                         \
+                                                         pool_sum, stats, Ho, Wo, tiles_x, tiles_y);                  \
     }
 #define DW_ACT(S_)                                                                                                    \
     switch (act) {                                                                                                    \

@@ -921,6 +921,18 @@ POSE_API int pose_bn_finalize(const float *partials, long cap_floats, long count
     return launch_status();
 }
 
+/* the same fold over an explicit number of partial rows [parts, 2, C] (statistics emitted by the producing kernel:
+   pose_dwconv3x3_bn_stats_bf16) */
+POSE_API int pose_bn_finalize_parts(const float *partials, int parts, long count, const float *gamma, const float *beta, float eps,
+                                    float momentum, int C, float *mean_rstd, float *scale_shift, float *running_mean,
+                                    float *running_var, pose_stream_t stream) {
+    REQ(partials && gamma && beta && mean_rstd && scale_shift, POSE_E_NULL);
+    REQ(count > 0 && C > 0 && parts > 0, POSE_E_SHAPE);
+    bn_finalize_kernel<<<(C + 7) / 8, 256, 0, (cudaStream_t)stream>>>(partials, parts, (float)count, gamma, beta, eps, momentum, C,
+                                                                         mean_rstd, scale_shift, running_mean, running_var);
+    return launch_status();
+}
+
 POSE_API int pose_bn_apply_bf16(const void *Y, long M, int C, const float *scale_shift, int act, float out_scale,
                                 const void *residual, long ld_res, void *out, long ld_out, pose_stream_t stream) {
     REQ(Y && scale_shift && out, POSE_E_NULL);

@@ -176,8 +176,11 @@ class CnnTrainPlan:
             Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
             y = self.buf(name + ".y", Bn * Ho * Wo, co)
             wd = self.pk32[self.pk[name][1]:]
-            self.call("pose_dwconv3x3_bf16", x.data_ptr(), Bn, H, W, co, wd.data_ptr(), self.zero_bias(co).data_ptr(), stride,
-                      0, y.data_ptr(), None, 0)
+            # the depthwise kernel emits the first stage of the batch statistics of its own output (no separate pass)
+            part = self.partials()
+            self.call("pose_dwconv3x3_bn_stats_bf16", x.data_ptr(), Bn, H, W, co, wd.data_ptr(), stride, y.data_ptr(),
+                      part.data_ptr(), part.numel())
+            stat_parts = Bn * self.lib.pose_dwconv3x3_pool_parts(H, W, stride)
             kind = "dw"
         elif name in self.pk:
             _, fwd, bwd, cp, stage, _ui = self.pk[name]
@@ -196,12 +199,17 @@ class CnnTrainPlan:
             kind = "1x1"
         M = Bn * Ho * Wo
         part = self.partials()
-        self.call("pose_bn_stats_bf16", y.data_ptr(), M, co, co, part.data_ptr(), part.numel())
         mr = self.buf(name + ".mr", 2 * co, dtype=torch.float32)
         ss = self.buf(name + ".ss", 2 * co, dtype=torch.float32)
-        self.call("pose_bn_finalize", part.data_ptr(), part.numel(), M, flat.f32(bn.weight).data_ptr(), flat.f32(bn.bias).data_ptr(),
-                  float(bn.eps), float(bn.momentum), co, mr.data_ptr(), ss.data_ptr(), bn.running_mean.data_ptr(),
-                  bn.running_var.data_ptr())
+        if kind == "dw":
+            self.call("pose_bn_finalize_parts", part.data_ptr(), stat_parts, M, flat.f32(bn.weight).data_ptr(),
+                      flat.f32(bn.bias).data_ptr(), float(bn.eps), float(bn.momentum), co, mr.data_ptr(), ss.data_ptr(),
+                      bn.running_mean.data_ptr(), bn.running_var.data_ptr())
+        else:
+            self.call("pose_bn_stats_bf16", y.data_ptr(), M, co, co, part.data_ptr(), part.numel())
+            self.call("pose_bn_finalize", part.data_ptr(), part.numel(), M, flat.f32(bn.weight).data_ptr(),
+                      flat.f32(bn.bias).data_ptr(), float(bn.eps), float(bn.momentum), co, mr.data_ptr(), ss.data_ptr(),
+                      bn.running_mean.data_ptr(), bn.running_var.data_ptr())
         if out is None:
             out = self.buf(name + ".a", M, co)
             ld_out = co

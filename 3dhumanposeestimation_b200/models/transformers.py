@@ -652,7 +652,7 @@ class VitPlan:
             dx = self.encoder_block_bwd(f"bb{i}.", dx, Ti + 1, blk.norm1, blk.attn.qkv.weight, blk.attn.qkv.bias,
                                         blk.attn.proj.weight, blk.attn.proj.bias, blk.norm2, blk.mlp.fc1, blk.mlp.fc2,
                                         bb.num_heads)
-            if i % 3 == 0:
+            if i % 3 == 0 or i < 3:      # groups of three; the last blocks one by one: a short exposed all-reduce tail
                 done(blk.norm1.weight)
         self.call("pose_batch_rowsum_bf16", dx.data_ptr(), B, Ti + 1, 0, Ti + 1, E, flat.g32(bb.pos_embed).data_ptr())
         self.call("pose_batch_rowsum_bf16", dx.data_ptr(), B, Ti + 1, 0, 1, E, flat.g32(bb.cls_token).data_ptr())

@@ -308,6 +308,14 @@ typedef struct pose_repack_entry {
 int pose_conv2d_wgrad_bf16(const void *dY, const void *X, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
                            int dil, int pad, float *dWk, int k_splits, pose_stream_t stream);
 int pose_bn_stats_bf16(const void *Y, long M, int C, long ld, float *partials, long cap_floats, pose_stream_t stream);
+/* depthwise 3x3 (no bias, no activation) that also emits the first stage of the BatchNorm batch statistics of its (bf16-
+ * rounded) output: partials [B * pose_dwconv3x3_pool_parts(H, W, stride), 2, C]; fold with pose_bn_finalize_parts.  The
+ * separate statistics pass over the convolution output disappears (cnn.py:135-139 ConvBnAct with groups = channels). */
+int pose_dwconv3x3_bn_stats_bf16(const void *X, int B, int H, int W, int C, const float *Wd, int stride, void *Y, float *partials,
+                                 long cap_floats, pose_stream_t stream);
+int pose_bn_finalize_parts(const float *partials, int parts, long count, const float *gamma, const float *beta, float eps,
+                           float momentum, int C, float *mean_rstd, float *scale_shift, float *running_mean, float *running_var,
+                           pose_stream_t stream);
 int pose_bn_finalize(const float *partials, long cap_floats, long count, const float *gamma, const float *beta, float eps,
                      float momentum, int C, float *mean_rstd, float *scale_shift, float *running_mean, float *running_var,
                      pose_stream_t stream);
