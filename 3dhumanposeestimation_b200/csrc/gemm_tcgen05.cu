@@ -126,6 +126,33 @@ __device__ __forceinline__ float gelu_erf(float v) {     // nn.GELU() (exact, er
     return 0.5f * v * (1.0f + er);
 }
 
+// Two exact-GELU evaluations on the packed fp32 pipe (FFMA2 / FMUL2: two operations per issue slot).  The epilogues of the
+// MLP GEMMs were bound by the FMA pipe (~17 fp32 / integer-multiply operations per element against a K = 768 main loop);
+// `g` receives gelu'(v) when WITH_GRAD.  Same Abramowitz-Stegun erf as erf_abs_exp.
+template <bool WITH_GRAD>
+__device__ __forceinline__ float2 gelu2(float2 v, float2 &g, float out_scale) {
+    const float2 x = __fmul2_rn(v, make_float2(0.70710678118654752f, 0.70710678118654752f));
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), ax, make_float2(1.0f, 1.0f));
+    float2 t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+    const float2 ee = __fmul2_rn(__fmul2_rn(ax, ax), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(ee.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(ee.y));
+    float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+    p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
+    p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
+    p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
+    p = __fmul2_rn(p, t);
+    float2 h = __ffma2_rn(__fmul2_rn(p, e), make_float2(-0.5f, -0.5f), make_float2(0.5f, 0.5f));     // erf(|x|) / 2
+    h.x = copysignf(h.x, x.x);
+    h.y = copysignf(h.y, x.y);
+    const float2 phi = __fadd2_rn(h, make_float2(0.5f, 0.5f));
+    if (WITH_GRAD) g = __ffma2_rn(__fmul2_rn(v, make_float2(0.3989422804014327f, 0.3989422804014327f)), e, phi);
+    return __fmul2_rn(__fmul2_rn(v, phi), make_float2(out_scale, out_scale));
+}
+
 template <int ACT>
 __device__ __forceinline__ float fast_act(float v) {
     if (ACT == 1) return fmaxf(v, 0.f);
@@ -320,7 +347,7 @@ __device__ __forceinline__ uint32_t sw64(int r, int c) { return (uint32_t)(r * 6
 // accumulators live the exact-GELU / derivative epilogues kept ~58 words per thread in local memory); the TMEM stage is
 // released after the last load.
 template <int ACT>
-__device__ __forceinline__ void epilogue_tma(uint32_t tmem_chunk, uint64_t *acc_empty_bar, const Epilogue &ep,
+__device__ __forceinline__ void epilogue_tma(uint32_t tmem_chunk, uint64_t *acc_empty_bar, bool release, const Epilogue &ep,
                                              const CUtensorMap *map_c, const CUtensorMap *map_pre, uint32_t out_stg,
                                              uint32_t aux_stg, uint64_t *auxbar, uint32_t &aux_phase, long row0, int lane,
                                              int col0) {
@@ -333,7 +360,7 @@ __device__ __forceinline__ void epilogue_tma(uint32_t tmem_chunk, uint64_t *acc_
     for (int c = 0; c < 4; ++c) {                      // 8 columns at a time, rolled: low register pressure, 4x less code
         uint32_t acc[8];
         tmem_ld8(tmem_chunk + c * 8, acc);
-        if (c == 3) {                                  // the whole chunk has left TMEM: release the accumulator stage
+        if (c == 3 && release) {                       // the warp's last chunk has left TMEM: release the accumulator stage
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty_bar)) : "memory");
@@ -361,7 +388,16 @@ __device__ __forceinline__ void epilogue_tma(uint32_t tmem_chunk, uint64_t *acc_
                 x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
                 x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
             }
-            if (ep.preact != nullptr) {
+            if (ACT == 3) {                             // exact GELU: packed pairs
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    float2 gg = make_float2(0.f, 0.f);
+                    const float2 y = ep.preact != nullptr ? gelu2<true>(make_float2(x[j], x[j + 1]), gg, ep.out_scale)
+                                                          : gelu2<false>(make_float2(x[j], x[j + 1]), gg, ep.out_scale);
+                    x[j] = y.x; x[j + 1] = y.y;
+                    g[j] = gg.x; g[j + 1] = gg.y;
+                }
+            } else if (ep.preact != nullptr) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = act_with_grad<ACT>(x[j], g[j]) * ep.out_scale;
             } else {
@@ -372,7 +408,12 @@ __device__ __forceinline__ void epilogue_tma(uint32_t tmem_chunk, uint64_t *acc_
         if (ep.drop_thresh) {
             const uint32_t i0 = (uint32_t)(grow * ep.ldc + col0 + c * 8);   // < 2^32 (host check)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = drop_keep32(ep.drop_seed.key0, i0 + j, ep.drop_thresh) ? x[j] * ep.drop_scale : 0.f;
+            for (int j = 0; j < 8; j += 2) {            // mask pair, one packed multiply
+                const float2 mk = make_float2(drop_keep32(ep.drop_seed.key0, i0 + j, ep.drop_thresh) ? ep.drop_scale : 0.f,
+                                              drop_keep32(ep.drop_seed.key0, i0 + j + 1, ep.drop_thresh) ? ep.drop_scale : 0.f);
+                const float2 y = __fmul2_rn(make_float2(x[j], x[j + 1]), mk);
+                x[j] = y.x; x[j + 1] = y.y;
+            }
         }
         if (ACT < 5 && ep.residual != nullptr) {
 #pragma unroll
@@ -573,33 +614,44 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BN;
             const int r = quarter * 32 + lane;
             if constexpr (TMA_EPI != 0) {
-                // ---- row-per-lane epilogue with TMA stores (one 32 x 32 chunk per warp: BN <= 128) ----
-                const int col0 = n0 + cgrp * 32;
-                const bool mine = cgrp < BN / 32 && col0 < N;       // warp-uniform
+                // ---- row-per-lane epilogue with TMA stores: chunk c = cgrp + 4 * ci of the tile (one per warp at BN = 128, two at
+                //      BN = 256; the warp's staging tiles are reused chunk after chunk) ----
+                constexpr int kMineT = (BN / 32 + 3) / 4;
                 const long row0 = (long)mt * BM + quarter * 32;
-                if (lane == 0 && mine) {
-                    tma_store_wait_read();                          // the previous tile's stores have left both staging tiles
-                    if (ep.residual != nullptr) {
-                        mbar_expect_tx(aux_bar + (warp - 2), 32 * 64);
-                        tma_load_2d((void *)(staging + (warp - 2) * S::kWarpStaging + 2048), &map_aux, aux_bar + (warp - 2), col0,
-                                    (int)row0);
+                bool waited = false;
+#pragma unroll 1
+                for (int ci = 0; ci < kMineT; ++ci) {
+                    const int c = cgrp + 4 * ci;
+                    const int col0 = n0 + c * 32;
+                    const bool mine = c < BN / 32 && col0 < N;          // warp-uniform
+                    const bool last = ci == kMineT - 1;
+                    if (lane == 0 && mine) {
+                        tma_store_wait_read();                          // the previous stores have left both staging tiles
+                        if (ep.residual != nullptr) {
+                            mbar_expect_tx(aux_bar + (warp - 2), 32 * 64);
+                            tma_load_2d((void *)(staging + (warp - 2) * S::kWarpStaging + 2048), &map_aux, aux_bar + (warp - 2), col0,
+                                        (int)row0);
+                        }
                     }
-                }
-                __syncwarp();
-                mbar_wait(acc_full + as, aph);
-                tc_fence_after();
-                const uint32_t chunk = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(cgrp * 32);
-                if (mine) {
-                    switch (ep.act) {
-#define EPI_TMA(A_) case A_: epilogue_tma<A_>(chunk, acc_empty + as, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
-                        EPI_TMA(0) EPI_TMA(1) EPI_TMA(2) EPI_TMA(3) EPI_TMA(4) EPI_TMA(5) EPI_TMA(6)
-                        default: epilogue_tma<7>(chunk, acc_empty + as, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
-#undef EPI_TMA
-                    }
-                } else {
-                    tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
+                    if (!waited) {
+                        mbar_wait(acc_full + as, aph);
+                        tc_fence_after();
+                        waited = true;
+                    }
+                    const uint32_t chunk = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(c * 32);
+                    if (mine) {
+                        switch (ep.act) {
+#define EPI_TMA(A_) case A_: epilogue_tma<A_>(chunk, acc_empty + as, last, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
+                            EPI_TMA(0) EPI_TMA(1) EPI_TMA(2) EPI_TMA(3) EPI_TMA(4) EPI_TMA(5) EPI_TMA(6)
+                            default: epilogue_tma<7>(chunk, acc_empty + as, last, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
+#undef EPI_TMA
+                        }
+                    } else if (last) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
+                    }
                 }
             } else {
             long row;       // global output row of tile row r (this lane's accumulator row)
@@ -740,13 +792,13 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
     static const bool tma_off = getenv("POSE_NO_TMA_EPILOGUE") != nullptr;     // A/B switch for measurements
     static const bool tma_all = getenv("POSE_TMA_EPILOGUE_ALL") != nullptr;    // measurements: TMA path for every bf16 GEMM
     const bool heavy = ep.act == 3 || ep.act >= 5 || ep.preact != nullptr || tma_all;
-    if (MODE == 0 && BN <= 128 && ep.out_bf16 && !ep.accumulate && ep.vec && N % 32 == 0 && heavy && !tma_off) {
+    if (MODE == 0 && ep.out_bf16 && !ep.accumulate && ep.vec && N % 32 == 0 && heavy && !tma_off) {
         int e = make_map_tile32(&mc, ep.C, M, N, ep.ldc);
         if (!e && ep.residual) e = make_map_tile32(&maux, ep.residual, M, N, ep.ldr);
         if (!e && ep.preact) e = make_map_tile32(&mpre, ep.preact, M, N, ep.ldc);
         ep.tma = e ? 0 : 1;
     }
-    constexpr int kTma = (MODE == 0 && BN <= 128) ? 1 : 0;
+    constexpr int kTma = MODE == 0 ? 1 : 0;
     constexpr int kStagesT = (kTma && BN == 128) ? kStages + 1 : kStages;      // 5 x 32 KB stages fit beside the TMA staging
     using S0 = GemmSmem<BN, kStages, BKC, 0>;
     using S1 = GemmSmem<BN, kStagesT, BKC, kTma>;
@@ -776,18 +828,20 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
 
 // 128 x 256 tiles (3 stages of 48 KB): the 128 x 128 main loop reads 32 KB of operands per 256 tensor-core cycles, which is
 // the whole 128 B/clk shared-memory read bandwidth of the SM; the wide tile needs 96 B/clk.  Used for plain epilogues
-// (the TMA-store epilogue of the GELU / derivative GEMMs is a 128-column design) when there are enough tiles to go round.
+// and for the TMA-store epilogue of the GELU / derivative GEMMs (two chunks per warp) when there are enough tiles to go round.
 static bool wide_tile_ok(const Epilogue &ep, int N, int K, int m_tiles, int k_splits) {
     static const bool off = getenv("POSE_GEMM_NO_BN256") != nullptr;      // A/B switch for measurements
     if (off || N % 256 || K < 512) return false;          // short contractions are output-write bound: nothing to gain
+    static const bool heavy_narrow = getenv("POSE_GEMM_HEAVY_BN128") != nullptr;      // A/B switch for measurements
     const bool heavy = ep.act == 3 || ep.act >= 5 || ep.preact != nullptr;
-    if (heavy && ep.out_bf16 && !ep.accumulate && ep.vec) return false;  // those take the TMA-store epilogue
+    if (heavy_narrow && heavy && ep.out_bf16 && !ep.accumulate && ep.vec) return false;
     return (long)m_tiles * (N / 256) * k_splits >= kNumSMs;
 }
 // short contractions with per-element epilogue work (activation, residual read) are epilogue bound: two 32-column chunks
 // per epilogue warp lose to the 128-column tile there (measured: 37.0 vs 34.4 us at K = 768 with a residual)
 static bool wide_tile_fwd_ok(const Epilogue &ep, int N, int K, int m_tiles) {
-    if ((ep.act != 0 || ep.residual != nullptr) && K < 1024) return false;
+    const bool tma_heavy = (ep.act == 3 || ep.act >= 5 || ep.preact != nullptr) && ep.out_bf16 && !ep.accumulate && ep.vec;
+    if (!tma_heavy && (ep.act != 0 || ep.residual != nullptr) && K < 1024) return false;
     return wide_tile_ok(ep, N, K, m_tiles, 1);
 }
 

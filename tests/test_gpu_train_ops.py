@@ -77,9 +77,10 @@ def test_weight_gradient_gemm_split_k_accumulates(pose, M, Nout, Kin, splits):
     assert torch.allclose(dw, want, rtol=1e-3, atol=tol), (dw - want).abs().max().item()
 
 
-def test_forward_gemm_saves_the_activation_derivative(pose):
+@pytest.mark.parametrize("M", [500, 16448])        # 16448 rows: 128 x 256 tiles with the two-chunk TMA-store epilogue
+def test_forward_gemm_saves_the_activation_derivative(pose, M):
     g = torch.Generator().manual_seed(3)
-    M, K, N = 500, 768, 3072
+    K, N = 768, 3072
     a = torch.randn(M, K, generator=g).to(DEV).bfloat16()
     w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).bfloat16()
     b = torch.randn(N, generator=g).to(DEV)
