@@ -37,6 +37,7 @@ class CnnTrainPlan:
         self.cm = cm
         self.model, self.B, self.dev = model, B, device
         self.lib = _lib.lib()
+        self._sp = None          # stream handle of the current forward / backward (see call)
         c = model.config
         S = int(c.heatmap_size)
         if tuple(c.image_size) != (S, S):
@@ -128,7 +129,11 @@ class CnnTrainPlan:
         return t
 
     def call(self, name, *args):
-        _lib.check(getattr(self.lib, name)(*args, _lib.stream_ptr()), name)
+        # the stream handle is looked up once per forward / backward (a property chain in torch, ~3 us: it was the largest
+        # single item of the per-launch host cost of a step with 500-600 launches)
+        rc = getattr(self.lib, name)(*args, self._sp if self._sp is not None else _lib.stream_ptr())
+        if rc:
+            _lib.check(rc, name)
         self.launches += 1
 
     def ws(self, name, n):
@@ -570,6 +575,7 @@ class CnnTrainPlan:
                   self.pk32.data_ptr(), self.pk16.data_ptr())
 
     def forward(self, image, depth, kp, save=True):
+        self._sp = _lib.stream_ptr()
         m, Bn, S = self.model, self.B, self.S
         c = m.config
         _lib.require_cuda(image, "image", torch.float32)
@@ -641,6 +647,7 @@ class CnnTrainPlan:
         return h
 
     def backward(self, dout, section_done=None):
+        self._sp = _lib.stream_ptr()
         if not getattr(self, "saved", False):
             raise RuntimeError("backward needs a training-mode forward on this plan first")
         m, Bn, flat, b = self.model, self.B, self.flat, self.bufs

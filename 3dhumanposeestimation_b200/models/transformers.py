@@ -243,6 +243,7 @@ class VitPlan:
     def __init__(self, model: TransformerPoseEstimation, B: int, device):
         self.model, self.B, self.dev = model, B, device
         self.lib = _lib.lib()
+        self._sp = None          # stream handle of the current forward / backward (see call)
         c = model.config
         self.J = c.num_joints
         self.E = c.transformer_embed_dim
@@ -279,7 +280,11 @@ class VitPlan:
         return t
 
     def call(self, name, *args):
-        _lib.check(getattr(self.lib, name)(*args, _lib.stream_ptr()), name)
+        # the stream handle is looked up once per forward / backward (a property chain in torch, ~3 us: it was the largest
+        # single item of the per-launch host cost of a step with 500-600 launches)
+        rc = getattr(self.lib, name)(*args, self._sp if self._sp is not None else _lib.stream_ptr())
+        if rc:
+            _lib.check(rc, name)
         self.launches += 1
 
     def seed(self, site):
@@ -393,6 +398,7 @@ class VitPlan:
         return x_img2, x_hm2
 
     def forward(self, image, depth, kp, save):
+        self._sp = _lib.stream_ptr()
         m, B, E = self.model, self.B, self.E
         c = m.config
         _lib.require_cuda(image, "image", torch.float32)
@@ -583,6 +589,7 @@ class VitPlan:
         """dout: gradient of the [B, J, 3] output (fp32).  Accumulates into the flat .grad buffer.
         section_done(flat, lo, hi) is called as soon as every kernel writing flat.grad[lo:hi) has been enqueued
         (the data-parallel trainer all-reduces that range while the rest of the backward runs)."""
+        self._sp = _lib.stream_ptr()
         if not getattr(self, "saved", False):
             raise RuntimeError("backward needs a training-mode forward on this plan first")
         m, B, E, b = self.model, self.B, self.E, self.bufs

@@ -38,6 +38,7 @@ class FlatParams:
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.shadow = torch.zeros(n, dtype=torch.bfloat16, device=dev)
         self.index = {}
+        self._views = {}
         with torch.no_grad():
             for p, off in zip(params, self.offsets):
                 view = self.master[off:off + p.numel()].view(p.shape)
@@ -81,22 +82,38 @@ class FlatParams:
         return True
 
     # views ------------------------------------------------------------------------------------------
+    # The accessors below are called several times per launch by the plans: the views are cached (the flat buffers are
+    # allocated once, so a view never goes stale) -- building two or three torch views per call was a measurable share of
+    # the host time of a 500-launch step.
+    def _cached(self, kind, p, rows, make):
+        key = (kind, id(p), None if rows is None else (int(rows[0]), int(rows[1])))
+        v = self._views.get(key)
+        if v is None:
+            v = self._views[key] = make()
+        return v
+
     def w16(self, p, rows=None):
         """bf16 shadow of parameter p as a 2-D [out, in...] matrix (optionally a row range)."""
-        off = self.index[id(p)]
-        v = self.shadow[off:off + p.numel()].view(p.shape[0], -1)
-        return v if rows is None else v[rows[0]:rows[1]]
+        def make():
+            off = self.index[id(p)]
+            v = self.shadow[off:off + p.numel()].view(p.shape[0], -1)
+            return v if rows is None else v[rows[0]:rows[1]]
+        return self._cached(0, p, rows, make)
 
     def f32(self, p):
-        off = self.index[id(p)]
-        return self.master[off:off + p.numel()].view(p.shape)
+        def make():
+            off = self.index[id(p)]
+            return self.master[off:off + p.numel()].view(p.shape)
+        return self._cached(1, p, None, make)
 
     def g32(self, p, rows=None):
-        off = self.index[id(p)]
-        v = self.grad[off:off + p.numel()].view(p.shape)
-        if rows is None:
-            return v
-        return v.view(p.shape[0], -1)[rows[0]:rows[1]] if p.dim() > 1 else v[rows[0]:rows[1]]
+        def make():
+            off = self.index[id(p)]
+            v = self.grad[off:off + p.numel()].view(p.shape)
+            if rows is None:
+                return v
+            return v.view(p.shape[0], -1)[rows[0]:rows[1]] if p.dim() > 1 else v[rows[0]:rows[1]]
+        return self._cached(2, p, rows, make)
 
     # shadow -----------------------------------------------------------------------------------------
     def version(self):
