@@ -124,7 +124,7 @@ __device__ __forceinline__ void attn_epilogue(uint32_t tmem_base) {
 // S = Q K^T of step t + 1, whose operands arrive by TMA during the softmax of step t.
 constexpr int kFwdKC = 64;
 template <int HD>
-__global__ void __launch_bounds__(kAttnThreads, 2)
+__global__ void __launch_bounds__(kAttnThreads, 3)      // 80 registers, 67 KB, 128 TMEM columns: three CTAs per SM
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, __nv_bfloat16 *__restrict__ O, float *__restrict__ lse, int Nq, int Nk,
                    int Nkp, long ldo, long bso, float scale, uint32_t drop_thresh, float drop_scale,
