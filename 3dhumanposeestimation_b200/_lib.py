@@ -124,6 +124,7 @@ SIGNATURES = {
     "pose_dropout_bf16": (c_int, [c_void_p, C.c_long, c_float, C.c_uint64, c_void_p, c_void_p]),
     "pose_param_repack": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pose_eval_metrics": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "pose_collate_pad": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pose_infer_prep": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p]),
     "pose_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_long, c_float, c_float, c_float,

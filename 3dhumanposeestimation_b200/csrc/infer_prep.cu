@@ -69,3 +69,46 @@ POSE_API int pose_infer_prep(const float *depth, int B, int h, int w, int H, int
     }
     return launch_status();
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Collate (reference: src/dataset/collator.py:10-61 Human36MCollator): variable-sized samples
+// image [3, h_b, w_b] / depth [1, h_b, w_b] fp32 -> zero-padded batch [B, 3, Hm, Wm] / [B, 1, Hm, Wm] (F.pad on the right /
+// bottom, then torch.stack), one launch for the whole batch through a device table of sample pointers.  Optionally the
+// depth is rescaled on the way, depth * (max - min) + min (src/dataset/chunked_dataset.py:159-164).
+// ---------------------------------------------------------------------------------------------------------
+namespace pose {
+struct CollateEntry {
+    const float *image, *depth;
+    int h, w;
+    float dscale, dshift;
+};
+static_assert(sizeof(CollateEntry) == 32, "CollateEntry must stay 32 bytes (host mirror in dataset/collator.py)");
+
+__global__ void __launch_bounds__(256)
+collate_pad_kernel(const CollateEntry *__restrict__ table, int Hm, int Wm, float *__restrict__ image, float *__restrict__ depth) {
+    const CollateEntry e = table[blockIdx.y];
+    const long plane = (long)Hm * Wm;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < 4 * plane; i += (long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i / plane);
+        const long p = i - ch * plane;
+        const int y = (int)(p / Wm), x = (int)(p - (long)y * Wm);
+        const bool in = y < e.h && x < e.w;
+        if (ch < 3) {
+            image[((long)blockIdx.y * 3 + ch) * plane + p] = in ? __ldg(e.image + ((long)ch * e.h + y) * e.w + x) : 0.f;
+        } else {
+            // the padding is applied AFTER the rescale in the reference (the dataset rescales, the collator pads): zeros stay zeros
+            depth[(long)blockIdx.y * plane + p] = in ? __fadd_rn(__fmul_rn(__ldg(e.depth + (long)y * e.w + x), e.dscale), e.dshift) : 0.f;
+        }
+    }
+}
+}  // namespace pose
+
+POSE_API int pose_collate_pad(const void *table, int B, int Hm, int Wm, float *image, float *depth, pose_stream_t stream) {
+    if (!table || !image || !depth) return POSE_E_NULL;
+    if (B <= 0 || Hm <= 0 || Wm <= 0) return POSE_E_SHAPE;
+    long gx = (4L * Hm * Wm + 255) / 256;
+    const long cap = ((long)kNumSMs * 16 + B - 1) / B;
+    if (gx > cap) gx = cap;
+    collate_pad_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, (cudaStream_t)stream>>>((const CollateEntry *)table, Hm, Wm, image, depth);
+    return launch_status();
+}

@@ -366,6 +366,15 @@ int pose_eval_metrics(const float *pred, const float *gt, int B, int J, float *p
 int pose_infer_prep(const float *depth, int B, int h, int w, int H, int W, float *depth_out, const float *kpts_px_conf, int K,
                     float img_w, float img_h, float *kp_norm, float *kp_norm_conf, pose_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * next row: collate on the device     reference: src/dataset/collator.py:10-61 (Human36MCollator)
+ *    table: B entries of 32 bytes on the device {const float *image [3,h,w]; const float *depth [1,h,w]; int h, w;
+ *    float depth_scale, depth_shift}; image [B,3,Hm,Wm] / depth [B,1,Hm,Wm] fp32 = every sample zero padded on the right /
+ *    bottom to the batch maximum (F.pad + torch.stack), depth optionally rescaled depth * scale + shift on the way
+ *    (src/dataset/chunked_dataset.py:159-164; pass scale 1, shift 0 for a plain copy).
+ * ------------------------------------------------------------------------------------------- */
+int pose_collate_pad(const void *table, int B, int Hm, int Wm, float *image, float *depth, pose_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

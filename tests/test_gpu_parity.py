@@ -439,3 +439,38 @@ def test_run_inference_mirrors_the_reference_call(pose):
     assert out.shape == (17, 3) and np.isfinite(out).all() and not m.training
     with torch.no_grad():
         assert np.array_equal(out, m(img, dep, kp)[0].float().cpu().numpy())
+
+
+def _ref_collate(batch):
+    """src/dataset/collator.py:20-61 restated with the same torch calls (F.pad right / bottom, torch.stack)."""
+    mh = max(s["image"].shape[1] for s in batch)
+    mw = max(s["image"].shape[2] for s in batch)
+    pad = lambda t: torch.nn.functional.pad(t, (0, mw - t.shape[2], 0, mh - t.shape[1]))   # noqa: E731
+    return torch.stack([pad(s["image"]) for s in batch]), torch.stack([pad(s["depth"]) for s in batch]), (mh, mw)
+
+
+def test_collator_matches_the_reference_padding(pose):
+    """Human36MCollator on the device, bit-exact (ragged sizes, a single sample, equal sizes)."""
+    import importlib
+    col = importlib.import_module("3dhumanposeestimation_b200.dataset.collator").Human36MCollator()
+    g = torch.Generator().manual_seed(9)
+    for sizes in ([(204, 204), (307, 307), (256, 256), (230, 251)], [(64, 48)], [(32, 32), (32, 32)]):
+        batch = []
+        for i, (h, w) in enumerate(sizes):
+            batch.append({"image": torch.rand(3, h, w, generator=g).to(DEV), "depth": torch.rand(1, h, w, generator=g).to(DEV),
+                          "keypoints_2d": torch.rand(17, 2, generator=g).to(DEV), "joints_3d": torch.randn(17, 3, generator=g).to(DEV),
+                          "camera_params": {"f": [1.0, 1.0]}, "image_path": f"p{i}", "action": "a", "subaction": 1,
+                          "image_size": torch.tensor([h, w]), "frame_idx": i})
+        out = col(batch)
+        img, dep, pad = _ref_collate(batch)
+        assert torch.equal(out["image"], img) and torch.equal(out["depth"], dep)
+        assert out["padding"] == [pad] * len(sizes) and out["image_path"] == [f"p{i}" for i in range(len(sizes))]
+        assert out["keypoints_2d"].shape == (len(sizes), 17, 2) and out["image_size"].shape == (len(sizes), 2)
+        # the dataset's depth rescale (chunked_dataset.py:159-164) fused into the same launch
+        rng = [(0.5 * i, 0.5 * i + 3.0) for i in range(len(sizes))]
+        out2 = col(batch, depth_range=rng)
+        want = torch.stack([torch.nn.functional.pad(s["depth"] * (hi - lo) + lo, (0, pad[1] - s["depth"].shape[2], 0, pad[0] - s["depth"].shape[1]))
+                            for s, (lo, hi) in zip(batch, rng)])
+        assert torch.equal(out2["depth"], want)
+    with pytest.raises(Exception):
+        col([{**batch[0], "image": batch[0]["image"].cpu()}])          # CPU tensors: no fallback
