@@ -890,13 +890,25 @@ using namespace pose;
 
 #define REQ(c, e) do { if (!(c)) return (e); } while (0)
 
-// number of per-block partial slots a row reduction over [M, C] uses, given a scratch capacity in floats
-static int bn_parts(long M, int C, long cap_floats) {
+// number of per-block partial slots a row reduction over [M, C] uses, given a scratch capacity in floats: one wave of
+// RESIDENT CTAs (per_sm from the occupancy calculator) -- with a fixed 4 per SM the 80-register backward reduction (3
+// resident CTAs per SM) ran a second, one-third-full wave
+static int bn_parts(long M, int C, long cap_floats, int per_sm) {
     long parts = rowmap_grid(M, C, 8);
-    if (parts > kNumSMs * 4) parts = kNumSMs * 4;      // 4 CTAs per SM saturate HBM; fewer partials to fold
+    if (parts > (long)kNumSMs * per_sm) parts = (long)kNumSMs * per_sm;
     const long fit = cap_floats / (2L * C);
     if (parts > fit) parts = fit;
     return (int)(parts < 1 ? 1 : parts);
+}
+template <class K>
+static int resident_ctas(K kern, int threads) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, 0) != cudaSuccess || n < 1) n = 1;
+    return n > 8 ? 8 : n;
+}
+static int one_wave(int grid, int per_sm) { return grid < kNumSMs * per_sm ? grid : kNumSMs * per_sm; }   // grid-stride kernels
+static int bn_stats_parts(long M, int C, long cap_floats) {
+    return bn_parts(M, C, cap_floats, resident_ctas(bn_stats_kernel, rowmap_threads(C)));
 }
 
 POSE_API int pose_bn_stats_bf16(const void *Y, long M, int C, long ld, float *partials, long cap_floats, pose_stream_t stream) {
@@ -905,7 +917,7 @@ POSE_API int pose_bn_stats_bf16(const void *Y, long M, int C, long ld, float *pa
     REQ((uintptr_t)Y % 16 == 0, POSE_E_ALIGN);
     REQ(C <= 3072, POSE_E_UNSUPPORTED);
     REQ(cap_floats >= 2L * C, POSE_E_WORKSPACE);
-    bn_stats_kernel<<<bn_parts(M, C, cap_floats), rowmap_threads(C), 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Y, M, C, ld,
+    bn_stats_kernel<<<bn_stats_parts(M, C, cap_floats), rowmap_threads(C), 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Y, M, C, ld,
                                                                                                partials);
     return launch_status();
 }
@@ -915,7 +927,7 @@ POSE_API int pose_bn_finalize(const float *partials, long cap_floats, long count
                               float *running_var, pose_stream_t stream) {
     REQ(partials && gamma && beta && mean_rstd && scale_shift, POSE_E_NULL);
     REQ(count > 0 && C > 0, POSE_E_SHAPE);
-    bn_finalize_kernel<<<(C + 7) / 8, 256, 0, (cudaStream_t)stream>>>(partials, bn_parts(count, C, cap_floats), (float)count,
+    bn_finalize_kernel<<<(C + 7) / 8, 256, 0, (cudaStream_t)stream>>>(partials, bn_stats_parts(count, C, cap_floats), (float)count,
                                                                          gamma, beta, eps, momentum, C, mean_rstd, scale_shift,
                                                                          running_mean, running_var);
     return launch_status();
@@ -940,10 +952,10 @@ POSE_API int pose_bn_apply_bf16(const void *Y, long M, int C, const float *scale
         POSE_E_SHAPE);
     REQ((uintptr_t)Y % 16 == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)residual % 16 == 0, POSE_E_ALIGN);
     REQ(C <= 3072 && act >= 0 && act <= 2, POSE_E_UNSUPPORTED);
-    const int grid = rowmap_grid(M, C, 4), thr = rowmap_threads(C);
+    const int thr = rowmap_threads(C);
     cudaStream_t s = (cudaStream_t)stream;
 #define BN_APPLY(A_)                                                                                                   \
-    bn_apply_kernel<A_><<<grid, thr, 0, s>>>((const __nv_bfloat16 *)Y, M, C, scale_shift, out_scale,                    \
+    bn_apply_kernel<A_><<<one_wave(rowmap_grid(M, C, 4), resident_ctas(bn_apply_kernel<A_>, thr)), thr, 0, s>>>((const __nv_bfloat16 *)Y, M, C, scale_shift, out_scale,                    \
                                              (const __nv_bfloat16 *)residual, ld_res, (__nv_bfloat16 *)out, ld_out)
     if (act == 0) BN_APPLY(0); else if (act == 1) BN_APPLY(1); else BN_APPLY(2);
 #undef BN_APPLY
@@ -959,13 +971,14 @@ POSE_API int pose_bn_bwd_bf16(const void *dA, long ld_da, const void *Y, long M,
     REQ(C <= 3072 && act >= 0 && act <= 2, POSE_E_UNSUPPORTED);
     REQ(cap_floats >= 2L * C, POSE_E_WORKSPACE);
     cudaStream_t s = (cudaStream_t)stream;
-    const int thr = rowmap_threads(C), parts = bn_parts(M, C, cap_floats);
+    const int thr = rowmap_threads(C);
 #define BN_BWD(A_)                                                                                                     \
+    const int parts = bn_parts(M, C, cap_floats, resident_ctas(bn_bwd_reduce_kernel<A_>, thr));                        \
     bn_bwd_reduce_kernel<A_><<<parts, thr, 0, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, M, C,     \
                                                   scale_shift, mean_rstd, out_scale, partials);                        \
     bn_bwd_coef_kernel<<<(C + 7) / 8, 256, 0, s>>>  (partials, parts, 1.0f / (float)M, scale_shift, mean_rstd, C, coef,    \
                                                       dgamma, dbeta);                                                  \
-    bn_bwd_apply_kernel<A_><<<rowmap_grid(M, C, 4), thr, 0, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, M, \
+    bn_bwd_apply_kernel<A_><<<one_wave(rowmap_grid(M, C, 4), resident_ctas(bn_bwd_apply_kernel<A_>, thr)), thr, 0, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, M, \
                                                                 C, scale_shift, coef, out_scale, (__nv_bfloat16 *)dY)
     if (act == 0) { BN_BWD(0); } else if (act == 1) { BN_BWD(1); } else { BN_BWD(2); }
 #undef BN_BWD
