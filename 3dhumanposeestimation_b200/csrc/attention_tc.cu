@@ -122,6 +122,7 @@ __device__ __forceinline__ void attn_epilogue(uint32_t tmem_base) {
 // columns and 65 KB of shared memory: several CTAs share an SM and cover each other's tensor / TMA round trips.  The loop
 // is software pipelined over the flattened (query tile, key chunk) steps: O += P V of step t is issued together with
 // S = Q K^T of step t + 1, whose operands arrive by TMA during the softmax of step t.
+constexpr int kTilesPerCta = 1;      // query tiles of 128 rows per forward / dq CTA
 constexpr int kFwdKC = 64;
 template <int HD>
 __global__ void __launch_bounds__(kAttnThreads, 3)      // 80 registers, 67 KB, 128 TMEM columns: three CTAs per SM
@@ -138,6 +139,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     auto Kc = [&](int i) { return Ps + 16384 + i * 2 * KB; };       // double-buffered key / value chunks
     auto Vc = [&](int i) { return Ps + 16384 + KB + i * 2 * KB; };
     const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
+    // blockIdx.z: this CTA's range of query tiles (one tile per CTA: key / value chunks are re-streamed per tile anyway, and
+    // the finer granularity cuts the last-wave loss of 768 three-tile CTAs over 296-444 resident slots)
+    const int q_begin = blockIdx.z * kTilesPerCta * 128, q_end = min(Nq, q_begin + kTilesPerCta * 128);
     const int warp = threadIdx.x >> 5, quarter = warp & 3, grp = warp >> 2;
     const int r = quarter * 32 + (threadIdx.x & 31);              // this thread's query row (shared by its twin in the other group)
     __shared__ float red_m[2][128], red_s[2][128];
@@ -159,7 +163,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         if (threadIdx.x == 0) {
             uint64_t *lb = sync.load_bar();
             mbar_expect_tx(lb, 16384 + 2 * box_bytes(n0));
-            tma_rows(Qs, &mapQ, lb, h * HD, 0, b, 128);
+            tma_rows(Qs, &mapQ, lb, h * HD, q_begin, b, 128);
             tma_rows(Kc(0), &mapK, lb, h * HD, 0, b, n0);
             tma_rows(Vc(0), &mapV, lb, h * HD, 0, b, n0);
         }
@@ -169,8 +173,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     }
 
     int t = 0;
-    for (int q0 = 0; q0 < Nq; q0 += 128) {
-        const bool last_tile = q0 + 128 >= Nq;
+    for (int q0 = q_begin; q0 < q_end; q0 += 128) {
+        const bool last_tile = q0 + 128 >= q_end;
         const bool live = q0 + quarter * 32 < Nq;        // warps whose 32 rows are all padding skip the softmax
         const uint32_t drop_row = (uint32_t)(((b * heads + h) * Nq + q0 + r) * Nk);   // mask index of (row, key 0); < 2^32 (host check)
         float m = -INFINITY, l = 0.f;                    // running row maximum (raw scores) and this thread's share of the row sum
@@ -296,6 +300,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     auto Kc = [&](int i) { return dSs + 16384 + i * 2 * KB; };      // double-buffered key / value chunks
     auto Vc = [&](int i) { return dSs + 16384 + KB + i * 2 * KB; };
     const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
+    // blockIdx.z: this CTA's range of query tiles (one tile per CTA: key / value chunks are re-streamed per tile anyway, and
+    // the finer granularity cuts the last-wave loss of 768 three-tile CTAs over 296-444 resident slots)
+    const int q_begin = blockIdx.z * kTilesPerCta * 128, q_end = min(Nq, q_begin + kTilesPerCta * 128);
     const int warp = threadIdx.x >> 5, quarter = warp & 3, grp = warp >> 2;
     const int r = quarter * 32 + (threadIdx.x & 31);
     const __nv_bfloat16 *og = O + b * bso + (long)h * HD, *dog = dO + b * bsdo + (long)h * HD;
@@ -321,8 +328,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         if (threadIdx.x == 0) {
             uint64_t *lb = sync.load_bar();
             mbar_expect_tx(lb, 2 * 16384 + 2 * box_bytes(n0));
-            tma_rows(Qs, &mapQ, lb, h * HD, 0, b, 128);
-            tma_rows(dOs, &mapdO, lb, h * HD, 0, b, 128);
+            tma_rows(Qs, &mapQ, lb, h * HD, q_begin, b, 128);
+            tma_rows(dOs, &mapdO, lb, h * HD, q_begin, b, 128);
             tma_rows(Kc(0), &mapK, lb, h * HD, 0, b, n0);
             tma_rows(Vc(0), &mapV, lb, h * HD, 0, b, n0);
         }
@@ -332,8 +339,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     }
 
     int t = 0;
-    for (int q0 = 0; q0 < Nq; q0 += 128) {
-        const bool last_tile = q0 + 128 >= Nq;
+    for (int q0 = q_begin; q0 < q_end; q0 += 128) {
+        const bool last_tile = q0 + 128 >= q_end;
         const bool row_ok = q0 + r < Nq;
         const bool live = q0 + quarter * 32 < Nq;
         const uint32_t drop_row = (uint32_t)(((b * heads + h) * Nq + q0 + r) * Nk);   // mask index of (row, key 0); < 2^32 (host check)
@@ -625,7 +632,7 @@ POSE_API int pose_attention_bf16(const void *Q, const void *K, const void *V, vo
     if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || bsq % 8 || bsk % 8 || bsv % 8 || bso % 8) return POSE_E_ALIGN;
     if ((uintptr_t)Q % 16 || (uintptr_t)K % 16 || (uintptr_t)V % 16 || (uintptr_t)O % 16) return POSE_E_ALIGN;
     const int Nkp = (Nk + 15) / 16 * 16;
-    const dim3 grid(heads, B);
+    const dim3 grid(heads, B, (Nq + kTilesPerCta * 128 - 1) / (kTilesPerCta * 128));
     cudaStream_t s = (cudaStream_t)stream;
     const int cols = heads * head_dim;
     if (ldq < cols || ldk < cols || ldv < cols || ldo < cols) return POSE_E_SHAPE;
@@ -663,7 +670,7 @@ POSE_API int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V
         if ((uintptr_t)q % 16) return POSE_E_ALIGN;
     const int Nkp = (Nk + 15) / 16 * 16;
     cudaStream_t s = (cudaStream_t)stream;
-    const dim3 g1(heads, B), g2((Nk + 127) / 128, heads, B);
+    const dim3 g1(heads, B, (Nq + kTilesPerCta * 128 - 1) / (kTilesPerCta * 128)), g2((Nk + 127) / 128, heads, B);
     const int cols = heads * head_dim;
     if (ldq < cols || ldk < cols || ldv < cols || ldo < cols || lddo < cols) return POSE_E_SHAPE;
     CUtensorMap mq, mk, mv, md;
