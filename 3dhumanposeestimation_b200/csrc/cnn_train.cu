@@ -860,6 +860,26 @@ repack_kernel(const RepackEntry *__restrict__ table, const float *__restrict__ s
         case 3: n = (long)e.d0 * e.d1; break;
         default: n = e.d0; break;
     }
+    if (e.kind == 1 || e.kind == 2) {
+        // destination-major: coalesced bf16 stores, strided fp32 gathers (L2 hits) -- the source-major loop scattered 2-byte
+        // stores over 32 sectors per warp
+        const int K = e.d2, Ci = e.d1, Co = e.d0;
+        const int inner = e.kind == 1 ? e.d3 : Co;               // fastest destination index: padded ci (kind 1) / co (kind 2)
+        const long nd = e.kind == 1 ? (long)Co * K * K * e.d3 : (long)Ci * K * K * Co;
+        for (long j = (long)blockIdx.x * 256 + threadIdx.x; j < nd; j += (long)gridDim.x * 256) {
+            long t = j;
+            const int in = (int)(t % inner); t /= inner;
+            const int kw = (int)(t % K); t /= K;
+            const int kh = (int)(t % K);
+            const int outer = (int)(t / K);
+            if (e.kind == 1) {
+                if (in < Ci) dst_bf16[e.dst + j] = __float2bfloat16_rn(s[(((long)outer * Ci + in) * K + kh) * K + kw]);
+            } else {
+                dst_bf16[e.dst + j] = __float2bfloat16_rn(s[(((long)in * Ci + outer) * K + (K - 1 - kh)) * K + (K - 1 - kw)]);
+            }
+        }
+        return;
+    }
     for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
         if (e.kind == 0 || e.kind == 6) {
             const long c = i / 9, k = i - c * 9;
