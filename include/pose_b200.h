@@ -142,7 +142,10 @@ typedef struct pose_gemm_epilogue {
     int32_t reserved;
     /* nn.Dropout fused after the activation and before the residual add: element (row, col) is kept iff
      * hash(drop_seed, row * ldc + col) >= drop_p * 2^32 and scaled by 1 / (1 - drop_p); with act 5..7 the same mask gates
-     * the gradient.  pose_dropout_bf16 over the compact [M, ldc] tensor with the same seed reproduces the mask. */
+     * the gradient.  pose_dropout_bf16 over the compact [M, ldc] tensor with the same seed reproduces the mask.
+     * hash(seed, i) = lowbias32(lo32(i) ^ key(seed, hi32(i))), key = a 64-bit murmur finaliser (csrc/common.cuh); the
+     * fused kernels use a 32-bit counter: M * ldc (attention: B * heads * Nq * Nk) must stay below 2^32
+     * (POSE_E_UNSUPPORTED otherwise). */
     uint64_t drop_seed;
     float drop_p;
     int32_t reserved2;
