@@ -135,22 +135,22 @@ patchify_kernel(const float *__restrict__ src0, int C0, const float *__restrict_
 // the forward: X / dX / dRes use the input addressing, dY the output addressing.
 // ---------------------------------------------------------------------------------------------------------
 template <int D8PL>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 layernorm_bwd_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__restrict__ dY,
                      const float *__restrict__ gamma, float eps, long M, int rows, long in_group, long in_off,
                      long out_group, long out_off, int D, const __nv_bfloat16 *__restrict__ dRes,
                      __nv_bfloat16 *__restrict__ dX, float *__restrict__ dgamma, float *__restrict__ dbeta) {
-    __shared__ float red[8][D8PL * 256];
+    // dgamma / dbeta partials live in shared memory, one private row pair per warp (a lane only ever touches its own
+    // columns: no synchronisation until the final fold).  Keeping those 48 accumulators in registers held the kernel at
+    // 168 registers = one CTA (8 warps) per SM, each warp walking its rows strictly one after the other.
+    extern __shared__ __align__(16) float s_acc[];          // [8 warps][2][D]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float gacc[D8PL][8], bacc[D8PL][8], gm[D8PL][8];
+    float *ga = s_acc + (size_t)warp * 2 * D, *ba = ga + D;
 #pragma unroll
     for (int q = 0; q < D8PL; ++q) {
         const int c = (q * 32 + lane) * 8;
-        const float4 g0 = __ldg((const float4 *)(gamma + c)), g1 = __ldg((const float4 *)(gamma + c) + 1);
-        gm[q][0] = g0.x; gm[q][1] = g0.y; gm[q][2] = g0.z; gm[q][3] = g0.w;
-        gm[q][4] = g1.x; gm[q][5] = g1.y; gm[q][6] = g1.z; gm[q][7] = g1.w;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) gacc[q][k] = bacc[q][k] = 0.f;
+        *(float4 *)(ga + c) = make_float4(0.f, 0.f, 0.f, 0.f); *(float4 *)(ga + c + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *(float4 *)(ba + c) = make_float4(0.f, 0.f, 0.f, 0.f); *(float4 *)(ba + c + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (long r = (long)blockIdx.x * 8 + warp; r < M; r += (long)gridDim.x * 8) {
         const long g = r / rows, i = r - g * rows;
@@ -178,16 +178,24 @@ layernorm_bwd_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *_
         const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int q = 0; q < D8PL; ++q)
+        for (int q = 0; q < D8PL; ++q) {
+            const int c = (q * 32 + lane) * 8;
+            float ga8[8], ba8[8], gm[8];
+            *(float4 *)ga8 = *(const float4 *)(ga + c); *(float4 *)(ga8 + 4) = *(const float4 *)(ga + c + 4);
+            *(float4 *)ba8 = *(const float4 *)(ba + c); *(float4 *)(ba8 + 4) = *(const float4 *)(ba + c + 4);
+            *(float4 *)gm = __ldg((const float4 *)(gamma + c)); *(float4 *)(gm + 4) = __ldg((const float4 *)(gamma + c) + 1);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 v[q][k] *= rstd;                                // xhat
-                gacc[q][k] += d[q][k] * v[q][k];
-                bacc[q][k] += d[q][k];
-                d[q][k] *= gm[q][k];                            // g * dY
+                ga8[k] += d[q][k] * v[q][k];
+                ba8[k] += d[q][k];
+                d[q][k] *= gm[k];                               // g * dY
                 s1 += d[q][k];
                 s2 += d[q][k] * v[q][k];
             }
+            *(float4 *)(ga + c) = *(const float4 *)ga8; *(float4 *)(ga + c + 4) = *(const float4 *)(ga8 + 4);
+            *(float4 *)(ba + c) = *(const float4 *)ba8; *(float4 *)(ba + c + 4) = *(const float4 *)(ba8 + 4);
+        }
         s1 = warp_sum(s1) / (float)D;
         s2 = warp_sum(s2) / (float)D;
 #pragma unroll
@@ -205,20 +213,15 @@ layernorm_bwd_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *_
         }
     }
     // fold the 8 warps' partials, then one atomic per column per CTA
+    __syncthreads();
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < D8PL; ++q)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) red[warp][(q * 32 + lane) * 8 + k] = pass == 0 ? gacc[q][k] : bacc[q][k];
-        __syncthreads();
         float *dst = pass == 0 ? dgamma : dbeta;
         if (dst != nullptr)
             for (int c = threadIdx.x; c < D; c += 256) {
                 float t = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) t += red[w][c];
+                for (int w = 0; w < 8; ++w) t += s_acc[((size_t)w * 2 + pass) * D + c];
                 atomicAdd(dst + c, t);
             }
     }
@@ -417,16 +420,26 @@ POSE_API int pose_layernorm_bwd_bf16(const void *X, const void *dY, const float 
     if ((uintptr_t)X % 16 || (uintptr_t)dY % 16 || (uintptr_t)dX % 16 || (uintptr_t)gamma % 16 || (dRes && (uintptr_t)dRes % 16))
         return POSE_E_ALIGN;
     long blocks = (M + 7) / 8;
-    const int grid = (int)(blocks < kNumSMs * 2 ? blocks : kNumSMs * 2);
+    const int smem = 8 * 2 * D * (int)sizeof(float);
     cudaStream_t s = (cudaStream_t)stream;
 #define LNB_LAUNCH(N_)                                                                                                  \
-    layernorm_bwd_kernel<N_><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)X, (const __nv_bfloat16 *)dY, gamma, eps, M,   \
+    static bool cfg##N_ = false;                                                                                        \
+    if (!cfg##N_) {                                                                                                     \
+        if (cudaFuncSetAttribute(layernorm_bwd_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) \
+            return POSE_E_UNSUPPORTED;                                                                                  \
+        cfg##N_ = true;                                                                                                 \
+    }                                                                                                                   \
+    int per_sm = 1;                                                                                                     \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_bwd_kernel<N_>, 256, smem) != cudaSuccess || per_sm < 1) \
+        per_sm = 1;                                                                                                     \
+    const int grid = (int)(blocks < (long)kNumSMs * per_sm ? blocks : (long)kNumSMs * per_sm);   /* one resident wave */   \
+    layernorm_bwd_kernel<N_><<<grid, 256, smem, s>>>((const __nv_bfloat16 *)X, (const __nv_bfloat16 *)dY, gamma, eps, M,   \
                                                   rows, in_group, in_off, out_group, out_off, D,                        \
                                                   (const __nv_bfloat16 *)dRes, (__nv_bfloat16 *)dX, dgamma, dbeta)
-    if (D == 256) LNB_LAUNCH(1);
-    else if (D == 512) LNB_LAUNCH(2);
-    else if (D == 768) LNB_LAUNCH(3);
-    else if (D == 1024) LNB_LAUNCH(4);
+    if (D == 256) { LNB_LAUNCH(1); }
+    else if (D == 512) { LNB_LAUNCH(2); }
+    else if (D == 768) { LNB_LAUNCH(3); }
+    else if (D == 1024) { LNB_LAUNCH(4); }
     else return POSE_E_UNSUPPORTED;
 #undef LNB_LAUNCH
     return launch_status();
