@@ -246,14 +246,13 @@ __global__ void __launch_bounds__(384)
 bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dA, long ld_da, const __nv_bfloat16 *__restrict__ Y, long M, int C,
                      const float *__restrict__ scale_shift, const float *__restrict__ mean_rstd, float out_scale,
                      float *__restrict__ partials) {
+    // The second sum is accumulated as sum(dz * y); the coefficient kernel turns it into sum(dz * xhat) =
+    // rstd * (sum(dz * y) - mean * sum(dz)).  That drops 16 per-channel constants from the registers of this kernel
+    // (80 -> 4 resident CTAs per SM instead of 3) and one FMA per element.
     const RowMap rm(C);
-    float a[8], b[8], rs[8], mr[8];
+    float a[8], b[8];
     ld8f(scale_shift + rm.c0, a);
     ld8f(scale_shift + C + rm.c0, b);
-    ld8f(mean_rstd + rm.c0, mr);
-    ld8f(mean_rstd + C + rm.c0, rs);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) mr[j] *= rs[j];              // xhat = y * rstd - mean * rstd
     float acc[2][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
@@ -267,7 +266,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dA, long ld_da, const __n
         for (int j = 0; j < 8; ++j) {
             const float dz = d[j] * out_scale * dactf<ACT>(fmaf(y[j], a[j], b[j]));
             acc[0][j] += dz;
-            acc[1][j] = fmaf(dz, fmaf(y[j], rs[j], -mr[j]), acc[1][j]);
+            acc[1][j] = fmaf(dz, y[j], acc[1][j]);
         }
     };
     for (; r + step < M; r += 2 * step) {               // two rows = four independent 16-byte loads in flight per thread
@@ -293,9 +292,10 @@ bn_bwd_coef_kernel(const float *__restrict__ partials, int parts, float inv_m, c
     float s1, s2;
     fold_parts(partials, parts, C, c, s1, s2);
     if (threadIdx.x < 8 && c < C) {
+        const float a = scale_shift[c], mean = mean_rstd[c], rstd = mean_rstd[C + c];
+        s2 = rstd * (s2 - mean * s1);                      // sum(dz * y) -> sum(dz * xhat)
         dgamma[c] += s2;
         dbeta[c] += s1;
-        const float a = scale_shift[c], mean = mean_rstd[c], rstd = mean_rstd[C + c];
         const float c1 = s1 * inv_m, c2 = s2 * inv_m;
         coef[c] = a * c2 * rstd;
         coef[C + c] = a * (c1 - c2 * mean * rstd);
