@@ -102,3 +102,21 @@ def test_checkpoint_round_trip_in_the_reference_format(tmp_path):
         raise AssertionError("expected ValueError")
     except ValueError:
         pass
+
+
+def test_next_row_host_mirrors_refuse_cpu_tensors():
+    """infer.prepare_model_inputs / Human36MCollator: no CPU fallback (the product path fails loudly without the GPU)."""
+    import importlib
+    import pytest
+    import torch
+    infer = importlib.import_module("3dhumanposeestimation_b200.infer")
+    col = importlib.import_module("3dhumanposeestimation_b200.dataset.collator").Human36MCollator()
+    with pytest.raises(Exception):
+        infer.prepare_model_inputs(torch.rand(1, 1, 8, 8), torch.rand(1, 17, 3), (8, 8), (16, 16))
+    sample = {"image": torch.rand(3, 8, 8), "depth": torch.rand(1, 8, 8), "keypoints_2d": torch.rand(17, 2),
+              "joints_3d": torch.rand(17, 3), "camera_params": {}, "image_path": "p", "action": "a", "subaction": 1,
+              "image_size": torch.tensor([8, 8]), "frame_idx": 0}
+    with pytest.raises(Exception):
+        col([sample])
+    with pytest.raises(ValueError):
+        col([])
