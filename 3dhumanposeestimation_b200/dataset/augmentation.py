@@ -156,6 +156,11 @@ class PoseAugmentor:
         return {"image": image_out, "depth": depth_out, "keypoints_2d": kp_out, "joints_3d": joints_out,
                 "camera": cam_out, "sizes": sizes, "params": params}
 
+    @staticmethod
+    def launches_per_batch() -> int:
+        """Kernels launched by one augment_batch call: operand pack, per-sample tables, fused cluster kernel."""
+        return 3
+
     def kernel_error_flag(self) -> int:
         """Debug aid (synchronises): non-zero if the fused kernel ever saw a band that did not fit the
         launch geometry computed by pose_augment_plan."""

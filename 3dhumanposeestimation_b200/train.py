@@ -73,6 +73,16 @@ class Trainer:
         return out5
 
 
+    # ---- bookkeeping for the measurement contract ----------------------------------------------------------
+    def launches_per_step(self, plan) -> int:
+        """Kernels of this library launched by one step: the plan's forward + backward, the fused loss, AdamW and the
+        workspace clear (memset)."""
+        return int(plan.launches) + 3
+
+    def launch_mode(self) -> str:
+        return "eager launches through the C ABI (one ctypes call per kernel)"
+
+
 def broadcast_parameters(model, src=0, process_group=None):
     """Replicas start from rank `src`'s parameters and buffers (one flat broadcast)."""
     from .params import FlatParams

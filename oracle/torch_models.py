@@ -149,9 +149,11 @@ def heatmaps(kp, hs, sigma):  # common.py:23-51
     return hm * (kp > 0).all(-1)[..., None, None]
 
 
-def cnn_forward(sd, cfg, image, depth, kp, train=False, return_stats=False, trace=None):
+def cnn_forward(sd, cfg, image, depth, kp, train=False, return_stats=False, trace=None, dropout=0.0):
     """cfg: an object / dict with the reference ModelConfig('cnn') attributes.  `trace` (dict) collects the output of
-    every ConvBnAct by state-dict prefix (layer-by-layer comparisons in the tests)."""
+    every ConvBnAct by state-dict prefix (layer-by-layer comparisons in the tests).  `dropout` > 0 (with train=True)
+    applies nn.Dropout after every hidden head layer like the reference's training mode (common.py:73-79); parity
+    runs keep it at 0."""
     g = (lambda k: cfg[k]) if isinstance(cfg, dict) else (lambda k: getattr(cfg, k))
     c = _Ctx(sd, train, g("activation"), trace)
     x = torch.cat([image, depth, heatmaps(kp, g("heatmap_size"), g("heatmap_sigma"))], 1)
@@ -172,8 +174,10 @@ def cnn_forward(sd, cfg, image, depth, kp, train=False, return_stats=False, trac
     x = c.eca(x, "global_features.2")
     x = x.mean((2, 3))
     n_lin = len(g("regression_dims"))
-    for i in range(n_lin):   # dropout is the identity here: parity runs use eval() / p = 0
+    for i in range(n_lin):   # dropout is the identity unless asked for: parity runs use eval() / p = 0
         x = _act(F.linear(x, sd[f"pose_head.decoder.{i}.0.weight"], sd[f"pose_head.decoder.{i}.0.bias"]), g("activation"))
+        if train and dropout > 0.0:
+            x = F.dropout(x, dropout, True)
     x = F.linear(x, sd[f"pose_head.decoder.{n_lin}.weight"], sd[f"pose_head.decoder.{n_lin}.bias"])
     out = x.view(-1, g("num_joints"), 3)
     return (out, c.new_stats) if return_stats else out
@@ -224,9 +228,19 @@ def _ln(x, sd, p, eps):
     return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], eps)
 
 
-def _mha(sd, p, q_in, kv_in, heads):
-    """nn.MultiheadAttention(batch_first=True) forward in eval mode (dropout off): packed in_proj, scaled
-    dot-product attention, out_proj.  The averaged attention weights the reference discards are not computed."""
+def _attend(q, k, v, hd, sdpa, attn_p):
+    if sdpa:
+        return F.scaled_dot_product_attention(q, k, v, dropout_p=attn_p)
+    a = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), -1)
+    if attn_p > 0.0:
+        a = F.dropout(a, attn_p, True)
+    return a @ v
+
+
+def _mha(sd, p, q_in, kv_in, heads, sdpa=False, attn_p=0.0):
+    """nn.MultiheadAttention(batch_first=True) forward: packed in_proj, scaled dot-product attention (dropout on the
+    probabilities when attn_p > 0), out_proj.  The averaged attention weights the reference discards are not
+    computed.  `sdpa` routes the core through F.scaled_dot_product_attention (fused flash kernels on a GPU)."""
     E = q_in.shape[-1]
     w, b = sd[p + ".in_proj_weight"], sd[p + ".in_proj_bias"]
     q = F.linear(q_in, w[:E], b[:E])
@@ -238,17 +252,21 @@ def _mha(sd, p, q_in, kv_in, heads):
     q = q.view(B, Nq, heads, hd).transpose(1, 2)
     k = k.view(B, Nk, heads, hd).transpose(1, 2)
     v = v.view(B, Nk, heads, hd).transpose(1, 2)
-    a = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), -1)
-    o = (a @ v).transpose(1, 2).reshape(B, Nq, E)
+    o = _attend(q, k, v, hd, sdpa, attn_p).transpose(1, 2).reshape(B, Nq, E)
     return F.linear(o, sd[p + ".out_proj.weight"], sd[p + ".out_proj.bias"])
 
 
-def _mlp2(sd, p, x, i0, i1):
-    return F.linear(F.gelu(F.linear(x, sd[f"{p}.{i0}.weight"], sd[f"{p}.{i0}.bias"])), sd[f"{p}.{i1}.weight"],
-                    sd[f"{p}.{i1}.bias"])
+def _drop(x, p):
+    return F.dropout(x, p, True) if p > 0.0 else x
 
 
-def vit_backbone_features(sd, p, x, heads=12, eps=1e-6):
+def _mlp2(sd, p, x, i0, i1, drop=0.0):
+    """Linear -> GELU -> Dropout -> Linear -> Dropout (transformers.py:66-72)."""
+    h = _drop(F.gelu(F.linear(x, sd[f"{p}.{i0}.weight"], sd[f"{p}.{i0}.bias"])), drop)
+    return _drop(F.linear(h, sd[f"{p}.{i1}.weight"], sd[f"{p}.{i1}.bias"]), drop)
+
+
+def vit_backbone_features(sd, p, x, heads=12, eps=1e-6, sdpa=False):
     """timm 1.0.15 VisionTransformer.forward_features for vit_base_patch16 (published algorithm; timm is not under
     /root/reference and not installed -- SURVEY.md 8c): conv patch embed -> [cls] + tokens + pos_embed -> pre-LN
     blocks (LayerNorm eps 1e-6, fused qkv Linear, 12 heads x 64, exact-erf GELU MLP) -> final LayerNorm."""
@@ -265,8 +283,7 @@ def vit_backbone_features(sd, p, x, heads=12, eps=1e-6):
         qkv = F.linear(h, sd[bp + ".attn.qkv.weight"], sd[bp + ".attn.qkv.bias"])
         B, N, _ = qkv.shape
         q, k, v = qkv.view(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
-        a = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), -1)
-        o = (a @ v).transpose(1, 2).reshape(B, N, E)
+        o = _attend(q, k, v, hd, sdpa, 0.0).transpose(1, 2).reshape(B, N, E)
         t = t + F.linear(o, sd[bp + ".attn.proj.weight"], sd[bp + ".attn.proj.bias"])
         h = _ln(t, sd, bp + ".norm2", eps)
         t = t + F.linear(F.gelu(F.linear(h, sd[bp + ".mlp.fc1.weight"], sd[bp + ".mlp.fc1.bias"])),
@@ -275,11 +292,16 @@ def vit_backbone_features(sd, p, x, heads=12, eps=1e-6):
     return _ln(t, sd, p + ".norm", eps)
 
 
-def vit_forward(sd, cfg, image, depth, kp):
-    """TransformerPoseEstimation.forward (reference: src/models/transformers.py:326-373) in eval mode."""
+def vit_forward(sd, cfg, image, depth, kp, train=False, sdpa=False):
+    """TransformerPoseEstimation.forward (reference: src/models/transformers.py:326-373).  Default: eval mode (every
+    dropout off).  train=True applies the reference's dropout sites with the config's rates (attention probabilities,
+    after each attention / MLP Linear, head) -- the timm backbone has none; `sdpa` uses the fused attention kernels."""
     g = (lambda k: cfg[k]) if isinstance(cfg, dict) else (lambda k: getattr(cfg, k))
     heads = g("transformer_heads")
-    tok = vit_backbone_features(sd, "vit_backbone", torch.cat([image, depth], 1))[:, 1:]   # drop the cls prefix token
+    dp = float(g("transformer_dropout_rate")) if train else 0.0
+    ap = float(g("transformer_attention_dropout_rate")) if train else 0.0
+    hp = float(g("regression_dropout")) if train else 0.0
+    tok = vit_backbone_features(sd, "vit_backbone", torch.cat([image, depth], 1), sdpa=sdpa)[:, 1:]   # drop the cls prefix token
     hm = heatmaps(kp, g("heatmap_size"), g("heatmap_sigma"))
     w = sd["heatmap_patch_embed.proj.weight"]
     hm_tok = F.conv2d(hm, w, sd["heatmap_patch_embed.proj.bias"], stride=w.shape[-1]).flatten(2).transpose(1, 2)
@@ -287,25 +309,37 @@ def vit_forward(sd, cfg, image, depth, kp):
     x_img, x_hm = tok, hm_tok
     for i in range(g("num_cross_modal_layers")):     # CrossModalFusionBlock, transformers.py:85-137 (LayerNorm eps 1e-5)
         p = f"cross_modal_fusion_layers.{i}"
-        x_img = x_img + _mha(sd, p + ".cross_attn_img_to_hm", _ln(x_img, sd, p + ".norm_img_q", 1e-5),
-                             _ln(x_hm, sd, p + ".norm_hm_kv", 1e-5), heads)
-        x_hm = x_hm + _mha(sd, p + ".cross_attn_hm_to_img", _ln(x_hm, sd, p + ".norm_hm_q", 1e-5),
-                           _ln(x_img, sd, p + ".norm_img_kv", 1e-5), heads)
-        x_img = x_img + _mlp2(sd, p + ".mlp_img", _ln(x_img, sd, p + ".norm_img_mlp", 1e-5), 0, 3)
-        x_hm = x_hm + _mlp2(sd, p + ".mlp_hm", _ln(x_hm, sd, p + ".norm_hm_mlp", 1e-5), 0, 3)
+        x_img = x_img + _drop(_mha(sd, p + ".cross_attn_img_to_hm", _ln(x_img, sd, p + ".norm_img_q", 1e-5),
+                                   _ln(x_hm, sd, p + ".norm_hm_kv", 1e-5), heads, sdpa, ap), dp)
+        x_hm = x_hm + _drop(_mha(sd, p + ".cross_attn_hm_to_img", _ln(x_hm, sd, p + ".norm_hm_q", 1e-5),
+                                 _ln(x_img, sd, p + ".norm_img_kv", 1e-5), heads, sdpa, ap), dp)
+        x_img = x_img + _mlp2(sd, p + ".mlp_img", _ln(x_img, sd, p + ".norm_img_mlp", 1e-5), 0, 3, dp)
+        x_hm = x_hm + _mlp2(sd, p + ".mlp_hm", _ln(x_hm, sd, p + ".norm_hm_mlp", 1e-5), 0, 3, dp)
     t = torch.cat([sd["final_cls_token"].expand(x_img.shape[0], -1, -1), x_img, x_hm], 1) + sd["final_pos_embed"]
     for i in range(g("final_encoder_depth")):        # TransformerEncoderBlock, transformers.py:49-82
         p = f"final_encoder.{i}"
         h = _ln(t, sd, p + ".norm1", 1e-5)
-        t = t + _mha(sd, p + ".attn", h, h, heads)
-        t = t + _mlp2(sd, p + ".mlp", _ln(t, sd, p + ".norm2", 1e-5), 0, 3)
+        t = t + _drop(_mha(sd, p + ".attn", h, h, heads, sdpa, ap), dp)
+        t = t + _mlp2(sd, p + ".mlp", _ln(t, sd, p + ".norm2", 1e-5), 0, 3, dp)
     x = _ln(t[:, 0], sd, "norm_out", 1e-5)
     dims = g("regression_hidden_dims")
     for i in range(len(dims)):                       # transformers.py:20-26: Linear at decoder.{0,3,6,..}
-        x = F.gelu(F.linear(x, sd[f"pose_head.decoder.{3 * i}.weight"], sd[f"pose_head.decoder.{3 * i}.bias"]))
+        x = _drop(F.gelu(F.linear(x, sd[f"pose_head.decoder.{3 * i}.weight"], sd[f"pose_head.decoder.{3 * i}.bias"])), hp)
     n = 3 * len(dims)
     x = F.linear(x, sd[f"pose_head.decoder.{n}.weight"], sd[f"pose_head.decoder.{n}.bias"])
     return x.view(-1, g("num_joints"), 3)
+
+
+def composite_loss(pred, gt, w_mse=1.0, w_l1=1.0, w_ij=100.0, w_root=1.0):
+    """ComprehensivePoseLoss.forward (reference: src/loss.py:57-85, weights config.py:15-18) in plain torch ops."""
+    d = pred - gt
+    J = pred.shape[1]
+    iu = torch.triu_indices(J, J, 1, device=pred.device)
+
+    def pd(t):
+        return torch.linalg.norm(t[:, :, None] - t[:, None], dim=-1)[:, iu[0], iu[1]]
+    return (w_mse * (d ** 2).mean() + w_l1 * d.abs().mean() + w_ij * (pd(pred) - pd(gt)).abs().mean()
+            + w_root * d[:, 0].abs().mean())
 
 
 def fill_vit_state_dict(sd, seed=0, out_scale_mm=300.0):
