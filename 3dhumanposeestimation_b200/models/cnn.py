@@ -252,7 +252,7 @@ def _fold_bn(conv_w, bn):
 class CnnInferencePlan:
     """Flat list of kernel launches for eval-mode CNNPoseEstimation.forward at a fixed batch size.
     Buffers are allocated once; folded bf16 weights are rebuilt whenever a parameter or buffer of the
-    model changes (optimizer steps and load_state_dict bump tensor versions)."""
+    model changes (in-place torch writes bump tensor versions; the fused AdamW bumps FlatParams.generation)."""
 
     def __init__(self, model: CNNPoseEstimation, B: int, device):
         self.model, self.B, self.dev = model, B, device
@@ -287,7 +287,10 @@ class CnnInferencePlan:
     def _param_version(self):
         if self._tracked is None:
             self._tracked = list(self.model.parameters()) + list(self.model.buffers())
-        return sum(t._version for t in self._tracked) + sum(t.data_ptr() & 0xFFFF for t in self._tracked[:4])
+        # pose_adamw_step writes through raw pointers (no _version bump): FlatParams.generation records those writes
+        ent = getattr(self._tracked[0], "_pose_flat", None)
+        gen = ent[0].generation if ent is not None else 0
+        return sum(t._version for t in self._tracked) + sum(t.data_ptr() & 0xFFFF for t in self._tracked[:4]) + gen
 
     def _epi(self, out, ldc, bias, act, out_scale=1.0, residual=None, ldr=0, res_scale=0.0, fp32=False, col_off=0):
         e = _lib.PoseGemmEpilogue()

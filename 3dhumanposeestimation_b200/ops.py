@@ -21,12 +21,15 @@ def to_bf16(x: torch.Tensor) -> torch.Tensor:
 
 
 def cached_bf16(param: torch.Tensor) -> torch.Tensor:
-    """bf16 shadow copy of an fp32 master parameter, refreshed when the parameter is updated in place
-    (optimizer steps bump ``_version``).  Master weights keep the reference's fp32 [out, in] layout."""
+    """bf16 shadow copy of an fp32 master parameter, refreshed when the parameter is updated in place: torch writes
+    bump ``_version``; the fused AdamW writes through raw pointers and bumps ``FlatParams.generation`` instead.
+    Master weights keep the reference's fp32 [out, in] layout."""
     key = id(param)
     ent = _bf16_cache.get(key)
-    if ent is None or ent[0] != param._version or ent[1] != param.data_ptr():
-        ent = (param._version, param.data_ptr(), to_bf16(param.detach().contiguous()))
+    flat = getattr(param, "_pose_flat", None)
+    version = param._version + (flat[0].generation if flat is not None else 0)
+    if ent is None or ent[0] != version or ent[1] != param.data_ptr():
+        ent = (version, param.data_ptr(), to_bf16(param.detach().contiguous()))
         _bf16_cache[key] = ent
     return ent[2]
 

@@ -20,7 +20,11 @@ class AdamW(torch.optim.Optimizer):
         if params and isinstance(params[0], dict):
             raise NotImplementedError("parameter groups: the fused AdamW updates one flat buffer with one setting "
                                       "(the reference uses a single group)")
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        # the remaining keys are torch.optim.AdamW's own defaults: a state_dict saved here loads into the reference's
+        # torch.optim.AdamW (main.py:130-134) and the other way round
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False,
+                                      maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                                      decoupled_weight_decay=True))
         self.grad_scale = grad_scale
         self._flat = None
         self._step = 0
@@ -52,7 +56,54 @@ class AdamW(torch.optim.Optimizer):
                                           _lib.stream_ptr())
         _lib.check(code, "pose_adamw_step")
         flat.mark_shadow_current()
+        flat.generation += 1          # the kernel wrote the parameters through raw pointers: _version did not move
         return loss
+
+    # ---- checkpointing: torch.optim.AdamW's per-parameter layout (src/train.py:300-306, main.py:130-134) ----------
+    def state_dict(self):
+        """``{"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [...]}`` exactly as torch.optim.AdamW
+        writes it: the flat moment buffers are scattered into per-parameter tensors (copies)."""
+        flat = self._resolve()
+        params = self.param_groups[0]["params"]
+        self.state.clear()
+        if self._step > 0:
+            for p, off in zip(flat.params, flat.offsets):
+                n = p.numel()
+                self.state[p] = {"step": torch.tensor(float(self._step), dtype=torch.float32),
+                                 "exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
+                                 "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).clone()}
+        assert len(params) == len(flat.params)
+        sd = super().state_dict()
+        self.state.clear()
+        return sd
+
+    def load_state_dict(self, state_dict):
+        """Accepts a state dict of torch.optim.AdamW (a reference checkpoint's ``optimizer_state_dict``) or of this
+        class: per-parameter moments are gathered into the flat buffers, the step count resumes bias correction."""
+        flat = self._resolve()
+        groups = state_dict.get("param_groups", [])
+        if len(groups) != 1:
+            raise ValueError("the fused AdamW holds one parameter group (as the reference does)")
+        g = groups[0]
+        if g.get("amsgrad", False) or g.get("maximize", False):
+            raise NotImplementedError("amsgrad / maximize are not implemented by the fused AdamW")
+        super().load_state_dict(state_dict)
+        steps = set()
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for p, off in zip(flat.params, flat.offsets):
+            st = self.state.get(p)
+            if not st:
+                continue
+            n = p.numel()
+            self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): one fused launch applies one bias "
+                             "correction")
+        self._step = steps.pop() if steps else 0
+        self.state.clear()
 
     def zero_grad(self, set_to_none=True):
         """step() already cleared the flat gradient buffer; without a preceding step, clear it here.  The views

@@ -48,6 +48,7 @@ class FlatParams:
                 self.index[id(p)] = off
         self.attach_grads()
         self._shadow_version = None
+        self.generation = 0     # bumped by every writer that bypasses torch (pose_adamw_step): caches key on it
         self.refresh_shadow()
 
     # ------------------------------------------------------------------------------------------------
@@ -117,7 +118,7 @@ class FlatParams:
 
     # shadow -----------------------------------------------------------------------------------------
     def version(self):
-        return sum(p._version for p in self.params)
+        return sum(p._version for p in self.params) + self.generation
 
     def refresh_shadow(self, force=False):
         """bf16 shadow <- fp32 master (one cast launch) whenever any parameter changed in place
