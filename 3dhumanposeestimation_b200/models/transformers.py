@@ -51,6 +51,13 @@ class PoseRegressionHead(nn.Module):  # transformers.py:7-31 (flat Sequential: d
     def linears(self):
         return [m for m in self.decoder if isinstance(m, nn.Linear)]
 
+    def forward(self, x):  # transformers.py:28-31 (standalone use; the model's plan runs the same GEMMs in its own buffers)
+        from ..ops import mlp_head_forward
+        drops = [m.p for m in self.decoder if isinstance(m, nn.Dropout)]
+        pose = mlp_head_forward(x.reshape(x.size(0), -1), self.linears(), self.activation,
+                                drops[0] if (self.training and drops) else 0.0)
+        return pose.view(-1, self.num_joints, 3)
+
 
 class PatchEmbedding(nn.Module):  # transformers.py:33-47
     def __init__(self, img_size_h, img_size_w, patch_size, in_chans, embed_dim):
@@ -217,7 +224,8 @@ class TransformerPoseEstimation(nn.Module):  # transformers.py:140-373
         plan = self.plan(image.shape[0], image.device)
         if self.training and torch.is_grad_enabled():
             return _VitTrainFn.apply(plan, image, depth, keypoints_2d, self.final_cls_token)
-        return plan.forward(image, depth, keypoints_2d, save=False).view(-1, self.config.num_joints, 3).clone()
+        return plan.forward(image, depth, keypoints_2d, save=False,
+                            training=self.training).view(-1, self.config.num_joints, 3).clone()
 
 
 class _VitTrainFn(torch.autograd.Function):
@@ -348,7 +356,8 @@ class VitPlan:
                   drop[0] if drop else 0.0, drop[1] if drop else 0)
         return o
 
-    def encoder_block(self, pre, x, T, norm1, wqkv, bqkv, wo, bo, norm2, fc1, fc2, heads, save, p_drop=0.0, p_attn=0.0):
+    def encoder_block(self, pre, x, T, norm1, wqkv, bqkv, wo, bo, norm2, fc1, fc2, heads, save, p_drop=0.0, p_attn=0.0,
+                      act=None):
         """pre-LN transformer block (timm Block and TransformerEncoderBlock, transformers.py:75-82); dropout on the
         attention weights, on the projected attention output, after the activation and after fc2 (transformers.py:61-72)."""
         M, E = self.B * T, self.E
@@ -359,7 +368,8 @@ class VitPlan:
                            drop=self.drop(pre + "attn", p_attn))
         x1 = self.linear(pre + "x1", o, M, wo, bo, residual=x, drop=self.drop(pre + "proj", p_drop))
         h2 = self.layernorm(pre + "h2", x1, norm2, M)
-        g = self.linear(pre + "g", h2, M, fc1.weight, fc1.bias, act=self.act, preact=save, drop=self.drop(pre + "act", p_drop))
+        g = self.linear(pre + "g", h2, M, fc1.weight, fc1.bias, act=self.act if act is None else act, preact=save,
+                        drop=self.drop(pre + "act", p_drop))
         if save:
             g = g[0]
         return self.linear(pre + "x2", g, M, fc2.weight, fc2.bias, residual=x1, drop=self.drop(pre + "fc2", p_drop))
@@ -397,7 +407,7 @@ class VitPlan:
         x_hm2 = self.mlp_residual(pre + "mh.", x_hm1, Mh, blk.norm_hm_mlp, blk.mlp_hm, save)
         return x_img2, x_hm2
 
-    def forward(self, image, depth, kp, save):
+    def forward(self, image, depth, kp, save, training=None):
         self._sp = _lib.stream_ptr()
         m, B, E = self.model, self.B, self.E
         c = m.config
@@ -408,8 +418,10 @@ class VitPlan:
                 tuple(kp.shape) != (B, self.J, 2) or c.image_in_channels != 4:
             raise ValueError(f"expected image [{B},3,{self.H},{self.W}], depth [{B},1,{self.H},{self.W}], "
                              f"keypoints [{B},{self.J},2]")
-        self.training = bool(save)
-        if save:
+        # dropout follows the module's mode (the reference applies it in train mode with or without autograd);
+        # `save` only decides whether the backward's operands are kept
+        self.training = bool(save) if training is None else bool(training)
+        if self.training:
             self.step_count += 1
         self.flat.refresh_shadow()
         self.launches = 0
@@ -426,7 +438,7 @@ class VitPlan:
         for i, blk in enumerate(bb.blocks):
             x = self.encoder_block(f"bb{i}.", x, Ti + 1, blk.norm1, blk.attn.qkv.weight, blk.attn.qkv.bias,
                                    blk.attn.proj.weight, blk.attn.proj.bias, blk.norm2, blk.mlp.fc1, blk.mlp.fc2,
-                                   bb.num_heads, save)
+                                   bb.num_heads, save, act=3)   # timm's Mlp is exact GELU whatever config.activation says
         self.bb_out = x
         # final norm of the patch tokens only: the prefix (cls) token is dropped (transformers.py:336-346)
         x_img = self.layernorm("x_img", x, bb.norm, B * Ti, rows=Ti, in_group=Ti + 1, in_off=1)

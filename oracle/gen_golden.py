@@ -426,11 +426,46 @@ def gen_metrics():
                         pa_mpjpe=np.float32(utils.compute_pa_mpjpe(tp, tg).item()), pa_per_sample=per)
 
 
+COLLATE_CASES = ([(20, 20), (31, 31), (26, 26), (23, 25)], [(16, 12)], [(8, 8), (8, 8)])
+
+
+def collate_batch(sizes, seed):
+    """The seeded sample list both this script and tests/test_gpu_parity.py build (CPU tensors)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    batch = []
+    for i, (h, w) in enumerate(sizes):
+        batch.append({"image": torch.rand(3, h, w, generator=g), "depth": torch.rand(1, h, w, generator=g),
+                      "keypoints_2d": torch.rand(17, 2, generator=g), "joints_3d": torch.randn(17, 3, generator=g),
+                      "camera_params": {"f": [1.0 + i, 1.0]}, "image_path": f"p{i}", "action": "a", "subaction": i % 2 + 1,
+                      "image_size": torch.tensor([h, w]), "frame_idx": i})
+    return batch
+
+
+def gen_collate():
+    """Human36MCollator of the live reference (src/dataset/collator.py:10-61) on ragged, single-sample and equal-size
+    batches: padded images / depths, stacked key-points / joints / sizes and the padding field."""
+    from dataset.collator import Human36MCollator
+    col = Human36MCollator()
+    out = {"versions": versions(), "n_cases": np.int32(len(COLLATE_CASES))}
+    for c, sizes in enumerate(COLLATE_CASES):
+        r = col(collate_batch(sizes, 900 + c))
+        out[f"c{c}_sizes"] = np.array(sizes, np.int32)
+        out[f"c{c}_image"] = r["image"].numpy()
+        out[f"c{c}_depth"] = r["depth"].numpy()
+        out[f"c{c}_keypoints_2d"] = r["keypoints_2d"].numpy()
+        out[f"c{c}_joints_3d"] = r["joints_3d"].numpy()
+        out[f"c{c}_image_size"] = r["image_size"].numpy()
+        out[f"c{c}_padding"] = np.array(r["padding"], np.int32)
+        out[f"c{c}_lists"] = json.dumps({k: r[k] for k in ("camera_params", "image_path", "action", "subaction", "frame_idx")})
+    np.savez_compressed(os.path.join(OUT, "collate.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, os.path.join(REF, "src"))
     os.chdir(tempfile.mkdtemp(prefix="pose_golden_"))
-    which = sys.argv[1:] or ["augment", "heatmap", "loss", "config", "cnn", "vit", "cnn_train", "metrics"]
+    which = sys.argv[1:] or ["augment", "heatmap", "loss", "config", "cnn", "vit", "cnn_train", "metrics", "collate"]
     for w in which:
         globals()["gen_" + w]()
         print("wrote", w)

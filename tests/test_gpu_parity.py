@@ -380,6 +380,65 @@ def test_regression_head_matches_fp32_reference(pose):
         assert err < 3e-2 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("flavour", ["common", "transformers"])
+def test_regression_head_training_mode_autograd_and_dropout(pose, flavour):
+    """Standalone PoseRegressionHead in training mode (common.py:69-89 / transformers.py:7-31): dropout + autograd through
+    the module itself.  The counter-based mask is exposed through pose_dropout_bf16 (same seed, tensor of ones), so the
+    fused forward / backward can be compared with plain fp32 PyTorch using that very mask.  Tolerance: bf16 operands."""
+    import importlib
+    ops = importlib.import_module("3dhumanposeestimation_b200.ops")
+    lib = pose._lib.lib()
+    torch.manual_seed(3)
+    if flavour == "common":
+        head = pose.PoseRegressionHead(1024, 17, hidden_dims=[1024, 512], dropout=0.2, activation="silu").to(DEV).train()
+        lins = [m[0] if isinstance(m, torch.nn.Sequential) else m for m in head.decoder]
+        p, act = 0.2, torch.nn.functional.silu
+    else:
+        tf = importlib.import_module("3dhumanposeestimation_b200.models.transformers")
+        head = tf.PoseRegressionHead(768, 17, hidden_dims=[1024, 512, 256], dropout=0.25, activation="gelu").to(DEV).train()
+        lins = head.linears()
+        p, act = 0.25, torch.nn.functional.gelu
+    B = 192
+    x = torch.randn(B, lins[0].in_features, device=DEV, requires_grad=True)
+    seed = ((torch.initial_seed() & 0xFFFFFFFF) << 20) + (ops._head_calls[0] + 1) * 16     # the seed the call will draw
+    out = head(x)
+    assert out.shape == (B, 17, 3) and out.dtype == torch.float32 and out.requires_grad
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    got = {"x": x.grad.clone()}
+    for i, lin in enumerate(lins):
+        got[f"w{i}"], got[f"b{i}"] = lin.weight.grad.clone(), lin.bias.grad.clone()
+        lin.weight.grad = lin.bias.grad = None
+    # plain PyTorch with the same masks
+    xr = x.detach().clone().requires_grad_()
+    h = xr
+    for i, lin in enumerate(lins):
+        h = torch.nn.functional.linear(h, lin.weight, lin.bias)
+        if i < len(lins) - 1:
+            ones = torch.ones(B, lin.out_features, device=DEV, dtype=torch.bfloat16)
+            mask = torch.empty_like(ones)
+            rc = lib.pose_dropout_bf16(ones.data_ptr(), ones.numel(), p, seed + i, mask.data_ptr(), pose._lib.stream_ptr())
+            assert rc == 0
+            keep = (mask != 0).float()
+            assert abs(keep.mean().item() - (1 - p)) < 0.02
+            h = act(h) * keep / (1 - p)
+    ref = h.view(B, 17, 3)
+    (ref * w).sum().backward()
+    assert (out - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item())
+
+    def rel(a, b):
+        return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+    assert rel(got["x"], xr.grad) < 2e-2, rel(got["x"], xr.grad)
+    for i, lin in enumerate(lins):
+        assert rel(got[f"w{i}"], lin.weight.grad) < 2e-2, (i, rel(got[f"w{i}"], lin.weight.grad))
+        assert rel(got[f"b{i}"], lin.bias.grad) < 2e-2, (i, rel(got[f"b{i}"], lin.bias.grad))
+    # eval mode: no dropout, deterministic, no autograd graph needed
+    head.eval()
+    with torch.no_grad():
+        a, b = head(x.detach()), head(x.detach())
+    assert torch.equal(a, b)
+
+
 def test_eval_metrics_match_the_reference(pose, oracle, golden):
     """MPJPE / PA-MPJPE on the device (one thread per sample, closed-form 3x3 SVD) vs the live reference's values and the
     C oracle, incl. the reflection, similarity-transform, identical-pose and collapsed-prediction cases; 1e-3 relative."""
@@ -441,36 +500,45 @@ def test_run_inference_mirrors_the_reference_call(pose):
         assert np.array_equal(out, m(img, dep, kp)[0].float().cpu().numpy())
 
 
-def _ref_collate(batch):
-    """src/dataset/collator.py:20-61 restated with the same torch calls (F.pad right / bottom, torch.stack)."""
-    mh = max(s["image"].shape[1] for s in batch)
-    mw = max(s["image"].shape[2] for s in batch)
-    pad = lambda t: torch.nn.functional.pad(t, (0, mw - t.shape[2], 0, mh - t.shape[1]))   # noqa: E731
-    return torch.stack([pad(s["image"]) for s in batch]), torch.stack([pad(s["depth"]) for s in batch]), (mh, mw)
+def _collate_batch(sizes, seed):
+    """The seeded sample list oracle/gen_golden.py::collate_batch fed to the live reference collator."""
+    g = torch.Generator().manual_seed(seed)
+    batch = []
+    for i, (h, w) in enumerate(sizes):
+        batch.append({"image": torch.rand(3, h, w, generator=g), "depth": torch.rand(1, h, w, generator=g),
+                      "keypoints_2d": torch.rand(17, 2, generator=g), "joints_3d": torch.randn(17, 3, generator=g),
+                      "camera_params": {"f": [1.0 + i, 1.0]}, "image_path": f"p{i}", "action": "a", "subaction": i % 2 + 1,
+                      "image_size": torch.tensor([h, w]), "frame_idx": i})
+    return batch
 
 
-def test_collator_matches_the_reference_padding(pose):
-    """Human36MCollator on the device, bit-exact (ragged sizes, a single sample, equal sizes)."""
+def test_collator_matches_the_live_reference_golden(pose, golden):
+    """Human36MCollator on the device against the LIVE reference collator's outputs
+    (src/dataset/collator.py:10-61, frozen by oracle/gen_golden.py::gen_collate): ragged sizes, a single sample, equal
+    sizes -- every field of the result dictionary, bit-exact."""
     import importlib
     col = importlib.import_module("3dhumanposeestimation_b200.dataset.collator").Human36MCollator()
-    g = torch.Generator().manual_seed(9)
-    for sizes in ([(204, 204), (307, 307), (256, 256), (230, 251)], [(64, 48)], [(32, 32), (32, 32)]):
-        batch = []
-        for i, (h, w) in enumerate(sizes):
-            batch.append({"image": torch.rand(3, h, w, generator=g).to(DEV), "depth": torch.rand(1, h, w, generator=g).to(DEV),
-                          "keypoints_2d": torch.rand(17, 2, generator=g).to(DEV), "joints_3d": torch.randn(17, 3, generator=g).to(DEV),
-                          "camera_params": {"f": [1.0, 1.0]}, "image_path": f"p{i}", "action": "a", "subaction": 1,
-                          "image_size": torch.tensor([h, w]), "frame_idx": i})
+    gold = golden("collate.npz")
+    for c in range(int(gold["n_cases"])):
+        sizes = [tuple(int(v) for v in row) for row in gold[f"c{c}_sizes"]]
+        batch = [{k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in smp.items()}
+                 for smp in _collate_batch(sizes, 900 + c)]
         out = col(batch)
-        img, dep, pad = _ref_collate(batch)
-        assert torch.equal(out["image"], img) and torch.equal(out["depth"], dep)
-        assert out["padding"] == [pad] * len(sizes) and out["image_path"] == [f"p{i}" for i in range(len(sizes))]
-        assert out["keypoints_2d"].shape == (len(sizes), 17, 2) and out["image_size"].shape == (len(sizes), 2)
-        # the dataset's depth rescale (chunked_dataset.py:159-164) fused into the same launch
+        for key in ("image", "depth", "keypoints_2d", "joints_3d", "image_size"):
+            want = gold[f"c{c}_{key}"]
+            got = out[key].cpu().numpy()
+            assert got.shape == want.shape and got.dtype == want.dtype, (c, key, got.shape, got.dtype)
+            assert np.array_equal(got, want), (c, key)
+        assert [tuple(p) for p in out["padding"]] == [tuple(int(v) for v in row) for row in gold[f"c{c}_padding"]]
+        lists = json.loads(str(gold[f"c{c}_lists"]))
+        for key, want in lists.items():
+            assert out[key] == want, (c, key)
+        # the dataset's depth rescale (chunked_dataset.py:159-164) fused into the same launch: same torch ops as the reference
         rng = [(0.5 * i, 0.5 * i + 3.0) for i in range(len(sizes))]
         out2 = col(batch, depth_range=rng)
-        want = torch.stack([torch.nn.functional.pad(s["depth"] * (hi - lo) + lo, (0, pad[1] - s["depth"].shape[2], 0, pad[0] - s["depth"].shape[1]))
-                            for s, (lo, hi) in zip(batch, rng)])
+        mh, mw = out["padding"][0]
+        want = torch.stack([torch.nn.functional.pad(smp["depth"] * (hi - lo) + lo, (0, mw - smp["depth"].shape[2], 0, mh - smp["depth"].shape[1]))
+                            for smp, (lo, hi) in zip(batch, rng)])
         assert torch.equal(out2["depth"], want)
     with pytest.raises(Exception):
         col([{**batch[0], "image": batch[0]["image"].cpu()}])          # CPU tensors: no fallback

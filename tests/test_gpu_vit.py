@@ -210,6 +210,71 @@ def test_fused_adamw_matches_torch(pose):
             assert (p.grad == 0).all()                                             # and the gradient cleared
 
 
+def test_optimizer_state_round_trip_with_torch_adamw(pose, tmp_path):
+    """optimizer_state_dict of the reference's checkpoints (src/train.py:300-306, main.py:130-134): the fused AdamW saves
+    torch.optim.AdamW's per-parameter layout and loads it back.  (i) save -> load into a fresh fused optimizer -> the
+    continued run is bit-identical to the uninterrupted one; (ii) the saved dict loads into torch.optim.AdamW and that
+    continues the same trajectory; (iii) a state dict written by torch.optim.AdamW resumes the fused optimizer."""
+    g = torch.Generator().manual_seed(21)
+    shapes = [(300, 17), (51,), (64, 64, 3)]
+    init = [torch.randn(s, generator=g) for s in shapes]
+    grads = [[torch.randn(s, generator=g) for s in shapes] for _ in range(6)]
+
+    def fresh(kind):
+        ps = [torch.nn.Parameter(t.clone().to(DEV)) for t in init]
+        opt = (pose.AdamW if kind == "fused" else torch.optim.AdamW)(ps, lr=1e-2, weight_decay=0.05)
+        return ps, opt
+
+    def run(ps, opt, steps):
+        for k in steps:
+            for p, gr in zip(ps, grads[k]):
+                if p.grad is None:
+                    p.grad = gr.clone().to(DEV)
+                else:
+                    p.grad.copy_(gr.to(DEV))
+            opt.step()
+
+    # uninterrupted reference trajectories
+    ps_a, opt_a = fresh("fused")
+    pose.params.FlatParams.of(ps_a)
+    run(ps_a, opt_a, range(6))
+    # (i) fused -> file -> fused
+    ps_b, opt_b = fresh("fused")
+    pose.params.FlatParams.of(ps_b)
+    run(ps_b, opt_b, range(3))
+    sd = opt_b.state_dict()
+    assert set(sd) == {"state", "param_groups"} and sorted(sd["state"]) == [0, 1, 2]
+    assert all(set(v) == {"step", "exp_avg", "exp_avg_sq"} and float(v["step"]) == 3.0 for v in sd["state"].values())
+    assert [tuple(sd["state"][i]["exp_avg"].shape) for i in range(3)] == shapes
+    path = tmp_path / "opt.pth"
+    torch.save({"optimizer_state_dict": sd, "params": [p.detach().cpu() for p in ps_b]}, path)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    ps_c = [torch.nn.Parameter(t.clone().to(DEV)) for t in ck["params"]]
+    opt_c = pose.AdamW(ps_c, lr=1e-2, weight_decay=0.05)
+    pose.params.FlatParams.of(ps_c)
+    opt_c.load_state_dict(ck["optimizer_state_dict"])
+    run(ps_c, opt_c, range(3, 6))
+    for a, c in zip(ps_a, ps_c):
+        assert torch.equal(a, c)
+    # (ii) fused -> torch.optim.AdamW
+    ps_t = [torch.nn.Parameter(t.clone().to(DEV)) for t in ck["params"]]
+    opt_t = torch.optim.AdamW(ps_t, lr=1e-2, weight_decay=0.05)
+    opt_t.load_state_dict(ck["optimizer_state_dict"])
+    run(ps_t, opt_t, range(3, 6))
+    for a, t in zip(ps_a, ps_t):
+        assert torch.allclose(a, t, rtol=1e-5, atol=1e-6)
+    # (iii) torch.optim.AdamW -> fused
+    ps_r, opt_r = fresh("torch")
+    run(ps_r, opt_r, range(3))
+    ps_f = [torch.nn.Parameter(p.detach().clone()) for p in ps_r]
+    opt_f = pose.AdamW(ps_f, lr=1e-2, weight_decay=0.05)
+    pose.params.FlatParams.of(ps_f)
+    opt_f.load_state_dict(opt_r.state_dict())
+    run(ps_f, opt_f, range(3, 6))
+    for a, f in zip(ps_a, ps_f):
+        assert torch.allclose(a, f, rtol=1e-5, atol=1e-6)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def _model(pose, **kw):
     cfg = pose.ModelConfig("transformer", image_size=(256, 256), vit_pretrained=False, **kw)
