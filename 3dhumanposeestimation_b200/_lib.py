@@ -15,13 +15,22 @@ LIB_PATH = os.environ.get("POSE_B200_LIB") or os.path.join(_HERE, "libpose_b200.
 c_int, c_float, c_size_t, c_void_p = C.c_int, C.c_float, C.c_size_t, C.c_void_p
 
 
+class PoseBnFuse(C.Structure):
+    """Mirror of `pose_bn_fuse` in include/pose_b200.h."""
+
+    _fields_ = [("partials", C.c_void_p), ("cap_floats", C.c_int64), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("eps", C.c_float), ("momentum", C.c_float), ("count", C.c_int64), ("mean_rstd", C.c_void_p),
+                ("scale_shift", C.c_void_p), ("running_mean", C.c_void_p), ("running_var", C.c_void_p)]
+
+
 class PoseGemmEpilogue(C.Structure):
     """Mirror of `pose_gemm_epilogue` in include/pose_b200.h."""
 
     _fields_ = [("bias", C.c_void_p), ("residual", C.c_void_p), ("C", C.c_void_p), ("ldc", C.c_int32),
                 ("ldr", C.c_int32), ("act", C.c_int32), ("out_dtype", C.c_int32), ("out_scale", C.c_float),
                 ("res_scale", C.c_float), ("preact", C.c_void_p), ("accumulate", C.c_int32), ("reserved", C.c_int32),
-                ("drop_seed", C.c_uint64), ("drop_p", C.c_float), ("reserved2", C.c_int32)]
+                ("drop_seed", C.c_uint64), ("drop_p", C.c_float), ("reserved2", C.c_int32),
+                ("bn", C.POINTER(PoseBnFuse))]
 
 
 class PoseRepackEntry(C.Structure):

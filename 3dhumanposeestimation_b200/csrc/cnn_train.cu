@@ -904,6 +904,14 @@ repack_kernel(const RepackEntry *__restrict__ table, const float *__restrict__ s
     }
 }
 
+int launch_bn_finalize_parts(const float *partials, int parts, long count, const float *gamma, const float *beta, float eps,
+                             float momentum, int C, float *mean_rstd, float *scale_shift, float *running_mean,
+                             float *running_var, cudaStream_t stream) {
+    bn_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(partials, parts, (float)count, gamma, beta, eps, momentum, C, mean_rstd,
+                                                         scale_shift, running_mean, running_var);
+    return launch_status();
+}
+
 }  // namespace pose
 
 using namespace pose;

@@ -16,6 +16,12 @@ inline int launch_status() {
     return e == cudaSuccess ? POSE_OK : (int)e;
 }
 
+// cnn_train.cu: second stage of the BatchNorm statistics (fold of [parts, 2, C] partials -> mean / rstd, scale / shift,
+// running statistics); also launched by the GEMM / convolution when the statistics come out of its epilogue (pose_bn_fuse)
+int launch_bn_finalize_parts(const float *partials, int parts, long count, const float *gamma, const float *beta, float eps,
+                             float momentum, int C, float *mean_rstd, float *scale_shift, float *running_mean,
+                             float *running_var, cudaStream_t stream);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -57,15 +57,21 @@ struct Epilogue {
     uint32_t drop_thresh;            // dropout after the activation (before the residual): keep iff hash >= thresh
     float drop_scale;                // 1 / (1 - p)
     DropSeed drop_seed;              // element index = row * ldc + col (common.cuh: drop_keep)
+    float *stats;                    // [parts, 2, N] fp32 or null: per-CTA column sums / sums of squares of the fp32 result
+                                     // (training-mode BatchNorm statistics taken from the accumulators, fixed order)
+    const pose_bn_fuse *bn;          // host side only: the fold launched behind the kernel
 };
 
 struct ConvGeom {          // MODE 1 only
     int Ho, Wo;            // output height / width
-    int TH, TW, TN;        // output patch of one M tile: TN images x TH x TW pixels (= 128), Ho % TH == 0, Wo % TW == 0
+    int TH, TW, TN;        // output patch of one M tile: TN images x TH x TW pixels (= 128); edge patches may be ragged (rows
+                           // past Ho / Wo are loaded as whatever the TMA box covers -- zeros outside the tensor -- and masked
+                           // in the epilogue; in the weight gradient their dY is the TMA zero fill)
     int Nimg;
     int KW, taps;          // filter width, KH * KW
     int stride, dil, pad;
     int cchunks;           // Cin_pad / BKC
+    int tiles_w, tiles_h;  // ceil(Wo / TW), ceil(Ho / TH)
 };
 
 template <int BN, int kStages, int BKC, int TMA_EPI = 0>
@@ -211,8 +217,9 @@ __device__ __forceinline__ void red_add_f4(float *p, float4 v) {
 // stays small (a run-time switch per element made the unrolled epilogue overflow the instruction cache).
 template <int ACT, int kPitch>
 __device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, long row, int lane, int col,
-                                              int N) {
+                                              int N, uint32_t wstat) {
     const int sub_r = lane >> 3, colq = (lane & 7) * 4;
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);   // column statistics (ACT 0 only)
     float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ep.bias != nullptr) bz = __ldg((const float4 *)(ep.bias + col));
 #pragma unroll
@@ -266,6 +273,10 @@ __device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, 
                 x.z += f1.x * ep.res_scale; x.w += f1.y * ep.res_scale;
             }
         }
+        if (ACT == 0 && ep.stats != nullptr) {
+            s1.x += x.x; s1.y += x.y; s1.z += x.z; s1.w += x.w;
+            s2.x = fmaf(x.x, x.x, s2.x); s2.y = fmaf(x.y, x.y, s2.y); s2.z = fmaf(x.z, x.z, s2.z); s2.w = fmaf(x.w, x.w, s2.w);
+        }
         if (ep.accumulate) {
             red_add_f4((float *)ep.C + grow * ep.ldc + col, x);
         } else if (ep.out_bf16) {
@@ -273,6 +284,20 @@ __device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, 
             *(uint2 *)((__nv_bfloat16 *)ep.C + grow * ep.ldc + col) = make_uint2(*(uint32_t *)&p0, *(uint32_t *)&p1);
         } else {
             *(float4 *)((float *)ep.C + grow * ep.ldc + col) = x;
+        }
+    }
+    if (ACT == 0 && ep.stats != nullptr) {
+        // fold the four row groups of the warp (lanes l, l + 8, l + 16, l + 24 own the same columns) in a fixed order and add
+        // the chunk's 32-row column sums to the warp's private running totals in shared memory
+#define FOLD_(v_) v_ += __shfl_xor_sync(0xffffffffu, v_, 8); v_ += __shfl_xor_sync(0xffffffffu, v_, 16);
+        FOLD_(s1.x) FOLD_(s1.y) FOLD_(s1.z) FOLD_(s1.w) FOLD_(s2.x) FOLD_(s2.y) FOLD_(s2.z) FOLD_(s2.w)
+#undef FOLD_
+        if (lane < 8) {
+            const float4 t1 = lds128(wstat + colq * 4), t2 = lds128(wstat + 128 + colq * 4);
+            sts128(wstat + colq * 4, __float_as_uint(t1.x + s1.x), __float_as_uint(t1.y + s1.y), __float_as_uint(t1.z + s1.z),
+                   __float_as_uint(t1.w + s1.w));
+            sts128(wstat + 128 + colq * 4, __float_as_uint(t2.x + s2.x), __float_as_uint(t2.y + s2.y), __float_as_uint(t2.z + s2.z),
+                   __float_as_uint(t2.w + s2.w));
         }
     }
 }
@@ -505,7 +530,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BN;
                 int img = 0, oh0 = 0, ow0 = 0;
                 if (MODE == 1) {
-                    const int tiles_w = cg.Wo / cg.TW, tiles_h = cg.Ho / cg.TH;
+                    const int tiles_w = cg.tiles_w, tiles_h = cg.tiles_h;
                     int t = mt;
                     const int tw = t % tiles_w;
                     t /= tiles_w;
@@ -524,7 +549,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         // convolution weight gradient: the contraction block is a patch of 64 OUTPUT PIXELS; A = dY^T
                         // (two boxes of 64 output channels), B = the input activation at one filter tap per 64-column
                         // block (4-D boxes, zero fill outside the image = the convolution padding)
-                        const int tiles_w = cg.Wo / cg.TW, tiles_h = cg.Ho / cg.TH;
+                        const int tiles_w = cg.tiles_w, tiles_h = cg.tiles_h;
                         int t = kb;
                         const int tw = t % tiles_w;
                         t /= tiles_w;
@@ -608,6 +633,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint32_t stg = smem_u32(staging + (warp - 2) * S::kWarpStaging);
         const int colq = (lane & 7) * 4;  // phase-2 mapping: 8 lanes per row, 4 columns per lane
         uint32_t tile_iter = 0, aux_phase = 0;
+        // column statistics (ep.stats): the warp's running totals live behind its transpose buffer (2 chunks x 2 x 32 fp32);
+        // the host sizes the grid as a multiple of n_tiles, so every tile of this CTA covers the same columns
+        const uint32_t wstat0 = stg + 32 * S::kStagePitch;
+        if (TMA_EPI == 0 && ep.stats != nullptr) {
+            sts128(wstat0 + lane * 16, 0u, 0u, 0u, 0u);
+            __syncwarp();
+        }
         for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++tile_iter) {
             const int tile = item % mn_tiles;
             const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
@@ -659,7 +691,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 row = (long)mt * BM + r;
                 if (row >= M) row = -1;
             } else {
-                const int tiles_w = cg.Wo / cg.TW, tiles_h = cg.Ho / cg.TH;
+                const int tiles_w = cg.tiles_w, tiles_h = cg.tiles_h;
                 int t = mt;
                 const int tw = t % tiles_w;
                 t /= tiles_w;
@@ -669,7 +701,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int dn = r / per_img, rr = r - dn * per_img;
                 const int dh = rr / cg.TW, dw = rr - dh * cg.TW;
                 row = ((long)(img + dn) * cg.Ho + th * cg.TH + dh) * cg.Wo + tw * cg.TW + dw;
-                if (img + dn >= cg.Nimg) row = -1;
+                if (img + dn >= cg.Nimg || th * cg.TH + dh >= cg.Ho || tw * cg.TW + dw >= cg.Wo) row = -1;
             }
             mbar_wait(acc_full + as, aph);
             tc_fence_after();
@@ -699,18 +731,33 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const bool fast = ep.vec && col0 + 32 <= N;   // warp-uniform
                 if (!fast) epilogue_rows_slow<S::kStagePitch>(stg, ep, row, lane, col, N);
                 else switch (ep.act) {
-                    case 0: epilogue_rows<0, S::kStagePitch>(stg, ep, row, lane, col, N); break;
-                    case 1: epilogue_rows<1, S::kStagePitch>(stg, ep, row, lane, col, N); break;
-                    case 2: epilogue_rows<2, S::kStagePitch>(stg, ep, row, lane, col, N); break;
-                    case 3: epilogue_rows<3, S::kStagePitch>(stg, ep, row, lane, col, N); break;
-                    case 4: epilogue_rows<4, S::kStagePitch>(stg, ep, row, lane, col, N); break;
-                    case 5: epilogue_rows<5, S::kStagePitch>(stg, ep, row, lane, col, N); break;
-                    case 6: epilogue_rows<6, S::kStagePitch>(stg, ep, row, lane, col, N); break;
-                    default: epilogue_rows<7, S::kStagePitch>(stg, ep, row, lane, col, N); break;
+                    case 0: epilogue_rows<0, S::kStagePitch>(stg, ep, row, lane, col, N, wstat0 + ci * 256); break;
+                    case 1: epilogue_rows<1, S::kStagePitch>(stg, ep, row, lane, col, N, wstat0 + ci * 256); break;
+                    case 2: epilogue_rows<2, S::kStagePitch>(stg, ep, row, lane, col, N, wstat0 + ci * 256); break;
+                    case 3: epilogue_rows<3, S::kStagePitch>(stg, ep, row, lane, col, N, wstat0 + ci * 256); break;
+                    case 4: epilogue_rows<4, S::kStagePitch>(stg, ep, row, lane, col, N, wstat0 + ci * 256); break;
+                    case 5: epilogue_rows<5, S::kStagePitch>(stg, ep, row, lane, col, N, wstat0 + ci * 256); break;
+                    case 6: epilogue_rows<6, S::kStagePitch>(stg, ep, row, lane, col, N, wstat0 + ci * 256); break;
+                    default: epilogue_rows<7, S::kStagePitch>(stg, ep, row, lane, col, N, wstat0 + ci * 256); break;
                 }
                 __syncwarp();   // staging is rewritten by the next chunk
             }
             }   // !TMA_EPI
+        }
+        if (TMA_EPI == 0 && ep.stats != nullptr) {
+            // partial row (blockIdx / n_tiles) * 4 + quarter of [parts, 2, N]: every (row, column) has exactly one writer
+            __syncwarp();
+            const int n0 = (blockIdx.x % n_tiles) * BN;
+            float *dst = ep.stats + (long)((blockIdx.x / n_tiles) * 4 + quarter) * 2 * N;
+#pragma unroll
+            for (int ci = 0; ci < (BN / 32 + 3) / 4; ++ci) {
+                const int c = cgrp + 4 * ci;
+                const int col0 = n0 + c * 32;
+                if (c < BN / 32 && col0 < N) {
+                    dst[col0 + lane] = lds32(wstat0 + ci * 256 + lane * 4);
+                    dst[N + col0 + lane] = lds32(wstat0 + ci * 256 + 128 + lane * 4);
+                }
+            }
         }
     }
     if (TMA_EPI != 0 && warp >= 2 && lane == 0) tma_store_wait_all();      // bulk stores of this thread have completed
@@ -821,7 +868,20 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
     const int kb_per = (num_kb + k_splits - 1) / k_splits;
     k_splits = (num_kb + kb_per - 1) / kb_per;            // no empty split
     const long total = (long)m_tiles * n_tiles * k_splits;
-    const int grid = (int)(total < kNumSMs ? total : kNumSMs);
+    int grid = (int)(total < kNumSMs ? total : kNumSMs);
+    if (ep.stats != nullptr) {
+        // column statistics: every CTA must see ONE column tile (grid a multiple of n_tiles; tiles are N-fastest)
+        if (ep.tma || k_splits != 1 || n_tiles > grid || N % 32) return POSE_E_UNSUPPORTED;
+        grid = grid / n_tiles * n_tiles;
+        const int parts = grid / n_tiles * 4;
+        if (ep.bn->cap_floats < (int64_t)parts * 2 * N) return POSE_E_WORKSPACE;
+        kern<<<grid, kGemmThreadsP, smem_bytes, s>>>(ma, mw, mc, maux, mpre, M, N, K, ep, cg, m_tiles, n_tiles, kb_per, k_splits);
+        int e = launch_status();
+        if (e) return e;
+        const pose_bn_fuse *bn = ep.bn;
+        return launch_bn_finalize_parts(bn->partials, parts, (long)bn->count, bn->gamma, bn->beta, bn->eps, bn->momentum, N,
+                                        bn->mean_rstd, bn->scale_shift, bn->running_mean, bn->running_var, s);
+    }
     kern<<<grid, kGemmThreadsP, smem_bytes, s>>>(ma, mw, mc, maux, mpre, M, N, K, ep, cg, m_tiles, n_tiles, kb_per, k_splits);
     return launch_status();
 }
@@ -888,6 +948,17 @@ static int check_epilogue(const pose_gemm_epilogue *e, long M, int N, Epilogue &
     ep.drop_thresh = e->drop_p > 0.f ? drop_threshold(e->drop_p) : 0u;
     ep.drop_scale = e->drop_p > 0.f ? 1.0f / (1.0f - e->drop_p) : 1.0f;
     ep.drop_seed = make_drop_seed(e->drop_seed);
+    ep.stats = nullptr;
+    ep.bn = e->bn;
+    if (e->bn != nullptr) {
+        const pose_bn_fuse *bn = e->bn;
+        if (!bn->partials || !bn->gamma || !bn->beta || !bn->mean_rstd || !bn->scale_shift) return POSE_E_NULL;
+        if (bn->count <= 0) return POSE_E_SHAPE;
+        // statistics of the raw contraction (+ bias): no activation, residual, dropout or accumulation in the same epilogue
+        if (e->act != 0 || e->residual || e->accumulate || e->preact || e->drop_p > 0.f || !ep.vec || N % 32)
+            return POSE_E_UNSUPPORTED;
+        ep.stats = bn->partials;
+    }
     return POSE_OK;
 }
 
@@ -977,16 +1048,29 @@ POSE_API int pose_conv2d_bf16(const void *X, int Nimg, int H, int Wd, int Cin, c
     const int bkc = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 0);
     if (!bkc) return POSE_E_UNSUPPORTED;  // channels-last activations are padded to a multiple of 32 channels
     const int Ho = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, Wo = (Wd + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
-    // output patch per M tile: TW = largest power of two <= 128 dividing Wo, then rows, then whole images
+    // output patch per M tile (128 pixels): TW x TH pixels of TN images.  Preferred: TW = largest power of two <= 128
+    // dividing Wo, then rows, then whole images; when Ho / Wo do not tile exactly (250 x 250 from a 500 x 500 input) the
+    // patch shape with the least padding is used and the edge patches are ragged
     int TW = 128;
     while (TW > 1 && (Wo % TW)) TW >>= 1;
     int TH = BM / TW, TN = 1;
+    bool exact = true;
     if (TH > Ho) {
-        if ((TH % Ho) || TW != Wo) return POSE_E_UNSUPPORTED;
-        TN = TH / Ho;
-        TH = Ho;
+        if ((TH % Ho) || TW != Wo) exact = false;
+        else { TN = TH / Ho; TH = Ho; }
     }
-    if (TW * TH * TN != BM || Ho % TH || Wo % TW) return POSE_E_UNSUPPORTED;
+    if (exact && (TW * TH * TN != BM || Ho % TH || Wo % TW)) exact = false;
+    if (!exact) {
+        long best = -1;
+        TN = 1;
+        for (int tw = 128; tw >= 4; tw >>= 1) {
+            const int th = BM / tw;
+            if (tw * stride > 256 || th * stride > 256) continue;           // TMA box limits
+            const long cover = (long)((Wo + tw - 1) / tw) * tw * ((Ho + th - 1) / th) * th;
+            if (best < 0 || cover < best) { best = cover; TW = tw; TH = th; }
+        }
+        if (best < 0) return POSE_E_UNSUPPORTED;
+    }
     const int K = KH * KW * Cin, N = Cout;
     Epilogue ep;
     int e = check_epilogue(epilogue, (long)Nimg * Ho * Wo, N, ep);
@@ -994,8 +1078,9 @@ POSE_API int pose_conv2d_bf16(const void *X, int Nimg, int H, int Wd, int Cin, c
     CUtensorMap ma;
     e = make_map_nhwc(&ma, X, Nimg, H, Wd, Cin, bkc, TW, TH, TN, stride);
     if (e) return e;
-    ConvGeom cg = {Ho, Wo, TH, TW, TN, Nimg, KW, KH * KW, stride, dil, pad, Cin / bkc};
-    const int m_tiles = ((Nimg + TN - 1) / TN) * (Ho / TH) * (Wo / TW);
+    const int tiles_w = (Wo + TW - 1) / TW, tiles_h = (Ho + TH - 1) / TH;
+    ConvGeom cg = {Ho, Wo, TH, TW, TN, Nimg, KW, KH * KW, stride, dil, pad, Cin / bkc, tiles_w, tiles_h};
+    const int m_tiles = ((Nimg + TN - 1) / TN) * tiles_h * tiles_w;
     const int M = Nimg * Ho * Wo;
     cudaStream_t s = (cudaStream_t)stream;
     if (bkc == 64) return dispatch_bn<64, 1>(ma, Wt, K, M, N, K, ep, cg, m_tiles, s);
@@ -1014,13 +1099,25 @@ POSE_API int pose_conv2d_wgrad_bf16(const void *dY, const void *X, int Nimg, int
     int TW = 64;
     while (TW > 1 && (Wo % TW)) TW >>= 1;
     int TH = 64 / TW, TN = 1;
+    bool exact = true;
     if (TH > Ho) {
-        if ((TH % Ho) || TW != Wo) return POSE_E_UNSUPPORTED;
-        TN = TH / Ho;
-        TH = Ho;
+        if ((TH % Ho) || TW != Wo) exact = false;
+        else { TN = TH / Ho; TH = Ho; }
     }
-    if (TW * TH * TN != 64 || Ho % TH || Wo % TW) return POSE_E_UNSUPPORTED;
-    const int patches = ((Nimg + TN - 1) / TN) * (Ho / TH) * (Wo / TW);
+    if (exact && (TW * TH * TN != 64 || Ho % TH || Wo % TW)) exact = false;
+    if (!exact) {           // ragged edge patches: dY outside the map is the TMA zero fill, so they add nothing
+        long best = -1;
+        TN = 1;
+        for (int tw = 64; tw >= 4; tw >>= 1) {
+            const int th = 64 / tw;
+            if (tw * stride > 256 || th * stride > 256) continue;
+            const long cover = (long)((Wo + tw - 1) / tw) * tw * ((Ho + th - 1) / th) * th;
+            if (best < 0 || cover < best) { best = cover; TW = tw; TH = th; }
+        }
+        if (best < 0) return POSE_E_UNSUPPORTED;
+    }
+    const int tiles_w = (Wo + TW - 1) / TW, tiles_h = (Ho + TH - 1) / TH;
+    const int patches = ((Nimg + TN - 1) / TN) * tiles_h * tiles_w;
     const int M = Cout, N = KH * KW * Cin, K = patches * 64;
     pose_gemm_epilogue pe = {nullptr, nullptr, dWk, N, 0, 0, 0, 1.0f, 0.0f, nullptr, 1, 0, 0ull, 0.0f, 0};
     Epilogue ep;
@@ -1031,7 +1128,7 @@ POSE_API int pose_conv2d_wgrad_bf16(const void *dY, const void *X, int Nimg, int
     if (e) return e;
     e = make_map_nhwc(&mw, X, Nimg, H, Wd, Cin, 64, TW, TH, TN, stride);
     if (e) return e;
-    ConvGeom cg = {Ho, Wo, TH, TW, TN, Nimg, KW, KH * KW, stride, dil, pad, Cin / 64};
+    ConvGeom cg = {Ho, Wo, TH, TW, TN, Nimg, KW, KH * KW, stride, dil, pad, Cin / 64, tiles_w, tiles_h};
     const int m_tiles = (M + BM - 1) / BM;
     return launch_gemm<128, 4, 64, 2, 1, 1>(ma, mw, M, N, K, ep, cg, m_tiles, (cudaStream_t)stream, k_splits);
 }

@@ -187,30 +187,49 @@ class CnnTrainPlan:
                       part.data_ptr(), part.numel())
             stat_parts = Bn * self.lib.pose_dwconv3x3_pool_parts(H, W, stride)
             kind = "dw"
-        elif name in self.pk:
-            _, fwd, bwd, cp, stage, _ui = self.pk[name]
-            Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
-            Wo = (W + 2 * pad - dil * (kh - 1) - 1) // stride + 1
-            y = self.buf(name + ".y", Bn * Ho * Wo, co)
-            e = self._epi(y, co)
-            self.call("pose_conv2d_bf16", x.data_ptr(), Bn, H, W, cin, self.pk16[fwd:].data_ptr(), co, kh, kh, stride, dil,
-                      pad, C.byref(e))
-            kind = "conv"
         else:
-            Ho, Wo = H, W
-            y = self.buf(name + ".y", Bn * H * W, co)
-            w16 = flat.w16(conv.weight)
-            self.gemm(x.data_ptr(), cin, w16.data_ptr(), cin, Bn * H * W, co, cin, self._epi(y, co))
-            kind = "1x1"
+            spatial = name in self.pk
+            if spatial:
+                _, fwd, bwd, cp, stage, _ui = self.pk[name]
+                Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+                Wo = (W + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+            else:
+                Ho, Wo = H, W
+            M = Bn * Ho * Wo
+            y = self.buf(name + ".y", M, co)
+            mr = self.buf(name + ".mr", 2 * co, dtype=torch.float32)
+            ss = self.buf(name + ".ss", 2 * co, dtype=torch.float32)
+            e = self._epi(y, co)
+            fused = co % 32 == 0
+            if fused:
+                # batch statistics from the fp32 accumulators in the epilogue + the fold, in the same call (pose_bn_fuse)
+                part = self.partials()
+                f = _lib.PoseBnFuse()
+                f.partials, f.cap_floats = part.data_ptr(), part.numel()
+                f.gamma, f.beta = flat.f32(bn.weight).data_ptr(), flat.f32(bn.bias).data_ptr()
+                f.eps, f.momentum, f.count = float(bn.eps), float(bn.momentum), M
+                f.mean_rstd, f.scale_shift = mr.data_ptr(), ss.data_ptr()
+                f.running_mean, f.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+                e.bn = C.pointer(f)
+            if spatial:
+                self.call("pose_conv2d_bf16", x.data_ptr(), Bn, H, W, cin, self.pk16[fwd:].data_ptr(), co, kh, kh, stride,
+                          dil, pad, C.byref(e))
+                kind = "conv"
+            else:
+                w16 = flat.w16(conv.weight)
+                self.gemm(x.data_ptr(), cin, w16.data_ptr(), cin, M, co, cin, e)
+                kind = "1x1"
+            if fused:
+                self.launches += 1          # the fold launched by the same call
         M = Bn * Ho * Wo
         part = self.partials()
-        mr = self.buf(name + ".mr", 2 * co, dtype=torch.float32)
-        ss = self.buf(name + ".ss", 2 * co, dtype=torch.float32)
         if kind == "dw":
+            mr = self.buf(name + ".mr", 2 * co, dtype=torch.float32)
+            ss = self.buf(name + ".ss", 2 * co, dtype=torch.float32)
             self.call("pose_bn_finalize_parts", part.data_ptr(), stat_parts, M, flat.f32(bn.weight).data_ptr(),
                       flat.f32(bn.bias).data_ptr(), float(bn.eps), float(bn.momentum), co, mr.data_ptr(), ss.data_ptr(),
                       bn.running_mean.data_ptr(), bn.running_var.data_ptr())
-        else:
+        elif not fused:
             self.call("pose_bn_stats_bf16", y.data_ptr(), M, co, co, part.data_ptr(), part.numel())
             self.call("pose_bn_finalize", part.data_ptr(), part.numel(), M, flat.f32(bn.weight).data_ptr(),
                       flat.f32(bn.bias).data_ptr(), float(bn.eps), float(bn.momentum), co, mr.data_ptr(), ss.data_ptr(),

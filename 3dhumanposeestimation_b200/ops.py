@@ -6,7 +6,6 @@ import torch
 from . import _lib
 from .utils import activation_id
 
-_bf16_cache = {}
 
 
 def to_bf16(x: torch.Tensor) -> torch.Tensor:
@@ -24,13 +23,14 @@ def cached_bf16(param: torch.Tensor) -> torch.Tensor:
     """bf16 shadow copy of an fp32 master parameter, refreshed when the parameter is updated in place: torch writes
     bump ``_version``; the fused AdamW writes through raw pointers and bumps ``FlatParams.generation`` instead.
     Master weights keep the reference's fp32 [out, in] layout."""
-    key = id(param)
-    ent = _bf16_cache.get(key)
+    # the cache entry lives ON the parameter object (an id()-keyed table can hand a freed parameter's entry to a new one
+    # that reuses the id and the allocation)
+    ent = getattr(param, "_pose_bf16", None)
     flat = getattr(param, "_pose_flat", None)
     version = param._version + (flat[0].generation if flat is not None else 0)
     if ent is None or ent[0] != version or ent[1] != param.data_ptr():
         ent = (version, param.data_ptr(), to_bf16(param.detach().contiguous()))
-        _bf16_cache[key] = ent
+        param._pose_bf16 = ent
     return ent[2]
 
 

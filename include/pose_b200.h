@@ -130,6 +130,7 @@ int pose_cast_f32_bf16(const float *in, void *out, long n, pose_stream_t stream)
  * bias [N] fp32 or NULL (a folded BatchNorm leaves only this), residual [M, ldr] bf16 or NULL, C [M, ldc] fp32
  * (out_dtype 0) or bf16 (1).  Writing with ldc > N into a column slice implements torch.cat along channels.
  * act: 0 none, 1 relu, 2 silu, 3 gelu(erf), 4 sigmoid. */
+struct pose_bn_fuse;
 typedef struct pose_gemm_epilogue {
     const float *bias;
     const void *residual;
@@ -149,7 +150,27 @@ typedef struct pose_gemm_epilogue {
     uint64_t drop_seed;
     float drop_p;
     int32_t reserved2;
+    /* training-mode BatchNorm fused behind the contraction (ConvBnAct, src/models/cnn.py:135-139; nn.BatchNorm2d of
+     * src/utils.py:186-187): NULL = off.  See pose_bn_fuse below. */
+    const struct pose_bn_fuse *bn;
 } pose_gemm_epilogue;
+
+/* Batch statistics of a convolution's output taken from the fp32 ACCUMULATORS in the epilogue of the producing GEMM /
+ * implicit-GEMM convolution (act 0, bf16 or fp32 output, N a multiple of 32): every persistent CTA keeps per-column sums
+ * and sums of squares over its tiles (fixed order, no atomics), writes one partial row per TMEM lane quarter into
+ * `partials` [parts, 2, N], and the same call launches the fold: mean / rstd, the affine coefficients
+ * z = y * scale + shift, and nn.BatchNorm2d's running-statistics update (momentum, unbiased variance) -- the
+ * pose_bn_stats_bf16 pass over the bf16 output is not needed.  `count` = rows of the output (N * Ho * Wo). */
+typedef struct pose_bn_fuse {
+    float *partials;            /* scratch, cap_floats >= 4 * 148 * 2 * N */
+    int64_t cap_floats;
+    const float *gamma, *beta;  /* [N] */
+    float eps, momentum;
+    int64_t count;
+    float *mean_rstd;           /* [2, N] out */
+    float *scale_shift;         /* [2, N] out */
+    float *running_mean, *running_var;   /* [N] in/out or NULL */
+} pose_bn_fuse;
 
 int pose_gemm_bf16_ex(const void *A, int lda, const void *W, int ldw, int M, int N, int K,
                       const pose_gemm_epilogue *epilogue, pose_stream_t stream);

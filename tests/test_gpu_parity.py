@@ -428,10 +428,11 @@ def test_regression_head_training_mode_autograd_and_dropout(pose, flavour):
 
     def rel(a, b):
         return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
-    assert rel(got["x"], xr.grad) < 2e-2, rel(got["x"], xr.grad)
+    errs = {"x": rel(got["x"], xr.grad)}
     for i, lin in enumerate(lins):
-        assert rel(got[f"w{i}"], lin.weight.grad) < 2e-2, (i, rel(got[f"w{i}"], lin.weight.grad))
-        assert rel(got[f"b{i}"], lin.bias.grad) < 2e-2, (i, rel(got[f"b{i}"], lin.bias.grad))
+        errs[f"w{i}"] = rel(got[f"w{i}"], lin.weight.grad)
+        errs[f"b{i}"] = rel(got[f"b{i}"], lin.bias.grad)
+    assert max(errs.values()) < 2e-2, errs
     # eval mode: no dropout, deterministic, no autograd graph needed
     head.eval()
     with torch.no_grad():

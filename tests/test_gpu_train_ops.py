@@ -101,3 +101,84 @@ def test_forward_gemm_saves_the_activation_derivative(pose, M):
         fn(wu).backward(torch.ones_like(wu))
         far = (wu.detach().abs() > 0.05)          # relu' is discontinuous at 0: compare away from it
         assert torch.allclose(u.float()[far], wu.grad[far], rtol=2e-2, atol=2e-2)
+
+
+def _bn_fuse(pose, N, count, gamma, beta, rm, rv, eps=1e-5, momentum=0.1):
+    f = pose._lib.PoseBnFuse()
+    part = torch.empty(4 * 148 * 2 * N, device=DEV)
+    mr, ss = torch.empty(2 * N, device=DEV), torch.empty(2 * N, device=DEV)
+    f.partials, f.cap_floats = part.data_ptr(), part.numel()
+    f.gamma, f.beta, f.eps, f.momentum, f.count = gamma.data_ptr(), beta.data_ptr(), eps, momentum, count
+    f.mean_rstd, f.scale_shift = mr.data_ptr(), ss.data_ptr()
+    f.running_mean, f.running_var = rm.data_ptr(), rv.data_ptr()
+    return f, (part, mr, ss)
+
+
+def _check_bn_fuse(y32, mr, ss, rm, rv, gamma, beta, eps=1e-5, momentum=0.1):
+    """mean / rstd / scale / shift / running statistics of nn.BatchNorm2d in training mode over the fp32 rows y32 [M, N]
+    (src/utils.py:186-187); fp32 sums in a different order: 1e-5 relative on the moments."""
+    M, N = y32.shape
+    mean = y32.double().mean(0)
+    var = y32.double().var(0, unbiased=False)
+    rstd = (var + eps).rsqrt()
+    assert torch.allclose(mr[:N].double(), mean, rtol=1e-4, atol=1e-4 * y32.abs().max().item())
+    assert torch.allclose(mr[N:].double(), rstd, rtol=2e-4)
+    a = gamma.double() * rstd
+    assert torch.allclose(ss[:N].double(), a, rtol=2e-4, atol=1e-6)
+    assert torch.allclose(ss[N:].double(), beta.double() - mean * a, rtol=2e-4, atol=2e-4 * (mean * a).abs().max().item() + 1e-6)
+    assert torch.allclose(rm.double(), momentum * mean, rtol=1e-4, atol=1e-5 * y32.abs().max().item())
+    assert torch.allclose(rv.double(), (1 - momentum) * 1.0 + momentum * var * M / (M - 1), rtol=2e-4)
+
+
+@pytest.mark.parametrize("M,N,K", [(128 * 64 * 4, 64, 64), (5000, 128, 128), (32768, 3072, 512), (8192 + 77, 768, 256),
+                                   (300, 32, 64), (16384, 512, 3072), (40000, 256, 768)])
+def test_gemm_epilogue_emits_batchnorm_statistics_from_the_accumulators(pose, M, N, K):
+    """pose_bn_fuse: the 1x1-convolution GEMM of ConvBnAct (cnn.py:122-139) returns the batch statistics of its fp32
+    accumulators and the folded scale / shift in the same call (128 x {32,64,128,256} tiles, ragged M, several column tiles
+    per CTA grid), deterministically."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).bfloat16()
+    w[: N // 2] += 0.05                                      # non-zero channel means
+    gamma, beta = (torch.rand(N, generator=g) + 0.5).to(DEV), torch.randn(N, generator=g).to(DEV)
+    runs = []
+    for _ in range(2):
+        rm, rv = torch.zeros(N, device=DEV), torch.ones(N, device=DEV)
+        y = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        f, (part, mr, ss) = _bn_fuse(pose, N, M, gamma, beta, rm, rv)
+        e = _epi(pose, y)
+        e.bn = C.pointer(f)
+        pose._lib.check(pose._lib.lib().pose_gemm_bf16_ex(x.data_ptr(), K, w.data_ptr(), K, M, N, K, C.byref(e),
+                                                          pose._lib.stream_ptr()), "gemm")
+        torch.cuda.synchronize()
+        runs.append((y.clone(), mr.clone(), ss.clone(), rm.clone(), rv.clone()))
+    y32 = x.float() @ w.float().t()
+    y, mr, ss, rm, rv = runs[0]
+    assert torch.allclose(y.float(), y32, rtol=2 ** -7, atol=1e-2)
+    _check_bn_fuse(y32, mr, ss, rm, rv, gamma, beta)
+    for a, b in zip(runs[0], runs[1]):
+        assert torch.equal(a, b)                             # fixed-order partial sums: bit-reproducible
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,k,stride,dil", [(4, 64, 64, 64, 3, 1, 1), (3, 64, 64, 64, 5, 2, 1), (8, 16, 512, 512, 3, 1, 6),
+                                                      (5, 16, 64, 128, 3, 1, 18)])
+def test_conv_epilogue_emits_batchnorm_statistics(pose, B, H, Cin, Cout, k, stride, dil):
+    """The same fused statistics behind the implicit-GEMM convolution (conv1.0 / conv1.1 / WASP branches)."""
+    g = torch.Generator().manual_seed(B * H + Cout + k)
+    x = torch.randn(B, H, H, Cin, generator=g).to(DEV).bfloat16()
+    w = (torch.randn(Cout, k, k, Cin, generator=g) / (k * k * Cin) ** 0.5).to(DEV).bfloat16()
+    pad = dil * (k - 1) // 2
+    Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    M = B * Ho * Ho
+    gamma, beta = (torch.rand(Cout, generator=g) + 0.5).to(DEV), torch.randn(Cout, generator=g).to(DEV)
+    rm, rv = torch.zeros(Cout, device=DEV), torch.ones(Cout, device=DEV)
+    y = torch.empty(M, Cout, device=DEV, dtype=torch.bfloat16)
+    f, (part, mr, ss) = _bn_fuse(pose, Cout, M, gamma, beta, rm, rv)
+    e = _epi(pose, y)
+    e.bn = C.pointer(f)
+    pose._lib.check(pose._lib.lib().pose_conv2d_bf16(x.data_ptr(), B, H, H, Cin, w.data_ptr(), Cout, k, k, stride, dil, pad,
+                                                     C.byref(e), pose._lib.stream_ptr()), "conv")
+    y32 = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), stride=stride, padding=pad, dilation=dil)
+    y32 = y32.permute(0, 2, 3, 1).reshape(M, Cout)
+    assert torch.allclose(y.float(), y32, rtol=2 ** -7, atol=1e-2)
+    _check_bn_fuse(y32, mr, ss, rm, rv, gamma, beta)
