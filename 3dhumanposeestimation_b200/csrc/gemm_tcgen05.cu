@@ -82,6 +82,8 @@ struct GemmSmem {
     static constexpr int kStagePitch = 144;                      // 32 fp32 + 16 B pad: conflict-free 16 B accesses
     // per epilogue warp: a 32 x 32 fp32 transpose buffer (4608 B), or two 32 x 32 bf16 TMA tiles (output at +0,
     // auxiliary at +2048); the smaller TMA staging leaves room for one more pipeline stage
+    // TMA_EPI 2 (lean plain epilogue): one 2560-byte region (residual tile / column-reduction half tiles / output tile in
+    // turn) at +0 and the running column statistics (512) at +3072
     static constexpr int kWarpStaging = TMA_EPI ? 4096 : 5120;
     static constexpr int kStagingBytes = 16 * kWarpStaging;
     static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + kStagingBytes + 1024;  // + alignment slack
@@ -462,6 +464,89 @@ __device__ __forceinline__ void epilogue_tma(uint32_t tmem_chunk, uint64_t *acc_
     }
 }
 
+// ---- lean TMA epilogue (TMA_EPI 2) -------------------------------------------------------------------------------------
+// The 1x1 convolutions of the CNN are short contractions (K = 64..768) whose cost is the output write: the transposing
+// epilogue above spends ~630 instructions per 32 x 32 chunk (ncu: profiles/r02_gemm_1x1_k256_plain_epilogue_full_raw.csv,
+// issue bound at 2.3 TB/s).  This variant handles exactly what those layers need -- C = acc (+ residual), bf16, no bias /
+// activation -- in ~40 instructions per chunk: one 32-column tcgen05.ld, 16 packed converts, four 16-byte stores into a
+// 64-byte-swizzled tile and one TMA store.  Optional column statistics (training-mode BatchNorm): the fp32 chunk goes
+// through a padded staging tile and every lane sums two columns over 16 rows with packed FADD2 / FFMA2 (~75 instructions).
+__device__ __forceinline__ float2 lds64f(uint32_t saddr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64f(uint32_t saddr, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr), "f"(v.x), "f"(v.y) : "memory");
+}
+// One staging region R per warp is reused in sequence: residual tile (TMA load) -> fp32 half tiles of the column reduction
+// -> bf16 output tile (TMA store); 2560 B, so the kernel keeps the five-stage operand ring of the other TMA epilogue.
+__device__ __forceinline__ void epilogue_lean(uint32_t tmem_chunk, uint64_t *acc_empty_bar, bool release, const Epilogue &ep,
+                                              const CUtensorMap *map_c, uint32_t R, float2 (&st)[2][2], uint64_t *auxbar,
+                                              uint32_t &aux_phase, long row0, int lane, int col0) {
+    uint32_t acc[32];
+    tmem_ld32(tmem_chunk, acc);
+    if (release) {                                      // the warp's last chunk has left TMEM: release the accumulator stage
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty_bar)) : "memory");
+    }
+    if (ep.residual != nullptr) {                       // + residual tile (TMA load issued by the caller)
+        mbar_wait(auxbar, aux_phase);
+        aux_phase ^= 1;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint4 pk = lds128u(R + sw64(lane, c));
+            const __nv_bfloat162 *h = (const __nv_bfloat162 *)&pk;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 t = __bfloat1622float2(h[q]);
+                acc[c * 8 + 2 * q] = __float_as_uint(__uint_as_float(acc[c * 8 + 2 * q]) + t.x);
+                acc[c * 8 + 2 * q + 1] = __float_as_uint(__uint_as_float(acc[c * 8 + 2 * q + 1]) + t.y);
+            }
+        }
+        __syncwarp();                                   // every lane has read its row: R may be rewritten
+    }
+    if (ep.stats != nullptr) {
+        // column sums / sums of squares of the fp32 chunk, 16 columns per pass through R (pitch 80 B: conflict-free 16-byte
+        // stores); lane (g, jq) adds columns 2 jq, 2 jq + 1 of the eight rows 4 r + g to its running totals `st`, which stay
+        // in registers for the whole kernel (folded across lanes once, after the last tile).  Rows past M are zero (TMA zero
+        // fill of A and of the residual) and add nothing.
+        const int g = lane >> 3, jq = lane & 7;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                sts128(R + lane * 80 + j * 16, acc[16 * p + 4 * j], acc[16 * p + 4 * j + 1], acc[16 * p + 4 * j + 2], acc[16 * p + 4 * j + 3]);
+            __syncwarp();
+            float2 s1 = st[p][0], s2 = st[p][1];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float2 v = lds64f(R + (4 * r + g) * 80 + jq * 8);
+                s1 = __fadd2_rn(s1, v);
+                s2 = __ffma2_rn(v, v, s2);
+            }
+            st[p][0] = s1;
+            st[p][1] = s2;
+            __syncwarp();                               // R is rewritten by the next pass / the output tile
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        __nv_bfloat162 p[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            p[q] = __floats2bfloat162_rn(__uint_as_float(acc[c * 8 + 2 * q]), __uint_as_float(acc[c * 8 + 2 * q + 1]));
+        sts128(R + sw64(lane, c), *(uint32_t *)&p[0], *(uint32_t *)&p[1], *(uint32_t *)&p[2], *(uint32_t *)&p[3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(map_c, R, col0, (int)row0);
+        tma_store_commit();
+    }
+}
+
 // PERSISTENT kernel: grid = min(tiles, SMs); every CTA walks tiles t = blockIdx.x, += gridDim.x (N fastest so an A
 // tile is reused from L2 by its N neighbours).  The TMA ring runs ahead across tile boundaries, the accumulator is
 // double buffered in TMEM (2 x BN columns), so the epilogue of tile i overlaps the MMAs of tile i + 1.
@@ -636,6 +721,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // column statistics (ep.stats): the warp's running totals live behind its transpose buffer (2 chunks x 2 x 32 fp32);
         // the host sizes the grid as a multiple of n_tiles, so every tile of this CTA covers the same columns
         const uint32_t wstat0 = stg + 32 * S::kStagePitch;
+        float2 lst[(BN / 32 + 3) / 4][2][2];             // TMA_EPI 2: per-lane running column sums [chunk][pass][sum, sum sq]
+#pragma unroll
+        for (int i = 0; i < (BN / 32 + 3) / 4; ++i)
+#pragma unroll
+            for (int p = 0; p < 2; ++p) lst[i][p][0] = lst[i][p][1] = make_float2(0.f, 0.f);
         if (TMA_EPI == 0 && ep.stats != nullptr) {
             sts128(wstat0 + lane * 16, 0u, 0u, 0u, 0u);
             __syncwarp();
@@ -645,7 +735,41 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
             const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BN;
             const int r = quarter * 32 + lane;
-            if constexpr (TMA_EPI != 0) {
+            if constexpr (TMA_EPI == 2) {
+                // ---- lean plain epilogue (see epilogue_lean) ----
+                constexpr int kMineT = (BN / 32 + 3) / 4;
+                const long row0 = (long)mt * BM + quarter * 32;
+                bool waited = false;
+#pragma unroll
+                for (int ci = 0; ci < kMineT; ++ci) {                   // unrolled: lst[ci] must stay in registers
+                    const int c = cgrp + 4 * ci;
+                    const int col0 = n0 + c * 32;
+                    const bool mine = c < BN / 32 && col0 < N;          // warp-uniform
+                    const bool last = ci == kMineT - 1;
+                    if (lane == 0 && mine) {
+                        tma_store_wait_read();                          // the previous store has left the output tile
+                        if (ep.residual != nullptr) {
+                            mbar_expect_tx(aux_bar + (warp - 2), 32 * 64);
+                            tma_load_2d((void *)(staging + (warp - 2) * S::kWarpStaging), &map_aux, aux_bar + (warp - 2), col0, (int)row0);
+                        }
+                    }
+                    __syncwarp();
+                    if (!waited) {
+                        mbar_wait(acc_full + as, aph);
+                        tc_fence_after();
+                        waited = true;
+                    }
+                    const uint32_t chunk = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(c * 32);
+                    if (mine) {
+                        epilogue_lean(chunk, acc_empty + as, last, ep, &map_c, stg, lst[ci], aux_bar + (warp - 2), aux_phase, row0, lane,
+                                      col0);
+                    } else if (last) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
+                    }
+                }
+            } else if constexpr (TMA_EPI != 0) {
                 // ---- row-per-lane epilogue with TMA stores: chunk c = cgrp + 4 * ci of the tile (one per warp at BN = 128, two at
                 //      BN = 256; the warp's staging tiles are reused chunk after chunk) ----
                 constexpr int kMineT = (BN / 32 + 3) / 4;
@@ -744,7 +868,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             }   // !TMA_EPI
         }
-        if (TMA_EPI == 0 && ep.stats != nullptr) {
+        if (TMA_EPI != 1 && ep.stats != nullptr) {
             // partial row (blockIdx / n_tiles) * 4 + quarter of [parts, 2, N]: every (row, column) has exactly one writer
             __syncwarp();
             const int n0 = (blockIdx.x % n_tiles) * BN;
@@ -753,7 +877,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int ci = 0; ci < (BN / 32 + 3) / 4; ++ci) {
                 const int c = cgrp + 4 * ci;
                 const int col0 = n0 + c * 32;
-                if (c < BN / 32 && col0 < N) {
+                if (TMA_EPI == 2) {
+                    // fold the four row groups (lanes jq, jq + 8, jq + 16, jq + 24) in a fixed order
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+#define FOLD_(v_) v_ += __shfl_xor_sync(0xffffffffu, v_, 8); v_ += __shfl_xor_sync(0xffffffffu, v_, 16);
+                        FOLD_(lst[ci][p][0].x) FOLD_(lst[ci][p][0].y) FOLD_(lst[ci][p][1].x) FOLD_(lst[ci][p][1].y)
+#undef FOLD_
+                        if (lane < 8 && c < BN / 32 && col0 < N) {
+                            *(float2 *)(dst + col0 + p * 16 + 2 * lane) = lst[ci][p][0];
+                            *(float2 *)(dst + N + col0 + p * 16 + 2 * lane) = lst[ci][p][1];
+                        }
+                    }
+                } else if (c < BN / 32 && col0 < N) {
                     dst[col0 + lane] = lds32(wstat0 + ci * 256 + lane * 4);
                     dst[N + col0 + lane] = lds32(wstat0 + ci * 256 + 128 + lane * 4);
                 }
@@ -847,20 +983,37 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
     }
     constexpr int kTma = MODE == 0 ? 1 : 0;
     constexpr int kStagesT = (kTma && BN == 128) ? kStages + 1 : kStages;      // 5 x 32 KB stages fit beside the TMA staging
+    // lean plain epilogue (TMA_EPI 2; MODE 0, tiles up to 128 columns): bf16 C = acc (+ residual), optional column
+    // statistics (tools/bench_gemm_cnn.py measures it on the CNN's 1x1 shapes).
+    constexpr bool kHasLean = MODE == 0;
+    constexpr int kLean = kHasLean ? 2 : 0;
+    constexpr int kStagesL = kStagesT;
     using S0 = GemmSmem<BN, kStages, BKC, 0>;
     using S1 = GemmSmem<BN, kStagesT, BKC, kTma>;
-    static_assert(S0::kTotal <= 232448 && S1::kTotal <= 232448, "shared memory budget");
+    using S2 = GemmSmem<BN, kStagesL, BKC, kLean>;
+    static_assert(S0::kTotal <= 232448 && S1::kTotal <= 232448 && S2::kTotal <= 232448, "shared memory budget");
     auto kern_plain = gemm_bf16_tn_kernel<BN, kStages, BKC, MODE, A_MN, B_MN, 0>;
     auto kern_tma = gemm_bf16_tn_kernel<BN, kStagesT, BKC, MODE, A_MN, B_MN, kTma>;
+    auto kern_lean = gemm_bf16_tn_kernel<BN, kStagesL, BKC, MODE, A_MN, B_MN, kLean>;
     static bool configured = false;
     if (!configured) {
         cudaError_t ce = cudaFuncSetAttribute(kern_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, S0::kTotal);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, S1::kTotal);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(kern_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::kTotal);
         if (ce != cudaSuccess) return (int)ce;
         configured = true;
     }
-    auto kern = ep.tma ? kern_tma : kern_plain;
-    const int smem_bytes = ep.tma ? S1::kTotal : S0::kTotal;
+    static const bool lean_off = getenv("POSE_NO_LEAN_EPILOGUE") != nullptr;   // A/B switch for measurements
+    bool lean = false;
+    if (kHasLean && !lean_off && !ep.tma && ep.out_bf16 && !ep.accumulate && ep.vec && N % 32 == 0 && ep.act == 0 &&
+        ep.bias == nullptr && ep.preact == nullptr && ep.drop_thresh == 0 && ep.out_scale == 1.0f &&
+        (ep.residual == nullptr || ep.res_scale == 1.0f) && k_splits <= 1) {
+        int e = make_map_tile32(&mc, ep.C, M, N, ep.ldc);
+        if (!e && ep.residual) e = make_map_tile32(&maux, ep.residual, M, N, ep.ldr);
+        lean = !e;
+    }
+    auto kern = lean ? kern_lean : (ep.tma ? kern_tma : kern_plain);
+    const int smem_bytes = lean ? S2::kTotal : (ep.tma ? S1::kTotal : S0::kTotal);
     const int n_tiles = (N + BN - 1) / BN;
     const int num_kb = (K + BKC - 1) / BKC;
     if (k_splits < 1) k_splits = 1;
@@ -892,6 +1045,7 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
 static bool wide_tile_ok(const Epilogue &ep, int N, int K, int m_tiles, int k_splits) {
     static const bool off = getenv("POSE_GEMM_NO_BN256") != nullptr;      // A/B switch for measurements
     if (off || N % 256 || K < 512) return false;          // short contractions are output-write bound: nothing to gain
+
     static const bool heavy_narrow = getenv("POSE_GEMM_HEAVY_BN128") != nullptr;      // A/B switch for measurements
     const bool heavy = ep.act == 3 || ep.act >= 5 || ep.preact != nullptr;
     if (heavy_narrow && heavy && ep.out_bf16 && !ep.accumulate && ep.vec) return false;
