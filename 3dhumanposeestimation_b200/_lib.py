@@ -84,6 +84,7 @@ SIGNATURES = {
     "pose_coord_pool_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pose_coord_apply_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pose_avgpool2x2_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pose_adaptive_avgpool_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pose_sums_to_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "pose_layernorm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_float, C.c_long, c_int, C.c_long, C.c_long, C.c_long,
                                     C.c_long, c_int, c_void_p, c_void_p]),
@@ -128,6 +129,7 @@ SIGNATURES = {
     "pose_wasp_mix_bwd_bf16": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, C.c_long, c_int, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p]),
     "pose_avgpool2x2_bwd_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pose_adaptive_avgpool_bwd_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pose_scatter_strided_add_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pose_add_bf16": (c_int, [c_void_p, c_void_p, C.c_long, c_void_p, c_void_p]),
     "pose_dropout_bf16": (c_int, [c_void_p, C.c_long, c_float, C.c_uint64, c_void_p, c_void_p]),

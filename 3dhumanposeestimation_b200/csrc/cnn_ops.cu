@@ -458,6 +458,36 @@ coord_apply_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__r
     }
 }
 
+// nn.AdaptiveAvgPool2d((OH, OW)) (cnn.py:602), NHWC bf16: window i covers [floor(i H / OH), ceil((i + 1) H / OH))
+// (windows overlap when H is not a multiple of OH), fp32 sum / window size
+__global__ void __launch_bounds__(256)
+adaptive_avgpool_kernel(const __nv_bfloat16 *__restrict__ X, int H, int W, int C, int OH, int OW, long total8,
+                        __nv_bfloat16 *__restrict__ Y) {
+    const int C8 = C >> 3;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        long p = i / C8;
+        const int ox = (int)(p % OW);
+        p /= OW;
+        const int oy = (int)(p % OH);
+        const long b = p / OH;
+        const int y0 = (oy * H) / OH, y1 = ((oy + 1) * H + OH - 1) / OH;
+        const int x0 = (ox * W) / OW, x1 = ((ox + 1) * W + OW - 1) / OW;
+        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int y = y0; y < y1; ++y)
+            for (int x = x0; x < x1; ++x) {
+                float f[8];
+                unpack8(__ldg((const uint4 *)(X + (((b * H + y) * W) + x) * C + cg * 8)), f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s[k] += f[k];
+            }
+        const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] *= inv;
+        ((uint4 *)Y)[i] = pack8(s);
+    }
+}
+
 // 2x2 average pooling (AdaptiveAvgPool2d(8) on a 16x16 map, cnn.py:602), NHWC bf16
 __global__ void __launch_bounds__(256)
 avgpool2x2_kernel(const __nv_bfloat16 *__restrict__ X, int H, int W, int C, long total8, __nv_bfloat16 *__restrict__ Y) {
@@ -650,6 +680,16 @@ POSE_API int pose_coord_apply_bf16(const void *X, const void *G, int B, int H, i
     const long total8 = (long)B * H * W * (C / 8);
     coord_apply_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, (const __nv_bfloat16 *)G, H, W,
                                                                           C, total8, (__nv_bfloat16 *)Y);
+    return launch_status();
+}
+
+POSE_API int pose_adaptive_avgpool_bf16(const void *X, int B, int H, int W, int C, int OH, int OW, void *Y, pose_stream_t stream) {
+    if (!X || !Y) return POSE_E_NULL;
+    if (B <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || OH > H || OW > W || C <= 0 || C % 8) return POSE_E_SHAPE;
+    if ((uintptr_t)X % 16 || (uintptr_t)Y % 16) return POSE_E_ALIGN;
+    const long total8 = (long)B * OH * OW * (C / 8);
+    adaptive_avgpool_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)X, H, W, C, OH, OW, total8,
+                                                                               (__nv_bfloat16 *)Y);
     return launch_status();
 }
 

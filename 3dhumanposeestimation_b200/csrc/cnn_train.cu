@@ -766,6 +766,38 @@ __global__ void wasp_weights_bwd_kernel(const float *__restrict__ raw, const flo
 }
 
 // ---- pooling / striding / elementwise ---------------------------------------------------------------------
+// backward of nn.AdaptiveAvgPool2d: dX[b, y, x, c] = sum over the windows (oy, ox) that contain (y, x) of dY / window size
+// (gather form: deterministic, no atomics; a pixel lies in at most two windows per axis when OH <= H)
+__global__ void __launch_bounds__(256)
+adaptive_avgpool_bwd_kernel(const __nv_bfloat16 *__restrict__ dY, int H, int W, int C, int OH, int OW, long total8,
+                            __nv_bfloat16 *__restrict__ dX) {
+    const int C8 = C >> 3;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % C8);
+        long p = i / C8;
+        const int x = (int)(p % W);
+        p /= W;
+        const int y = (int)(p % H);
+        const long b = p / H;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int oy_c = (y * OH) / H, ox_c = (x * OW) / W;
+        for (int oy = max(0, oy_c - 1); oy <= min(OH - 1, oy_c + 1); ++oy) {
+            const int y0 = (oy * H) / OH, y1 = ((oy + 1) * H + OH - 1) / OH;
+            if (y < y0 || y >= y1) continue;
+            for (int ox = max(0, ox_c - 1); ox <= min(OW - 1, ox_c + 1); ++ox) {
+                const int x0 = (ox * W) / OW, x1 = ((ox + 1) * W + OW - 1) / OW;
+                if (x < x0 || x >= x1) continue;
+                float f[8];
+                up8(__ldg((const uint4 *)(dY + ((b * OH + oy) * OW + ox) * C + cg * 8)), f);
+                const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], inv, acc[j]);
+            }
+        }
+        ((uint4 *)dX)[i] = pk8(acc);
+    }
+}
+
 // dX[b, 2y+dy, 2x+dx, c] = 0.25 * dY[b, y, x, c]
 __global__ void __launch_bounds__(256)
 avgpool2x2_bwd_kernel(const __nv_bfloat16 *__restrict__ dY, int H, int W, int C, long total8, __nv_bfloat16 *__restrict__ dX) {
@@ -1141,6 +1173,17 @@ POSE_API int pose_wasp_mix_bwd_bf16(const void *dOut, const void *branches, int 
                                                                 (long)B * HW * C, (const __nv_bfloat16 *)glob, raw_weights, HW, C,
                                                                 total8, (__nv_bfloat16 *)dbranches, dglob, dots);
     wasp_weights_bwd_kernel<<<1, 32, 0, s>>>(raw_weights, dots, nb + 1, draw);
+    return launch_status();
+}
+
+POSE_API int pose_adaptive_avgpool_bwd_bf16(const void *dY, int B, int H, int W, int C, int OH, int OW, void *dX,
+                                            pose_stream_t stream) {
+    REQ(dY && dX, POSE_E_NULL);
+    REQ(B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && OH <= H && OW <= W && C > 0 && C % 8 == 0, POSE_E_SHAPE);
+    REQ((uintptr_t)dY % 16 == 0 && (uintptr_t)dX % 16 == 0, POSE_E_ALIGN);
+    const long total8 = (long)B * H * W * (C / 8);
+    adaptive_avgpool_bwd_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dY, H, W, C, OH, OW, total8,
+                                                                                   (__nv_bfloat16 *)dX);
     return launch_status();
 }
 

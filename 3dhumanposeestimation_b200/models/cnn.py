@@ -542,8 +542,12 @@ class CnnInferencePlan:
             y = self._buf(Bn, gp, gp, x.shape[-1])
             self._launch("pose_avgpool2x2_bf16", x.data_ptr(), Bn, H, H, x.shape[-1], y.data_ptr())
             x = y
+        elif H > gp:
+            y = self._buf(Bn, gp, gp, x.shape[-1])
+            self._launch("pose_adaptive_avgpool_bf16", x.data_ptr(), Bn, H, H, x.shape[-1], gp, gp, y.data_ptr())
+            x = y
         elif H != gp:
-            raise NotImplementedError(f"AdaptiveAvgPool2d({gp}) from {H}x{H}: only identity and 2x2 pooling are built")
+            raise NotImplementedError(f"AdaptiveAvgPool2d({gp}) from a smaller {H}x{H} map (up-sampling) is not built")
         x = self.conv1x1(x, m.global_features[1])
         ch = x.shape[-1]
         pool = self.pool_sums(x)

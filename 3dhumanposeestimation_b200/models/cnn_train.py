@@ -632,8 +632,13 @@ class CnnTrainPlan:
             self.call("pose_avgpool2x2_bf16", x.data_ptr(), Bn, H, H, s[3], y.data_ptr())
             self.pooled = (Bn, H, H, s[3])
             x, s = y, (Bn, gp, gp, s[3])
+        elif H > gp:
+            y = self.buf("gf.pool", Bn * gp * gp, s[3])
+            self.call("pose_adaptive_avgpool_bf16", x.data_ptr(), Bn, H, H, s[3], gp, gp, y.data_ptr())
+            self.pooled = (Bn, H, H, s[3])
+            x, s = y, (Bn, gp, gp, s[3])
         elif H != gp:
-            raise NotImplementedError(f"AdaptiveAvgPool2d({gp}) from {H}x{H}: only identity and 2x2 pooling are built")
+            raise NotImplementedError(f"AdaptiveAvgPool2d({gp}) from a smaller {H}x{H} map (up-sampling) is not built")
         x, s = self.cba_fwd("global_features.1", m.global_features[1], x, s)
         ch = s[3]
         eca = m.global_features[2]
@@ -718,7 +723,10 @@ class CnnTrainPlan:
         if self.pooled is not None:
             _, H, W, cc = self.pooled
             dfull = self.buf("gf.dpool", Bn * H * W, cc)
-            self.call("pose_avgpool2x2_bwd_bf16", d.data_ptr(), Bn, H, W, cc, dfull.data_ptr())
+            if H == 2 * gp:
+                self.call("pose_avgpool2x2_bwd_bf16", d.data_ptr(), Bn, H, W, cc, dfull.data_ptr())
+            else:
+                self.call("pose_adaptive_avgpool_bwd_bf16", d.data_ptr(), Bn, H, W, cc, gp, gp, dfull.data_ptr())
             d = dfull
         done(m.global_features[1].conv.weight)
         d = self.wasp_bwd(d)

@@ -235,6 +235,9 @@ int pose_channel_affine_bf16(const void *X, const float *mul, const void *add, i
 int pose_coord_pool_bf16(const void *X, int B, int H, int W, int C, void *P, pose_stream_t stream);
 int pose_coord_apply_bf16(const void *X, const void *G, int B, int H, int W, int C, void *Y, pose_stream_t stream);
 int pose_avgpool2x2_bf16(const void *X, int B, int H, int W, int C, void *Y, pose_stream_t stream);
+/* nn.AdaptiveAvgPool2d((OH, OW)) for any H >= OH, W >= OW (the reference default 500 x 500 input reaches the pool as a
+ * 32 x 32 map): window i = [floor(i H / OH), ceil((i + 1) H / OH)) */
+int pose_adaptive_avgpool_bf16(const void *X, int B, int H, int W, int C, int OH, int OW, void *Y, pose_stream_t stream);
 int pose_sums_to_bf16(const float *sums, int parts, int B, int C, float scale, void *out, pose_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -365,6 +368,7 @@ int pose_wasp_mix_bf16(const void *branches, int nb, const void *glob, const flo
 int pose_wasp_mix_bwd_bf16(const void *dOut, const void *branches, int nb, const void *glob, const float *raw_weights, int B,
                            long HW, int C, void *dbranches, float *dglob, float *dots, float *draw, pose_stream_t stream);
 int pose_avgpool2x2_bwd_bf16(const void *dY, int B, int H, int W, int C, void *dX, pose_stream_t stream);
+int pose_adaptive_avgpool_bwd_bf16(const void *dY, int B, int H, int W, int C, int OH, int OW, void *dX, pose_stream_t stream);
 int pose_scatter_strided_add_bf16(const void *dXs, int B, int Ho, int Wo, int H, int W, int C, int stride, void *dX,
                                   pose_stream_t stream);
 int pose_add_bf16(const void *a, const void *b, long n, void *out, pose_stream_t stream);

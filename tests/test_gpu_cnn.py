@@ -205,3 +205,67 @@ def test_cnn_full_size_matches_fp32_oracle(pose, B):
     assert torch.allclose(out3, out + 10.0, atol=1e-3)
     with pytest.raises(NotImplementedError), torch.no_grad():
         m.train()(img, dep, kp)            # batch statistics without a backward: eval() is the inference mode
+
+
+def test_cnn_reference_default_500x500_forward_and_training_step(pose):
+    """ModelConfig("cnn") defaults (src/model_config.py:59-66): 500 x 500 input, heat-map 500, AdaptiveAvgPool2d(8) from a
+    32 x 32 map (cnn.py:602).  Maps of 250 / 125 / 63 / 32 pixels: ragged implicit-GEMM patches, odd depthwise sizes, the
+    general adaptive pooling.  Eval forward within the 0.5 mm bar of the fp32 oracle; one training step: loss, every
+    parameter gradient against fp32 autograd (bf16 bars at batch 2: norm within 25 %, mean relative error no larger than
+    torch.autocast(bfloat16)'s on the same model)."""
+    from oracle import torch_models as tm
+    cfg = pose.ModelConfig("cnn", regression_dropout=0.0)
+    assert tuple(cfg.image_size) == (500, 500) and int(cfg.heatmap_size) == 500 and int(cfg.global_pool_size) == 8
+    m, sd = _load_filled(pose, cfg, 3)
+    sd = {k: v.to(DEV) for k, v in sd.items()}
+    B = 2
+    g = torch.Generator().manual_seed(77)
+    img, dep = torch.rand(B, 3, 500, 500, generator=g).to(DEV), torch.rand(B, 1, 500, 500, generator=g).to(DEV)
+    kp = (torch.rand(B, 17, 2, generator=g) * 0.9 + 0.05).to(DEV)
+    gt = (torch.randn(B, 17, 3, generator=g) * 300).to(DEV)
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            out = m(img, dep, kp)
+            ref = tm.cnn_forward(sd, cfg, img, dep, kp)
+        mpjpe = pose.utils.compute_mpjpe(out, ref).item()
+        print(f"500x500 CNN eval: MPJPE vs fp32 oracle {mpjpe:.4f} mm at joint magnitude {ref.norm(dim=2).mean().item():.1f} mm")
+        assert torch.isfinite(out).all() and mpjpe < 0.5, mpjpe
+        # training step
+        m.train()
+        crit = pose.ComprehensivePoseLoss()
+        pred = m(img, dep, kp)
+        total, _ = crit(pred, gt)
+        total.backward()
+        names = [n for n, _ in m.named_parameters()]
+        sdg = {k: (v.clone().requires_grad_() if k in names else v.clone()) for k, v in sd.items()}
+        po, _ = tm.cnn_forward(sdg, cfg, img, dep, kp, train=True, return_stats=True)
+        lref = tm.composite_loss(po, gt)
+        lref.backward()
+        # the same step under torch.autocast(bfloat16): the yardstick for what bf16 storage costs on this model
+        sda = {k: (v.clone().requires_grad_() if k in names else v.clone()) for k, v in sd.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            pa, _ = tm.cnn_forward(sda, cfg, img, dep, kp, train=True, return_stats=True)
+        tm.composite_loss(pa.float(), gt).backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert abs(total.item() - lref.item()) < 2e-2 * abs(lref.item()), (total.item(), lref.item())
+    gmax = max(sdg[n].grad.norm().item() for n in names)
+    errs, worst, norm_dev, auto = [], (0.0, None), (0.0, None), []
+    for n, p in m.named_parameters():
+        r = sdg[n].grad.double()
+        rn = r.norm().item()
+        if rn < 1e-5 * gmax:
+            continue                                     # analytically-zero gradients hold rounding noise
+        an = p.grad.double().norm().item()
+        norm_dev = max(norm_dev, (abs(an - rn) / rn, n))
+        e = (p.grad.double() - r).norm().item() / rn
+        errs.append(e)
+        auto.append((sda[n].grad.double() - r).norm().item() / rn)
+        worst = max(worst, (e, n))
+    mean_ours, mean_auto = sum(errs) / len(errs), sum(auto) / len(auto)
+    print(f"500x500 CNN train: mean relative gradient error {mean_ours:.4f} (autocast {mean_auto:.4f}), worst {worst}, "
+          f"worst norm deviation {norm_dev}")
+    assert norm_dev[0] < 0.25, norm_dev
+    assert mean_ours < mean_auto + 0.01, (mean_ours, mean_auto, worst)

@@ -182,27 +182,95 @@ def test_training_step_matches_fp32_autograd_and_the_reference(pose, golden):
     assert pose.utils.compute_mpjpe(p32, ref_pred).item() < 0.2              # fp32 oracle on this GPU == live reference
     mpjpe = pose.utils.compute_mpjpe(pred.detach(), p32).item()
     mpjpe16 = pose.utils.compute_mpjpe(p16, p32).item()
-    assert mpjpe < max(0.5, 1.5 * mpjpe16), (mpjpe, mpjpe16)
+    assert mpjpe < max(0.5, 1.0 * mpjpe16), (mpjpe, mpjpe16)       # at least as close to fp32 as torch.autocast(bfloat16)
     assert abs(total.item() - float(gd["loss"])) < 1e-2 * float(gd["loss"])
     gn_ref = dict(zip(list(gd["grad_names"]), gd["grad_norms"]))
     floor = 2e-6 * float(max(gd["grad_norms"]))      # analytically-zero gradients hold rounding noise (gen_golden.py)
-    ours, auto = [], []
+    ours, auto, dev, dev16 = [], [], [], []
     for n, p in m.named_parameters():
         r = g32[n]
         rn = r.norm().item()
         assert abs(rn - gn_ref[n]) <= 1e-2 * gn_ref[n] + floor, (n, rn, gn_ref[n])      # oracle == live reference
         an = p.grad.double().norm().item()
-        assert abs(an - rn) <= 0.15 * rn + 50 * floor, (n, an, rn)                      # every gradient has the right size
+        dev.append((abs(an - rn) / (rn + 50 * floor), n))
+        dev16.append(abs(g16[n].norm().item() - rn) / (rn + 50 * floor))
         ours.append(((p.grad.double() - r).norm().item() / (rn + 50 * floor), n))
         auto.append((g16[n] - r).norm().item() / (rn + 50 * floor))
     mean_ours, mean_auto = sum(r for r, _ in ours) / len(ours), sum(auto) / len(auto)
-    assert mean_ours < 1.25 * mean_auto + 0.01, (mean_ours, mean_auto, sorted(ours, reverse=True)[:8])
-    assert max(ours)[0] < 1.5 * max(auto) + 0.02, (sorted(ours, reverse=True)[:8], max(auto))
+    # every gradient has the right size: 1.6 % mean deviation of the norms (measured), worst parameter (an SE excitation
+    # weight behind 4 samples x 64 x 64 pixels of squeeze) no further out than autocast's worst
+    assert sum(d for d, _ in dev) / len(dev) < 0.03, sorted(dev, reverse=True)[:8]
+    assert max(dev)[0] < max(0.15, 1.1 * max(dev16)), (sorted(dev, reverse=True)[:8], max(dev16))
+    # and the right direction: mean relative error no larger than torch.autocast(bfloat16)'s
+    assert mean_ours < 1.0 * mean_auto + 0.005, (mean_ours, mean_auto, sorted(ours, reverse=True)[:8])
+    assert max(ours)[0] < 1.25 * max(auto) + 0.02, (sorted(ours, reverse=True)[:8], max(auto))
     # BatchNorm running statistics follow nn.BatchNorm2d (momentum 0.1, unbiased variance)
     after = m.state_dict()
     for k, v in new_stats.items():
         assert torch.allclose(after[k], v, rtol=2e-2, atol=2e-2), k
     assert int(after["conv1.0.norm.num_batches_tracked"]) == 1
+
+
+@pytest.mark.parametrize("B", [32, 128])
+def test_training_step_at_the_benchmark_batch_sizes(pose, B):
+    """BASELINE configs[2] runs batch 128 per GPU: the whole step (train-mode forward with batch statistics, composite loss,
+    backward) against the fp32 oracle's autograd on the same B200, next to torch.autocast(bfloat16) of the same model.
+    Bars: MPJPE and mean relative gradient error no larger than autocast's, gradient norms within 3 % on average."""
+    from oracle import torch_models as tm
+    torch.manual_seed(0)
+    cfg = pose.ModelConfig("cnn", image_size=(256, 256), heatmap_size=256, regression_dropout=0.0)
+    m = pose.CNNPoseEstimation(cfg)
+    sd = tm.fill_state_dict(m.state_dict(), seed=5)
+    m.load_state_dict(sd)
+    m = m.to(DEV).train()
+    sd = {k: v.to(DEV) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(100 + B)
+    img, dep = torch.rand(B, 3, 256, 256, generator=g).to(DEV), torch.rand(B, 1, 256, 256, generator=g).to(DEV)
+    kp = (torch.rand(B, 17, 2, generator=g) * 0.9 + 0.05).to(DEV)
+    gt = (torch.randn(B, 17, 3, generator=g) * 300).to(DEV)
+    pred = m(img, dep, kp)
+    total, _ = pose.ComprehensivePoseLoss()(pred, gt)
+    total.backward()
+    names = [n for n, _ in m.named_parameters()]
+
+    def oracle_step(autocast):
+        sdg = {k: (v.clone().requires_grad_() if k in names else v.clone()) for k, v in sd.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            po, _ = tm.cnn_forward(sdg, cfg, img, dep, kp, train=True, return_stats=True)
+        po = po.float()
+        loss = tm.composite_loss(po, gt)
+        loss.backward()
+        out = po.detach(), {n: sdg[n].grad.double() for n in names}, loss.item()
+        del sdg
+        return out
+
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        p32, g32, l32 = oracle_step(False)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    p16, g16, _ = oracle_step(True)
+    torch.cuda.empty_cache()
+    mpjpe = pose.utils.compute_mpjpe(pred.detach(), p32).item()
+    mpjpe16 = pose.utils.compute_mpjpe(p16, p32).item()
+    assert mpjpe < mpjpe16, (mpjpe, mpjpe16)
+    assert abs(total.item() - l32) < 1e-2 * l32, (total.item(), l32)
+    gmax = max(v.norm().item() for v in g32.values())
+    ours, auto, dev = [], [], []
+    for n, p in m.named_parameters():
+        r = g32[n]
+        rn = r.norm().item()
+        if rn < 1e-5 * gmax:
+            continue                 # analytically-zero gradients (a conv bias in front of a BatchNorm) hold rounding noise
+        ours.append(((p.grad.double() - r).norm().item() / rn, n))
+        auto.append((g16[n] - r).norm().item() / rn)
+        dev.append((abs(p.grad.double().norm().item() - rn) / rn, n))
+    mean_ours, mean_auto = sum(r for r, _ in ours) / len(ours), sum(auto) / len(auto)
+    print(f"CNN train B={B}: MPJPE {mpjpe:.2f} mm (autocast {mpjpe16:.2f}), mean gradient error {mean_ours:.4f} (autocast {mean_auto:.4f}), "
+          f"norm deviation mean {sum(d for d, _ in dev) / len(dev):.4f} max {max(dev)}")
+    assert mean_ours < mean_auto + 0.005, (mean_ours, mean_auto)
+    assert sum(d for d, _ in dev) / len(dev) < 0.03 and max(dev)[0] < 0.2, sorted(dev, reverse=True)[:6]
 
 
 def test_trainer_reduces_the_loss(pose, golden):
