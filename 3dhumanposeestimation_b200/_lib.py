@@ -140,6 +140,8 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     "pose_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_long, c_float, c_float, c_float,
                                 c_float, c_float, c_int, c_float, c_int, c_void_p]),
+    "pose_adamw_step_g16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_long, c_float, c_float,
+                                    c_float, c_float, c_float, c_int, c_float, c_int, c_void_p]),
 }
 
 _lib = None

@@ -332,13 +332,21 @@ cast_pad_kernel(const float *__restrict__ in, long ld_in, int cols, __nv_bfloat1
 // bf16 shadow weights the GEMMs read, and zeroing of the gradient for the next accumulation window.
 // 28 B/param of HBM traffic (+ 2 B for the shadow): 16 B loads, 16 + 2 B stores per 4 parameters x 4.
 // ---------------------------------------------------------------------------------------------------------
+template <bool G16>
 __global__ void __launch_bounds__(256)
-adamw_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-             __nv_bfloat16 *__restrict__ shadow, long n, float lr, float beta1, float beta2, float eps, float wd,
-             float bc1, float bc2_sqrt, float grad_scale, int zero_grad) {
+adamw_kernel(float *__restrict__ p, float *__restrict__ g, const __nv_bfloat16 *__restrict__ g16, float *__restrict__ m,
+             float *__restrict__ v, __nv_bfloat16 *__restrict__ shadow, long n, float lr, float beta1, float beta2, float eps,
+             float wd, float bc1, float bc2_sqrt, float grad_scale, int zero_grad) {
     const long n4 = n >> 2;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
-        float4 pp = ((float4 *)p)[i], gg = ((const float4 *)g)[i], mm = ((float4 *)m)[i], vv = ((float4 *)v)[i];
+        float4 pp = ((float4 *)p)[i], gg, mm = ((float4 *)m)[i], vv = ((float4 *)v)[i];
+        if (G16) {          // the all-reduced gradient arrives as bf16 (data-parallel exchange at half the wire bytes)
+            const uint2 pk = ((const uint2 *)g16)[i];
+            const float2 a = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.x), b = __bfloat1622float2(*(const __nv_bfloat162 *)&pk.y);
+            gg = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+            gg = ((const float4 *)g)[i];
+        }
         float *pa = (float *)&pp, *ga = (float *)&gg, *ma = (float *)&mm, *va = (float *)&vv;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -478,20 +486,41 @@ POSE_API int pose_token_slice_bf16(const void *src, int B, long T, long t_off, i
     return launch_status();
 }
 
-POSE_API int pose_adamw_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, void *shadow_bf16, long n,
-                             float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                             float grad_scale, int zero_grad, pose_stream_t stream) {
+static int adamw_launch(float *param, float *grad, const void *grad_bf16, float *exp_avg, float *exp_avg_sq, void *shadow_bf16, long n,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, int zero_grad,
+                        pose_stream_t stream) {
     if (!param || !grad || !exp_avg || !exp_avg_sq) return POSE_E_NULL;
     if (n <= 0 || n % 4 || step < 1) return POSE_E_SHAPE;
     if ((uintptr_t)param % 16 || (uintptr_t)grad % 16 || (uintptr_t)exp_avg % 16 || (uintptr_t)exp_avg_sq % 16 ||
-        (shadow_bf16 && (uintptr_t)shadow_bf16 % 8))
+        (shadow_bf16 && (uintptr_t)shadow_bf16 % 8) || (grad_bf16 && (uintptr_t)grad_bf16 % 8))
         return POSE_E_ALIGN;
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
-    adamw_kernel<<<grid_cap(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq,
-                                                                        (__nv_bfloat16 *)shadow_bf16, n, lr, beta1, beta2,
-                                                                        eps, weight_decay, bc1, bc2s, grad_scale, zero_grad);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (grad_bf16 != nullptr)
+        adamw_kernel<true><<<grid_cap(n / 4, 256), 256, 0, s>>>(param, grad, (const __nv_bfloat16 *)grad_bf16, exp_avg, exp_avg_sq,
+                                                                (__nv_bfloat16 *)shadow_bf16, n, lr, beta1, beta2, eps, weight_decay,
+                                                                bc1, bc2s, grad_scale, zero_grad);
+    else
+        adamw_kernel<false><<<grid_cap(n / 4, 256), 256, 0, s>>>(param, grad, nullptr, exp_avg, exp_avg_sq,
+                                                                 (__nv_bfloat16 *)shadow_bf16, n, lr, beta1, beta2, eps, weight_decay,
+                                                                 bc1, bc2s, grad_scale, zero_grad);
     return launch_status();
+}
+
+POSE_API int pose_adamw_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, void *shadow_bf16, long n,
+                             float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                             float grad_scale, int zero_grad, pose_stream_t stream) {
+    return adamw_launch(param, grad, nullptr, exp_avg, exp_avg_sq, shadow_bf16, n, lr, beta1, beta2, eps, weight_decay, step,
+                        grad_scale, zero_grad, stream);
+}
+
+POSE_API int pose_adamw_step_g16(float *param, float *grad, const void *grad_bf16, float *exp_avg, float *exp_avg_sq,
+                                 void *shadow_bf16, long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                 int step, float grad_scale, int zero_grad, pose_stream_t stream) {
+    if (!grad_bf16) return POSE_E_NULL;
+    return adamw_launch(param, grad, grad_bf16, exp_avg, exp_avg_sq, shadow_bf16, n, lr, beta1, beta2, eps, weight_decay, step,
+                        grad_scale, zero_grad, stream);
 }
 
 POSE_API int pose_cast_f32_bf16_2d(const float *in, long ld_in, long rows, int cols, void *out, long ld_out,

@@ -29,6 +29,7 @@ class AdamW(torch.optim.Optimizer):
         self._flat = None
         self._step = 0
         self.exp_avg = self.exp_avg_sq = None
+        self.grad16 = None     # set by Trainer (bf16 gradient exchange): the step reads the all-reduced bf16 gradient
 
     def _resolve(self):
         params = self.param_groups[0]["params"]
@@ -49,11 +50,15 @@ class AdamW(torch.optim.Optimizer):
         self._step += 1
         if not flat.grads_attached():
             raise RuntimeError("gradients are not views of the flat buffer: call backward() on a model output first")
-        code = _lib.lib().pose_adamw_step(flat.master.data_ptr(), flat.grad.data_ptr(), self.exp_avg.data_ptr(),
-                                          self.exp_avg_sq.data_ptr(), flat.shadow.data_ptr(), flat.numel, float(g["lr"]),
-                                          float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-                                          float(g["weight_decay"]), self._step, float(self.grad_scale), 1,
-                                          _lib.stream_ptr())
+        hyper = (flat.numel, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                 float(g["weight_decay"]), self._step, float(self.grad_scale), 1, _lib.stream_ptr())
+        if self.grad16 is not None:
+            code = _lib.lib().pose_adamw_step_g16(flat.master.data_ptr(), flat.grad.data_ptr(), self.grad16.data_ptr(),
+                                                  self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), flat.shadow.data_ptr(),
+                                                  *hyper)
+        else:
+            code = _lib.lib().pose_adamw_step(flat.master.data_ptr(), flat.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                              self.exp_avg_sq.data_ptr(), flat.shadow.data_ptr(), *hyper)
         _lib.check(code, "pose_adamw_step")
         flat.mark_shadow_current()
         flat.generation += 1          # the kernel wrote the parameters through raw pointers: _version did not move

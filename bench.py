@@ -63,7 +63,9 @@ def train_config(kind, world):
     return {"workload": f"{kind}_train",
             "model": "CNNPoseEstimation" if kind == "cnn" else "TransformerPoseEstimation (ViT-B/16 backbone)",
             "batch_per_gpu": spec["batch"], "global_batch": spec["batch"] * world, "image": [H, W],
-            "parallelism": f"dp{world}", "optimizer": "AdamW lr 1e-3 wd 0.01 (main.py:154-156), accumulation_steps 1",
+            "parallelism": f"dp{world}", "gradient_exchange": "none (1 GPU)" if world == 1 else
+            "all-reduce of the flat gradient in " + os.environ.get("POSE_GRAD_WIRE", "bf16") + " buckets of <= 64 MB, overlapped with backward",
+            "optimizer": "AdamW lr 1e-3 wd 0.01 (main.py:154-156), accumulation_steps 1",
             "step": "forward + ComprehensivePoseLoss + backward + AdamW (src/train.py:76-119), reference default "
                     "dropout rates, random init, synthetic 256x256 RGB-D batches",
             "l2": "activations of one step (GBs) exceed the 126 MB L2; inputs are re-read from HBM every step"}

@@ -302,6 +302,12 @@ int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V, const v
 int pose_adamw_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, void *shadow_bf16, long n, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, int zero_grad,
                     pose_stream_t stream);
+/* Data-parallel variant: the gradient is read from `grad_bf16` [n] (the bf16 copy of the flat gradient that went through
+ * the all-reduce: half the NVLink bytes of an fp32 exchange); `grad` (fp32, the buffer the backward pass accumulates
+ * into) is only cleared. */
+int pose_adamw_step_g16(float *param, float *grad, const void *grad_bf16, float *exp_avg, float *exp_avg_sq,
+                        void *shadow_bf16, long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        int step, float grad_scale, int zero_grad, pose_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * D/G. CNN training step                reference: loss.backward() over src/models/cnn.py (src/train.py:83-92)

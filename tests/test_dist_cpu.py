@@ -32,6 +32,10 @@ def _worker(rank, world, port, ret):
     want = torch.arange(1000, dtype=torch.float32) * (rank + 1)
     want[100:900] = torch.arange(100, 900, dtype=torch.float32) * 3          # 1x + 2x over the two ranks
     out["allreduce_ok"] = bool(torch.equal(grad, want))
+    # the bf16 wire format of the same exchange (Trainer(grad_wire="bf16")): small integers are exact in bf16
+    g16 = (torch.arange(1000, dtype=torch.float32) % 64 * (rank + 1)).bfloat16()
+    d.allreduce_range(g16, 0, 1000, 300)
+    out["allreduce_bf16_ok"] = bool(torch.equal(g16.float(), torch.arange(1000, dtype=torch.float32) % 64 * 3))
     ret[rank] = out
     dist.destroy_process_group()
 
@@ -48,6 +52,7 @@ def test_sharding_and_timing_reductions_world2():
     assert abs(r0["thr"] - 512.0 / 15e-3) < 1e-6          # all units / slowest rank
     assert r0["seed"] != r1["seed"]
     assert r0["allreduce_ok"] and r1["allreduce_ok"]
+    assert r0["allreduce_bf16_ok"] and r1["allreduce_bf16_ok"]
 
 
 def test_single_process_defaults():
