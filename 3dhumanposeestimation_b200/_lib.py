@@ -40,6 +40,12 @@ class PoseRepackEntry(C.Structure):
                 ("d2", C.c_int32), ("d3", C.c_int32), ("pad", C.c_int32)]
 
 
+class PoseStepState(C.Structure):
+    """Mirror of `pose_step_state` in include/pose_b200.h (lives in DEVICE memory; this mirror is for sizes / offsets)."""
+
+    _fields_ = [("drop_key", C.c_uint32), ("adam_step", C.c_int32), ("counter", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class PoseAugLaunch(C.Structure):
     """Mirror of `pose_aug_launch` in include/pose_b200.h."""
 
@@ -140,6 +146,8 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     "pose_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_long, c_float, c_float, c_float,
                                 c_float, c_float, c_int, c_float, c_int, c_void_p]),
+    "pose_step_state_bind": (c_int, [c_void_p]),
+    "pose_step_tick": (c_int, [c_void_p, c_void_p]),
     "pose_adamw_step_g16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_long, c_float, c_float,
                                     c_float, c_float, c_float, c_int, c_float, c_int, c_void_p]),
 }
@@ -161,6 +169,22 @@ def lib() -> C.CDLL:
             fn.argtypes = args
         _lib = handle
     return _lib
+
+
+_bound_state = None     # the device tensor (int32[4] = pose_step_state) currently bound, or None
+
+
+def bind_step_state(state) -> None:
+    """pose_step_state_bind: while bound, dropout keys and AdamW's step count come from device memory (CUDA-graph replay of
+    the training step).  The binding is a host-side pointer read when a kernel is launched (or captured)."""
+    global _bound_state
+    code = lib().pose_step_state_bind(state.data_ptr() if state is not None else None)
+    _bound_state = state
+    check(code, "pose_step_state_bind")
+
+
+def step_state_bound() -> bool:
+    return _bound_state is not None
 
 
 def check(code: int, what: str) -> None:

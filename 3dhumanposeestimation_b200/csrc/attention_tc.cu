@@ -130,6 +130,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
                    const __grid_constant__ CUtensorMap mapV, __nv_bfloat16 *__restrict__ O, float *__restrict__ lse, int Nq, int Nk,
                    int Nkp, long ldo, long bso, float scale, uint32_t drop_thresh, float drop_scale,
                    const DropSeed drop_seed) {
+    const uint32_t dkey = drop_thresh ? drop_key0(drop_seed) : 0u;     // per-launch dropout key (+ bound step state)
     constexpr int KC = kFwdKC, KB = KC * 128;
     unsigned char *smem;
     uint64_t *bar;
@@ -218,7 +219,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
                         p[j] = col < Nk ? ex2_approx(fmaf(__uint_as_float(v[j8 * 8 + j]), sl2, -ms)) : 0.f;
                         s4[j & 3] += p[j];
                         // attention-weight dropout (nn.MultiheadAttention(dropout=p)): the row still normalises by the full sum
-                        if (drop_thresh) p[j] = drop_keep32(drop_seed.key0, drop_row + col, drop_thresh) ? p[j] * drop_scale : 0.f;
+                        if (drop_thresh) p[j] = drop_keep32(dkey, drop_row + col, drop_thresh) ? p[j] * drop_scale : 0.f;
                     }
                     const int col8 = grp * 4 + j8;
                     if (col8 * 8 < n)
@@ -291,6 +292,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
                       __nv_bfloat16 *__restrict__ dQ, float *__restrict__ Dout, int Nq, int Nk, int Nkp, long ldo, long lddo,
                       long lddq, long bso, long bsdo, long bsdq, float scale, uint32_t drop_thresh, float drop_scale,
                       const DropSeed drop_seed) {
+    const uint32_t dkey = drop_thresh ? drop_key0(drop_seed) : 0u;     // per-launch dropout key (+ bound step state)
     constexpr int KC = kDqKC, KB = KC * 128;
     unsigned char *smem;
     uint64_t *bar;
@@ -392,7 +394,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
                         const int col = kc0 + sc * 32 + j8 * 8 + j;
                         const float pr = (col < Nk && row_ok) ? ex2_approx(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -l2)) : 0.f;
                         float dp = __uint_as_float(p[j8 * 8 + j]);
-                        if (drop_thresh) dp = drop_keep32(drop_seed.key0, drop_row + col, drop_thresh) ? dp * drop_scale : 0.f;
+                        if (drop_thresh) dp = drop_keep32(dkey, drop_row + col, drop_thresh) ? dp * drop_scale : 0.f;
                         ds[j] = pr * (dp - Dr) * scale;
                     }
                     const int col8 = sc * 4 + j8;
@@ -449,6 +451,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
                        const float *__restrict__ lse, const float *__restrict__ Dg, __nv_bfloat16 *__restrict__ dK,
                        __nv_bfloat16 *__restrict__ dV, int Nq, int Nk, long lddk, long lddv, long bsdk, long bsdv, float scale,
                        uint32_t drop_thresh, float drop_scale, const DropSeed drop_seed) {
+    const uint32_t dkey = drop_thresh ? drop_key0(drop_seed) : 0u;     // per-launch dropout key (+ bound step state)
     constexpr int QT = kDkvQT, QB = QT * 128;             // query rows per tile, bytes of one tile image
     unsigned char *smem;
     uint64_t *bar;
@@ -532,7 +535,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
                     const int col = c * 32 + j8 * 8 + j;                  // query within the tile
                     const float pr = col < rows ? ex2_approx(fmaf(__uint_as_float(s[j8 * 8 + j]), sl2, -lse_s[col])) : 0.f;
                     float keep = 1.0f;
-                    if (drop_thresh) keep = drop_keep32(drop_seed.key0, drop_col + (unsigned)(col * Nk), drop_thresh) ? drop_scale : 0.f;
+                    if (drop_thresh) keep = drop_keep32(dkey, drop_col + (unsigned)(col * Nk), drop_thresh) ? drop_scale : 0.f;
                     pv[j] = pr * keep;                                    // dV sees the dropped probabilities
                     ds[j] = pr * (__uint_as_float(p[j8 * 8 + j]) * keep - D_s[col]) * scale;
                 }

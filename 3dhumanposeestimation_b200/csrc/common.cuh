@@ -48,14 +48,21 @@ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
 struct DropSeed {
     unsigned long long s;      // seed * golden ratio
     uint32_t key0;             // mix32(s): the key of elements below 2^32
+    const uint32_t *step_key;  // device word XORed into every key, or null (pose_step_state_bind: the per-step part of the
+                               // seed lives in device memory so that a captured CUDA graph of the step can be replayed)
 };
+// abi.cu: the bound per-step state (device pointer) or null
+extern pose_step_state *g_step_state;
 inline DropSeed make_drop_seed(unsigned long long seed) {
     DropSeed d;
     d.s = seed * 0x9E3779B97F4A7C15ULL;
     d.key0 = mix32(d.s);
+    d.step_key = g_step_state ? &g_step_state->drop_key : nullptr;
     return d;
 }
-__device__ __forceinline__ uint32_t drop_key(const DropSeed &d, uint32_t hi) { return hi ? mix32(d.s + hi) : d.key0; }
+// key of the elements below 2^32 for this launch (one load per thread when a step state is bound)
+__device__ __forceinline__ uint32_t drop_key0(const DropSeed &d) { return d.step_key ? (d.key0 ^ __ldg(d.step_key)) : d.key0; }
+__device__ __forceinline__ uint32_t drop_key(const DropSeed &d, uint32_t hi) { return hi ? (mix32(d.s + hi) ^ (drop_key0(d) ^ d.key0)) : drop_key0(d); }
 // element `lo` (< 2^32) under a key: branch-free, 2 multiplies -- the form the fused kernels use (their hosts reject
 // tensors of 2^32 elements or more, so the key is always DropSeed::key0)
 __device__ __forceinline__ bool drop_keep32(uint32_t key, uint32_t lo, uint32_t thresh) { return lowbias32(lo ^ key) >= thresh; }

@@ -221,6 +221,7 @@ template <int ACT, int kPitch>
 __device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, long row, int lane, int col,
                                               int N, uint32_t wstat) {
     const int sub_r = lane >> 3, colq = (lane & 7) * 4;
+    const uint32_t dkey = ep.drop_thresh ? drop_key0(ep.drop_seed) : 0u;
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);   // column statistics (ACT 0 only)
     float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ep.bias != nullptr) bz = __ldg((const float4 *)(ep.bias + col));
@@ -239,10 +240,10 @@ __device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, 
             x.z *= act_grad<ACT>(u1.x) * ep.out_scale; x.w *= act_grad<ACT>(u1.y) * ep.out_scale;
             if (ep.drop_thresh) {     // the forward dropped act(u): the same mask gates the gradient
                 const uint32_t i0 = (uint32_t)(grow * ep.ldc + col);   // < 2^32 (host check)
-                x.x = drop_keep32(ep.drop_seed.key0, i0, ep.drop_thresh) ? x.x * ep.drop_scale : 0.f;
-                x.y = drop_keep32(ep.drop_seed.key0, i0 + 1, ep.drop_thresh) ? x.y * ep.drop_scale : 0.f;
-                x.z = drop_keep32(ep.drop_seed.key0, i0 + 2, ep.drop_thresh) ? x.z * ep.drop_scale : 0.f;
-                x.w = drop_keep32(ep.drop_seed.key0, i0 + 3, ep.drop_thresh) ? x.w * ep.drop_scale : 0.f;
+                x.x = drop_keep32(dkey, i0, ep.drop_thresh) ? x.x * ep.drop_scale : 0.f;
+                x.y = drop_keep32(dkey, i0 + 1, ep.drop_thresh) ? x.y * ep.drop_scale : 0.f;
+                x.z = drop_keep32(dkey, i0 + 2, ep.drop_thresh) ? x.z * ep.drop_scale : 0.f;
+                x.w = drop_keep32(dkey, i0 + 3, ep.drop_thresh) ? x.w * ep.drop_scale : 0.f;
             }
         } else {
             x.x += bz.x; x.y += bz.y; x.z += bz.z; x.w += bz.w;
@@ -262,10 +263,10 @@ __device__ __forceinline__ void epilogue_rows(uint32_t stg, const Epilogue &ep, 
             }
             if (ep.drop_thresh) {
                 const uint32_t i0 = (uint32_t)(grow * ep.ldc + col);   // < 2^32 (host check)
-                x.x = drop_keep32(ep.drop_seed.key0, i0, ep.drop_thresh) ? x.x * ep.drop_scale : 0.f;
-                x.y = drop_keep32(ep.drop_seed.key0, i0 + 1, ep.drop_thresh) ? x.y * ep.drop_scale : 0.f;
-                x.z = drop_keep32(ep.drop_seed.key0, i0 + 2, ep.drop_thresh) ? x.z * ep.drop_scale : 0.f;
-                x.w = drop_keep32(ep.drop_seed.key0, i0 + 3, ep.drop_thresh) ? x.w * ep.drop_scale : 0.f;
+                x.x = drop_keep32(dkey, i0, ep.drop_thresh) ? x.x * ep.drop_scale : 0.f;
+                x.y = drop_keep32(dkey, i0 + 1, ep.drop_thresh) ? x.y * ep.drop_scale : 0.f;
+                x.z = drop_keep32(dkey, i0 + 2, ep.drop_thresh) ? x.z * ep.drop_scale : 0.f;
+                x.w = drop_keep32(dkey, i0 + 3, ep.drop_thresh) ? x.w * ep.drop_scale : 0.f;
             }
             if (ep.residual != nullptr) {
                 const uint2 pk = __ldg((const uint2 *)(ep.residual + grow * ep.ldr + col));
@@ -311,6 +312,7 @@ __device__ __forceinline__ void epilogue_rows_slow(uint32_t stg, const Epilogue 
     // (inlined so that `ep` stays in the constant bank -- taking its address would spill it to local memory --
     //  but with rolled loops: this path only runs for ragged / unaligned edges)
     const int sub_r = lane >> 3, colq = (lane & 7) * 4;
+    const uint32_t dkey = ep.drop_thresh ? drop_key0(ep.drop_seed) : 0u;
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
         const int tr = g * 4 + sub_r;
@@ -324,7 +326,7 @@ __device__ __forceinline__ void epilogue_rows_slow(uint32_t stg, const Epilogue 
                 const float u = __bfloat162float(ep.residual[grow * ep.ldr + col + q]);
                 y *= (ep.act == 5 ? act_grad<5>(u) : (ep.act == 6 ? act_grad<6>(u) : act_grad<7>(u))) * ep.out_scale;
                 if (ep.drop_thresh)
-                    y = drop_keep32(ep.drop_seed.key0, (uint32_t)(grow * ep.ldc + col + q), ep.drop_thresh) ? y * ep.drop_scale : 0.f;
+                    y = drop_keep32(dkey, (uint32_t)(grow * ep.ldc + col + q), ep.drop_thresh) ? y * ep.drop_scale : 0.f;
             } else {
                 if (ep.bias != nullptr) y += __ldg(ep.bias + col + q);
                 float gq = 1.f;
@@ -338,7 +340,7 @@ __device__ __forceinline__ void epilogue_rows_slow(uint32_t stg, const Epilogue 
                 if (ep.preact != nullptr) ep.preact[grow * ep.ldc + col + q] = __float2bfloat16_rn(gq);
                 y *= ep.out_scale;
                 if (ep.drop_thresh)
-                    y = drop_keep32(ep.drop_seed.key0, (uint32_t)(grow * ep.ldc + col + q), ep.drop_thresh) ? y * ep.drop_scale : 0.f;
+                    y = drop_keep32(dkey, (uint32_t)(grow * ep.ldc + col + q), ep.drop_thresh) ? y * ep.drop_scale : 0.f;
                 if (ep.residual != nullptr) y += __bfloat162float(ep.residual[grow * ep.ldr + col + q]) * ep.res_scale;
             }
             if (ep.accumulate) atomicAdd((float *)ep.C + grow * ep.ldc + col + q, y);
@@ -379,6 +381,7 @@ __device__ __forceinline__ void epilogue_tma(uint32_t tmem_chunk, uint64_t *acc_
                                              uint32_t aux_stg, uint64_t *auxbar, uint32_t &aux_phase, long row0, int lane,
                                              int col0) {
     const long grow = row0 + lane;
+    const uint32_t dkey = ep.drop_thresh ? drop_key0(ep.drop_seed) : 0u;
     if (ep.residual != nullptr) {
         mbar_wait(auxbar, aux_phase);
         aux_phase ^= 1;
@@ -436,8 +439,8 @@ __device__ __forceinline__ void epilogue_tma(uint32_t tmem_chunk, uint64_t *acc_
             const uint32_t i0 = (uint32_t)(grow * ep.ldc + col0 + c * 8);   // < 2^32 (host check)
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {            // mask pair, one packed multiply
-                const float2 mk = make_float2(drop_keep32(ep.drop_seed.key0, i0 + j, ep.drop_thresh) ? ep.drop_scale : 0.f,
-                                              drop_keep32(ep.drop_seed.key0, i0 + j + 1, ep.drop_thresh) ? ep.drop_scale : 0.f);
+                const float2 mk = make_float2(drop_keep32(dkey, i0 + j, ep.drop_thresh) ? ep.drop_scale : 0.f,
+                                              drop_keep32(dkey, i0 + j + 1, ep.drop_thresh) ? ep.drop_scale : 0.f);
                 const float2 y = __fmul2_rn(make_float2(x[j], x[j + 1]), mk);
                 x[j] = y.x; x[j + 1] = y.y;
             }

@@ -336,7 +336,12 @@ template <bool G16>
 __global__ void __launch_bounds__(256)
 adamw_kernel(float *__restrict__ p, float *__restrict__ g, const __nv_bfloat16 *__restrict__ g16, float *__restrict__ m,
              float *__restrict__ v, __nv_bfloat16 *__restrict__ shadow, long n, float lr, float beta1, float beta2, float eps,
-             float wd, float bc1, float bc2_sqrt, float grad_scale, int zero_grad) {
+             float wd, float bc1, float bc2_sqrt, float grad_scale, int zero_grad, const int *__restrict__ step_dev) {
+    if (step_dev != nullptr) {      // step count from the bound pose_step_state (CUDA-graph replay): bias corrections here
+        const float st = (float)__ldg(step_dev);
+        bc1 = 1.0f - powf(beta1, st);
+        bc2_sqrt = sqrtf(1.0f - powf(beta2, st));
+    }
     const long n4 = n >> 2;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         float4 pp = ((float4 *)p)[i], gg, mm = ((float4 *)m)[i], vv = ((float4 *)v)[i];
@@ -490,7 +495,13 @@ static int adamw_launch(float *param, float *grad, const void *grad_bf16, float 
                         float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, int zero_grad,
                         pose_stream_t stream) {
     if (!param || !grad || !exp_avg || !exp_avg_sq) return POSE_E_NULL;
-    if (n <= 0 || n % 4 || step < 1) return POSE_E_SHAPE;
+    if (n <= 0 || n % 4 || step < 0) return POSE_E_SHAPE;
+    const int *step_dev = nullptr;
+    if (step == 0) {                 // the step count lives in the bound per-step state
+        if (!g_step_state) return POSE_E_SHAPE;
+        step_dev = &g_step_state->adam_step;
+        step = 1;
+    }
     if ((uintptr_t)param % 16 || (uintptr_t)grad % 16 || (uintptr_t)exp_avg % 16 || (uintptr_t)exp_avg_sq % 16 ||
         (shadow_bf16 && (uintptr_t)shadow_bf16 % 8) || (grad_bf16 && (uintptr_t)grad_bf16 % 8))
         return POSE_E_ALIGN;
@@ -500,11 +511,11 @@ static int adamw_launch(float *param, float *grad, const void *grad_bf16, float 
     if (grad_bf16 != nullptr)
         adamw_kernel<true><<<grid_cap(n / 4, 256), 256, 0, s>>>(param, grad, (const __nv_bfloat16 *)grad_bf16, exp_avg, exp_avg_sq,
                                                                 (__nv_bfloat16 *)shadow_bf16, n, lr, beta1, beta2, eps, weight_decay,
-                                                                bc1, bc2s, grad_scale, zero_grad);
+                                                                bc1, bc2s, grad_scale, zero_grad, step_dev);
     else
         adamw_kernel<false><<<grid_cap(n / 4, 256), 256, 0, s>>>(param, grad, nullptr, exp_avg, exp_avg_sq,
                                                                  (__nv_bfloat16 *)shadow_bf16, n, lr, beta1, beta2, eps, weight_decay,
-                                                                 bc1, bc2s, grad_scale, zero_grad);
+                                                                 bc1, bc2s, grad_scale, zero_grad, step_dev);
     return launch_status();
 }
 

@@ -128,6 +128,11 @@ class CnnTrainPlan:
             self.bufs[name] = t
         return t
 
+    def _seed(self, site):
+        """Dropout seed of a head layer: the step count is part of it unless a pose_step_state is bound (then the per-step
+        part lives in device memory and the seed is constant, so the captured step can be replayed)."""
+        return site + 1 if _lib.step_state_bound() else self.step_count * 16 + site
+
     def call(self, name, *args):
         # the stream handle is looked up once per forward / backward (a property chain in torch, ~3 us: it was the largest
         # single item of the per-launch host cost of a step with 500-600 launches)
@@ -662,7 +667,7 @@ class CnnTrainPlan:
             h = out
             if not last and self.drop_p > 0.0:
                 hd = self.buf(f"head{i}.drop", Bn, n_out)
-                self.call("pose_dropout_bf16", h.data_ptr(), h.numel(), self.drop_p, self.step_count * 16 + i, hd.data_ptr())
+                self.call("pose_dropout_bf16", h.data_ptr(), h.numel(), self.drop_p, self._seed(i), hd.data_ptr())
                 h = hd
         self.lins = lins
         if self.bn_tracked:
@@ -706,7 +711,7 @@ class CnnTrainPlan:
             e = self._epi(dx, n_i, act=ACT_GRAD[self.act] if u is not None else 0, residual=u, ldr=n_i)
             self.gemm_tr(dy.data_ptr(), ld, 0, flat.w16(lin.weight).data_ptr(), n_i, 1, Bn, n_i, n_o, e)
             if i > 0 and self.drop_p > 0.0:     # dropout mask of the forward (same seed); commutes with act'
-                self.call("pose_dropout_bf16", dx.data_ptr(), dx.numel(), self.drop_p, self.step_count * 16 + i - 1, dx.data_ptr())
+                self.call("pose_dropout_bf16", dx.data_ptr(), dx.numel(), self.drop_p, self._seed(i - 1), dx.data_ptr())
             dy, ld = dx, n_i
         done(lins[0].weight)
         # ECABlock + AdaptiveAvgPool2d(1): feat = mean * gate

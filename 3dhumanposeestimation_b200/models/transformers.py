@@ -300,7 +300,8 @@ class VitPlan:
         idx = self.seeds.get(site)
         if idx is None:
             idx = self.seeds[site] = len(self.seeds) + 1
-        return self.step_count * 4096 + idx
+        # with a bound pose_step_state the per-step part of the seed lives in device memory (graph replay)
+        return idx if _lib.step_state_bound() else self.step_count * 4096 + idx
 
     def drop(self, site, p):
         """(p, seed) for a dropout site, or None when dropout is off (eval mode / p = 0)."""

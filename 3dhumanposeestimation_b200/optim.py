@@ -30,6 +30,7 @@ class AdamW(torch.optim.Optimizer):
         self._step = 0
         self.exp_avg = self.exp_avg_sq = None
         self.grad16 = None     # set by Trainer (bf16 gradient exchange): the step reads the all-reduced bf16 gradient
+        self.device_step = False   # set by Trainer (graph replay): the kernel reads the step count from the bound pose_step_state
 
     def _resolve(self):
         params = self.param_groups[0]["params"]
@@ -51,7 +52,8 @@ class AdamW(torch.optim.Optimizer):
         if not flat.grads_attached():
             raise RuntimeError("gradients are not views of the flat buffer: call backward() on a model output first")
         hyper = (flat.numel, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-                 float(g["weight_decay"]), self._step, float(self.grad_scale), 1, _lib.stream_ptr())
+                 float(g["weight_decay"]), 0 if self.device_step else self._step, float(self.grad_scale), 1,
+                 _lib.stream_ptr())
         if self.grad16 is not None:
             code = _lib.lib().pose_adamw_step_g16(flat.master.data_ptr(), flat.grad.data_ptr(), self.grad16.data_ptr(),
                                                   self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), flat.shadow.data_ptr(),
@@ -60,8 +62,8 @@ class AdamW(torch.optim.Optimizer):
             code = _lib.lib().pose_adamw_step(flat.master.data_ptr(), flat.grad.data_ptr(), self.exp_avg.data_ptr(),
                                               self.exp_avg_sq.data_ptr(), flat.shadow.data_ptr(), *hyper)
         _lib.check(code, "pose_adamw_step")
-        flat.mark_shadow_current()
         flat.generation += 1          # the kernel wrote the parameters through raw pointers: _version did not move
+        flat.mark_shadow_current()    # ... and refreshed the bf16 shadow itself
         return loss
 
     # ---- checkpointing: torch.optim.AdamW's per-parameter layout (src/train.py:300-306, main.py:130-134) ----------

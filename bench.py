@@ -284,12 +284,14 @@ def step_roofline(pose, tr, plan, d, spec, world, value, pk):
     GB/s against the measured peaks.  The top-level fraction is the whole step's nominal training FLOPs over step time."""
     import torch
     trace_mod = importlib.import_module("3dhumanposeestimation_b200.trace")
+    graph_mode, tr.use_graph = tr.use_graph, False      # the traced step is launched kernel by kernel (events around each)
     with trace_mod.PlanTrace(plan) as t:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         tr.step(d["image"], d["depth"], d["kp"], d["gt"])
         e1.record()
         fam, ent = t.summary()
+    tr.use_graph = graph_mode
     traced_ms = e0.elapsed_time(e1)
     kern_ms = sum(v["ms"] for v in fam.values())
     groups = {}

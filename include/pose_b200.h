@@ -294,10 +294,27 @@ int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V, const v
                             float drop_p, uint64_t drop_seed, pose_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * G'. device-resident per-step state: what changes from one training step to the next -- the dropout stream and AdamW's
+ *    step count (bias correction) -- read from device memory, so that the whole step (src/train.py:76-119) can be captured
+ *    ONCE as a CUDA graph and replayed.  pose_step_tick (one thread) advances it at the start of a step: ++counter,
+ *    drop_key = hash(counter), ++adam_step.  While a state is bound (host-side, process-wide; NULL unbinds), every dropout
+ *    mask key becomes key(seed) ^ drop_key and pose_adamw_step[_g16] with step == 0 takes the step count from adam_step.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pose_step_state {
+    uint32_t drop_key;
+    int32_t adam_step;
+    uint32_t counter;
+    uint32_t reserved;
+} pose_step_state;
+int pose_step_state_bind(pose_step_state *dev_state);
+int pose_step_tick(pose_step_state *dev_state, pose_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * G. optimizer step                       reference: torch.optim.AdamW(lr 1e-3, weight_decay 0.01), main.py:154-156,
  *    src/train.py:117-119.  One launch over a flat fp32 parameter buffer (n % 4 == 0): p, exp_avg, exp_avg_sq updated
  *    in place from grad * grad_scale; shadow_bf16 (optional) receives the bf16 copy of the new parameters (the GEMM
- *    operands); zero_grad = 1 clears grad for the next accumulation window (optimizer.zero_grad()).
+ *    operands); zero_grad = 1 clears grad for the next accumulation window (optimizer.zero_grad()).  step >= 1, or 0 =
+ *    the bound pose_step_state's adam_step (G').
  * ------------------------------------------------------------------------------------------- */
 int pose_adamw_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, void *shadow_bf16, long n, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, int zero_grad,

@@ -86,3 +86,61 @@ def test_data_parallel_step_equals_accumulated_micro_batches(pose, tmp_path, kin
     for step in range(2):
         assert abs(r0["losses"][step] - ref_losses[step][0]) < 2e-2 * abs(ref_losses[step][0])
         assert abs(r1["losses"][step] - ref_losses[step][1]) < 2e-2 * abs(ref_losses[step][1])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CUDA-graph replay of the training step (one launch per step) against eager launches of the same step
+@pytest.mark.parametrize("kind", ["cnn", "vit"])
+def test_graph_replayed_step_matches_eager_launches(pose, kind):
+    """Trainer(graph=True): two eager steps, capture, replays -- against an eager Trainer on the same batches.  AdamW's
+    first steps move every weight by ~lr whatever the gradient's size, so two free-running trajectories drift apart on the
+    reordered fp32 sums of the split-K atomics alone; the graph trainer is therefore re-synchronised to the eager one after
+    every step and each step is compared on its own: same loss (the forward kernels are deterministic), same parameter
+    update (bias correction from the device-resident step count), and the optimizer state reports the right step."""
+    train = importlib.import_module("3dhumanposeestimation_b200.train")
+    batches = [_shard(r) for r in range(3)]
+    me, mg = _build(pose, kind), _build(pose, kind)
+    te = train.Trainer(me, pose.ComprehensivePoseLoss(), lr=1e-3, weight_decay=0.01, graph=False)
+    tg = train.Trainer(mg, pose.ComprehensivePoseLoss(), lr=1e-3, weight_decay=0.01, graph=True)
+    fe, fg = pose.params.FlatParams.of(me.parameters()), pose.params.FlatParams.of(mg.parameters())
+    for i in range(6):
+        before = fe.master.clone()
+        le = te.step(*batches[i % 3])[4].item()
+        lg = tg.step(*batches[i % 3])[4].item()
+        assert abs(le - lg) <= 1e-5 * abs(le), (i, le, lg)
+        moved = (fe.master - before).abs().sum().item()
+        diff = (fe.master - fg.master).abs().sum().item()
+        assert diff < 0.1 * moved, (i, diff, moved)
+        # re-synchronise: parameters, bf16 shadow, AdamW moments
+        fg.master.copy_(fe.master)
+        fg.refresh_shadow(force=True)
+        tg.opt.exp_avg.copy_(te.opt.exp_avg)
+        tg.opt.exp_avg_sq.copy_(te.opt.exp_avg_sq)
+    assert "graph" in tg.launch_mode() and "eager" in te.launch_mode()
+    assert te.opt.state_dict()["state"][0]["step"].item() == tg.opt.state_dict()["state"][0]["step"].item() == 6.0
+
+
+def test_graph_replay_draws_a_new_dropout_mask_every_step(pose):
+    """The dropout key lives in device memory (pose_step_state) and is advanced by the tick inside the graph: with frozen
+    parameters (lr = 0) and identical inputs, replays give different losses with the reference dropout rates and identical
+    ones without dropout."""
+    train = importlib.import_module("3dhumanposeestimation_b200.train")
+    from oracle import torch_models as tm
+    for rates, differ in ((dict(), True), (dict(transformer_dropout_rate=0.0, transformer_attention_dropout_rate=0.0,
+                                                regression_dropout=0.0), False)):
+        cfg = pose.ModelConfig("transformer", image_size=(256, 256), vit_pretrained=False, **rates)
+        m = pose.TransformerPoseEstimation(cfg)
+        m.load_state_dict(tm.fill_vit_state_dict(m.state_dict(), seed=7))
+        m = m.to("cuda").train()
+        tr = train.Trainer(m, pose.ComprehensivePoseLoss(), lr=0.0, weight_decay=0.0, graph=True)
+        b = _shard(0)
+        losses = [tr.step(*b)[4].item() for _ in range(6)]
+        assert "graph" in tr.launch_mode()
+        replayed = losses[3:]
+        if differ:
+            assert len(set(replayed)) == len(replayed), losses
+            assert max(replayed) - min(replayed) < 0.05 * abs(replayed[0]), losses       # same distribution, different masks
+        else:
+            assert len(set(losses)) == 1, losses
+        del tr, m
+        torch.cuda.empty_cache()
