@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..utils import activation_id, get_activation
+from ..utils import GraphedForward, activation_id, get_activation
 from .common import GaussianHeatmapGenerator, PoseRegressionHead
 
 
@@ -270,6 +270,7 @@ class CnnInferencePlan:
         self.keep = []       # tensors that must stay alive
         self._version = None
         self._tracked = None
+        self._graphed = None
         self.last_epi = None
         self.launches = 0
         self._build()
@@ -581,15 +582,29 @@ class CnnInferencePlan:
         Bn, S = self.B, self.S
         if tuple(image.shape) != (Bn, 3, S, S) or tuple(depth.shape) != (Bn, 1, S, S) or tuple(kp.shape) != (Bn, self.J, 2):
             raise ValueError(f"expected image [{Bn},3,{S},{S}], depth [{Bn},1,{S},{S}], keypoints [{Bn},{self.J},2]")
+        if Bn <= GraphedForward.MAX_BATCH:
+            # small batches are launch bound: the forward is replayed from one CUDA graph (weights are refreshed in place,
+            # outside the graph, whenever a parameter changed)
+            if self._graphed is None:
+                self._graphed = GraphedForward(self._enqueue, prepare=self._refresh_weights)
+            return self._graphed(image, depth, kp).view(Bn, self.J, 3).clone()
+        return self._enqueue(image, depth, kp).view(Bn, self.J, 3).clone()
+
+    def _refresh_weights(self):
         v = self._param_version()
         if v != self._version:
             with torch.no_grad():
                 for rebuild in self.weights:
                     rebuild()
             self._version = v
+
+    def _enqueue(self, image, depth, kp):
+        Bn, S = self.B, self.S
+        if not torch.cuda.is_current_stream_capturing():
+            self._refresh_weights()
         _lib.check(self.lib.pose_cnn_input_pack(image.data_ptr(), depth.data_ptr(), kp.data_ptr(), Bn, S, self.J,
                                                 float(self.model.config.heatmap_sigma), self.x0.data_ptr(),
                                                 _lib.stream_ptr()), "pose_cnn_input_pack")
         for step in self.steps:
             step()
-        return self.out.view(Bn, self.J, 3).clone()
+        return self.out

@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..params import FlatParams
-from ..utils import activation_id, get_activation
+from ..utils import GraphedForward, activation_id, get_activation
 from .common import GaussianHeatmapGenerator
 
 _VIT_TABLE = {  # timm model name -> (embed_dim, depth, heads, patch)
@@ -224,8 +224,16 @@ class TransformerPoseEstimation(nn.Module):  # transformers.py:140-373
         plan = self.plan(image.shape[0], image.device)
         if self.training and torch.is_grad_enabled():
             return _VitTrainFn.apply(plan, image, depth, keypoints_2d, self.final_cls_token)
-        return plan.forward(image, depth, keypoints_2d, save=False,
-                            training=self.training).view(-1, self.config.num_joints, 3).clone()
+        if not self.training and image.shape[0] <= GraphedForward.MAX_BATCH:
+            # eval forward of a small batch: launch bound -> replayed from one CUDA graph (the bf16 shadow weights are
+            # refreshed outside the graph when a parameter changed in place)
+            if plan.graphed is None:
+                plan.graphed = GraphedForward(lambda i, d, k: plan.forward(i, d, k, save=False, training=False),
+                                              prepare=plan.flat.refresh_shadow)
+            out = plan.graphed(image, depth, keypoints_2d)
+        else:
+            out = plan.forward(image, depth, keypoints_2d, save=False, training=self.training)
+        return out.view(-1, self.config.num_joints, 3).clone()
 
 
 class _VitTrainFn(torch.autograd.Function):
@@ -252,6 +260,7 @@ class VitPlan:
         self.model, self.B, self.dev = model, B, device
         self.lib = _lib.lib()
         self._sp = None          # stream handle of the current forward / backward (see call)
+        self.graphed = None      # GraphedForward of the eval forward (small batches)
         c = model.config
         self.J = c.num_joints
         self.E = c.transformer_embed_dim

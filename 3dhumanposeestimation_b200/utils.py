@@ -58,3 +58,48 @@ def compute_mpjpe(predicted_joints, ground_truth_joints):
 def compute_pa_mpjpe(predicted_joints, ground_truth_joints):
     """Procrustes-aligned MPJPE (src/utils.py:72-165, including its rotation convention): 0-dim device tensor."""
     return eval_metrics(predicted_joints, ground_truth_joints)[0][1]
+
+
+class GraphedForward:
+    """Eval-mode forward of a launch plan replayed from ONE CUDA graph (run_inference, infer.py:383-393, runs batch 1: a
+    forward of ~200 launches of a few microseconds each is launch bound).  `fn(*static_inputs)` must enqueue the forward on
+    the current stream and return a tensor that stays valid (a plan buffer).  Two eager calls warm the plan (allocations,
+    kernel attributes), the third captures; `prepare()` runs before every replay for host-side work that must stay outside
+    the graph (refreshing folded weights after a parameter update).  POSE_INFER_GRAPH=0 disables it."""
+
+    MAX_BATCH = 8
+
+    def __init__(self, fn, prepare=None):
+        import os
+        self.fn, self.prepare = fn, prepare
+        self.calls, self.graph, self.static, self.out = 0, None, None, None
+        self.enabled = os.environ.get("POSE_INFER_GRAPH", "1") != "0"
+
+    def __call__(self, *inputs):
+        import torch
+        if not self.enabled or torch.cuda.is_current_stream_capturing():
+            return self.fn(*inputs)
+        self.calls += 1
+        if self.calls <= 2:
+            return self.fn(*inputs)
+        if self.prepare is not None:
+            self.prepare()
+        if self.graph is None:
+            self.static = [torch.empty_like(t) for t in inputs]
+            for s_, t in zip(self.static, inputs):
+                s_.copy_(t)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph):
+                    self.out = self.fn(*self.static)
+            except Exception:
+                self.enabled = False
+                torch.cuda.synchronize()
+                return self.fn(*inputs)
+            self.graph = graph
+        else:
+            for s_, t in zip(self.static, inputs):
+                s_.copy_(t)
+        self.graph.replay()
+        return self.out

@@ -8,6 +8,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--model", default="vit"); ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--steps", type=int, default=5); ap.add_argument("--profile", action="store_true")
 ap.add_argument("--warmup", type=int, default=3); ap.add_argument("--dropout0", action="store_true")
+ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
 a = ap.parse_args()
 dev = torch.device("cuda")
 torch.manual_seed(0)
@@ -28,10 +29,14 @@ for _ in range(a.warmup):
 torch.cuda.synchronize()
 print("loss", o5.tolist())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if a.cuda_profiler:
+    torch.cuda.cudart().cudaProfilerStart()
 t0 = time.perf_counter(); e0.record()
 for _ in range(a.steps):
     o5 = tr.step(img, dep, kp, gt)
 e1.record(); torch.cuda.synchronize()
+if a.cuda_profiler:
+    torch.cuda.cudart().cudaProfilerStop()
 ms = e0.elapsed_time(e1) / a.steps
 print(f"{a.model} B={B}: {ms:.2f} ms/step  {B / ms * 1e3:.1f} samples/s  wall {(time.perf_counter() - t0) / a.steps * 1e3:.2f} ms  loss {o5[4].item():.3f}")
 plan = model.plan(B, dev)
