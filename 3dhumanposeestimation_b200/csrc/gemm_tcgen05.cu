@@ -72,6 +72,7 @@ struct ConvGeom {          // MODE 1 only
     int stride, dil, pad;
     int cchunks;           // Cin_pad / BKC
     int tiles_w, tiles_h;  // ceil(Wo / TW), ceil(Ho / TH)
+    int cw;                // MODE 2: channels per B block (64: 128-byte pixels, SWIZZLE_128B; 32: 64-byte pixels, SWIZZLE_64B)
 };
 
 template <int BN, int kStages, int BKC, int TMA_EPI = 0>
@@ -645,14 +646,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         const int pimg = (t / tiles_h) * cg.TN, poh = th * cg.TH, pow_ = tw * cg.TW;
                         tma_load_4d(sa, &map_a, full + s, mt * BM, pow_, poh, pimg);
                         tma_load_4d(sa + 64 * 128, &map_a, full + s, mt * BM + 64, pow_, poh, pimg);
-#pragma unroll
-                        for (int j = 0; j < BN / 64; ++j) {
-                            const int jb = n0 / 64 + j;
+                        const int cw = cg.cw, nblk = BN / cw;             // B blocks of one tap x cw channels x 64 pixels
+                        for (int j = 0; j < nblk; ++j) {
+                            const int jb = n0 / cw + j;
                             const int tap = jb / cg.cchunks, cc = jb - tap * cg.cchunks;
                             const int kh = tap / cg.KW, kw = tap - kh * cg.KW;
                             // past the last tap: a box that is entirely out of bounds (zero filled, full byte count)
-                            const int c0 = tap < cg.taps ? cc * 64 : cg.cchunks * 64;
-                            tma_load_4d(sb + j * 64 * 128, &map_w, full + s, c0, pow_ * cg.stride + kw * cg.dil - cg.pad,
+                            const int c0 = tap < cg.taps ? cc * cw : cg.cchunks * cw;
+                            tma_load_4d(sb + j * 64 * cw * 2, &map_w, full + s, c0, pow_ * cg.stride + kw * cg.dil - cg.pad,
                                         poh * cg.stride + kh * cg.dil - cg.pad, pimg);
                         }
                     } else if (MODE == 0 && A_MN) {
@@ -697,10 +698,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + s * S::kStageBytes), sb = sa + S::kABytes;
                     const uint64_t da = A_MN ? umma_desc_mn(sa, BKC * 128) : umma_desc_k<BKC * 2>(sa);
-                    const uint64_t db = B_MN ? umma_desc_mn(sb, BKC * 128) : umma_desc_k<BKC * 2>(sb);
+                    const bool b32 = MODE == 2 && cg.cw == 32;          // 32-channel pixels: 64-byte rows, SWIZZLE_64B
+                    const uint64_t db = b32 ? umma_desc_mn_sw64(sb, 64 * 64)
+                                            : (B_MN ? umma_desc_mn(sb, BKC * 128) : umma_desc_k<BKC * 2>(sb));
                     // advancing K by 16: K-major = 32 B inside the swizzled row (+2 in the >>4 address field);
-                    // MN-major = 16 contraction rows of 128 B (+128)
-                    constexpr uint64_t ka = A_MN ? 128 : 2, kbs = B_MN ? 128 : 2;
+                    // MN-major = 16 contraction rows of 128 B (+128) or of 64 B (+64)
+                    constexpr uint64_t ka = A_MN ? 128 : 2;
+                    const uint64_t kbs = b32 ? 64 : (B_MN ? 128 : 2);
 #pragma unroll
                     for (int k = 0; k < BKC / UMMA_K; ++k) {
                         tc_mma_f16(tmem_acc, da + (uint64_t)k * ka, db + (uint64_t)k * kbs, idesc,
@@ -1236,7 +1240,7 @@ POSE_API int pose_conv2d_bf16(const void *X, int Nimg, int H, int Wd, int Cin, c
     e = make_map_nhwc(&ma, X, Nimg, H, Wd, Cin, bkc, TW, TH, TN, stride);
     if (e) return e;
     const int tiles_w = (Wo + TW - 1) / TW, tiles_h = (Ho + TH - 1) / TH;
-    ConvGeom cg = {Ho, Wo, TH, TW, TN, Nimg, KW, KH * KW, stride, dil, pad, Cin / bkc, tiles_w, tiles_h};
+    ConvGeom cg = {Ho, Wo, TH, TW, TN, Nimg, KW, KH * KW, stride, dil, pad, Cin / bkc, tiles_w, tiles_h, 64};
     const int m_tiles = ((Nimg + TN - 1) / TN) * tiles_h * tiles_w;
     const int M = Nimg * Ho * Wo;
     cudaStream_t s = (cudaStream_t)stream;
@@ -1250,7 +1254,9 @@ POSE_API int pose_conv2d_wgrad_bf16(const void *dY, const void *X, int Nimg, int
     if (!dY || !X || !dWk) return POSE_E_NULL;
     if (Nimg <= 0 || H <= 0 || Wd <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || stride <= 0 || dil <= 0 || pad < 0)
         return POSE_E_SHAPE;
-    if (Cin % 64 || Cout % 8) return POSE_E_UNSUPPORTED;       // 128-byte channel chunks (the training input is padded)
+    // channel chunks of 128 bytes, or 32-channel pixels (the 21-channel network input padded to 32: 64-byte rows)
+    const int cw = Cin % 64 == 0 ? 64 : (Cin == 32 ? 32 : 0);
+    if (!cw || Cout % 8) return POSE_E_UNSUPPORTED;
     if ((uintptr_t)dY % 16 || (uintptr_t)X % 16 || (uintptr_t)dWk % 16) return POSE_E_ALIGN;
     const int Ho = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1, Wo = (Wd + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
     int TW = 64;
@@ -1283,9 +1289,9 @@ POSE_API int pose_conv2d_wgrad_bf16(const void *dY, const void *X, int Nimg, int
     CUtensorMap ma, mw;
     e = make_map_nhwc(&ma, dY, Nimg, Ho, Wo, Cout, 64, TW, TH, TN, 1);
     if (e) return e;
-    e = make_map_nhwc(&mw, X, Nimg, H, Wd, Cin, 64, TW, TH, TN, stride);
+    e = make_map_nhwc(&mw, X, Nimg, H, Wd, Cin, cw, TW, TH, TN, stride);
     if (e) return e;
-    ConvGeom cg = {Ho, Wo, TH, TW, TN, Nimg, KW, KH * KW, stride, dil, pad, Cin / 64, tiles_w, tiles_h};
+    ConvGeom cg = {Ho, Wo, TH, TW, TN, Nimg, KW, KH * KW, stride, dil, pad, Cin / cw, tiles_w, tiles_h, cw};
     const int m_tiles = (M + BM - 1) / BM;
     return launch_gemm<128, 4, 64, 2, 1, 1>(ma, mw, M, N, K, ep, cg, m_tiles, (cudaStream_t)stream, k_splits);
 }

@@ -149,6 +149,17 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_by
     d |= (uint64_t)2 << 61;
     return d;
 }
+// MN-major operand whose rows hold 32 elements (64 B: a 32-channel NHWC pixel), SWIZZLE_64B: ((32, n), (8, k)) :
+// ((1, LBO), (32, SBO)) -- 8 contraction rows = one 512 B swizzle atom, the next 32 MN elements LBO bytes further
+__device__ __forceinline__ uint64_t umma_desc_mn_sw64(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
 // cute::UMMA::InstrDescriptor for kind::f16: D = F32, A = B = BF16; bit 15 / 16 = A / B is MN-major
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn = 0, int b_mn = 0) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |

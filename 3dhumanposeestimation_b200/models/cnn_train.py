@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..params import FlatParams
-from ..utils import activation_id
+from ..utils import split_k, activation_id
 
 
 def _ceil8(n):
@@ -86,7 +86,7 @@ class CnnTrainPlan:
                     self._repack.append((src, self._pk32_off + n9, 6, co, 0, 0, 0))     # flipped taps: data gradient
                     self._pk32_off += 2 * n9
                 elif kh > 1 or conv.stride[0] > 1:
-                    cp = (ci + 63) // 64 * 64
+                    cp = 32 if ci <= 32 else (ci + 63) // 64 * 64     # the 21-channel network input: 64-byte pixels
                     fwd = self._pk16_off
                     self._pk16_off += (co * kh * kw * cp + 63) // 64 * 64
                     bwd = None
@@ -168,9 +168,7 @@ class CnnTrainPlan:
 
     @staticmethod
     def _splits(n_out, n_in, rows):
-        tiles = ((n_out + 127) // 128) * ((n_in + 127) // 128)
-        kb = (rows + 63) // 64
-        return max(1, min((148 * 2 + tiles - 1) // tiles, kb // 4 if kb >= 4 else 1))
+        return split_k(((n_out + 127) // 128) * ((n_in + 127) // 128), (rows + 63) // 64)
 
     # ---- ConvBnAct ------------------------------------------------------------------------------------
     def cba_fwd(self, name, cba, x, shape, act="default", out=None, ld_out=None, col_off=0, residual=None, ld_res=0):
@@ -305,8 +303,7 @@ class CnnTrainPlan:
             _, fwd, bwd, cp, stage, ui = self.pk[name]
             st = self.wsbuf[stage:]
             tiles = ((co + 127) // 128) * ((kh * kh * cp + 127) // 128)
-            patches = M // 64
-            splits = max(1, min((148 * 2 + tiles - 1) // tiles, patches // 4 if patches >= 4 else 1))
+            splits = split_k(tiles, (M + 63) // 64)
             self.call("pose_conv2d_wgrad_bf16", dy.data_ptr(), x.data_ptr(), Bn, H, W, r["cin"], co, kh, kh, stride, dil, pad,
                       st.data_ptr(), splits)
             # the gradient was staged in KRSC order: add it into the [Co,Ci,K,K] .grad view
@@ -616,10 +613,11 @@ class CnnTrainPlan:
         self.wsbuf.zero_()
         self.refresh_params()
         self.step_count += 1
-        x0 = self.buf("x0", Bn, S, S, 64)          # channels 32..63 stay zero (128-byte chunks for the weight gradient)
+        c0p = self.pk["conv1.0"][3]                # 21 input channels padded to 32 (64-byte pixels)
+        x0 = self.buf("x0", Bn, S, S, c0p)
         self.call("pose_cnn_input_pack_ex", image.data_ptr(), depth.data_ptr(), kp.data_ptr(), Bn, S, self.J,
-                  float(c.heatmap_sigma), 64, x0.data_ptr())
-        x, s = self.cba_fwd("conv1.0", m.conv1[0], x0, (Bn, S, S, 64))
+                  float(c.heatmap_sigma), c0p, x0.data_ptr())
+        x, s = self.cba_fwd("conv1.0", m.conv1[0], x0, (Bn, S, S, c0p))
         x, s = self.cba_fwd("conv1.1", m.conv1[1], x, s)
         self.blocks = []
         for i, stage in enumerate(m.stages):

@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..params import FlatParams
-from ..utils import GraphedForward, activation_id, get_activation
+from ..utils import GraphedForward, split_k, activation_id, get_activation
 from .common import GaussianHeatmapGenerator
 
 _VIT_TABLE = {  # timm model name -> (embed_dim, depth, heads, patch)
@@ -491,9 +491,7 @@ class VitPlan:
 
     # ---- backward ops --------------------------------------------------------------------------------
     def _splits(self, n_out, n_in, m_rows):
-        tiles = ((n_out + 127) // 128) * ((n_in + 127) // 128)
-        kb = (m_rows + 63) // 64
-        return max(1, min((148 * 2 + tiles - 1) // tiles, kb // 4 if kb >= 4 else 1))
+        return split_k(((n_out + 127) // 128) * ((n_in + 127) // 128), (m_rows + 63) // 64)
 
     def drop_grad(self, name, d, site, p):
         """Gradient entering a dropout site: the forward's mask (same seed) applied to d -> a new buffer."""

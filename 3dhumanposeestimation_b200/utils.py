@@ -60,6 +60,20 @@ def compute_pa_mpjpe(predicted_joints, ground_truth_joints):
     return eval_metrics(predicted_joints, ground_truth_joints)[0][1]
 
 
+def split_k(tiles: int, kblocks: int, sms: int = 148, max_splits: int = 128) -> int:
+    """Split-K factor of a weight-gradient contraction: `tiles` output tiles, `kblocks` 64-row blocks of contraction.
+    Work items = tiles * splits run in rounds of one per SM; a count just above a multiple of the SM count wastes almost a
+    whole round (measured: conv1.1's weight gradient 949 us at 300 items, 664 us at 295), so the factor minimises
+    rounds x (blocks per item + a fixed per-item cost for the epilogue's atomics)."""
+    best, best_cost = 1, None
+    for s in range(1, max(1, min(max_splits, kblocks // 4)) + 1):
+        rounds = -(-tiles * s // sms)
+        cost = rounds * (-(-kblocks // s) + 8)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = s, cost
+    return best
+
+
 class GraphedForward:
     """Eval-mode forward of a launch plan replayed from ONE CUDA graph (run_inference, infer.py:383-393, runs batch 1: a
     forward of ~200 launches of a few microseconds each is launch bound).  `fn(*static_inputs)` must enqueue the forward on

@@ -54,7 +54,9 @@ def test_batchnorm_training_forward_backward(pose, M, Cc, act):
 
 
 @pytest.mark.parametrize("B,H,Cin,Cout,k,stride,dil", [
-    (2, 64, 64, 64, 5, 2, 1),      # conv1.0 (training operand padded to 64 channels)
+    (2, 64, 64, 64, 5, 2, 1),      # conv1.0 with the operand padded to 64 channels
+    (2, 64, 32, 64, 5, 2, 1),      # conv1.0 as trained: 21 input channels padded to 32 (64-byte pixels, SWIZZLE_64B operand)
+    (3, 32, 32, 64, 3, 1, 1),      # 32-channel pixels, 3 x 3
     (2, 64, 64, 64, 3, 1, 1),      # conv1.1
     (3, 16, 512, 512, 3, 1, 6),    # WASP dilated
     (2, 16, 128, 192, 3, 1, 18),   # dilation larger than the map
