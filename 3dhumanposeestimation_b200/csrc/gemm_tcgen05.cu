@@ -617,7 +617,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int split = item / mn_tiles, tile = item - split * mn_tiles;
                 const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
                 const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BN;
+                // Every index below advances incrementally: this single thread issues all loads of the CTA, and the runtime
+                // integer divisions that used to decode (tap, channel chunk) / (patch column, row, image) from the block
+                // number on every k-block were the critical path of the convolution kernels.
                 int img = 0, oh0 = 0, ow0 = 0;
+                int f_cc = 0, f_kw = 0, f_kh = 0;                       // MODE 1: channel chunk / filter tap of block kb
+                int p_tw = 0, p_th = 0, p_img = 0;                      // MODE 2: 64-pixel patch of block kb
+                int w_c0[4], w_dx[4], w_dy[4];                          // MODE 2: the B blocks of this column tile
                 if (MODE == 1) {
                     const int tiles_w = cg.tiles_w, tiles_h = cg.tiles_h;
                     int t = mt;
@@ -625,8 +631,30 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     t /= tiles_w;
                     const int th = t % tiles_h;
                     img = (t / tiles_h) * cg.TN;
-                    oh0 = th * cg.TH;
-                    ow0 = tw * cg.TW;
+                    oh0 = th * cg.TH * cg.stride - cg.pad;
+                    ow0 = tw * cg.TW * cg.stride - cg.pad;
+                    const int tap = kb0 / cg.cchunks;
+                    f_cc = kb0 - tap * cg.cchunks;
+                    f_kh = tap / cg.KW;
+                    f_kw = tap - f_kh * cg.KW;
+                }
+                if (MODE == 2) {
+                    int t = kb0;
+                    p_tw = t % cg.tiles_w;
+                    t /= cg.tiles_w;
+                    p_th = t % cg.tiles_h;
+                    p_img = (t / cg.tiles_h) * cg.TN;
+                    const int cw = cg.cw;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int jb = n0 / cw + j;
+                        const int tap = jb / cg.cchunks, cc = jb - tap * cg.cchunks;
+                        const int kh = tap / cg.KW, kw = tap - kh * cg.KW;
+                        // past the last tap: a box that is entirely out of bounds (zero filled, full byte count)
+                        w_c0[j] = tap < cg.taps ? cc * cw : cg.cchunks * cw;
+                        w_dx[j] = kw * cg.dil - cg.pad;
+                        w_dy[j] = kh * cg.dil - cg.pad;
+                    }
                 }
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % kStages;
@@ -636,25 +664,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     mbar_expect_tx(full + s, S::kStageBytes);
                     if (MODE == 2) {
                         // convolution weight gradient: the contraction block is a patch of 64 OUTPUT PIXELS; A = dY^T
-                        // (two boxes of 64 output channels), B = the input activation at one filter tap per 64-column
-                        // block (4-D boxes, zero fill outside the image = the convolution padding)
-                        const int tiles_w = cg.tiles_w, tiles_h = cg.tiles_h;
-                        int t = kb;
-                        const int tw = t % tiles_w;
-                        t /= tiles_w;
-                        const int th = t % tiles_h;
-                        const int pimg = (t / tiles_h) * cg.TN, poh = th * cg.TH, pow_ = tw * cg.TW;
-                        tma_load_4d(sa, &map_a, full + s, mt * BM, pow_, poh, pimg);
-                        tma_load_4d(sa + 64 * 128, &map_a, full + s, mt * BM + 64, pow_, poh, pimg);
-                        const int cw = cg.cw, nblk = BN / cw;             // B blocks of one tap x cw channels x 64 pixels
-                        for (int j = 0; j < nblk; ++j) {
-                            const int jb = n0 / cw + j;
-                            const int tap = jb / cg.cchunks, cc = jb - tap * cg.cchunks;
-                            const int kh = tap / cg.KW, kw = tap - kh * cg.KW;
-                            // past the last tap: a box that is entirely out of bounds (zero filled, full byte count)
-                            const int c0 = tap < cg.taps ? cc * cw : cg.cchunks * cw;
-                            tma_load_4d(sb + j * 64 * cw * 2, &map_w, full + s, c0, pow_ * cg.stride + kw * cg.dil - cg.pad,
-                                        poh * cg.stride + kh * cg.dil - cg.pad, pimg);
+                        // (two boxes of 64 output channels), B = the input activation at one filter tap per block of cw
+                        // columns (4-D boxes, zero fill outside the image = the convolution padding)
+                        const int poh = p_th * cg.TH, pow_ = p_tw * cg.TW;
+                        tma_load_4d(sa, &map_a, full + s, mt * BM, pow_, poh, p_img);
+                        tma_load_4d(sa + 64 * 128, &map_a, full + s, mt * BM + 64, pow_, poh, p_img);
+                        const int bstride = 64 * cg.cw * 2, nblk = BN * 128 / bstride;    // 2 blocks of 64 channels or 4 of 32
+                        const int px = pow_ * cg.stride, py = poh * cg.stride;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < nblk) tma_load_4d(sb + j * bstride, &map_w, full + s, w_c0[j], px + w_dx[j], py + w_dy[j], p_img);
+                        if (++p_tw == cg.tiles_w) {
+                            p_tw = 0;
+                            if (++p_th == cg.tiles_h) {
+                                p_th = 0;
+                                p_img += cg.TN;
+                            }
                         }
                     } else if (MODE == 0 && A_MN) {
                         // two boxes of 64 MN elements x BKC contraction rows
@@ -663,10 +688,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     } else if (MODE == 0) {
                         tma_load_2d(sa, &map_a, full + s, kb * BKC, mt * BM);
                     } else {
-                        const int tap = kb / cg.cchunks, cc = kb - tap * cg.cchunks;
-                        const int kh = tap / cg.KW, kw = tap - kh * cg.KW;
-                        tma_load_4d(sa, &map_a, full + s, cc * BKC, ow0 * cg.stride + kw * cg.dil - cg.pad,
-                                    oh0 * cg.stride + kh * cg.dil - cg.pad, img);
+                        tma_load_4d(sa, &map_a, full + s, f_cc * BKC, ow0 + f_kw * cg.dil, oh0 + f_kh * cg.dil, img);
+                        if (++f_cc == cg.cchunks) {
+                            f_cc = 0;
+                            if (++f_kw == cg.KW) {
+                                f_kw = 0;
+                                ++f_kh;
+                            }
+                        }
                     }
                     if (MODE == 2) {
                     } else if (B_MN) {
