@@ -369,6 +369,64 @@ dwconv_bwd_data_kernel(const __nv_bfloat16 *__restrict__ dY, const float *__rest
     }
 }
 
+// Stride-2 data gradient, one CTA per input row: an input pixel receives 1, 2 or 4 taps depending on the parity of its
+// coordinates (even: the centre tap; odd: the two outer taps), so the tap list is decided per row / per column instead of
+// testing all nine taps with runtime divisions per element (the generic kernel above ran at ~1.3 TB/s on the two stride-2
+// layers of stages 1 and 2: 1.1 ms per step).  A thread walks (pixel, 8-channel group) items of the row: consecutive
+// threads write consecutive 16-byte chunks.
+__global__ void __launch_bounds__(256)
+dwconv_bwd_data_s2_kernel(const __nv_bfloat16 *__restrict__ dY, const float *__restrict__ Wd, int H, int W, int C, int Ho, int Wo,
+                          const __nv_bfloat16 *__restrict__ add, __nv_bfloat16 *__restrict__ dX) {
+    const int C8 = C >> 3;
+    const long row = blockIdx.x;                 // b * H + iy
+    const int iy = (int)(row % H);
+    const long b = row / H;
+    // rows of dY that reach this input row: oy * 2 + ky - 1 = iy
+    int ny = 0, kys[2], oys[2];
+    if (iy & 1) {
+        const int o0 = (iy + 1) >> 1, o1 = (iy - 1) >> 1;
+        if (o0 < Ho) { kys[ny] = 0; oys[ny] = o0; ++ny; }
+        if (o1 < Ho) { kys[ny] = 2; oys[ny] = o1; ++ny; }
+    } else if ((iy >> 1) < Ho) {
+        kys[0] = 1; oys[0] = iy >> 1; ny = 1;
+    }
+    const int items = W * C8;
+    __nv_bfloat16 *out = dX + row * (long)W * C;
+    const __nv_bfloat16 *addr = add != nullptr ? add + row * (long)W * C : nullptr;
+    for (int e = threadIdx.x; e < items; e += blockDim.x) {
+        const int ix = e / C8, cg = e - ix * C8;
+        float acc[8];
+        if (addr != nullptr) up8(__ldg((const uint4 *)addr + e), acc);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        }
+        int nx = 0, kxs[2], oxs[2];
+        if (ix & 1) {
+            const int o0 = (ix + 1) >> 1, o1 = (ix - 1) >> 1;
+            if (o0 < Wo) { kxs[nx] = 0; oxs[nx] = o0; ++nx; }
+            if (o1 < Wo) { kxs[nx] = 2; oxs[nx] = o1; ++nx; }
+        } else if ((ix >> 1) < Wo) {
+            kxs[0] = 1; oxs[0] = ix >> 1; nx = 1;
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            if (a >= ny) break;
+            const __nv_bfloat16 *drow = dY + ((b * Ho + oys[a]) * Wo) * (long)C + cg * 8;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (q >= nx) break;
+                float d[8], w[8];
+                up8(__ldg((const uint4 *)(drow + (long)oxs[q] * C)), d);
+                ld8f(Wd + (long)(kys[a] * 3 + kxs[q]) * C + cg * 8, w);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(d[j], w[j], acc[j]);
+            }
+        }
+        ((uint4 *)out)[e] = pk8(acc);
+    }
+}
+
 // dW[c * 9 + k] += sum_{b,oy,ox} dY[b,oy,ox,c] * X[b, oy*s+ky-1, ox*s+kx-1, c]   (parameter layout [C,1,3,3])
 // Same tiling as the forward kernel: a CTA walks output tiles (TH x TW pixels x 64 channels), stages the input halo
 // tile in shared memory once, and every thread keeps 9 x 8 fp32 partials in registers across all its tiles; one fold
@@ -525,33 +583,44 @@ gate_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dO, const __nv_bfloat16
 }
 
 // dX[b,p,c] = add + dOut[b,p,c] * gate[b,c] + dmean[b,c] * inv_hw
-__global__ void __launch_bounds__(256)
+// grid (row blocks, B); a thread owns one 8-channel group of its image for its whole life (gate and dmean / HW in
+// registers) and walks rows -- no per-element index arithmetic (the flat-index version decoded (image, channel group) with
+// 64-bit divisions per element and ran at half the bandwidth of its neighbours)
+__global__ void __launch_bounds__(384)
 gate_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ gate, const __nv_bfloat16 *__restrict__ dmean,
-                      float inv_hw, long HW, int C, const __nv_bfloat16 *__restrict__ add, long total8,
-                      __nv_bfloat16 *__restrict__ dX) {
-    const int C8 = C >> 3;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(i % C8);
-        const long b = (i / C8) / HW;
-        float d[8], m[8];
-        if (dO != nullptr) up8(__ldg((const uint4 *)dO + i), d);
-        else {
+                      float inv_hw, long HW, int C, const __nv_bfloat16 *__restrict__ add, __nv_bfloat16 *__restrict__ dX) {
+    const RowMap rm(C);
+    const long b = blockIdx.y, base = b * HW;
+    float g[8], m[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) d[j] = 0.f;
-        }
-        if (dmean != nullptr) up8(__ldg((const uint4 *)(dmean + b * C + cg * 8)), m);
+    for (int j = 0; j < 8; ++j) {
+        g[j] = gate != nullptr ? __ldg(gate + b * C + rm.c0 + j) : 1.0f;
+        m[j] = 0.f;
+    }
+    if (dmean != nullptr) {
+        up8(__ldg((const uint4 *)(dmean + b * C + rm.c0)), m);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            d[j] *= gate != nullptr ? __ldg(gate + b * C + cg * 8 + j) : 1.0f;
-            if (dmean != nullptr) d[j] = fmaf(m[j], inv_hw, d[j]);
+        for (int j = 0; j < 8; ++j) m[j] *= inv_hw;
+    }
+    const long step = (long)gridDim.x * rm.rpb;
+    for (long r = (long)blockIdx.x * rm.rpb + rm.rsub; r < HW; r += step) {
+        const long off = (base + r) * C + rm.c0;
+        float d[8];
+        if (dO != nullptr) {
+            up8(__ldg((const uint4 *)(dO + off)), d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] = fmaf(d[j], g[j], m[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] = m[j];
         }
         if (add != nullptr) {
             float a[8];
-            up8(__ldg((const uint4 *)add + i), a);
+            up8(__ldg((const uint4 *)(add + off)), a);
 #pragma unroll
             for (int j = 0; j < 8; ++j) d[j] += a[j];
         }
-        ((uint4 *)dX)[i] = pk8(d);
+        *(uint4 *)(dX + off) = pk8(d);
     }
 }
 
@@ -1053,8 +1122,12 @@ POSE_API int pose_dwconv3x3_bwd_bf16(const void *dY, const void *X, const float 
     cudaStream_t s = (cudaStream_t)stream;
     if (dX) {
         const long total8 = (long)B * H * W * (C / 8);
-        dwconv_bwd_data_kernel<<<grid_for(total8), 256, 0, s>>>((const __nv_bfloat16 *)dY, Wd, H, W, C, Ho, Wo, stride,
-                                                               (const __nv_bfloat16 *)add, total8, (__nv_bfloat16 *)dX);
+        if (stride == 2 && (long)B * H < 2147483647L && (uintptr_t)Wd % 16 == 0)
+            dwconv_bwd_data_s2_kernel<<<(unsigned)((long)B * H), 256, 0, s>>>((const __nv_bfloat16 *)dY, Wd, H, W, C, Ho, Wo,
+                                                                            (const __nv_bfloat16 *)add, (__nv_bfloat16 *)dX);
+        else
+            dwconv_bwd_data_kernel<<<grid_for(total8), 256, 0, s>>>((const __nv_bfloat16 *)dY, Wd, H, W, C, Ho, Wo, stride,
+                                                                   (const __nv_bfloat16 *)add, total8, (__nv_bfloat16 *)dX);
     }
     if (dW) {
         const int th = stride == 1 ? DwT<1>::TH : DwT<2>::TH, tw = stride == 1 ? DwT<1>::TW : DwT<2>::TW;
@@ -1107,10 +1180,16 @@ POSE_API int pose_gate_bwd_apply_bf16(const void *dOut, const float *gate, const
                                       const void *add, void *dX, pose_stream_t stream) {
     REQ((dOut || dmean) && dX, POSE_E_NULL);      /* dOut NULL: dX = dmean / HW broadcast (gradient of a global average) */
     REQ(B > 0 && HW > 0 && C > 0 && C % 8 == 0, POSE_E_SHAPE);
-    const long total8 = (long)B * HW * (C / 8);
-    gate_bwd_apply_kernel<<<grid_for(total8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dOut, gate,
-                                                                             (const __nv_bfloat16 *)dmean, inv_hw, HW, C,
-                                                                             (const __nv_bfloat16 *)add, total8, (__nv_bfloat16 *)dX);
+    REQ(C <= 3072, POSE_E_UNSUPPORTED);
+    // enough row blocks per image for ~8 CTAs per SM over the batch, at least 4 rows per thread
+    const int rpb = rowmap_threads(C) / (C / 8);
+    long gx = (HW + (long)rpb * 4 - 1) / ((long)rpb * 4);
+    const long cap = ((long)kNumSMs * 8 + B - 1) / B;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    gate_bwd_apply_kernel<<<dim3((unsigned)gx, B), rowmap_threads(C), 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16 *)dOut, gate, (const __nv_bfloat16 *)dmean, inv_hw, HW, C, (const __nv_bfloat16 *)add,
+        (__nv_bfloat16 *)dX);
     return launch_status();
 }
 
