@@ -1003,15 +1003,19 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
                        const ConvGeom &cg, int m_tiles, cudaStream_t s, int k_splits = 1) {
     Epilogue ep = ep_in;
     CUtensorMap mc = {}, maux = {}, mpre = {};
-    // Epilogue choice (measured on the ViT shapes, same box): the row-per-lane TMA epilogue wins whenever the epilogue has
-    // real per-element work -- exact GELU (103 vs 111 us), saving the activation derivative (109 vs 117 us), multiplying
-    // by a saved derivative (105 vs 212 us) -- and loses ~10 % on plain / SiLU / residual-only epilogues, whose 64-byte
-    // row stores compete with the operand loads for the TMA / L2 path that already bounds the 128 x 128 main loop.
+    // Epilogue choice.  Round 1 measured the row-per-lane TMA epilogue ahead only for epilogues with real per-element work
+    // (exact GELU, saved derivative, multiply-by-derivative) and ~10 % behind on plain / SiLU / residual-only ones; with the
+    // operand ring one stage deeper it now wins on every bf16 epilogue of the ViT step (25.6 -> 25.0 ms with it everywhere:
+    // the transposing epilogue costs ~630 instructions per 32 x 32 chunk), so it is the default for bf16 outputs; the
+    // transposing epilogue remains for fp32 / accumulating / ragged outputs and the convolution modes.
     ep.tma = 0;
-    static const bool tma_off = getenv("POSE_NO_TMA_EPILOGUE") != nullptr;     // A/B switch for measurements
-    static const bool tma_all = getenv("POSE_TMA_EPILOGUE_ALL") != nullptr;    // measurements: TMA path for every bf16 GEMM
-    const bool heavy = ep.act == 3 || ep.act >= 5 || ep.preact != nullptr || tma_all;
-    if (MODE == 0 && ep.out_bf16 && !ep.accumulate && ep.vec && N % 32 == 0 && heavy && !tma_off) {
+    static const bool tma_off = getenv("POSE_NO_TMA_EPILOGUE") != nullptr;     // A/B switches for measurements
+    static const bool tma_heavy_only = getenv("POSE_TMA_EPILOGUE_HEAVY_ONLY") != nullptr;
+    const bool heavy = ep.act == 3 || ep.act >= 5 || ep.preact != nullptr || !tma_heavy_only;
+    const bool lean_shape = ep.act == 0 && ep.bias == nullptr && ep.preact == nullptr && ep.drop_thresh == 0 &&
+                            ep.out_scale == 1.0f && (ep.residual == nullptr || ep.res_scale == 1.0f) && k_splits <= 1;
+    if (MODE == 0 && ep.out_bf16 && !ep.accumulate && ep.vec && N % 32 == 0 && heavy && !tma_off && !lean_shape &&
+        ep.stats == nullptr) {
         int e = make_map_tile32(&mc, ep.C, M, N, ep.ldc);
         if (!e && ep.residual) e = make_map_tile32(&maux, ep.residual, M, N, ep.ldr);
         if (!e && ep.preact) e = make_map_tile32(&mpre, ep.preact, M, N, ep.ldc);
@@ -1041,9 +1045,7 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
     }
     static const bool lean_off = getenv("POSE_NO_LEAN_EPILOGUE") != nullptr;   // A/B switch for measurements
     bool lean = false;
-    if (kHasLean && !lean_off && !ep.tma && ep.out_bf16 && !ep.accumulate && ep.vec && N % 32 == 0 && ep.act == 0 &&
-        ep.bias == nullptr && ep.preact == nullptr && ep.drop_thresh == 0 && ep.out_scale == 1.0f &&
-        (ep.residual == nullptr || ep.res_scale == 1.0f) && k_splits <= 1) {
+    if (kHasLean && !lean_off && !ep.tma && ep.out_bf16 && !ep.accumulate && ep.vec && N % 32 == 0 && lean_shape) {
         int e = make_map_tile32(&mc, ep.C, M, N, ep.ldc);
         if (!e && ep.residual) e = make_map_tile32(&maux, ep.residual, M, N, ep.ldr);
         lean = !e;
