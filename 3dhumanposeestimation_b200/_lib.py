@@ -62,6 +62,7 @@ SIGNATURES = {
     "pose_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
     "pose_loss_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, C.POINTER(c_float), c_void_p, c_void_p, c_float,
                                   c_void_p, c_size_t, c_void_p]),
+    "pose_heatmap_patchify_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     "pose_heatmap_render": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_int, c_int,
                                     c_void_p]),
     "pose_augment_plan": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, C.POINTER(PoseAugLaunch)]),

@@ -114,7 +114,58 @@ heatmap_generic_kernel(const float *__restrict__ kp, int B, int J, int hs, Heatm
     }
 }
 
+// Heat-maps rendered straight into the operand of the ViT's heat-map patch embedding (transformers.py:41-46, :348-350):
+// out[(b * PH + py) * PW + px][(j * P + ky) * P + kx] = bf16(gauss_j(y = py P + ky, x = px P + kx)) -- the [B, J, hs, hs] fp32
+// planes of GaussianHeatmapGenerator never exist.  Same arithmetic as heatmap_planes_kernel (the bf16 value is the
+// rounding of the reference's fp32 value).  A thread writes 8 consecutive kx (16 bytes); P % 8 == 0.
+__global__ void __launch_bounds__(256)
+heatmap_patchify_kernel(const float *__restrict__ kp, int J, int hs, int P, HeatmapConst c, long total8,
+                        __nv_bfloat16 *__restrict__ out) {
+    const int PW = hs / P, P8 = P >> 3;
+    const int per_patch8 = J * P * P8;            // 16-byte groups of one patch row of the GEMM operand
+    const int patches = PW * PW;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int k8 = (int)(i % per_patch8);
+        const long pidx = i / per_patch8;
+        const int pp = (int)(pidx % patches);
+        const long b = pidx / patches;
+        const int py = pp / PW, px = pp - py * PW;
+        const int kx8 = k8 % P8, t = k8 / P8;
+        const int ky = t % P, j = t / P;
+        const float kx = __ldg(kp + (b * J + j) * 2), kyf = __ldg(kp + (b * J + j) * 2 + 1);
+        const float mux = __fmul_rn(kx, c.scale), muy = __fmul_rn(kyf, c.scale);
+        const float valid = (kx > 0.0f && kyf > 0.0f) ? 1.0f : 0.0f;
+        const float dy = __fsub_rn((float)(py * P + ky), muy), dy2 = __fmul_rn(dy, dy);
+        const int x0 = px * P + kx8 * 8;
+        __nv_bfloat162 pk[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float dx0 = __fsub_rn((float)(x0 + 2 * q), mux), dx1 = __fsub_rn((float)(x0 + 2 * q + 1), mux);
+            pk[q] = __floats2bfloat162_rn(gauss(__fmul_rn(dx0, dx0), dy2, c.denom, c.rcp_denom, valid),
+                                          gauss(__fmul_rn(dx1, dx1), dy2, c.denom, c.rcp_denom, valid));
+        }
+        ((uint4 *)out)[i] = make_uint4(*(unsigned *)&pk[0], *(unsigned *)&pk[1], *(unsigned *)&pk[2], *(unsigned *)&pk[3]);
+    }
+}
+
 }  // namespace pose
+
+POSE_API int pose_heatmap_patchify_bf16(const float *kp, int B, int J, int hs, float sigma, int P, void *out,
+                                        pose_stream_t stream) {
+    using namespace pose;
+    if (!kp || !out) return POSE_E_NULL;
+    if (B <= 0 || J <= 0 || hs <= 0 || P <= 0 || hs % P || P % 8 || !(sigma > 0.0f)) return POSE_E_SHAPE;
+    if ((uintptr_t)out % 16) return POSE_E_ALIGN;
+    HeatmapConst c;
+    c.scale = (float)(hs - 1);
+    c.denom = (float)(2.0 * (double)sigma * (double)sigma);
+    c.rcp_denom = (float)(1.0 / (double)c.denom);
+    const long total8 = (long)B * (hs / P) * (hs / P) * J * P * (P / 8);
+    long blocks = (total8 + 255) / 256;
+    const int grid = (int)(blocks < (long)kNumSMs * 16 ? blocks : (long)kNumSMs * 16);
+    heatmap_patchify_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kp, J, hs, P, c, total8, (__nv_bfloat16 *)out);
+    return launch_status();
+}
 
 POSE_API int pose_heatmap_render(const float *kp, int B, int J, int hs, float sigma, void *out, int out_dtype,
                                  int out_layout, int c_stride, int c_offset, pose_stream_t stream) {

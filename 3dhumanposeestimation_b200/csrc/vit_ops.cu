@@ -127,6 +127,29 @@ patchify_kernel(const float *__restrict__ src0, int C0, const float *__restrict_
         out[i] = __float2bfloat16_rn(v);
     }
 }
+// P % 8 == 0 and 16-byte aligned planes: a thread converts 8 consecutive kx (two float4 loads, one 16-byte store); the
+// index of a 16-byte group is decoded with 32-bit arithmetic below the patch level (the element-wise version above spends
+// seven 64-bit divisions per element: 0.7 TB/s)
+__global__ void __launch_bounds__(256)
+patchify8_kernel(const float *__restrict__ src0, int C0, const float *__restrict__ src1, int C1, int H, int W, int P,
+                 long total8, __nv_bfloat16 *__restrict__ out) {
+    const int C = C0 + C1, PW = W / P, PH = H / P, P8 = P >> 3, K8 = C * P * P8, patches = PW * PH;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+        const int k8 = (int)(i % K8);
+        const long pidx = i / K8;
+        const int pp = (int)(pidx % patches);
+        const long b = pidx / patches;
+        const int py = pp / PW, px = pp - py * PW;
+        const int kx8 = k8 % P8, t = k8 / P8;
+        const int ky = t % P, c = t / P;
+        const int y = py * P + ky, x = px * P + kx8 * 8;
+        const float *src = c < C0 ? src0 + ((b * C0 + c) * H + y) * (long)W + x : src1 + ((b * C1 + (c - C0)) * H + y) * (long)W + x;
+        const float4 lo = __ldg((const float4 *)src), hi = __ldg((const float4 *)src + 1);
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(lo.x, lo.y), p1 = __floats2bfloat162_rn(lo.z, lo.w);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(hi.x, hi.y), p3 = __floats2bfloat162_rn(hi.z, hi.w);
+        ((uint4 *)out)[i] = make_uint4(*(uint32_t *)&p0, *(uint32_t *)&p1, *(uint32_t *)&p2, *(uint32_t *)&p3);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // LayerNorm backward.  dX = dRes + rstd * (g*dY - mean(g*dY) - xhat * mean(g*dY*xhat)); dgamma += sum dY*xhat,
@@ -420,8 +443,12 @@ POSE_API int pose_patchify_bf16(const float *src0, int C0, const float *src1, in
     if (!src0 || !out || (C1 > 0 && !src1)) return POSE_E_NULL;
     if (B <= 0 || C0 <= 0 || C1 < 0 || H <= 0 || W <= 0 || P <= 0 || H % P || W % P) return POSE_E_SHAPE;
     const long total = (long)B * (H / P) * (W / P) * (C0 + C1) * P * P;
-    patchify_kernel<<<grid_cap(total), 256, 0, (cudaStream_t)stream>>>(src0, C0, src1, C1, H, W, P, total,
-                                                                      (__nv_bfloat16 *)out);
+    if (P % 8 == 0 && W % 4 == 0 && (uintptr_t)src0 % 16 == 0 && (!src1 || (uintptr_t)src1 % 16 == 0) && (uintptr_t)out % 16 == 0)
+        patchify8_kernel<<<grid_cap(total / 8), 256, 0, (cudaStream_t)stream>>>(src0, C0, src1, C1, H, W, P, total / 8,
+                                                                               (__nv_bfloat16 *)out);
+    else
+        patchify_kernel<<<grid_cap(total), 256, 0, (cudaStream_t)stream>>>(src0, C0, src1, C1, H, W, P, total,
+                                                                          (__nv_bfloat16 *)out);
     return launch_status();
 }
 

@@ -454,10 +454,14 @@ class VitPlan:
         x_img = self.layernorm("x_img", x, bb.norm, B * Ti, rows=Ti, in_group=Ti + 1, in_off=1)
         # ---- heat-map stream ---------------------------------------------------------------------------
         hs, hp = int(c.heatmap_size), int(c.heatmap_patch_size)
-        hm = self.buf("hm", B, self.J, hs, hs, dtype=torch.float32)
-        self.call("pose_heatmap_render", kp.data_ptr(), B, self.J, hs, float(c.heatmap_sigma), hm.data_ptr(), 0, 0, 0, 0)
         phm = self.buf("phm", B * Th, self.J * hp * hp)
-        self.call("pose_patchify_bf16", hm.data_ptr(), self.J, None, 0, B, hs, hs, hp, phm.data_ptr())
+        if hp % 8 == 0:
+            # the Gaussians are rendered straight into the patch-embedding GEMM's A operand (no fp32 planes in HBM)
+            self.call("pose_heatmap_patchify_bf16", kp.data_ptr(), B, self.J, hs, float(c.heatmap_sigma), hp, phm.data_ptr())
+        else:
+            hm = self.buf("hm", B, self.J, hs, hs, dtype=torch.float32)
+            self.call("pose_heatmap_render", kp.data_ptr(), B, self.J, hs, float(c.heatmap_sigma), hm.data_ptr(), 0, 0, 0, 0)
+            self.call("pose_patchify_bf16", hm.data_ptr(), self.J, None, 0, B, hs, hs, hp, phm.data_ptr())
         hpe = m.heatmap_patch_embed.proj
         hm_tok = self.linear("hm_tok", phm, B * Th, hpe.weight, hpe.bias)
         x_hm = self.buf("x_hm", B * Th, E)

@@ -64,6 +64,10 @@ int pose_loss_fwd_bwd(const float *pred, const float *gt, int B, int J, const fl
  * ------------------------------------------------------------------------------------------- */
 int pose_heatmap_render(const float *kp, int B, int J, int hs, float sigma, void *out, int out_dtype,
                         int out_layout, int c_stride, int c_offset, pose_stream_t stream);
+/* The same heat-maps rendered straight into the bf16 operand of the ViT's heat-map patch embedding
+ * (src/models/transformers.py:41-46, :348-350): out [B * (hs/P)^2, J * P * P], row = patch, column = (j, ky, kx) = the
+ * flattened Conv2d(J, E, P, P) weight; the fp32 planes are never written.  P % 8 == 0, hs % P == 0. */
+int pose_heatmap_patchify_bf16(const float *kp, int B, int J, int hs, float sigma, int P, void *out, pose_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * A. PoseAugmentor.__call__ (batched)            reference: src/dataset/augmentation.py:182-351

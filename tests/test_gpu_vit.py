@@ -430,3 +430,34 @@ def test_fused_optimizer_step_changes_the_next_forward(pose, golden):
         opt.zero_grad()
         losses.append(total.item())
     assert losses[-1] < losses[0], losses
+
+
+def test_patchify_and_fused_heatmap_patch_operand(pose, oracle):
+    """The patch-embedding operands (transformers.py:41-46): (i) image + depth planes -> [B * patches, 4 * P * P] bf16, bit-equal
+    to torch's unfold of the concatenated planes; (ii) the Gaussians rendered straight into the heat-map stream's operand
+    equal the bf16 rounding of the reference's fp32 heat-maps (the C oracle's values, <= 2 ulp from the planes kernel),
+    patch by patch -- the fp32 planes never exist."""
+    lib, sp, check = _lib(pose)
+    g = torch.Generator().manual_seed(31)
+    B, H, P = 3, 64, 16
+    img, dep = torch.rand(B, 3, H, H, generator=g).to(DEV), torch.rand(B, 1, H, H, generator=g).to(DEV)
+    out = torch.empty(B * (H // P) ** 2, 4 * P * P, device=DEV, dtype=torch.bfloat16)
+    check(lib.pose_patchify_bf16(img.data_ptr(), 3, dep.data_ptr(), 1, B, H, H, P, out.data_ptr(), sp()), "patchify")
+    x = torch.cat([img, dep], 1)
+    want = torch.nn.functional.unfold(x, P, stride=P).transpose(1, 2).reshape(B * (H // P) ** 2, 4 * P * P).bfloat16()
+    assert torch.equal(out, want)
+    # heat-map stream: hs 64, sigma 2, 16 x 16 patches (the reference's ViT configuration) and an 8-pixel patch variant
+    J = 17
+    kp = (torch.rand(B, J, 2, generator=g) * 0.9 + 0.05)
+    kp[0, 3] = -1.0                                   # invalid key-point: an all-zero plane
+    for hs, sigma, hp in ((64, 2.0, 16), (32, 1.5, 8)):
+        planes = torch.empty(B, J, hs, hs, device=DEV)
+        check(lib.pose_heatmap_render(kp.to(DEV).data_ptr(), B, J, hs, sigma, planes.data_ptr(), 0, 0, 0, 0, sp()), "render")
+        fused = torch.empty(B * (hs // hp) ** 2, J * hp * hp, device=DEV, dtype=torch.bfloat16)
+        check(lib.pose_heatmap_patchify_bf16(kp.to(DEV).data_ptr(), B, J, hs, sigma, hp, fused.data_ptr(), sp()), "hm patchify")
+        want = torch.nn.functional.unfold(planes, hp, stride=hp).transpose(1, 2).reshape(fused.shape).bfloat16()
+        assert torch.equal(fused, want)               # same arithmetic as the planes kernel, rounded once to bf16
+        ref = torch.from_numpy(oracle.heatmap(kp.numpy(), hs, sigma)).to(DEV)
+        refp = torch.nn.functional.unfold(ref, hp, stride=hp).transpose(1, 2).reshape(fused.shape)
+        assert (fused.float() - refp).abs().max().item() <= 2 ** -8       # bf16 rounding of values in [0, 1]
+        assert fused.float().sum().item() > 0
