@@ -20,7 +20,8 @@ from .dataset.augmentation import PoseAugmentor  # noqa: F401
 from .models.cnn import CNNPoseEstimation  # noqa: F401
 from .models.transformers import TransformerPoseEstimation  # noqa: F401
 from .optim import AdamW  # noqa: F401
+from .dataset.transforms import Resize, resize_frames  # noqa: F401
 from . import _lib, ops  # noqa: F401
 
 __all__ = ["ModelConfig", "ComprehensivePoseLoss", "GaussianHeatmapGenerator", "PoseRegressionHead",
-           "PoseAugmentor", "CNNPoseEstimation", "TransformerPoseEstimation", "AdamW"]
+           "PoseAugmentor", "CNNPoseEstimation", "TransformerPoseEstimation", "AdamW", "Resize", "resize_frames"]

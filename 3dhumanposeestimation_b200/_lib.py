@@ -147,6 +147,9 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     "pose_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_long, c_float, c_float, c_float,
                                 c_float, c_float, c_int, c_float, c_int, c_void_p]),
+    "pose_resize_workspace_bytes": (C.c_size_t, [c_int, c_int, c_int, c_int]),
+    "pose_resize_bilinear_aa": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                        C.c_size_t, c_void_p, c_void_p]),
     "pose_step_state_bind": (c_int, [c_void_p]),
     "pose_step_tick": (c_int, [c_void_p, c_void_p]),
     "pose_adamw_step_g16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_long, c_float, c_float,

@@ -27,6 +27,8 @@ EXTRA = {
     # libImaging / numpy evaluate a*b+c with two roundings; bit-exact parity needs the same
     "augment.cu": ["-fmad=false"],
     "heatmap.cu": ["-fmad=false"],
+    # ATen's anti-aliased resize: the tap order decides which products are fused; nothing else may be contracted
+    "resize.cu": ["-fmad=false"],
 }
 
 

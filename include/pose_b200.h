@@ -298,6 +298,19 @@ int pose_attention_bwd_bf16(const void *Q, const void *K, const void *V, const v
                             float drop_p, uint64_t drop_seed, pose_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * 8f-2. transforms.Resize(image_size) of decoded frames     reference: main.py:171-173, applied per frame in
+ *    src/dataset/chunked_dataset.py:100-129; depth rescale :159-164.
+ *    = F.interpolate(mode="bilinear", align_corners=False, antialias=True) of float frames: ATen's separable anti-aliased
+ *    resampling, bit-equal to the CPU tensor the reference's DataLoader worker produces (weights, promotions and tap order
+ *    restated, see csrc/resize.cu).  src [B, C, H, W] fp32 in [0, 1] (in_dtype 0) or uint8 (1: converted as `.float() /
+ *    255.0`); dst [B, C, OH, OW] fp32; mul / add [B] fp32 or NULL: dst = dst * mul[b] + add[b] (depth * (max - min) + min).
+ *    workspace: pose_resize_workspace_bytes(H, W, OH, OW), 16-byte aligned (weight tables, rebuilt by every call).
+ * ------------------------------------------------------------------------------------------- */
+size_t pose_resize_workspace_bytes(int H, int W, int OH, int OW);
+int pose_resize_bilinear_aa(const void *src, int in_dtype, int B, int C, int H, int W, int OH, int OW, const float *mul,
+                            const float *add, void *workspace, size_t workspace_bytes, float *dst, pose_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * G'. device-resident per-step state: what changes from one training step to the next -- the dropout stream and AdamW's
  *    step count (bias correction) -- read from device memory, so that the whole step (src/train.py:76-119) can be captured
  *    ONCE as a CUDA graph and replayed.  pose_step_tick (one thread) advances it at the start of a step: ++counter,

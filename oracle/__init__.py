@@ -164,6 +164,17 @@ def heatmap(kp, hs: int, sigma: float) -> np.ndarray:
     return out
 
 
+def tensor_resize_aa(img, out_h: int, out_w: int, mode: int = 2) -> np.ndarray:
+    """transforms.Resize on a float32 [C, H, W] frame (F.interpolate bilinear, antialias=True) as ATen's CPU kernel
+    computes it; mode 2 = the shipped tap order (bit-equal to torch 2.11, tests/golden/resize.npz), 0 / 1 = plain / fused
+    accumulation everywhere."""
+    img = _f32(img)
+    c, h, w = img.shape
+    out = np.empty((c, out_h, out_w), np.float32)
+    lib().oracle_resize_bilinear_aa(_p(img), c, h, w, out_h, out_w, mode, _p(out))
+    return out
+
+
 def heatmap_peak(kp, hs: int) -> np.ndarray:
     kp = _f32(kp)
     B, J = kp.shape[:2]

@@ -461,11 +461,44 @@ def gen_collate():
     np.savez_compressed(os.path.join(OUT, "collate.npz"), **out)
 
 
+RESIZE_CASES = ((3, 125, 126, 32, 32), (1, 100, 100, 64, 64), (3, 250, 251, 64, 64), (1, 37, 53, 16, 24), (3, 96, 128, 64, 64))
+
+
+def resize_frame(case, seed):
+    """Seeded uint8 frame (what torchvision.io.read_image returns) both this script and the tests build."""
+    c, h, w = case[:3]
+    return np.random.default_rng(seed).integers(0, 256, (c, h, w), dtype=np.uint8)
+
+
+def gen_resize():
+    """transforms.Resize(size) exactly as the reference applies it to a decoded frame (main.py:171-173,
+    src/dataset/chunked_dataset.py:100-129): read_image -> .float() / 255.0 -> Resize; and the depth rescale of :159-164
+    on the single-channel cases.  The C oracle's restatement of ATen's anti-aliased kernel must reproduce every frame bit
+    for bit (asserted here, with the library versions recorded)."""
+    import torch
+    from torchvision import transforms
+    if REPO not in sys.path:
+        sys.path.insert(0, REPO)
+    import oracle
+    out = {"versions": versions(), "n_cases": np.int32(len(RESIZE_CASES)), "cases": np.array(RESIZE_CASES, np.int32)}
+    for i, case in enumerate(RESIZE_CASES):
+        u8 = resize_frame(case, 700 + i)
+        x = torch.from_numpy(u8).float() / 255.0
+        y = transforms.Compose([transforms.Resize((case[3], case[4]))])(x)
+        assert np.array_equal(oracle.tensor_resize_aa(x.numpy(), case[3], case[4]), y.numpy()), case
+        out[f"r{i}"] = y.numpy()
+        if case[0] == 1:
+            lo, hi = 0.35 + i, 7.25 + i
+            out[f"r{i}_depth"] = (y * (hi - lo) + lo).numpy()
+            out[f"r{i}_range"] = np.array([lo, hi], np.float64)
+    np.savez_compressed(os.path.join(OUT, "resize.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, os.path.join(REF, "src"))
     os.chdir(tempfile.mkdtemp(prefix="pose_golden_"))
-    which = sys.argv[1:] or ["augment", "heatmap", "loss", "config", "cnn", "vit", "cnn_train", "metrics", "collate"]
+    which = sys.argv[1:] or ["augment", "heatmap", "loss", "config", "cnn", "vit", "cnn_train", "metrics", "collate", "resize"]
     for w in which:
         globals()["gen_" + w]()
         print("wrote", w)

@@ -740,3 +740,75 @@ ORACLE_API float oracle_pa_mpjpe(const float *pred, const float *gt, int B, int 
     }
     return (float)(total / B);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * transforms.Resize(image_size) on a float32 [C, H, W] tensor (reference: main.py:171-173 applied in
+ * src/dataset/chunked_dataset.py:100-129) = torch.nn.functional.interpolate(mode="bilinear", align_corners=False,
+ * antialias=True): ATen's separable anti-aliased resampling on the CPU (UpSampleKernel.cpp,
+ * _compute_indices_min_size_weights_aa + basic_loop_aa_horizontal / _vertical; torch is a third-party dependency, not
+ * under /root/reference: restated from its published algorithm and pinned by tests/golden/resize.npz from the live call).
+ * Width pass first into an fp32 temporary [C, H, OW], then the height pass.  Triangle filter of support max(scale, 1),
+ * weights normalised by their sum, fp32 arithmetic with the mixed float / double promotions of the C++ source.
+ * Accumulation order of the shipped x86 build (probed tap by tap against torch 2.11, see oracle/gen_golden.py::gen_resize):
+ * t = s0 * w0, then the remaining taps in order, in blocks of four with separate multiply and add, and the last (n - 1) % 4
+ * taps with a fused multiply-add (the compiler's unrolled body vs. its contracted scalar tail).  `fma` = 0 / 1 force
+ * plain / fused accumulation everywhere (kept for the probe), 2 = the shipped pattern.
+ * ------------------------------------------------------------------------------------------- */
+static int aa_weights(int i, int in_size, float scale, float support, int max_interp, float *w, int *xmin_out) {
+    const float center = (float)((double)scale * ((double)i + 0.5));
+    const float invscale = scale >= 1.0f ? (float)(1.0 / (double)scale) : 1.0f;
+    long xmin = (long)((double)center - (double)support + 0.5);
+    if (xmin < 0) xmin = 0;
+    long xmax = (long)((double)center + (double)support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    long xsize = xmax - xmin;
+    if (xsize < 0) xsize = 0;
+    if (xsize > max_interp) xsize = max_interp;
+    float total = 0.0f;
+    for (long j = 0; j < xsize; ++j) {
+        /* (j + xmin - center + 0.5) * invscale: int64 - float -> float, + 0.5 -> double, * float -> double, -> float */
+        float x = (float)(((double)((float)(j + xmin) - center) + 0.5) * (double)invscale);
+        if (x < 0.0f) x = -x;
+        const float wt = x < 1.0f ? 1.0f - x : 0.0f;
+        w[j] = wt;
+        total += wt;
+    }
+    if (total != 0.0f)
+        for (long j = 0; j < xsize; ++j) w[j] /= total;
+    *xmin_out = (int)xmin;
+    return (int)xsize;
+}
+
+ORACLE_API void oracle_resize_bilinear_aa(const float *src, int C, int H, int W, int OH, int OW, int fma, float *dst) {
+    const float sw = (float)W / (float)OW, sh = (float)H / (float)OH;
+    const float supw = sw >= 1.0f ? 1.0f * sw : 1.0f, suph = sh >= 1.0f ? 1.0f * sh : 1.0f;
+    const int miw = (int)ceilf(supw) * 2 + 1, mih = (int)ceilf(suph) * 2 + 1;
+    float *tmp = (float *)malloc((size_t)C * H * OW * sizeof(float));
+    float *w = (float *)malloc((size_t)(miw > mih ? miw : mih) * sizeof(float));
+    for (int ox = 0; ox < OW; ++ox) {
+        int xmin;
+        const int n = aa_weights(ox, W, sw, supw, miw, w, &xmin);
+        for (int c = 0; c < C; ++c)
+            for (int y = 0; y < H; ++y) {
+                const float *s = src + ((size_t)c * H + y) * W + xmin;
+                float t = n > 0 ? s[0] * w[0] : 0.0f;
+                const int blk = fma == 2 ? 1 + ((n - 1) / 4) * 4 : (fma ? 1 : n);      /* taps [1, blk): mul + add */
+                for (int j = 1; j < n; ++j) t = j >= blk ? fmaf(s[j], w[j], t) : t + s[j] * w[j];
+                tmp[((size_t)c * H + y) * OW + ox] = t;
+            }
+    }
+    for (int oy = 0; oy < OH; ++oy) {
+        int ymin;
+        const int n = aa_weights(oy, H, sh, suph, mih, w, &ymin);
+        for (int c = 0; c < C; ++c)
+            for (int x = 0; x < OW; ++x) {
+                const float *s = tmp + ((size_t)c * H + ymin) * OW + x;
+                float t = n > 0 ? s[0] * w[0] : 0.0f;
+                const int blk = fma == 2 ? 1 + ((n - 1) / 4) * 4 : (fma ? 1 : n);
+                for (int j = 1; j < n; ++j) t = j >= blk ? fmaf(s[(size_t)j * OW], w[j], t) : t + s[(size_t)j * OW] * w[j];
+                dst[((size_t)c * OH + oy) * OW + x] = t;
+            }
+    }
+    free(tmp);
+    free(w);
+}

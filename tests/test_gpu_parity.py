@@ -543,3 +543,37 @@ def test_collator_matches_the_live_reference_golden(pose, golden):
         assert torch.equal(out2["depth"], want)
     with pytest.raises(Exception):
         col([{**batch[0], "image": batch[0]["image"].cpu()}])          # CPU tensors: no fallback
+
+
+def test_resize_of_decoded_frames_matches_the_reference_bit_for_bit(pose, oracle, golden):
+    """transforms.Resize(image_size) + depth rescale on the device (pose_resize_bilinear_aa) against the
+    live torchvision outputs frozen in tests/golden/resize.npz and against the C oracle at the dataset's real frame size
+    (1000 x 1002 -> 256 x 256), uint8 and float32 inputs, batched.  Bit-exact."""
+    import importlib
+    tr = importlib.import_module("3dhumanposeestimation_b200.dataset.transforms")
+    gold = golden("resize.npz")
+    for i in range(int(gold["n_cases"])):
+        c, h, w, oh, ow = (int(v) for v in gold["cases"][i])
+        u8 = np.random.default_rng(700 + i).integers(0, 256, (c, h, w), dtype=np.uint8)
+        got8 = tr.Resize((oh, ow))(torch.from_numpy(u8).to(DEV))
+        # float32 frames as the reference builds them on the CPU (`.float() / 255.0`: an IEEE division there; torch's CUDA
+        # division by a scalar multiplies by the reciprocal instead, so the conversion is done before the copy)
+        gotf = tr.resize_frames((torch.from_numpy(u8).float() / 255.0).to(DEV), (oh, ow))
+        assert got8.dtype == torch.float32 and tuple(got8.shape) == (c, oh, ow)
+        assert np.array_equal(got8.cpu().numpy(), gold[f"r{i}"]), (i, np.abs(got8.cpu().numpy() - gold[f"r{i}"]).max())
+        assert np.array_equal(gotf.cpu().numpy(), gold[f"r{i}"])
+        if c == 1:
+            lo, hi = (float(v) for v in gold[f"r{i}_range"])
+            gd = tr.resize_frames(torch.from_numpy(u8).to(DEV)[None], (oh, ow), depth_range=[(lo, hi)])[0]
+            assert np.array_equal(gd.cpu().numpy(), gold[f"r{i}_depth"])
+    # the dataset's frame size, a batch of frames in one launch
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, (3, 3, 1000, 1002), dtype=np.uint8)
+    out = tr.resize_frames(torch.from_numpy(frames).to(DEV), (256, 256)).cpu().numpy()
+    for b in range(3):
+        ref = oracle.tensor_resize_aa(frames[b].astype(np.float32) / np.float32(255.0), 256, 256)
+        assert np.array_equal(out[b], ref), (b, np.abs(out[b] - ref).max())
+    big = tr.resize_frames(torch.from_numpy(frames[:1]).to(DEV), (500, 500)).cpu().numpy()[0]
+    assert np.array_equal(big, oracle.tensor_resize_aa(frames[0].astype(np.float32) / np.float32(255.0), 500, 500))
+    with pytest.raises(Exception):
+        tr.Resize(64)(torch.rand(3, 80, 80))            # CPU tensor: no fallback

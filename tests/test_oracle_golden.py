@@ -129,3 +129,19 @@ def test_infer_prep_oracle_matches_the_live_torch_call():
     k = rng.random((2, 17, 3), dtype=np.float32) * np.float32(640.0)
     kp2, kp3 = infer_ref.normalise_keypoints(k, 640, 480)
     assert np.array_equal(kp2[..., 0], k[..., 0] / np.float32(640)) and np.array_equal(kp3[..., 2], k[..., 2])
+
+
+def test_resize_oracle_reproduces_the_live_torchvision_resize(oracle, golden):
+    """transforms.Resize as the reference applies it to decoded frames (main.py:171-173,
+    chunked_dataset.py:100-129).  The C restatement of ATen's anti-aliased kernel equals the live outputs bit for bit
+    (down-scaling with 5-9 taps, up-scaling, non-square frames)."""
+    gold = golden("resize.npz")
+    for i in range(int(gold["n_cases"])):
+        c, h, w, oh, ow = (int(v) for v in gold["cases"][i])
+        u8 = np.random.default_rng(700 + i).integers(0, 256, (c, h, w), dtype=np.uint8)
+        x = u8.astype(np.float32) / np.float32(255.0)
+        got = oracle.tensor_resize_aa(x, oh, ow)
+        assert np.array_equal(got, gold[f"r{i}"]), (i, np.abs(got - gold[f"r{i}"]).max())
+        if c == 1:
+            lo, hi = (float(v) for v in gold[f"r{i}_range"])
+            assert np.array_equal(got * np.float32(hi - lo) + np.float32(lo), gold[f"r{i}_depth"])
