@@ -99,6 +99,46 @@ __device__ __forceinline__ float dactf(float z) {
     }
     return 1.f;
 }
+// The same on packed fp32 pairs (FFMA2 / FMUL2 / FADD2: two lanes per issue slot).  The BatchNorm passes are instruction
+// bound as much as bandwidth bound (identical shapes: 121 us without an activation, 163 us with SiLU evaluated lane by
+// lane), so their SiLU variants run the affine map, the activation and the reductions on pairs.
+__device__ __forceinline__ float2 tanh2(float2 v) { return make_float2(tanh_fast(v.x), tanh_fast(v.y)); }
+template <int ACT>
+__device__ __forceinline__ float2 actf2(float2 z) {                 // act(z)
+    if (ACT == 2) {
+        const float2 h = __fmul2_rn(z, make_float2(0.5f, 0.5f));
+        return __ffma2_rn(h, tanh2(h), h);                          // 0.5 z (1 + tanh(0.5 z))
+    }
+    if (ACT == 1) return make_float2(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f));
+    return z;
+}
+template <int ACT>
+__device__ __forceinline__ float2 dactf2(float2 z) {                // act'(z)
+    if (ACT == 2) {
+        const float2 t = tanh2(__fmul2_rn(z, make_float2(0.5f, 0.5f)));
+        const float2 sg = __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+        const float2 om = __ffma2_rn(sg, make_float2(-1.0f, -1.0f), make_float2(1.0f, 1.0f));
+        return __fmul2_rn(sg, __ffma2_rn(z, om, make_float2(1.0f, 1.0f)));       // sg (1 + z (1 - sg))
+    }
+    if (ACT == 1) return make_float2(z.x > 0.f ? 1.f : 0.f, z.y > 0.f ? 1.f : 0.f);
+    return make_float2(1.f, 1.f);
+}
+__device__ __forceinline__ void up8p(const uint4 &p, float2 (&f)[4]) {
+    const __nv_bfloat162 *h = (const __nv_bfloat162 *)&p;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f[q] = __bfloat1622float2(h[q]);
+}
+__device__ __forceinline__ uint4 pk8p(const float2 (&f)[4]) {
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[q].x, f[q].y);
+    return *(uint4 *)h;
+}
+__device__ __forceinline__ void ld8p(const float *p, float2 (&f)[4]) {
+    const float4 a = __ldg((const float4 *)p), b = __ldg((const float4 *)p + 1);
+    f[0] = make_float2(a.x, a.y); f[1] = make_float2(a.z, a.w); f[2] = make_float2(b.x, b.y); f[3] = make_float2(b.z, b.w);
+}
+
 // block-level fold of K * 8 per-thread partials over the rsub lanes that share a channel group; the block's result is
 // either WRITTEN to its own slot (deterministic two-stage reductions: out_off = blockIdx * K * C) or added atomically
 template <int K, bool ATOMIC = true>
@@ -222,22 +262,33 @@ __global__ void __launch_bounds__(384)
 bn_apply_kernel(const __nv_bfloat16 *__restrict__ Y, long M, int C, const float *__restrict__ scale_shift, float out_scale,
                 const __nv_bfloat16 *__restrict__ residual, long ld_res, __nv_bfloat16 *__restrict__ out, long ld_out) {
     const RowMap rm(C);
-    float a[8], b[8];
-    ld8f(scale_shift + rm.c0, a);
-    ld8f(scale_shift + C + rm.c0, b);
-    for (long r = (long)blockIdx.x * rm.rpb + rm.rsub; r < M; r += (long)gridDim.x * rm.rpb) {
-        float y[8];
-        up8(__ldg((const uint4 *)(Y + r * C + rm.c0)), y);
+    float2 a[4], b[4];
+    ld8p(scale_shift + rm.c0, a);
+    ld8p(scale_shift + C + rm.c0, b);
+    const float2 os2 = make_float2(out_scale, out_scale);
+    const long step = (long)gridDim.x * rm.rpb;
+    auto body = [&](long r, const uint4 &vy) {
+        float2 y[4];
+        up8p(vy, y);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = out_scale * actf<ACT>(fmaf(y[j], a[j], b[j]));
+        for (int j = 0; j < 4; ++j) y[j] = __fmul2_rn(os2, actf2<ACT>(__ffma2_rn(y[j], a[j], b[j])));
         if (residual != nullptr) {
-            float q[8];
-            up8(__ldg((const uint4 *)(residual + r * ld_res + rm.c0)), q);
+            float2 q[4];
+            up8p(__ldg((const uint4 *)(residual + r * ld_res + rm.c0)), q);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] += q[j];
+            for (int j = 0; j < 4; ++j) y[j] = __fadd2_rn(y[j], q[j]);
         }
-        *(uint4 *)(out + r * ld_out + rm.c0) = pk8(y);
+        *(uint4 *)(out + r * ld_out + rm.c0) = pk8p(y);
+    };
+    long r = (long)blockIdx.x * rm.rpb + rm.rsub;
+    for (; r + 3 * step < M; r += 4 * step) {            // four independent 16-byte loads in flight per thread
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg((const uint4 *)(Y + (r + u * step) * C + rm.c0));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) body(r + u * step, v[u]);
     }
+    for (; r < M; r += step) body(r, __ldg((const uint4 *)(Y + r * C + rm.c0)));
 }
 
 // pass 1 of the backward: sums2[c] += dz, sums2[C + c] += dz * xhat, dz = dA * out_scale * act'(z)
@@ -250,34 +301,45 @@ bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dA, long ld_da, const __n
     // rstd * (sum(dz * y) - mean * sum(dz)).  That drops 16 per-channel constants from the registers of this kernel
     // (80 -> 4 resident CTAs per SM instead of 3) and one FMA per element.
     const RowMap rm(C);
-    float a[8], b[8];
-    ld8f(scale_shift + rm.c0, a);
-    ld8f(scale_shift + C + rm.c0, b);
-    float acc[2][8];
+    float2 a[4], b[4];
+    ld8p(scale_shift + rm.c0, a);
+    ld8p(scale_shift + C + rm.c0, b);
+    float2 s1[4], s2[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+    for (int j = 0; j < 4; ++j) s1[j] = s2[j] = make_float2(0.f, 0.f);
+    const float2 os2 = make_float2(out_scale, out_scale);
     const long step = (long)gridDim.x * rm.rpb;
     long r = (long)blockIdx.x * rm.rpb + rm.rsub;
     auto body = [&](const uint4 &vy, const uint4 &vd) {
-        float y[8], d[8];
-        up8(vy, y);
-        up8(vd, d);
+        float2 y[4], d[4];
+        up8p(vy, y);
+        up8p(vd, d);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float dz = d[j] * out_scale * dactf<ACT>(fmaf(y[j], a[j], b[j]));
-            acc[0][j] += dz;
-            acc[1][j] = fmaf(dz, y[j], acc[1][j]);
+        for (int j = 0; j < 4; ++j) {
+            const float2 dz = __fmul2_rn(__fmul2_rn(d[j], os2), dactf2<ACT>(__ffma2_rn(y[j], a[j], b[j])));
+            s1[j] = __fadd2_rn(s1[j], dz);
+            s2[j] = __ffma2_rn(dz, y[j], s2[j]);
         }
     };
-    for (; r + step < M; r += 2 * step) {               // two rows = four independent 16-byte loads in flight per thread
-        const uint4 y0 = __ldg((const uint4 *)(Y + r * C + rm.c0)), d0 = __ldg((const uint4 *)(dA + r * ld_da + rm.c0));
-        const uint4 y1 = __ldg((const uint4 *)(Y + (r + step) * C + rm.c0)), d1 = __ldg((const uint4 *)(dA + (r + step) * ld_da + rm.c0));
-        body(y0, d0);
-        body(y1, d1);
+    for (; r + 3 * step < M; r += 4 * step) {           // four rows = eight independent 16-byte loads in flight per thread
+        uint4 vy[4], vd[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            vy[u] = __ldg((const uint4 *)(Y + (r + u * step) * C + rm.c0));
+            vd[u] = __ldg((const uint4 *)(dA + (r + u * step) * ld_da + rm.c0));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) body(vy[u], vd[u]);
     }
     for (; r < M; r += step) {
         const uint4 y0 = __ldg((const uint4 *)(Y + r * C + rm.c0)), d0 = __ldg((const uint4 *)(dA + r * ld_da + rm.c0));
         body(y0, d0);
+    }
+    float acc[2][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        acc[0][2 * j] = s1[j].x; acc[0][2 * j + 1] = s1[j].y;
+        acc[1][2 * j] = s2[j].x; acc[1][2 * j + 1] = s2[j].y;
     }
     rowmap_fold<2, false>(rm, C, acc, partials, (long)blockIdx.x * 2 * C);
 }
@@ -309,21 +371,35 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dA, long ld_da, const __nv
                     const float *__restrict__ scale_shift, const float *__restrict__ coef, float out_scale,
                     __nv_bfloat16 *__restrict__ dY) {
     const RowMap rm(C);
-    float a[8], b[8], k2[8], k3[8];
-    ld8f(scale_shift + rm.c0, a);
-    ld8f(scale_shift + C + rm.c0, b);
-    ld8f(coef + rm.c0, k2);
-    ld8f(coef + C + rm.c0, k3);
-    for (long r = (long)blockIdx.x * rm.rpb + rm.rsub; r < M; r += (long)gridDim.x * rm.rpb) {
-        float y[8], d[8];
-        up8(__ldg((const uint4 *)(Y + r * C + rm.c0)), y);
-        up8(__ldg((const uint4 *)(dA + r * ld_da + rm.c0)), d);
+    float2 a[4], b[4], k2[4], k3[4];
+    ld8p(scale_shift + rm.c0, a);
+    ld8p(scale_shift + C + rm.c0, b);
+    ld8p(coef + rm.c0, k2);
+    ld8p(coef + C + rm.c0, k3);
+    const float2 os2 = make_float2(out_scale, out_scale);
+    const long step = (long)gridDim.x * rm.rpb;
+    auto body = [&](long r, const uint4 &vy, const uint4 &vd) {
+        float2 y[4], d[4];
+        up8p(vy, y);
+        up8p(vd, d);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float dz = d[j] * out_scale * dactf<ACT>(fmaf(y[j], a[j], b[j]));
-            d[j] = fmaf(a[j], dz, -fmaf(k2[j], y[j], k3[j]));
+        for (int j = 0; j < 4; ++j) {
+            const float2 dz = __fmul2_rn(__fmul2_rn(d[j], os2), dactf2<ACT>(__ffma2_rn(y[j], a[j], b[j])));
+            const float2 t = __ffma2_rn(k2[j], y[j], k3[j]);
+            d[j] = __ffma2_rn(a[j], dz, make_float2(-t.x, -t.y));              // a dz - (k2 y + k3)
         }
-        *(uint4 *)(dY + r * C + rm.c0) = pk8(d);
+        *(uint4 *)(dY + r * C + rm.c0) = pk8p(d);
+    };
+    long r = (long)blockIdx.x * rm.rpb + rm.rsub;
+    for (; r + step < M; r += 2 * step) {                // two rows = four independent 16-byte loads in flight per thread
+        const uint4 y0 = __ldg((const uint4 *)(Y + r * C + rm.c0)), d0 = __ldg((const uint4 *)(dA + r * ld_da + rm.c0));
+        const uint4 y1 = __ldg((const uint4 *)(Y + (r + step) * C + rm.c0)), d1 = __ldg((const uint4 *)(dA + (r + step) * ld_da + rm.c0));
+        body(r, y0, d0);
+        body(r + step, y1, d1);
+    }
+    for (; r < M; r += step) {
+        const uint4 y0 = __ldg((const uint4 *)(Y + r * C + rm.c0)), d0 = __ldg((const uint4 *)(dA + r * ld_da + rm.c0));
+        body(r, y0, d0);
     }
 }
 
