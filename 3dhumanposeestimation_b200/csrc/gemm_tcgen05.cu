@@ -75,9 +75,10 @@ struct ConvGeom {          // MODE 1 only
     int cw;                // MODE 2: channels per B block (64: 128-byte pixels, SWIZZLE_128B; 32: 64-byte pixels, SWIZZLE_64B)
 };
 
-template <int BN, int kStages, int BKC, int TMA_EPI = 0>
+template <int BN, int kStages, int BKC, int TMA_EPI = 0, int CG2 = 0>
 struct GemmSmem {
-    static constexpr int kABytes = BM * BKC * 2, kBBytes = BN * BKC * 2;
+    // CG2 (CTA pair): each CTA of the pair keeps its 128 rows of A and HALF of the B tile
+    static constexpr int kABytes = BM * BKC * 2, kBBytes = (BN >> CG2) * BKC * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarrierBytes = 1024;                   // keeps the staging buffers 1024 B aligned (TMA swizzle)
     static constexpr int kStagePitch = 144;                      // 32 fp32 + 16 B pad: conflict-free 16 B accesses
@@ -377,7 +378,7 @@ __device__ __forceinline__ uint32_t sw64(int r, int c) { return (uint32_t)(r * 6
 // accumulators live the exact-GELU / derivative epilogues kept ~58 words per thread in local memory); the TMEM stage is
 // released after the last load.
 template <int ACT>
-__device__ __forceinline__ void epilogue_tma(uint32_t tmem_chunk, uint64_t *acc_empty_bar, bool release, const Epilogue &ep,
+__device__ __forceinline__ void epilogue_tma(uint32_t tmem_chunk, uint32_t acc_empty_bar, bool release, const Epilogue &ep,
                                              const CUtensorMap *map_c, const CUtensorMap *map_pre, uint32_t out_stg,
                                              uint32_t aux_stg, uint64_t *auxbar, uint32_t &aux_phase, long row0, int lane,
                                              int col0) {
@@ -394,7 +395,7 @@ __device__ __forceinline__ void epilogue_tma(uint32_t tmem_chunk, uint64_t *acc_
         if (c == 3 && release) {                       // the warp's last chunk has left TMEM: release the accumulator stage
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty_bar)) : "memory");
+            if (lane == 0) mbar_arrive_cluster(acc_empty_bar);
         }
         float x[8], g[8];
 #pragma unroll
@@ -485,7 +486,7 @@ __device__ __forceinline__ void sts64f(uint32_t saddr, float2 v) {
 }
 // One staging region R per warp is reused in sequence: residual tile (TMA load) -> fp32 half tiles of the column reduction
 // -> bf16 output tile (TMA store); 2560 B, so the kernel keeps the five-stage operand ring of the other TMA epilogue.
-__device__ __forceinline__ void epilogue_lean(uint32_t tmem_chunk, uint64_t *acc_empty_bar, bool release, const Epilogue &ep,
+__device__ __forceinline__ void epilogue_lean(uint32_t tmem_chunk, uint32_t acc_empty_bar, bool release, const Epilogue &ep,
                                               const CUtensorMap *map_c, uint32_t R, float2 (&st)[2][2], uint64_t *auxbar,
                                               uint32_t &aux_phase, long row0, int lane, int col0) {
     uint32_t acc[32];
@@ -493,7 +494,7 @@ __device__ __forceinline__ void epilogue_lean(uint32_t tmem_chunk, uint64_t *acc
     if (release) {                                      // the warp's last chunk has left TMEM: release the accumulator stage
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty_bar)) : "memory");
+        if (lane == 0) mbar_arrive_cluster(acc_empty_bar);
     }
     if (ep.residual != nullptr) {                       // + residual tile (TMA load issued by the caller)
         mbar_wait(auxbar, aux_phase);
@@ -560,13 +561,13 @@ __device__ __forceinline__ void epilogue_lean(uint32_t tmem_chunk, uint64_t *acc
 // epilogue accumulates with red.global.add (ep.accumulate).
 // TMA_EPI selects the epilogue at compile time (each instantiation carries only one of the two: the combined kernel was
 // 28 K instructions and measurably slower on every path).
-template <int BN, int kStages, int BKC, int MODE, int A_MN, int B_MN, int TMA_EPI>
+template <int BN, int kStages, int BKC, int MODE, int A_MN, int B_MN, int TMA_EPI, int CG2 = 0>
 __global__ void __launch_bounds__(kGemmThreadsP, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_aux,
                     const __grid_constant__ CUtensorMap map_pre, int M, int N, int K, const Epilogue ep, const ConvGeom cg,
                     int m_tiles, int n_tiles, int kb_per, int k_splits) {
-    using S = GemmSmem<BN, kStages, BKC, TMA_EPI>;
+    using S = GemmSmem<BN, kStages, BKC, TMA_EPI, CG2>;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);  // swizzle atoms: 1024 B
     unsigned char *bars = smem + kStages * S::kStageBytes;
@@ -584,39 +585,53 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int total_tiles = mn_tiles * k_splits;      // work items
     constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // power of two >= 32 (BN in {32, 64, 128})
 
+    // CG2: the two CTAs of a cluster form a pair; rank 0 (the leader) issues the M = 256 MMAs for both.  `m_tiles` then counts
+    // 256-row PAIR tiles, the pair walks them together and this CTA owns rows [mt2 * 256 + crank * 128, + 128) of each.
+    const uint32_t crank = CG2 ? cluster_ctarank() : 0u;
+    const int cta_id = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, cta_n = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(full + s, 1);
+            mbar_init(full + s, CG2 ? 2 : 1);            // pair: both CTAs' producers arrive (with their byte counts) on the leader's
             mbar_init(empty + s, 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(acc_full + s, 1);
-            mbar_init(acc_empty + s, kEpiWarps);
+            mbar_init(acc_empty + s, CG2 ? 2 * kEpiWarps : kEpiWarps);   // pair: the epilogue warps of both CTAs release the leader
         }
         for (int s = 0; s < 16; ++s) mbar_init(aux_bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG2) cluster_sync_all();                         // the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // where the epilogue warps release an accumulator stage: the leader's acc_empty barriers
+    const uint32_t acc_rel[2] = {CG2 ? mapa_u32(smem_u32(acc_empty), 0) : smem_u32(acc_empty),
+                                 CG2 ? mapa_u32(smem_u32(acc_empty + 1), 0) : smem_u32(acc_empty + 1)};
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
             uint32_t it = 0;
-            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+            for (int item = cta_id; item < total_tiles; item += cta_n) {
                 const int split = item / mn_tiles, tile = item - split * mn_tiles;
                 const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
-                const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BN;
+                const int mt2 = tile / n_tiles, n0 = (tile - mt2 * n_tiles) * BN;
+                const int mt = CG2 ? mt2 * 2 + (int)crank : mt2;
                 // Every index below advances incrementally: this single thread issues all loads of the CTA, and the runtime
                 // integer divisions that used to decode (tap, channel chunk) / (patch column, row, image) from the block
                 // number on every k-block were the critical path of the convolution kernels.
@@ -661,6 +676,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const uint32_t ph = (it / kStages) & 1;
                     mbar_wait(empty + s, ph ^ 1);
                     unsigned char *sa = smem + s * S::kStageBytes, *sb = sa + S::kABytes;
+                    if (CG2) {
+                        // CTA pair: this CTA's A rows and its half of the B tile; the bytes are counted on the leader's barrier
+                        const uint32_t lf = mapa_u32(smem_u32(full + s), 0);
+                        mbar_expect_tx_cluster(lf, S::kStageBytes);
+                        if (A_MN) {
+                            tma_load_2d_2sm(sa, &map_a, lf, mt * BM, kb * BKC);
+                            tma_load_2d_2sm(sa + BKC * 128, &map_a, lf, mt * BM + 64, kb * BKC);
+                        } else {
+                            tma_load_2d_2sm(sa, &map_a, lf, kb * BKC, mt * BM);
+                        }
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < BN / 128; ++j)
+                                tma_load_2d_2sm(sb + j * BKC * 128, &map_w, lf, n0 + ((int)crank * (BN / 128) + j) * 64, kb * BKC);
+                        } else {
+                            tma_load_2d_2sm(sb, &map_w, lf, kb * BKC, n0 + (int)crank * (BN / 2));
+                        }
+                        continue;
+                    }
                     mbar_expect_tx(full + s, S::kStageBytes);
                     if (MODE == 2) {
                         // convolution weight gradient: the contraction block is a patch of 64 OUTPUT PIXELS; A = dY^T
@@ -710,9 +744,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+        constexpr uint32_t idesc = umma_idesc_bf16(CG2 ? 2 * BM : BM, BN, A_MN, B_MN);
         uint32_t it = 0, tile_iter = 0;
-        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++tile_iter) {
+        for (int item = (CG2 && crank != 0) ? total_tiles : cta_id; item < total_tiles; item += cta_n, ++tile_iter) {   // pair: leader only
             const int split = item / mn_tiles;
             const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
             const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
@@ -736,11 +770,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const uint64_t kbs = b32 ? 64 : (B_MN ? 128 : 2);
 #pragma unroll
                     for (int k = 0; k < BKC / UMMA_K; ++k) {
-                        tc_mma_f16(tmem_acc, da + (uint64_t)k * ka, db + (uint64_t)k * kbs, idesc,
-                                   ((kb - kb0) | k) ? 1u : 0u);
+                        if (CG2)
+                            tc_mma_f16_2sm(tmem_acc, da + (uint64_t)k * ka, db + (uint64_t)k * kbs, idesc, ((kb - kb0) | k) ? 1u : 0u);
+                        else
+                            tc_mma_f16(tmem_acc, da + (uint64_t)k * ka, db + (uint64_t)k * kbs, idesc, ((kb - kb0) | k) ? 1u : 0u);
                     }
-                    tc_commit(empty + s);                          // frees the smem stage when these MMAs retire
-                    if (kb == kb1 - 1) tc_commit(acc_full + as);   // accumulator complete
+                    if (CG2) {
+                        tc_commit_2sm(empty + s, 3);                          // frees this stage in BOTH CTAs
+                        if (kb == kb1 - 1) tc_commit_2sm(acc_full + as, 3);   // accumulator complete (each CTA reads its own TMEM)
+                    } else {
+                        tc_commit(empty + s);                          // frees the smem stage when these MMAs retire
+                        if (kb == kb1 - 1) tc_commit(acc_full + as);   // accumulator complete
+                    }
                 }
                 __syncwarp();
             }
@@ -766,10 +807,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             sts128(wstat0 + lane * 16, 0u, 0u, 0u, 0u);
             __syncwarp();
         }
-        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++tile_iter) {
+        for (int item = cta_id; item < total_tiles; item += cta_n, ++tile_iter) {
             const int tile = item % mn_tiles;
             const uint32_t as = tile_iter & 1, aph = (tile_iter >> 1) & 1;
-            const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BN;
+            const int mt2 = tile / n_tiles, n0 = (tile - mt2 * n_tiles) * BN;
+            const int mt = CG2 ? mt2 * 2 + (int)crank : mt2;
             const int r = quarter * 32 + lane;
             if constexpr (TMA_EPI == 2) {
                 // ---- lean plain epilogue (see epilogue_lean) ----
@@ -797,12 +839,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     }
                     const uint32_t chunk = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(c * 32);
                     if (mine) {
-                        epilogue_lean(chunk, acc_empty + as, last, ep, &map_c, stg, lst[ci], aux_bar + (warp - 2), aux_phase, row0, lane,
+                        epilogue_lean(chunk, acc_rel[as], last, ep, &map_c, stg, lst[ci], aux_bar + (warp - 2), aux_phase, row0, lane,
                                       col0);
                     } else if (last) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
+                        if (lane == 0) mbar_arrive_cluster(acc_rel[as]);
                     }
                 }
             } else if constexpr (TMA_EPI != 0) {
@@ -834,15 +876,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const uint32_t chunk = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(c * 32);
                     if (mine) {
                         switch (ep.act) {
-#define EPI_TMA(A_) case A_: epilogue_tma<A_>(chunk, acc_empty + as, last, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
+#define EPI_TMA(A_) case A_: epilogue_tma<A_>(chunk, acc_rel[as], last, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
                             EPI_TMA(0) EPI_TMA(1) EPI_TMA(2) EPI_TMA(3) EPI_TMA(4) EPI_TMA(5) EPI_TMA(6)
-                            default: epilogue_tma<7>(chunk, acc_empty + as, last, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
+                            default: epilogue_tma<7>(chunk, acc_rel[as], last, ep, &map_c, &map_pre, stg, stg + 2048, aux_bar + (warp - 2), aux_phase, row0, lane, col0); break;
 #undef EPI_TMA
                         }
                     } else if (last) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
+                        if (lane == 0) mbar_arrive_cluster(acc_rel[as]);
                     }
                 }
             } else {
@@ -875,7 +917,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_empty + as)) : "memory");
+            if (lane == 0) mbar_arrive_cluster(acc_rel[as]);
 #pragma unroll
             for (int ci = 0; ci < kMine; ++ci) {
                 const int c = cgrp + 4 * ci;
@@ -935,8 +977,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (TMA_EPI != 0 && warp >= 2 && lane == 0) tma_store_wait_all();      // bulk stores of this thread have completed
     tc_fence_before();
     __syncthreads();
+    if (CG2) cluster_sync_all();          // the leader's MMAs read the peer's shared memory and write its TMEM: leave together
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        if (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -1000,7 +1044,7 @@ static int make_map_tile32(CUtensorMap *map, const void *ptr, long rows, long co
 
 template <int BN, int kStages, int BKC, int MODE, int A_MN = 0, int B_MN = 0>
 static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int N, int K, const Epilogue &ep_in,
-                       const ConvGeom &cg, int m_tiles, cudaStream_t s, int k_splits = 1) {
+                       const ConvGeom &cg, int m_tiles, cudaStream_t s, int k_splits = 1, bool pair = false) {
     Epilogue ep = ep_in;
     CUtensorMap mc = {}, maux = {}, mpre = {};
     // Epilogue choice.  Round 1 measured the row-per-lane TMA epilogue ahead only for epilogues with real per-element work
@@ -1073,6 +1117,44 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
         return launch_bn_finalize_parts(bn->partials, parts, (long)bn->count, bn->gamma, bn->beta, bn->eps, bn->momentum, N,
                                         bn->mean_rstd, bn->scale_shift, bn->running_mean, bn->running_var, s);
     }
+    if constexpr (MODE == 0 && BN == 256) {
+        if (pair) {
+            // CTA pairs (cta_group::2): clusters of two CTAs, each pair walks 256-row tiles; B tile halved per CTA, so the
+            // operand ring is 32 KB per stage (4 stages beside the transposing epilogue's staging, 5 beside the TMA ones)
+            using P0 = GemmSmem<BN, 4, BKC, 0, 1>;
+            using P1 = GemmSmem<BN, 5, BKC, 1, 1>;
+            static_assert(P0::kTotal <= 232448 && P1::kTotal <= 232448, "shared memory budget");
+            auto pk_plain = gemm_bf16_tn_kernel<BN, 4, BKC, MODE, A_MN, B_MN, 0, 1>;
+            auto pk_tma = gemm_bf16_tn_kernel<BN, 5, BKC, MODE, A_MN, B_MN, 1, 1>;
+            auto pk_lean = gemm_bf16_tn_kernel<BN, 5, BKC, MODE, A_MN, B_MN, 2, 1>;
+            static bool pconf = false;
+            if (!pconf) {
+                cudaError_t ce = cudaFuncSetAttribute(pk_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, P0::kTotal);
+                if (ce == cudaSuccess) ce = cudaFuncSetAttribute(pk_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::kTotal);
+                if (ce == cudaSuccess) ce = cudaFuncSetAttribute(pk_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, P1::kTotal);
+                if (ce != cudaSuccess) return (int)ce;
+                pconf = true;
+            }
+            auto pk = lean ? pk_lean : (ep.tma ? pk_tma : pk_plain);
+            const int m_pairs = (m_tiles + 1) / 2;
+            const long ptotal = (long)m_pairs * n_tiles * k_splits;
+            const int pairs = (int)(ptotal < kNumSMs / 2 ? ptotal : kNumSMs / 2);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * pairs);
+            cfg.blockDim = dim3(kGemmThreadsP);
+            cfg.dynamicSmemBytes = lean || ep.tma ? P1::kTotal : P0::kTotal;
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            cudaError_t ce = cudaLaunchKernelEx(&cfg, pk, ma, mw, mc, maux, mpre, M, N, K, ep, cg, m_pairs, n_tiles, kb_per, k_splits);
+            return ce == cudaSuccess ? launch_status() : (int)ce;
+        }
+    }
     kern<<<grid, kGemmThreadsP, smem_bytes, s>>>(ma, mw, mc, maux, mpre, M, N, K, ep, cg, m_tiles, n_tiles, kb_per, k_splits);
     return launch_status();
 }
@@ -1097,16 +1179,26 @@ static bool wide_tile_fwd_ok(const Epilogue &ep, int N, int K, int m_tiles) {
     return wide_tile_ok(ep, N, K, m_tiles, 1);
 }
 
+// CTA pairs pay off where the main loop is bound by operand traffic (L2 requests / shared-memory fill): large tiles counts,
+// long contractions.  POSE_GEMM_PAIR=0 disables them (A/B switch for measurements).
+static bool pair_ok(const Epilogue &ep, int M, int N, int K, int k_splits) {
+    static const bool on = getenv("POSE_GEMM_PAIR") == nullptr || atoi(getenv("POSE_GEMM_PAIR")) != 0;
+    if (!on || ep.stats != nullptr || N % 256 || M < 256) return false;
+    const long pair_items = (long)((M + 255) / 256) * (N / 256) * (k_splits > 1 ? k_splits : 1);
+    return pair_items >= kNumSMs / 4;
+}
+
 template <int BKC, int MODE>
 static int dispatch_bn(const CUtensorMap &ma, const void *W, int ldw, int M, int N, int K, const Epilogue &ep,
                        const ConvGeom &cg, int m_tiles, cudaStream_t s) {
     CUtensorMap mw;
     int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
     if (MODE == 0 && BKC == 64 && wide_tile_fwd_ok(ep, N, K, m_tiles)) bn = 256;
-    int e = make_map_2d(&mw, W, N, K, ldw, bn, BKC);
+    const bool pair = MODE == 0 && bn == 256 && pair_ok(ep, M, N, K, 1);
+    int e = make_map_2d(&mw, W, N, K, ldw, pair ? bn / 2 : bn, BKC);        // a CTA of a pair loads half of the B tile
     if (e) return e;
     if constexpr (MODE == 0 && BKC == 64) {
-        if (bn == 256) return launch_gemm<256, 3, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
+        if (bn == 256) return launch_gemm<256, 3, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s, 1, pair);
     }
     if (bn == 32) return launch_gemm<32, 6, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
     if (bn == 64) return launch_gemm<64, 6, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
@@ -1217,8 +1309,9 @@ POSE_API int pose_gemm_bf16_tr(const void *A, long lda, int a_mn, const void *W,
     }
     if (wide_tile_ok(ep, N, K / (k_splits > 1 ? k_splits : 1), m_tiles, k_splits > 1 ? 2 * k_splits : 1)) {
         if (k_splits > 1) k_splits *= 2;                 // the caller sized the splits for 128-column tiles
-        if (a_mn) return launch_gemm<256, 3, 64, 0, 1, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);
-        return launch_gemm<256, 3, 64, 0, 0, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);
+        const bool pair = pair_ok(ep, M, N, K, k_splits);
+        if (a_mn) return launch_gemm<256, 3, 64, 0, 1, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits, pair);
+        return launch_gemm<256, 3, 64, 0, 0, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits, pair);
     }
     if (a_mn) return launch_gemm<128, 4, 64, 0, 1, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);
     return launch_gemm<128, 4, 64, 0, 0, 1>(ma, mw, M, N, K, ep, cg, m_tiles, s, k_splits);
