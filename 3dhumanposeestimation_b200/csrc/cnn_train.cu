@@ -5,6 +5,7 @@
 // the per-step re-layout of the parameters the tensor-core kernels read (one table-driven launch).
 // Channels-last bf16 activations, fp32 statistics and parameter gradients (accumulated like torch's .grad).
 #include "tc_common.cuh"
+#include "rowpipe.cuh"
 
 namespace pose {
 
@@ -141,9 +142,11 @@ __device__ __forceinline__ void ld8p(const float *p, float2 (&f)[4]) {
 
 // block-level fold of K * 8 per-thread partials over the rsub lanes that share a channel group; the block's result is
 // either WRITTEN to its own slot (deterministic two-stage reductions: out_off = blockIdx * K * C) or added atomically
-template <int K, bool ATOMIC = true>
+template <int K, bool ATOMIC = true, bool DYN = false>
 __device__ __forceinline__ void rowmap_fold(const RowMap &rm, int C, float (&acc)[K][8], float *__restrict__ out, long out_off) {
-    __shared__ float red[384 * 8 * K];
+    __shared__ float red_static[DYN ? 1 : 384 * 8 * K];
+    float *red = DYN ? (float *)g_rowpipe : red_static;      // DYN: the row pipeline's ring (drained) holds the scratch
+    if (DYN) __syncthreads();
     const int G = C >> 3;
 #pragma unroll
     for (int k = 0; k < K; ++k)
@@ -166,36 +169,28 @@ __device__ __forceinline__ void rowmap_fold(const RowMap &rm, int C, float (&acc
 __global__ void __launch_bounds__(384)
 bn_stats_kernel(const __nv_bfloat16 *__restrict__ Y, long M, int C, long ld, float *__restrict__ partials) {
     const RowMap rm(C);
+    float2 s1[4], s2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s1[j] = s2[j] = make_float2(0.f, 0.f);
+    const void *const base[1] = {Y};
+    const long pitch[1] = {ld * 2};
+    row_stream<1>(base, pitch, rm.c0 * 2L, (long)blockIdx.x * rm.rpb + rm.rsub, (long)gridDim.x * rm.rpb, M,
+                  [&](long, const uint4 (&v)[1]) {
+        float2 y[4];
+        up8q(v[0], y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s1[j] = __fadd2_rn(s1[j], y[j]);
+            s2[j] = __ffma2_rn(y[j], y[j], s2[j]);
+        }
+    });
     float acc[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
-    const long step = (long)gridDim.x * rm.rpb;
-    long r = (long)blockIdx.x * rm.rpb + rm.rsub;
-    for (; r + 3 * step < M; r += 4 * step) {           // four independent 16-byte loads in flight per thread
-        uint4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldg((const uint4 *)(Y + (r + u * step) * ld + rm.c0));
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            float y[8];
-            up8(v[u], y);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                acc[0][j] += y[j];
-                acc[1][j] = fmaf(y[j], y[j], acc[1][j]);
-            }
-        }
+    for (int j = 0; j < 4; ++j) {
+        acc[0][2 * j] = s1[j].x; acc[0][2 * j + 1] = s1[j].y;
+        acc[1][2 * j] = s2[j].x; acc[1][2 * j + 1] = s2[j].y;
     }
-    for (; r < M; r += step) {
-        float y[8];
-        up8(__ldg((const uint4 *)(Y + r * ld + rm.c0)), y);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            acc[0][j] += y[j];
-            acc[1][j] = fmaf(y[j], y[j], acc[1][j]);
-        }
-    }
-    rowmap_fold<2, false>(rm, C, acc, partials, (long)blockIdx.x * 2 * C);
+    rowmap_fold<2, false, true>(rm, C, acc, partials, (long)blockIdx.x * 2 * C);
 }
 
 // Second stage of the two-stage reductions: block = 8 channels x 32 part lanes; every lane adds its share of the
@@ -257,8 +252,8 @@ bn_finalize_kernel(const float *__restrict__ partials, int parts, float count, c
 }
 
 // out[r, :] (pitch ld_out) = residual[r, :] + out_scale * act(y * scale + shift)
-template <int ACT>
-__global__ void __launch_bounds__(384)
+template <int ACT, bool RES>
+__global__ void __launch_bounds__(384, RES ? 1 : 3)
 bn_apply_kernel(const __nv_bfloat16 *__restrict__ Y, long M, int C, const float *__restrict__ scale_shift, float out_scale,
                 const __nv_bfloat16 *__restrict__ residual, long ld_res, __nv_bfloat16 *__restrict__ out, long ld_out) {
     const RowMap rm(C);
@@ -266,29 +261,39 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ Y, long M, int C, const float 
     ld8p(scale_shift + rm.c0, a);
     ld8p(scale_shift + C + rm.c0, b);
     const float2 os2 = make_float2(out_scale, out_scale);
-    const long step = (long)gridDim.x * rm.rpb;
-    auto body = [&](long r, const uint4 &vy) {
-        float2 y[4];
-        up8p(vy, y);
+    if (!RES) {
+        // one input tensor and few live registers: ptxas keeps four plain loads in flight and 6 CTAs resident, which
+        // measured slightly faster (70.6 vs 76.5 us on 131072 x 768) than the cp.async ring
+        const long step = (long)gridDim.x * rm.rpb;
+        auto body = [&](long r, const uint4 &vy) {
+            float2 y[4];
+            up8q(vy, y);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) y[j] = __fmul2_rn(os2, actf2<ACT>(__ffma2_rn(y[j], a[j], b[j])));
-        if (residual != nullptr) {
-            float2 q[4];
-            up8p(__ldg((const uint4 *)(residual + r * ld_res + rm.c0)), q);
+            for (int j = 0; j < 4; ++j) y[j] = __fmul2_rn(os2, actf2<ACT>(__ffma2_rn(y[j], a[j], b[j])));
+            *(uint4 *)(out + r * ld_out + rm.c0) = pk8p(y);
+        };
+        long r = (long)blockIdx.x * rm.rpb + rm.rsub;
+        for (; r + 3 * step < M; r += 4 * step) {
+            uint4 v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) y[j] = __fadd2_rn(y[j], q[j]);
+            for (int u = 0; u < 4; ++u) v[u] = ldg_batch(Y + (r + u * step) * C + rm.c0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) body(r + u * step, v[u]);
         }
-        *(uint4 *)(out + r * ld_out + rm.c0) = pk8p(y);
-    };
-    long r = (long)blockIdx.x * rm.rpb + rm.rsub;
-    for (; r + 3 * step < M; r += 4 * step) {            // four independent 16-byte loads in flight per thread
-        uint4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldg((const uint4 *)(Y + (r + u * step) * C + rm.c0));
-#pragma unroll
-        for (int u = 0; u < 4; ++u) body(r + u * step, v[u]);
+        for (; r < M; r += step) body(r, ldg_batch(Y + r * C + rm.c0));
+        return;
     }
-    for (; r < M; r += step) body(r, __ldg((const uint4 *)(Y + r * C + rm.c0)));
+    const void *const base[2] = {Y, residual};
+    const long pitch[2] = {C * 2L, ld_res * 2};
+    row_stream<2>(base, pitch, rm.c0 * 2L, (long)blockIdx.x * rm.rpb + rm.rsub, (long)gridDim.x * rm.rpb, M,
+                  [&](long r, const uint4 (&v)[2]) {
+        float2 y[4], q[4];
+        up8q(v[0], y);
+        up8q(v[1], q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = __fadd2_rn(__fmul2_rn(os2, actf2<ACT>(__ffma2_rn(y[j], a[j], b[j]))), q[j]);
+        *(uint4 *)(out + r * ld_out + rm.c0) = pk8p(y);
+    });
 }
 
 // pass 1 of the backward: sums2[c] += dz, sums2[C + c] += dz * xhat, dz = dA * out_scale * act'(z)
@@ -308,40 +313,27 @@ bn_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dA, long ld_da, const __n
 #pragma unroll
     for (int j = 0; j < 4; ++j) s1[j] = s2[j] = make_float2(0.f, 0.f);
     const float2 os2 = make_float2(out_scale, out_scale);
-    const long step = (long)gridDim.x * rm.rpb;
-    long r = (long)blockIdx.x * rm.rpb + rm.rsub;
-    auto body = [&](const uint4 &vy, const uint4 &vd) {
+    const void *const base[2] = {Y, dA};
+    const long pitch[2] = {C * 2L, ld_da * 2};
+    row_stream<2>(base, pitch, rm.c0 * 2L, (long)blockIdx.x * rm.rpb + rm.rsub, (long)gridDim.x * rm.rpb, M,
+                  [&](long, const uint4 (&v)[2]) {
         float2 y[4], d[4];
-        up8p(vy, y);
-        up8p(vd, d);
+        up8q(v[0], y);
+        up8q(v[1], d);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 dz = __fmul2_rn(__fmul2_rn(d[j], os2), dactf2<ACT>(__ffma2_rn(y[j], a[j], b[j])));
             s1[j] = __fadd2_rn(s1[j], dz);
             s2[j] = __ffma2_rn(dz, y[j], s2[j]);
         }
-    };
-    for (; r + 3 * step < M; r += 4 * step) {           // four rows = eight independent 16-byte loads in flight per thread
-        uint4 vy[4], vd[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            vy[u] = __ldg((const uint4 *)(Y + (r + u * step) * C + rm.c0));
-            vd[u] = __ldg((const uint4 *)(dA + (r + u * step) * ld_da + rm.c0));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) body(vy[u], vd[u]);
-    }
-    for (; r < M; r += step) {
-        const uint4 y0 = __ldg((const uint4 *)(Y + r * C + rm.c0)), d0 = __ldg((const uint4 *)(dA + r * ld_da + rm.c0));
-        body(y0, d0);
-    }
+    });
     float acc[2][8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         acc[0][2 * j] = s1[j].x; acc[0][2 * j + 1] = s1[j].y;
         acc[1][2 * j] = s2[j].x; acc[1][2 * j + 1] = s2[j].y;
     }
-    rowmap_fold<2, false>(rm, C, acc, partials, (long)blockIdx.x * 2 * C);
+    rowmap_fold<2, false, true>(rm, C, acc, partials, (long)blockIdx.x * 2 * C);
 }
 
 // between the passes: fold the per-block partials in a fixed order, accumulate dgamma += s2, dbeta += s1, and emit the two
@@ -377,11 +369,13 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dA, long ld_da, const __nv
     ld8p(coef + rm.c0, k2);
     ld8p(coef + C + rm.c0, k3);
     const float2 os2 = make_float2(out_scale, out_scale);
-    const long step = (long)gridDim.x * rm.rpb;
-    auto body = [&](long r, const uint4 &vy, const uint4 &vd) {
+    const void *const base[2] = {Y, dA};
+    const long pitch[2] = {C * 2L, ld_da * 2};
+    row_stream<2>(base, pitch, rm.c0 * 2L, (long)blockIdx.x * rm.rpb + rm.rsub, (long)gridDim.x * rm.rpb, M,
+                  [&](long r, const uint4 (&v)[2]) {
         float2 y[4], d[4];
-        up8p(vy, y);
-        up8p(vd, d);
+        up8q(v[0], y);
+        up8q(v[1], d);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 dz = __fmul2_rn(__fmul2_rn(d[j], os2), dactf2<ACT>(__ffma2_rn(y[j], a[j], b[j])));
@@ -389,18 +383,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dA, long ld_da, const __nv
             d[j] = __ffma2_rn(a[j], dz, make_float2(-t.x, -t.y));              // a dz - (k2 y + k3)
         }
         *(uint4 *)(dY + r * C + rm.c0) = pk8p(d);
-    };
-    long r = (long)blockIdx.x * rm.rpb + rm.rsub;
-    for (; r + step < M; r += 2 * step) {                // two rows = four independent 16-byte loads in flight per thread
-        const uint4 y0 = __ldg((const uint4 *)(Y + r * C + rm.c0)), d0 = __ldg((const uint4 *)(dA + r * ld_da + rm.c0));
-        const uint4 y1 = __ldg((const uint4 *)(Y + (r + step) * C + rm.c0)), d1 = __ldg((const uint4 *)(dA + (r + step) * ld_da + rm.c0));
-        body(r, y0, d0);
-        body(r + step, y1, d1);
-    }
-    for (; r < M; r += step) {
-        const uint4 y0 = __ldg((const uint4 *)(Y + r * C + rm.c0)), d0 = __ldg((const uint4 *)(dA + r * ld_da + rm.c0));
-        body(r, y0, d0);
-    }
+    });
 }
 
 // ---- depthwise 3x3 backward ---------------------------------------------------------------------------------
@@ -648,21 +631,29 @@ gate_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dO, const __nv_bfloat16
     float acc[1][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
-    for (long r = (long)blockIdx.x * rm.rpb + rm.rsub; r < HW; r += (long)gridDim.x * rm.rpb) {
-        float d[8], x[8];
-        up8(__ldg((const uint4 *)(dO + (base + r) * C + rm.c0)), d);
-        up8(__ldg((const uint4 *)(X + (base + r) * C + rm.c0)), x);
+    const void *const src[2] = {dO + base * C, X + base * C};
+    const long pitch[2] = {C * 2L, C * 2L};
+    float2 a2[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[0][j] = fmaf(d[j], x[j], acc[0][j]);
-    }
-    rowmap_fold<1>(rm, C, acc, out, (long)blockIdx.y * C);
+    for (int j = 0; j < 4; ++j) a2[j] = make_float2(0.f, 0.f);
+    row_stream<2>(src, pitch, rm.c0 * 2L, (long)blockIdx.x * rm.rpb + rm.rsub, (long)gridDim.x * rm.rpb, HW,
+                  [&](long, const uint4 (&v)[2]) {
+        float2 d[4], x[4];
+        up8q(v[0], d);
+        up8q(v[1], x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a2[j] = __ffma2_rn(d[j], x[j], a2[j]);
+    });
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[0][2 * j] = a2[j].x; acc[0][2 * j + 1] = a2[j].y; }
+    rowmap_fold<1, true, true>(rm, C, acc, out, (long)blockIdx.y * C);
 }
 
 // dX[b,p,c] = add + dOut[b,p,c] * gate[b,c] + dmean[b,c] * inv_hw
 // grid (row blocks, B); a thread owns one 8-channel group of its image for its whole life (gate and dmean / HW in
 // registers) and walks rows -- no per-element index arithmetic (the flat-index version decoded (image, channel group) with
 // 64-bit divisions per element and ran at half the bandwidth of its neighbours)
-__global__ void __launch_bounds__(384)
+__global__ void __launch_bounds__(384, 2)
 gate_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ gate, const __nv_bfloat16 *__restrict__ dmean,
                       float inv_hw, long HW, int C, const __nv_bfloat16 *__restrict__ add, __nv_bfloat16 *__restrict__ dX) {
     const RowMap rm(C);
@@ -679,24 +670,51 @@ gate_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dO, const float *__restr
         for (int j = 0; j < 8; ++j) m[j] *= inv_hw;
     }
     const long step = (long)gridDim.x * rm.rpb;
-    for (long r = (long)blockIdx.x * rm.rpb + rm.rsub; r < HW; r += step) {
-        const long off = (base + r) * C + rm.c0;
-        float d[8];
-        if (dO != nullptr) {
-            up8(__ldg((const uint4 *)(dO + off)), d);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) d[j] = fmaf(d[j], g[j], m[j]);
-        } else {
+    long r = (long)blockIdx.x * rm.rpb + rm.rsub;
+    if (dO == nullptr) {                               // broadcast of dmean / HW (+ add): gradient of a global average
+        for (; r < HW; r += step) {
+            const long off = (base + r) * C + rm.c0;
+            float d[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) d[j] = m[j];
+            if (add != nullptr) {
+                float a[8];
+                up8(__ldg((const uint4 *)(add + off)), a);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) d[j] += a[j];
+            }
+            *(uint4 *)(dX + off) = pk8(d);
         }
+        return;
+    }
+    auto body = [&](long off, const uint4 &vd, const uint4 &va) {
+        float d[8];
+        up8(vd, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = fmaf(d[j], g[j], m[j]);
         if (add != nullptr) {
             float a[8];
-            up8(__ldg((const uint4 *)(add + off)), a);
+            up8(va, a);
 #pragma unroll
             for (int j = 0; j < 8; ++j) d[j] += a[j];
         }
         *(uint4 *)(dX + off) = pk8(d);
+    };
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    for (; r + 3 * step < HW; r += 4 * step) {         // a batch of four (eight with `add`) 16-byte loads in flight per thread
+        uint4 vd[4], va[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long off = (base + r + u * step) * C + rm.c0;
+            vd[u] = ldg_batch(dO + off);
+            va[u] = add != nullptr ? ldg_batch(add + off) : z4;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) body((base + r + u * step) * C + rm.c0, vd[u], va[u]);
+    }
+    for (; r < HW; r += step) {
+        const long off = (base + r) * C + rm.c0;
+        body(off, ldg_batch(dO + off), add != nullptr ? ldg_batch(add + off) : z4);
     }
 }
 
@@ -1106,14 +1124,17 @@ static int bn_parts(long M, int C, long cap_floats, int per_sm) {
     return (int)(parts < 1 ? 1 : parts);
 }
 template <class K>
-static int resident_ctas(K kern, int threads) {
+static int resident_ctas(K kern, int threads, size_t smem = 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, 0) != cudaSuccess || n < 1) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem) != cudaSuccess || n < 1) n = 1;
     return n > 8 ? 8 : n;
 }
 static int one_wave(int grid, int per_sm) { return grid < kNumSMs * per_sm ? grid : kNumSMs * per_sm; }   // grid-stride kernels
 static int bn_stats_parts(long M, int C, long cap_floats) {
-    return bn_parts(M, C, cap_floats, resident_ctas(bn_stats_kernel, rowmap_threads(C)));
+    static const bool once = (rowpipe_optin(bn_stats_kernel), true);
+    (void)once;
+    const int thr = rowmap_threads(C);
+    return bn_parts(M, C, cap_floats, resident_ctas(bn_stats_kernel, thr, rowpipe_bytes(1, thr)));
 }
 
 POSE_API int pose_bn_stats_bf16(const void *Y, long M, int C, long ld, float *partials, long cap_floats, pose_stream_t stream) {
@@ -1122,8 +1143,9 @@ POSE_API int pose_bn_stats_bf16(const void *Y, long M, int C, long ld, float *pa
     REQ((uintptr_t)Y % 16 == 0, POSE_E_ALIGN);
     REQ(C <= 3072, POSE_E_UNSUPPORTED);
     REQ(cap_floats >= 2L * C, POSE_E_WORKSPACE);
-    bn_stats_kernel<<<bn_stats_parts(M, C, cap_floats), rowmap_threads(C), 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)Y, M, C, ld,
-                                                                                               partials);
+    const int thr = rowmap_threads(C);
+    bn_stats_kernel<<<bn_stats_parts(M, C, cap_floats), thr, rowpipe_bytes(1, thr), (cudaStream_t)stream>>>((const __nv_bfloat16 *)Y, M, C,
+                                                                                                      ld, partials);
     return launch_status();
 }
 
@@ -1159,10 +1181,18 @@ POSE_API int pose_bn_apply_bf16(const void *Y, long M, int C, const float *scale
     REQ(C <= 3072 && act >= 0 && act <= 2, POSE_E_UNSUPPORTED);
     const int thr = rowmap_threads(C);
     cudaStream_t s = (cudaStream_t)stream;
-#define BN_APPLY(A_)                                                                                                   \
-    bn_apply_kernel<A_><<<one_wave(rowmap_grid(M, C, 4), resident_ctas(bn_apply_kernel<A_>, thr)), thr, 0, s>>>((const __nv_bfloat16 *)Y, M, C, scale_shift, out_scale,                    \
-                                             (const __nv_bfloat16 *)residual, ld_res, (__nv_bfloat16 *)out, ld_out)
-    if (act == 0) BN_APPLY(0); else if (act == 1) BN_APPLY(1); else BN_APPLY(2);
+#define BN_APPLY(A_, R_)                                                                                               \
+    {                                                                                                                  \
+        static const bool once = (rowpipe_optin(bn_apply_kernel<A_, R_>), true);                                       \
+        (void)once;                                                                                                    \
+        const size_t sm = R_ ? rowpipe_bytes(2, thr) : 0;                                                              \
+        bn_apply_kernel<A_, R_><<<one_wave(rowmap_grid(M, C, 4), resident_ctas(bn_apply_kernel<A_, R_>, thr, sm)), thr, sm, s>>>(     \
+            (const __nv_bfloat16 *)Y, M, C, scale_shift, out_scale, (const __nv_bfloat16 *)residual, ld_res,           \
+            (__nv_bfloat16 *)out, ld_out);                                                                             \
+    }
+#define BN_APPLY_R(A_) if (residual) BN_APPLY(A_, true) else BN_APPLY(A_, false)
+    if (act == 0) BN_APPLY_R(0) else if (act == 1) BN_APPLY_R(1) else BN_APPLY_R(2)
+#undef BN_APPLY_R
 #undef BN_APPLY
     return launch_status();
 }
@@ -1178,13 +1208,16 @@ POSE_API int pose_bn_bwd_bf16(const void *dA, long ld_da, const void *Y, long M,
     cudaStream_t s = (cudaStream_t)stream;
     const int thr = rowmap_threads(C);
 #define BN_BWD(A_)                                                                                                     \
-    const int parts = bn_parts(M, C, cap_floats, resident_ctas(bn_bwd_reduce_kernel<A_>, thr));                        \
-    bn_bwd_reduce_kernel<A_><<<parts, thr, 0, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, M, C,     \
-                                                  scale_shift, mean_rstd, out_scale, partials);                        \
-    bn_bwd_coef_kernel<<<(C + 7) / 8, 256, 0, s>>>  (partials, parts, 1.0f / (float)M, scale_shift, mean_rstd, C, coef,    \
-                                                      dgamma, dbeta);                                                  \
-    bn_bwd_apply_kernel<A_><<<one_wave(rowmap_grid(M, C, 4), resident_ctas(bn_bwd_apply_kernel<A_>, thr)), thr, 0, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, M, \
-                                                                C, scale_shift, coef, out_scale, (__nv_bfloat16 *)dY)
+    static const bool once = (rowpipe_optin(bn_bwd_reduce_kernel<A_>), rowpipe_optin(bn_bwd_apply_kernel<A_>), true);  \
+    (void)once;                                                                                                        \
+    const size_t sm = rowpipe_bytes(2, thr);                                                                           \
+    const int parts = bn_parts(M, C, cap_floats, resident_ctas(bn_bwd_reduce_kernel<A_>, thr, sm));                    \
+    bn_bwd_reduce_kernel<A_><<<parts, thr, sm, s>>>((const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, M, C,    \
+                                                   scale_shift, mean_rstd, out_scale, partials);                       \
+    bn_bwd_coef_kernel<<<(C + 7) / 8, 256, 0, s>>>(partials, parts, 1.0f / (float)M, scale_shift, mean_rstd, C, coef,     \
+                                                    dgamma, dbeta);                                                    \
+    bn_bwd_apply_kernel<A_><<<one_wave(rowmap_grid(M, C, 4), resident_ctas(bn_bwd_apply_kernel<A_>, thr, sm)), thr, sm, s>>>(      \
+        (const __nv_bfloat16 *)dA, ld_da, (const __nv_bfloat16 *)Y, M, C, scale_shift, coef, out_scale, (__nv_bfloat16 *)dY)
     if (act == 0) { BN_BWD(0); } else if (act == 1) { BN_BWD(1); } else { BN_BWD(2); }
 #undef BN_BWD
     return launch_status();
@@ -1247,8 +1280,11 @@ POSE_API int pose_gate_bwd_reduce_bf16(const void *dOut, const void *X, int B, l
     const long cap = (kNumSMs * 8 + B - 1) / B;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
-    gate_bwd_reduce_kernel<<<dim3((unsigned)gx, B), rowmap_threads(C), 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dOut,
-                                                                                                 (const __nv_bfloat16 *)X, HW, C, dgate);
+    static const bool once = (rowpipe_optin(gate_bwd_reduce_kernel), true);
+    (void)once;
+    const int thr = rowmap_threads(C);
+    gate_bwd_reduce_kernel<<<dim3((unsigned)gx, B), thr, rowpipe_bytes(2, thr), (cudaStream_t)stream>>>(
+        (const __nv_bfloat16 *)dOut, (const __nv_bfloat16 *)X, HW, C, dgate);
     return launch_status();
 }
 

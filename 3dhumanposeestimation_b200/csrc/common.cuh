@@ -81,6 +81,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// 128-bit read-only global load that the compiler may not sink towards its first use: the row-streaming kernels issue a
+// batch of these before touching any of the data (NVVM otherwise moves every __ldg next to its consumer, which leaves two
+// 16-byte requests in flight per thread -- measured 4.4 TB/s on the BatchNorm passes)
+__device__ __forceinline__ uint4 ldg_batch(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 // streaming 128-bit store: outputs are written once and not re-read by the producing kernel
 __device__ __forceinline__ void st_stream_f4(float *p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
