@@ -122,6 +122,12 @@ SIGNATURES = {
                                    c_void_p]),
     "pose_bn_bwd_bf16": (c_int, [c_void_p, C.c_long, c_void_p, C.c_long, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p,
                                  C.c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pose_dwconv3x3_bnbwd_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                          c_void_p, C.c_long, c_void_p]),
+    "pose_gate_bwd_apply_bn_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, C.c_long, c_int, c_void_p, c_void_p,
+                                            c_int, c_void_p, c_void_p, C.c_long, c_void_p, c_void_p]),
+    "pose_bn_bwd_from_dz_bf16": (c_int, [c_void_p, C.c_long, c_void_p, C.c_long, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pose_dwconv3x3_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
     "pose_gate_bwd_reduce_bf16": (c_int, [c_void_p, c_void_p, c_int, C.c_long, c_int, c_void_p, c_void_p]),

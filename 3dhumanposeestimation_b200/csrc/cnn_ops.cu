@@ -160,14 +160,46 @@ __device__ __forceinline__ void dw_emit(float (&a)[4], int stats, float (&psum)[
     }
 }
 
+// BatchNorm-backward tail (ACT 11 / 12, the data gradient of a stride-1 depthwise layer whose input came out of a
+// BatchNorm + ReLU / SiLU): the value just computed is dA of that layer; with its saved conv output y (4 channels, `yv`) the
+// kernel emits dz = dA * act'(y * scale + shift) instead, and the per-thread partial sums of dz and dz * y -- the first
+// pass of that BatchNorm's backward (pose_bn_bwd_bf16's reduction) never runs.
+template <int ACT>
+__device__ __forceinline__ void dw_emit_bnb(const float (&a)[4], const uint2 &yv, const float2 (&sc)[2], const float2 (&sh)[2],
+                                            float (&psum)[4], float (&psq)[4], __nv_bfloat16 *dst) {
+    float2 y[2];
+    unpack4(yv, y);
+    float dz[4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float2 z = __ffma2_rn(y[k], sc[k], sh[k]);
+        float2 g;
+        if (ACT == 12) {
+            const float tx = tanh_approx(0.5f * z.x), ty = tanh_approx(0.5f * z.y);
+            const float sx = 0.5f + 0.5f * tx, sy = 0.5f + 0.5f * ty;
+            g = make_float2(sx * (1.0f + z.x * (1.0f - sx)), sy * (1.0f + z.y * (1.0f - sy)));
+        } else {
+            g = make_float2(z.x > 0.f ? 1.f : 0.f, z.y > 0.f ? 1.f : 0.f);
+        }
+        dz[2 * k] = a[2 * k] * g.x;
+        dz[2 * k + 1] = a[2 * k + 1] * g.y;
+        psum[2 * k] += dz[2 * k];
+        psum[2 * k + 1] += dz[2 * k + 1];
+        psq[2 * k] = fmaf(dz[2 * k], y[k].x, psq[2 * k]);
+        psq[2 * k + 1] = fmaf(dz[2 * k + 1], y[k].y, psq[2 * k + 1]);
+    }
+    *(uint2 *)dst = pack4(dz);
+}
+
 // A thread owns FOUR channels (16 channel groups x 16 pixel lanes): 36 filter taps in registers instead of 72 keeps the
 // kernel under 85 registers, so three CTAs (24 warps, three halo tiles in flight) share an SM; with eight channels per
 // thread it ran one CTA per SM at 20 % of the HBM roofline.
 template <int STRIDE, int ACT>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, ACT >= 10 ? 2 : 3)
 dwconv3x3_kernel(const __grid_constant__ CUtensorMap mapX, const float *__restrict__ Wd, const float *__restrict__ bias,
                  int B, int H, int W, int C, __nv_bfloat16 *__restrict__ Y, float *__restrict__ pool, int stats, int Ho, int Wo,
-                 int tiles_x, int tiles_y) {
+                 int tiles_x, int tiles_y, const __nv_bfloat16 *__restrict__ Ybn, const float *__restrict__ bn_ss) {
+    constexpr bool BNB = ACT >= 10;        // BatchNorm-backward tail (stride 1 only): see dw_emit_bnb
     // pool (optional): stats == 0: [B * tiles, C] sums of the activated outputs (SE / ECA squeeze);
     //                  stats == 1: [B * tiles, 2, C] sums of y and y^2 of the bf16-ROUNDED outputs = the first stage of
     //                  the BatchNorm batch statistics (the separate pass over the conv output disappears)
@@ -195,6 +227,12 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap mapX, const float *__restri
 #pragma unroll
         for (int t = 0; t < 9; ++t) w[t][k] = c_ok ? __ldg((const float2 *)(Wd + (long)t * C + c0) + k) : make_float2(0.f, 0.f);
     }
+    float2 bsc[2], bsh[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        bsc[k] = (BNB && c_ok) ? __ldg((const float2 *)(bn_ss + c0) + k) : make_float2(0.f, 0.f);
+        bsh[k] = (BNB && c_ok) ? __ldg((const float2 *)(bn_ss + C + c0) + k) : make_float2(0.f, 0.f);
+    }
     long item = blockIdx.x;
     if (item < n_items && threadIdx.x == 0)
         dw_stage_tile<STRIDE>(s_dyn, &mapX, &s_bar[0], (int)(item / per_img), (int)(item % per_img), tiles_x, c_slab);
@@ -203,11 +241,22 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap mapX, const float *__restri
         if (next < n_items && threadIdx.x == 0)     // (the buffer was released by the barrier that ended the previous iteration)
             dw_stage_tile<STRIDE>(s_dyn + ((it + 1) & 1) * T::kSmem, &mapX, &s_bar[(it + 1) & 1], (int)(next / per_img),
                                   (int)(next % per_img), tiles_x, c_slab);
-        mbar_wait(&s_bar[it & 1], (it >> 1) & 1);
         const unsigned char *s_in = s_dyn + (it & 1) * T::kSmem + cg * 8;      // this thread's channels of pixel 0
         const int b = (int)(item / per_img), tile = (int)(item - (long)b * per_img);
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         const int oy0 = ty * T::TH, ox0 = tx * T::TW;
+        // BNB: this thread's column of the consumer layer's saved conv outputs (one 8-byte load per tile row), requested
+        // before the wait on the halo tile so that all of them are in flight together
+        uint2 yv[BNB ? T::TH : 1];
+        if (BNB) {
+#pragma unroll
+            for (int q = 0; q < (BNB ? T::TH : 1); ++q) {
+                yv[q] = make_uint2(0u, 0u);
+                if (ox0 + pl < Wo && oy0 + q < Ho && c_ok)
+                    yv[q] = __ldg((const uint2 *)(Ybn + (((long)b * Ho + oy0 + q) * Wo + ox0 + pl) * C + c0));
+            }
+        }
+        mbar_wait(&s_bar[it & 1], (it >> 1) & 1);
         float psum[4], psq[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) psum[k] = psq[k] = 0.f;
@@ -218,7 +267,7 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap mapX, const float *__restri
             static_assert(STRIDE != 1 || T::TW == 16, "one pixel lane per tile column");
             const int pxx = pl;
             const int ox = ox0 + pxx;
-#pragma unroll 1
+#pragma unroll(BNB ? T::TH / 2 : 1)
             for (int r0 = 0; r0 < T::TH; r0 += 2) {
                 float2 v0[2] = {bs[0], bs[1]}, v1[2] = {bs[0], bs[1]};
 #pragma unroll
@@ -238,8 +287,14 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap mapX, const float *__restri
                     }
                 float a0[4] = {v0[0].x, v0[0].y, v0[1].x, v0[1].y}, a1[4] = {v1[0].x, v1[0].y, v1[1].x, v1[1].y};
                 if (ox < Wo && c_ok) {
-                    if (oy0 + r0 < Ho) dw_emit<ACT>(a0, stats, psum, psq, Y + (((long)b * Ho + oy0 + r0) * Wo + ox) * C + c0);
-                    if (oy0 + r0 + 1 < Ho) dw_emit<ACT>(a1, stats, psum, psq, Y + (((long)b * Ho + oy0 + r0 + 1) * Wo + ox) * C + c0);
+                    __nv_bfloat16 *d0 = Y + (((long)b * Ho + oy0 + r0) * Wo + ox) * C + c0, *d1 = d0 + (long)Wo * C;
+                    if (BNB) {
+                        if (oy0 + r0 < Ho) dw_emit_bnb<ACT>(a0, yv[BNB ? r0 : 0], bsc, bsh, psum, psq, d0);
+                        if (oy0 + r0 + 1 < Ho) dw_emit_bnb<ACT>(a1, yv[BNB ? r0 + 1 : 0], bsc, bsh, psum, psq, d1);
+                    } else {
+                        if (oy0 + r0 < Ho) dw_emit<ACT>(a0, stats, psum, psq, d0);
+                        if (oy0 + r0 + 1 < Ho) dw_emit<ACT>(a1, stats, psum, psq, d1);
+                    }
                 }
             }
         } else {
@@ -259,7 +314,7 @@ dwconv3x3_kernel(const __grid_constant__ CUtensorMap mapX, const float *__restri
                         for (int k = 0; k < 2; ++k) v[k] = __ffma2_rn(f[k], w[ky * 3 + kx][k], v[k]);
                     }
                 float acc[4] = {v[0].x, v[0].y, v[1].x, v[1].y};
-                if (oy < Ho && ox < Wo && c_ok) dw_emit<ACT>(acc, stats, psum, psq, Y + (((long)b * Ho + oy) * Wo + ox) * C + c0);
+                if (!BNB && oy < Ho && ox < Wo && c_ok) dw_emit<ACT>(acc, stats, psum, psq, Y + (((long)b * Ho + oy) * Wo + ox) * C + c0);
             }
         }
         if (pool != nullptr) {  // fixed-order reduction over the 16 pixel lanes of the CTA, one write per channel
@@ -596,7 +651,8 @@ POSE_API int pose_dwconv3x3_pool_parts(int H, int W, int stride) {
 }
 
 static int dwconv3x3_launch(const void *X, int B, int H, int W, int C, const float *Wd, const float *bias, int stride, int act,
-                            void *Y, float *pool_sum, int pool_parts, int stats, pose_stream_t stream);
+                            void *Y, float *pool_sum, int pool_parts, int stats, pose_stream_t stream,
+                            const void *Ybn = nullptr, const float *bn_ss = nullptr);
 
 POSE_API int pose_dwconv3x3_bf16(const void *X, int B, int H, int W, int C, const float *Wd, const float *bias, int stride,
                                  int act, void *Y, float *pool_sum, int pool_parts, pose_stream_t stream) {
@@ -612,8 +668,22 @@ POSE_API int pose_dwconv3x3_bn_stats_bf16(const void *X, int B, int H, int W, in
     return dwconv3x3_launch(X, B, H, W, C, Wd, nullptr, stride, 0, Y, partials, parts, 1, stream);
 }
 
+POSE_API int pose_dwconv3x3_bnbwd_bf16(const void *dY, int B, int H, int W, int C, const float *Wflip, const void *Yprev,
+                                       const float *scale_shift_prev, int act_prev, void *dZ, float *partials, long cap_floats,
+                                       pose_stream_t stream) {
+    if (!partials || !Yprev || !scale_shift_prev) return POSE_E_NULL;
+    if (H <= 0 || W <= 0) return POSE_E_SHAPE;
+    if (act_prev != 1 && act_prev != 2) return POSE_E_UNSUPPORTED;
+    if ((uintptr_t)Yprev % 8) return POSE_E_ALIGN;
+    const int parts = pose_dwconv3x3_pool_parts(H, W, 1);
+    if ((long)B * parts * 2 * C > cap_floats) return POSE_E_WORKSPACE;
+    return dwconv3x3_launch(dY, B, H, W, C, Wflip, nullptr, 1, 10 + act_prev, dZ, partials, parts, 1, stream, Yprev,
+                            scale_shift_prev);
+}
+
 static int dwconv3x3_launch(const void *X, int B, int H, int W, int C, const float *Wd, const float *bias, int stride, int act,
-                            void *Y, float *pool_sum, int pool_parts, int stats, pose_stream_t stream) {
+                            void *Y, float *pool_sum, int pool_parts, int stats, pose_stream_t stream, const void *Ybn,
+                            const float *bn_ss) {
     if (!X || !Wd || (!bias && !stats) || !Y) return POSE_E_NULL;
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 || (stride != 1 && stride != 2)) return POSE_E_SHAPE;
     if ((uintptr_t)X % 16 || (uintptr_t)Y % 16) return POSE_E_ALIGN;
@@ -624,11 +694,11 @@ static int dwconv3x3_launch(const void *X, int B, int H, int W, int C, const flo
     const int tiles_y = (Ho + th - 1) / th, tiles_x = (Wo + tw - 1) / tw;
     const int gy = (C + kDwSlab - 1) / kDwSlab;
     long gx = (long)B * tiles_x * tiles_y;
-    const long cap = ((long)kNumSMs * 3 + gy - 1) / gy;           // 3 resident CTAs per SM over all channel slabs
+    const long cap = ((long)kNumSMs * (act >= 10 ? 2 : 3) + gy - 1) / gy;   // resident CTAs per SM (3; 2 with the BatchNorm tail) over all channel slabs
     if (gx > cap) gx = cap;
     dim3 grid((unsigned)gx, gy);
     cudaStream_t s = (cudaStream_t)stream;
-    if (act < 0 || act > 4) return POSE_E_UNSUPPORTED;
+    if (act < 0 || (act > 4 && act != 11 && act != 12) || (act >= 10 && (stride != 1 || !Ybn || !bn_ss))) return POSE_E_UNSUPPORTED;
     const int smem = 2 * (stride == 1 ? DwTile<1>::kSmem : DwTile<2>::kSmem) + 2 * 16 * kDwSlab * 4;
     CUtensorMap mapX;
     {
@@ -645,7 +715,8 @@ static int dwconv3x3_launch(const void *X, int B, int H, int W, int C, const flo
             cfg = true;                                                                                               \
         }                                                                                                             \
         dwconv3x3_kernel<S_, A_><<<grid, 256, smem, s>>>(mapX, Wd, bias, B, H, W, C, (__nv_bfloat16 *)Y, \
-                                                         pool_sum, stats, Ho, Wo, tiles_x, tiles_y);                  \
+                                                         pool_sum, stats, Ho, Wo, tiles_x, tiles_y,                   \
+                                                         (const __nv_bfloat16 *)Ybn, bn_ss);                          \
     }
 #define DW_ACT(S_)                                                                                                    \
     switch (act) {                                                                                                    \
@@ -655,6 +726,7 @@ static int dwconv3x3_launch(const void *X, int B, int H, int W, int C, const flo
         case 3: DW_LAUNCH(S_, 3); break;                                                                              \
         default: DW_LAUNCH(S_, 4); break;                                                                             \
     }
+    if (act == 11) { DW_LAUNCH(1, 11) } else if (act == 12) { DW_LAUNCH(1, 12) } else
     if (stride == 1) { DW_ACT(1) } else { DW_ACT(2) }
 #undef DW_ACT
 #undef DW_LAUNCH

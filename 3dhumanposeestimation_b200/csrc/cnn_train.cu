@@ -718,6 +718,53 @@ gate_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dO, const float *__restr
     }
 }
 
+// The same with the BatchNorm-backward tail of the layer that produced the gated map (the depthwise ConvBnAct in front of an
+// SE / ECA block): dA = dO * gate + dmean / HW never reaches memory; with that layer's saved conv output y the kernel writes
+// dz = dA * act'(y * scale + shift) and the per-CTA partial sums of dz and dz * y ([gridDim.y * gridDim.x, 2, C]): the first
+// pass of pose_bn_bwd_bf16 (one read of dA and y) disappears.
+template <int ACT>
+__global__ void __launch_bounds__(384)
+gate_bwd_apply_bn_kernel(const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ gate, const __nv_bfloat16 *__restrict__ dmean,
+                         float inv_hw, long HW, int C, const __nv_bfloat16 *__restrict__ Ybn, const float *__restrict__ scale_shift,
+                         __nv_bfloat16 *__restrict__ dZ, float *__restrict__ partials) {
+    const RowMap rm(C);
+    const long b = blockIdx.y, base = b * HW;
+    float2 g[4], m[4], a[4], sh[4], s1[4], s2[4];
+    ld8p(gate + b * C + rm.c0, g);
+    up8q(__ldg((const uint4 *)(dmean + b * C + rm.c0)), m);
+    ld8p(scale_shift + rm.c0, a);
+    ld8p(scale_shift + C + rm.c0, sh);
+    const float2 ih2 = make_float2(inv_hw, inv_hw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        m[j] = __fmul2_rn(m[j], ih2);
+        s1[j] = s2[j] = make_float2(0.f, 0.f);
+    }
+    const void *const src[2] = {dO + base * C, Ybn + base * C};
+    const long pitch[2] = {C * 2L, C * 2L};
+    row_stream<2>(src, pitch, rm.c0 * 2L, (long)blockIdx.x * rm.rpb + rm.rsub, (long)gridDim.x * rm.rpb, HW,
+                  [&](long r, const uint4 (&v)[2]) {
+        float2 d[4], y[4];
+        up8q(v[0], d);
+        up8q(v[1], y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 dz = __fmul2_rn(__ffma2_rn(d[j], g[j], m[j]), dactf2<ACT>(__ffma2_rn(y[j], a[j], sh[j])));
+            s1[j] = __fadd2_rn(s1[j], dz);
+            s2[j] = __ffma2_rn(dz, y[j], s2[j]);
+            d[j] = dz;
+        }
+        *(uint4 *)(dZ + (base + r) * C + rm.c0) = pk8p(d);
+    });
+    float acc[2][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        acc[0][2 * j] = s1[j].x; acc[0][2 * j + 1] = s1[j].y;
+        acc[1][2 * j] = s2[j].x; acc[1][2 * j + 1] = s2[j].y;
+    }
+    rowmap_fold<2, false, true>(rm, C, acc, partials, ((long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
+}
+
 // dz[b,c] (bf16) = dgate[b,c] * g (1 - g)     (through the sigmoid of the SE gate; operand of the SE backward GEMMs)
 __global__ void __launch_bounds__(256)
 sigmoid_bwd_kernel(const float *__restrict__ dgate, const float *__restrict__ gate, long n, __nv_bfloat16 *__restrict__ dz) {
@@ -780,27 +827,50 @@ eca_bwd_kernel(const float *__restrict__ dgate_in, const __nv_bfloat16 *__restri
 // dZ [B, H+W, 2C] bf16 = gradient at the INPUT of the sigmoids of G (zero in the halves the forward does not use):
 //   rows h < H, cols c      : (sum_w dOut * X * a_w) * a_h (1 - a_h)
 //   rows H + w, cols C + c  : (sum_h dOut * X * a_h) * a_w (1 - a_w)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 coord_bwd_reduce_kernel(const __nv_bfloat16 *__restrict__ dO, const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__restrict__ G,
                         int H, int W, int C, __nv_bfloat16 *__restrict__ dZ) {
+    // grid (image, chunk): the (H + W) x C / 8 reductions of an image are spread over gridDim.y CTAs (one CTA per image left
+    // 20 SMs idle and every thread walking eight strictly serial reductions: 71 us for 134 MB)
     const int b = blockIdx.x, C8 = C >> 3;
     const int n_rows = H + W;
-    for (int i = threadIdx.x; i < n_rows * C8; i += 256) {
+    for (int i = blockIdx.y * 256 + threadIdx.x; i < n_rows * C8; i += gridDim.y * 256) {
         const int r = i / C8, cg = i - r * C8;
         const bool is_h = r < H;
         const int n = is_h ? W : H;
         float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int q = 0; q < n; ++q) {
+        auto offs = [&](int q, long &off, long &grow) {
             const int y = is_h ? r : q, x = is_h ? q : r - H;
-            float d[8], xv[8], go[8];
-            const long off = (((long)b * H + y) * W + x) * C + cg * 8;
-            up8(__ldg((const uint4 *)(dO + off)), d);
-            up8(__ldg((const uint4 *)(X + off)), xv);
+            off = (((long)b * H + y) * W + x) * C + cg * 8;
             // the OTHER direction's gate at this pixel
-            const long grow = is_h ? ((long)b * n_rows + H + x) * 2L * C + C : ((long)b * n_rows + y) * 2L * C;
-            up8(__ldg((const uint4 *)(G + grow + cg * 8)), go);
+            grow = (is_h ? ((long)b * n_rows + H + x) * 2L * C + C : ((long)b * n_rows + y) * 2L * C) + cg * 8;
+        };
+        auto acc = [&](const uint4 &vd, const uint4 &vx, const uint4 &vg) {
+            float d[8], xv[8], go[8];
+            up8(vd, d);
+            up8(vx, xv);
+            up8(vg, go);
 #pragma unroll
             for (int j = 0; j < 8; ++j) s[j] = fmaf(d[j] * xv[j], go[j], s[j]);
+        };
+        int q = 0;
+        for (; q + 3 < n; q += 4) {                       // twelve independent 16-byte loads in flight
+            uint4 vd[4], vx[4], vg[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                long off, grow;
+                offs(q + u, off, grow);
+                vd[u] = ldg_batch(dO + off);
+                vx[u] = ldg_batch(X + off);
+                vg[u] = ldg_batch(G + grow);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc(vd[u], vx[u], vg[u]);
+        }
+        for (; q < n; ++q) {
+            long off, grow;
+            offs(q, off, grow);
+            acc(ldg_batch(dO + off), ldg_batch(X + off), ldg_batch(G + grow));
         }
         float gs[8], z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const long row = ((long)b * n_rows + r) * 2L * C;
@@ -869,10 +939,13 @@ wasp_mix_kernel(const __nv_bfloat16 *__restrict__ branches, int nb, long branch_
 
 // backward: dbranch_i = w_i * dOut (written), dglob[b,c] = w_last * sum_p dOut (atomic, fp32 [B,C]),
 // dots[i] += <dOut, branch_i> (i < nb), dots[nb] += <dOut, glob broadcast>   (fp32 [nb+1], zeroed by the caller)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(384, 2)
 wasp_mix_bwd_kernel(const __nv_bfloat16 *__restrict__ dO, const __nv_bfloat16 *__restrict__ branches, int nb, long branch_stride,
-                    const __nv_bfloat16 *__restrict__ glob, const float *__restrict__ raw, long HW, int C, long total8,
+                    const __nv_bfloat16 *__restrict__ glob, const float *__restrict__ raw, long HW, int C,
                     __nv_bfloat16 *__restrict__ dbranches, float *__restrict__ dglob, float *__restrict__ dots) {
+    // grid (row blocks, image); a thread owns one 8-channel group of its image and walks rows: the broadcast branch's
+    // gradient (a per-image column sum of dO) accumulates in registers and is folded once per CTA -- the flat-index
+    // version issued one atomicAdd per ELEMENT (33 M per step) and decoded (image, group) with 64-bit divisions
     __shared__ float w[8];
     __shared__ float sdots[8];
     if (threadIdx.x == 0) {
@@ -883,38 +956,53 @@ wasp_mix_bwd_kernel(const __nv_bfloat16 *__restrict__ dO, const __nv_bfloat16 *_
     }
     if (threadIdx.x < 8) sdots[threadIdx.x] = 0.f;
     __syncthreads();
-    const int C8 = C >> 3;
+    const RowMap rm(C);
+    const long b = blockIdx.y, base = b * HW;
+    float g8[8], acc[1][8];
+    up8(__ldg((const uint4 *)(glob + b * C + rm.c0)), g8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
     float dot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(i % C8);
-        const long b = (i / C8) / HW;
-        float d[8], f[8], o[8];
-        up8(__ldg((const uint4 *)dO + i), d);
-        up8(__ldg((const uint4 *)(glob + b * C + cg * 8)), f);
+    const long step = (long)gridDim.x * rm.rpb;
+    for (long r = (long)blockIdx.x * rm.rpb + rm.rsub; r < HW; r += step) {
+        const long off = (base + r) * C + rm.c0;
+        uint4 vb[7];
+        const uint4 vd = ldg_batch(dO + off);
+#pragma unroll
+        for (int q = 0; q < 7; ++q)
+            if (q < nb) vb[q] = ldg_batch(branches + q * branch_stride + off);
+        float d[8];
+        up8(vd, d);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            dot[nb] = fmaf(d[j], f[j], dot[nb]);
-            atomicAdd(dglob + b * C + cg * 8 + j, w[nb] * d[j]);
+            dot[7] = fmaf(d[j], g8[j], dot[7]);
+            acc[0][j] += d[j];
         }
-        for (int q = 0; q < nb; ++q) {
-            up8(__ldg((const uint4 *)(branches + q * branch_stride) + i), f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                dot[q] = fmaf(d[j], f[j], dot[q]);
-                o[j] = w[q] * d[j];
+        for (int q = 0; q < 7; ++q)
+            if (q < nb) {
+                float f[8], o[8];
+                up8(vb[q], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    dot[q] = fmaf(d[j], f[j], dot[q]);
+                    o[j] = w[q] * d[j];
+                }
+                *(uint4 *)(dbranches + q * branch_stride + off) = pk8(o);
             }
-            ((uint4 *)(dbranches + q * branch_stride))[i] = pk8(o);
-        }
     }
-    for (int q = 0; q <= nb; ++q) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] *= w[nb];
+    rowmap_fold<1>(rm, C, acc, dglob, b * C);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
         const float s = warp_sum(dot[q]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&sdots[q], s);
+        if ((threadIdx.x & 31) == 0 && (q < nb || q == 7)) atomicAdd(&sdots[q == 7 ? nb : q], s);
     }
     __syncthreads();
     if (threadIdx.x <= nb) atomicAdd(dots + threadIdx.x, sdots[threadIdx.x]);
 }
 
-// softmax backward for the nb+1 raw mixing weights: draw[i] += w_i * (dots[i] - sum_j w_j dots[j])
 __global__ void wasp_weights_bwd_kernel(const float *__restrict__ raw, const float *__restrict__ dots, int n, float *__restrict__ draw) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         float w[8], m = -1e30f, s = 0.f, t = 0.f;
@@ -1055,44 +1143,46 @@ repack_kernel(const RepackEntry *__restrict__ table, const float *__restrict__ s
         case 3: n = (long)e.d0 * e.d1; break;
         default: n = e.d0; break;
     }
+    // all index arithmetic in 32 bits (a parameter tensor has far fewer than 2^31 elements; the host checks): the 64-bit
+    // divisions and remainders that decoded every element cost ~150 instructions each and made this the slowest
+    // "copy" of the step (182 us for 43 tensors, 24 us per weight-gradient unpack)
     if (e.kind == 1 || e.kind == 2) {
         // destination-major: coalesced bf16 stores, strided fp32 gathers (L2 hits) -- the source-major loop scattered 2-byte
         // stores over 32 sectors per warp
-        const int K = e.d2, Ci = e.d1, Co = e.d0;
-        const int inner = e.kind == 1 ? e.d3 : Co;               // fastest destination index: padded ci (kind 1) / co (kind 2)
-        const long nd = e.kind == 1 ? (long)Co * K * K * e.d3 : (long)Ci * K * K * Co;
-        for (long j = (long)blockIdx.x * 256 + threadIdx.x; j < nd; j += (long)gridDim.x * 256) {
-            long t = j;
-            const int in = (int)(t % inner); t /= inner;
-            const int kw = (int)(t % K); t /= K;
-            const int kh = (int)(t % K);
-            const int outer = (int)(t / K);
+        const unsigned K = e.d2, Ci = e.d1, Co = e.d0;
+        const unsigned inner = e.kind == 1 ? e.d3 : Co;          // fastest destination index: padded ci (kind 1) / co (kind 2)
+        const unsigned nd = e.kind == 1 ? Co * K * K * e.d3 : Ci * K * K * Co;
+        for (unsigned j = blockIdx.x * 256u + threadIdx.x; j < nd; j += gridDim.x * 256u) {
+            unsigned t = j;
+            const unsigned in = t % inner; t /= inner;
+            const unsigned kw = t % K; t /= K;
+            const unsigned kh = t % K;
+            const unsigned outer = t / K;
             if (e.kind == 1) {
-                if (in < Ci) dst_bf16[e.dst + j] = __float2bfloat16_rn(s[(((long)outer * Ci + in) * K + kh) * K + kw]);
+                if (in < Ci) dst_bf16[e.dst + j] = __float2bfloat16_rn(s[((outer * Ci + in) * K + kh) * K + kw]);
             } else {
-                dst_bf16[e.dst + j] = __float2bfloat16_rn(s[(((long)in * Ci + outer) * K + (K - 1 - kh)) * K + (K - 1 - kw)]);
+                dst_bf16[e.dst + j] = __float2bfloat16_rn(s[((in * Ci + outer) * K + (K - 1 - kh)) * K + (K - 1 - kw)]);
             }
         }
         return;
     }
-    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+    if (e.kind == 5) {
+        // destination-major over the [Co,Ci,K,K] gradient (coalesced read-modify-write), gathers from the KRSC staging
+        const unsigned K = e.d2, Ci = e.d1, KK = K * K, Cp = e.d3;
+        for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < (unsigned)n; i += gridDim.x * 256u) {
+            const unsigned tap = i % KK, t = i / KK;
+            const unsigned ci = t % Ci, co = t / Ci;
+            dst_f32[e.dst + i] += s[(co * KK + tap) * Cp + ci];
+        }
+        return;
+    }
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < (unsigned)n; i += gridDim.x * 256u) {
         if (e.kind == 0 || e.kind == 6) {
-            const long c = i / 9, k = i - c * 9;
+            const unsigned c = i / 9, k = i - c * 9;
             dst_f32[e.dst + (e.kind == 0 ? k : 8 - k) * e.d0 + c] = s[i];
-        } else if (e.kind == 1 || e.kind == 2 || e.kind == 5) {
-            const int K = e.d2, Ci = e.d1, Co = e.d0;
-            long t = i;
-            const int kw = (int)(t % K); t /= K;
-            const int kh = (int)(t % K); t /= K;
-            const int ci = (int)(t % Ci);
-            const int co = (int)(t / Ci);
-            if (e.kind == 1) dst_bf16[e.dst + (((long)co * K + kh) * K + kw) * e.d3 + ci] = __float2bfloat16_rn(s[i]);
-            else if (e.kind == 2)
-                dst_bf16[e.dst + (((long)ci * K + (K - 1 - kh)) * K + (K - 1 - kw)) * Co + co] = __float2bfloat16_rn(s[i]);
-            else dst_f32[e.dst + i] += s[(((long)co * K + kh) * K + kw) * e.d3 + ci];
         } else if (e.kind == 3) {
-            const long r = i / e.d1, c = i - r * e.d1;
-            dst_bf16[e.dst + r * e.d2 + c] = __float2bfloat16_rn(s[i]);
+            const unsigned r = i / e.d1, c = i - r * e.d1;
+            dst_bf16[e.dst + (long)r * e.d2 + c] = __float2bfloat16_rn(s[i]);
         } else {
             dst_f32[e.dst + i] = s[i];
         }
@@ -1305,6 +1395,57 @@ POSE_API int pose_gate_bwd_apply_bf16(const void *dOut, const float *gate, const
     return launch_status();
 }
 
+POSE_API int pose_gate_bwd_apply_bn_bf16(const void *dOut, const float *gate, const void *dmean, float inv_hw, int B, long HW, int C,
+                                         const void *Yprev, const float *scale_shift_prev, int act_prev, void *dZ, float *partials,
+                                         long cap_floats, int *parts_out, pose_stream_t stream) {
+    REQ(dOut && gate && dmean && Yprev && scale_shift_prev && dZ && partials && parts_out, POSE_E_NULL);
+    REQ(B > 0 && HW > 0 && C > 0 && C % 8 == 0, POSE_E_SHAPE);
+    REQ(C <= 3072 && (act_prev == 1 || act_prev == 2), POSE_E_UNSUPPORTED);
+    REQ((uintptr_t)dOut % 16 == 0 && (uintptr_t)Yprev % 16 == 0 && (uintptr_t)dZ % 16 == 0 && (uintptr_t)dmean % 16 == 0, POSE_E_ALIGN);
+    const int thr = rowmap_threads(C), rpb = thr / (C / 8);
+    const size_t sm = rowpipe_bytes(2, thr);
+    static const bool once = (rowpipe_optin(gate_bwd_apply_bn_kernel<1>), rowpipe_optin(gate_bwd_apply_bn_kernel<2>), true);
+    (void)once;
+    const int per_sm = act_prev == 1 ? resident_ctas(gate_bwd_apply_bn_kernel<1>, thr, sm) : resident_ctas(gate_bwd_apply_bn_kernel<2>, thr, sm);
+    long gx = (HW + (long)rpb * 4 - 1) / ((long)rpb * 4);
+    const long cap = ((long)kNumSMs * per_sm + B - 1) / B;       // one wave of resident CTAs over the batch
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    REQ(gx * B * 2L * C <= cap_floats, POSE_E_WORKSPACE);
+    *parts_out = (int)(gx * B);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (act_prev == 1)
+        gate_bwd_apply_bn_kernel<1><<<dim3((unsigned)gx, B), thr, sm, s>>>((const __nv_bfloat16 *)dOut, gate, (const __nv_bfloat16 *)dmean, inv_hw,
+                                                                         HW, C, (const __nv_bfloat16 *)Yprev, scale_shift_prev,
+                                                                         (__nv_bfloat16 *)dZ, partials);
+    else
+        gate_bwd_apply_bn_kernel<2><<<dim3((unsigned)gx, B), thr, sm, s>>>((const __nv_bfloat16 *)dOut, gate, (const __nv_bfloat16 *)dmean, inv_hw,
+                                                                         HW, C, (const __nv_bfloat16 *)Yprev, scale_shift_prev,
+                                                                         (__nv_bfloat16 *)dZ, partials);
+    return launch_status();
+}
+
+/* second half of the BatchNorm backward when the producer of the incoming gradient already emitted dz = dA * act'(z) and the
+   [parts, 2, C] partial sums of dz and dz * y (pose_gate_bwd_apply_bn_bf16, pose_dwconv3x3_bnbwd_bf16): fold -> dgamma, dbeta,
+   coefficients -> dY = a dz - k2 y - k3 */
+POSE_API int pose_bn_bwd_from_dz_bf16(const void *dZ, long ld_dz, const void *Y, long M, int C, const float *scale_shift,
+                                      const float *mean_rstd, const float *partials, int parts, float *coef, void *dY,
+                                      float *dgamma, float *dbeta, pose_stream_t stream) {
+    REQ(dZ && Y && scale_shift && mean_rstd && partials && coef && dY && dgamma && dbeta, POSE_E_NULL);
+    REQ(M > 0 && C > 0 && C % 8 == 0 && ld_dz >= C && ld_dz % 8 == 0 && parts > 0, POSE_E_SHAPE);
+    REQ((uintptr_t)dZ % 16 == 0 && (uintptr_t)Y % 16 == 0 && (uintptr_t)dY % 16 == 0, POSE_E_ALIGN);
+    REQ(C <= 3072, POSE_E_UNSUPPORTED);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int thr = rowmap_threads(C);
+    static const bool once = (rowpipe_optin(bn_bwd_apply_kernel<0>), true);
+    (void)once;
+    const size_t sm = rowpipe_bytes(2, thr);
+    bn_bwd_coef_kernel<<<(C + 7) / 8, 256, 0, s>>>(partials, parts, 1.0f / (float)M, scale_shift, mean_rstd, C, coef, dgamma, dbeta);
+    bn_bwd_apply_kernel<0><<<one_wave(rowmap_grid(M, C, 4), resident_ctas(bn_bwd_apply_kernel<0>, thr, sm)), thr, sm, s>>>(
+        (const __nv_bfloat16 *)dZ, ld_dz, (const __nv_bfloat16 *)Y, M, C, scale_shift, coef, 1.0f, (__nv_bfloat16 *)dY);
+    return launch_status();
+}
+
 POSE_API int pose_sigmoid_bwd(const float *dgate, const float *gate, long n, void *dz, pose_stream_t stream) {
     REQ(dgate && gate && dz, POSE_E_NULL);
     REQ(n > 0, POSE_E_SHAPE);
@@ -1326,7 +1467,10 @@ POSE_API int pose_coord_bwd_reduce_bf16(const void *dOut, const void *X, const v
                                         pose_stream_t stream) {
     REQ(dOut && X && G && dZ, POSE_E_NULL);
     REQ(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, POSE_E_SHAPE);
-    coord_bwd_reduce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dOut, (const __nv_bfloat16 *)X,
+    const int items = (H + W) * (C / 8);
+    int chunks = (items + 255) / 256;
+    if (chunks > 16) chunks = 16;
+    coord_bwd_reduce_kernel<<<dim3(B, chunks), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)dOut, (const __nv_bfloat16 *)X,
                                                                 (const __nv_bfloat16 *)G, H, W, C, (__nv_bfloat16 *)dZ);
     return launch_status();
 }
@@ -1358,11 +1502,16 @@ POSE_API int pose_wasp_mix_bwd_bf16(const void *dOut, const void *branches, int 
                                     pose_stream_t stream) {
     REQ(dOut && branches && glob && raw_weights && dbranches && dglob && dots && draw, POSE_E_NULL);
     REQ(nb > 0 && nb < 8 && B > 0 && HW > 0 && C > 0 && C % 8 == 0, POSE_E_SHAPE);
-    const long total8 = (long)B * HW * (C / 8);
+    REQ(C <= 3072, POSE_E_UNSUPPORTED);
     cudaStream_t s = (cudaStream_t)stream;
-    wasp_mix_bwd_kernel<<<grid_for(total8, 256, 4), 256, 0, s>>>((const __nv_bfloat16 *)dOut, (const __nv_bfloat16 *)branches, nb,
-                                                                (long)B * HW * C, (const __nv_bfloat16 *)glob, raw_weights, HW, C,
-                                                                total8, (__nv_bfloat16 *)dbranches, dglob, dots);
+    const int thr = rowmap_threads(C), rpb = thr / (C / 8);
+    long gx = (HW + (long)rpb * 4 - 1) / ((long)rpb * 4);
+    const long cap = ((long)kNumSMs * 4 + B - 1) / B;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    wasp_mix_bwd_kernel<<<dim3((unsigned)gx, B), thr, 0, s>>>((const __nv_bfloat16 *)dOut, (const __nv_bfloat16 *)branches, nb,
+                                                             (long)B * HW * C, (const __nv_bfloat16 *)glob, raw_weights, HW, C,
+                                                             (__nv_bfloat16 *)dbranches, dglob, dots);
     wasp_weights_bwd_kernel<<<1, 32, 0, s>>>(raw_weights, dots, nb + 1, draw);
     return launch_status();
 }

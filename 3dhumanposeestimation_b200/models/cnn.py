@@ -359,6 +359,13 @@ class CnnInferencePlan:
         a = 0 if (act is None or cba.activation is None) else (self.act if act == "default" else activation_id(act))
         e = self._epi(out, out.shape[-1], b32, a, out_scale, residual,
                       residual.shape[-1] if residual is not None else 0, res_scale)
+        if kh == kw and kh > 1 and stride == 1 and 2 * pad == dil * (kh - 1) and dil >= H and dil >= W:
+            # the dilation reaches across the whole map (WASP rate 18 on a 16 x 16 map): every tap but the centre reads only
+            # zero padding, so the layer is the 1x1 convolution with the centre-tap weights (KRSC rows of pitch K*K*Cin)
+            ctr = (kh // 2 * kw + kw // 2) * cin_x
+            self._launch("pose_gemm_bf16_ex", x.data_ptr(), cin_x, w16.data_ptr() + 2 * ctr, kh * kw * cin_x, Bn * H * W, cout,
+                         cin_x, C.byref(e))
+            return out
         self._launch("pose_conv2d_bf16", x.data_ptr(), Bn, H, W, cin_x, w16.data_ptr(), cout, kh, kw, stride, dil, pad,
                      C.byref(e))
         return out

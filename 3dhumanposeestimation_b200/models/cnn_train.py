@@ -12,6 +12,7 @@ Parameter gradients accumulate in the flat fp32 ``.grad`` buffer (params.FlatPar
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -55,6 +56,13 @@ class CnnTrainPlan:
         self.launches = 0
         self.step_count = 0
         self.drop_p = float(c.regression_dropout)
+        # BatchNorm backward: reduction pass carried by the producer of the incoming gradient (A/B switches).  Measured on
+        # the 768-channel layers at B = 128: SE-gate backward + tail 123 us (74 without) but the BatchNorm backward drops from
+        # 182 to 109 us: on.  The depthwise data gradient is issue bound already (100 us); with the tail it runs two CTAs per
+        # SM at twice the instructions (294 us) against 100 + 75 us for the separate reduction pass: off.
+        self.fuse_bn_bwd = os.environ.get("POSE_FUSE_BN_BWD", "1") != "0"
+        self.fuse_bn_bwd_dw = os.environ.get("POSE_FUSE_BN_BWD_DW", "0") == "1"
+        self._emit_parts = None
         # fp32 workspace zeroed once per step: BN sums, gate gradients, spatial-conv weight-gradient staging
         self._ws_off, self._ws_items = 0, {}
         self._pk32_off, self._pk16_off = 0, 0
@@ -214,7 +222,15 @@ class CnnTrainPlan:
                 f.mean_rstd, f.scale_shift = mr.data_ptr(), ss.data_ptr()
                 f.running_mean, f.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
                 e.bn = C.pointer(f)
-            if spatial:
+            # a dilated 'same' convolution whose dilation reaches across the whole map (WASP rate 18 on the 16 x 16 map of a
+            # 256 x 256 input): every tap but the centre reads only zero padding, so the layer IS the 1x1 convolution with
+            # the centre-tap weights -- a plain GEMM over the packed KRSC weights with pitch K*K*Cp (1/9 of the work)
+            center = spatial and kh > 1 and stride == 1 and 2 * pad == dil * (kh - 1) and dil >= H and dil >= W and cin == cp
+            if center:
+                ctr = (kh // 2 * kh + kh // 2) * cp
+                self.gemm(x.data_ptr(), cin, self.pk16[fwd + ctr:].data_ptr(), kh * kh * cp, M, co, cin, e)
+                kind = "conv"
+            elif spatial:
                 self.call("pose_conv2d_bf16", x.data_ptr(), Bn, H, W, cin, self.pk16[fwd:].data_ptr(), co, kh, kh, stride,
                           dil, pad, C.byref(e))
                 kind = "conv"
@@ -244,7 +260,7 @@ class CnnTrainPlan:
         self.call("pose_bn_apply_bf16", y.data_ptr(), M, co, ss.data_ptr(), a_id, 1.0,
                   residual.data_ptr() if residual is not None else None, ld_res, optr, ld_out)
         self.rec[name] = dict(kind=kind, x=x, shape=shape, y=y, mr=mr, ss=ss, act=a_id, M=M, co=co, cin=cin,
-                              oshape=(Bn, Ho, Wo, co), cba=cba)
+                              oshape=(Bn, Ho, Wo, co), cba=cba, center=kind == "conv" and center)
         return out, (Bn, Ho, Wo, co)
 
     def partials(self):
@@ -263,9 +279,14 @@ class CnnTrainPlan:
             self.bufs["zero_bias"] = t
         return t
 
-    def cba_bwd(self, name, dA, ld_da, need_dx=True, dx_add=None, ld_add=0, da_off=0):
+    def cba_bwd(self, name, dA, ld_da, need_dx=True, dx_add=None, ld_add=0, da_off=0, dz_parts=None, bn_next=None):
         """dA: gradient of the layer output (pitch ld_da, column offset da_off).  Accumulates dgamma / dbeta / dW.
-        Returns dx [M_in, Cin] (+ dx_add fused into the data-gradient epilogue) or None."""
+        Returns dx [M_in, Cin] (+ dx_add fused into the data-gradient epilogue) or None.
+
+        dz_parts: the producer of `dA` already multiplied by act'(z) of THIS layer and left `dz_parts` rows of partial sums in
+        the shared scratch (the reduction pass of the BatchNorm backward is skipped).  bn_next: record of the layer whose
+        output this layer consumed; where the data gradient is produced by a kernel that can carry that layer's reduction
+        (stride-1 depthwise), it does, and self._emit_parts tells the caller."""
         r = self.rec[name]
         cba, flat = r["cba"], self.flat
         conv, bn = cba.conv, cba.norm
@@ -274,9 +295,15 @@ class CnnTrainPlan:
         _, Ho, Wo, _ = r["oshape"]
         dy = self.buf(name + ".dy", M, co)
         part = self.partials()
-        self.call("pose_bn_bwd_bf16", dA.data_ptr() + 2 * da_off, ld_da, r["y"].data_ptr(), M, co, r["ss"].data_ptr(),
-                  r["mr"].data_ptr(), r["act"], 1.0, part.data_ptr(), part.numel(), self.bufs["bn.coef"].data_ptr(),
-                  dy.data_ptr(), flat.g32(bn.weight).data_ptr(), flat.g32(bn.bias).data_ptr())
+        self._emit_parts = None
+        if dz_parts is not None:
+            self.call("pose_bn_bwd_from_dz_bf16", dA.data_ptr() + 2 * da_off, ld_da, r["y"].data_ptr(), M, co, r["ss"].data_ptr(),
+                      r["mr"].data_ptr(), part.data_ptr(), dz_parts, self.bufs["bn.coef"].data_ptr(), dy.data_ptr(),
+                      flat.g32(bn.weight).data_ptr(), flat.g32(bn.bias).data_ptr())
+        else:
+            self.call("pose_bn_bwd_bf16", dA.data_ptr() + 2 * da_off, ld_da, r["y"].data_ptr(), M, co, r["ss"].data_ptr(),
+                      r["mr"].data_ptr(), r["act"], 1.0, part.data_ptr(), part.numel(), self.bufs["bn.coef"].data_ptr(),
+                      dy.data_ptr(), flat.g32(bn.weight).data_ptr(), flat.g32(bn.bias).data_ptr())
         x = r["x"]
         kh = conv.kernel_size[0]
         stride, dil, pad = conv.stride[0], conv.dilation[0], conv.padding[0]
@@ -289,6 +316,19 @@ class CnnTrainPlan:
             if need_dx and stride == 1:
                 # stride 1: the data gradient is the forward (shared-memory tiled) kernel over dY with flipped taps
                 wf = self.pk32[self.pk[name][2]:]
+                fuse = (bn_next is not None and dx_add is None and self.fuse_bn_bwd_dw and bn_next["act"] in (1, 2)
+                        and bn_next["co"] == co and bn_next["M"] == Bn * H * W)
+                if fuse:
+                    # ... which also carries the reduction pass of the BatchNorm in front of this layer (emits dz)
+                    parts = Bn * self.lib.pose_dwconv3x3_pool_parts(Ho, Wo, 1)
+                    fuse = parts * 2 * co <= part.numel()
+                if fuse:
+                    self.call("pose_dwconv3x3_bnbwd_bf16", dy.data_ptr(), Bn, Ho, Wo, co, wf.data_ptr(), bn_next["y"].data_ptr(),
+                              bn_next["ss"].data_ptr(), bn_next["act"], dx.data_ptr(), part.data_ptr(), part.numel())
+                    self.call("pose_dwconv3x3_bwd_bf16", dy.data_ptr(), x.data_ptr(), wd.data_ptr(), Bn, H, W, co, stride, None,
+                              None, flat.g32(conv.weight).data_ptr())
+                    self._emit_parts = parts
+                    return dx
                 self.call("pose_dwconv3x3_bf16", dy.data_ptr(), Bn, Ho, Wo, co, wf.data_ptr(), self.zero_bias(co).data_ptr(), 1,
                           0, dx.data_ptr(), None, 0)
                 if dx_add is not None:
@@ -302,6 +342,20 @@ class CnnTrainPlan:
         if r["kind"] == "conv":
             _, fwd, bwd, cp, stage, ui = self.pk[name]
             st = self.wsbuf[stage:]
+            if r["center"]:
+                # centre-tap-only layer (see cba_fwd): both gradients are the 1x1 convolution's GEMMs on strided views of
+                # the KRSC staging buffer / the flipped [Ci,K,K,Co] weights
+                ctr = kh // 2 * kh + kh // 2
+                self.gemm_tr(dy.data_ptr(), co, 1, x.data_ptr(), cin, 1, co, cin, M,
+                             self._epi(st[ctr * cp:], kh * kh * cp, accumulate=1), self._splits(co, cin, M))
+                self.call("pose_param_repack", self.unpack_table.data_ptr() + ui * C.sizeof(_lib.PoseRepackEntry), 1,
+                          self.wsbuf.data_ptr(), flat.grad.data_ptr(), None)
+                if not need_dx:
+                    return None
+                dx = self.buf(name + ".dx", Bn * H * W, cin)
+                e = self._epi(dx, cin, residual=add_ptr, ldr=ld_add or cin)
+                self.gemm(dy.data_ptr(), co, self.pk16[bwd + ctr * co:].data_ptr(), kh * kh * co, M, cin, co, e)
+                return dx
             tiles = ((co + 127) // 128) * ((kh * kh * cp + 127) // 128)
             splits = split_k(tiles, (M + 63) // 64)
             self.call("pose_conv2d_wgrad_bf16", dy.data_ptr(), x.data_ptr(), Bn, H, W, r["cin"], co, kh, kh, stride, dil, pad,
@@ -400,10 +454,12 @@ class CnnTrainPlan:
         self.rec[name] = dict(x=x, shape=shape, P=P, y1=y1, mr=mr, ss=ss, a1=a1, G=G, att=att)
         return out
 
-    def att_bwd(self, name, dout, add=None):
-        """dout: gradient of the gated output [B*HW, C]; returns the gradient of the block input (+ add)."""
+    def att_bwd(self, name, dout, add=None, bn_next=None):
+        """dout: gradient of the gated output [B*HW, C]; returns the gradient of the block input (+ add).  bn_next: as in
+        cba_bwd (the SE / ECA gate backward can carry the reduction pass of the BatchNorm in front of the block)."""
         cm, flat = self.cm, self.flat
         r = self.rec[name]
+        self._emit_parts = None
         att, x = r["att"], r["x"]
         Bn, H, W, ch = r["shape"]
         HW = H * W
@@ -435,6 +491,15 @@ class CnnTrainPlan:
                 self.call("pose_eca_bwd", dgate.data_ptr(), None, gate.data_ptr(), pool.data_ptr(), pool.shape[1], 1.0 / HW,
                           flat.f32(att.conv.weight).data_ptr(), k, Bn, ch, 0, dmean.data_ptr(),
                           flat.g32(att.conv.weight).data_ptr())
+            if (bn_next is not None and add is None and self.fuse_bn_bwd and bn_next["act"] in (1, 2) and bn_next["co"] == ch
+                    and bn_next["M"] == Bn * HW):
+                part = self.partials()
+                n_parts = C.c_int(0)
+                self.call("pose_gate_bwd_apply_bn_bf16", dout.data_ptr(), gate.data_ptr(), dmean.data_ptr(), 1.0 / HW, Bn, HW, ch,
+                          bn_next["y"].data_ptr(), bn_next["ss"].data_ptr(), bn_next["act"], dx.data_ptr(), part.data_ptr(),
+                          part.numel(), C.byref(n_parts))
+                self._emit_parts = n_parts.value
+                return dx
             self.call("pose_gate_bwd_apply_bf16", dout.data_ptr(), gate.data_ptr(), dmean.data_ptr(), 1.0 / HW, Bn, HW, ch, addp,
                       dx.data_ptr())
             return dx
@@ -491,11 +556,16 @@ class CnnTrainPlan:
         d = self.cba_bwd(f"{name}.conv.{cbas[-1][0]}", dout, co)
         res = dout if blk.use_residual else None
         first_is_dw = len(cbas) == 2
+        dw_name = f"{name}.conv.{cbas[-2][0]}"
+        parts = None
         if atts:
-            d = self.att_bwd(f"{name}.conv.{atts[0][0]}", d)
-        d = self.cba_bwd(f"{name}.conv.{cbas[-2][0]}", d, d.shape[1], dx_add=res if first_is_dw else None)
+            d = self.att_bwd(f"{name}.conv.{atts[0][0]}", d, bn_next=self.rec[dw_name])
+            parts = self._emit_parts
+        d = self.cba_bwd(dw_name, d, d.shape[1], dx_add=res if first_is_dw else None, dz_parts=parts,
+                         bn_next=None if first_is_dw else self.rec[f"{name}.conv.{cbas[0][0]}"])
+        parts = self._emit_parts
         if not first_is_dw:
-            d = self.cba_bwd(f"{name}.conv.{cbas[0][0]}", d, d.shape[1], dx_add=res)
+            d = self.cba_bwd(f"{name}.conv.{cbas[0][0]}", d, d.shape[1], dx_add=res, dz_parts=parts)
         return d
 
     def dual_fwd(self, name, blk, x, shape):
@@ -532,14 +602,16 @@ class CnnTrainPlan:
         dcat = self.cba_bwd(name + ".fusion", d, cout)
         # dense path (columns cout..)
         g = self.cba_bwd(name + ".dense_path.1.pointwise", dcat, ldc, da_off=cout)
-        g = self.cba_bwd(name + ".dense_path.1.depthwise", g, g.shape[1])
+        g = self.cba_bwd(name + ".dense_path.1.depthwise", g, g.shape[1], bn_next=self.rec[name + ".dense_path.0"])
+        parts = self._emit_parts
         identity = not isinstance(blk.shortcut, cm.ConvBnAct)
-        dx = self.cba_bwd(name + ".dense_path.0", g, g.shape[1], dx_add=dcat if identity else None, ld_add=ldc)
+        dx = self.cba_bwd(name + ".dense_path.0", g, g.shape[1], dx_add=dcat if identity else None, ld_add=ldc, dz_parts=parts)
         # residual path (columns 0..cout)
         g = self.cba_bwd(name + ".residual_path.2", dcat, ldc)
         g = self.cba_bwd(name + ".residual_path.1.pointwise", g, g.shape[1])
-        g = self.cba_bwd(name + ".residual_path.1.depthwise", g, g.shape[1])
-        dx = self.cba_bwd(name + ".residual_path.0", g, g.shape[1], dx_add=dx)
+        g = self.cba_bwd(name + ".residual_path.1.depthwise", g, g.shape[1], bn_next=self.rec[name + ".residual_path.0"])
+        parts = self._emit_parts
+        dx = self.cba_bwd(name + ".residual_path.0", g, g.shape[1], dx_add=dx, dz_parts=parts)
         if not identity:
             dx = self.cba_bwd(name + ".shortcut", dcat, ldc, dx_add=dx)
         return dx

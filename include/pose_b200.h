@@ -393,6 +393,23 @@ int pose_bn_bwd_bf16(const void *dA, long ld_da, const void *Y, long M, int C, c
                      float *dbeta, pose_stream_t stream);
 int pose_dwconv3x3_bwd_bf16(const void *dY, const void *X, const float *Wd, int B, int H, int W, int C, int stride,
                             const void *add, void *dX, float *dW, pose_stream_t stream);
+/* BatchNorm backward with its reduction pass folded into the PRODUCER of the incoming gradient (src/models/cnn.py:135-139
+ * under loss.backward()): the producer multiplies by act'(z) of the layer whose output it differentiates -- reading that
+ * layer's saved conv output `Yprev` and (scale, shift) -- writes dz instead of dA and emits [parts, 2, C] partial sums of dz
+ * and dz * y; pose_bn_bwd_from_dz_bf16 folds them (dgamma, dbeta accumulated, coef [2, C] scratch) and writes dY.
+ *   pose_dwconv3x3_bnbwd_bf16    producer = data gradient of a stride-1 depthwise 3x3 (taps flipped: repack kind 6);
+ *                                parts = B * pose_dwconv3x3_pool_parts(H, W, 1)
+ *   pose_gate_bwd_apply_bn_bf16  producer = backward of x * gate[b, c] (SE / ECA); *parts_out receives the partial count
+ * act_prev: 1 relu, 2 silu. */
+int pose_dwconv3x3_bnbwd_bf16(const void *dY, int B, int H, int W, int C, const float *Wflip, const void *Yprev,
+                              const float *scale_shift_prev, int act_prev, void *dZ, float *partials, long cap_floats,
+                              pose_stream_t stream);
+int pose_gate_bwd_apply_bn_bf16(const void *dOut, const float *gate, const void *dmean, float inv_hw, int B, long HW, int C,
+                                const void *Yprev, const float *scale_shift_prev, int act_prev, void *dZ, float *partials,
+                                long cap_floats, int *parts_out, pose_stream_t stream);
+int pose_bn_bwd_from_dz_bf16(const void *dZ, long ld_dz, const void *Y, long M, int C, const float *scale_shift,
+                             const float *mean_rstd, const float *partials, int parts, float *coef, void *dY, float *dgamma,
+                             float *dbeta, pose_stream_t stream);
 int pose_gate_bwd_reduce_bf16(const void *dOut, const void *X, int B, long HW, int C, float *dgate, pose_stream_t stream);
 int pose_gate_bwd_apply_bf16(const void *dOut, const float *gate, const void *dmean, float inv_hw, int B, long HW, int C,
                              const void *add, void *dX, pose_stream_t stream);

@@ -282,3 +282,91 @@ def test_trainer_reduces_the_loss(pose, golden):
     tr = train.Trainer(m, pose.ComprehensivePoseLoss(), lr=2e-4)
     losses = [tr.step(img, dep, kp, gt)[4].item() for _ in range(5)]
     assert losses[-1] < losses[0], losses
+
+
+def _bn_setup(M, Cc, g):
+    y = (torch.randn(M, Cc, generator=g) * 1.5 + 0.3).to(DEV).bfloat16()
+    gamma, beta = (torch.rand(Cc, generator=g) + 0.5).to(DEV), (torch.randn(Cc, generator=g) * 0.2).to(DEV)
+    mean, var = y.float().mean(0), y.float().var(0, unbiased=False)
+    rstd = torch.rsqrt(var + 1e-5)
+    mr = torch.cat([mean, rstd]).contiguous()
+    ss = torch.cat([gamma * rstd, beta - mean * gamma * rstd]).contiguous()
+    return y, gamma, beta, mr, ss
+
+
+def _bn_bwd_reference(y, gamma, beta, dA, act):
+    """fp32 autograd of a = act(batch_norm(y)) for the incoming gradient dA."""
+    yr = y.float().requires_grad_()
+    gr, br = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    z = F.batch_norm(yr, None, None, gr, br, True, 0.1, 1e-5)
+    a = F.silu(z) if act == 2 else F.relu(z)
+    a.backward(dA)
+    return yr.grad, gr.grad, br.grad
+
+
+@pytest.mark.parametrize("B,HW,Cc,act", [(3, 200, 64, 2), (2, 1024, 768, 2), (5, 64, 3072, 1), (4, 37, 16, 2)])
+def test_batchnorm_backward_reduction_carried_by_the_gate_backward(pose, B, HW, Cc, act):
+    """pose_gate_bwd_apply_bn_bf16 + pose_bn_bwd_from_dz_bf16 == the SE / ECA gate backward followed by the BatchNorm + act
+    backward of the layer in front of it (fp32 autograd of both)."""
+    lib, sp, check = _lib(pose)
+    g = torch.Generator().manual_seed(B * 7 + Cc)
+    M = B * HW
+    y, gamma, beta, mr, ss = _bn_setup(M, Cc, g)
+    dO = torch.randn(M, Cc, generator=g).to(DEV).bfloat16()
+    gate = torch.rand(B, Cc, generator=g).to(DEV)
+    dmean = torch.randn(B, Cc, generator=g).to(DEV).bfloat16()
+    part = torch.empty(4 << 20, device=DEV)
+    coef = torch.empty(2 * Cc, device=DEV)
+    dz, dy = torch.empty_like(y), torch.empty_like(y)
+    dg, db = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
+    n_parts = C.c_int(0)
+    check(lib.pose_gate_bwd_apply_bn_bf16(dO.data_ptr(), gate.data_ptr(), dmean.data_ptr(), 1.0 / HW, B, HW, Cc, y.data_ptr(),
+                                          ss.data_ptr(), act, dz.data_ptr(), part.data_ptr(), part.numel(), C.byref(n_parts), sp()),
+          "gate_bn")
+    assert n_parts.value > 0
+    check(lib.pose_bn_bwd_from_dz_bf16(dz.data_ptr(), Cc, y.data_ptr(), M, Cc, ss.data_ptr(), mr.data_ptr(), part.data_ptr(),
+                                       n_parts.value, coef.data_ptr(), dy.data_ptr(), dg.data_ptr(), db.data_ptr(), sp()), "from_dz")
+    dA = (dO.float().view(B, HW, Cc) * gate[:, None, :] + dmean.float()[:, None, :] / HW).view(M, Cc)
+    want, wg, wb = _bn_bwd_reference(y, gamma, beta, dA, act)
+    scale = want.abs().max().item()
+    assert (dy.float() - want).abs().max().item() < 2e-2 * scale + 1e-3
+    assert torch.allclose(dg, wg, rtol=2e-2, atol=2e-2 * M ** 0.5)
+    assert torch.allclose(db, wb, rtol=2e-2, atol=2e-2 * M ** 0.5)
+    # deterministic: fixed-order partial sums
+    dg2, db2 = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
+    check(lib.pose_gate_bwd_apply_bn_bf16(dO.data_ptr(), gate.data_ptr(), dmean.data_ptr(), 1.0 / HW, B, HW, Cc, y.data_ptr(),
+                                          ss.data_ptr(), act, dz.data_ptr(), part.data_ptr(), part.numel(), C.byref(n_parts), sp()),
+          "gate_bn")
+    check(lib.pose_bn_bwd_from_dz_bf16(dz.data_ptr(), Cc, y.data_ptr(), M, Cc, ss.data_ptr(), mr.data_ptr(), part.data_ptr(),
+                                       n_parts.value, coef.data_ptr(), dy.data_ptr(), dg2.data_ptr(), db2.data_ptr(), sp()), "from_dz")
+    assert torch.equal(dg, dg2) and torch.equal(db, db2)
+
+
+@pytest.mark.parametrize("B,H,W,Cc,act", [(2, 32, 32, 128, 2), (3, 16, 16, 768, 2), (2, 19, 13, 64, 1), (1, 8, 40, 24, 2)])
+def test_batchnorm_backward_reduction_carried_by_the_depthwise_data_gradient(pose, B, H, W, Cc, act):
+    """pose_dwconv3x3_bnbwd_bf16 + pose_bn_bwd_from_dz_bf16 == data gradient of a stride-1 depthwise 3x3 followed by the
+    BatchNorm + act backward of the layer that produced its input (fp32 autograd of both)."""
+    lib, sp, check = _lib(pose)
+    g = torch.Generator().manual_seed(H * 3 + Cc)
+    M = B * H * W
+    y, gamma, beta, mr, ss = _bn_setup(M, Cc, g)
+    dyw = torch.randn(B, H, W, Cc, generator=g).to(DEV).bfloat16()            # gradient of the depthwise OUTPUT
+    wdw = (torch.randn(Cc, 1, 3, 3, generator=g) * 0.3).to(DEV)
+    wflip = wdw.view(Cc, 9).flip(1).t().contiguous()                          # [9, C], taps flipped (repack kind 6)
+    parts = B * lib.pose_dwconv3x3_pool_parts(H, W, 1)
+    part = torch.empty(max(parts * 2 * Cc, 1 << 16), device=DEV)
+    coef = torch.empty(2 * Cc, device=DEV)
+    dz, dy = torch.empty_like(y), torch.empty_like(y)
+    dg, db = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
+    check(lib.pose_dwconv3x3_bnbwd_bf16(dyw.data_ptr(), B, H, W, Cc, wflip.data_ptr(), y.data_ptr(), ss.data_ptr(), act,
+                                        dz.data_ptr(), part.data_ptr(), part.numel(), sp()), "dw_bnbwd")
+    check(lib.pose_bn_bwd_from_dz_bf16(dz.data_ptr(), Cc, y.data_ptr(), M, Cc, ss.data_ptr(), mr.data_ptr(), part.data_ptr(), parts,
+                                       coef.data_ptr(), dy.data_ptr(), dg.data_ptr(), db.data_ptr(), sp()), "from_dz")
+    xin = torch.zeros(B, Cc, H, W, device=DEV, requires_grad=True)
+    F.conv2d(xin, wdw, None, 1, 1, 1, Cc).backward(dyw.float().permute(0, 3, 1, 2))
+    dA = xin.grad.permute(0, 2, 3, 1).reshape(M, Cc)
+    want, wg, wb = _bn_bwd_reference(y, gamma, beta, dA, act)
+    scale = want.abs().max().item()
+    assert (dy.float() - want).abs().max().item() < 2e-2 * scale + 1e-3
+    assert torch.allclose(dg, wg, rtol=2e-2, atol=2e-2 * M ** 0.5)
+    assert torch.allclose(db, wb, rtol=2e-2, atol=2e-2 * M ** 0.5)

@@ -13,6 +13,7 @@ def timed(fn, reps=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e3
 
+DROP = float(sys.argv[1]) if len(sys.argv) > 1 else 0.0
 for (B, heads, hd, N) in ((64, 12, 64, 257), (64, 12, 64, 256), (64, 16, 48, 273), (64, 16, 48, 256), (64, 12, 64, 320)):
     E_ = heads * hd
     T = max(N, 273)
@@ -24,9 +25,9 @@ for (B, heads, hd, N) in ((64, 12, 64, 257), (64, 12, 64, 256), (64, 16, 48, 273
     ld, bs, bso = 3 * E_, T * 3 * E_, T * E_
     sc = 1 / math.sqrt(hd)
     f = timed(lambda: lib.pose_attention_bf16(p, p + 2 * E_, p + 4 * E_, o.data_ptr(), B, heads, N, N, hd, ld, ld, ld, E_, bs, bs, bs, bso,
-                                              sc, lse.data_ptr(), 0.0, 0, sp()))
+                                              sc, lse.data_ptr(), DROP, 5, sp()))
     b = timed(lambda: lib.pose_attention_bwd_bf16(p, p + 2 * E_, p + 4 * E_, o.data_ptr(), do.data_ptr(), lse.data_ptr(), dp, dp + 2 * E_,
                                                   dp + 4 * E_, dws.data_ptr(), B, heads, N, N, hd, ld, ld, ld, E_, E_, ld, ld, ld, bs, bs, bs,
-                                                  bso, bso, bs, bs, bs, sc, 0.0, 0, sp()))
+                                                  bso, bso, bs, bs, bs, sc, DROP, 5, sp()))
     fl = 4.0 * B * heads * N * N * hd
-    print(f"B={B} heads={heads} hd={hd} N={N}: fwd {f:7.1f} us ({fl / f / 1e6:6.1f} TFLOP/s)  bwd {b:7.1f} us ({2.5 * fl / b / 1e6:6.1f} TFLOP/s)")
+    print(f"drop={DROP} B={B} heads={heads} hd={hd} N={N}: fwd {f:7.1f} us ({fl / f / 1e6:6.1f} TFLOP/s)  bwd {b:7.1f} us ({2.5 * fl / b / 1e6:6.1f} TFLOP/s)")
