@@ -73,6 +73,8 @@ struct ConvGeom {          // MODE 1 only
     int cchunks;           // Cin_pad / BKC
     int tiles_w, tiles_h;  // ceil(Wo / TW), ceil(Ho / TH)
     int cw;                // MODE 2: channels per B block (64: 128-byte pixels, SWIZZLE_128B; 32: 64-byte pixels, SWIZZLE_64B)
+    int linear;            // MODE 1, host side: tile row r of M tile mt IS output pixel mt * 128 + r (full-width or single-row
+                           // patches that tile the map exactly), so the TMA-store epilogues of the plain GEMM apply
 };
 
 template <int BN, int kStages, int BKC, int TMA_EPI = 0, int CG2 = 0>
@@ -1058,18 +1060,21 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
     const bool heavy = ep.act == 3 || ep.act >= 5 || ep.preact != nullptr || !tma_heavy_only;
     const bool lean_shape = ep.act == 0 && ep.bias == nullptr && ep.preact == nullptr && ep.drop_thresh == 0 &&
                             ep.out_scale == 1.0f && (ep.residual == nullptr || ep.res_scale == 1.0f) && k_splits <= 1;
-    if (MODE == 0 && ep.out_bf16 && !ep.accumulate && ep.vec && N % 32 == 0 && heavy && !tma_off && !lean_shape &&
+    // the TMA-store epilogues address output rows linearly: the plain GEMM, and convolutions whose patches are linear
+    static const bool conv_tma_off = getenv("POSE_NO_CONV_TMA_EPILOGUE") != nullptr;      // A/B switch for measurements
+    const bool rows_linear = MODE == 0 || (MODE == 1 && cg.linear && !conv_tma_off);
+    if (rows_linear && ep.out_bf16 && !ep.accumulate && ep.vec && N % 32 == 0 && heavy && !tma_off && !lean_shape &&
         ep.stats == nullptr) {
         int e = make_map_tile32(&mc, ep.C, M, N, ep.ldc);
         if (!e && ep.residual) e = make_map_tile32(&maux, ep.residual, M, N, ep.ldr);
         if (!e && ep.preact) e = make_map_tile32(&mpre, ep.preact, M, N, ep.ldc);
         ep.tma = e ? 0 : 1;
     }
-    constexpr int kTma = MODE == 0 ? 1 : 0;
+    constexpr int kTma = (MODE == 0 || MODE == 1) ? 1 : 0;
     constexpr int kStagesT = (kTma && BN == 128) ? kStages + 1 : kStages;      // 5 x 32 KB stages fit beside the TMA staging
     // lean plain epilogue (TMA_EPI 2; MODE 0, tiles up to 128 columns): bf16 C = acc (+ residual), optional column
     // statistics (tools/bench_gemm_cnn.py measures it on the CNN's 1x1 shapes).
-    constexpr bool kHasLean = MODE == 0;
+    constexpr bool kHasLean = MODE == 0 || MODE == 1;
     constexpr int kLean = kHasLean ? 2 : 0;
     constexpr int kStagesL = kStagesT;
     using S0 = GemmSmem<BN, kStages, BKC, 0>;
@@ -1089,7 +1094,7 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
     }
     static const bool lean_off = getenv("POSE_NO_LEAN_EPILOGUE") != nullptr;   // A/B switch for measurements
     bool lean = false;
-    if (kHasLean && !lean_off && !ep.tma && ep.out_bf16 && !ep.accumulate && ep.vec && N % 32 == 0 && lean_shape) {
+    if (kHasLean && rows_linear && !lean_off && !ep.tma && ep.out_bf16 && !ep.accumulate && ep.vec && N % 32 == 0 && lean_shape) {
         int e = make_map_tile32(&mc, ep.C, M, N, ep.ldc);
         if (!e && ep.residual) e = make_map_tile32(&maux, ep.residual, M, N, ep.ldr);
         lean = !e;
@@ -1364,7 +1369,8 @@ POSE_API int pose_conv2d_bf16(const void *X, int Nimg, int H, int Wd, int Cin, c
     e = make_map_nhwc(&ma, X, Nimg, H, Wd, Cin, bkc, TW, TH, TN, stride);
     if (e) return e;
     const int tiles_w = (Wo + TW - 1) / TW, tiles_h = (Ho + TH - 1) / TH;
-    ConvGeom cg = {Ho, Wo, TH, TW, TN, Nimg, KW, KH * KW, stride, dil, pad, Cin / bkc, tiles_w, tiles_h, 64};
+    ConvGeom cg = {Ho, Wo, TH, TW, TN, Nimg, KW, KH * KW, stride, dil, pad, Cin / bkc, tiles_w, tiles_h, 64,
+                   exact && (TW == Wo || TH == 1) ? 1 : 0};
     const int m_tiles = ((Nimg + TN - 1) / TN) * tiles_h * tiles_w;
     const int M = Nimg * Ho * Wo;
     cudaStream_t s = (cudaStream_t)stream;
