@@ -45,6 +45,13 @@ def work(name, a):
         return "batchnorm", 0.0, (4.0 + (2.0 if a[6] else 0.0)) * a[1] * a[2]
     if name == "pose_bn_bwd_bf16":
         return "batchnorm", 0.0, 10.0 * a[3] * a[4]
+    if name == "pose_bn_bwd_from_dz_bf16":               # dz and y read, dY written (the reduction ran in the producer)
+        return "batchnorm", 0.0, 6.0 * a[3] * a[4]
+    if name == "pose_gate_bwd_apply_bn_bf16":            # dOut and the BatchNorm's y read, dz written: the reduction pass of
+        return "batchnorm", 0.0, 6.0 * a[4] * a[5] * a[6]    # that BatchNorm is this launch (counted with its family)
+    if name == "pose_dwconv3x3_bnbwd_bf16":
+        B, H, W, C = a[1:5]
+        return "depthwise", 0.0, 2.0 * B * C * 3 * H * W
     if name in ("pose_bn_finalize", "pose_bn_finalize_parts"):
         return "batchnorm", 0.0, 0.0
     if name in ("pose_dwconv3x3_bf16", "pose_dwconv3x3_bn_stats_bf16"):
