@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..params import FlatParams
-from ..utils import split_k, activation_id
+from ..utils import split_k, wgrad_splits, activation_id
 
 
 def _ceil8(n):
@@ -176,7 +176,7 @@ class CnnTrainPlan:
 
     @staticmethod
     def _splits(n_out, n_in, rows):
-        return split_k(((n_out + 127) // 128) * ((n_in + 127) // 128), (rows + 63) // 64)
+        return wgrad_splits(n_out, n_in, rows)
 
     # ---- ConvBnAct ------------------------------------------------------------------------------------
     def cba_fwd(self, name, cba, x, shape, act="default", out=None, ld_out=None, col_off=0, residual=None, ld_res=0):

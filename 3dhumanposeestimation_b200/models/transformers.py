@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..params import FlatParams
-from ..utils import GraphedForward, split_k, activation_id, get_activation
+from ..utils import GraphedForward, wgrad_splits, activation_id, get_activation
 from .common import GaussianHeatmapGenerator
 
 _VIT_TABLE = {  # timm model name -> (embed_dim, depth, heads, patch)
@@ -495,7 +495,7 @@ class VitPlan:
 
     # ---- backward ops --------------------------------------------------------------------------------
     def _splits(self, n_out, n_in, m_rows):
-        return split_k(((n_out + 127) // 128) * ((n_in + 127) // 128), (m_rows + 63) // 64)
+        return wgrad_splits(n_out, n_in, m_rows)
 
     def drop_grad(self, name, d, site, p):
         """Gradient entering a dropout site: the forward's mask (same seed) applied to d -> a new buffer."""

@@ -74,6 +74,18 @@ def split_k(tiles: int, kblocks: int, sms: int = 148, max_splits: int = 128) -> 
     return best
 
 
+def wgrad_splits(n_out: int, n_in: int, rows: int) -> int:
+    """Split-K factor passed to pose_gemm_bf16_tr for dW[n_out, n_in] = dY^T X over `rows` samples.  split_k sizes it for
+    128 x 128 tiles; when that lands on ONE split although the contraction is long and the output is 256-column tileable,
+    two splits switch the kernel to 256-column CTA-pair tiles (the library doubles the factor for them) whose work items
+    still fill the machine -- measured on the ViT's fc1 / fc2 weight gradients (768 x 3072 over 16448 rows): 90 -> 63 us."""
+    kblocks = (rows + 63) // 64
+    s = split_k(((n_out + 127) // 128) * ((n_in + 127) // 128), kblocks)
+    if s == 1 and n_in % 256 == 0 and n_out >= 256 and kblocks >= 64:
+        s = 2
+    return s
+
+
 class GraphedForward:
     """Eval-mode forward of a launch plan replayed from ONE CUDA graph (run_inference, infer.py:383-393, runs batch 1: a
     forward of ~200 launches of a few microseconds each is launch bound).  `fn(*static_inputs)` must enqueue the forward on

@@ -44,5 +44,10 @@ fwd(T, 3072, 768, 0); fwd(T, 3072, 768, 3); fwd(T, 3072, 768, 3, preact=True); f
 fwd(T, 768, 3072, 0); fwd(T, 768, 3072, 0, res=True); fwd(T, 2304, 768, 0); fwd(T, 768, 768, 0, res=True)
 dgrad(T, 3072, 768, 0); dgrad(T, 3072, 768, 5); dgrad(T, 768, 3072); dgrad(T, 768, 2304); dgrad(T, 768, 768)
 for s in (1, 2, 4, 8): wgrad(768, 3072, T, s)
-wgrad(3072, 768, T, 2); wgrad(2304, 768, T, 4); wgrad(768, 768, T, 8)
+for s in (1, 2, 4): wgrad(3072, 768, T, s)
+for s in (1, 2, 4, 8): wgrad(2304, 768, T, s)
+for s in (1, 2, 4, 8): wgrad(768, 768, T, s)
+T2 = 64 * 273
+for s in (1, 2, 4): wgrad(768, 3072, T2, s)
+for s in (2, 4, 8): wgrad(768, 768, T2, s)
 fwd(8192, 8192, 8192, 0)
