@@ -120,6 +120,7 @@ SIGNATURES = {
                                              C.c_long, c_void_p]),
     "pose_bn_apply_bf16": (c_int, [c_void_p, C.c_long, c_int, c_void_p, c_int, c_float, c_void_p, C.c_long, c_void_p, C.c_long,
                                    c_void_p]),
+    "pose_bn_apply_pool_bf16": (c_int, [c_void_p, c_int, C.c_long, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "pose_bn_bwd_bf16": (c_int, [c_void_p, C.c_long, c_void_p, C.c_long, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p,
                                  C.c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pose_dwconv3x3_bnbwd_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,

@@ -296,6 +296,47 @@ bn_apply_kernel(const __nv_bfloat16 *__restrict__ Y, long M, int C, const float 
     });
 }
 
+// out = act(y * scale + shift) for the layer in front of an SE / ECA block, plus the squeeze of that block: per-(image, row
+// block) channel sums of the bf16-ROUNDED outputs, pool [B, gridDim.x, C] (written, not accumulated: the consumers fold the
+// parts in a fixed order).  grid (row blocks, image); the separate pool_sum pass over `out` disappears.
+template <int ACT>
+__global__ void __launch_bounds__(384, 2)
+bn_apply_pool_kernel(const __nv_bfloat16 *__restrict__ Y, long HW, int C, const float *__restrict__ scale_shift,
+                     __nv_bfloat16 *__restrict__ out, float *__restrict__ pool) {
+    const RowMap rm(C);
+    const long base = (long)blockIdx.y * HW;
+    float2 a[4], b[4], s[4];
+    ld8p(scale_shift + rm.c0, a);
+    ld8p(scale_shift + C + rm.c0, b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] = make_float2(0.f, 0.f);
+    const long step = (long)gridDim.x * rm.rpb;
+    auto body = [&](long r, const uint4 &vy) {
+        float2 y[4], q[4];
+        up8q(vy, y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = actf2<ACT>(__ffma2_rn(y[j], a[j], b[j]));
+        const uint4 pk = pk8p(y);
+        *(uint4 *)(out + (base + r) * C + rm.c0) = pk;
+        up8q(pk, q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] = __fadd2_rn(s[j], q[j]);
+    };
+    long r = (long)blockIdx.x * rm.rpb + rm.rsub;
+    for (; r + 3 * step < HW; r += 4 * step) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg_batch(Y + (base + r + u * step) * C + rm.c0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) body(r + u * step, v[u]);
+    }
+    for (; r < HW; r += step) body(r, ldg_batch(Y + (base + r) * C + rm.c0));
+    float acc[1][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[0][2 * j] = s[j].x; acc[0][2 * j + 1] = s[j].y; }
+    rowmap_fold<1, false>(rm, C, acc, pool, ((long)blockIdx.y * gridDim.x + blockIdx.x) * C);
+}
+
 // pass 1 of the backward: sums2[c] += dz, sums2[C + c] += dz * xhat, dz = dA * out_scale * act'(z)
 template <int ACT>
 __global__ void __launch_bounds__(384)
@@ -1284,6 +1325,21 @@ POSE_API int pose_bn_apply_bf16(const void *Y, long M, int C, const float *scale
     if (act == 0) BN_APPLY_R(0) else if (act == 1) BN_APPLY_R(1) else BN_APPLY_R(2)
 #undef BN_APPLY_R
 #undef BN_APPLY
+    return launch_status();
+}
+
+POSE_API int pose_bn_apply_pool_bf16(const void *Y, int B, long HW, int C, const float *scale_shift, int act, void *out,
+                                     float *pool, int parts, pose_stream_t stream) {
+    REQ(Y && scale_shift && out && pool, POSE_E_NULL);
+    REQ(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && parts > 0, POSE_E_SHAPE);
+    REQ((uintptr_t)Y % 16 == 0 && (uintptr_t)out % 16 == 0, POSE_E_ALIGN);
+    REQ(C <= 3072 && act >= 0 && act <= 2, POSE_E_UNSUPPORTED);
+    const int thr = rowmap_threads(C);
+    const dim3 grid((unsigned)parts, (unsigned)B);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (act == 0) bn_apply_pool_kernel<0><<<grid, thr, 0, s>>>((const __nv_bfloat16 *)Y, HW, C, scale_shift, (__nv_bfloat16 *)out, pool);
+    else if (act == 1) bn_apply_pool_kernel<1><<<grid, thr, 0, s>>>((const __nv_bfloat16 *)Y, HW, C, scale_shift, (__nv_bfloat16 *)out, pool);
+    else bn_apply_pool_kernel<2><<<grid, thr, 0, s>>>((const __nv_bfloat16 *)Y, HW, C, scale_shift, (__nv_bfloat16 *)out, pool);
     return launch_status();
 }
 

@@ -179,7 +179,8 @@ class CnnTrainPlan:
         return wgrad_splits(n_out, n_in, rows)
 
     # ---- ConvBnAct ------------------------------------------------------------------------------------
-    def cba_fwd(self, name, cba, x, shape, act="default", out=None, ld_out=None, col_off=0, residual=None, ld_res=0):
+    def cba_fwd(self, name, cba, x, shape, act="default", out=None, ld_out=None, col_off=0, residual=None, ld_res=0,
+                pool=None):
         """x: [B,H,W,Cin] bf16 (channels-last).  Returns (a, (B,Ho,Wo,Cout)); records what the backward needs."""
         Bn, H, W, cin = shape
         conv, bn = cba.conv, cba.norm
@@ -257,8 +258,17 @@ class CnnTrainPlan:
             out = self.buf(name + ".a", M, co)
             ld_out = co
         optr = out.data_ptr() + 2 * col_off
-        self.call("pose_bn_apply_bf16", y.data_ptr(), M, co, ss.data_ptr(), a_id, 1.0,
-                  residual.data_ptr() if residual is not None else None, ld_res, optr, ld_out)
+        self._pool = None
+        if pool is not None and residual is None and ld_out == co and col_off == 0:
+            # the layer feeds an SE / ECA block: its squeeze (per-image channel sums) rides along with the normalisation
+            HWo = Ho * Wo
+            parts = max(1, min(HWo // 8 if HWo >= 8 else 1, (148 * 4) // Bn))      # one wave of resident CTAs
+            pl = self.buf(pool, Bn, parts, co, dtype=torch.float32)
+            self.call("pose_bn_apply_pool_bf16", y.data_ptr(), Bn, HWo, co, ss.data_ptr(), a_id, optr, pl.data_ptr(), parts)
+            self._pool = pl
+        else:
+            self.call("pose_bn_apply_bf16", y.data_ptr(), M, co, ss.data_ptr(), a_id, 1.0,
+                      residual.data_ptr() if residual is not None else None, ld_res, optr, ld_out)
         self.rec[name] = dict(kind=kind, x=x, shape=shape, y=y, mr=mr, ss=ss, act=a_id, M=M, co=co, cin=cin,
                               oshape=(Bn, Ho, Wo, co), cba=cba, center=kind == "conv" and center)
         return out, (Bn, Ho, Wo, co)
@@ -401,12 +411,13 @@ class CnnTrainPlan:
         self.call("pose_pool_sum_bf16", x.data_ptr(), Bn, HW, ch, pool.data_ptr(), parts)
         return pool
 
-    def att_fwd(self, name, att, x, shape):
+    def att_fwd(self, name, att, x, shape, pool=None):
         cm, flat = self.cm, self.flat
         Bn, H, W, ch = shape
         HW = H * W
         if isinstance(att, (cm.SEBlock, cm.ECABlock)):
-            pool = self.pool_sums(name + ".pool", x, Bn, HW, ch)
+            if pool is None:
+                pool = self.pool_sums(name + ".pool", x, Bn, HW, ch)
             gate = self.buf(name + ".gate", Bn, ch, dtype=torch.float32)
             if isinstance(att, cm.SEBlock):
                 w1, w2 = att.fc[0].weight, att.fc[2].weight
@@ -541,9 +552,11 @@ class CnnTrainPlan:
         y, s = x, shape
         if len(cbas) == 3:
             y, s = self.cba_fwd(f"{name}.conv.{cbas[0][0]}", cbas[0][1], y, s)
-        y, s = self.cba_fwd(f"{name}.conv.{cbas[-2][0]}", cbas[-2][1], y, s)
+        gated = bool(atts) and isinstance(atts[0][1], (cm.SEBlock, cm.ECABlock))
+        y, s = self.cba_fwd(f"{name}.conv.{cbas[-2][0]}", cbas[-2][1], y, s,
+                            pool=f"{name}.conv.{atts[0][0]}.pool" if gated else None)
         if atts:
-            y = self.att_fwd(f"{name}.conv.{atts[0][0]}", atts[0][1], y, s)
+            y = self.att_fwd(f"{name}.conv.{atts[0][0]}", atts[0][1], y, s, pool=self._pool if gated else None)
         return self.cba_fwd(f"{name}.conv.{cbas[-1][0]}", cbas[-1][1], y, s, act=None,
                             residual=x if blk.use_residual else None, ld_res=shape[3])
 
@@ -588,9 +601,11 @@ class CnnTrainPlan:
         d, sd = self.cba_fwd(name + ".dense_path.1.depthwise", blk.dense_path[1].depthwise, d, sd)
         self.cba_fwd(name + ".dense_path.1.pointwise", blk.dense_path[1].pointwise, d, sd, out=cat, ld_out=cout + dense,
                      col_off=cout)
-        f, sf = self.cba_fwd(name + ".fusion", blk.fusion, cat, (s[0], s[1], s[2], cout + dense))
+        gated = blk.attention is not None and isinstance(blk.attention, (cm.SEBlock, cm.ECABlock))
+        f, sf = self.cba_fwd(name + ".fusion", blk.fusion, cat, (s[0], s[1], s[2], cout + dense),
+                             pool=name + ".attention.pool" if gated else None)
         if blk.attention is not None:
-            f = self.att_fwd(name + ".attention", blk.attention, f, sf)
+            f = self.att_fwd(name + ".attention", blk.attention, f, sf, pool=self._pool if gated else None)
         return f, sf
 
     def dual_bwd(self, name, blk, dout):

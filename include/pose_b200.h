@@ -388,6 +388,10 @@ int pose_bn_finalize(const float *partials, long cap_floats, long count, const f
                      pose_stream_t stream);
 int pose_bn_apply_bf16(const void *Y, long M, int C, const float *scale_shift, int act, float out_scale, const void *residual,
                        long ld_res, void *out, long ld_out, pose_stream_t stream);
+/* pose_bn_apply_bf16 (no residual, compact output) for the layer in front of an SE / ECA block, fused with that block's
+ * squeeze (cnn.py:22-23, 40-41): pool [B, parts, C] receives per-(image, row block) channel sums of the bf16 outputs. */
+int pose_bn_apply_pool_bf16(const void *Y, int B, long HW, int C, const float *scale_shift, int act, void *out, float *pool,
+                            int parts, pose_stream_t stream);
 int pose_bn_bwd_bf16(const void *dA, long ld_da, const void *Y, long M, int C, const float *scale_shift, const float *mean_rstd,
                      int act, float out_scale, float *partials, long cap_floats, float *coef, void *dY, float *dgamma,
                      float *dbeta, pose_stream_t stream);
