@@ -764,7 +764,7 @@ gate_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dO, const float *__restr
 // dz = dA * act'(y * scale + shift) and the per-CTA partial sums of dz and dz * y ([gridDim.y * gridDim.x, 2, C]): the first
 // pass of pose_bn_bwd_bf16 (one read of dA and y) disappears.
 template <int ACT>
-__global__ void __launch_bounds__(384)
+__global__ void __launch_bounds__(384, 2)
 gate_bwd_apply_bn_kernel(const __nv_bfloat16 *__restrict__ dO, const float *__restrict__ gate, const __nv_bfloat16 *__restrict__ dmean,
                          float inv_hw, long HW, int C, const __nv_bfloat16 *__restrict__ Ybn, const float *__restrict__ scale_shift,
                          __nv_bfloat16 *__restrict__ dZ, float *__restrict__ partials) {

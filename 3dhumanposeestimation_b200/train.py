@@ -36,6 +36,12 @@ class Trainer:
         self.bucket_bytes = bucket_bytes
         self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
         self._pending = []
+        # coalescing threshold of the gradient exchange (bytes of fp32 gradient; 0 = every announced section on its own).
+        # Measured at 8 GPUs, ViT B = 64 / GPU: per-section exchange 26.08 ms / step, 128 MB 25.62, one exchange after the
+        # backward 25.68 (1 GPU: 24.1): short collectives spread over the whole backward cost more in interference
+        # with the persistent GEMM grids than their overlap hides
+        self.comm_min_bytes = int(os.environ.get("POSE_DP_MIN_BYTES", str(128 << 20)))
+        self._pend_hi = self._pend_lo = None
         self.out5 = None
         # gradient exchange format: "bf16" halves the bytes on NVLink (each finished section of the flat fp32 gradient is
         # cast to a bf16 staging buffer on the communication stream, all-reduced there, and read by the fused AdamW
@@ -56,9 +62,26 @@ class Trainer:
 
     # ---- gradient exchange ---------------------------------------------------------------------------
     def _section_done(self, flat, lo, hi):
-        """Gradients in flat[lo:hi) are final: all-reduce them on the communication stream (bucketed)."""
+        """Gradients in flat[lo:hi) are final: all-reduce them on the communication stream (bucketed).  Sections arrive
+        from the tail of the flat buffer towards its head; they are coalesced until `comm_min_bytes` of gradient are
+        pending (or the head is reached), so that the exchange runs as a few long collectives instead of many short
+        ones sharing the SMs with the backward kernels for the whole pass."""
         if self.world == 1 or hi <= lo:
             return
+        if self._pend_hi is not None and self._pend_lo != hi:      # not adjacent to what is pending: send that first
+            plo, phi = self._pend_lo, self._pend_hi
+            self._pend_hi = self._pend_lo = None
+            self._exchange(flat, plo, phi)
+        if self._pend_hi is None:
+            self._pend_hi = hi
+        self._pend_lo = lo
+        if lo > 0 and (self._pend_hi - lo) * 4 < self.comm_min_bytes:
+            return
+        lo, hi = self._pend_lo, self._pend_hi
+        self._pend_hi = self._pend_lo = None
+        self._exchange(flat, lo, hi)
+
+    def _exchange(self, flat, lo, hi):
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm_stream):
