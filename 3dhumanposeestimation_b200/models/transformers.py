@@ -162,15 +162,66 @@ class VisionTransformerBackbone(nn.Module):
                 nn.init.zeros_(m.bias)
 
 
+def adapt_timm_vit_state_dict(sd, in_chans, num_patches_hw, num_prefix_tokens=1):
+    """A timm ``VisionTransformer`` state dict (3-channel patch embedding, the position embedding of its pre-training
+    resolution) -> the tensors of ``VisionTransformerBackbone`` for this model:
+      * patch_embed.proj.weight 3 -> `in_chans` channels exactly like the reference (src/models/transformers.py:179-214:
+        the RGB filters are kept, every extra channel gets their mean; fewer channels: the mean repeated);
+      * pos_embed resampled to the new patch grid the way timm does when ``img_size`` differs (``resample_abs_pos_embed``:
+        prefix tokens kept, the grid interpolated bicubically with antialiasing);
+      * classifier head / pre-logits entries dropped (``num_classes=0``)."""
+    out = {k: v for k, v in sd.items() if not k.startswith(("head.", "fc_norm.", "head_drop."))}
+    w = out["patch_embed.proj.weight"]
+    c0 = w.shape[1]
+    if in_chans > c0:
+        extra = w.mean(dim=1, keepdim=True).repeat(1, in_chans - c0, 1, 1)
+        out["patch_embed.proj.weight"] = torch.cat([w, extra], dim=1)
+    elif in_chans < c0:
+        out["patch_embed.proj.weight"] = w.mean(dim=1, keepdim=True).repeat(1, in_chans, 1, 1)
+    pe = out["pos_embed"]
+    gh, gw = num_patches_hw
+    n_old = pe.shape[1] - num_prefix_tokens
+    if n_old != gh * gw:
+        g0 = int(round(n_old ** 0.5))
+        if g0 * g0 != n_old:
+            raise ValueError(f"pos_embed with {n_old} grid tokens is not a square grid")
+        prefix, grid = pe[:, :num_prefix_tokens], pe[:, num_prefix_tokens:]
+        grid = grid.reshape(1, g0, g0, -1).permute(0, 3, 1, 2).float()
+        grid = torch.nn.functional.interpolate(grid, size=(gh, gw), mode="bicubic", antialias=True)
+        grid = grid.permute(0, 2, 3, 1).reshape(1, gh * gw, -1).to(pe.dtype)
+        out["pos_embed"] = torch.cat([prefix, grid], dim=1)
+    return out
+
+
+def _pretrained_vit_state_dict(name):
+    """vit_pretrained=True (the reference's default, transformers.py:174-179): the weights come from a local file named by
+    POSE_VIT_WEIGHTS (a ``torch.save``d timm state dict -- there is no network on the training boxes) or, when timm is
+    installed, from ``timm.create_model(name, pretrained=True)``."""
+    import os
+    path = os.environ.get("POSE_VIT_WEIGHTS")
+    if path:
+        sd = torch.load(path, map_location="cpu", weights_only=True)
+        return sd.get("state_dict", sd.get("model", sd)) if isinstance(sd, dict) else sd
+    try:
+        import timm
+    except ImportError:
+        raise NotImplementedError(
+            "vit_pretrained=True needs the timm weights: point POSE_VIT_WEIGHTS at a saved timm state dict of "
+            f"{name!r} (or install timm), or construct with vit_pretrained=False and load a checkpoint") from None
+    return timm.create_model(name, pretrained=True, num_classes=0).state_dict()
+
+
 class TransformerPoseEstimation(nn.Module):  # transformers.py:140-373
     def __init__(self, config):
         super().__init__()
         c = config
-        if getattr(c, "vit_pretrained", False):
-            raise NotImplementedError("vit_pretrained=True downloads timm weights; construct with vit_pretrained=False "
-                                      "and load a checkpoint with load_state_dict (keys match the reference)")
         self.config = c
         self.vit_backbone = VisionTransformerBackbone(c.vit_model_name, tuple(c.image_size), c.image_in_channels)
+        if getattr(c, "vit_pretrained", False):
+            p = self.vit_backbone.patch_size
+            sd = adapt_timm_vit_state_dict(_pretrained_vit_state_dict(c.vit_model_name), c.image_in_channels,
+                                           (c.image_size[0] // p, c.image_size[1] // p))
+            self.vit_backbone.load_state_dict(sd)
         c.transformer_embed_dim = self.vit_backbone.embed_dim
         E = c.transformer_embed_dim
         self.heatmap_generator = GaussianHeatmapGenerator(c.num_joints, c.heatmap_size, c.heatmap_sigma)

@@ -1,5 +1,8 @@
 """CPU: host-side logic of the drop-in classes (no kernels launched)."""
+import importlib
+
 import numpy as np
+import pytest
 
 
 def test_draw_params_consumes_rng_in_reference_order(pose, golden):
@@ -120,3 +123,35 @@ def test_next_row_host_mirrors_refuse_cpu_tensors():
         col([sample])
     with pytest.raises(ValueError):
         col([])
+
+
+def test_vit_pretrained_weights_from_a_local_timm_state_dict(pose, tmp_path, monkeypatch):
+    """ModelConfig("transformer") defaults to vit_pretrained=True (reference model_config.py / transformers.py:174-214): the
+    timm weights come from POSE_VIT_WEIGHTS; the 3 -> 4 channel patch embedding is adapted like the reference (RGB filters
+    kept, the depth channel gets their mean) and the position embedding is resampled from the 14 x 14 pre-training grid."""
+    import torch
+    tr = importlib.import_module("3dhumanposeestimation_b200.models.transformers")
+    torch.manual_seed(3)
+    donor = tr.VisionTransformerBackbone("vit_base_patch16_224", (224, 224), 3)
+    sd = {k: torch.randn_like(v) * 0.05 for k, v in donor.state_dict().items()}
+    sd["head.weight"], sd["head.bias"] = torch.zeros(1000, 768), torch.zeros(1000)     # classifier of the checkpoint: dropped
+    path = tmp_path / "vit_base_patch16_224.pth"
+    torch.save(sd, path)
+    monkeypatch.setenv("POSE_VIT_WEIGHTS", str(path))
+    cfg = pose.ModelConfig("transformer", image_size=(256, 256))
+    assert cfg.vit_pretrained is True
+    m = pose.TransformerPoseEstimation(cfg)
+    got = m.vit_backbone.state_dict()
+    w = got["patch_embed.proj.weight"]
+    assert tuple(w.shape) == (768, 4, 16, 16)
+    assert torch.equal(w[:, :3], sd["patch_embed.proj.weight"])
+    assert torch.allclose(w[:, 3:], sd["patch_embed.proj.weight"].mean(dim=1, keepdim=True))
+    pe = got["pos_embed"]
+    assert tuple(pe.shape) == (1, 257, 768) and torch.equal(pe[:, 0], sd["pos_embed"][:, 0])
+    ref = torch.nn.functional.interpolate(sd["pos_embed"][:, 1:].reshape(1, 14, 14, 768).permute(0, 3, 1, 2), size=(16, 16),
+                                          mode="bicubic", antialias=True).permute(0, 2, 3, 1).reshape(1, 256, 768)
+    assert torch.allclose(pe[:, 1:], ref)
+    assert torch.equal(got["blocks.5.attn.qkv.weight"], sd["blocks.5.attn.qkv.weight"])
+    monkeypatch.delenv("POSE_VIT_WEIGHTS")
+    with pytest.raises(NotImplementedError, match="POSE_VIT_WEIGHTS"):
+        pose.TransformerPoseEstimation(pose.ModelConfig("transformer", image_size=(256, 256)))
