@@ -116,6 +116,132 @@ __device__ __forceinline__ void attn_epilogue(uint32_t tmem_base) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// One token outside the tiles.  The backbone's sequences are 256 patches + 1 class token: 257 = 2 x 128 + 1 rows made a
+// third query tile and a fifth key chunk that were all padding but one row / column (forward 88 us at 257 tokens against
+// 62 us at 256).  With `AttnTail` the tensor-core tiles run on tokens 1 .. Nt - 1 (operand maps and output pointers are
+// shifted by one token on the host) and token 0 is handled on the CUDA cores:
+//   * as a KEY   inside every tile CTA: its score s_x = q_r . k_0 seeds the online softmax of row r (m = s_x, l = 1) and its
+//                value row is added to the accumulator in the epilogue (O_r += p_x v_0) -- a rank-1 update;
+//   * as a QUERY by ONE extra CTA per sample (blockIdx.z == 0, blockIdx.x == 0; all heads at once): a first version with one
+//                CTA per (sample, head) spent ~9 us per CTA in three dependent global round trips while holding a 66 KB
+//                slot -- 768 of them cost more (30 us) than the padding they replaced.  Here a warp owns a token row
+//                (all heads: 1536 contiguous bytes, three 16-byte chunks per lane), and the 64 CTAs start first and run
+//                beside the tiles.
+struct AttnTail {
+    const __nv_bfloat16 *q, *k, *v;    // ORIGINAL operand bases (token 0 of sample 0); null: no tail
+    __nv_bfloat16 *o;                  // original output base
+    float *lse;                        // original log-sum-exp base [B, heads, Nt] (may be null)
+    long ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso;
+    int Nt;                            // tokens in total (tiles cover Nt - 1)
+};
+constexpr int kTailBatch = 3;          // token rows in flight per warp (9 x 16 B per lane)
+
+// the extra query row (token 0) of every head of sample b against all Nt keys.  256 threads; E = heads * 64 = 256 * CPL / 8.
+// dynamic shared memory: s_q [E] | s_p [heads][Nt] | s_o [8][E]
+template <int CPL>      // 16-byte chunks of a token row per lane (E = 256 * CPL elements)
+__device__ void attn_tail_query_fwd(const AttnTail &x, unsigned char *smem, int b, int heads, float scale) {
+    constexpr int E = 256 * CPL;
+    float *s_q = (float *)smem, *s_p = s_q + E, *s_o = s_p + heads * x.Nt;
+    __shared__ float s_max[32], s_sum[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < E; i += kAttnThreads) s_q[i] = __bfloat162float(x.q[b * x.bsq + i]) * scale * kLog2e;
+    __syncthreads();
+    // ---- scores: s[h][t] = q_h . k_t,h (log2 units) ----
+    {
+        float q[CPL][8];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) q[j][e] = s_q[(lane + 32 * j) * 8 + e];
+        const __nv_bfloat16 *kb = x.k + b * x.bsk;
+        for (int t0 = warp * kTailBatch; t0 < x.Nt; t0 += 8 * kTailBatch) {
+            uint4 w[kTailBatch][CPL];
+#pragma unroll
+            for (int u = 0; u < kTailBatch; ++u)
+#pragma unroll
+                for (int j = 0; j < CPL; ++j)
+                    w[u][j] = t0 + u < x.Nt ? __ldg((const uint4 *)(kb + (long)(t0 + u) * x.ldk) + lane + 32 * j) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < kTailBatch; ++u)
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    const uint32_t ww[4] = {w[u][j].x, w[u][j].y, w[u][j].z, w[u][j].w};
+                    float acc = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        acc = fmaf(q[j][2 * e], __uint_as_float(ww[e] << 16), acc);
+                        acc = fmaf(q[j][2 * e + 1], __uint_as_float(ww[e] & 0xffff0000u), acc);
+                    }
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 4);       // the 8 lanes of a head (64 elements = 8 chunks)
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                    if ((lane & 7) == 0 && t0 + u < x.Nt) s_p[((lane >> 3) + 4 * j) * x.Nt + t0 + u] = acc;
+                }
+        }
+    }
+    __syncthreads();
+    // ---- softmax statistics per head (a warp per head), probabilities back into s_p ----
+    for (int h = warp; h < heads; h += 8) {
+        float *ph = s_p + h * x.Nt;
+        float mx = -INFINITY;
+        for (int t = lane; t < x.Nt; t += 32) mx = fmaxf(mx, ph[t]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int t = lane; t < x.Nt; t += 32) {
+            const float pv = ex2_approx(ph[t] - mx);
+            ph[t] = pv;
+            sum += pv;
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) { s_max[h] = mx; s_sum[h] = sum; }
+    }
+    __syncthreads();
+    // ---- o_h = p_h V_h: per-warp partial sums over its token rows ----
+    {
+        float acc[CPL][8];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+        const __nv_bfloat16 *vb = x.v + b * x.bsv;
+        for (int t0 = warp * kTailBatch; t0 < x.Nt; t0 += 8 * kTailBatch) {
+            uint4 w[kTailBatch][CPL];
+#pragma unroll
+            for (int u = 0; u < kTailBatch; ++u)
+#pragma unroll
+                for (int j = 0; j < CPL; ++j)
+                    w[u][j] = t0 + u < x.Nt ? __ldg((const uint4 *)(vb + (long)(t0 + u) * x.ldv) + lane + 32 * j) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < kTailBatch; ++u)
+                if (t0 + u < x.Nt)
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) {
+                        const float pv = s_p[((lane >> 3) + 4 * j) * x.Nt + t0 + u];
+                        const uint32_t ww[4] = {w[u][j].x, w[u][j].y, w[u][j].z, w[u][j].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            acc[j][2 * e] = fmaf(pv, __uint_as_float(ww[e] << 16), acc[j][2 * e]);
+                            acc[j][2 * e + 1] = fmaf(pv, __uint_as_float(ww[e] & 0xffff0000u), acc[j][2 * e + 1]);
+                        }
+                    }
+        }
+#pragma unroll
+        for (int j = 0; j < CPL; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s_o[warp * E + (lane + 32 * j) * 8 + e] = acc[j][e];
+    }
+    __syncthreads();
+    for (int c = tid; c < E; c += kAttnThreads) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += s_o[w * E + c];
+        x.o[b * x.bso + c] = __float2bfloat16_rn(tot / s_sum[c >> 6]);
+    }
+    if (tid < heads && x.lse != nullptr) x.lse[((long)b * heads + tid) * x.Nt] = s_max[tid] * 0.6931471805599453f + __logf(s_sum[tid]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Forward, one CTA per (sample, head): query tiles of 128 rows x key chunks of 64 streamed through double-buffered shared
 // memory, ONLINE softmax (running row maximum / sum, the O accumulator in TMEM rescaled when the maximum moves), so the
 // sequence length is unbounded (the 512 x 512 default of the reference: 1025 tokens) and the CTA needs only 128 TMEM
@@ -129,7 +255,13 @@ __global__ void __launch_bounds__(kAttnThreads, 3)      // 80 registers, 67 KB, 
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, __nv_bfloat16 *__restrict__ O, float *__restrict__ lse, int Nq, int Nk,
                    int Nkp, long ldo, long bso, float scale, uint32_t drop_thresh, float drop_scale,
-                   const DropSeed drop_seed) {
+                   const DropSeed drop_seed, const AttnTail tail, int lse_ld) {
+    const bool has_tail = tail.q != nullptr;
+    if (has_tail && blockIdx.z == 0) {                   // the z = 0 plane is scheduled first: one worker CTA per sample
+        extern __shared__ unsigned char smem_tail[];
+        if (blockIdx.x == 0) attn_tail_query_fwd<HD * 12 / 256>(tail, smem_tail, blockIdx.y, gridDim.x, scale);
+        return;
+    }
     const uint32_t dkey = drop_thresh ? drop_key0(drop_seed) : 0u;     // per-launch dropout key (+ bound step state)
     constexpr int KC = kFwdKC, KB = KC * 128;
     unsigned char *smem;
@@ -142,12 +274,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     const int h = blockIdx.x, b = blockIdx.y, heads = gridDim.x;
     // blockIdx.z: this CTA's range of query tiles (one tile per CTA: key / value chunks are re-streamed per tile anyway, and
     // the finer granularity cuts the last-wave loss of 768 three-tile CTAs over 296-444 resident slots)
-    const int q_begin = blockIdx.z * kTilesPerCta * 128, q_end = min(Nq, q_begin + kTilesPerCta * 128);
+    const int q_begin = ((int)blockIdx.z - (has_tail ? 1 : 0)) * kTilesPerCta * 128, q_end = min(Nq, q_begin + kTilesPerCta * 128);
     const int warp = threadIdx.x >> 5, quarter = warp & 3, grp = warp >> 2;
     const int r = quarter * 32 + (threadIdx.x & 31);              // this thread's query row (shared by its twin in the other group)
     __shared__ float red_m[2][128], red_s[2][128];
+    __shared__ float s_vx[64];                           // tail: value row of the extra key
     __nv_bfloat16 *og = O + b * bso + (long)h * HD;
     const float sl2 = scale * kLog2e;
+    if (has_tail && threadIdx.x < 64)
+        s_vx[threadIdx.x] = threadIdx.x < HD ? __bfloat162float(tail.v[b * tail.bsv + (long)h * HD + threadIdx.x]) : 0.f;
     const uint32_t tS = tmem, tO = tmem + 64;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int nch = (Nkp + KC - 1) / KC;
@@ -179,6 +314,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         const bool live = q0 + quarter * 32 < Nq;        // warps whose 32 rows are all padding skip the softmax
         const uint32_t drop_row = (uint32_t)(((b * heads + h) * Nq + q0 + r) * Nk);   // mask index of (row, key 0); < 2^32 (host check)
         float m = -INFINITY, l = 0.f;                    // running row maximum (raw scores) and this thread's share of the row sum
+        float sx = 0.f;
+        if (has_tail) {
+            // raw score of this thread's query row against the extra key: the Q tile is in shared memory (row r, 16-byte chunks
+            // XOR-swizzled by r & 7), the key row comes straight from global memory (the same 128 bytes for every thread)
+            const uint4 *kx = (const uint4 *)(tail.k + b * tail.bsk + (long)h * HD);
+#pragma unroll
+            for (int c8 = 0; c8 < HD / 8; ++c8) {
+                const uint4 qv = *(const uint4 *)(Qs + r * 128 + ((c8 ^ (r & 7)) << 4)), kv = __ldg(kx + c8);
+                const __nv_bfloat162 *qh = (const __nv_bfloat162 *)&qv, *kh = (const __nv_bfloat162 *)&kv;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 a = __bfloat1622float2(qh[j]), bq = __bfloat1622float2(kh[j]);
+                    sx = fmaf(a.x, bq.x, sx);
+                    sx = fmaf(a.y, bq.y, sx);
+                }
+            }
+            m = sx;                                       // the online softmax starts from this one key
+            l = grp == 0 ? 1.0f : 0.f;
+        }
         for (int c = 0; c < nch; ++c, ++t) {
             const int kc0 = c * KC, n = min(KC, Nkp - kc0);
             const bool last_c = c == nch - 1;
@@ -258,10 +412,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         if (live) {                                      // warp-uniform: tcgen05.ld is a warp-collective instruction
             const float sum = red_s[0][r] + red_s[1][r];
             const float inv = 1.0f / sum;
-            if (grp == 0 && lse != nullptr && q0 + r < Nq) lse[((long)b * heads + h) * Nq + q0 + r] = m * scale + __logf(sum);
+            if (grp == 0 && lse != nullptr && q0 + r < Nq) lse[((long)b * heads + h) * lse_ld + q0 + r] = m * scale + __logf(sum);
             uint32_t v[32];
             const int c = grp;                           // each group stores one 32-column half of the output row
             tmem_ld32(tO + lane_off + c * 32, v);
+            if (has_tail) {                              // + p_x v_0 (relative to the final row maximum, like the accumulator)
+                const float px = ex2_approx((sx - m) * sl2);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(px, s_vx[c * 32 + j], __uint_as_float(v[j])));
+            }
             if (q0 + r < Nq)
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) {
@@ -612,6 +771,18 @@ static int make_map_tokens(CUtensorMap *map, const void *ptr, int cols, int T, i
     return r == CUDA_SUCCESS ? POSE_OK : POSE_E_SHAPE;
 }
 
+// tail mode: self-attention over 128 m + 1 tokens of 12 heads x 64 (the tiles then carry no padding), no attention dropout
+// (the mask index of the tiles would have to skip the extra column), enough (sample, head) pairs that the per-sample worker
+// CTAs (~25 us) hide behind the tiles, and the worker's scratch fits the kernel's dynamic shared memory.
+// POSE_ATTN_TAIL=0 switches it off (A/B measurements), 2 forces it at any batch (tests)
+static bool attn_tail_ok(int B, int heads, int Nq, int Nk, int head_dim, uint32_t drop_thresh, int smem_bytes) {
+    const char *env = getenv("POSE_ATTN_TAIL");          // read per call: the tests force the mode at small batch (2)
+    const int mode = env ? atoi(env) : 1;
+    const long scratch = 4L * (heads * head_dim + (long)heads * Nq + 8L * heads * head_dim);
+    return mode != 0 && Nq == Nk && Nq > 128 && (Nq - 1) % 128 == 0 && head_dim == 64 && heads == 12 && drop_thresh == 0 &&
+           (mode == 2 || (long)B * heads >= 2 * kNumSMs) && scratch <= smem_bytes;
+}
+
 template <class Kern>
 static int set_smem(Kern kern, int bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -634,11 +805,25 @@ POSE_API int pose_attention_bf16(const void *Q, const void *K, const void *V, vo
     if (drop_p > 0.f && (double)B * heads * Nq * Nk >= 4294967296.0) return POSE_E_UNSUPPORTED;   // 32-bit mask counter
     if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || bsq % 8 || bsk % 8 || bsv % 8 || bso % 8) return POSE_E_ALIGN;
     if ((uintptr_t)Q % 16 || (uintptr_t)K % 16 || (uintptr_t)V % 16 || (uintptr_t)O % 16) return POSE_E_ALIGN;
-    const int Nkp = (Nk + 15) / 16 * 16;
-    const dim3 grid(heads, B, (Nq + kTilesPerCta * 128 - 1) / (kTilesPerCta * 128));
     cudaStream_t s = (cudaStream_t)stream;
     const int cols = heads * head_dim;
     if (ldq < cols || ldk < cols || ldv < cols || ldo < cols) return POSE_E_SHAPE;
+    // one token outside the tiles (see AttnTail)
+    AttnTail tail = {};
+    const int lse_ld = Nq;
+    if (attn_tail_ok(B, heads, Nq, Nk, head_dim, dth, kFwdSmem)) {
+        tail = {(const __nv_bfloat16 *)Q, (const __nv_bfloat16 *)K, (const __nv_bfloat16 *)V, (__nv_bfloat16 *)O, lse,
+                ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, Nq};
+        Q = (const __nv_bfloat16 *)Q + ldq;
+        K = (const __nv_bfloat16 *)K + ldk;
+        V = (const __nv_bfloat16 *)V + ldv;
+        O = (__nv_bfloat16 *)O + ldo;
+        if (lse) lse += 1;
+        Nq -= 1;
+        Nk -= 1;
+    }
+    const int Nkp = (Nk + 15) / 16 * 16;
+    const dim3 grid(heads, B, (Nq + kTilesPerCta * 128 - 1) / (kTilesPerCta * 128) + (tail.q ? 1 : 0));
     CUtensorMap mq, mk, mv;
     int e;
     if ((e = make_map_tokens(&mq, Q, cols, Nq, B, ldq, bsq))) return e;
@@ -647,7 +832,7 @@ POSE_API int pose_attention_bf16(const void *Q, const void *K, const void *V, vo
 #define FWD(HD_)                                                                                                       \
     if ((e = set_smem(attn_fwd_tc_kernel<HD_>, kFwdSmem))) return e;                                                    \
     attn_fwd_tc_kernel<HD_><<<grid, kAttnThreads, kFwdSmem, s>>>(mq, mk, mv, (__nv_bfloat16 *)O, lse, Nq, Nk, Nkp, ldo, bso, \
-                                                                scale, dth, dsc, make_drop_seed(drop_seed))
+                                                                scale, dth, dsc, make_drop_seed(drop_seed), tail, lse_ld)
     if (head_dim == 64) { FWD(64); } else { FWD(48); }
 #undef FWD
     return launch_status();

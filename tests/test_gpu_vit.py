@@ -102,6 +102,15 @@ def test_attention_forward_backward(pose, hd, heads, Nq, Nk):
     assert torch.allclose(dkv.float(), kvr.grad, **tol), (dkv.float() - kvr.grad).abs().max().item()
 
 
+def test_attention_class_token_outside_the_tiles(pose, monkeypatch):
+    """257 = 2 x 128 + 1 tokens: the tensor-core tiles run on tokens 1..256 and the class token is handled on the CUDA cores
+    (AttnTail in csrc/attention_tc.cu); the mode needs a large batch by default, POSE_ATTN_TAIL=2 forces it."""
+    monkeypatch.setenv("POSE_ATTN_TAIL", "2")
+    test_attention_forward_backward(pose, 64, 12, 257, 257)
+    monkeypatch.setenv("POSE_ATTN_TAIL", "0")
+    test_attention_forward_backward(pose, 64, 12, 257, 257)
+
+
 @pytest.mark.parametrize("hd,heads,Nq,Nk", [(48, 16, 273, 273), (64, 12, 257, 257), (48, 16, 16, 256), (64, 3, 1025, 1025)])
 def test_attention_weight_dropout_forward_backward(pose, hd, heads, Nq, Nk):
     """nn.MultiheadAttention(dropout=p): the mask is a counter-based hash of (seed, element); pose_dropout_bf16 over a
