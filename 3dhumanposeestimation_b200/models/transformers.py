@@ -222,6 +222,13 @@ class TransformerPoseEstimation(nn.Module):  # transformers.py:140-373
             sd = adapt_timm_vit_state_dict(_pretrained_vit_state_dict(c.vit_model_name), c.image_in_channels,
                                            (c.image_size[0] // p, c.image_size[1] // p))
             self.vit_backbone.load_state_dict(sd)
+        if getattr(c, "vit_freeze_backbone", False):
+            # transformers.py:226-236: everything in the backbone but the patch embedding that was adapted to a different
+            # channel count (a pre-trained 3-channel embedding widened to RGB-D stays trainable)
+            adapted = c.image_in_channels != 3
+            for pname, prm in self.vit_backbone.named_parameters():
+                if not (pname.startswith("patch_embed.proj") and adapted):
+                    prm.requires_grad = False
         c.transformer_embed_dim = self.vit_backbone.embed_dim
         E = c.transformer_embed_dim
         self.heatmap_generator = GaussianHeatmapGenerator(c.num_joints, c.heatmap_size, c.heatmap_sigma)
@@ -563,11 +570,12 @@ class VitPlan:
         was drop(act(u))) or None."""
         w16 = self.flat.w16(weight, rows)
         N, K = w16.shape
-        gw = self.flat.g32(weight, rows).view(N, K)
-        e = self._epi(gw, K, accumulate=1)
-        self.call("pose_gemm_bf16_tr", dy.data_ptr(), ldy, 1, x.data_ptr(), K, 1, N, K, M, self._splits(N, K, M),
-                  C.byref(e))
-        if bias is not None:
+        if weight.requires_grad:                 # frozen layers (vit_freeze_backbone) only pass the data gradient on
+            gw = self.flat.g32(weight, rows).view(N, K)
+            e = self._epi(gw, K, accumulate=1)
+            self.call("pose_gemm_bf16_tr", dy.data_ptr(), ldy, 1, x.data_ptr(), K, 1, N, K, M, self._splits(N, K, M),
+                      C.byref(e))
+        if bias is not None and bias.requires_grad:
             self.call("pose_colsum_bf16", dy.data_ptr(), M, N, ldy, self.flat.g32(bias, rows).data_ptr())
         if dx_name is None:
             return None
@@ -581,8 +589,9 @@ class VitPlan:
             rows, in_group = M, M
         self.call("pose_layernorm_bwd_bf16", x.data_ptr(), dy.data_ptr(), self.flat.f32(ln.weight).data_ptr(),
                   float(ln.eps), M, rows, in_group, in_off, rows, 0, self.E,
-                  dres.data_ptr() if dres is not None else None, dx.data_ptr(), self.flat.g32(ln.weight).data_ptr(),
-                  self.flat.g32(ln.bias).data_ptr())
+                  dres.data_ptr() if dres is not None else None, dx.data_ptr(),
+                  self.flat.g32(ln.weight).data_ptr() if ln.weight.requires_grad else None,
+                  self.flat.g32(ln.bias).data_ptr() if ln.bias.requires_grad else None)
         return dx
 
     def attention_bwd(self, name, q, k, v, o, do, dq, dk, dv, Nq, Nk, heads, ldq, ldk, ldv, lddq, lddk, lddv, drop=None):
@@ -736,8 +745,10 @@ class VitPlan:
                                         bb.num_heads)
             if i % 3 == 0 or i < 3:      # groups of three; the last blocks one by one: a short exposed all-reduce tail
                 done(blk.norm1.weight)
-        self.call("pose_batch_rowsum_bf16", dx.data_ptr(), B, Ti + 1, 0, Ti + 1, E, flat.g32(bb.pos_embed).data_ptr())
-        self.call("pose_batch_rowsum_bf16", dx.data_ptr(), B, Ti + 1, 0, 1, E, flat.g32(bb.cls_token).data_ptr())
+        if bb.pos_embed.requires_grad:
+            self.call("pose_batch_rowsum_bf16", dx.data_ptr(), B, Ti + 1, 0, Ti + 1, E, flat.g32(bb.pos_embed).data_ptr())
+        if bb.cls_token.requires_grad:
+            self.call("pose_batch_rowsum_bf16", dx.data_ptr(), B, Ti + 1, 0, 1, E, flat.g32(bb.cls_token).data_ptr())
         dtok = self.buf("d.tok", B * Ti, E)
         self.call("pose_token_slice_bf16", dx.data_ptr(), B, Ti + 1, 1, Ti, E, dtok.data_ptr())
         self.linear_bwd(dtok, E, B * Ti, b["pimg"], bb.patch_embed.proj.weight, bb.patch_embed.proj.bias)

@@ -27,6 +27,7 @@ class AdamW(torch.optim.Optimizer):
                                       decoupled_weight_decay=True))
         self.grad_scale = grad_scale
         self._flat = None
+        self._ranges = []
         self._step = 0
         self.exp_avg = self.exp_avg_sq = None
         self.grad16 = None     # set by Trainer (bf16 gradient exchange): the step reads the all-reduced bf16 gradient
@@ -35,9 +36,19 @@ class AdamW(torch.optim.Optimizer):
     def _resolve(self):
         params = self.param_groups[0]["params"]
         if self._flat is None or not self._flat.intact():
-            if any(not p.requires_grad for p in params):
-                raise NotImplementedError("frozen parameters (vit_freeze_backbone) are not supported by the fused AdamW")
             self._flat = FlatParams.of(params)
+            # frozen parameters (vit_freeze_backbone, transformers.py:226-236) stay in the flat buffer but are never
+            # touched: torch.optim.AdamW skips parameters without a gradient (no update, no weight decay).  The step runs
+            # over the maximal contiguous trainable ranges (one launch when nothing is frozen).
+            self._ranges = []
+            ends = list(self._flat.offsets[1:]) + [self._flat.numel]          # padded extents (offsets are aligned)
+            for p, off, end in zip(self._flat.params, self._flat.offsets, ends):
+                if not p.requires_grad:
+                    continue
+                if self._ranges and self._ranges[-1][1] == off:
+                    self._ranges[-1][1] = end
+                else:
+                    self._ranges.append([off, end])
             if self.exp_avg is None or self.exp_avg.numel() != self._flat.numel:
                 self.exp_avg = torch.zeros_like(self._flat.master)
                 self.exp_avg_sq = torch.zeros_like(self._flat.master)
@@ -51,17 +62,20 @@ class AdamW(torch.optim.Optimizer):
         self._step += 1
         if not flat.grads_attached():
             raise RuntimeError("gradients are not views of the flat buffer: call backward() on a model output first")
-        hyper = (flat.numel, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-                 float(g["weight_decay"]), 0 if self.device_step else self._step, float(self.grad_scale), 1,
-                 _lib.stream_ptr())
-        if self.grad16 is not None:
-            code = _lib.lib().pose_adamw_step_g16(flat.master.data_ptr(), flat.grad.data_ptr(), self.grad16.data_ptr(),
-                                                  self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), flat.shadow.data_ptr(),
-                                                  *hyper)
-        else:
-            code = _lib.lib().pose_adamw_step(flat.master.data_ptr(), flat.grad.data_ptr(), self.exp_avg.data_ptr(),
-                                              self.exp_avg_sq.data_ptr(), flat.shadow.data_ptr(), *hyper)
-        _lib.check(code, "pose_adamw_step")
+        for lo, hi in self._ranges:
+            hyper = (hi - lo, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                     float(g["weight_decay"]), 0 if self.device_step else self._step, float(self.grad_scale), 1,
+                     _lib.stream_ptr())
+            if self.grad16 is not None:
+                code = _lib.lib().pose_adamw_step_g16(flat.master.data_ptr() + 4 * lo, flat.grad.data_ptr() + 4 * lo,
+                                                      self.grad16.data_ptr() + 2 * lo, self.exp_avg.data_ptr() + 4 * lo,
+                                                      self.exp_avg_sq.data_ptr() + 4 * lo, flat.shadow.data_ptr() + 2 * lo,
+                                                      *hyper)
+            else:
+                code = _lib.lib().pose_adamw_step(flat.master.data_ptr() + 4 * lo, flat.grad.data_ptr() + 4 * lo,
+                                                  self.exp_avg.data_ptr() + 4 * lo, self.exp_avg_sq.data_ptr() + 4 * lo,
+                                                  flat.shadow.data_ptr() + 2 * lo, *hyper)
+            _lib.check(code, "pose_adamw_step")
         flat.generation += 1          # the kernel wrote the parameters through raw pointers: _version did not move
         flat.mark_shadow_current()    # ... and refreshed the bf16 shadow itself
         return loss
@@ -75,6 +89,8 @@ class AdamW(torch.optim.Optimizer):
         self.state.clear()
         if self._step > 0:
             for p, off in zip(flat.params, flat.offsets):
+                if not p.requires_grad:          # torch.optim.AdamW keeps no state for parameters without gradients
+                    continue
                 n = p.numel()
                 self.state[p] = {"step": torch.tensor(float(self._step), dtype=torch.float32),
                                  "exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),

@@ -2,6 +2,7 @@
 eval-mode forward against the golden frozen from the live reference (0.5 mm MPJPE, BASELINE.json:north_star), and one
 training step (loss, every parameter's gradient, fused AdamW) against fp32 autograd over the oracle restatement, which
 gen_golden.py pins to the live reference's gradients."""
+import importlib
 import json
 import math
 import os
@@ -470,3 +471,39 @@ def test_patchify_and_fused_heatmap_patch_operand(pose, oracle):
         refp = torch.nn.functional.unfold(ref, hp, stride=hp).transpose(1, 2).reshape(fused.shape)
         assert (fused.float() - refp).abs().max().item() <= 2 ** -8       # bf16 rounding of values in [0, 1]
         assert fused.float().sum().item() > 0
+
+
+def test_vit_freeze_backbone_trains_everything_else(pose):
+    """vit_freeze_backbone (transformers.py:226-236): the backbone keeps its weights -- except the patch embedding adapted to
+    RGB-D -- while every other parameter receives the same gradient and update as in the unfrozen model."""
+    train = importlib.import_module("3dhumanposeestimation_b200.train")
+    kw = dict(image_size=(256, 256), vit_pretrained=False, transformer_dropout_rate=0.0, transformer_attention_dropout_rate=0.0,
+              regression_dropout=0.0)
+    torch.manual_seed(11)
+    mf = pose.TransformerPoseEstimation(pose.ModelConfig("transformer", vit_freeze_backbone=True, **kw)).to(DEV).train()
+    mu = pose.TransformerPoseEstimation(pose.ModelConfig("transformer", **kw)).to(DEV).train()
+    mu.load_state_dict(mf.state_dict())
+    frozen = {n for n, p in mf.named_parameters() if not p.requires_grad}
+    assert frozen and all(n.startswith("vit_backbone.") and not n.startswith("vit_backbone.patch_embed.proj") for n in frozen)
+    assert mf.vit_backbone.patch_embed.proj.weight.requires_grad
+    B = 2
+    g = torch.Generator().manual_seed(5)
+    img, dep = torch.rand(B, 3, 256, 256, generator=g).to(DEV), torch.rand(B, 1, 256, 256, generator=g).to(DEV)
+    kp = (torch.rand(B, 17, 2, generator=g) * 0.9 + 0.05).to(DEV)
+    gt = (torch.randn(B, 17, 3, generator=g) * 300).to(DEV)
+    before = {n: p.detach().clone() for n, p in mf.named_parameters()}
+    tf = train.Trainer(mf, pose.ComprehensivePoseLoss(), lr=1e-3, weight_decay=0.01, graph=False)
+    tu = train.Trainer(mu, pose.ComprehensivePoseLoss(), lr=1e-3, weight_decay=0.01, graph=False)
+    lf, lu = tf.step(img, dep, kp, gt)[4].item(), tu.step(img, dep, kp, gt)[4].item()
+    assert abs(lf - lu) <= 1e-5 * abs(lu)
+    pu = dict(mu.named_parameters())
+    for n, p in mf.named_parameters():
+        if n in frozen:
+            assert torch.equal(p, before[n]), n                   # no update, no weight decay
+        else:
+            assert not torch.equal(p, before[n]), n
+            # same update as the unfrozen model (split-K atomics reorder fp32 sums: AdamW's first step is ~lr * sign(g))
+            assert (p - pu[n]).abs().max().item() <= 2.1e-3, n
+            assert ((p - pu[n]).abs() > 1e-4).float().mean().item() < 0.02, n
+    sd = tf.opt.state_dict()
+    assert len(sd["state"]) == sum(1 for p in mf.parameters() if p.requires_grad)
