@@ -155,3 +155,17 @@ def test_vit_pretrained_weights_from_a_local_timm_state_dict(pose, tmp_path, mon
     monkeypatch.delenv("POSE_VIT_WEIGHTS")
     with pytest.raises(NotImplementedError, match="POSE_VIT_WEIGHTS"):
         pose.TransformerPoseEstimation(pose.ModelConfig("transformer", image_size=(256, 256)))
+
+
+def test_weight_gradient_split_factors(pose):
+    """utils.wgrad_splits: wave-aware split-K for 128 x 128 tiles, and two splits (-> 256-column CTA-pair tiles inside the
+    library) where that tiling would be a single wave over a long contraction (the ViT's fc1 / fc2 weight gradients)."""
+    u = importlib.import_module("3dhumanposeestimation_b200.utils")
+    rows = 64 * 257
+    assert u.wgrad_splits(768, 3072, rows) == 2 and u.wgrad_splits(3072, 768, rows) == 2      # 144 tiles: one wave -> 2
+    assert u.wgrad_splits(2304, 768, rows) == 4 and u.wgrad_splits(768, 768, rows) == 4        # already split: unchanged
+    assert u.wgrad_splits(768, 3072, 64 * 16) == u.split_k(144, 16)                            # short contraction: unchanged
+    assert u.wgrad_splits(51, 512, rows) == u.split_k(4, 257)                                   # narrow output: unchanged
+    for tiles, kb in ((1, 4), (36, 2048), (300, 37), (148, 257)):
+        s = u.split_k(tiles, kb)
+        assert 1 <= s <= max(1, kb // 4)
