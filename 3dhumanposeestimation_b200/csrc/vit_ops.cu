@@ -5,6 +5,7 @@
 //
 // Attention itself runs on the tcgen05 tensor cores: attention_tc.cu.
 #include "common.cuh"
+#include "rowpipe.cuh"
 
 namespace pose {
 
@@ -22,6 +23,13 @@ __device__ __forceinline__ uint4 pack8v(const float (&f)[8]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
     return *(uint4 *)h;
+}
+
+// 8 bf16 -> four fp32 pairs in two instructions per pair (shift, mask)
+__device__ __forceinline__ void unpack8p(const uint4 &p, float2 (&f)[4]) {
+    const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f[q] = make_float2(__uint_as_float(w[q] << 16), __uint_as_float(w[q] & 0xffff0000u));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -158,7 +166,7 @@ patchify8_kernel(const float *__restrict__ src0, int C0, const float *__restrict
 // the forward: X / dX / dRes use the input addressing, dY the output addressing.
 // ---------------------------------------------------------------------------------------------------------
 template <int D8PL>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *__restrict__ dY,
                      const float *__restrict__ gamma, float eps, long M, int rows, long in_group, long in_off,
                      long out_group, long out_off, int D, const __nv_bfloat16 *__restrict__ dRes,
@@ -175,64 +183,101 @@ layernorm_bwd_kernel(const __nv_bfloat16 *__restrict__ X, const __nv_bfloat16 *_
         *(float4 *)(ga + c) = make_float4(0.f, 0.f, 0.f, 0.f); *(float4 *)(ga + c + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         *(float4 *)(ba + c) = make_float4(0.f, 0.f, 0.f, 0.f); *(float4 *)(ba + c + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (long r = (long)blockIdx.x * 8 + warp; r < M; r += (long)gridDim.x * 8) {
-        const long g = r / rows, i = r - g * rows;
+    // Everything elementwise runs on packed fp32 pairs (FADD2 / FMUL2 / FFMA2: two lanes per issue slot): the scalar version
+    // executed 31 instructions per element and was issue / latency bound at 2.3 TB/s on L2-resident tensors
+    // (profiles/r02h_ln_bwd_full_raw.csv).
+    const float inv_d = 1.0f / (float)D;
+    // A warp walks its rows strictly one after the other and every row is a chain of dependent latencies (row loads, three
+    // warp reductions, the residual load): 33 us for 76 MB with 24 warps per SM.  The NEXT row of the warp is therefore
+    // copied into a lane-private shared-memory slot with cp.async while the current one is processed ([warp][tensor][chunk]
+    // [lane] uint4 behind the accumulators; nobody else reads a lane's slots, so cp.async.wait_group is the only sync).
+    const uint32_t slot = (uint32_t)__cvta_generic_to_shared(s_acc + (size_t)8 * 2 * D) + (uint32_t)(((warp * 3 * D8PL) * 32 + lane) * 16);
+    const long rstep = (long)gridDim.x * 8;
+    auto issue = [&](long rr_) {
+        const long g = rr_ / rows, i = rr_ - g * rows;
         const long rin = g * in_group + in_off + i, rout = g * out_group + out_off + i;
-        const __nv_bfloat16 *x = X + rin * D;
-        const __nv_bfloat16 *dy = dY + rout * D;
-        float v[D8PL][8], d[D8PL][8];
-        float s = 0.f;
 #pragma unroll
         for (int q = 0; q < D8PL; ++q) {
-            unpack8v(__ldg((const uint4 *)x + q * 32 + lane), v[q]);
-            unpack8v(__ldg((const uint4 *)dy + q * 32 + lane), d[q]);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s += v[q][k];
+            cp16(slot + (uint32_t)((0 * D8PL + q) * 32 * 16), (const uint4 *)(X + rin * D) + q * 32 + lane);
+            cp16(slot + (uint32_t)((1 * D8PL + q) * 32 * 16), (const uint4 *)(dY + rout * D) + q * 32 + lane);
+            if (dRes != nullptr) cp16(slot + (uint32_t)((2 * D8PL + q) * 32 * 16), (const uint4 *)(dRes + rin * D) + q * 32 + lane);
         }
-        const float mean = warp_sum(s) / (float)D;
-        float ss = 0.f;
+        cp_async_commit();
+    };
+    long r = (long)blockIdx.x * 8 + warp;
+    if (r < M) issue(r);
+    for (; r < M; r += rstep) {
+        const long g = r / rows, i = r - g * rows;
+        const long rin = g * in_group + in_off + i;
+        cp_async_wait<0>();
+        float2 v[D8PL][4], d[D8PL][4];
+        uint4 rres[D8PL];
+        float2 sa = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < D8PL; ++q) {
+            unpack8p(lds16(slot + (uint32_t)((0 * D8PL + q) * 32 * 16)), v[q]);
+            unpack8p(lds16(slot + (uint32_t)((1 * D8PL + q) * 32 * 16)), d[q]);
+            rres[q] = dRes != nullptr ? lds16(slot + (uint32_t)((2 * D8PL + q) * 32 * 16)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sa = __fadd2_rn(sa, v[q][k]);
+        }
+        if (r + rstep < M) issue(r + rstep);        // the slots were just read: the next row lands while this one is processed
+        const float mean = warp_sum(sa.x + sa.y) * inv_d;
+        const float2 nm = make_float2(-mean, -mean);
+        float2 sq = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < D8PL; ++q)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                v[q][k] -= mean;
-                ss += v[q][k] * v[q][k];
+            for (int k = 0; k < 4; ++k) {
+                v[q][k] = __fadd2_rn(v[q][k], nm);
+                sq = __ffma2_rn(v[q][k], v[q][k], sq);
             }
-        const float rstd = rsqrtf(warp_sum(ss) / (float)D + eps);
-        float s1 = 0.f, s2 = 0.f;
+        const float rstd = rsqrtf(warp_sum(sq.x + sq.y) * inv_d + eps);
+        const float2 rs2 = make_float2(rstd, rstd);
+        float2 t1 = make_float2(0.f, 0.f), t2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < D8PL; ++q) {
             const int c = (q * 32 + lane) * 8;
-            float ga8[8], ba8[8], gm[8];
-            *(float4 *)ga8 = *(const float4 *)(ga + c); *(float4 *)(ga8 + 4) = *(const float4 *)(ga + c + 4);
-            *(float4 *)ba8 = *(const float4 *)(ba + c); *(float4 *)(ba8 + 4) = *(const float4 *)(ba + c + 4);
-            *(float4 *)gm = __ldg((const float4 *)(gamma + c)); *(float4 *)(gm + 4) = __ldg((const float4 *)(gamma + c) + 1);
+            float2 ga8[4], ba8[4], gm[4];
+            *(float4 *)&ga8[0] = *(const float4 *)(ga + c); *(float4 *)&ga8[2] = *(const float4 *)(ga + c + 4);
+            *(float4 *)&ba8[0] = *(const float4 *)(ba + c); *(float4 *)&ba8[2] = *(const float4 *)(ba + c + 4);
+            *(float4 *)&gm[0] = __ldg((const float4 *)(gamma + c)); *(float4 *)&gm[2] = __ldg((const float4 *)(gamma + c) + 1);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                v[q][k] *= rstd;                                // xhat
-                ga8[k] += d[q][k] * v[q][k];
-                ba8[k] += d[q][k];
-                d[q][k] *= gm[k];                               // g * dY
-                s1 += d[q][k];
-                s2 += d[q][k] * v[q][k];
+            for (int k = 0; k < 4; ++k) {
+                v[q][k] = __fmul2_rn(v[q][k], rs2);                     // xhat
+                ga8[k] = __ffma2_rn(d[q][k], v[q][k], ga8[k]);
+                ba8[k] = __fadd2_rn(ba8[k], d[q][k]);
+                d[q][k] = __fmul2_rn(d[q][k], gm[k]);                   // g * dY
+                t1 = __fadd2_rn(t1, d[q][k]);
+                t2 = __ffma2_rn(d[q][k], v[q][k], t2);
             }
-            *(float4 *)(ga + c) = *(const float4 *)ga8; *(float4 *)(ga + c + 4) = *(const float4 *)(ga8 + 4);
-            *(float4 *)(ba + c) = *(const float4 *)ba8; *(float4 *)(ba + c + 4) = *(const float4 *)(ba8 + 4);
+            *(float4 *)(ga + c) = *(const float4 *)&ga8[0]; *(float4 *)(ga + c + 4) = *(const float4 *)&ga8[2];
+            *(float4 *)(ba + c) = *(const float4 *)&ba8[0]; *(float4 *)(ba + c + 4) = *(const float4 *)&ba8[2];
         }
-        s1 = warp_sum(s1) / (float)D;
-        s2 = warp_sum(s2) / (float)D;
+        // the two row sums travel through one butterfly
+        float s1 = t1.x + t1.y, s2 = t2.x + t2.y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        const float2 ns1 = make_float2(-s1 * inv_d, -s1 * inv_d), ns2 = make_float2(-s2 * inv_d, -s2 * inv_d);
 #pragma unroll
         for (int q = 0; q < D8PL; ++q) {
-            float o[8];
+            float2 o[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = rstd * (d[q][k] - s1 - v[q][k] * s2);
+            for (int k = 0; k < 4; ++k)
+                o[k] = __fmul2_rn(rs2, __fadd2_rn(__ffma2_rn(v[q][k], ns2, d[q][k]), ns1));   // rstd (g dY - s1 - xhat s2)
             if (dRes != nullptr) {
-                float rr[8];
-                unpack8v(__ldg((const uint4 *)(dRes + rin * D) + q * 32 + lane), rr);
+                float2 rv[4];
+                unpack8p(rres[q], rv);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) o[k] += rr[k];
+                for (int k = 0; k < 4; ++k) o[k] = __fadd2_rn(o[k], rv[k]);
             }
-            ((uint4 *)(dX + rin * D))[q * 32 + lane] = pack8v(o);
+            __nv_bfloat162 h[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(o[k].x, o[k].y);
+            ((uint4 *)(dX + rin * D))[q * 32 + lane] = *(uint4 *)h;
         }
     }
     // fold the 8 warps' partials, then one atomic per column per CTA
@@ -460,7 +505,7 @@ POSE_API int pose_layernorm_bwd_bf16(const void *X, const void *dY, const float 
     if ((uintptr_t)X % 16 || (uintptr_t)dY % 16 || (uintptr_t)dX % 16 || (uintptr_t)gamma % 16 || (dRes && (uintptr_t)dRes % 16))
         return POSE_E_ALIGN;
     long blocks = (M + 7) / 8;
-    const int smem = 8 * 2 * D * (int)sizeof(float);
+    const int smem = 8 * 2 * D * (int)sizeof(float) + 8 * 3 * (D / 256) * 32 * 16;     // accumulators + the next-row slots
     cudaStream_t s = (cudaStream_t)stream;
 #define LNB_LAUNCH(N_)                                                                                                  \
     static bool cfg##N_ = false;                                                                                        \
