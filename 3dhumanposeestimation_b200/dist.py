@@ -71,3 +71,34 @@ def allreduce_range(flat_grad: torch.Tensor, lo: int, hi: int, bucket_elems: int
     """Sum-all-reduce flat_grad[lo:hi) in buckets (the data-parallel gradient exchange)."""
     for a, b in bucket_ranges(lo, hi, bucket_elems):
         dist.all_reduce(flat_grad[a:b], op=dist.ReduceOp.SUM, group=group)
+
+
+class SectionCoalescer:
+    """Groups the gradient sections a backward pass announces (each [lo, hi) of the flat buffer, arriving from the tail of
+    the buffer towards its head) into exchanges of at least `min_elems` elements: `add` returns the ranges to all-reduce
+    now -- nothing while less than `min_elems` are pending, everything pending once the head (lo == 0) is reached.
+    A section that is not adjacent to the pending range flushes it first, so no element is ever exchanged twice or left out."""
+
+    def __init__(self, min_elems: int):
+        self.min_elems = int(min_elems)
+        self.lo = self.hi = None
+
+    def add(self, lo: int, hi: int):
+        out = []
+        if hi <= lo:
+            return out
+        if self.hi is not None and self.lo != hi:
+            out.append((self.lo, self.hi))
+            self.lo = self.hi = None
+        if self.hi is None:
+            self.hi = hi
+        self.lo = lo
+        if lo == 0 or self.hi - lo >= self.min_elems:
+            out.append((self.lo, self.hi))
+            self.lo = self.hi = None
+        return out
+
+    def flush(self):
+        out = [] if self.hi is None else [(self.lo, self.hi)]
+        self.lo = self.hi = None
+        return out

@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib  # noqa: F401
-from .dist import allreduce_range
+from .dist import SectionCoalescer, allreduce_range
 from .loss import pose_loss_fwd_bwd
 from .optim import AdamW
 
@@ -41,7 +41,7 @@ class Trainer:
         # backward 25.68 (1 GPU: 24.1): short collectives spread over the whole backward cost more in interference
         # with the persistent GEMM grids than their overlap hides
         self.comm_min_bytes = int(os.environ.get("POSE_DP_MIN_BYTES", str(128 << 20)))
-        self._pend_hi = self._pend_lo = None
+        self._coalesce = SectionCoalescer(self.comm_min_bytes // 4)
         self.out5 = None
         # gradient exchange format: "bf16" halves the bytes on NVLink (each finished section of the flat fp32 gradient is
         # cast to a bf16 staging buffer on the communication stream, all-reduced there, and read by the fused AdamW
@@ -68,18 +68,9 @@ class Trainer:
         ones sharing the SMs with the backward kernels for the whole pass."""
         if self.world == 1 or hi <= lo:
             return
-        if self._pend_hi is not None and self._pend_lo != hi:      # not adjacent to what is pending: send that first
-            plo, phi = self._pend_lo, self._pend_hi
-            self._pend_hi = self._pend_lo = None
-            self._exchange(flat, plo, phi)
-        if self._pend_hi is None:
-            self._pend_hi = hi
-        self._pend_lo = lo
-        if lo > 0 and (self._pend_hi - lo) * 4 < self.comm_min_bytes:
-            return
-        lo, hi = self._pend_lo, self._pend_hi
-        self._pend_hi = self._pend_lo = None
-        self._exchange(flat, lo, hi)
+        self._flat_for_flush = flat
+        for a, b in self._coalesce.add(lo, hi):
+            self._exchange(flat, a, b)
 
     def _exchange(self, flat, lo, hi):
         ev = torch.cuda.Event()
@@ -98,6 +89,8 @@ class Trainer:
 
     def _wait_comm(self):
         if self.world > 1:
+            for a, b in self._coalesce.flush():          # (a backward that did not announce the head of the buffer)
+                self._exchange(self._flat_for_flush, a, b)
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     # ---- one batch -----------------------------------------------------------------------------------

@@ -63,3 +63,29 @@ def test_single_process_defaults():
     assert d.max_over_ranks(3.5) == 3.5 and d.job_throughput(100, 50.0) == 2000.0
     assert d.bucket_ranges(10, 100, 40) == [(60, 100), (20, 60), (10, 20)]      # model tail first
     assert d.bucket_ranges(5, 5, 8) == []
+
+
+def test_gradient_sections_are_coalesced_without_gaps_or_repeats():
+    """dist.SectionCoalescer (the Trainer's exchange schedule): announced sections arrive tail first; exchanges cover every
+    element exactly once, none is shorter than the threshold except the one that reaches the head."""
+    d = importlib.import_module("3dhumanposeestimation_b200.dist")
+    n = 1000
+    cuts = [1000, 950, 700, 690, 400, 390, 120, 0]                 # backward announces [950,1000), [700,950), ...
+    for min_elems in (0, 100, 300, 10_000):
+        c = d.SectionCoalescer(min_elems)
+        sent = []
+        for hi, lo in zip(cuts[:-1], cuts[1:]):
+            sent += c.add(lo, hi)
+        assert c.flush() == []                                      # the head was announced: nothing is left pending
+        cover = torch.zeros(n)
+        for a, b in sent:
+            cover[a:b] += 1
+        assert bool((cover == 1).all()), (min_elems, sent)
+        assert all(b - a >= min_elems or a == 0 for a, b in sent), (min_elems, sent)
+        if min_elems == 0:
+            assert sent == list(zip(cuts[1:], cuts[:-1]))
+        if min_elems == 10_000:
+            assert sent == [(0, 1000)]
+    c = d.SectionCoalescer(500)
+    assert c.add(900, 1000) == [] and c.add(100, 200) == [(900, 1000)]     # not adjacent: the pending range goes first
+    assert c.flush() == [(100, 200)] and c.add(5, 5) == []
