@@ -1169,7 +1169,12 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, int M, int 
 // and for the TMA-store epilogue of the GELU / derivative GEMMs (two chunks per warp) when there are enough tiles to go round.
 static bool wide_tile_ok(const Epilogue &ep, int N, int K, int m_tiles, int k_splits) {
     static const bool off = getenv("POSE_GEMM_NO_BN256") != nullptr;      // A/B switch for measurements
-    if (off || N % 256 || K < 512) return false;          // short contractions are output-write bound: nothing to gain
+    // Shortest contraction that takes the wide tile.  Round 1 set 512 ("short contractions are output-write bound") with the
+    // transposing epilogue; with the lean TMA-store epilogue the K = 256 layers are bound by the L2 -> shared-memory fills
+    // instead, and a 128 x 256 tile needs 25 % fewer of them per output: 131072 x 768 x 256 with BatchNorm statistics
+    // 136 -> 93 us, CNN step 22.39 -> 22.16 ms (128: no further change).  POSE_GEMM_WIDE_MIN_K overrides (A/B).
+    static const int min_k = getenv("POSE_GEMM_WIDE_MIN_K") ? atoi(getenv("POSE_GEMM_WIDE_MIN_K")) : 256;
+    if (off || N % 256 || K < min_k) return false;
 
     static const bool heavy_narrow = getenv("POSE_GEMM_HEAVY_BN128") != nullptr;      // A/B switch for measurements
     const bool heavy = ep.act == 3 || ep.act >= 5 || ep.preact != nullptr;
