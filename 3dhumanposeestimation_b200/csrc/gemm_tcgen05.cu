@@ -1203,11 +1203,14 @@ static int dispatch_bn(const CUtensorMap &ma, const void *W, int ldw, int M, int
                        const ConvGeom &cg, int m_tiles, cudaStream_t s) {
     CUtensorMap mw;
     int bn = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
-    if (MODE == 0 && BKC == 64 && wide_tile_fwd_ok(ep, N, K, m_tiles)) bn = 256;
+    // 128 x 256 tiles: the plain GEMM, and the implicit-GEMM convolutions with long contractions (the 512-channel dilated
+    // 3x3 layers: K = 4608) -- POSE_CONV_NO_BN256 switches the latter off (A/B measurements)
+    static const bool conv_wide_off = getenv("POSE_CONV_NO_BN256") != nullptr;
+    if ((MODE == 0 || (MODE == 1 && !conv_wide_off && K >= 1024)) && BKC == 64 && wide_tile_fwd_ok(ep, N, K, m_tiles)) bn = 256;
     const bool pair = MODE == 0 && bn == 256 && pair_ok(ep, M, N, K, 1);
     int e = make_map_2d(&mw, W, N, K, ldw, pair ? bn / 2 : bn, BKC);        // a CTA of a pair loads half of the B tile
     if (e) return e;
-    if constexpr (MODE == 0 && BKC == 64) {
+    if constexpr ((MODE == 0 || MODE == 1) && BKC == 64) {
         if (bn == 256) return launch_gemm<256, 3, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s, 1, pair);
     }
     if (bn == 32) return launch_gemm<32, 6, BKC, MODE>(ma, mw, M, N, K, ep, cg, m_tiles, s);
