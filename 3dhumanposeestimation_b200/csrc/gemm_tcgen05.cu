@@ -1431,6 +1431,12 @@ POSE_API int pose_conv2d_wgrad_bf16(const void *dY, const void *X, int Nimg, int
     if (e) return e;
     ConvGeom cg = {Ho, Wo, TH, TW, TN, Nimg, KW, KH * KW, stride, dil, pad, Cin / cw, tiles_w, tiles_h, cw};
     const int m_tiles = (M + BM - 1) / BM;
+    // 128 x 256 tiles (four 64-channel blocks per column tile) for the wide layers: as in pose_gemm_bf16_tr the caller
+    // sized the splits for 128-column tiles, so the factor doubles -- the 512-channel dilated 3x3 layers ran ONE wave of 144
+    // narrow tiles.  POSE_CONV_WGRAD_NO_BN256 switches it off (A/B measurements)
+    static const bool wide_off = getenv("POSE_CONV_WGRAD_NO_BN256") != nullptr;
+    if (!wide_off && cw == 64 && N % 256 == 0 && M >= 256 && K >= 8192 && (long)m_tiles * (N / 256) * 2 * k_splits >= kNumSMs / 2)
+        return launch_gemm<256, 3, 64, 2, 1, 1>(ma, mw, M, N, K, ep, cg, m_tiles, (cudaStream_t)stream, 2 * k_splits);
     return launch_gemm<128, 4, 64, 2, 1, 1>(ma, mw, M, N, K, ep, cg, m_tiles, (cudaStream_t)stream, k_splits);
 }
 
