@@ -1185,7 +1185,11 @@ static bool wide_tile_ok(const Epilogue &ep, int N, int K, int m_tiles, int k_sp
 // per epilogue warp lose to the 128-column tile there (measured: 37.0 vs 34.4 us at K = 768 with a residual)
 static bool wide_tile_fwd_ok(const Epilogue &ep, int N, int K, int m_tiles) {
     const bool tma_heavy = (ep.act == 3 || ep.act >= 5 || ep.preact != nullptr) && ep.out_bf16 && !ep.accumulate && ep.vec;
-    if (!tma_heavy && (ep.act != 0 || ep.residual != nullptr) && K < 1024) return false;
+    // (round 1 kept activation / residual epilogues on 128-column tiles below K = 1024; re-measured at the end of round 2
+    // with the TMA-store epilogues: CNN eval forward at B = 512 22.24 -> 21.35 ms with the wide tile from K = 256, ViT step
+    // 23.41 -> 23.32 ms.  POSE_GEMM_WIDE_ACT_MIN_K overrides, A/B)
+    static const int act_min_k = getenv("POSE_GEMM_WIDE_ACT_MIN_K") ? atoi(getenv("POSE_GEMM_WIDE_ACT_MIN_K")) : 256;
+    if (!tma_heavy && (ep.act != 0 || ep.residual != nullptr) && K < act_min_k) return false;
     return wide_tile_ok(ep, N, K, m_tiles, 1);
 }
 
